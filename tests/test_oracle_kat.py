@@ -1,0 +1,174 @@
+"""Pins the CPU oracle to the only numbers the reference itself printed,
+plus self-consistency checks (finite differences, identities, Philox known-answer vectors)."""
+import math
+
+import numpy as np
+import torch
+
+from oracle import dgp_oracle as O
+
+
+def _kat1_model(S=10):
+    # Notebooks_dgp/nb_DGP_regression.ipynb cell 10 / cells 14-18
+    np.random.seed(0)
+    X = np.random.uniform(0, 1, 50)[:, None]
+    Z = np.random.uniform(0, 1, 25)[:, None]
+    Y = (X >= 0.5).astype(np.float64) + 1e-2 * np.random.randn(50, 1)
+    kernels = [(np.array([1.0]), 1.0)] * 3
+    model = O.make_dgp(X, Y, Z, kernels, [1, 1], lik_var=1.0, num_samples=S)
+    return model, torch.as_tensor(X), torch.as_tensor(Y)
+
+
+def _zs(model, N, S, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(S, N, l.D_out, dtype=torch.float64, generator=g) for l in model.layers]
+
+
+def test_kat1_elbo_at_prior():
+    model, X, Y = _kat1_model()
+    for seed in (0, 1, 2):
+        val = float(O.elbo(model, X, Y, _zs(model, 50, 10, seed)))
+        assert abs(val - (-85.98812279560475)) <= 1e-10 * 85.98812279560475, val
+
+
+def test_kat1b_after_qsqrt_scaling():
+    model, X, Y = _kat1_model()
+    for l in model.layers[:-1]:  # models/dgp.py:268-269
+        l.q_sqrt = l.q_sqrt * 1e-3
+    val = float(O.elbo(model, X, Y, _zs(model, 50, 10, 3)))
+    expected = -85.98812279559426 - 2 * 0.5 * (25 * 1e-6 - 25 + 25 * math.log(1e6))
+    assert abs(val - expected) <= 1e-10 * abs(expected), (val, expected)
+    assert abs(expected - (-406.37591174470)) < 1e-8
+
+
+def test_kat2_bo_constraint_model():
+    # nb_dgp_BO cells 30/61: N = M = 5, Z = X, standardised targets (sum Y^2 = N), after q_sqrt *= 1e-3
+    rng = np.random.default_rng(5)
+    X = rng.uniform(0, 1, (5, 1))
+    Y = rng.standard_normal((5, 1))
+    Y = (Y - Y.mean()) / Y.std()
+    kernels = [(np.array([1.0]), 1.0)] * 3
+    model = O.make_dgp(X, Y, X.copy(), kernels, [1, 1], lik_var=1.0, num_samples=10)
+    for l in model.layers[:-1]:
+        l.q_sqrt = l.q_sqrt * 1e-3
+    val = float(O.elbo(model, torch.as_tensor(X), torch.as_tensor(Y), _zs(model, 5, 10, 0)))
+    assert abs(val - (-73.6722504558447)) <= 1e-9 * 73.67, val
+
+
+def test_kat3_number_parameters():
+    model, _, _ = _kat1_model()
+    assert O.number_parameters(model) == 2032
+
+
+def test_prior_identities():
+    model, X, Y = _kat1_model()
+    for l in model.layers:
+        assert abs(float(O.layer_KL(l))) < 1e-8
+    m, v = O.conditional_ND(model.layers[-1], torch.rand(7, 1, dtype=torch.float64))
+    assert torch.allclose(v, torch.ones_like(v), atol=1e-9)
+    assert torch.allclose(m, torch.zeros_like(m), atol=1e-12)
+
+
+def test_white_nonwhite_equivalence():
+    prob = O.synthetic_problem(3, [3], 12, 20)
+    lay = prob["layers"][0]
+    nw = O.make_layer(lay["Z"], lay["lengthscales"], 1.0, 3, "identity", q_mu=lay["q_mu"], q_sqrt=lay["q_sqrt"])
+    _, Lu = O.kuu_chol(nw)
+    w = O.make_layer(lay["Z"], lay["lengthscales"], 1.0, 3, "identity", white=True, q_mu=lay["q_mu"], q_sqrt=lay["q_sqrt"])
+    nw2 = O.make_layer(lay["Z"], lay["lengthscales"], 1.0, 3, "identity", q_mu=Lu @ w.q_mu, q_sqrt=Lu[None] @ w.q_sqrt)
+    X = torch.as_tensor(prob["X"])
+    m1, v1 = O.conditional_ND(w, X)
+    m2, v2 = O.conditional_ND(nw2, X)
+    assert torch.allclose(m1, m2, rtol=1e-9, atol=1e-11)
+    assert torch.allclose(v1, v2, rtol=1e-9, atol=1e-11)
+    assert abs(float(O.layer_KL(w) - O.layer_KL(nw2))) < 1e-8
+
+
+def test_autograd_vs_finite_differences():
+    prob = O.synthetic_problem(3, [3], 10, 16)
+    model = O.model_from_problem(prob, num_samples=4)
+    X, Y = torch.as_tensor(prob["X"]), torch.as_tensor(prob["Y"])
+    zs = _zs(model, 16, 4, 7)
+    val, grads = O.elbo_and_grads(model, X, Y, zs)
+    h = 1e-6
+    rng = np.random.default_rng(0)
+    for name in ["layers.0.Z", "layers.0.lengthscales", "layers.0.variance", "layers.0.q_mu", "layers.1.q_sqrt",
+                 "layers.1.Z", "lik_var"]:
+        p = model.named_params()[name]
+        flat = p.view(-1)
+        idxs = rng.choice(flat.numel(), size=min(3, flat.numel()), replace=False)
+        if name.endswith("q_sqrt"):
+            idxs = [0, 10 + 1, 2 * 10 + 1]  # lower-triangular entries
+        for i in idxs:
+            old = float(flat[i])
+            flat[i] = old + h
+            fp = float(O.elbo(model, X, Y, zs))
+            flat[i] = old - h
+            fm = float(O.elbo(model, X, Y, zs))
+            flat[i] = old
+            fd = (fp - fm) / (2 * h)
+            g = float(grads[name].view(-1)[i])
+            assert abs(fd - g) <= 2e-5 * max(1.0, abs(g)), (name, i, fd, g)
+
+
+def test_fill_triangular_matches_tfp_doc_example():
+    # tfp FillTriangular docstring: [1..6] -> [[4,0,0],[6,5,0],[3,2,1]]
+    out = O.fill_triangular(np.arange(1.0, 7.0))
+    assert (out == np.array([[4, 0, 0], [6, 5, 0], [3, 2, 1]])).all()
+    x = np.random.default_rng(0).standard_normal((2, 10))
+    assert np.allclose(O.fill_triangular_inverse(O.fill_triangular(x)), x)
+
+
+def test_softplus_roundtrip():
+    th = np.array([1e-3, 0.1, 1.0, 30.0])
+    assert np.allclose(O.softplus(O.softplus_inv(th)), th, rtol=1e-12)
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors: philox4x32 10 rounds
+    r = O.philox4x32_10(0, 0, 0, 0, 0, 0)
+    assert [int(x) for x in r] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = 0xFFFFFFFF
+    r = O.philox4x32_10(f, f, f, f, f, f)
+    assert [int(x) for x in r] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    r = O.philox4x32_10(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0)
+    assert [int(x) for x in r] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_philox_normal_moments_and_shard_invariance():
+    z = O.philox_normal(1234, 1, 8, 4096, 4)
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01
+    z2 = O.philox_normal(1234, 1, 8, 2048, 4, n_offset=2048)
+    assert np.array_equal(z[:, 2048:], z2)
+
+
+def test_ei_and_ehvi_basic():
+    g = torch.Generator().manual_seed(0)
+    Fm = torch.randn(16, 5, 1, dtype=torch.float64, generator=g)
+    Fv = torch.rand(16, 5, 1, dtype=torch.float64, generator=g) + 0.1
+    nei = O.ei_analytic(Fm, Fv, 0.3)
+    assert (nei <= 0).all()
+    # EHVI vs Monte-Carlo hypervolume improvement on one candidate
+    y0 = np.array([0.8, 0.5, 0.2])  # descending objective 0
+    y1 = np.array([0.2, 0.5, 0.8])
+    a, b = O.Y_ND(y0, y1, nadir=(1.1, 1.1), ideal=(-10.0, -10.0))
+    m0, v0, m1, v1 = [torch.tensor([x], dtype=torch.float64) for x in (0.4, 0.04, 0.3, 0.09)]
+    val = float(O.ehvi_exact(m0, v0, m1, v1, a, b))
+    rng = np.random.default_rng(0)
+    f0 = 0.4 + 0.2 * rng.standard_normal(200000)
+    f1 = 0.3 + 0.3 * rng.standard_normal(200000)
+
+    def hv(front):
+        front = sorted(front)
+        tot, prev1 = 0.0, 1.1
+        for p0, p1 in front:
+            if p1 < prev1 and p0 < 1.1:
+                tot += (1.1 - p0) * (prev1 - p1)
+                prev1 = p1
+        return tot
+    base = hv(list(zip(y0, y1)))
+    # improvement computed on a subsample (python loop)
+    n = 4000
+    imp = np.mean([max(hv(list(zip(y0, y1)) + [(f0[i], f1[i])]) - base, 0.0)
+                   for i in range(n)])
+    assert abs(val - imp) < 0.02, (val, imp)
