@@ -1,0 +1,55 @@
+"""2-objective expected hypervolume improvement with the reference's interface (dgp_dace/EHVI.py:90-157, exact
+uncorrelated branch for a list of two DGPs). The moment matching and the strip sum run in libdgp_b200."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def Y_ND(Y, ND, nadir, ideal=[0, 0]):
+    """EHVI.py:90-100: the non-dominated front padded with nadir/ideal (host numpy, tens of points)."""
+    Y0 = np.asarray(Y[0])[ND]
+    Y1 = np.asarray(Y[1])[ND]
+    Y_ = [np.zeros((len(ND) + 2, 1)), np.zeros((len(ND) + 2, 1))]
+    Y_[0][1:-1] = Y0.reshape(-1, 1)
+    Y_[1][1:-1] = Y1.reshape(-1, 1)
+    Y_[0][0] = nadir[0]
+    Y_[0][-1] = ideal[0]
+    Y_[1][0] = ideal[1]
+    Y_[1][-1] = nadir[1]
+    return Y_
+
+
+def psi(a, b, mu, sigma):
+    """EHVI.py:102-104 on tensors (helper for callers; the EHVI kernel evaluates it in-kernel)."""
+    u = (b - mu) / sigma
+    pdf = torch.exp(-0.5 * u * u) / np.sqrt(2 * np.pi)
+    cdf = 0.5 * torch.erfc(-u / np.sqrt(2.0))
+    return sigma * pdf + (a - mu) * cdf
+
+
+def EHVI(model_Y, Xcand, YND, corr=False, approximation='None', S=1000, zs=None, seed=None):
+    """EHVI.py:107-157 for `model_Y` = [dgp0, dgp1], approximation='None', corr=False -> [N, 1]."""
+    if not isinstance(model_Y, list) or len(model_Y) != 2 or any(getattr(m, "name", None) != 'dgp' for m in model_Y):
+        raise NotImplementedError("only a list of two DGP models is on the accelerated path (SURVEY §8 a12)")
+    if approximation != 'None' or corr:
+        raise NotImplementedError("only the exact uncorrelated EHVI is on the accelerated path")
+    zs = zs or [None, None]
+    seeds = seed if isinstance(seed, (list, tuple)) else [seed, seed]
+    # moment matching over the S propagated samples (EHVI.py:112-119), predict_f moments (no likelihood variance)
+    m0, v0 = model_Y[0].predict_moments(Xcand, S, add_lik_var=False, zs=zs[0], seed=seeds[0])
+    m1, v1 = model_Y[1].predict_moments(Xcand, S, add_lik_var=False, zs=zs[1], seed=seeds[1])
+    if m0.shape[1] != 1 or m1.shape[1] != 1:
+        raise ValueError("each objective model must have one output")
+    N = m0.shape[0]
+    dev = m0.device
+    y0 = _lib.as_device(np.asarray(YND[0], dtype=np.float64).reshape(-1), dev)
+    y1 = _lib.as_device(np.asarray(YND[1], dtype=np.float64).reshape(-1), dev)
+    out = torch.empty((N, 1), dtype=torch.float64, device=dev)
+    if N == 0:
+        return out
+    _lib.get_context(dev).call("dgp_ehvi2d", _lib.ptr(m0), _lib.ptr(v0), _lib.ptr(m1), _lib.ptr(v1), N, _lib.ptr(y0),
+                               _lib.ptr(y1), int(y0.numel()), _lib.ptr(out))
+    return out

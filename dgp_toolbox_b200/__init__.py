@@ -1,0 +1,13 @@
+"""dgp_toolbox_b200 — B200-native doubly-stochastic DGP hot path behind the dgp-toolbox class API.
+
+Importing the package loads libdgp_b200.so (hand-written sm_100a CUDA behind a C ABI); it raises if the library has
+not been built. There is no CPU fallback.
+"""
+from . import _lib  # noqa: F401  (fails loudly when the CUDA library is missing)
+from . import gpflow_shim as gpflow  # noqa: F401
+from .gpflow_shim import RBF, Gaussian, Identity, Linear, Parameter, SquaredExponential, Zero  # noqa: F401
+from .models.dgp import DGP, DGP_Base  # noqa: F401
+from .utils.layers import Layer, SVGP_Layer  # noqa: F401
+from .utils.layer_initializations import init_layers_linear  # noqa: F401
+from .Infill_criteria import EI  # noqa: F401
+from .EHVI import EHVI, Y_ND, psi  # noqa: F401

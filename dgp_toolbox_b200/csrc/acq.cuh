@@ -1,0 +1,80 @@
+// Acquisition epilogues: mixture moments over the S samples, EI (analytic + MC), exact 2-D EHVI.
+// Reference: dgp_dace/models/dgp.py:362-366, dgp_dace/Infill_criteria.py:36-52, dgp_dace/EHVI.py:102-104,154-157.
+#pragma once
+#include "common.cuh"
+
+namespace dgp {
+
+__device__ __forceinline__ double norm_cdf(double x) { return 0.5 * erfc(-x * 0.70710678118654752440); }
+__device__ __forceinline__ double norm_pdf(double x) { return 0.39894228040143267794 * exp(-0.5 * x * x); }
+
+// mean[n,d] = mean_s mu ; var[n,d] = mean_s (v + add + mu^2) - mean^2     (inputs [S,N,D])
+__global__ void mixture_moments_kernel(const double* __restrict__ Fmean, const double* __restrict__ Fvar, long S, long ND,
+                                       const double* __restrict__ likvar, int add_lik, double* __restrict__ mean,
+                                       double* __restrict__ var) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ND) return;
+  const double add = add_lik ? likvar[0] : 0.0;
+  double sm = 0.0, sq = 0.0;
+  for (long s = 0; s < S; ++s) {
+    double m = Fmean[s * ND + i], v = Fvar[s * ND + i] + add;
+    sm += m;
+    sq += v + m * m;
+  }
+  double mu = sm / (double)S;
+  mean[i] = mu;
+  var[i] = sq / (double)S - mu * mu;
+}
+
+// -EI from moments: Normal(mean, sqrt(var)); t1 = (y_min - mean) cdf(y_min); t2 = var * pdf(y_min)
+__global__ void ei_analytic_kernel(const double* __restrict__ mean, const double* __restrict__ var, long n, double y_min,
+                                   double* __restrict__ out) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double m = mean[i], v = var[i], s = sqrt(v);
+  double u = (y_min - m) / s;
+  double t1 = (y_min - m) * norm_cdf(u);
+  double t2 = v * (norm_pdf(u) / s);
+  out[i] = -(t1 + t2);
+}
+
+// -EI by Monte-Carlo: mean_s where(F - y_min < 0, y_min - F, 0)     (F [S,N,D])
+__global__ void ei_mc_kernel(const double* __restrict__ F, long S, long ND, double y_min, double* __restrict__ out) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ND) return;
+  double acc = 0.0;
+  for (long s = 0; s < S; ++s) {
+    double f = F[s * ND + i];
+    acc += (f - y_min) < 0.0 ? (y_min - f) : 0.0;
+  }
+  out[i] = -(acc / (double)S);
+}
+
+__device__ __forceinline__ double psi_fn(double a, double b, double mu, double sigma) {
+  double u = (b - mu) / sigma;
+  return sigma * norm_pdf(u) + (a - mu) * norm_cdf(u);
+}
+
+// Exact uncorrelated 2-objective EHVI strip sum over the padded front (n entries, staged in shared memory).
+__global__ void ehvi2d_kernel(const double* __restrict__ m0, const double* __restrict__ v0, const double* __restrict__ m1,
+                              const double* __restrict__ v1, long N, const double* __restrict__ ynd0,
+                              const double* __restrict__ ynd1, int n, double* __restrict__ out) {
+  extern __shared__ double sh[];
+  double* y0 = sh;
+  double* y1 = sh + n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { y0[i] = ynd0[i]; y1[i] = ynd1[i]; }
+  __syncthreads();
+  long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  const double mu0 = m0[c], s0 = sqrt(v0[c]), mu1 = m1[c], s1 = sqrt(v1[c]);
+  const double cdf_last = norm_cdf((y0[n - 1] - mu0) / s0);
+  double t1 = 0.0, t2 = 0.0;
+  for (int i = 1; i < n; ++i) {
+    const double d1 = psi_fn(y1[i], y1[i], mu1, s1) - psi_fn(y1[i], y1[0], mu1, s1);
+    if (i < n - 1) t1 += (y0[i - 1] - y0[i]) * (norm_cdf((y0[i] - mu0) / s0) - cdf_last) * d1;
+    t2 += (psi_fn(y0[i - 1], y0[i - 1], mu0, s0) - psi_fn(y0[i - 1], y0[i], mu0, s0)) * d1;
+  }
+  out[c] = t1 + t2;
+}
+
+}  // namespace dgp

@@ -1,0 +1,824 @@
+// C ABI of the B200-native doubly-stochastic DGP hot path (see include/dgp_b200.h for the contract and the
+// reference methods each entry point replaces). Host orchestration only: every flop runs in the kernels of
+// gemm.cuh (FP64 DMMA contractions), layer.cuh (streaming stages), prep.cuh / small.cuh (replicated M^2 / M^3 work)
+// and acq.cuh (acquisition epilogues). There is no CPU fallback: without a CUDA device every call fails.
+#include "../../include/dgp_b200.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "acq.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "layer.cuh"
+#include "philox.cuh"
+#include "prep.cuh"
+#include "small.cuh"
+
+using namespace dgp;
+
+struct dgp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // bump arena for per-call device scratch; grown (never shrunk) between calls
+  char* ws = nullptr;
+  size_t cap = 0, used = 0;
+  bool dry = false;
+  size_t ws_limit = (size_t)24 << 30;   // chunks of the minibatch are sized to stay under this
+  int* d_info = nullptr;                // Cholesky failure flag
+  double* h_pinned = nullptr;           // staging for the *_host entry points
+  size_t h_pinned_bytes = 0;
+  double* d_stage = nullptr;            // device side of that staging (outside the arena, which may be re-grown)
+  size_t d_stage_bytes = 0;
+  long launches = 0;                    // kernels launched since the last dgp_reset_launch_count
+};
+
+namespace {
+
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      c->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                                \
+      return DGP_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+#define RC(expr)                 \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != DGP_OK) return rc__; \
+  } while (0)
+// kernel launch, skipped while planning the workspace
+#define LAUNCH(kern, grid, block, smem, ...)                          \
+  do {                                                                \
+    if (!c->dry) {                                                    \
+      kern<<<grid, block, smem, c->stream>>>(__VA_ARGS__);            \
+      ++c->launches;                                                  \
+      CK(cudaGetLastError());                                         \
+    }                                                                 \
+  } while (0)
+
+double* walloc(dgp_ctx* c, size_t n_doubles) {
+  size_t bytes = (n_doubles * sizeof(double) + 255) & ~(size_t)255;
+  size_t off = c->used;
+  c->used += bytes;
+  if (c->dry) return nullptr;
+  return reinterpret_cast<double*>(c->ws + off);
+}
+
+int ensure_ws(dgp_ctx* c, size_t need) {
+  if (need <= c->cap) return DGP_OK;
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->ws) CK(cudaFree(c->ws));
+  c->ws = nullptr;
+  c->cap = 0;
+  size_t want = need + (need >> 3);
+  cudaError_t e = cudaMalloc(&c->ws, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = need;
+    CK(cudaMalloc(&c->ws, want));
+  }
+  c->cap = want;
+  return DGP_OK;
+}
+
+int gemm(dgp_ctx* c, GemmArgs g, bool nt) {
+  if (c->dry) return DGP_OK;
+  cudaError_t e = gemm_launch(g, nt, c->stream);
+  c->launches += g.splitk > 1 ? 2 : 1;
+  if (e != cudaSuccess) {
+    c->err = std::string("gemm_launch: ") + cudaGetErrorString(e);
+    return DGP_ERR_CUDA;
+  }
+  return DGP_OK;
+}
+
+GemmArgs gargs(const double* A, long lda, const double* B, long ldb, double* C, long ldc, int M, int N, int K) {
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K;
+  g.alpha = 1.0; g.beta = 0.0; g.batch = 1; g.splitk = 1; g.kblocks = 1; g.kblk = K; g.bscale_mul = 1.0;
+  return g;
+}
+
+// largest split count <= target that keeps K / splitk a multiple of 16
+constexpr size_t kSplitkPartDoubles = (size_t)96 << 20;   // 768 MB of split-K partial tiles at most
+int pick_splitk(long K, long tiles, size_t out_doubles, int target_blocks = 148 * 4) {
+  long units = K / 16;
+  long want = (target_blocks + tiles - 1) / tiles;
+  if (want < 1) want = 1;
+  if (want > 64) want = 64;
+  if ((size_t)want * out_doubles > kSplitkPartDoubles) want = (long)(kSplitkPartDoubles / out_doubles);
+  if (want < 1) want = 1;
+  if (want > units) want = units;
+  for (long s = want; s >= 1; --s)
+    if (units % s == 0) return (int)s;
+  return 1;
+}
+
+template <typename F>
+int dispatch_dmax(int D, F&& f) {
+  if (D <= 1) return f(std::integral_constant<int, 1>());
+  if (D <= 2) return f(std::integral_constant<int, 2>());
+  if (D <= 4) return f(std::integral_constant<int, 4>());
+  if (D <= 8) return f(std::integral_constant<int, 8>());
+  if (D <= 16) return f(std::integral_constant<int, 16>());
+  return f(std::integral_constant<int, 32>());
+}
+
+int check_layer(dgp_ctx* c, const dgp_layer_desc& L) {
+  if (L.D_in < 1 || L.D_in > kMaxD - 1 || L.D_out < 1 || L.D_out > kMaxD || L.M < 1) {
+    c->err = "layer widths must satisfy 1 <= D_in <= 31, 1 <= D_out <= 32, M >= 1";
+    return DGP_ERR_ARG;
+  }
+  if (round_up(L.M, kTileM) > 768) { c->err = "M > 768 is not supported by the single-CTA Cholesky"; return DGP_ERR_UNSUPPORTED; }
+  if (L.white) { c->err = "white=True layers are not implemented (reference default is white=False, dgp.py:248)"; return DGP_ERR_UNSUPPORTED; }
+  if (L.kernel_kind != 0) { c->err = "only the SquaredExponential/RBF kernel is implemented"; return DGP_ERR_UNSUPPORTED; }
+  if (L.mean_kind < 0 || L.mean_kind > 2) { c->err = "mean_kind must be 0 (Zero), 1 (Identity) or 2 (Linear)"; return DGP_ERR_ARG; }
+  if (L.mean_kind == 1 && L.D_in != L.D_out) { c->err = "Identity mean function needs D_in == D_out"; return DGP_ERR_ARG; }
+  if (L.mean_kind == 2 && !L.mf_W) { c->err = "Linear mean function needs mf_W"; return DGP_ERR_ARG; }
+  if (!L.Z || !L.lengthscales || !L.variance || !L.q_mu || !L.q_sqrt) { c->err = "null parameter pointer in layer descriptor"; return DGP_ERR_ARG; }
+  return DGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-step replicated state of one layer (a1): everything derived from (Z, l, s2, q_mu, q_sqrt)
+// ---------------------------------------------------------------------------------------------------------
+struct LayerWs {
+  int M = 0, Mp = 0, D_in = 0, D_out = 0;
+  double *Ku = nullptr, *Knj = nullptr, *L = nullptr, *Linv = nullptr, *LinvT = nullptr;
+  double *RpT = nullptr, *Rcat = nullptr, *qmuP = nullptr;
+  // gradient / KL only
+  double *Kinv = nullptr, *alpha = nullptr, *KRcat = nullptr, *LRcat = nullptr, *KSK = nullptr;
+  // gradient accumulators over the chunks of the minibatch
+  double *dKu = nullptr, *dR = nullptr, *dqmu = nullptr, *H = nullptr, *rbf_red = nullptr, *sgv = nullptr;
+  double *dZk = nullptr, *kuu_part = nullptr, *kuu_red = nullptr, *kl = nullptr;
+};
+
+enum PrepLevel { PREP_FWD = 0, PREP_KL = 1, PREP_GRAD = 2 };
+
+int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& lw, PrepLevel level) {
+  const int nl = model->num_layers;
+  lw.assign(nl, LayerWs());
+  std::vector<CholArgs> hargs(nl);
+  int maxMp = 0;
+  for (int l = 0; l < nl; ++l) {
+    const dgp_layer_desc& d = model->layers[l];
+    RC(check_layer(c, d));
+    LayerWs& w = lw[l];
+    w.M = d.M; w.Mp = (int)round_up(d.M, kTileM); w.D_in = d.D_in; w.D_out = d.D_out;
+    const size_t mm = (size_t)w.Mp * w.Mp;
+    w.Ku = walloc(c, mm); w.Knj = walloc(c, mm); w.L = walloc(c, mm); w.Linv = walloc(c, mm); w.LinvT = walloc(c, mm);
+    w.RpT = walloc(c, mm * w.D_out); w.Rcat = walloc(c, mm * w.D_out); w.qmuP = walloc(c, (size_t)w.Mp * 32);
+    if (level >= PREP_KL) {
+      w.Kinv = walloc(c, mm); w.alpha = walloc(c, (size_t)w.Mp * 32);
+      w.LRcat = walloc(c, mm * w.D_out); w.kl = walloc(c, 1);
+    }
+    if (level >= PREP_GRAD) {
+      w.KRcat = walloc(c, mm * w.D_out); w.KSK = walloc(c, mm);
+      w.dKu = walloc(c, mm); w.dR = walloc(c, mm * w.D_out); w.dqmu = walloc(c, (size_t)w.Mp * 32);
+      w.H = walloc(c, (size_t)w.Mp * 32); w.rbf_red = walloc(c, 32); w.sgv = walloc(c, 4);
+      w.dZk = walloc(c, (size_t)w.M * w.D_in); w.kuu_part = walloc(c, (size_t)w.M * (w.D_in + 1)); w.kuu_red = walloc(c, 32);
+    }
+    if (w.Mp > maxMp) maxMp = w.Mp;
+    hargs[l] = CholArgs{w.Ku, w.L, w.Linv, w.LinvT, w.Mp, c->d_info};
+  }
+  CholArgs* dargs = reinterpret_cast<CholArgs*>(walloc(c, (sizeof(CholArgs) * nl + 7) / 8));
+  if (c->dry) return DGP_OK;
+
+  CK(cudaMemsetAsync(c->d_info, 0, sizeof(int), c->stream));
+  CK(cudaMemcpyAsync(dargs, hargs.data(), sizeof(CholArgs) * nl, cudaMemcpyHostToDevice, c->stream));
+  for (int l = 0; l < nl; ++l) {
+    const dgp_layer_desc& d = model->layers[l];
+    LayerWs& w = lw[l];
+    const long mm = (long)w.Mp * w.Mp;
+    LAUNCH(kuu_build_kernel, (unsigned)((mm + 255) / 256), 256, 0, d.Z, d.lengthscales, d.variance, w.M, w.Mp, w.D_in, d.jitter, w.Ku, w.Knj);
+    const long np = mm * w.D_out > (long)w.Mp * 32 ? mm * w.D_out : (long)w.Mp * 32;
+    LAUNCH(pad_params_kernel, (unsigned)((np + 255) / 256), 256, 0, d.q_sqrt, d.q_mu, w.M, w.Mp, w.D_out, w.RpT, w.Rcat, w.qmuP);
+  }
+  {
+    static bool configured = false;
+    const size_t smem = chol_smem_bytes(768);
+    if (!configured) {
+      CK(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    LAUNCH(chol_inv_kernel, nl, kCholThreads, chol_smem_bytes(maxMp), dargs);
+  }
+  if (level >= PREP_KL) {
+    for (int l = 0; l < nl; ++l) {
+      LayerWs& w = lw[l];
+      const int Mp = w.Mp, D = w.D_out;
+      GemmArgs g = gargs(w.LinvT, Mp, w.Linv, Mp, w.Kinv, Mp, Mp, Mp, Mp);   // Kinv = Linv^T Linv
+      g.a_tri = 2;
+      RC(gemm(c, g, false));
+      g = gargs(w.Kinv, Mp, w.qmuP, 32, w.alpha, 32, Mp, 32, Mp);            // alpha = Kinv q_mu
+      RC(gemm(c, g, false));
+      g = gargs(w.Linv, Mp, w.Rcat, (long)D * Mp, w.LRcat, (long)D * Mp, Mp, D * Mp, Mp);   // Linv [R_1 .. R_D]
+      g.a_tri = 1;
+      RC(gemm(c, g, false));
+      LAUNCH(kl_kernel, 1, 1024, 0, w.L, w.Rcat, w.LRcat, w.qmuP, w.alpha, w.M, Mp, D, w.kl);
+      if (level >= PREP_GRAD) {
+        g = gargs(w.Kinv, Mp, w.Rcat, (long)D * Mp, w.KRcat, (long)D * Mp, Mp, D * Mp, Mp);  // Kinv [R_1 .. R_D]
+        RC(gemm(c, g, false));
+        g = gargs(w.KRcat, (long)D * Mp, w.KRcat, (long)D * Mp, w.KSK, Mp, Mp, Mp, D * Mp);   // sum_d (Kinv R_d)(Kinv R_d)^T
+        RC(gemm(c, g, true));
+      }
+    }
+  }
+  return DGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// one chunk of the minibatch: Nc points x S samples, chained through the layers
+// ---------------------------------------------------------------------------------------------------------
+struct ChunkLayer {
+  const double* Xin = nullptr; long xmod = 0;     // layer input [P][D_in] (layer 0: X rows, shared over S)
+  double *F = nullptr, *Fmean = nullptr, *Fvar = nullptr, *z = nullptr;   // [P][D_out]
+  double *A = nullptr, *T = nullptr;              // [Mp][Pp], [D_out][Mp][Pp]  (stash for the adjoint)
+};
+
+struct ChunkIO {   // caller-visible arrays [S][N][D_l], any may be null
+  const double* const* zs = nullptr;
+  double* const* Fs = nullptr;
+  double* const* Fmeans = nullptr;
+  double* const* Fvars = nullptr;
+};
+
+struct Temps { double *t0 = nullptr, *t1 = nullptr, *t2 = nullptr; };   // three [maxMp][Pp] planes
+
+int forward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, ChunkLayer& cl, const Temps& tmp, bool stash,
+                  double* Tshared, int layer, long Nc, long S, long N_total, long n0, unsigned long long seed, long n_offset,
+                  const ChunkIO& io, bool need_sample) {
+  const long P = Nc * S, Pp = round_up(P, kTileP);
+  const int Mp = w.Mp, D = w.D_out;
+  double* K = tmp.t0;
+  double* V = tmp.t1;
+  double* A = stash ? cl.A : tmp.t2;
+  double* T = stash ? cl.T : Tshared;
+  LAUNCH(kuf_kernel, dim3((unsigned)(Pp / kKufCols), (unsigned)(Mp / kKufRows)), 256, 0, cl.Xin, cl.xmod, d.Z, d.lengthscales,
+         d.variance, w.M, Mp, w.D_in, P, Pp, K);
+  GemmArgs g = gargs(w.Linv, Mp, K, Pp, V, Pp, Mp, (int)Pp, Mp);    // V = Lu^-1 Kuf            (layers.py:245)
+  g.a_tri = 1;
+  RC(gemm(c, g, false));
+  g = gargs(w.LinvT, Mp, V, Pp, A, Pp, Mp, (int)Pp, Mp);            // A = Lu^-T V              (layers.py:247)
+  g.a_tri = 2;
+  RC(gemm(c, g, false));
+  g = gargs(w.RpT, Mp, A, Pp, T, Pp, Mp, (int)Pp, Mp);              // T_d = q_sqrt_d^T A       (layers.py:257-271)
+  g.a_tri = 2; g.batch = D; g.sA = (long)Mp * Mp; g.sB = 0; g.sC = (long)Mp * Pp;
+  RC(gemm(c, g, false));
+
+  MomentsArgs a;
+  memset(&a, 0, sizeof(a));
+  a.V = V; a.A = A; a.T = T; a.qmu = d.q_mu; a.var = d.variance;
+  a.Xin = cl.Xin; a.xmod = cl.xmod; a.D_in = w.D_in;
+  a.mfW = d.mf_W; a.mfb = d.mf_b; a.mean_kind = d.mean_kind;
+  a.z_in = (io.zs && io.zs[layer]) ? io.zs[layer] : nullptr;
+  a.seed = seed; a.layer = layer; a.Nc = Nc; a.N_total = N_total; a.n0 = n0; a.n_offset = n_offset;
+  a.M = w.M; a.Mp = Mp; a.D_out = D; a.P = P; a.Pp = Pp; a.jitter = d.jitter;
+  a.Fmean = cl.Fmean; a.Fvar = cl.Fvar; a.F = need_sample ? cl.F : nullptr; a.z = need_sample ? cl.z : nullptr;
+  a.xFmean = (io.Fmeans && io.Fmeans[layer]) ? io.Fmeans[layer] : nullptr;
+  a.xFvar = (io.Fvars && io.Fvars[layer]) ? io.Fvars[layer] : nullptr;
+  a.xF = (io.Fs && io.Fs[layer]) ? io.Fs[layer] : nullptr;
+  const size_t smem = (size_t)w.M * D * sizeof(double);
+  return dispatch_dmax(D, [&](auto dm) -> int {
+    constexpr int DM = decltype(dm)::value;
+    if (!c->dry) {
+      CK(cudaFuncSetAttribute(moments_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    }
+    LAUNCH(moments_kernel<DM>, (unsigned)((P + 127) / 128), 128, smem, a);
+    return DGP_OK;
+  });
+}
+
+struct Upstream { double *Gm, *GvT, *GmPad, *gq, *part; long nblocks; };
+
+int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const ChunkLayer& cl, const Temps& tmp,
+                   const Upstream& up, double* dXin, double* XaugPad, double* rbf_part, double* splitk_part, long Nc, long S,
+                   bool first_chunk) {
+  const long P = Nc * S, Pp = round_up(P, kTileP);
+  const int Mp = w.Mp, D = w.D_out;
+  const double beta = first_chunk ? 0.0 : 1.0;
+  double* dA = tmp.t0;
+  double* W = tmp.t1;
+  double* Gbar = tmp.t2;
+  // dA' = q_mu Gm^T + sum_d R_d (2 Gv_d o T_d)                                       
+  GemmArgs g = gargs(w.qmuP, 32, up.GmPad, 32, dA, Pp, Mp, (int)Pp, 32);
+  RC(gemm(c, g, true));
+  g = gargs(w.Rcat, (long)D * Mp, cl.T, Pp, dA, Pp, Mp, (int)Pp, D * Mp);
+  g.a_tri = 1; g.kblocks = D; g.kblk = Mp; g.bscale = up.GvT; g.ld_bscale = Pp; g.bscale_mul = 2.0; g.beta = 1.0;
+  if (D == 1) { g.kblocks = 1; }
+  RC(gemm(c, g, false));
+  // W = Ku^-1 dA'
+  g = gargs(w.Kinv, Mp, dA, Pp, W, Pp, Mp, (int)Pp, Mp);
+  RC(gemm(c, g, false));
+  // RBF adjoint on the Kuf block: W -> Wg (in place), Gbar, dXin, [X,1], partial sums for dl / ds2
+  RbfBwdArgs r;
+  memset(&r, 0, sizeof(r));
+  r.W = W; r.A = cl.A; r.gq = up.gq; r.Gbar = Gbar; r.Xin = cl.Xin; r.xmod = cl.xmod; r.Z = d.Z; r.ls = d.lengthscales;
+  r.var = d.variance; r.M = w.M; r.Mp = Mp; r.D_in = w.D_in; r.P = P; r.Pp = Pp; r.Gm = up.Gm; r.D_out = D;
+  r.mean_kind = d.mean_kind; r.mfW = d.mf_W; r.dXin = dXin; r.XaugPad = XaugPad; r.part = rbf_part;
+  const long nb = Pp / 128;
+  const size_t smem = ((size_t)w.M * w.D_in + kMaxD + 32) * sizeof(double);
+  RC(dispatch_dmax(w.D_in, [&](auto dm) -> int {
+    constexpr int DM = decltype(dm)::value;
+    if (!c->dry) CK(cudaFuncSetAttribute(rbf_bwd_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LAUNCH(rbf_bwd_kernel<DM>, (unsigned)nb, 128, smem, r);
+    return DGP_OK;
+  }));
+  LAUNCH(reduce_partials_kernel, w.D_in + 1, 256, 0, rbf_part, nb, w.D_in + 1, w.rbf_red, first_chunk ? 0 : 1);
+  LAUNCH(reduce_partials_kernel, 3, 256, 0, up.part, up.nblocks, 3, w.sgv, first_chunk ? 0 : 1);
+  const long mt = Mp / 64;
+  // dKu (data part) = -Wg A^T
+  g = gargs(W, Pp, cl.A, Pp, w.dKu, Mp, Mp, Mp, (int)Pp);
+  g.alpha = -1.0; g.beta = beta; g.splitk = pick_splitk(Pp, mt * mt, (size_t)Mp * Mp); g.part = splitk_part;
+  RC(gemm(c, g, true));
+  // dq_sqrt_d (data part) = tril(A diag(2 Gv_d) T_d^T)
+  g = gargs(cl.A, Pp, cl.T, Pp, w.dR, Mp, Mp, Mp, (int)Pp);
+  g.alpha = 2.0; g.beta = beta; g.batch = D; g.sA = 0; g.sB = (long)Mp * Pp; g.sC = (long)Mp * Mp; g.c_lower = 1;
+  g.kscale = up.GvT; g.sScale = Pp; g.splitk = pick_splitk(Pp, mt * (mt + 1) / 2 * D, (size_t)D * Mp * Mp); g.part = splitk_part;
+  RC(gemm(c, g, true));
+  // dq_mu (data part) = A Gm ;  H = Gbar [X, 1]
+  g = gargs(cl.A, Pp, up.GmPad, 32, w.dqmu, 32, Mp, 32, (int)Pp);
+  g.beta = beta; g.splitk = pick_splitk(Pp, mt, (size_t)Mp * 32); g.part = splitk_part;
+  RC(gemm(c, g, false));
+  g = gargs(Gbar, Pp, XaugPad, 32, w.H, 32, Mp, 32, (int)Pp);
+  g.beta = beta; g.splitk = pick_splitk(Pp, mt, (size_t)Mp * 32); g.part = splitk_part;
+  RC(gemm(c, g, false));
+  return DGP_OK;
+}
+
+struct RunOpts {
+  bool want_grad = false, want_elbo = false;
+  const double* Y = nullptr; int Dy = 0;
+  double scale = 1.0, kl_weight = 1.0;
+  double* out_flat = nullptr;            // elbo / gradient buffer (device)
+  ChunkIO io;
+  // prediction outputs
+  double* pm = nullptr; double* pv = nullptr; int add_lik = 0;   // mixture moments [N][D_L]
+  double* ei = nullptr; double y_min = 0.0; int ei_analytic = 1; // -EI [N][D_L]
+  bool need_last_sample = false;
+};
+
+size_t max_splitk_part(const std::vector<LayerWs>& lw) {
+  size_t m = 0;
+  for (const LayerWs& w : lw) {
+    size_t v = (size_t)64 * w.D_out * w.Mp * w.Mp;
+    if (v > m) m = v;
+  }
+  return m < kSplitkPartDoubles ? m : kSplitkPartDoubles + ((size_t)32 * 1024 * 1024 / 8);
+}
+
+// Runs the chain over all chunks. Returns via opts outputs. `plan` semantics are handled by c->dry.
+int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, long S, unsigned long long seed, long n_offset,
+              RunOpts& o) {
+  const int nl = model->num_layers;
+  if (nl < 1 || N < 1 || S < 1) { c->err = "need num_layers >= 1, N >= 1, S >= 1"; return DGP_ERR_ARG; }
+  for (int l = 1; l < nl; ++l)
+    if (model->layers[l].D_in != model->layers[l - 1].D_out) { c->err = "layer widths do not chain"; return DGP_ERR_ARG; }
+  const bool grad = o.want_grad;
+  if ((grad || o.want_elbo) && model->layers[nl - 1].D_out != o.Dy) { c->err = "Y width must equal the last layer's D_out"; return DGP_ERR_ARG; }
+  if ((grad || o.want_elbo) && !model->lik_variance) { c->err = "lik_variance is null"; return DGP_ERR_ARG; }
+
+  std::vector<LayerWs> lw;
+  RC(prep_layers(c, model, lw, grad ? PREP_GRAD : (o.want_elbo ? PREP_KL : PREP_FWD)));
+  const size_t base_used = c->used;
+
+  int maxMp = 0, maxD = 1;
+  size_t pp_doubles = 0;   // workspace doubles per padded point-sample
+  for (int l = 0; l < nl; ++l) {
+    const LayerWs& w = lw[l];
+    if (w.Mp > maxMp) maxMp = w.Mp;
+    if (w.D_out > maxD) maxD = w.D_out;
+    pp_doubles += 4 * (size_t)w.D_out;                              // F, Fmean, Fvar, z
+    if (grad) pp_doubles += (size_t)(1 + w.D_out) * w.Mp;            // A, T stash
+  }
+  pp_doubles += 3 * (size_t)maxMp;                                   // temps
+  if (!grad) pp_doubles += (size_t)maxD * maxMp;                     // shared T
+  if (grad) pp_doubles += 2 * (size_t)maxD + 32 + 1 + 32 + 2 * 32;   // Gm, GvT, GmPad, gq, XaugPad, dX ping-pong
+  size_t fixed = base_used + (grad ? max_splitk_part(lw) * sizeof(double) : 0) + ((size_t)8 << 20);
+  long Nc_max;
+  {
+    size_t avail = c->ws_limit > fixed ? c->ws_limit - fixed : 0;
+    long pmax = (long)(avail / (pp_doubles * sizeof(double)));
+    pmax = pmax / kTileP * kTileP - kTileP;
+    Nc_max = pmax / S;
+    if (Nc_max < 1) Nc_max = 1;
+    if (Nc_max > N) Nc_max = N;
+    // equalise the chunks
+    long nchunks = (N + Nc_max - 1) / Nc_max;
+    Nc_max = (N + nchunks - 1) / nchunks;
+  }
+  const long Ppmax = round_up(Nc_max * S, kTileP);
+
+  // chunk-sized buffers (allocated once, reused by every chunk)
+  std::vector<ChunkLayer> cls(nl);
+  for (int l = 0; l < nl; ++l) {
+    const LayerWs& w = lw[l];
+    cls[l].F = walloc(c, (size_t)Ppmax * w.D_out);
+    cls[l].Fmean = walloc(c, (size_t)Ppmax * w.D_out);
+    cls[l].Fvar = walloc(c, (size_t)Ppmax * w.D_out);
+    cls[l].z = walloc(c, (size_t)Ppmax * w.D_out);
+    if (grad) {
+      cls[l].A = walloc(c, (size_t)w.Mp * Ppmax);
+      cls[l].T = walloc(c, (size_t)w.D_out * w.Mp * Ppmax);
+    }
+  }
+  Temps tmp;
+  tmp.t0 = walloc(c, (size_t)maxMp * Ppmax);
+  tmp.t1 = walloc(c, (size_t)maxMp * Ppmax);
+  tmp.t2 = walloc(c, (size_t)maxMp * Ppmax);
+  double* Tshared = grad ? nullptr : walloc(c, (size_t)maxD * maxMp * Ppmax);
+  Upstream up{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+  double *XaugPad = nullptr, *dXa = nullptr, *dXb = nullptr, *rbf_part = nullptr, *skpart = nullptr, *lik_part = nullptr;
+  double* acc = nullptr;   // [0] data term, [1] d/d lik variance (accumulated over chunks)
+  const long nbmax = Ppmax / 128;
+  if (grad || o.want_elbo) {
+    lik_part = walloc(c, (size_t)nbmax * 3);
+    acc = walloc(c, 4);
+  }
+  if (grad) {
+    up.Gm = walloc(c, (size_t)Ppmax * maxD);
+    up.GvT = walloc(c, (size_t)Ppmax * maxD);
+    up.GmPad = walloc(c, (size_t)Ppmax * 32);
+    up.gq = walloc(c, (size_t)Ppmax);
+    XaugPad = walloc(c, (size_t)Ppmax * 32);
+    dXa = walloc(c, (size_t)Ppmax * 32);
+    dXb = walloc(c, (size_t)Ppmax * 32);
+    rbf_part = walloc(c, (size_t)nbmax * 32);
+    skpart = walloc(c, max_splitk_part(lw));
+  }
+  if (c->dry) return DGP_OK;
+
+  const int DL = model->layers[nl - 1].D_out;
+  long n0 = 0;
+  bool first = true;
+  while (n0 < N) {
+    const long Nc = (N - n0 < Nc_max) ? (N - n0) : Nc_max;
+    const long P = Nc * S, Pp = round_up(P, kTileP);
+    // ---- forward chain (models/dgp.py:49-61) ----
+    for (int l = 0; l < nl; ++l) {
+      const dgp_layer_desc& d = model->layers[l];
+      ChunkLayer& cl = cls[l];
+      if (l == 0) { cl.Xin = X + n0 * d.D_in; cl.xmod = Nc; }
+      else { cl.Xin = cls[l - 1].F; cl.xmod = P; }
+      const bool last = l == nl - 1;
+      const bool need_sample = !last || o.need_last_sample || (o.io.Fs && o.io.Fs[l]);
+      RC(forward_layer(c, d, lw[l], cl, tmp, grad, Tshared, l, Nc, S, N, n0, seed, n_offset, o.io, need_sample));
+    }
+    const ChunkLayer& clL = cls[nl - 1];
+    // ---- prediction epilogues ----
+    if (o.pm) {
+      const long ND = Nc * DL;
+      LAUNCH(mixture_moments_kernel, (unsigned)((ND + 255) / 256), 256, 0, clL.Fmean, clL.Fvar, S, ND, model->lik_variance,
+             o.add_lik, o.pm + n0 * DL, o.pv + n0 * DL);
+    }
+    if (o.ei) {
+      const long ND = Nc * DL;
+      if (o.ei_analytic) {
+        double* m = tmp.t0;
+        double* v = tmp.t0 + ND;
+        LAUNCH(mixture_moments_kernel, (unsigned)((ND + 255) / 256), 256, 0, clL.Fmean, clL.Fvar, S, ND, model->lik_variance, 0, m, v);
+        LAUNCH(ei_analytic_kernel, (unsigned)((ND + 255) / 256), 256, 0, m, v, ND, o.y_min, o.ei + n0 * DL);
+      } else {
+        LAUNCH(ei_mc_kernel, (unsigned)((ND + 255) / 256), 256, 0, clL.F, S, ND, o.y_min, o.ei + n0 * DL);
+      }
+    }
+    // ---- likelihood + adjoint chain ----
+    if (grad || o.want_elbo) {
+      UpstreamOut uo{up.Gm, up.GvT, up.GmPad, up.gq, lik_part};
+      const long nb = Pp / 128;
+      LAUNCH(likelihood_kernel, (unsigned)nb, 128, 0, clL.Fmean, clL.Fvar, o.Y + n0 * o.Dy, model->lik_variance, Nc, P, Pp, DL,
+             o.scale / (double)S, grad ? 1 : 0, uo);
+      LAUNCH(reduce_partials_kernel, 2, 256, 0, lik_part, nb, 3, acc, first ? 0 : 1);
+      if (grad) {
+        up.part = lik_part; up.nblocks = nb;
+        double* dX_next = dXa;
+        for (int l = nl - 1; l >= 0; --l) {
+          const dgp_layer_desc& d = model->layers[l];
+          if (l < nl - 1) {
+            // Gm = G_F, Gv = G_F z / (2 sqrt(var + jitter))                          (adjoint of utils/utils.py:40-41)
+            UpstreamOut uh{up.Gm, up.GvT, up.GmPad, up.gq, lik_part};
+            LAUNCH(upstream_kernel, (unsigned)nb, 128, 0, dX_next, cls[l].z, cls[l].Fvar, P, Pp, d.D_out, d.jitter, uh);
+          }
+          double* dXin = (l > 0) ? (dX_next == dXa ? dXb : dXa) : nullptr;
+          RC(backward_layer(c, d, lw[l], cls[l], tmp, up, dXin, XaugPad, rbf_part, skpart, Nc, S, first));
+          if (dXin) dX_next = dXin;
+        }
+      }
+    }
+    n0 += Nc;
+    first = false;
+  }
+
+  // ---- replicated epilogue: KL, its adjoint, RBF adjoint on Kuu, gradient assembly ----
+  if (grad || o.want_elbo) {
+    double* out = o.out_flat;
+    std::vector<dgp_layer_grad_offsets> offs(nl);
+    dgp_grad_layout(model, offs.data());
+    // out[0] = data term, out[2] = d/d lik variance, out[1] = kl_weight * sum KL
+    CK(cudaMemcpyAsync(out, acc, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(out + 2, acc + 1, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    std::vector<const double*> klp(nl);
+    for (int l = 0; l < nl; ++l) klp[l] = lw[l].kl;
+    double* klsum = acc + 2;
+    CK(cudaMemsetAsync(klsum, 0, sizeof(double), c->stream));
+    for (int l = 0; l < nl; ++l) LAUNCH(reduce_partials_kernel, 1, 256, 0, lw[l].kl, 1, 1, klsum, 1);
+    LAUNCH(scale_copy_kernel, 1, 32, 0, klsum, o.kl_weight, out + 1);
+    if (grad) {
+      for (int l = 0; l < nl; ++l) {
+        const dgp_layer_desc& d = model->layers[l];
+        LayerWs& w = lw[l];
+        const long mm = (long)w.Mp * w.Mp;
+        LAUNCH(dku_assemble_kernel, (unsigned)((mm + 255) / 256), 256, 0, w.dKu, w.Kinv, w.KSK, w.alpha, w.Knj, w.M, w.Mp, w.D_out,
+               o.kl_weight, 1);
+        LAUNCH(kuu_bwd_kernel, w.M, 128, 0, w.dKu, d.Z, d.lengthscales, d.variance, w.M, w.Mp, w.D_in, w.dZk, w.kuu_part);
+        LAUNCH(reduce_partials_kernel, w.D_in + 1, 256, 0, w.kuu_part, (long)w.M, w.D_in + 1, w.kuu_red, 0);
+        FinalizeArgs f;
+        memset(&f, 0, sizeof(f));
+        f.Gd = w.dR; f.KR = w.KRcat; f.Rcat = w.Rcat; f.dqmu = w.dqmu; f.alpha = w.alpha; f.H = w.H; f.dZk = w.dZk;
+        f.rbf_red = w.rbf_red; f.kuu_red = w.kuu_red; f.sgv = w.sgv; f.Z = d.Z; f.ls = d.lengthscales;
+        f.M = w.M; f.Mp = w.Mp; f.D_in = w.D_in; f.D_out = w.D_out; f.klw = o.kl_weight;
+        f.dZ = out + offs[l].dZ; f.dls = out + offs[l].dlengthscales; f.dvar = out + offs[l].dvariance;
+        f.dq_mu = out + offs[l].dq_mu; f.dq_sqrt = out + offs[l].dq_sqrt;
+        const long nq = (long)w.D_out * w.M * w.M;
+        LAUNCH(finalize_layer_kernel, (unsigned)((nq + 255) / 256), 256, 0, f);
+      }
+    }
+  }
+  return DGP_OK;
+}
+
+// plan (dry) pass to size the arena, then the real pass
+int run_model_planned(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, long S, unsigned long long seed,
+                      long n_offset, RunOpts& o) {
+  CK(cudaSetDevice(c->device));
+  c->dry = true; c->used = 0;
+  int rc = run_model(c, model, X, N, S, seed, n_offset, o);
+  c->dry = false;
+  if (rc != DGP_OK) return rc;
+  RC(ensure_ws(c, c->used));
+  c->used = 0;
+  RC(run_model(c, model, X, N, S, seed, n_offset, o));
+  return DGP_OK;
+}
+
+int check_chol(dgp_ctx* c) {
+  int info = 0;
+  CK(cudaMemcpyAsync(&info, c->d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (info) { c->err = "Kuu + jitter I is not positive definite (Cholesky pivot <= 0)"; return DGP_ERR_NUMERIC; }
+  return DGP_OK;
+}
+
+}  // namespace
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+extern "C" {
+
+int dgp_version(void) { return 100; }
+
+int dgp_ctx_create(int device, void* cuda_stream, dgp_ctx** out) {
+  if (!out) return DGP_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return DGP_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return DGP_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return DGP_ERR_CUDA;
+  if (prop.major != 10) return DGP_ERR_UNSUPPORTED;   // sm_100a only: no fallback path exists
+  dgp_ctx* c = new dgp_ctx();
+  c->device = device;
+  c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  if (cudaMalloc(&c->d_info, sizeof(int)) != cudaSuccess) { delete c; return DGP_ERR_CUDA; }
+  const char* lim = getenv("DGP_B200_WS_GB");
+  if (lim && atof(lim) > 0.0) c->ws_limit = (size_t)(atof(lim) * (double)((size_t)1 << 30));
+  *out = c;
+  return DGP_OK;
+}
+
+void dgp_ctx_destroy(dgp_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->ws) cudaFree(c->ws);
+  if (c->d_info) cudaFree(c->d_info);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->d_stage) cudaFree(c->d_stage);
+  delete c;
+}
+
+const char* dgp_last_error(dgp_ctx* c) { return c ? c->err.c_str() : "null ctx"; }
+
+int dgp_set_stream(dgp_ctx* c, void* cuda_stream) {
+  if (!c) return DGP_ERR_ARG;
+  c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  return DGP_OK;
+}
+
+int64_t dgp_workspace_bytes(dgp_ctx* c) { return c ? (int64_t)c->cap : 0; }
+
+int dgp_set_workspace_limit(dgp_ctx* c, int64_t bytes) {
+  if (!c || bytes < ((int64_t)64 << 20)) return DGP_ERR_ARG;
+  c->ws_limit = (size_t)bytes;
+  return DGP_OK;
+}
+
+int64_t dgp_launch_count(dgp_ctx* c, int reset) {
+  if (!c) return 0;
+  long v = c->launches;
+  if (reset) c->launches = 0;
+  return v;
+}
+
+int dgp_philox_normal(dgp_ctx* c, uint64_t seed, int layer, int64_t S, int64_t N, int D, int64_t n_offset, double* z_out) {
+  if (!c || !z_out || S < 1 || N < 1 || D < 1) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  const long total = S * N * D;
+  LAUNCH(philox_normal_kernel, (unsigned)((total + 255) / 256), 256, 0, (unsigned long long)seed, layer, (long)S, (long)N, D,
+         (long)n_offset, z_out);
+  return DGP_OK;
+}
+
+int dgp_kernel_K(dgp_ctx* c, int D, const double* lengthscales, const double* variance, const double* X, int64_t n1,
+                 const double* X2, int64_t n2, double* K_out) {
+  if (!c || !X || !X2 || !K_out || D < 1 || D > kMaxD || n1 < 1 || n2 < 1) return DGP_ERR_ARG;
+  if (n1 > 2147483647LL) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  LAUNCH(kuf_kernel, dim3((unsigned)((n2 + kKufCols - 1) / kKufCols), (unsigned)((n1 + kKufRows - 1) / kKufRows)), 256, 0, X2,
+         (long)n2, X, lengthscales, variance, (int)n1, (int)n1, D, (long)n2, (long)n2, K_out);
+  return DGP_OK;
+}
+
+int dgp_kuu_chol(dgp_ctx* c, const dgp_layer_desc* layer, double* Ku_out, double* Lu_out) {
+  if (!c || !layer) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  dgp_model_desc m{1, layer, nullptr};
+  std::vector<LayerWs> lw;
+  c->dry = true; c->used = 0;
+  int rc = prep_layers(c, &m, lw, PREP_FWD);
+  c->dry = false;
+  RC(rc);
+  RC(ensure_ws(c, c->used));
+  c->used = 0;
+  RC(prep_layers(c, &m, lw, PREP_FWD));
+  const long mm = (long)layer->M * layer->M;
+  if (Ku_out) LAUNCH(unpad_square_kernel, (unsigned)((mm + 255) / 256), 256, 0, lw[0].Ku, lw[0].M, lw[0].Mp, Ku_out);
+  if (Lu_out) LAUNCH(unpad_square_kernel, (unsigned)((mm + 255) / 256), 256, 0, lw[0].L, lw[0].M, lw[0].Mp, Lu_out);
+  return check_chol(c);
+}
+
+int dgp_kl(dgp_ctx* c, const dgp_layer_desc* layer, double* kl_out) {
+  if (!c || !layer || !kl_out) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  dgp_model_desc m{1, layer, nullptr};
+  std::vector<LayerWs> lw;
+  c->dry = true; c->used = 0;
+  int rc = prep_layers(c, &m, lw, PREP_KL);
+  c->dry = false;
+  RC(rc);
+  RC(ensure_ws(c, c->used));
+  c->used = 0;
+  RC(prep_layers(c, &m, lw, PREP_KL));
+  CK(cudaMemcpyAsync(kl_out, lw[0].kl, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  return check_chol(c);
+}
+
+int dgp_conditional_nd(dgp_ctx* c, const dgp_layer_desc* layer, const double* X, int64_t P, double* mean, double* var) {
+  if (!c || !layer || !X || !mean || !var || P < 1) return DGP_ERR_ARG;
+  dgp_model_desc m{1, layer, nullptr};
+  RunOpts o;
+  double* fm[1] = {mean};
+  double* fv[1] = {var};
+  o.io.Fmeans = fm; o.io.Fvars = fv;
+  RC(run_model_planned(c, &m, X, P, 1, 0, 0, o));
+  return check_chol(c);
+}
+
+int dgp_propagate(dgp_ctx* c, const dgp_model_desc* model, const double* X, int64_t N, int64_t S, const double* const* zs_host,
+                  uint64_t seed, int64_t n_offset, double* const* Fs_host, double* const* Fmeans_host, double* const* Fvars_host) {
+  if (!c || !model || !X) return DGP_ERR_ARG;
+  RunOpts o;
+  o.io.zs = zs_host; o.io.Fs = Fs_host; o.io.Fmeans = Fmeans_host; o.io.Fvars = Fvars_host;
+  RC(run_model_planned(c, model, X, N, S, seed, n_offset, o));
+  return check_chol(c);
+}
+
+int64_t dgp_grad_size(const dgp_model_desc* model) {
+  if (!model) return 0;
+  int64_t n = 3;
+  for (int l = 0; l < model->num_layers; ++l) {
+    const dgp_layer_desc& d = model->layers[l];
+    n += (int64_t)d.M * d.D_in + d.D_in + 1 + (int64_t)d.M * d.D_out + (int64_t)d.D_out * d.M * d.M;
+  }
+  return n;
+}
+
+int dgp_grad_layout(const dgp_model_desc* model, dgp_layer_grad_offsets* offs) {
+  if (!model || !offs) return DGP_ERR_ARG;
+  int64_t n = 3;
+  for (int l = 0; l < model->num_layers; ++l) {
+    const dgp_layer_desc& d = model->layers[l];
+    offs[l].dZ = n; n += (int64_t)d.M * d.D_in;
+    offs[l].dlengthscales = n; n += d.D_in;
+    offs[l].dvariance = n; n += 1;
+    offs[l].dq_mu = n; n += (int64_t)d.M * d.D_out;
+    offs[l].dq_sqrt = n; n += (int64_t)d.D_out * d.M * d.M;
+  }
+  return DGP_OK;
+}
+
+int dgp_elbo_grad(dgp_ctx* c, const dgp_model_desc* model, const double* X, const double* Y, int64_t N, int64_t S, double scale,
+                  double kl_weight, const double* const* zs_host, uint64_t seed, int64_t n_offset, int want_grad,
+                  double* out_flat) {
+  if (!c || !model || !X || !Y || !out_flat) return DGP_ERR_ARG;
+  RunOpts o;
+  o.want_grad = want_grad != 0; o.want_elbo = true;
+  o.Y = Y; o.Dy = model->layers[model->num_layers - 1].D_out;
+  o.scale = scale; o.kl_weight = kl_weight; o.out_flat = out_flat; o.io.zs = zs_host;
+  return run_model_planned(c, model, X, N, S, seed, n_offset, o);
+}
+
+int dgp_elbo_grad_host(dgp_ctx* c, const dgp_model_desc* model, const double* X_host, const double* Y_host, int64_t N,
+                       int64_t S, double scale, double kl_weight, uint64_t seed, int64_t n_offset, int want_grad,
+                       double* out_flat_host) {
+  if (!c || !model || !X_host || !Y_host || !out_flat_host || N < 1) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  const int D0 = model->layers[0].D_in, Dy = model->layers[model->num_layers - 1].D_out;
+  const int64_t gs = want_grad ? dgp_grad_size(model) : 3;
+  const size_t nx = (size_t)N * D0, ny = (size_t)N * Dy;
+  const size_t need = (nx + ny + (size_t)gs) * sizeof(double);
+  if (c->h_pinned_bytes < need) {
+    if (c->h_pinned) CK(cudaFreeHost(c->h_pinned));
+    c->h_pinned = nullptr; c->h_pinned_bytes = 0;
+    CK(cudaMallocHost(&c->h_pinned, need));
+    c->h_pinned_bytes = need;
+  }
+  // device staging lives outside the arena (the arena may be re-grown by the call below)
+  if (c->d_stage_bytes < need) {
+    if (c->d_stage) CK(cudaFree(c->d_stage));
+    c->d_stage = nullptr; c->d_stage_bytes = 0;
+    CK(cudaMalloc(&c->d_stage, need));
+    c->d_stage_bytes = need;
+  }
+  double* d_stage = c->d_stage;
+  memcpy(c->h_pinned, X_host, nx * sizeof(double));
+  memcpy(c->h_pinned + nx, Y_host, ny * sizeof(double));
+  CK(cudaMemcpyAsync(d_stage, c->h_pinned, (nx + ny) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  double* d_out = d_stage + nx + ny;
+  RC(dgp_elbo_grad(c, model, d_stage, d_stage + nx, N, S, scale, kl_weight, nullptr, seed, n_offset, want_grad, d_out));
+  CK(cudaMemcpyAsync(c->h_pinned + nx + ny, d_out, (size_t)gs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  memcpy(out_flat_host, c->h_pinned + nx + ny, (size_t)gs * sizeof(double));
+  return check_chol(c);
+}
+
+int dgp_predict_moments(dgp_ctx* c, const dgp_model_desc* model, const double* X, int64_t N, int64_t S,
+                        const double* const* zs_host, uint64_t seed, int64_t n_offset, int add_lik_var, double* mean, double* var) {
+  if (!c || !model || !X || !mean || !var) return DGP_ERR_ARG;
+  if (add_lik_var && !model->lik_variance) { c->err = "lik_variance is null"; return DGP_ERR_ARG; }
+  RunOpts o;
+  o.io.zs = zs_host; o.pm = mean; o.pv = var; o.add_lik = add_lik_var;
+  return run_model_planned(c, model, X, N, S, seed, n_offset, o);
+}
+
+int dgp_ei(dgp_ctx* c, const dgp_model_desc* model, const double* X, int64_t N, int64_t S, const double* const* zs_host,
+           uint64_t seed, int64_t n_offset, double y_min, int analytic, double* neg_ei) {
+  if (!c || !model || !X || !neg_ei) return DGP_ERR_ARG;
+  RunOpts o;
+  o.io.zs = zs_host; o.ei = neg_ei; o.y_min = y_min; o.ei_analytic = analytic; o.need_last_sample = !analytic;
+  return run_model_planned(c, model, X, N, S, seed, n_offset, o);
+}
+
+int dgp_ehvi2d(dgp_ctx* c, const double* m0, const double* v0, const double* m1, const double* v1, int64_t N, const double* ynd0,
+               const double* ynd1, int n, double* out) {
+  if (!c || !m0 || !v0 || !m1 || !v1 || !ynd0 || !ynd1 || !out || N < 1 || n < 2 || n > 2048) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  LAUNCH(ehvi2d_kernel, (unsigned)((N + 127) / 128), 128, 2 * (size_t)n * sizeof(double), m0, v0, m1, v1, (long)N, ynd0, ynd1, n, out);
+  return DGP_OK;
+}
+
+int dgp_debug_gemm(dgp_ctx* c, int nt, int M, int N, int K, double alpha, const double* A, const double* B, double beta,
+                   double* C, int a_tri, int c_lower, int batch, int splitk, const double* kscale) {
+  if (!c) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  GemmArgs g = gargs(A, K, B, nt ? K : N, C, N, M, N, K);
+  g.alpha = alpha; g.beta = beta; g.a_tri = a_tri; g.c_lower = c_lower; g.batch = batch < 1 ? 1 : batch;
+  g.sA = (long)M * K; g.sB = nt ? (long)N * K : (long)K * N; g.sC = (long)M * N;
+  g.kscale = kscale; g.sScale = K;
+  g.splitk = splitk < 1 ? 1 : splitk;
+  if (g.splitk > 1) {
+    RC(ensure_ws(c, (size_t)g.splitk * g.batch * M * N * sizeof(double)));
+    g.part = reinterpret_cast<double*>(c->ws);
+  }
+  return gemm(c, g, nt != 0);
+}
+
+}  // extern "C"

@@ -1,0 +1,249 @@
+// FP64 tensor-core (DMMA.8x8x4) GEMM engine used by every dense / triangular contraction on the DGP path.
+//
+//   NN:  C[b] = alpha * A[b] (M x K, row-major) * B[b] (K x N, row-major) + beta * C[b]
+//   NT:  C[b] = alpha * A[b] (M x K) * diag(kscale[b]) * B[b]^T (B is N x K, row-major) + beta * C[b]
+//
+// Operands are staged global -> shared with a STAGES-deep cp.async ring; each warp owns a (BM/WM) x (BN/WN)
+// sub-tile held as DMMA accumulator fragments. All dimensions are multiples of the tile sizes (buffers on the
+// path are padded by construction), so there is no bounds checking in the inner loop.
+//   a_tri = 1: A is lower triangular (K-range clipped at the row block), 2: upper triangular.
+//   c_lower = 1: only tiles touching the lower triangle of C are computed (symmetric rank-k updates).
+//   splitk > 1: K is cut into splitk chunks, partial tiles go to `part` and are summed in a fixed order
+//               (deterministic, no atomics) by gemm_splitk_reduce.
+#pragma once
+#include "common.cuh"
+
+namespace dgp {
+
+struct GemmArgs {
+  const double* A; long lda; long sA;
+  const double* B; long ldb; long sB;
+  double* C; long ldc; long sC;
+  int M, N, K;
+  double alpha, beta;
+  const double* kscale; long sScale;
+  int a_tri;
+  int c_lower;
+  int batch;
+  int splitk;
+  double* part;
+  // K-concatenation: K = kblocks * kblk; A is [M][kblocks*kblk], B is the row-stacked [kblocks*kblk][N] (NN only).
+  // With a_tri = 1 every block is lower triangular (its k-range is clipped at the row block). kblocks <= 1: plain GEMM.
+  int kblocks; int kblk;
+  // Optional column scale of B in NN mode: B[k][n] *= bscale_mul * bscale[(k / kblk) * ld_bscale + n].
+  const double* bscale; long ld_bscale; double bscale_mul;
+};
+
+template <int BM, int BN, int BK, int WM, int WN, bool NT, int STAGES>
+struct GemmCfg {
+  static constexpr int THREADS = WM * WN * 32;
+  static constexpr int TM = BM / WM / 8, TN = BN / WN / 8;
+  static constexpr int LDA = BK + 4;
+  static constexpr int LDB = NT ? BK + 4 : BN + 4;
+  static constexpr int A_STAGE = BM * LDA;
+  static constexpr int B_STAGE = NT ? BN * LDB : BK * LDB;
+  static constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE + BK) * sizeof(double);
+};
+
+template <int BM, int BN, int BK, int WM, int WN, bool NT, int STAGES>
+__global__ void __launch_bounds__(WM* WN * 32) gemm_kernel(GemmArgs g) {
+  using Cfg = GemmCfg<BM, BN, BK, WM, WN, NT, STAGES>;
+  constexpr int THREADS = Cfg::THREADS, TM = Cfg::TM, TN = Cfg::TN, LDA = Cfg::LDA, LDB = Cfg::LDB;
+  constexpr int A_STAGE = Cfg::A_STAGE, B_STAGE = Cfg::B_STAGE;
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;
+  double* Bs = As + STAGES * A_STAGE;
+  double* Ss = Bs + STAGES * B_STAGE;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g8 = lane >> 2, t4 = lane & 3;
+  const int wm = warp / WN, wn = warp % WN;
+
+  const int mt_count = g.M / BM, nt_count = g.N / BN;
+  long bid = blockIdx.x;
+  const int mt = (int)(bid % mt_count); bid /= mt_count;
+  const int b = (int)(bid % g.batch); bid /= g.batch;
+  const int nt = (int)(bid % nt_count); bid /= nt_count;
+  const int split = (int)bid;
+  const int m0 = mt * BM, n0 = nt * BN;
+  if (g.c_lower && n0 >= m0 + BM) return;
+
+  const int kchunk = g.K / g.splitk;
+  int kbeg = split * kchunk, kend = kbeg + kchunk;
+  if (g.a_tri == 1) kend = min(kend, m0 + BM);
+  if (g.a_tri == 2) kbeg = max(kbeg, (m0 / BK) * BK);
+  int ktiles = kend > kbeg ? (kend - kbeg) / BK : 0;
+  int tpb = ktiles > 0 ? ktiles : 1;   // k-tiles per concatenated block
+  const int kblk = g.kblocks > 1 ? g.kblk : 0;
+  if (g.kblocks > 1) {
+    const int hi = g.a_tri == 1 ? min(g.kblk, m0 + BM) : g.kblk;
+    kbeg = 0;
+    tpb = hi / BK;
+    ktiles = g.kblocks * tpb;
+  }
+  auto koff = [&](int kt) { const int blk = kt / tpb; return blk * kblk + kbeg + (kt - blk * tpb) * BK; };
+
+  const double* Ab = g.A + (long)b * g.sA;
+  const double* Bb = g.B + (long)b * g.sB;
+  const double* Sb = g.kscale ? g.kscale + (long)b * g.sScale : nullptr;
+
+  auto load_stage = [&](int stage, int k0) {
+    double* as = As + stage * A_STAGE;
+    double* bs = Bs + stage * B_STAGE;
+    constexpr int A_CHUNKS = BM * BK / 2;
+    for (int c = tid; c < A_CHUNKS; c += THREADS) {
+      int r = c / (BK / 2), cc = c % (BK / 2);
+      cp_async16(as + r * LDA + cc * 2, Ab + (long)(m0 + r) * g.lda + k0 + cc * 2);
+    }
+    if (NT) {
+      constexpr int B_CHUNKS = BN * BK / 2;
+      for (int c = tid; c < B_CHUNKS; c += THREADS) {
+        int r = c / (BK / 2), cc = c % (BK / 2);
+        cp_async16(bs + r * LDB + cc * 2, Bb + (long)(n0 + r) * g.ldb + k0 + cc * 2);
+      }
+    } else {
+      constexpr int B_CHUNKS = BK * BN / 2;
+      for (int c = tid; c < B_CHUNKS; c += THREADS) {
+        int r = c / (BN / 2), cc = c % (BN / 2);
+        cp_async16(bs + r * LDB + cc * 2, Bb + (long)(k0 + r) * g.ldb + n0 + cc * 2);
+      }
+    }
+    if (Sb) {
+      for (int c = tid; c < BK / 2; c += THREADS) cp_async16(Ss + stage * BK + c * 2, Sb + k0 + c * 2);
+    }
+  };
+
+  double c0[TM][TN], c1[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) { c0[i][j] = 0.0; c1[i][j] = 0.0; }
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < ktiles) load_stage(s, koff(s));
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < ktiles; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      int nk = kt + STAGES - 1;
+      if (nk < ktiles) load_stage(nk % STAGES, koff(nk));
+      cp_async_commit();
+    }
+    const int st = kt % STAGES;
+    const double* as = As + st * A_STAGE + (wm * TM * 8 + g8) * LDA + t4;
+    const double* bs = NT ? Bs + st * B_STAGE + (wn * TN * 8 + g8) * LDB + t4
+                          : Bs + st * B_STAGE + t4 * LDB + wn * TN * 8 + g8;
+    const double* ss = Ss + st * BK + t4;
+    double bsc[TN];
+    if (!NT && g.bscale) {
+      const double* bp = g.bscale + (long)(kt / tpb) * g.ld_bscale + n0 + wn * TN * 8 + g8;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) bsc[j] = g.bscale_mul * bp[j * 8];
+    }
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+      double a[TM], bb[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = as[i * 8 * LDA + kk * 4];
+      if (Sb) {
+        double s = ss[kk * 4];
+#pragma unroll
+        for (int i = 0; i < TM; ++i) a[i] *= s;
+      }
+#pragma unroll
+      for (int j = 0; j < TN; ++j) bb[j] = NT ? bs[j * 8 * LDB + kk * 4] : bs[kk * 4 * LDB + j * 8];
+      if (!NT && g.bscale) {
+#pragma unroll
+        for (int j = 0; j < TN; ++j) bb[j] *= bsc[j];
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) dmma884(c0[i][j], c1[i][j], a[i], bb[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  if (g.splitk > 1) {
+    double* P = g.part + ((long)split * g.batch + b) * (long)g.M * g.N;
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        int row = m0 + wm * TM * 8 + i * 8 + g8, col = n0 + wn * TN * 8 + j * 8 + 2 * t4;
+        *reinterpret_cast<double2*>(P + (long)row * g.N + col) = make_double2(c0[i][j], c1[i][j]);
+      }
+  } else {
+    double* Cb = g.C + (long)b * g.sC;
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        int row = m0 + wm * TM * 8 + i * 8 + g8, col = n0 + wn * TN * 8 + j * 8 + 2 * t4;
+        double2* p = reinterpret_cast<double2*>(Cb + (long)row * g.ldc + col);
+        double2 v = make_double2(g.alpha * c0[i][j], g.alpha * c1[i][j]);
+        if (g.beta != 0.0) { double2 o = *p; v.x += g.beta * o.x; v.y += g.beta * o.y; }
+        *p = v;
+      }
+  }
+}
+
+// Sums split-K partials in split order (deterministic): C = alpha * sum_s part[s] + beta * C.
+__global__ void gemm_splitk_reduce(GemmArgs g, int BM, int BN) {
+  long total = (long)g.batch * g.M * g.N;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    int col = (int)(idx % g.N);
+    long r = idx / g.N;
+    int row = (int)(r % g.M);
+    int b = (int)(r / g.M);
+    if (g.c_lower && (col / BN) * BN >= (row / BM) * BM + BM) continue;
+    double s = 0.0;
+    for (int k = 0; k < g.splitk; ++k) s += g.part[((long)k * g.batch + b) * (long)g.M * g.N + (long)row * g.N + col];
+    double* p = g.C + (long)b * g.sC + (long)row * g.ldc + col;
+    double v = g.alpha * s;
+    if (g.beta != 0.0) v += g.beta * *p;
+    *p = v;
+  }
+}
+
+template <int BM, int BN, int BK, int WM, int WN, bool NT, int STAGES>
+inline cudaError_t gemm_launch_cfg(const GemmArgs& g, cudaStream_t st) {
+  using Cfg = GemmCfg<BM, BN, BK, WM, WN, NT, STAGES>;
+  auto kern = gemm_kernel<BM, BN, BK, WM, WN, NT, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  long blocks = (long)(g.M / BM) * (g.N / BN) * g.batch * g.splitk;
+  kern<<<(unsigned)blocks, Cfg::THREADS, Cfg::SMEM, st>>>(g);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (g.splitk > 1) {
+    long total = (long)g.batch * g.M * g.N;
+    int rb = (int)((total + 255) / 256);
+    if (rb > 148 * 8) rb = 148 * 8;
+    gemm_splitk_reduce<<<rb, 256, 0, st>>>(g, BM, BN);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+// Picks a tile configuration. Returns cudaErrorInvalidValue when the shape is not tile-aligned.
+inline cudaError_t gemm_launch(const GemmArgs& g, bool nt, cudaStream_t st) {
+  if (g.M % 64 || g.K % 16 || g.splitk < 1 || (g.K / g.splitk) % 16 || (g.splitk > 1 && !g.part)) return cudaErrorInvalidValue;
+  if (g.kblocks > 1 && (nt || g.splitk != 1 || g.kblk % 16 || g.kblocks * g.kblk != g.K || g.a_tri == 2)) return cudaErrorInvalidValue;
+  if (g.N == 32 && !nt) return gemm_launch_cfg<64, 32, 16, 2, 1, false, 3>(g, st);
+  if (g.N % 64) return cudaErrorInvalidValue;
+  bool big = (g.M % 128 == 0) && (g.N % 128 == 0) && g.a_tri == 0 && ((long)g.M * g.N * g.batch >= 128L * 128 * 64);
+  if (big) {
+    return nt ? gemm_launch_cfg<128, 128, 16, 4, 4, true, 3>(g, st) : gemm_launch_cfg<128, 128, 16, 4, 4, false, 3>(g, st);
+  }
+  return nt ? gemm_launch_cfg<64, 64, 16, 2, 2, true, 3>(g, st) : gemm_launch_cfg<64, 64, 16, 2, 2, false, 3>(g, st);
+}
+
+}  // namespace dgp

@@ -1,0 +1,192 @@
+// Per-layer, per-step replicated work: Kuu build, blocked Cholesky, explicit triangular inverse.
+// One CTA per layer (all layers of the model in one launch); matrices live in L2, panels in shared memory.
+// Reference semantics: dgp_dace/utils/layers.py:227-234 (Ku = Kuu + jitter I, Lu = chol(Ku)).
+#pragma once
+#include "common.cuh"
+
+namespace dgp {
+
+// Ku[i][j] = s2 * exp(-0.5 * sum_j ((z_i - z_j)/l)^2) + jitter * (i==j) for i,j < M; identity on the padding.
+// Knj receives the same matrix without jitter (zero on the padding) for the RBF backward of Kuu.
+__global__ void kuu_build_kernel(const double* __restrict__ Z, const double* __restrict__ ls, const double* __restrict__ var,
+                                 int M, int Mp, int D, double jitter, double* __restrict__ Ku, double* __restrict__ Knj) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)Mp * Mp) return;
+  int i = (int)(idx / Mp), j = (int)(idx % Mp);
+  double k = 0.0, kj = 0.0;
+  if (i < M && j < M) {
+    double r2 = 0.0;
+    for (int d = 0; d < D; ++d) {
+      double t = (Z[(long)i * D + d] - Z[(long)j * D + d]) / ls[d];
+      r2 = fma(t, t, r2);
+    }
+    k = var[0] * exp(-0.5 * r2);
+    kj = k + (i == j ? jitter : 0.0);
+  } else {
+    kj = (i == j) ? 1.0 : 0.0;
+  }
+  Ku[idx] = kj;
+  Knj[idx] = k;
+}
+
+struct CholArgs {
+  const double* Ku;  // [Mp][Mp]
+  double* L;         // [Mp][Mp] lower, zero above the diagonal
+  double* Linv;      // [Mp][Mp] lower
+  double* LinvT;     // [Mp][Mp] upper
+  int Mp;
+  int* info;         // set to 1 when a pivot is not positive
+};
+
+constexpr int kCholNB = 32;
+constexpr int kCholThreads = 512;
+
+// dynamic shared memory: D[32][33] + panel[(Mp)][33]  (panel reused as the G block [32][Mp+1] of the inverse)
+inline size_t chol_smem_bytes(int Mp) { return (size_t)(32 * 33 + (size_t)Mp * 33 + 64) * sizeof(double); }
+
+__global__ void __launch_bounds__(kCholThreads) chol_inv_kernel(const CholArgs* __restrict__ args) {
+  const CholArgs a = args[blockIdx.x];
+  const int n = a.Mp, tid = threadIdx.x, nth = blockDim.x;
+  extern __shared__ __align__(16) double sm[];
+  double* D = sm;              // [32][33]
+  double* Pn = sm + 32 * 33;   // [n][33]
+  double* L = a.L;
+
+  for (long idx = tid; idx < (long)n * n; idx += nth) {
+    int i = (int)(idx / n), j = (int)(idx % n);
+    L[idx] = (j <= i) ? a.Ku[idx] : 0.0;
+  }
+  __syncthreads();
+
+  const int nb = n / kCholNB;
+  for (int kb = 0; kb < nb; ++kb) {
+    const int k0 = kb * kCholNB;
+    // 1. diagonal block -> smem, unblocked Cholesky by warp 0
+    for (int idx = tid; idx < 1024; idx += nth) {
+      int r = idx >> 5, c = idx & 31;
+      D[r * 33 + c] = L[(long)(k0 + r) * n + k0 + c];
+    }
+    __syncthreads();
+    if (tid < 32) {
+      const int r = tid;
+      for (int j = 0; j < 32; ++j) {
+        double djj = D[j * 33 + j];
+        if (r == j) {
+          if (!(djj > 0.0)) *a.info = 1;
+          D[j * 33 + j] = sqrt(djj);
+        }
+        __syncwarp();
+        double piv = D[j * 33 + j];
+        if (r > j) D[r * 33 + j] = D[r * 33 + j] / piv;
+        __syncwarp();
+        if (r > j) {
+          double lrj = D[r * 33 + j];
+          for (int c = j + 1; c <= r; ++c) D[r * 33 + c] -= lrj * D[c * 33 + j];
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 1024; idx += nth) {
+      int r = idx >> 5, c = idx & 31;
+      L[(long)(k0 + r) * n + k0 + c] = (c <= r) ? D[r * 33 + c] : 0.0;
+    }
+    // 2. panel solve: X * Lkk^T = A  (one thread per row below the block)
+    const int nt = n - k0 - kCholNB;
+    for (int r = tid; r < nt; r += nth) {
+      double x[32];
+      const double* arow = L + (long)(k0 + kCholNB + r) * n + k0;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) x[c] = arow[c];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        double s = x[c];
+#pragma unroll
+        for (int k = 0; k < c; ++k) s -= x[k] * D[c * 33 + k];
+        x[c] = s / D[c * 33 + c];
+      }
+      double* orow = L + (long)(k0 + kCholNB + r) * n + k0;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) { orow[c] = x[c]; Pn[r * 33 + c] = x[c]; }
+    }
+    __syncthreads();
+    // 3. trailing update on the lower triangle, 4x4 micro-tiles
+    const int nt4 = nt / 4;
+    for (int tix = tid; tix < nt4 * nt4; tix += nth) {
+      int ti = tix / nt4, tj = tix % nt4;
+      if (tj > ti) continue;
+      double acc[4][4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] = 0.0;
+      const double* pi = Pn + (ti * 4) * 33;
+      const double* pj = Pn + (tj * 4) * 33;
+      for (int c = 0; c < 32; ++c) {
+        double ai[4], bj[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) { ai[p] = pi[p * 33 + c]; bj[p] = pj[p * 33 + c]; }
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[p][q] = fma(ai[p], bj[q], acc[p][q]);
+      }
+      const int r0 = k0 + kCholNB + ti * 4, c0 = k0 + kCholNB + tj * 4;
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (c0 + q <= r0 + p) L[(long)(r0 + p) * n + c0 + q] -= acc[p][q];
+    }
+    __syncthreads();
+  }
+
+  // ---- explicit inverse, block row by block row: X_i = Lii^{-1} (E_i - L[i, 0:i0] X[0:i0, :]) ----
+  double* X = a.Linv;
+  double* G = Pn;  // [32][n+1]
+  const int ldg = n + 1;
+  for (int ib = 0; ib < nb; ++ib) {
+    const int i0 = ib * kCholNB;
+    for (int idx = tid; idx < 1024; idx += nth) {
+      int r = idx >> 5, c = idx & 31;
+      D[r * 33 + c] = L[(long)(i0 + r) * n + i0 + c];
+    }
+    const int ncols = i0 + kCholNB;
+    for (int idx = tid; idx < 32 * ncols; idx += nth) {
+      int r = idx / ncols, c = idx % ncols;
+      double s;
+      if (c >= i0) {
+        s = (c - i0 == r) ? 1.0 : 0.0;
+      } else {
+        s = 0.0;
+        const double* lrow = L + (long)(i0 + r) * n;
+        for (int k = c; k < i0; ++k) s = fma(-lrow[k], X[(long)k * n + c], s);
+      }
+      G[r * ldg + c] = s;
+    }
+    __syncthreads();
+    for (int c = tid; c < ncols; c += nth) {
+      double x[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        double s = G[r * ldg + c];
+#pragma unroll
+        for (int k = 0; k < r; ++k) s -= D[r * 33 + k] * x[k];
+        x[r] = s / D[r * 33 + r];
+      }
+#pragma unroll
+      for (int r = 0; r < 32; ++r) X[(long)(i0 + r) * n + c] = x[r];
+    }
+    for (int idx = tid; idx < 32 * (n - ncols); idx += nth) {
+      int r = idx / (n - ncols), c = ncols + idx % (n - ncols);
+      X[(long)(i0 + r) * n + c] = 0.0;
+    }
+    __syncthreads();
+  }
+  for (long idx = tid; idx < (long)n * n; idx += nth) {
+    int i = (int)(idx / n), j = (int)(idx % n);
+    a.LinvT[(long)j * n + i] = X[idx];
+  }
+}
+
+}  // namespace dgp

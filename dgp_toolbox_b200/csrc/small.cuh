@@ -1,0 +1,153 @@
+// M^2 / M^3-class replicated kernels: parameter padding, KL (utils/layers.py:280-308), its adjoint, the RBF adjoint
+// on Kuu and the final gradient assembly.
+#pragma once
+#include "common.cuh"
+
+namespace dgp {
+
+// RpT[d][i][j] = q_sqrt[d][j][i] (upper triangular, A-operand of T_d = R_d^T A); Rcat[i][d*Mp + j] = q_sqrt[d][i][j]
+// (lower-triangular blocks side by side, A-operand of the K-concatenated products); qmuP[Mp][32]. Zero on the padding.
+__global__ void pad_params_kernel(const double* __restrict__ q_sqrt, const double* __restrict__ q_mu, int M, int Mp, int D,
+                                  double* __restrict__ RpT, double* __restrict__ Rcat, double* __restrict__ qmuP) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long nR = (long)D * Mp * Mp;
+  if (idx < nR) {
+    int j = (int)(idx % Mp);
+    long r = idx / Mp;
+    int i = (int)(r % Mp), d = (int)(r / Mp);
+    RpT[idx] = (j < M && i <= j) ? q_sqrt[((long)d * M + j) * M + i] : 0.0;
+    Rcat[(long)i * D * Mp + (long)d * Mp + j] = (i < M && j <= i) ? q_sqrt[((long)d * M + i) * M + j] : 0.0;
+  }
+  if (idx < (long)Mp * 32) {
+    int d = (int)(idx % 32), m = (int)(idx / 32);
+    qmuP[idx] = (m < M && d < D) ? q_mu[(long)m * D + d] : 0.0;
+  }
+}
+
+// KL = -0.5 D M - sum log|R_ii| + D sum log L_ii + 0.5 |Linv R|_F^2 + 0.5 sum q_mu o alpha     (non-white, layers.py:280-308)
+// LR = Linv Rcat [Mp][D*Mp]; alpha = Kinv q_mu [Mp][32]. Single block, fixed reduction tree.
+__global__ void __launch_bounds__(1024) kl_kernel(const double* __restrict__ L, const double* __restrict__ Rcat,
+                                                  const double* __restrict__ LR, const double* __restrict__ qmuP,
+                                                  const double* __restrict__ alpha, int M, int Mp, int D, double* __restrict__ kl) {
+  __shared__ double red[32];
+  double s = 0.0;
+  const long nLR = (long)D * Mp * Mp;
+  for (long i = threadIdx.x; i < nLR; i += blockDim.x) { double v = LR[i]; s = fma(0.5 * v, v, s); }
+  for (long i = threadIdx.x; i < (long)Mp * 32; i += blockDim.x) s = fma(0.5 * qmuP[i], alpha[i], s);
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    s += (double)D * log(L[(long)i * Mp + i]);
+    for (int d = 0; d < D; ++d) { double r = Rcat[(long)i * D * Mp + (long)d * Mp + i]; s -= 0.5 * log(r * r); }
+  }
+  double r = block_sum(s, red);
+  if (threadIdx.x == 0) kl[0] = r - 0.5 * (double)D * (double)M;
+}
+
+// dKu = dKu_data - klw * (0.5 D Kinv - 0.5 Kinv Ssum Kinv - 0.5 alpha alpha^T); Gbar = dKu o Knj (in place into dKu)
+__global__ void dku_assemble_kernel(double* __restrict__ dKu, const double* __restrict__ Kinv, const double* __restrict__ KSK,
+                                    const double* __restrict__ alpha, const double* __restrict__ Knj, int M, int Mp, int D,
+                                    double klw, int have_data) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)Mp * Mp) return;
+  int i = (int)(idx / Mp), j = (int)(idx % Mp);
+  double v = 0.0;
+  if (i < M && j < M) {
+    double aa = 0.0;
+    for (int d = 0; d < D; ++d) aa = fma(alpha[i * 32 + d], alpha[j * 32 + d], aa);
+    v = (have_data ? dKu[idx] : 0.0) - klw * (0.5 * D * Kinv[idx] - 0.5 * KSK[idx] - 0.5 * aa);
+    v *= Knj[idx];
+  }
+  dKu[idx] = v;
+}
+
+// RBF adjoint on Kuu, one block per inducing row a:
+//   dZ[a][j] = -sum_b (G[a][b] + G[b][a]) (z_a - z_b)_j / l_j^2 ; part[a][j] = sum_b G[a][b] (z_a - z_b)_j^2 / l_j^3 ; part[a][D] = sum_b G[a][b]/s2
+__global__ void __launch_bounds__(128) kuu_bwd_kernel(const double* __restrict__ G, const double* __restrict__ Z,
+                                                      const double* __restrict__ ls, const double* __restrict__ var, int M, int Mp,
+                                                      int D, double* __restrict__ dZk, double* __restrict__ part) {
+  __shared__ double red[32];
+  const int a = blockIdx.x;
+  double accz[kMaxD], accl[kMaxD], accs = 0.0;
+  for (int j = 0; j < D; ++j) { accz[j] = 0.0; accl[j] = 0.0; }
+  for (int b = threadIdx.x; b < M; b += blockDim.x) {
+    const double gab = G[(long)a * Mp + b], gba = G[(long)b * Mp + a];
+    accs += gab;
+    for (int j = 0; j < D; ++j) {
+      const double il = 1.0 / ls[j];
+      const double t = (Z[(long)a * D + j] - Z[(long)b * D + j]) * il;
+      accz[j] -= (gab + gba) * t * il;
+      accl[j] += gab * t * t * il;
+    }
+  }
+  for (int j = 0; j < D; ++j) {
+    double rz = block_sum(accz[j], red);
+    double rl = block_sum(accl[j], red);
+    if (threadIdx.x == 0) { dZk[(long)a * D + j] = rz; part[(long)a * (D + 1) + j] = rl; }
+  }
+  double rs = block_sum(accs / var[0], red);
+  if (threadIdx.x == 0) part[(long)a * (D + 1) + D] = rs;
+}
+
+struct FinalizeArgs {
+  // inputs
+  const double* Gd;       // [D_out][Mp][Mp]  tril(A dT_d^T)     (null when no data term)
+  const double* KR;       // [Mp][D_out*Mp]   Kinv Rcat
+  const double* Rcat;     // [Mp][D_out*Mp]
+  const double* dqmu;     // [Mp][32] data part (null when no data term)
+  const double* alpha;    // [Mp][32]
+  const double* H;        // [Mp][32] Gbar [X,1]  (null when no data term)
+  const double* dZk;      // [M][D_in] Kuu part
+  const double* rbf_red;  // [D_in+1] data-part partial sums (dl_j..., ds2)  (null when no data term)
+  const double* kuu_red;  // [D_in+1]
+  const double* sgv;      // [3] -> [2] = sum Gv (K_diag term)   (null when no data term)
+  const double* Z; const double* ls;
+  int M, Mp, D_in, D_out;
+  double klw;
+  // outputs (unpadded, inside the flat gradient buffer)
+  double* dZ; double* dls; double* dvar; double* dq_mu; double* dq_sqrt;
+};
+
+__global__ void finalize_layer_kernel(FinalizeArgs a) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long nq = (long)a.D_out * a.M * a.M;
+  if (idx < nq) {
+    int j = (int)(idx % a.M);
+    long r = idx / a.M;
+    int i = (int)(r % a.M), d = (int)(r / a.M);
+    double v = 0.0;
+    if (j <= i) {
+      const long off = ((long)d * a.Mp + i) * a.Mp + j;
+      const long offc = (long)i * a.D_out * a.Mp + (long)d * a.Mp + j;
+      v = (a.Gd ? a.Gd[off] : 0.0) - a.klw * (a.KR[offc] - (i == j ? 1.0 / a.Rcat[offc] : 0.0));
+    }
+    a.dq_sqrt[idx] = v;
+  }
+  if (idx < (long)a.M * a.D_out) {
+    int d = (int)(idx % a.D_out), m = (int)(idx / a.D_out);
+    a.dq_mu[idx] = (a.dqmu ? a.dqmu[m * 32 + d] : 0.0) - a.klw * a.alpha[m * 32 + d];
+  }
+  if (idx < (long)a.M * a.D_in) {
+    int j = (int)(idx % a.D_in), m = (int)(idx / a.D_in);
+    double v = a.dZk[idx];
+    if (a.H) {
+      const double il = 1.0 / a.ls[j];
+      v -= (a.Z[idx] * a.H[m * 32 + a.D_in] - a.H[m * 32 + j]) * il * il;
+    }
+    a.dZ[idx] = v;
+  }
+  if (idx < a.D_in) a.dls[idx] = (a.rbf_red ? a.rbf_red[idx] : 0.0) + a.kuu_red[idx];
+  if (idx == 0) a.dvar[0] = (a.rbf_red ? a.rbf_red[a.D_in] : 0.0) + a.kuu_red[a.D_in] + (a.sgv ? a.sgv[2] : 0.0);
+}
+
+__global__ void scale_copy_kernel(const double* in, double s, double* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = s * in[0];
+}
+
+// Copies the leading [M][M] block of a padded [Mp][Mp] matrix.
+__global__ void unpad_square_kernel(const double* __restrict__ in, int M, int Mp, double* __restrict__ out) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)M * M) return;
+  int i = (int)(idx / M), j = (int)(idx % M);
+  out[idx] = in[(long)i * Mp + j];
+}
+
+}  // namespace dgp

@@ -1,0 +1,266 @@
+"""DGP_Base / DGP with the reference's interface (dgp_dace/models/dgp.py:21-130,221-254,348-366).
+
+propagate / predict / ELBO and the ELBO gradient run in libdgp_b200 (hand-written sm_100a CUDA behind the C ABI of
+include/dgp_b200.h). The optimiser loops keep the reference's structure (dgp.py:255-345): a Python `for` around one
+ELBO+gradient evaluation per step, Adam on the *unconstrained* variables exactly as tf.GradientTape sees them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .. import gpflow_shim as gpflow
+from ..gpflow_shim import _Module
+from ..utils.layer_initializations import init_layers_linear
+from ..utils.utils import BroadcastingLikelihood
+
+
+class DGP_Base(_Module):
+    """dgp_dace/models/dgp.py:21-130."""
+
+    def __init__(self, likelihood, layers, num_samples=1, seed=0, **kwargs):
+        self.name = "dgp"
+        self.num_samples = num_samples
+        self.likelihood = BroadcastingLikelihood(likelihood)
+        self.layers = layers
+        self.seed = int(seed)        # Philox key of the in-kernel draws (replaces tf.random.normal, utils/layers.py:113)
+        self._draw = 0               # advanced once per stochastic evaluation so successive steps use fresh draws
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def device(self):
+        return self.layers[0].feature.Z.value.device
+
+    @property
+    def parameters(self):
+        out = []
+        for l in self.layers:
+            out.extend(l.parameters)
+        out.extend(self.likelihood.likelihood.parameters)
+        return out
+
+    @property
+    def trainable_variables(self):
+        return self.trainable_parameters
+
+    def _model_desc(self):
+        keep = []
+        arr = (_lib.LayerDesc * len(self.layers))()
+        for i, l in enumerate(self.layers):
+            d, k = l._desc()
+            arr[i] = d
+            keep.append(k)
+        lv = self.likelihood.likelihood.variance.value.reshape(1)
+        keep.append(lv)
+        m = _lib.ModelDesc(len(self.layers), arr, lv.data_ptr())
+        keep.append(arr)
+        return m, keep
+
+    def _next_seed(self, seed):
+        if seed is not None:
+            return int(seed)
+        s = (self.seed + 0x9E3779B97F4A7C15 * self._draw) & 0xFFFFFFFFFFFFFFFF
+        self._draw += 1
+        return s
+
+    def _zs(self, zs, S, N):
+        if zs is None:
+            return None, None
+        ts = [None if z is None else _lib.as_device(z, self.device).reshape(S, N, l.num_outputs)
+              for z, l in zip(zs, self.layers)]
+        return ts, _lib.ptr_array(ts)
+
+    # ------------------------------------------------------------------ a7: propagate
+    def propagate(self, X, full_cov=False, S=1, zs=None, seed=None, n_offset=0):
+        """dgp.py:34-63 -> (Fs, Fmeans, Fvars), lists of [S,N,D_l] tensors."""
+        if full_cov:
+            raise NotImplementedError("full_cov=True is out of scope of the accelerated path (SURVEY §8 f4)")
+        X = _lib.as_device(X, self.device)
+        N = X.shape[0]
+        mk = lambda: [torch.empty((S, N, l.num_outputs), dtype=torch.float64, device=X.device) for l in self.layers]
+        Fs, Fmeans, Fvars = mk(), mk(), mk()
+        if N == 0 or S == 0:
+            return Fs, Fmeans, Fvars
+        m, keep = self._model_desc()
+        zt, zp = self._zs(zs, S, N)
+        _lib.get_context(X.device).call("dgp_propagate", C.byref(m), _lib.ptr(X), N, S, zp, self._next_seed(seed), int(n_offset),
+                                        _lib.ptr_array(Fs), _lib.ptr_array(Fmeans), _lib.ptr_array(Fvars))
+        return Fs, Fmeans, Fvars
+
+    def predict_f(self, X, full_cov=False, S=1, zs=None, seed=None):
+        """dgp.py:66-77: last layer's mean and variance [S,N,D_L]."""
+        if full_cov:
+            raise NotImplementedError("full_cov=True is out of scope of the accelerated path (SURVEY §8 f4)")
+        X = _lib.as_device(X, self.device)
+        N, L = X.shape[0], len(self.layers)
+        D = self.layers[-1].num_outputs
+        Fmean = torch.empty((S, N, D), dtype=torch.float64, device=X.device)
+        Fvar = torch.empty_like(Fmean)
+        if N == 0 or S == 0:
+            return Fmean, Fvar
+        m, keep = self._model_desc()
+        zt, zp = self._zs(zs, S, N)
+        _lib.get_context(X.device).call("dgp_propagate", C.byref(m), _lib.ptr(X), N, S, zp, self._next_seed(seed), 0, None,
+                                        _lib.ptr_array([None] * (L - 1) + [Fmean]), _lib.ptr_array([None] * (L - 1) + [Fvar]))
+        return Fmean, Fvar
+
+    # ------------------------------------------------------------------ a8-a10: ELBO and its gradient
+    def E_log_p_Y(self, X, Y, zs=None, seed=None):
+        """dgp.py:79-87 -> [N, D]."""
+        Fmean, Fvar = self.predict_f(X, S=self.num_samples, zs=zs, seed=seed)
+        Y = _lib.as_device(Y, self.device)
+        return self.likelihood.variational_expectations(Fmean, Fvar, Y).mean(0)
+
+    def grad_layout(self):
+        m, keep = self._model_desc()
+        offs = (_lib.GradOffsets * len(self.layers))()
+        _lib.lib.dgp_grad_layout(C.byref(m), offs)
+        return int(_lib.lib.dgp_grad_size(C.byref(m))), offs
+
+    def elbo_flat(self, data, want_grad=True, scale=1.0, kl_weight=1.0, zs=None, seed=None, n_offset=0, out=None):
+        """One dgp_elbo_grad call. Returns the flat device buffer
+        [data term, kl_weight*sum KL, d/d lik_var, per layer dZ, dlengthscales, dvariance, dq_mu, dq_sqrt] (constrained space)."""
+        X, Y = data
+        X = _lib.as_device(X, self.device)
+        Y = _lib.as_device(Y, self.device)
+        N, S = X.shape[0], self.num_samples
+        m, keep = self._model_desc()
+        n = int(_lib.lib.dgp_grad_size(C.byref(m))) if want_grad else 3
+        if out is None:
+            out = torch.empty(n, dtype=torch.float64, device=X.device)
+        zt, zp = self._zs(zs, S, N)
+        _lib.get_context(X.device).call("dgp_elbo_grad", C.byref(m), _lib.ptr(X), _lib.ptr(Y), N, S, float(scale), float(kl_weight),
+                                        zp, self._next_seed(seed), int(n_offset), 1 if want_grad else 0, _lib.ptr(out))
+        return out
+
+    def elbo_flat_host(self, X_host: np.ndarray, Y_host: np.ndarray, want_grad=True, scale=1.0, kl_weight=1.0, seed=None,
+                       n_offset=0, out_host=None):
+        """dgp_elbo_grad_host: HOST numpy in, HOST numpy out; the host<->device copies are part of the call."""
+        X_host = np.ascontiguousarray(X_host, dtype=np.float64)
+        Y_host = np.ascontiguousarray(Y_host, dtype=np.float64)
+        m, keep = self._model_desc()
+        n = int(_lib.lib.dgp_grad_size(C.byref(m))) if want_grad else 3
+        if out_host is None:
+            out_host = np.empty(n, dtype=np.float64)
+        _lib.get_context(self.device).call("dgp_elbo_grad_host", C.byref(m), X_host.ctypes.data_as(C.c_void_p),
+                                           Y_host.ctypes.data_as(C.c_void_p), X_host.shape[0], self.num_samples, float(scale),
+                                           float(kl_weight), self._next_seed(seed), int(n_offset), 1 if want_grad else 0,
+                                           out_host.ctypes.data_as(C.c_void_p))
+        return out_host
+
+    def ELBO(self, data, zs=None, seed=None):
+        """dgp.py:89-100 -> 0-d tensor. The reference's minibatch scale is identically 1 (dgp.py:95-99)."""
+        flat = self.elbo_flat(data, want_grad=False, zs=zs, seed=seed)
+        return flat[0] - flat[1]
+
+    def ELBO_closure(self, data, zs=None, seed=None):
+        """dgp.py:102-109 (the reference wraps ELBO in tf.function; here it is already one C-ABI call)."""
+        return self.ELBO(data, zs=zs, seed=seed)
+
+    def unpack_grads(self, flat):
+        """flat buffer -> {Parameter: constrained-space gradient tensor} (views into `flat`)."""
+        _, offs = self.grad_layout()
+        out = {}
+        for l, o in zip(self.layers, offs):
+            M, D_in = l.feature.Z.shape
+            D_out = l.num_outputs
+            out[l.feature.Z] = flat[o.dZ:o.dZ + M * D_in].reshape(M, D_in)
+            gl = flat[o.dlengthscales:o.dlengthscales + D_in]
+            out[l.kern.lengthscales] = gl if l.kern.lengthscales.value.numel() == D_in and l.kern.lengthscales.value.dim() > 0 \
+                else gl.sum().reshape(l.kern.lengthscales.value.shape)
+            out[l.kern.variance] = flat[o.dvariance:o.dvariance + 1].reshape(())
+            out[l.q_mu] = flat[o.dq_mu:o.dq_mu + M * D_out].reshape(M, D_out)
+            out[l.q_sqrt] = flat[o.dq_sqrt:o.dq_sqrt + D_out * M * M].reshape(D_out, M, M)
+        out[self.likelihood.likelihood.variance] = flat[2].reshape(())
+        return out
+
+    def ELBO_and_grads(self, data, zs=None, seed=None, scale=1.0):
+        """ELBO and constrained-space gradients as a dict keyed like the oracle (`layers.i.Z`, ..., `lik_var`)."""
+        flat = self.elbo_flat(data, want_grad=True, zs=zs, seed=seed, scale=scale)
+        g = self.unpack_grads(flat)
+        named = {}
+        for i, l in enumerate(self.layers):
+            named[f"layers.{i}.Z"] = g[l.feature.Z]
+            named[f"layers.{i}.lengthscales"] = g[l.kern.lengthscales]
+            named[f"layers.{i}.variance"] = g[l.kern.variance]
+            named[f"layers.{i}.q_mu"] = g[l.q_mu]
+            named[f"layers.{i}.q_sqrt"] = g[l.q_sqrt]
+        named["lik_var"] = g[self.likelihood.likelihood.variance]
+        return flat[0] - flat[1], named
+
+    # ------------------------------------------------------------------ a11: prediction
+    def predict_y(self, Xnew, num_samples, zs=None, seed=None):
+        """dgp.py:113-124: (mu, var + sigma_n^2), both [S,N,D_L]."""
+        Fmean, Fvar = self.predict_f(Xnew, S=num_samples, zs=zs, seed=seed)
+        return self.likelihood.predict_mean_and_var(Fmean, Fvar)
+
+    def predict_density(self, Xnew, Ynew, num_samples):
+        raise NotImplementedError("broken in the reference (tf.log, dgp.py:129); not on the accelerated path")
+
+    def predict_moments(self, Xnew, num_samples, add_lik_var=True, zs=None, seed=None):
+        """Mixture moments over the S samples reduced on the device (dgp.py:362-366; Infill_criteria.py:39-41)."""
+        X = _lib.as_device(Xnew, self.device)
+        N, D = X.shape[0], self.layers[-1].num_outputs
+        mean = torch.empty((N, D), dtype=torch.float64, device=X.device)
+        var = torch.empty_like(mean)
+        if N == 0:
+            return mean, var
+        m, keep = self._model_desc()
+        zt, zp = self._zs(zs, num_samples, N)
+        _lib.get_context(X.device).call("dgp_predict_moments", C.byref(m), _lib.ptr(X), N, num_samples, zp, self._next_seed(seed), 0,
+                                        1 if add_lik_var else 0, _lib.ptr(mean), _lib.ptr(var))
+        return mean, var
+
+    # ------------------------------------------------------------------ optimisers (callers of the hot path)
+    def _adam_state(self, params):
+        return {p: (torch.zeros_like(p.value), torch.zeros_like(p.value)) for p in params}
+
+    def _adam_step(self, params, grads, state, t, lr, beta_1, beta_2, epsilon):
+        """Keras/TF Adam on the unconstrained variables; `grads` are constrained-space d ELBO (we minimise -ELBO)."""
+        lr_t = lr * np.sqrt(1.0 - beta_2 ** t) / (1.0 - beta_1 ** t)
+        for p in params:
+            g = -p.grad_to_unconstrained(grads[p])
+            m, v = state[p]
+            m.mul_(beta_1).add_(g, alpha=1.0 - beta_1)
+            v.mul_(beta_2).addcmul_(g, g, value=1.0 - beta_2)
+            u = p.unconstrained()
+            u.sub_(lr_t * m / (v.sqrt() + epsilon))
+            p.set_unconstrained(u)
+
+    def optimize_adam(self, data, iterations=5000, lr=0.01, beta_1=0.9, beta_2=0.999, epsilon=1e-07, messages=100):
+        """dgp.py:132-154."""
+        params = self.trainable_parameters
+        state = self._adam_state(params)
+        for step in range(iterations):
+            flat = self.elbo_flat(data, want_grad=True)
+            self._adam_step(params, self.unpack_grads(flat), state, step + 1, lr, beta_1, beta_2, epsilon)
+            if step % messages == 0:
+                print(f"ELBO: {(flat[0] - flat[1]).item()}")
+
+    def number_parameters(self, trainable=True):
+        """dgp.py:348-360."""
+        ps = self.trainable_parameters if trainable else self.parameters
+        return int(sum(int(np.prod(p.shape)) if len(p.shape) else 1 for p in ps))
+
+
+class DGP(DGP_Base):
+    """dgp_dace/models/dgp.py:221-366: doubly-stochastic DGP with linear/identity mean functions."""
+
+    def __init__(self, X, Y, Z, kernels, num_units, likelihood, num_outputs=None, mean_function=None, white=False, **kwargs):
+        layers = init_layers_linear(X, Y, Z, kernels, num_units, num_outputs=num_outputs,
+                                    mean_function=mean_function, white=white)
+        DGP_Base.__init__(self, likelihood, layers, **kwargs)
+        self.data = (_lib.as_device(X, self.device), _lib.as_device(Y, self.device))
+
+    def optimize_adam(self, iterations=5000, lr=0.01, beta_1=0.9, beta_2=0.999, epsilon=1e-07, messages=100):
+        """dgp.py:255-279: hidden layers' q_sqrt *= 1e-3 first (:268-269), then Adam."""
+        for layer in self.layers[:-1]:
+            layer.q_sqrt.assign(layer.q_sqrt.value * 1e-3)
+        DGP_Base.optimize_adam(self, self.data, iterations, lr, beta_1, beta_2, epsilon, messages)
+
+    def predict(self, Xnew, num_samples, zs=None, seed=None):
+        """dgp.py:362-366 (mixture moments of predict_y), reduced on the device."""
+        return self.predict_moments(Xnew, num_samples, add_lik_var=True, zs=zs, seed=seed)

@@ -1,0 +1,123 @@
+/* dgp_b200.h — C ABI of the B200-native doubly-stochastic DGP hot path.
+ *
+ * The reference (Hebbalali/dgp-toolbox) has no FFI layer: its boundary is the Python class API
+ * (dgp_dace/utils/layers.py, dgp_dace/models/dgp.py, dgp_dace/Infill_criteria.py, dgp_dace/EHVI.py).  Each entry point
+ * below names the reference method whose arithmetic it replaces; dgp_toolbox_b200/*.py binds them with ctypes and
+ * keeps the reference's class/method names.
+ *
+ * Conventions: every pointer is a DEVICE pointer on the ctx's device unless the name ends in _host; all arrays are
+ * C-contiguous float64; calls are asynchronous on the ctx's stream; the caller pre-allocates every output; return
+ * value 0 = success, negative = error (message via dgp_last_error).  One ctx per GPU per host thread.
+ */
+#ifndef DGP_B200_H
+#define DGP_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dgp_ctx dgp_ctx;
+
+/* One SVGP layer = the state of reference SVGP_Layer (dgp_dace/utils/layers.py:181-224). */
+typedef struct {
+  int32_t D_in, D_out, M;
+  int32_t white;              /* reference `white` flag; only 0 (the reference default, dgp.py:248) is implemented */
+  int32_t mean_kind;          /* 0 Zero, 1 Identity, 2 Linear (utils/layer_initializations.py:27,42,52) */
+  int32_t kernel_kind;        /* 0 SquaredExponential / RBF (ARD) */
+  const double* Z;            /* [M, D_in]   feature.Z */
+  const double* lengthscales; /* [D_in]      kern.lengthscales (host side broadcasts an isotropic value) */
+  const double* variance;     /* [1]         kern.variance */
+  const double* q_mu;         /* [M, D_out] */
+  const double* q_sqrt;       /* [D_out, M, M] lower triangular, dense storage */
+  const double* mf_W;         /* [D_in, D_out] Linear.A or NULL */
+  const double* mf_b;         /* [D_out] Linear.b or NULL */
+  double jitter;              /* gpflow.default_jitter() = 1e-6 */
+} dgp_layer_desc;
+
+typedef struct {
+  int32_t num_layers;
+  const dgp_layer_desc* layers; /* HOST array of descriptors */
+  const double* lik_variance;   /* [1] Gaussian likelihood variance */
+} dgp_model_desc;
+
+/* offsets (in doubles) into the flat ELBO/gradient buffer of dgp_elbo_grad */
+typedef struct { int64_t dZ, dlengthscales, dvariance, dq_mu, dq_sqrt; } dgp_layer_grad_offsets;
+
+int dgp_ctx_create(int device, void* cuda_stream, dgp_ctx** out);
+void dgp_ctx_destroy(dgp_ctx* ctx);
+const char* dgp_last_error(dgp_ctx* ctx);
+int dgp_version(void);
+int dgp_set_stream(dgp_ctx* ctx, void* cuda_stream);
+/* bytes of device workspace currently held by the ctx; the minibatch is processed in chunks of points sized so that the
+ * workspace stays under the limit (default 24 GiB, env DGP_B200_WS_GB) */
+int64_t dgp_workspace_bytes(dgp_ctx* ctx);
+int dgp_set_workspace_limit(dgp_ctx* ctx, int64_t bytes);
+/* number of kernels this ctx has launched (reset != 0 zeroes the counter afterwards) */
+int64_t dgp_launch_count(dgp_ctx* ctx, int reset);
+
+/* kern.K(X, X2) of the GPflow SquaredExponential the reference layers hold (utils/layers.py:221,230,243):
+ * K_out [n1, n2] = variance * exp(-0.5 * sum_j ((X[i,j] - X2[k,j]) / lengthscales[j])^2). */
+int dgp_kernel_K(dgp_ctx* ctx, int D, const double* lengthscales, const double* variance, const double* X, int64_t n1,
+                 const double* X2, int64_t n2, double* K_out);
+
+/* z[s,n,d] for one layer: the Philox-4x32-10 stream the fused path consumes when zs == NULL
+ * (replaces tf.random.normal at utils/layers.py:113; counter = (n + n_offset, s, d, layer)). */
+int dgp_philox_normal(dgp_ctx* ctx, uint64_t seed, int layer, int64_t S, int64_t N, int D, int64_t n_offset, double* z_out);
+
+/* SVGP_Layer.build_cholesky_if_needed (utils/layers.py:227-234): Ku [M,M] = Kuu + jitter I, Lu [M,M] = chol(Ku). */
+int dgp_kuu_chol(dgp_ctx* ctx, const dgp_layer_desc* layer, double* Ku_out, double* Lu_out);
+
+/* SVGP_Layer.conditional_ND (utils/layers.py:237-278), full_cov=False: X [P, D_in] -> mean, var [P, D_out]. */
+int dgp_conditional_nd(dgp_ctx* ctx, const dgp_layer_desc* layer, const double* X, int64_t P, double* mean, double* var);
+
+/* SVGP_Layer.KL (utils/layers.py:280-308) -> kl_out[1]. */
+int dgp_kl(dgp_ctx* ctx, const dgp_layer_desc* layer, double* kl_out);
+
+/* DGP_Base.propagate (models/dgp.py:34-63): X [N, D0] tiled S times, chained through the layers.
+ * zs_host: HOST array of num_layers device pointers [S,N,D_out_l] (entries or the array itself may be NULL -> Philox).
+ * Fs/Fmeans/Fvars_host: HOST arrays of num_layers device pointers [S,N,D_out_l]; entries (or arrays) may be NULL. */
+int dgp_propagate(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, int64_t N, int64_t S,
+                  const double* const* zs_host, uint64_t seed, int64_t n_offset,
+                  double* const* Fs_host, double* const* Fmeans_host, double* const* Fvars_host);
+
+/* size (doubles) and layout of the flat buffer: [0] data term = scale * sum_n mean_s ve, [1] kl_weight * sum_l KL_l,
+ * [2] d/d lik_variance, then per layer dZ, dlengthscales, dvariance, dq_mu, dq_sqrt (constrained space). ELBO = [0] - [1]. */
+int64_t dgp_grad_size(const dgp_model_desc* model);
+int dgp_grad_layout(const dgp_model_desc* model, dgp_layer_grad_offsets* offsets_host /* [num_layers] */);
+
+/* DGP_Base.ELBO (models/dgp.py:89-100) and, when want_grad != 0, its gradient w.r.t. every parameter
+ * (replaces tape.gradient at models/dgp.py:275). scale multiplies the data term (the reference's is 1);
+ * kl_weight multiplies KL and its gradients (1/world_size on sharded runs so that a sum-allreduce restores them). */
+int dgp_elbo_grad(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, const double* Y, int64_t N, int64_t S,
+                  double scale, double kl_weight, const double* const* zs_host, uint64_t seed, int64_t n_offset,
+                  int want_grad, double* out_flat);
+
+/* Same as dgp_elbo_grad with HOST X [N,D0], Y [N,Dy] and HOST result buffer: host<->device copies are part of the call. */
+int dgp_elbo_grad_host(dgp_ctx* ctx, const dgp_model_desc* model, const double* X_host, const double* Y_host, int64_t N,
+                       int64_t S, double scale, double kl_weight, uint64_t seed, int64_t n_offset, int want_grad,
+                       double* out_flat_host);
+
+/* DGP_Base.predict_f / predict_y + DGP.predict mixture moments (models/dgp.py:66-77,113-124,362-366; also
+ * Infill_criteria.py:39-41, EHVI.py:112-119): mean [N, D_L], var [N, D_L]; add_lik_var != 0 adds sigma_n^2 (predict_y). */
+int dgp_predict_moments(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, int64_t N, int64_t S,
+                        const double* const* zs_host, uint64_t seed, int64_t n_offset, int add_lik_var,
+                        double* mean, double* var);
+
+/* EI.run for a DGP (Infill_criteria.py:36-52): returns -EI [N,1]. analytic != 0: moment-matched closed form;
+ * analytic == 0: Monte-Carlo mean_s max(y_min - F, 0) on the propagated samples. */
+int dgp_ei(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, int64_t N, int64_t S,
+           const double* const* zs_host, uint64_t seed, int64_t n_offset, double y_min, int analytic, double* neg_ei);
+
+/* EHVI exact 2-objective strip sum (EHVI.py:102-104,154-157) from per-objective moments [N]; ynd0/ynd1: padded
+ * Pareto front (EHVI.py:90-100), n entries each, DEVICE pointers. */
+int dgp_ehvi2d(dgp_ctx* ctx, const double* m0, const double* v0, const double* m1, const double* v1, int64_t N,
+               const double* ynd0, const double* ynd1, int n, double* out);
+
+/* Debug / test hook for the DMMA GEMM engine: C = alpha * A * op(B) + beta * C (row-major, tile-aligned shapes). */
+int dgp_debug_gemm(dgp_ctx* ctx, int nt, int M, int N, int K, double alpha, const double* A, const double* B, double beta,
+                   double* C, int a_tri, int c_lower, int batch, int splitk, const double* kscale);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -505,9 +505,10 @@ def philox_normal(seed: int, layer: int, S: int, N: int, D: int, n_offset: int =
 # --------------------------------------------------------------------------------------
 # synthetic benchmark inputs shared by tests and bench.py's cpu_baseline leg
 # --------------------------------------------------------------------------------------
-def synthetic_problem(D0, num_units, M, N, seed_shift=0, lik_var=0.1):
+def synthetic_problem(D0, num_units, M, N, seed_shift=0, lik_var=0.1, ls_scale=1.0):
     """X ~ N(0,I), Y = sin(sum x / sqrt(D0)) + 0.1 eps, Z_l ~ N(0,I), l = sqrt(D_in), sigma^2 = 1,
-    q_mu = 0.1 N(0,1), q_sqrt = 0.5 I + 0.05 tril(N(0,1)). Returns numpy dict."""
+    q_mu = 0.1 N(0,1), q_sqrt = 0.5 I + 0.05 tril(N(0,1)). ls_scale shrinks the lengthscales for low-dimensional
+    problems, where l = sqrt(D_in) would make cond(Ku) jitter-limited (~1e7) and 1e-9 parity meaningless. Returns numpy dict."""
     rng = np.random.default_rng(0 + seed_shift)
     X = rng.standard_normal((N, D0))
     Y = np.sin(X.sum(1, keepdims=True) / math.sqrt(D0)) + 0.1 * np.random.default_rng(1 + seed_shift).standard_normal((N, 1))
@@ -528,7 +529,7 @@ def synthetic_problem(D0, num_units, M, N, seed_shift=0, lik_var=0.1):
             kind, W = "linear", V[:dout, :].T
         else:
             kind, W = "linear", np.concatenate([np.eye(din), np.zeros((din, dout - din))], 1)
-        layers.append(dict(Z=Z, lengthscales=np.full(din, math.sqrt(din)), variance=1.0, q_mu=q_mu, q_sqrt=q_sqrt,
+        layers.append(dict(Z=Z, lengthscales=np.full(din, ls_scale * math.sqrt(din)), variance=1.0, q_mu=q_mu, q_sqrt=q_sqrt,
                            mean_kind=kind, mf_W=W, mf_b=None if W is None else np.zeros(dout)))
     return dict(X=X, Y=Y, layers=layers, lik_var=lik_var)
 

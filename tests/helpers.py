@@ -1,0 +1,46 @@
+"""Shared builders: the same synthetic problem (oracle.dgp_oracle.synthetic_problem) as an oracle model and
+as a dgp_toolbox_b200 DGP_Base with identical parameters."""
+import numpy as np
+import torch
+
+from oracle import dgp_oracle as O
+
+
+def product_model_from_problem(prob, num_samples, seed=1234, device=None):
+    import dgp_toolbox_b200 as D
+    layers = []
+    for l in prob["layers"]:
+        kern = D.SquaredExponential(variance=l["variance"], lengthscales=l["lengthscales"])
+        if l["mean_kind"] == "zero":
+            mf = D.Zero()
+        elif l["mean_kind"] == "identity":
+            mf = D.Identity()
+        else:
+            mf = D.Linear(l["mf_W"], l["mf_b"])
+        layer = D.SVGP_Layer(kern, l["Z"], l["q_mu"].shape[1], mf)
+        layer.q_mu.assign(l["q_mu"])
+        layer.q_sqrt.assign(l["q_sqrt"])
+        layers.append(layer)
+    return D.DGP_Base(D.Gaussian(prob["lik_var"]), layers, num_samples=num_samples, seed=seed)
+
+
+def both_models(D0, num_units, M, N, S, seed_shift=0, lik_var=0.1, ls_scale=None):
+    if ls_scale is None:   # keep cond(Ku) <~ 1e5 so that 1e-9 relative parity is above the conditioning noise floor
+        ls_scale = {1: 0.05, 2: 0.15}.get(D0, 1.0) if min([D0] + list(num_units)) <= 2 else 1.0
+    prob = O.synthetic_problem(D0, num_units, M, N, seed_shift=seed_shift, lik_var=lik_var, ls_scale=ls_scale)
+    om = O.model_from_problem(prob, S)
+    pm = product_model_from_problem(prob, S)
+    return prob, om, pm
+
+
+def rel_err(a, b, scale=None):
+    """max |a - b| / max(|b|_inf, scale) — relative to the un-cancelled scale of the quantity (SURVEY §7 hard parts)."""
+    a = a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a)
+    b = b.detach().cpu().numpy() if hasattr(b, "detach") else np.asarray(b)
+    den = max(float(np.max(np.abs(b))) if b.size else 0.0, scale or 0.0, 1e-300)
+    return float(np.max(np.abs(a - b))) / den if b.size else 0.0
+
+
+def oracle_zs(model, N, S, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(S, N, l.D_out, dtype=torch.float64, generator=g) for l in model.layers]

@@ -1,0 +1,197 @@
+"""GPU parity: the CUDA path (through the C ABI, via the drop-in classes) against the CPU oracle on identical seeded
+inputs. Tolerance: 1e-9 relative (float64, north_star), relative to the un-cancelled scale of each quantity."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dgp_oracle as O
+from tests.helpers import both_models, oracle_zs, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+SHAPES = [
+    # D0, num_units, M, N, S
+    (2, [2], 50, 100, 10),          # config-1 shape (nb_DGP_regression-like: D=2, M=50, S=10)
+    (8, [8, 8], 64, 48, 4),         # config-2 structure, small
+    (8, [8, 8, 8], 256, 64, 8),     # config-2: 3 hidden layers (4 SVGP layers), M=256
+    (5, [3, 6], 40, 37, 3),         # ragged: PCA-narrowing and zero-padding Linear mean functions, odd sizes
+    (1, [1, 1], 25, 50, 10),        # KAT-1 shape
+]
+
+
+@pytest.mark.parametrize("D0,num_units,M,N,S", SHAPES)
+def test_propagate_matches_oracle(D0, num_units, M, N, S):
+    prob, om, pm = both_models(D0, num_units, M, N, S)
+    zs = oracle_zs(om, N, S, 7)
+    X = torch.as_tensor(prob["X"])
+    Fs_o, Fm_o, Fv_o = O.propagate(om.layers, X, S, zs)
+    Fs, Fm, Fv = pm.propagate(prob["X"], S=S, zs=zs)
+    for l in range(len(om.layers)):
+        s2 = float(om.layers[l].variance)
+        assert rel_err(Fm[l], Fm_o[l]) < TOL, ("mean", l)
+        assert rel_err(Fv[l], Fv_o[l], scale=s2) < TOL, ("var", l)
+        assert rel_err(Fs[l], Fs_o[l]) < TOL, ("sample", l)
+
+
+@pytest.mark.parametrize("D0,num_units,M,N,S", SHAPES)
+def test_elbo_and_gradients_match_oracle(D0, num_units, M, N, S):
+    prob, om, pm = both_models(D0, num_units, M, N, S)
+    zs = oracle_zs(om, N, S, 11)
+    X, Y = torch.as_tensor(prob["X"]), torch.as_tensor(prob["Y"])
+    val_o, g_o = O.elbo_and_grads(om, X, Y, zs)
+    val, g = pm.ELBO_and_grads((prob["X"], prob["Y"]), zs=zs)
+    assert abs(float(val) - float(val_o)) <= TOL * abs(float(val_o))
+    for k, go in g_o.items():
+        gg = g[k]
+        assert tuple(gg.shape) == tuple(go.shape) or gg.numel() == go.numel(), k
+        assert rel_err(gg.reshape(go.shape), go) < TOL, k
+
+
+def test_elbo_value_only_and_scale():
+    prob, om, pm = both_models(3, [3], 30, 40, 5)
+    zs = oracle_zs(om, 40, 5, 3)
+    X, Y = torch.as_tensor(prob["X"]), torch.as_tensor(prob["Y"])
+    v_o = float(O.elbo(om, X, Y, zs))
+    assert abs(float(pm.ELBO((prob["X"], prob["Y"]), zs=zs)) - v_o) <= TOL * abs(v_o)
+    v_o3 = float(O.elbo(om, X, Y, zs, scale=3.0))
+    flat = pm.elbo_flat((prob["X"], prob["Y"]), want_grad=False, scale=3.0, zs=zs)
+    assert abs(float(flat[0] - flat[1]) - v_o3) <= TOL * abs(v_o3)
+
+
+def test_layer_methods_match_oracle():
+    prob, om, pm = both_models(4, [4], 33, 20, 2)
+    X = torch.as_tensor(prob["X"])
+    for lo, lp in zip(om.layers[:1], pm.layers[:1]):
+        m_o, v_o = O.conditional_ND(lo, X)
+        m, v = lp.conditional_ND(prob["X"])
+        assert rel_err(m, m_o) < TOL and rel_err(v, v_o, scale=float(lo.variance)) < TOL
+        assert abs(float(lp.KL()) - float(O.layer_KL(lo))) <= TOL * abs(float(O.layer_KL(lo)))
+        Ku_o, Lu_o = O.kuu_chol(lo)
+        lp.build_cholesky_if_needed()
+        assert rel_err(lp.Ku, Ku_o) < TOL and rel_err(lp.Lu, Lu_o) < TOL
+        K_o = O.rbf_K(lo.Z, X, lo.lengthscales, lo.variance)
+        assert rel_err(lp.kern.K(lp.feature.Z.value, prob["X"]), K_o) < TOL
+        X3 = torch.randn(3, 7, 4, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+        z = torch.randn(3, 7, 4, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+        s_o, m_o, v_o = O.sample_from_conditional(lo, X3, z)
+        s, m, v = lp.sample_from_conditional(X3, z=z)
+        assert rel_err(s, s_o) < TOL and rel_err(m, m_o) < TOL and rel_err(v, v_o, scale=float(lo.variance)) < TOL
+        m2, v2 = lp.conditional_SND(X3)
+        assert rel_err(m2, m_o) < TOL
+
+
+def test_kat1_notebook_elbo_through_cuda():
+    """SURVEY §8c KAT-1 / KAT-1b / KAT-3 through the drop-in DGP class (constructor path included)."""
+    import dgp_toolbox_b200 as D
+    np.random.seed(0)
+    X = np.random.uniform(0, 1, 50)[:, None]
+    Z = np.random.uniform(0, 1, 25)[:, None]
+    Y = (X >= 0.5).astype(np.float64) + 1e-2 * np.random.randn(50, 1)
+    kernels = [D.RBF(lengthscales=[1.0], variance=1.0) for _ in range(3)]
+    model = D.DGP(X, Y, Z, kernels, [1, 1], D.Gaussian(), num_samples=10)
+    assert model.number_parameters(trainable=False) == 2032
+    val = float(model.ELBO((X, Y)))
+    assert abs(val - (-85.98812279560475)) <= 1e-9 * 85.98812279560475, val
+    for layer in model.layers[:-1]:
+        layer.q_sqrt.assign(layer.q_sqrt.value * 1e-3)
+    val = float(model.ELBO((X, Y)))
+    assert abs(val - (-406.37591174470)) <= 1e-9 * 406.37591174470, val
+
+
+def test_philox_stream_is_bit_exact_and_drives_the_chain():
+    import dgp_toolbox_b200 as D
+    prob, om, pm = both_models(3, [2], 20, 33, 6)
+    S, N = 6, 33
+    ctx = D._lib.get_context(0)
+    zs = []
+    for l, layer in enumerate(pm.layers):
+        z = torch.empty((S, N, layer.num_outputs), dtype=torch.float64, device="cuda")
+        ctx.call("dgp_philox_normal", 1234, l, S, N, layer.num_outputs, 5, D._lib.ptr(z))
+        z_o = O.philox_normal(1234, l, S, N, layer.num_outputs, n_offset=5)
+        # integer plumbing is bit exact; log/cos differ by <= a few ulp between libm and CUDA
+        assert np.max(np.abs(z.cpu().numpy() - z_o)) < 1e-13
+        zs.append(torch.as_tensor(z_o))
+    X = torch.as_tensor(prob["X"])
+    Fs_o, Fm_o, _ = O.propagate(om.layers, X, S, zs)
+    Fs, Fm, _ = pm.propagate(prob["X"], S=S, zs=None, seed=1234, n_offset=5)   # in-kernel draws
+    assert rel_err(Fs[-1], Fs_o[-1]) < TOL and rel_err(Fm[-1], Fm_o[-1]) < TOL
+
+
+def test_predict_ei_ehvi_match_oracle():
+    import dgp_toolbox_b200 as D
+    prob, om, pm = both_models(4, [4], 48, 60, 8)
+    S, N = 8, 60
+    zs = oracle_zs(om, N, S, 5)
+    X = torch.as_tensor(prob["X"])
+    m_o, v_o = O.predict(om, X, S, zs)
+    m, v = pm.predict_moments(prob["X"], S, add_lik_var=True, zs=zs)
+    assert rel_err(m, m_o) < TOL and rel_err(v, v_o) < TOL
+    ym, yv = pm.predict_y(prob["X"], S, zs=zs)
+    ym_o, yv_o = O.predict_y(om, X, S, zs)
+    assert rel_err(ym, ym_o) < TOL and rel_err(yv, yv_o) < TOL
+    # EI analytic + MC
+    Fs_o, Fm_o, Fv_o = O.propagate(om.layers, X, S, zs)
+    y_min = float(prob["Y"].min())
+    ei = D.EI(y_min, 4)
+    assert rel_err(ei.run(pm, prob["X"], analytic=True, num_samples=S, zs=zs), O.ei_analytic(Fm_o[-1], Fv_o[-1], y_min)) < 1e-8
+    assert rel_err(ei.run(pm, prob["X"], analytic=False, num_samples=S, zs=zs), O.ei_mc(Fs_o[-1], y_min)) < TOL
+    # EHVI with two DGPs
+    prob2, om2, pm2 = both_models(4, [4], 48, 60, 8, seed_shift=100)
+    zs2 = oracle_zs(om2, N, S, 6)
+    m0, v0 = O.mixture_moments(*O.predict_f(om, X, S, zs))
+    m1, v1 = O.mixture_moments(*O.predict_f(om2, X, S, zs2))
+    y0 = np.linspace(0.95, 0.05, 12)
+    y1 = 1.0 - np.sqrt(y0)
+    a, b = O.Y_ND(y0, y1, nadir=(1.1, 1.1), ideal=(-0.1, -0.1))
+    e_o = O.ehvi_exact(m0, v0, m1, v1, a, b)
+    e = D.EHVI([pm, pm2], prob["X"], [a, b], S=S, zs=[zs, zs2])
+    assert rel_err(e, e_o) < 1e-8
+
+
+def test_chunked_minibatch_equals_single_pass():
+    """The workspace limit splits the minibatch into chunks of points; results must not depend on the split."""
+    import dgp_toolbox_b200 as D
+    prob, om, pm = both_models(4, [4], 64, 700, 4)
+    ctx = D._lib.get_context(0)
+    ref = pm.elbo_flat((prob["X"], prob["Y"]), want_grad=True, seed=99).clone()
+    ctx.set_workspace_limit(64 << 20)
+    try:
+        chunked = pm.elbo_flat((prob["X"], prob["Y"]), want_grad=True, seed=99).clone()
+    finally:
+        ctx.set_workspace_limit(24 << 30)
+    assert rel_err(chunked, ref) < 1e-11
+
+
+def test_host_entry_point_matches_device_entry_point():
+    prob, om, pm = both_models(3, [3], 32, 50, 4)
+    dev = pm.elbo_flat((prob["X"], prob["Y"]), want_grad=True, seed=5).cpu().numpy()
+    host = pm.elbo_flat_host(prob["X"], prob["Y"], want_grad=True, seed=5)
+    assert np.array_equal(dev, host)
+
+
+def test_gemm_engine_against_torch():
+    import dgp_toolbox_b200 as D
+    ctx = D._lib.get_context(0)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for (nt, M, N, K, tri, clow, batch, splitk) in [(0, 128, 256, 64, 0, 0, 1, 1), (0, 128, 128, 128, 1, 0, 2, 1),
+                                                     (0, 128, 128, 128, 2, 0, 1, 1), (1, 128, 128, 512, 0, 1, 3, 4),
+                                                     (0, 64, 32, 256, 0, 0, 1, 4), (1, 256, 256, 1024, 0, 0, 1, 8)]:
+        A = torch.randn(batch, M, K, dtype=torch.float64, device="cuda", generator=g)
+        if tri == 1:
+            A = torch.tril(A)
+        if tri == 2:
+            A = torch.triu(A)
+        B = torch.randn(batch, N, K, dtype=torch.float64, device="cuda", generator=g) if nt else \
+            torch.randn(batch, K, N, dtype=torch.float64, device="cuda", generator=g)
+        Cm = torch.randn(batch, M, N, dtype=torch.float64, device="cuda", generator=g)
+        ks = torch.randn(batch, K, dtype=torch.float64, device="cuda", generator=g) if nt else None
+        ref = 1.5 * (A * ks[:, None, :] if nt else A) @ (B.transpose(1, 2) if nt else B) + 0.5 * Cm
+        out = Cm.clone()
+        ctx.call("dgp_debug_gemm", nt, M, N, K, 1.5, D._lib.ptr(A), D._lib.ptr(B), 0.5, D._lib.ptr(out), tri, clow, batch, splitk,
+                 D._lib.ptr(ks))
+        if clow:
+            ref, out = torch.tril(ref), torch.tril(out)
+        assert rel_err(out, ref) < 1e-12, (nt, M, N, K, tri, clow, batch, splitk)
