@@ -1,0 +1,263 @@
+#!/usr/bin/env python
+"""Benchmark of the DGP hot path: ELBO + gradient point-samples/s on BASELINE.json's config 2
+(3-layer DGP = 4 SVGP layers, ARD-RBF, D=8, M=256 inducing points, S=32 Monte-Carlo samples, float64).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the reference's CPU algorithm on host cores
+
+One step = one ELBO+gradient evaluation over one minibatch of N_b points per GPU (weak scaling: every rank owns N_b
+points x S samples) followed, for N > 1, by ONE NCCL sum-allreduce of the flat [ELBO terms, gradients] buffer.
+`value` times device-resident inputs; `e2e` times the host-buffer entry point (H2D of the minibatch, D2H of the result).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "DGP ELBO+grad point-samples/s"
+UNIT = "point-samples/s"
+FP64_PEAK_FALLBACK_TFLOPS = 37.07   # profiles/r01_fp64_peaks.json (DMMA.8x8x4 register-resident loop, this pool's B200)
+
+
+def fp64_peak():
+    """MEASURED_PEAKS.json has no FP64 figure (bf16 + HBM only), so the denominator is this repo's own calibration
+    (tools/fp64_peaks.cu run on this pool's B200, committed as profiles/r01_fp64_peaks.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")) as f:
+            return float(json.load(f)["summary"]["fp64_dmma_tflops"]), "profiles/r01_fp64_peaks.json (own DMMA calibration; MEASURED_PEAKS.json has no FP64 entry)"
+    except Exception:
+        return FP64_PEAK_FALLBACK_TFLOPS, "fallback constant (own r01 DMMA calibration)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_throughput(cfg, nb_cpu, steps, warmup):
+    """The reference's CPU algorithm for the path: TensorFlow/GPflow are not installable here (no network, absent from the
+    image), so this is the op-for-op float64 restatement in oracle/ (kind = "port"), run on all host cores."""
+    import torch
+    from oracle import dgp_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    prob = O.synthetic_problem(cfg["D0"], cfg["num_units"], cfg["M"], nb_cpu)
+    om = O.model_from_problem(prob, cfg["S"])
+    g = torch.Generator().manual_seed(0)
+    zs = [torch.randn(cfg["S"], nb_cpu, l.D_out, dtype=torch.float64, generator=g) for l in om.layers]
+    X, Y = torch.as_tensor(prob["X"]), torch.as_tensor(prob["Y"])
+    for _ in range(warmup):
+        O.elbo_and_grads(om, X, Y, zs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.elbo_and_grads(om, X, Y, zs)
+    dt = (time.perf_counter() - t0) / steps
+    return nb_cpu * cfg["S"] / dt, dt, cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2")
+    ap.add_argument("--nb", type=int, default=16384, help="minibatch points per GPU per step")
+    ap.add_argument("--nb-cpu", type=int, default=256, help="points of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    from dgp_toolbox_b200 import synthetic  # numpy-only module; does not need a GPU
+    cfg = synthetic.CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    f_fwd, f_step = synthetic.flops_per_point_sample(cfg["D0"], cfg["num_units"], cfg["M"])
+    workload = (f"{len(cfg['num_units'])}-layer DGP ({len(cfg['num_units']) + 1} SVGP layers), ARD-RBF, D={cfg['D0']}, "
+                f"M={cfg['M']}, S={cfg['S']}, minibatch ELBO+grad, float64")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        val, dt, cores = cpu_reference_throughput(cfg, args.nb_cpu, args.steps, warmup)
+        sample = f"N_b={args.nb_cpu} points x S={cfg['S']} samples per step (reference formulation materialises [D_out,M,S*N] twice)"
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "points_per_step": args.nb_cpu, "samples": cfg["S"]},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "TensorFlow/GPflow absent from the image: oracle/ float64 torch-CPU restatement of the reference op sequence",
+        }))
+        return
+
+    import torch
+    import torch.distributed as dist
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import dgp_toolbox_b200 as D
+    from dgp_toolbox_b200.distributed import ShardedELBO
+
+    ctx = D._lib.get_context(local_rank)
+    ctx.set_workspace_limit(64 << 30)
+    prob = synthetic.synthetic_problem(cfg["D0"], cfg["num_units"], cfg["M"], 8)
+    model = synthetic.model_from_problem(prob, cfg["S"])
+    sharded = ShardedELBO(model)
+    nb, S = args.nb, cfg["S"]
+    n_pool = 4   # distinct minibatches cycled through (fresh X, Y every step)
+    pool_host = []
+    for i in range(n_pool):
+        X, Y = synthetic.minibatch(cfg["D0"], nb, i * world + rank)
+        pool_host.append((torch.from_numpy(X).pin_memory(), torch.from_numpy(Y).pin_memory()))
+    pool_dev = [(x.cuda(), y.cuda()) for x, y in pool_host]
+    scale = 1.0e6 / (nb * world)   # N = 1M points behind the minibatch (BASELINE config 2)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_dev(i):
+        X, Y = pool_dev[i % n_pool]
+        return sharded.step(X, Y, n_offset=(i * world + rank) * nb, scale=scale, seed=1234 + i)
+
+    def step_host(i):
+        X, Y = pool_host[i % n_pool]
+        return sharded.step_host(X, Y, n_offset=(i * world + rank) * nb, scale=scale, seed=1234 + i)
+
+    def timed(fn, k):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            out = fn(i)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    for i in range(warmup):
+        step_dev(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.launch_count(reset=True)
+    ctx.get_profile(reset=True)
+    ctx.set_profiling(True)
+    ms_total, out = timed(step_dev, args.steps)
+    prof = ctx.get_profile(reset=True)
+    ctx.set_profiling(False)
+    launches = ctx.launch_count(reset=True)
+    clocks = sampler.stop() if rank == 0 else None
+    elbo = float((out[0] - out[1]).item())
+
+    for i in range(warmup):
+        step_host(i)
+    ms_e2e, _ = timed(step_host, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ps_per_step = nb * S * world
+    ms_step = ms_total / args.steps
+    value = ps_per_step / (ms_step * 1e-3)
+    e2e_value = ps_per_step / (ms_e2e / args.steps * 1e-3)
+    peak, peak_src = fp64_peak()
+    gemm_ms = sum(prof[k][0] for k in ("gemm_fwd", "gemm_bwd_data", "gemm_bwd_param"))
+    gemm_launches = sum(prof[k][1] for k in ("gemm_fwd", "gemm_bwd_data", "gemm_bwd_param"))
+    all_ms = sum(v[0] for v in prof.values())
+    flops_rank_step = f_step * nb * S
+    achieved = flops_rank_step * args.steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    n_grad, _ = model.grad_layout()
+    roofline = {
+        "bound": "tensor", "kernel": "dgp::gemm_kernel (FP64 DMMA.8x8x4 contractions: Lu^-1 Kuf, Lu^-T V, q_sqrt^T A and their adjoints)",
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        "peak_source": peak_src,
+        "algorithmic_flops_per_point_sample": f_step, "launches_in_region": gemm_launches,
+        "kernel_ms_per_step": gemm_ms / args.steps, "share_of_step": gemm_ms / all_ms if all_ms > 0 else None,
+        "whole_step_frac": flops_rank_step / (ms_step * 1e-3) / 1e12 / peak,
+        "categories_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload, "points_per_gpu_per_step": nb, "samples": S, "point_samples_per_step": ps_per_step,
+                   "parallelism": f"dp{world} (points sharded, parameters replicated, one allreduce of {n_grad} doubles)",
+                   "l2": "per-step working set (stashed A/T tiles, >30 GB) far exceeds the 126 MB L2; a different minibatch every step"},
+        "roofline": roofline,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * nb * (cfg["D0"] + 1) * 8,
+                "d2h_bytes_per_step": n_grad * 8, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "elbo_last_step": elbo,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        val, dt, cores = cpu_reference_throughput(cfg, args.nb_cpu, 3, 1)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"N_b={args.nb_cpu} points x S={S} samples, 3 steps after 1 warm-up ({dt:.2f} s/step)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

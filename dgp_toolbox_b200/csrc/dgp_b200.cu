@@ -34,6 +34,14 @@ struct dgp_ctx {
   double* d_stage = nullptr;            // device side of that staging (outside the arena, which may be re-grown)
   size_t d_stage_bytes = 0;
   long launches = 0;                    // kernels launched since the last dgp_reset_launch_count
+  // optional per-category device timing (CUDA event pairs around every launch, on the ctx's stream)
+  bool profiling = false;
+  int cat = 0;
+  std::vector<cudaEvent_t> ev_pool;
+  struct Span { int cat; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  double cat_ms[DGP_PROFILE_CATEGORIES] = {0};
+  long cat_launches[DGP_PROFILE_CATEGORIES] = {0};
 };
 
 namespace {
@@ -51,15 +59,33 @@ namespace {
     int rc__ = (expr);           \
     if (rc__ != DGP_OK) return rc__; \
   } while (0)
+cudaEvent_t prof_event(dgp_ctx* c) {
+  cudaEvent_t e = nullptr;
+  if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+  else cudaEventCreate(&e);
+  return e;
+}
+struct ProfScope {   // records an event pair around the launches issued during its lifetime
+  dgp_ctx* c; cudaEvent_t a = nullptr;
+  explicit ProfScope(dgp_ctx* ctx) : c(ctx) {
+    if (c->profiling && !c->dry) { a = prof_event(c); cudaEventRecord(a, c->stream); }
+  }
+  ~ProfScope() {
+    if (a) { cudaEvent_t b = prof_event(c); cudaEventRecord(b, c->stream); c->spans.push_back({c->cat, a, b}); }
+  }
+};
 // kernel launch, skipped while planning the workspace
 #define LAUNCH(kern, grid, block, smem, ...)                          \
   do {                                                                \
     if (!c->dry) {                                                    \
+      ProfScope ps__(c);                                              \
       kern<<<grid, block, smem, c->stream>>>(__VA_ARGS__);            \
       ++c->launches;                                                  \
+      ++c->cat_launches[c->cat];                                      \
       CK(cudaGetLastError());                                         \
     }                                                                 \
   } while (0)
+#define CAT(x) c->cat = (x)
 
 double* walloc(dgp_ctx* c, size_t n_doubles) {
   size_t bytes = (n_doubles * sizeof(double) + 255) & ~(size_t)255;
@@ -88,8 +114,10 @@ int ensure_ws(dgp_ctx* c, size_t need) {
 
 int gemm(dgp_ctx* c, GemmArgs g, bool nt) {
   if (c->dry) return DGP_OK;
+  ProfScope ps(c);
   cudaError_t e = gemm_launch(g, nt, c->stream);
   c->launches += g.splitk > 1 ? 2 : 1;
+  c->cat_launches[c->cat] += g.splitk > 1 ? 2 : 1;
   if (e != cudaSuccess) {
     c->err = std::string("gemm_launch: ") + cudaGetErrorString(e);
     return DGP_ERR_CUDA;
@@ -191,6 +219,7 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
   CholArgs* dargs = reinterpret_cast<CholArgs*>(walloc(c, (sizeof(CholArgs) * nl + 7) / 8));
   if (c->dry) return DGP_OK;
 
+  CAT(DGP_CAT_PREP);
   CK(cudaMemsetAsync(c->d_info, 0, sizeof(int), c->stream));
   CK(cudaMemcpyAsync(dargs, hargs.data(), sizeof(CholArgs) * nl, cudaMemcpyHostToDevice, c->stream));
   for (int l = 0; l < nl; ++l) {
@@ -261,8 +290,10 @@ int forward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, ChunkLa
   double* V = tmp.t1;
   double* A = stash ? cl.A : tmp.t2;
   double* T = stash ? cl.T : Tshared;
+  CAT(DGP_CAT_KUF);
   LAUNCH(kuf_kernel, dim3((unsigned)(Pp / kKufCols), (unsigned)(Mp / kKufRows)), 256, 0, cl.Xin, cl.xmod, d.Z, d.lengthscales,
          d.variance, w.M, Mp, w.D_in, P, Pp, K);
+  CAT(DGP_CAT_GEMM_FWD);
   GemmArgs g = gargs(w.Linv, Mp, K, Pp, V, Pp, Mp, (int)Pp, Mp);    // V = Lu^-1 Kuf            (layers.py:245)
   g.a_tri = 1;
   RC(gemm(c, g, false));
@@ -273,6 +304,7 @@ int forward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, ChunkLa
   g.a_tri = 2; g.batch = D; g.sA = (long)Mp * Mp; g.sB = 0; g.sC = (long)Mp * Pp;
   RC(gemm(c, g, false));
 
+  CAT(DGP_CAT_MOMENTS);
   MomentsArgs a;
   memset(&a, 0, sizeof(a));
   a.V = V; a.A = A; a.T = T; a.qmu = d.q_mu; a.var = d.variance;
@@ -308,6 +340,7 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
   double* W = tmp.t1;
   double* Gbar = tmp.t2;
   // dA' = q_mu Gm^T + sum_d R_d (2 Gv_d o T_d)                                       
+  CAT(DGP_CAT_GEMM_BWD_DATA);
   GemmArgs g = gargs(w.qmuP, 32, up.GmPad, 32, dA, Pp, Mp, (int)Pp, 32);
   RC(gemm(c, g, true));
   g = gargs(w.Rcat, (long)D * Mp, cl.T, Pp, dA, Pp, Mp, (int)Pp, D * Mp);
@@ -318,6 +351,7 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
   g = gargs(w.Kinv, Mp, dA, Pp, W, Pp, Mp, (int)Pp, Mp);
   RC(gemm(c, g, false));
   // RBF adjoint on the Kuf block: W -> Wg (in place), Gbar, dXin, [X,1], partial sums for dl / ds2
+  CAT(DGP_CAT_RBF_BWD);
   RbfBwdArgs r;
   memset(&r, 0, sizeof(r));
   r.W = W; r.A = cl.A; r.gq = up.gq; r.Gbar = Gbar; r.Xin = cl.Xin; r.xmod = cl.xmod; r.Z = d.Z; r.ls = d.lengthscales;
@@ -334,6 +368,7 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
   LAUNCH(reduce_partials_kernel, w.D_in + 1, 256, 0, rbf_part, nb, w.D_in + 1, w.rbf_red, first_chunk ? 0 : 1);
   LAUNCH(reduce_partials_kernel, 3, 256, 0, up.part, up.nblocks, 3, w.sgv, first_chunk ? 0 : 1);
   const long mt = Mp / 64;
+  CAT(DGP_CAT_GEMM_BWD_PARAM);
   // dKu (data part) = -Wg A^T
   g = gargs(W, Pp, cl.A, Pp, w.dKu, Mp, Mp, Mp, (int)Pp);
   g.alpha = -1.0; g.beta = beta; g.splitk = pick_splitk(Pp, mt * mt, (size_t)Mp * Mp); g.part = splitk_part;
@@ -472,6 +507,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
       RC(forward_layer(c, d, lw[l], cl, tmp, grad, Tshared, l, Nc, S, N, n0, seed, n_offset, o.io, need_sample));
     }
     const ChunkLayer& clL = cls[nl - 1];
+    CAT(DGP_CAT_OTHER);
     // ---- prediction epilogues ----
     if (o.pm) {
       const long ND = Nc * DL;
@@ -501,6 +537,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
         double* dX_next = dXa;
         for (int l = nl - 1; l >= 0; --l) {
           const dgp_layer_desc& d = model->layers[l];
+          CAT(DGP_CAT_OTHER);
           if (l < nl - 1) {
             // Gm = G_F, Gv = G_F z / (2 sqrt(var + jitter))                          (adjoint of utils/utils.py:40-41)
             UpstreamOut uh{up.Gm, up.GvT, up.GmPad, up.gq, lik_part};
@@ -517,6 +554,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
   }
 
   // ---- replicated epilogue: KL, its adjoint, RBF adjoint on Kuu, gradient assembly ----
+  CAT(DGP_CAT_PREP);
   if (grad || o.want_elbo) {
     double* out = o.out_flat;
     std::vector<dgp_layer_grad_offsets> offs(nl);
@@ -612,6 +650,8 @@ void dgp_ctx_destroy(dgp_ctx* c) {
   if (c->d_info) cudaFree(c->d_info);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->d_stage) cudaFree(c->d_stage);
+  for (auto& s : c->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
   delete c;
 }
 
@@ -628,6 +668,30 @@ int64_t dgp_workspace_bytes(dgp_ctx* c) { return c ? (int64_t)c->cap : 0; }
 int dgp_set_workspace_limit(dgp_ctx* c, int64_t bytes) {
   if (!c || bytes < ((int64_t)64 << 20)) return DGP_ERR_ARG;
   c->ws_limit = (size_t)bytes;
+  return DGP_OK;
+}
+
+int dgp_set_profiling(dgp_ctx* c, int on) {
+  if (!c) return DGP_ERR_ARG;
+  c->profiling = on != 0;
+  return DGP_OK;
+}
+
+int dgp_get_profile(dgp_ctx* c, double* ms_out, int64_t* launches_out, int reset) {
+  if (!c) return DGP_ERR_ARG;
+  CK(cudaStreamSynchronize(c->stream));
+  for (auto& s : c->spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) c->cat_ms[s.cat] += ms;
+    c->ev_pool.push_back(s.a);
+    c->ev_pool.push_back(s.b);
+  }
+  c->spans.clear();
+  for (int i = 0; i < DGP_PROFILE_CATEGORIES; ++i) {
+    if (ms_out) ms_out[i] = c->cat_ms[i];
+    if (launches_out) launches_out[i] = c->cat_launches[i];
+    if (reset) { c->cat_ms[i] = 0.0; c->cat_launches[i] = 0; }
+  }
   return DGP_OK;
 }
 

@@ -55,6 +55,20 @@ int dgp_set_workspace_limit(dgp_ctx* ctx, int64_t bytes);
 /* number of kernels this ctx has launched (reset != 0 zeroes the counter afterwards) */
 int64_t dgp_launch_count(dgp_ctx* ctx, int reset);
 
+/* Per-category device time of the ctx's launches, measured with CUDA event pairs on the ctx's stream (bench.py's
+ * live roofline figure). dgp_get_profile synchronises the stream; ms_out / launches_out have DGP_PROFILE_CATEGORIES entries. */
+#define DGP_PROFILE_CATEGORIES 8
+enum { DGP_CAT_PREP = 0,            /* Kuu build, Cholesky + inverse, KL, replicated M^3-class products, gradient assembly */
+       DGP_CAT_KUF = 1,             /* Kuf tiles (covs.Kuf) */
+       DGP_CAT_GEMM_FWD = 2,        /* V = Lu^-1 Kuf, A = Lu^-T V, T_d = q_sqrt_d^T A  (DMMA) */
+       DGP_CAT_MOMENTS = 3,         /* mean / variance / sample epilogue */
+       DGP_CAT_GEMM_BWD_DATA = 4,   /* dA' and W = Ku^-1 dA'  (DMMA) */
+       DGP_CAT_RBF_BWD = 5,         /* RBF adjoint on the Kuf block */
+       DGP_CAT_GEMM_BWD_PARAM = 6,  /* dKu, dq_sqrt, dq_mu, dZ contractions over the point-samples (DMMA) */
+       DGP_CAT_OTHER = 7 };         /* likelihood, upstream adjoints, acquisition epilogues */
+int dgp_set_profiling(dgp_ctx* ctx, int on);
+int dgp_get_profile(dgp_ctx* ctx, double* ms_out, int64_t* launches_out, int reset);
+
 /* kern.K(X, X2) of the GPflow SquaredExponential the reference layers hold (utils/layers.py:221,230,243):
  * K_out [n1, n2] = variance * exp(-0.5 * sum_j ((X[i,j] - X2[k,j]) / lengthscales[j])^2). */
 int dgp_kernel_K(dgp_ctx* ctx, int D, const double* lengthscales, const double* variance, const double* X, int64_t n1,
