@@ -54,6 +54,7 @@ _SIG = {
     "dgp_set_workspace_limit": (C.c_int, [_vp, _i64]),
     "dgp_launch_count": (_i64, [_vp, _i]),
     "dgp_set_profiling": (C.c_int, [_vp, _i]),
+    "dgp_set_fused": (C.c_int, [_vp, _i]),
     "dgp_get_profile": (C.c_int, [_vp, _vp, _vp, _i]),
     "dgp_philox_normal": (C.c_int, [_vp, _u64, _i, _i64, _i64, _i, _i64, _vp]),
     "dgp_kernel_K": (C.c_int, [_vp, _i, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
@@ -110,7 +111,7 @@ class Context:
     def launch_count(self, reset=False) -> int:
         return int(lib.dgp_launch_count(self.h, 1 if reset else 0))
 
-    PROFILE_CATEGORIES = ("prep", "kuf", "gemm_fwd", "moments", "gemm_bwd_data", "rbf_bwd", "gemm_bwd_param", "other")
+    PROFILE_CATEGORIES = ("prep", "kuf", "gemm_fwd", "moments", "gemm_bwd_data", "rbf_bwd", "gemm_bwd_param", "other", "fused_fwd")
 
     def set_profiling(self, on: bool):
         lib.dgp_set_profiling(self.h, 1 if on else 0)
@@ -122,6 +123,9 @@ class Context:
         cnt = (C.c_int64 * n)()
         lib.dgp_get_profile(self.h, C.cast(ms, _vp), C.cast(cnt, _vp), 1 if reset else 0)
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_CATEGORIES)}
+
+    def set_fused(self, on: bool):
+        lib.dgp_set_fused(self.h, 1 if on else 0)
 
     def set_workspace_limit(self, nbytes: int):
         rc = lib.dgp_set_workspace_limit(self.h, int(nbytes))

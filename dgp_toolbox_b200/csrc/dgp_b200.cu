@@ -11,6 +11,7 @@
 
 #include "acq.cuh"
 #include "common.cuh"
+#include "fused.cuh"
 #include "gemm.cuh"
 #include "layer.cuh"
 #include "philox.cuh"
@@ -28,11 +29,13 @@ struct dgp_ctx {
   size_t cap = 0, used = 0;
   bool dry = false;
   size_t ws_limit = (size_t)24 << 30;   // chunks of the minibatch are sized to stay under this
+  int num_sms = 148;
   int* d_info = nullptr;                // Cholesky failure flag
   double* h_pinned = nullptr;           // staging for the *_host entry points
   size_t h_pinned_bytes = 0;
   double* d_stage = nullptr;            // device side of that staging (outside the arena, which may be re-grown)
   size_t d_stage_bytes = 0;
+  bool use_fused = true;                // fused conditional kernel (fused.cuh); false -> unfused GEMM pipeline
   long launches = 0;                    // kernels launched since the last dgp_reset_launch_count
   // optional per-category device timing (CUDA event pairs around every launch, on the ctx's stream)
   bool profiling = false;
@@ -186,7 +189,52 @@ struct LayerWs {
   // gradient accumulators over the chunks of the minibatch
   double *dKu = nullptr, *dR = nullptr, *dqmu = nullptr, *H = nullptr, *rbf_red = nullptr, *sgv = nullptr;
   double *dZk = nullptr, *kuu_part = nullptr, *kuu_red = nullptr, *kl = nullptr;
+  // fused conditional kernel: scaled inducing inputs, packed operator stream, panel schedule
+  double *Zs = nullptr, *stream = nullptr;
+  PanelDesc* sched = nullptr;
+  int NP = 0, fcfg = -1;   // fcfg: index into the fused configurations, -1 = not available
 };
+
+// ---- fused kernel configurations ----
+struct FusedChoice { int BM, PT; };
+constexpr FusedChoice kFusedChoices[4] = {{128, 64}, {128, 32}, {64, 64}, {64, 32}};
+constexpr size_t kMaxSmem = 227 * 1024;
+
+size_t fused_smem(int cfg, int Mp, int D_in, int D_out) {
+  switch (cfg) {
+    case 0: return FusedCfg<128, 64, 4, 2>::smem_bytes(Mp, D_in, D_out);
+    case 1: return FusedCfg<128, 32, 4, 2>::smem_bytes(Mp, D_in, D_out);
+    case 2: return FusedCfg<64, 64, 2, 4>::smem_bytes(Mp, D_in, D_out);
+    default: return FusedCfg<64, 32, 2, 4>::smem_bytes(Mp, D_in, D_out);
+  }
+}
+
+int pick_fused_cfg(int Mp, int D_in, int D_out) {
+  for (int cfg = 0; cfg < 4; ++cfg) {
+    if (Mp % kFusedChoices[cfg].BM) continue;
+    if (fused_smem(cfg, Mp, D_in, D_out) <= kMaxSmem) return cfg;
+  }
+  return -1;
+}
+
+std::vector<PanelDesc> build_schedule(int Mp, int BM, int D_out) {
+  std::vector<PanelDesc> v;
+  const int nb = Mp / BM, kpb = BM / kPanelK, kt = Mp / kPanelK;
+  for (int i = nb - 1; i >= 0; --i)
+    for (int ks = 0; ks < (i + 1) * kpb; ++ks) {
+      int fl = (ks == 0 ? kPanelFirst : 0) | (ks == (i + 1) * kpb - 1 ? kPanelLast : 0) | (ks * kPanelK >= i * BM ? kPanelClip : 0);
+      if ((fl & kPanelLast) && i == 0) fl |= kPanelStageEnd;
+      v.push_back(PanelDesc{0, 0, i, ks * kPanelK, fl, 0});
+    }
+  for (int pass = 0; pass <= D_out; ++pass)
+    for (int i = 0; i < nb; ++i)
+      for (int ks = i * kpb; ks < kt; ++ks) {
+        int fl = (ks == i * kpb ? kPanelFirst : 0) | (ks == kt - 1 ? kPanelLast : 0) | (ks * kPanelK < (i + 1) * BM ? kPanelClip : 0);
+        if ((fl & kPanelLast) && i == nb - 1) fl |= kPanelStageEnd;
+        v.push_back(PanelDesc{pass == 0 ? 1 : 2, pass == 0 ? 0 : pass - 1, i, ks * kPanelK, fl, 0});
+      }
+  return v;
+}
 
 enum PrepLevel { PREP_FWD = 0, PREP_KL = 1, PREP_GRAD = 2 };
 
@@ -215,6 +263,15 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
     }
     if (w.Mp > maxMp) maxMp = w.Mp;
     hargs[l] = CholArgs{w.Ku, w.L, w.Linv, w.LinvT, w.Mp, c->d_info};
+    w.fcfg = c->use_fused ? pick_fused_cfg(w.Mp, w.D_in, w.D_out) : -1;
+    if (w.fcfg >= 0) {
+      const int BM = kFusedChoices[w.fcfg].BM;
+      const int nb = w.Mp / BM, kpb = BM / kPanelK;
+      w.NP = (2 + w.D_out) * kpb * nb * (nb + 1) / 2;
+      w.Zs = walloc(c, (size_t)w.M * w.D_in);
+      w.stream = walloc(c, (size_t)w.NP * BM * kPanelK);
+      w.sched = reinterpret_cast<PanelDesc*>(walloc(c, ((size_t)w.NP * sizeof(PanelDesc) + 7) / 8));
+    }
   }
   CholArgs* dargs = reinterpret_cast<CholArgs*>(walloc(c, (sizeof(CholArgs) * nl + 7) / 8));
   if (c->dry) return DGP_OK;
@@ -238,6 +295,18 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
       configured = true;
     }
     LAUNCH(chol_inv_kernel, nl, kCholThreads, chol_smem_bytes(maxMp), dargs);
+  }
+  for (int l = 0; l < nl; ++l) {   // operator stream of the fused conditional kernel
+    LayerWs& w = lw[l];
+    if (w.fcfg < 0) continue;
+    const dgp_layer_desc& d = model->layers[l];
+    const int BM = kFusedChoices[w.fcfg].BM;
+    std::vector<PanelDesc> sch = build_schedule(w.Mp, BM, w.D_out);
+    if ((int)sch.size() != w.NP) { c->err = "internal: panel schedule size mismatch"; return DGP_ERR_ARG; }
+    CK(cudaMemcpyAsync(w.sched, sch.data(), sch.size() * sizeof(PanelDesc), cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(scale_z_kernel, (unsigned)((w.M * w.D_in + 255) / 256), 256, 0, d.Z, d.lengthscales, w.M, w.D_in, w.Zs);
+    if (BM == 128) LAUNCH(pack_stream_kernel<128>, w.NP, 256, 0, w.sched, w.Linv, w.LinvT, w.RpT, w.Mp, w.stream);
+    else LAUNCH(pack_stream_kernel<64>, w.NP, 256, 0, w.sched, w.Linv, w.LinvT, w.RpT, w.Mp, w.stream);
   }
   if (level >= PREP_KL) {
     for (int l = 0; l < nl; ++l) {
@@ -286,6 +355,37 @@ int forward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, ChunkLa
                   const ChunkIO& io, bool need_sample) {
   const long P = Nc * S, Pp = round_up(P, kTileP);
   const int Mp = w.Mp, D = w.D_out;
+  if (w.fcfg >= 0) {
+    CAT(DGP_CAT_FUSED_FWD);
+    FusedFwdArgs f;
+    memset(&f, 0, sizeof(f));
+    f.stream = w.stream; f.sched = w.sched; f.NP = w.NP; f.Zs = w.Zs; f.ls = d.lengthscales; f.var = d.variance; f.qmu = d.q_mu;
+    f.Xin = cl.Xin; f.xmod = cl.xmod; f.D_in = w.D_in; f.mfW = d.mf_W; f.mfb = d.mf_b; f.mean_kind = d.mean_kind;
+    f.z_in = (io.zs && io.zs[layer]) ? io.zs[layer] : nullptr;
+    f.seed = seed; f.layer = layer; f.Nc = Nc; f.N_total = N_total; f.n0 = n0; f.n_offset = n_offset;
+    f.M = w.M; f.Mp = w.Mp; f.D_out = w.D_out; f.P = P; f.Pp = Pp; f.jitter = d.jitter;
+    f.Fmean = cl.Fmean; f.Fvar = cl.Fvar; f.F = need_sample ? cl.F : nullptr; f.z = need_sample ? cl.z : nullptr;
+    f.xFmean = (io.Fmeans && io.Fmeans[layer]) ? io.Fmeans[layer] : nullptr;
+    f.xFvar = (io.Fvars && io.Fvars[layer]) ? io.Fvars[layer] : nullptr;
+    f.xF = (io.Fs && io.Fs[layer]) ? io.Fs[layer] : nullptr;
+    f.stashA = stash ? cl.A : nullptr; f.stashT = stash ? cl.T : nullptr;
+    const size_t smem = fused_smem(w.fcfg, w.Mp, w.D_in, w.D_out);
+    const long ntiles = Pp / kFusedChoices[w.fcfg].PT;
+    const unsigned grid = (unsigned)(ntiles < c->num_sms ? ntiles : c->num_sms);
+#define FUSED_LAUNCH(BM_, PT_, WM_, WN_)                                                                                   \
+    do {                                                                                                                   \
+      if (!c->dry) CK(cudaFuncSetAttribute(fused_forward_kernel<BM_, PT_, WM_, WN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem)); \
+      LAUNCH((fused_forward_kernel<BM_, PT_, WM_, WN_>), grid, 256, smem, f);                                              \
+    } while (0)
+    switch (w.fcfg) {
+      case 0: FUSED_LAUNCH(128, 64, 4, 2); break;
+      case 1: FUSED_LAUNCH(128, 32, 4, 2); break;
+      case 2: FUSED_LAUNCH(64, 64, 2, 4); break;
+      default: FUSED_LAUNCH(64, 32, 2, 4); break;
+    }
+#undef FUSED_LAUNCH
+    return DGP_OK;
+  }
   double* K = tmp.t0;
   double* V = tmp.t1;
   double* A = stash ? cl.A : tmp.t2;
@@ -634,6 +734,8 @@ int dgp_ctx_create(int device, void* cuda_stream, dgp_ctx** out) {
   if (prop.major != 10) return DGP_ERR_UNSUPPORTED;   // sm_100a only: no fallback path exists
   dgp_ctx* c = new dgp_ctx();
   c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  if (getenv("DGP_B200_UNFUSED")) c->use_fused = false;
   c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
   if (cudaMalloc(&c->d_info, sizeof(int)) != cudaSuccess) { delete c; return DGP_ERR_CUDA; }
   const char* lim = getenv("DGP_B200_WS_GB");
@@ -668,6 +770,12 @@ int64_t dgp_workspace_bytes(dgp_ctx* c) { return c ? (int64_t)c->cap : 0; }
 int dgp_set_workspace_limit(dgp_ctx* c, int64_t bytes) {
   if (!c || bytes < ((int64_t)64 << 20)) return DGP_ERR_ARG;
   c->ws_limit = (size_t)bytes;
+  return DGP_OK;
+}
+
+int dgp_set_fused(dgp_ctx* c, int on) {
+  if (!c) return DGP_ERR_ARG;
+  c->use_fused = on != 0;
   return DGP_OK;
 }
 

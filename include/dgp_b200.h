@@ -57,7 +57,7 @@ int64_t dgp_launch_count(dgp_ctx* ctx, int reset);
 
 /* Per-category device time of the ctx's launches, measured with CUDA event pairs on the ctx's stream (bench.py's
  * live roofline figure). dgp_get_profile synchronises the stream; ms_out / launches_out have DGP_PROFILE_CATEGORIES entries. */
-#define DGP_PROFILE_CATEGORIES 8
+#define DGP_PROFILE_CATEGORIES 9
 enum { DGP_CAT_PREP = 0,            /* Kuu build, Cholesky + inverse, KL, replicated M^3-class products, gradient assembly */
        DGP_CAT_KUF = 1,             /* Kuf tiles (covs.Kuf) */
        DGP_CAT_GEMM_FWD = 2,        /* V = Lu^-1 Kuf, A = Lu^-T V, T_d = q_sqrt_d^T A  (DMMA) */
@@ -65,8 +65,11 @@ enum { DGP_CAT_PREP = 0,            /* Kuu build, Cholesky + inverse, KL, replic
        DGP_CAT_GEMM_BWD_DATA = 4,   /* dA' and W = Ku^-1 dA'  (DMMA) */
        DGP_CAT_RBF_BWD = 5,         /* RBF adjoint on the Kuf block */
        DGP_CAT_GEMM_BWD_PARAM = 6,  /* dKu, dq_sqrt, dq_mu, dZ contractions over the point-samples (DMMA) */
-       DGP_CAT_OTHER = 7 };         /* likelihood, upstream adjoints, acquisition epilogues */
+       DGP_CAT_OTHER = 7,           /* likelihood, upstream adjoints, acquisition epilogues */
+       DGP_CAT_FUSED_FWD = 8 };     /* fused conditional + sample kernel (Kuf, both solves, q_sqrt contraction, moments in one launch) */
 int dgp_set_profiling(dgp_ctx* ctx, int on);
+/* on = 0 routes the conditional through the unfused GEMM pipeline (debug / A-B measurement); default 1 */
+int dgp_set_fused(dgp_ctx* ctx, int on);
 int dgp_get_profile(dgp_ctx* ctx, double* ms_out, int64_t* launches_out, int reset);
 
 /* kern.K(X, X2) of the GPflow SquaredExponential the reference layers hold (utils/layers.py:221,230,243):

@@ -12,19 +12,33 @@ from tests.helpers import both_models, oracle_zs, rel_err
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
 
+
+@pytest.fixture(params=["fused", "unfused"])
+def conditional_path(request):
+    """Both implementations of the conditional: the fused kernel (default) and the unfused GEMM pipeline."""
+    import dgp_toolbox_b200 as D
+    ctx = D._lib.get_context(0)
+    ctx.set_fused(request.param == "fused")
+    yield request.param
+    ctx.set_fused(True)
+
+
 SHAPES = [
-    # D0, num_units, M, N, S
-    (2, [2], 50, 100, 10),          # config-1 shape (nb_DGP_regression-like: D=2, M=50, S=10)
-    (8, [8, 8], 64, 48, 4),         # config-2 structure, small
-    (8, [8, 8, 8], 256, 64, 8),     # config-2: 3 hidden layers (4 SVGP layers), M=256
-    (5, [3, 6], 40, 37, 3),         # ragged: PCA-narrowing and zero-padding Linear mean functions, odd sizes
-    (1, [1, 1], 25, 50, 10),        # KAT-1 shape
+    # D0, num_units, M, N, S, condition (False = the SURVEY §8d inputs exactly as specified, l = sqrt(D_in))
+    (2, [2], 50, 100, 10, True),          # config-1 shape (nb_DGP_regression-like: D=2, M=50, S=10)
+    (8, [8, 8], 64, 48, 4, True),         # config-2 structure, small
+    (8, [8, 8, 8], 256, 64, 8, False),    # config-2 exactly: 3 hidden layers (4 SVGP layers), M=256, cond(Ku) ~ 8e5
+    (8, [8, 8, 8], 256, 40, 32, True),    # config-2 with S=32
+    (5, [3, 6], 40, 37, 3, True),         # ragged: PCA-narrowing and zero-padding Linear mean functions, odd sizes
+    (1, [1, 1], 25, 50, 10, True),        # KAT-1 shape
+    (6, [6], 128, 150, 3, True),          # Mp = 128: BM=128 fused configuration with one row block
+    (4, [4], 320, 70, 2, True),           # Mp = 320: BM=64 fused configuration, 5 row blocks
 ]
 
 
-@pytest.mark.parametrize("D0,num_units,M,N,S", SHAPES)
-def test_propagate_matches_oracle(D0, num_units, M, N, S):
-    prob, om, pm = both_models(D0, num_units, M, N, S)
+@pytest.mark.parametrize("D0,num_units,M,N,S,cond", SHAPES)
+def test_propagate_matches_oracle(D0, num_units, M, N, S, cond, conditional_path):
+    prob, om, pm = both_models(D0, num_units, M, N, S, condition=cond)
     zs = oracle_zs(om, N, S, 7)
     X = torch.as_tensor(prob["X"])
     Fs_o, Fm_o, Fv_o = O.propagate(om.layers, X, S, zs)
@@ -36,9 +50,9 @@ def test_propagate_matches_oracle(D0, num_units, M, N, S):
         assert rel_err(Fs[l], Fs_o[l]) < TOL, ("sample", l)
 
 
-@pytest.mark.parametrize("D0,num_units,M,N,S", SHAPES)
-def test_elbo_and_gradients_match_oracle(D0, num_units, M, N, S):
-    prob, om, pm = both_models(D0, num_units, M, N, S)
+@pytest.mark.parametrize("D0,num_units,M,N,S,cond", SHAPES)
+def test_elbo_and_gradients_match_oracle(D0, num_units, M, N, S, cond, conditional_path):
+    prob, om, pm = both_models(D0, num_units, M, N, S, condition=cond)
     zs = oracle_zs(om, N, S, 11)
     X, Y = torch.as_tensor(prob["X"]), torch.as_tensor(prob["Y"])
     val_o, g_o = O.elbo_and_grads(om, X, Y, zs)
@@ -101,7 +115,7 @@ def test_kat1_notebook_elbo_through_cuda():
     assert abs(val - (-406.37591174470)) <= 1e-9 * 406.37591174470, val
 
 
-def test_philox_stream_is_bit_exact_and_drives_the_chain():
+def test_philox_stream_is_bit_exact_and_drives_the_chain(conditional_path):
     import dgp_toolbox_b200 as D
     prob, om, pm = both_models(3, [2], 20, 33, 6)
     S, N = 6, 33
@@ -151,7 +165,7 @@ def test_predict_ei_ehvi_match_oracle():
     assert rel_err(e, e_o) < 1e-8
 
 
-def test_chunked_minibatch_equals_single_pass():
+def test_chunked_minibatch_equals_single_pass(conditional_path):
     """The workspace limit splits the minibatch into chunks of points; results must not depend on the split."""
     import dgp_toolbox_b200 as D
     prob, om, pm = both_models(4, [4], 64, 700, 4)
