@@ -33,6 +33,50 @@ constexpr int kPanelK = 16;
 
 __device__ __forceinline__ int panel_swz(int row, int k) { return row * kPanelK + ((((k >> 2) ^ (row & 3)) << 2) | (k & 3)); }
 
+// The panel schedule as an iterator (same order as build_schedule() on the host, which feeds pack_stream_kernel):
+//   pass 0:        V  = Linv  * tile, row blocks i = nb-1 .. 0, k-panels 0 .. (i+1)*BM/16 - 1          (lower operator)
+//   pass 1:        A  = LinvT * tile, row blocks i = 0 .. nb-1, k-panels i*BM/16 .. Mp/16 - 1          (upper operator)
+//   pass 2 + d:    T_d = RpT_d * tile, same block order as pass 1
+// Kept in registers: no global loads inside the panel loop (an LDG there shares the scoreboard the cp.async ring uses
+// and would drain the whole ring every iteration).
+template <int BM>
+struct PanelIter {
+  int pass, i, ks, ks_end, nb, kt;
+  __device__ __forceinline__ void init(int Mp) {
+    nb = Mp / BM; kt = Mp / kPanelK;
+    pass = 0; i = nb - 1; ks = 0; ks_end = nb * (BM / kPanelK);
+  }
+  __device__ __forceinline__ PanelDesc get() const {
+    PanelDesc e;
+    e.kind = pass == 0 ? 0 : (pass == 1 ? 1 : 2);
+    e.d = pass >= 2 ? pass - 2 : 0;
+    e.i = i; e.k0 = ks * kPanelK; e.pad = 0;
+    const bool last = ks == ks_end - 1;
+    int fl = last ? kPanelLast : 0;
+    if (pass == 0) {
+      if (ks == 0) fl |= kPanelFirst;
+      if (e.k0 >= i * BM) fl |= kPanelClip;
+      if (last && i == 0) fl |= kPanelStageEnd;
+    } else {
+      if (ks == i * (BM / kPanelK)) fl |= kPanelFirst;
+      if (e.k0 < (i + 1) * BM) fl |= kPanelClip;
+      if (last && i == nb - 1) fl |= kPanelStageEnd;
+    }
+    e.flags = fl;
+    return e;
+  }
+  __device__ __forceinline__ void next() {
+    if (++ks < ks_end) return;
+    if (pass == 0) {
+      if (--i >= 0) { ks = 0; ks_end = (i + 1) * (BM / kPanelK); return; }
+      pass = 1; i = 0;
+    } else {
+      if (++i >= nb) { ++pass; i = 0; }
+    }
+    ks = i * (BM / kPanelK); ks_end = kt;
+  }
+};
+
 // One CTA per panel: copies the [BM x 16] block of the source operator into the stream, swizzled.
 template <int BM>
 __global__ void __launch_bounds__(256) pack_stream_kernel(const PanelDesc* __restrict__ sched, const double* __restrict__ Linv,
@@ -96,29 +140,32 @@ __global__ void __launch_bounds__(256, 1) fused_forward_kernel(FusedFwdArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g8 = lane >> 2, t4 = lane & 3;
   const int wm = warp / WN, wn = warp % WN;
-  const long ntiles = a.Pp / PT;   // padded tiles too: the stash planes must be fully written (zeros beyond P)
-  const long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const long total = my_tiles * a.NP;
+  const int ntiles = (int)(a.Pp / PT);   // padded tiles too: the stash planes must be fully written (zeros beyond P)
+  const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const double s2 = a.var[0];
 
-  auto issue = [&](long g) {
-    if (g < total) {
-      const double* src = a.stream + (g % a.NP) * (long)PANEL;
-      double* dst = pbuf + (g % STAGES) * PANEL;
+  // producer side of the ring: panel `iq` of the stream goes to stage `ist`; `ileft` panels remain for this CTA
+  int iq = 0, ist = 0;
+  long ileft = (long)my_tiles * a.NP;
+  const double* isrc = a.stream + tid * 2;
+  auto issue = [&]() {
+    if (ileft > 0) {
+      double* dst = pbuf + ist * PANEL + tid * 2;
 #pragma unroll
-      for (int c = 0; c < PANEL / 2 / 256; ++c) {
-        const int off = (c * 256 + tid) * 2;
-        cp_async16(dst + off, src + off);
-      }
+      for (int c = 0; c < PANEL / 2 / 256; ++c) cp_async16(dst + c * 512, isrc + c * 512);
+      --ileft;
+      isrc += PANEL;
+      if (++iq == a.NP) { iq = 0; isrc = a.stream + tid * 2; }
+      if (++ist == STAGES) ist = 0;
     }
     cp_async_commit();
   };
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) issue(s);
+  for (int s = 0; s < STAGES - 1; ++s) issue();
 
-  long g = 0;
-  for (long tl = 0; tl < my_tiles; ++tl) {
-    const long p0 = (blockIdx.x + tl * gridDim.x) * (long)PT;
+  int cst = 0;   // consumer stage
+  for (int tl = 0; tl < my_tiles; ++tl) {
+    const long p0 = (long)(blockIdx.x + tl * gridDim.x) * PT;
     __syncthreads();   // previous tile's epilogue is done with tile / colsum
     // ---- stage 1: scaled inputs, then the Kuf tile ----
     for (int idx = tid; idx < a.D_in * PT; idx += 256) {
@@ -149,21 +196,22 @@ __global__ void __launch_bounds__(256, 1) fused_forward_kernel(FusedFwdArgs a) {
     double c0[TM][TN], c1[TM][TN], sq0[TN], sq1[TN];
 #pragma unroll
     for (int j = 0; j < TN; ++j) { sq0[j] = 0.0; sq1[j] = 0.0; }
-    PanelDesc e_next = a.sched[0];
-    for (int q = 0; q < a.NP; ++q, ++g) {
+    PanelIter<BM> it;
+    it.init(a.Mp);
+    for (int q = 0; q < a.NP; ++q, it.next()) {
       cp_async_wait<STAGES - 2>();
       __syncthreads();
-      issue(g + STAGES - 1);
-      const PanelDesc e = e_next;
-      e_next = a.sched[q + 1 < a.NP ? q + 1 : 0];   // prefetched one panel ahead: its latency hides behind this panel's DMMAs
+      issue();
+      const PanelDesc e = it.get();
       if (e.flags & kPanelFirst) {
 #pragma unroll
         for (int i = 0; i < TM; ++i)
 #pragma unroll
           for (int j = 0; j < TN; ++j) { c0[i][j] = 0.0; c1[i][j] = 0.0; }
       }
-      const double* pan = pbuf + (g % STAGES) * PANEL;
-      const double* bt = tile + (long)(e.k0 + t4) * LDT + wn * TN * 8 + g8;
+      const double* pan = pbuf + cst * PANEL;
+      if (++cst == STAGES) cst = 0;
+      const double* bt = tile + (e.k0 + t4) * LDT + wn * TN * 8 + g8;
       // m-tiles of this warp that intersect the operator's triangle inside this panel: [imin, imax). The rest of the
       // panel is zero for them, so whole (panel, m-tile) pairs are skipped with a real (warp-uniform) branch.
       int imin = 0, imax = TM;
