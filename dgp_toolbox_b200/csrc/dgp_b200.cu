@@ -375,7 +375,7 @@ int forward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, ChunkLa
 #define FUSED_LAUNCH(BM_, PT_, WM_, WN_)                                                                                   \
     do {                                                                                                                   \
       if (!c->dry) CK(cudaFuncSetAttribute(fused_forward_kernel<BM_, PT_, WM_, WN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem)); \
-      LAUNCH((fused_forward_kernel<BM_, PT_, WM_, WN_>), grid, 256, smem, f);                                              \
+      LAUNCH((fused_forward_kernel<BM_, PT_, WM_, WN_>), grid, 288, smem, f);                                              \
     } while (0)
     switch (w.fcfg) {
       case 0: FUSED_LAUNCH(128, 64, 4, 2); break;

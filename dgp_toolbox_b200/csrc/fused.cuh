@@ -113,85 +113,141 @@ struct FusedFwdArgs {
   double* stashA; double* stashT;                       // [Mp][Pp], [D_out][Mp][Pp] or null
 };
 
+// ---- mbarrier / bulk-copy primitives (sm_90+; SASS: SYNCS.*, UBLKCP) ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA engine, no tensor map needed for a linear panel); completes `bytes` on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void group_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Thread layout: WM*WN = 8 consumer warps + 1 producer warp. The WN consumer GROUPS (WM warps each) own disjoint column
+// ranges of the tile and run decoupled from each other: they share only the operator-panel ring, which the producer warp
+// fills with one bulk copy per panel (full/empty mbarriers). While one group is in per-panel bookkeeping, block-end
+// write-back, the Kuf build or the epilogue, the other groups keep the DMMA pipe busy.
 template <int BM, int PT, int WM, int WN>
 struct FusedCfg {
-  static_assert(WM * WN == 8, "8 warps");
-  static constexpr int THREADS = 256;
-  static constexpr int TM = BM / (8 * WM), TN = PT / (8 * WN);
+  static_assert(WM * WN == 8, "8 consumer warps");
+  static constexpr int THREADS = 288;
+  static constexpr int GT = WM * 32;          // threads per consumer group
+  static constexpr int GC = PT / WN;          // tile columns per group
+  static constexpr int TM = BM / (8 * WM), TN = GC / 8;
   static constexpr int LDT = PT + 4;
   static constexpr int PANEL = BM * kPanelK;
   static constexpr int STAGES = 4;
   static size_t smem_bytes(int Mp, int D_in, int D_out) {
-    return ((size_t)Mp * LDT + (size_t)STAGES * PANEL + (size_t)D_in * PT + (size_t)(1 + D_out) * PT + (size_t)WM * PT) * sizeof(double);
+    return ((size_t)Mp * LDT + (size_t)STAGES * PANEL + (size_t)D_in * PT + (size_t)(1 + D_out) * PT + (size_t)WM * PT + 2 * STAGES) * sizeof(double);
   }
 };
 
 template <int BM, int PT, int WM, int WN>
-__global__ void __launch_bounds__(256, 1) fused_forward_kernel(FusedFwdArgs a) {
+__global__ void __launch_bounds__(288, 1) fused_forward_kernel(FusedFwdArgs a) {
   using Cfg = FusedCfg<BM, PT, WM, WN>;
-  constexpr int TM = Cfg::TM, TN = Cfg::TN, LDT = Cfg::LDT, PANEL = Cfg::PANEL, STAGES = Cfg::STAGES;
-  extern __shared__ __align__(16) double smem[];
-  double* tile = smem;                                   // [Mp][LDT]   Kuf -> V -> A
-  double* pbuf = tile + (size_t)a.Mp * LDT;              // [STAGES][PANEL]
-  double* xs = pbuf + STAGES * PANEL;                    // [D_in][PT]  scaled inputs
-  double* colsum = xs + a.D_in * PT;                     // [1 + D_out][PT]: |V|^2, |T_d|^2
-  double* part = colsum + (1 + a.D_out) * PT;            // [WM][PT]
+  constexpr int TM = Cfg::TM, TN = Cfg::TN, LDT = Cfg::LDT, PANEL = Cfg::PANEL, STAGES = Cfg::STAGES, GT = Cfg::GT, GC = Cfg::GC;
+  extern __shared__ __align__(128) double fsmem[];
+  double* pbuf = fsmem;                                  // [STAGES][PANEL]   (first: 128-byte aligned for the bulk copies)
+  double* tile = pbuf + STAGES * PANEL;                  // [Mp][LDT]   Kuf -> V -> A
+  double* xs_all = tile + (size_t)a.Mp * LDT;            // [WN][D_in][GC]  scaled inputs
+  double* colsum_all = xs_all + a.D_in * PT;             // [WN][1 + D_out][GC]: |V|^2, |T_d|^2
+  double* part_all = colsum_all + (1 + a.D_out) * PT;    // [WN][WM][GC]
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(part_all + WM * PT);   // [STAGES]
+  unsigned long long* empty = full + STAGES;                                               // [STAGES]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g8 = lane >> 2, t4 = lane & 3;
-  const int wm = warp / WN, wn = warp % WN;
   const int ntiles = (int)(a.Pp / PT);   // padded tiles too: the stash planes must be fully written (zeros beyond P)
   const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const double s2 = a.var[0];
 
-  // producer side of the ring: panel `iq` of the stream goes to stage `ist`; `ileft` panels remain for this CTA
-  int iq = 0, ist = 0;
-  long ileft = (long)my_tiles * a.NP;
-  const double* isrc = a.stream + tid * 2;
-  auto issue = [&]() {
-    if (ileft > 0) {
-      double* dst = pbuf + ist * PANEL + tid * 2;
-#pragma unroll
-      for (int c = 0; c < PANEL / 2 / 256; ++c) cp_async16(dst + c * 512, isrc + c * 512);
-      --ileft;
-      isrc += PANEL;
-      if (++iq == a.NP) { iq = 0; isrc = a.stream + tid * 2; }
-      if (++ist == STAGES) ist = 0;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 8) {
+    // ---- producer: one bulk copy per panel, in stream order, round after round ----
+    if (lane == 0) {
+      int st = 0, q = 0;
+      unsigned ph = 0;
+      const double* src = a.stream;
+      const long total = (long)my_tiles * a.NP;
+      for (long n = 0; n < total; ++n) {
+        mbar_wait(empty + st, ph ^ 1);
+        mbar_arrive_expect_tx(full + st, PANEL * 8);
+        bulk_g2s(pbuf + st * PANEL, src, PANEL * 8, full + st);
+        src += PANEL;
+        if (++q == a.NP) { q = 0; src = a.stream; }
+        if (++st == STAGES) { st = 0; ph ^= 1; }
+      }
     }
-    cp_async_commit();
-  };
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) issue();
+    return;
+  }
 
-  int cst = 0;   // consumer stage
+  // ---- consumers ----
+  const int g8 = lane >> 2, t4 = lane & 3;
+  const int wm = warp / WN, wn = warp % WN;       // group = wn
+  const int tg = wm * 32 + lane;                  // thread index inside the group
+  const int col0 = wn * GC;                       // first tile column of the group
+  double* xs = xs_all + wn * a.D_in * GC;
+  double* colsum = colsum_all + wn * (1 + a.D_out) * GC;
+  double* part = part_all + wn * WM * GC;
+  const int bar_id = 1 + wn;
+  const double s2 = a.var[0];
+  int cst = 0;
+  unsigned cph = 0;
+
   for (int tl = 0; tl < my_tiles; ++tl) {
-    const long p0 = (long)(blockIdx.x + tl * gridDim.x) * PT;
-    __syncthreads();   // previous tile's epilogue is done with tile / colsum
+    const long p0 = (long)(blockIdx.x + tl * gridDim.x) * PT + col0;   // first point-sample of this group's columns
+    group_sync(bar_id, GT);   // previous tile's epilogue is done with the group's columns / colsum
     // ---- stage 1: scaled inputs, then the Kuf tile ----
-    for (int idx = tid; idx < a.D_in * PT; idx += 256) {
-      const int j = idx / PT, c = idx % PT;
+    for (int idx = tg; idx < a.D_in * GC; idx += GT) {
+      const int j = idx / GC, c = idx % GC;
       const long p = p0 + c;
       xs[idx] = (p < a.P) ? a.Xin[(p % a.xmod) * a.D_in + j] * (1.0 / a.ls[j]) : 0.0;
     }
-    __syncthreads();
+    group_sync(bar_id, GT);
     {
-      const int c = tid % PT, mg = tid / PT;
-      constexpr int MG = 256 / PT;
+      const int c = tg % GC, mg = tg / GC;
+      constexpr int MG = GT / GC;
       const bool live = p0 + c < a.P;
+#pragma unroll 2
       for (int m = mg; m < a.Mp; m += MG) {
         double k = 0.0;
         if (m < a.M && live) {
           double r2 = 0.0;
           const double* zr = a.Zs + (long)m * a.D_in;
           for (int j = 0; j < a.D_in; ++j) {
-            const double t = zr[j] - xs[j * PT + c];
+            const double t = zr[j] - xs[j * GC + c];
             r2 = fma(t, t, r2);
           }
           k = s2 * exp(-0.5 * r2);
         }
-        tile[m * LDT + c] = k;
+        tile[m * LDT + col0 + c] = k;
       }
     }
+    group_sync(bar_id, GT);
     // ---- stages 2-4: flat loop over the operator panels ----
     double c0[TM][TN], c1[TM][TN], sq0[TN], sq1[TN];
 #pragma unroll
@@ -199,9 +255,6 @@ __global__ void __launch_bounds__(256, 1) fused_forward_kernel(FusedFwdArgs a) {
     PanelIter<BM> it;
     it.init(a.Mp);
     for (int q = 0; q < a.NP; ++q, it.next()) {
-      cp_async_wait<STAGES - 2>();
-      __syncthreads();
-      issue();
       const PanelDesc e = it.get();
       if (e.flags & kPanelFirst) {
 #pragma unroll
@@ -209,9 +262,6 @@ __global__ void __launch_bounds__(256, 1) fused_forward_kernel(FusedFwdArgs a) {
 #pragma unroll
           for (int j = 0; j < TN; ++j) { c0[i][j] = 0.0; c1[i][j] = 0.0; }
       }
-      const double* pan = pbuf + cst * PANEL;
-      if (++cst == STAGES) cst = 0;
-      const double* bt = tile + (e.k0 + t4) * LDT + wn * TN * 8 + g8;
       // m-tiles of this warp that intersect the operator's triangle inside this panel: [imin, imax). The rest of the
       // panel is zero for them, so whole (panel, m-tile) pairs are skipped with a real (warp-uniform) branch.
       int imin = 0, imax = TM;
@@ -225,11 +275,14 @@ __global__ void __launch_bounds__(256, 1) fused_forward_kernel(FusedFwdArgs a) {
           imax = num >= 0 ? min(TM, num / (8 * WM) + 1) : 0;
         }
       }
+      const double* bt = tile + (e.k0 + t4) * LDT + col0 + g8;
       double bv[4][TN];
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
         for (int j = 0; j < TN; ++j) bv[kk][j] = bt[kk * 4 * LDT + j * 8];
+      const double* pan = pbuf + cst * PANEL;
+      mbar_wait(full + cst, cph);           // the panel's bytes have landed
 #pragma unroll
       for (int i = 0; i < TM; ++i) {
         if (i >= imin && i < imax) {
@@ -244,6 +297,10 @@ __global__ void __launch_bounds__(256, 1) fused_forward_kernel(FusedFwdArgs a) {
             for (int j = 0; j < TN; ++j) dmma884(c0[i][j], c1[i][j], av[kk], bv[kk][j]);
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + cst);   // this warp is done with the stage
+      if (++cst == STAGES) { cst = 0; cph ^= 1; }
+
       if (e.flags & kPanelLast) {
         if (e.kind != 1) {   // column sums of squares of V / T_d
 #pragma unroll
@@ -251,14 +308,14 @@ __global__ void __launch_bounds__(256, 1) fused_forward_kernel(FusedFwdArgs a) {
 #pragma unroll
             for (int j = 0; j < TN; ++j) { sq0[j] = fma(c0[i][j], c0[i][j], sq0[j]); sq1[j] = fma(c1[i][j], c1[i][j], sq1[j]); }
         }
-        if (e.kind != 2) {   // in-place update of the resident tile
-          __syncthreads();   // every warp has finished reading the rows this block overwrites
+        if (e.kind != 2) {   // in-place update of the resident tile (group-local hazard: same columns, all rows)
+          group_sync(bar_id, GT);   // every warp of the group has finished reading the rows this block overwrites
 #pragma unroll
           for (int i = 0; i < TM; ++i)
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
-              const int row = e.i * BM + i * 8 * WM + wm * 8 + g8, col = wn * TN * 8 + j * 8 + 2 * t4;
-              *reinterpret_cast<double2*>(tile + (long)row * LDT + col) = make_double2(c0[i][j], c1[i][j]);
+              const int row = e.i * BM + i * 8 * WM + wm * 8 + g8, col = col0 + j * 8 + 2 * t4;
+              *reinterpret_cast<double2*>(tile + row * LDT + col) = make_double2(c0[i][j], c1[i][j]);
             }
         }
         double* st = e.kind == 1 ? a.stashA : (e.kind == 2 && a.stashT ? a.stashT + (long)e.d * a.Mp * a.Pp : nullptr);
@@ -267,10 +324,11 @@ __global__ void __launch_bounds__(256, 1) fused_forward_kernel(FusedFwdArgs a) {
           for (int i = 0; i < TM; ++i)
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
-              const int row = e.i * BM + i * 8 * WM + wm * 8 + g8, col = wn * TN * 8 + j * 8 + 2 * t4;
+              const int row = e.i * BM + i * 8 * WM + wm * 8 + g8, col = j * 8 + 2 * t4;
               *reinterpret_cast<double2*>(st + (long)row * a.Pp + p0 + col) = make_double2(c0[i][j], c1[i][j]);
             }
         }
+        if (e.kind != 2) group_sync(bar_id, GT);   // the new rows are visible before the next block reads them
         if ((e.flags & kPanelStageEnd) && e.kind != 1) {
           // reduce the per-thread partial sums over the 8 row lanes, then over the WM warps (fixed order)
 #pragma unroll
@@ -281,30 +339,40 @@ __global__ void __launch_bounds__(256, 1) fused_forward_kernel(FusedFwdArgs a) {
               sq1[j] += __shfl_xor_sync(0xffffffffu, sq1[j], o);
             }
             if (g8 == 0) {
-              const int col = wn * TN * 8 + j * 8 + 2 * t4;
-              part[wm * PT + col] = sq0[j];
-              part[wm * PT + col + 1] = sq1[j];
+              const int col = j * 8 + 2 * t4;
+              part[wm * GC + col] = sq0[j];
+              part[wm * GC + col + 1] = sq1[j];
             }
             sq0[j] = 0.0; sq1[j] = 0.0;
           }
-          __syncthreads();
-          if (tid < PT) {
+          group_sync(bar_id, GT);
+          if (tg < GC) {
             double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < WM; ++w) s += part[w * PT + tid];
-            colsum[(e.kind == 0 ? 0 : 1 + e.d) * PT + tid] = s;
+            for (int w = 0; w < WM; ++w) s += part[w * GC + tg];
+            colsum[(e.kind == 0 ? 0 : 1 + e.d) * GC + tg] = s;
           }
+          group_sync(bar_id, GT);
         }
       }
     }
-    __syncthreads();
     // ---- stage 5: moments, sample, outputs ----
-    for (int idx = tid; idx < PT * a.D_out; idx += 256) {
+    for (int idx = tg; idx < GC * a.D_out; idx += GT) {
       const int c = idx / a.D_out, d = idx % a.D_out;
       const long p = p0 + c;
       if (p >= a.P) continue;
-      double mean = 0.0;
-      for (int m = 0; m < a.M; ++m) mean = fma(tile[m * LDT + c], a.qmu[m * a.D_out + d], mean);
+      double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+      const double* tc = tile + col0 + c;
+      const double* qd = a.qmu + d;
+      int m = 0;
+      for (; m + 4 <= a.M; m += 4) {
+        m0 = fma(tc[(m + 0) * LDT], qd[(m + 0) * a.D_out], m0);
+        m1 = fma(tc[(m + 1) * LDT], qd[(m + 1) * a.D_out], m1);
+        m2 = fma(tc[(m + 2) * LDT], qd[(m + 2) * a.D_out], m2);
+        m3 = fma(tc[(m + 3) * LDT], qd[(m + 3) * a.D_out], m3);
+      }
+      for (; m < a.M; ++m) m0 = fma(tc[m * LDT], qd[m * a.D_out], m0);
+      const double mean = (m0 + m1) + (m2 + m3);
       const double* x = a.Xin + (p % a.xmod) * a.D_in;
       double mf = 0.0;
       if (a.mean_kind == 1) mf = x[d];
@@ -313,7 +381,7 @@ __global__ void __launch_bounds__(256, 1) fused_forward_kernel(FusedFwdArgs a) {
         if (a.mfb) mf += a.mfb[d];
       }
       const double mu = mean + mf;
-      const double var = s2 - colsum[c] + colsum[(1 + d) * PT + c];
+      const double var = s2 - colsum[c] + colsum[(1 + d) * GC + c];
       const long s = p / a.Nc, n = p % a.Nc;
       const long xrow = s * a.N_total + a.n0 + n;
       a.Fmean[p * a.D_out + d] = mu;
@@ -330,7 +398,6 @@ __global__ void __launch_bounds__(256, 1) fused_forward_kernel(FusedFwdArgs a) {
       }
     }
   }
-  cp_async_wait<0>();
 }
 
 }  // namespace dgp
