@@ -144,6 +144,44 @@ __device__ __forceinline__ void group_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Straight-line DMMA block for one operator panel restricted to the warp's m-tiles [LO, HI): k-step outer so that only
+// TN + (HI - LO) operand registers are live and the loads of k-step kk+1 overlap the DMMAs of k-step kk.
+template <int LO, int HI, int TM, int TN, int WM, int LDT>
+__device__ __forceinline__ void panel_block(double (&c0)[TM][TN], double (&c1)[TM][TN], const double* __restrict__ pan,
+                                            const double* __restrict__ bt, int wm, int g8, int t4) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    double bv[TN], av[HI - LO > 0 ? HI - LO : 1];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) bv[j] = bt[kk * 4 * LDT + j * 8];
+#pragma unroll
+    for (int i = LO; i < HI; ++i) {
+      const int row = i * 8 * WM + wm * 8 + g8;
+      av[i - LO] = pan[row * kPanelK + (((kk ^ (row & 3)) << 2) | t4)];
+    }
+#pragma unroll
+    for (int i = LO; i < HI; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) dmma884(c0[i][j], c1[i][j], av[i - LO], bv[j]);
+  }
+}
+
+// dispatch on the active m-tile range (a prefix [0, hi) for upper operators, a suffix [lo, TM) for lower ones)
+template <int TM, int TN, int WM, int LDT>
+__device__ __forceinline__ void panel_dispatch(double (&c0)[TM][TN], double (&c1)[TM][TN], const double* pan, const double* bt,
+                                               int wm, int g8, int t4, int lo, int hi) {
+  if (lo == 0) {
+    if (hi == TM) { panel_block<0, TM, TM, TN, WM, LDT>(c0, c1, pan, bt, wm, g8, t4); return; }
+    if constexpr (TM >= 2) { if (hi == 1) { panel_block<0, 1, TM, TN, WM, LDT>(c0, c1, pan, bt, wm, g8, t4); return; } }
+    if constexpr (TM >= 3) { if (hi == 2) { panel_block<0, 2, TM, TN, WM, LDT>(c0, c1, pan, bt, wm, g8, t4); return; } }
+    if constexpr (TM >= 4) { if (hi == 3) { panel_block<0, 3, TM, TN, WM, LDT>(c0, c1, pan, bt, wm, g8, t4); return; } }
+    return;   // hi == 0
+  }
+  if constexpr (TM >= 2) { if (lo == TM - 1) { panel_block<TM - 1, TM, TM, TN, WM, LDT>(c0, c1, pan, bt, wm, g8, t4); return; } }
+  if constexpr (TM >= 3) { if (lo == TM - 2) { panel_block<TM - 2, TM, TM, TN, WM, LDT>(c0, c1, pan, bt, wm, g8, t4); return; } }
+  if constexpr (TM >= 4) { if (lo == TM - 3) { panel_block<TM - 3, TM, TM, TN, WM, LDT>(c0, c1, pan, bt, wm, g8, t4); return; } }
+}
+
 // Thread layout: WM*WN = 8 consumer warps + 1 producer warp. The WN consumer GROUPS (WM warps each) own disjoint column
 // ranges of the tile and run decoupled from each other: they share only the operator-panel ring, which the producer warp
 // fills with one bulk copy per panel (full/empty mbarriers). While one group is in per-panel bookkeeping, block-end
@@ -217,6 +255,7 @@ __global__ void __launch_bounds__(288, 1) fused_forward_kernel(FusedFwdArgs a) {
   const double s2 = a.var[0];
   int cst = 0;
   unsigned cph = 0;
+  for (int idx = tg; idx < WM * GC; idx += GT) part[idx] = 0.0;
 
   for (int tl = 0; tl < my_tiles; ++tl) {
     const long p0 = (long)(blockIdx.x + tl * gridDim.x) * PT + col0;   // first point-sample of this group's columns
@@ -228,30 +267,38 @@ __global__ void __launch_bounds__(288, 1) fused_forward_kernel(FusedFwdArgs a) {
       xs[idx] = (p < a.P) ? a.Xin[(p % a.xmod) * a.D_in + j] * (1.0 / a.ls[j]) : 0.0;
     }
     group_sync(bar_id, GT);
-    {
-      const int c = tg % GC, mg = tg / GC;
-      constexpr int MG = GT / GC;
-      const bool live = p0 + c < a.P;
-#pragma unroll 2
-      for (int m = mg; m < a.Mp; m += MG) {
-        double k = 0.0;
-        if (m < a.M && live) {
+    // one inducing row per thread (its scaled coordinates stay in registers, one global-load latency per row), loop over
+    // the group's columns; xs reads are warp-wide broadcasts
+    for (int m = tg; m < a.Mp; m += GT) {
+      double* trow = tile + m * LDT + col0;
+      if (m < a.M) {
+        constexpr int ZR = 8;   // coordinates kept in registers; wider layers re-read the rest through L1
+        double zr[ZR];
+        const double* zg = a.Zs + (long)m * a.D_in;
+#pragma unroll
+        for (int j = 0; j < ZR; ++j)
+          if (j < a.D_in) zr[j] = zg[j];
+        for (int c = 0; c < GC; ++c) {
           double r2 = 0.0;
-          const double* zr = a.Zs + (long)m * a.D_in;
-          for (int j = 0; j < a.D_in; ++j) {
-            const double t = zr[j] - xs[j * GC + c];
+#pragma unroll
+          for (int j = 0; j < ZR; ++j)
+            if (j < a.D_in) {
+              const double t = zr[j] - xs[j * GC + c];
+              r2 = fma(t, t, r2);
+            }
+          for (int j = ZR; j < a.D_in; ++j) {
+            const double t = zg[j] - xs[j * GC + c];
             r2 = fma(t, t, r2);
           }
-          k = s2 * exp(-0.5 * r2);
+          trow[c] = (p0 + c < a.P) ? s2 * exp(-0.5 * r2) : 0.0;
         }
-        tile[m * LDT + col0 + c] = k;
+      } else {
+        for (int c = 0; c < GC; ++c) trow[c] = 0.0;
       }
     }
     group_sync(bar_id, GT);
     // ---- stages 2-4: flat loop over the operator panels ----
-    double c0[TM][TN], c1[TM][TN], sq0[TN], sq1[TN];
-#pragma unroll
-    for (int j = 0; j < TN; ++j) { sq0[j] = 0.0; sq1[j] = 0.0; }
+    double c0[TM][TN], c1[TM][TN];
     PanelIter<BM> it;
     it.init(a.Mp);
     for (int q = 0; q < a.NP; ++q, it.next()) {
@@ -276,37 +323,32 @@ __global__ void __launch_bounds__(288, 1) fused_forward_kernel(FusedFwdArgs a) {
         }
       }
       const double* bt = tile + (e.k0 + t4) * LDT + col0 + g8;
-      double bv[4][TN];
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) bv[kk][j] = bt[kk * 4 * LDT + j * 8];
       const double* pan = pbuf + cst * PANEL;
       mbar_wait(full + cst, cph);           // the panel's bytes have landed
-#pragma unroll
-      for (int i = 0; i < TM; ++i) {
-        if (i >= imin && i < imax) {
-          const int row = i * 8 * WM + wm * 8 + g8;
-          const double* pr = pan + row * kPanelK + t4;
-          double av[4];
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) av[kk] = pr[(kk ^ (row & 3)) << 2];
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-            for (int j = 0; j < TN; ++j) dmma884(c0[i][j], c1[i][j], av[kk], bv[kk][j]);
-        }
-      }
+      static_assert(TM <= 4, "panel_dispatch covers TM <= 4");
+      panel_dispatch<TM, TN, WM, LDT>(c0, c1, pan, bt, wm, g8, t4, imin, imax);
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + cst);   // this warp is done with the stage
       if (++cst == STAGES) { cst = 0; cph ^= 1; }
 
       if (e.flags & kPanelLast) {
-        if (e.kind != 1) {   // column sums of squares of V / T_d
+        if (e.kind != 1) {   // column sums of squares of V / T_d: reduce over this warp's rows, accumulate in part[wm][col]
 #pragma unroll
-          for (int i = 0; i < TM; ++i)
+          for (int j = 0; j < TN; ++j) {
+            double q0 = 0.0, q1 = 0.0;
 #pragma unroll
-            for (int j = 0; j < TN; ++j) { sq0[j] = fma(c0[i][j], c0[i][j], sq0[j]); sq1[j] = fma(c1[i][j], c1[i][j], sq1[j]); }
+            for (int i = 0; i < TM; ++i) { q0 = fma(c0[i][j], c0[i][j], q0); q1 = fma(c1[i][j], c1[i][j], q1); }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+              q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+              q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+            }
+            if (g8 == 0) {
+              const int col = j * 8 + 2 * t4;
+              part[wm * GC + col] += q0;
+              part[wm * GC + col + 1] += q1;
+            }
+          }
         }
         if (e.kind != 2) {   // in-place update of the resident tile (group-local hazard: same columns, all rows)
           group_sync(bar_id, GT);   // every warp of the group has finished reading the rows this block overwrites
@@ -330,26 +372,12 @@ __global__ void __launch_bounds__(288, 1) fused_forward_kernel(FusedFwdArgs a) {
         }
         if (e.kind != 2) group_sync(bar_id, GT);   // the new rows are visible before the next block reads them
         if ((e.flags & kPanelStageEnd) && e.kind != 1) {
-          // reduce the per-thread partial sums over the 8 row lanes, then over the WM warps (fixed order)
-#pragma unroll
-          for (int j = 0; j < TN; ++j) {
-#pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
-              sq0[j] += __shfl_xor_sync(0xffffffffu, sq0[j], o);
-              sq1[j] += __shfl_xor_sync(0xffffffffu, sq1[j], o);
-            }
-            if (g8 == 0) {
-              const int col = j * 8 + 2 * t4;
-              part[wm * GC + col] = sq0[j];
-              part[wm * GC + col + 1] = sq1[j];
-            }
-            sq0[j] = 0.0; sq1[j] = 0.0;
-          }
+          // sum the WM per-warp partials in a fixed order, then clear them for the next stage
           group_sync(bar_id, GT);
           if (tg < GC) {
             double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < WM; ++w) s += part[w * GC + tg];
+            for (int w = 0; w < WM; ++w) { s += part[w * GC + tg]; part[w * GC + tg] = 0.0; }
             colsum[(e.kind == 0 ? 0 : 1 + e.d) * GC + tg] = s;
           }
           group_sync(bar_id, GT);
