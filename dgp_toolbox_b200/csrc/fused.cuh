@@ -197,7 +197,7 @@ struct FusedCfg {
   static constexpr int PANEL = BM * kPanelK;
   static constexpr int STAGES = 4;
   static size_t smem_bytes(int Mp, int D_in, int D_out) {
-    return ((size_t)Mp * LDT + (size_t)STAGES * PANEL + (size_t)D_in * PT + (size_t)(1 + D_out) * PT + (size_t)WM * PT + 2 * STAGES) * sizeof(double);
+    return ((size_t)Mp * LDT + (size_t)STAGES * PANEL + (size_t)D_in * PT + (size_t)(1 + D_out) * PT + (size_t)WM * PT + 2 * STAGES + (size_t)(Mp / BM) * (Mp / BM + 1) * (BM / kPanelK)) * sizeof(double);
   }
 };
 
@@ -213,6 +213,10 @@ __global__ void __launch_bounds__(288, 1) fused_forward_kernel(FusedFwdArgs a) {
   double* part_all = colsum_all + (1 + a.D_out) * PT;    // [WN][WM][GC]
   unsigned long long* full = reinterpret_cast<unsigned long long*>(part_all + WM * PT);   // [STAGES]
   unsigned long long* empty = full + STAGES;                                               // [STAGES]
+  // per-panel descriptors of the V pass and of one upper pass (A and every T_d share it), unpacked with a handful of
+  // integer ops per panel instead of re-deriving block / clip state each time
+  uint2* ptab = reinterpret_cast<uint2*>(empty + STAGES);                                   // [NPv + NPa]
+  const int NPv = (a.Mp / BM) * (a.Mp / BM + 1) / 2 * (BM / kPanelK), NPa = NPv;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ntiles = (int)(a.Pp / PT);   // padded tiles too: the stash planes must be fully written (zeros beyond P)
@@ -221,6 +225,29 @@ __global__ void __launch_bounds__(288, 1) fused_forward_kernel(FusedFwdArgs a) {
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid == 32) {
+    PanelIter<BM> it;
+    it.init(a.Mp);
+    for (int q = 0; q < NPv + NPa; ++q, it.next()) {
+      const PanelDesc e = it.get();
+      unsigned y = 0;
+      for (int w = 0; w < WM; ++w) {
+        int lo = 0, hi = BM / (8 * WM);
+        if (e.flags & kPanelClip) {
+          const int krel = e.k0 - e.i * BM;   // k of the panel relative to the diagonal block
+          if (e.kind == 0) {                  // lower operator: row r needs k <= r  ->  rt + 7 >= krel
+            const int num = krel - 7 - w * 8;
+            lo = num > 0 ? (num + 8 * WM - 1) / (8 * WM) : 0;
+          } else {                            // upper operator: k >= r  ->  krel + 15 >= rt
+            const int num = krel + kPanelK - 1 - w * 8;
+            hi = num >= 0 ? min(hi, num / (8 * WM) + 1) : 0;
+          }
+        }
+        y |= (unsigned)(lo | (hi << 3)) << (6 * w);
+      }
+      ptab[q] = make_uint2((unsigned)e.k0 | ((unsigned)e.i << 12) | ((unsigned)e.flags << 18), y);
+    }
   }
   __syncthreads();
 
@@ -299,28 +326,20 @@ __global__ void __launch_bounds__(288, 1) fused_forward_kernel(FusedFwdArgs a) {
     group_sync(bar_id, GT);
     // ---- stages 2-4: flat loop over the operator panels ----
     double c0[TM][TN], c1[TM][TN];
-    PanelIter<BM> it;
-    it.init(a.Mp);
-    for (int q = 0; q < a.NP; ++q, it.next()) {
-      const PanelDesc e = it.get();
+    int pass = 0, qq = 0;   // pass 0: V, 1: A, 2 + d: T_d; qq: panel index inside the pass
+    for (int q = 0; q < a.NP; ++q) {
+      const uint2 tq = ptab[(pass == 0 ? 0 : NPv) + qq];
+      PanelDesc e;
+      e.kind = pass == 0 ? 0 : (pass == 1 ? 1 : 2);
+      e.d = pass - 2;
+      e.k0 = tq.x & 0xfff; e.i = (tq.x >> 12) & 63; e.flags = (tq.x >> 18) & 15;
+      const int imin = (tq.y >> (6 * wm)) & 7, imax = (tq.y >> (6 * wm + 3)) & 7;   // this warp's active m-tiles [imin, imax)
+      if (++qq == (pass == 0 ? NPv : NPa)) { qq = 0; ++pass; }
       if (e.flags & kPanelFirst) {
 #pragma unroll
         for (int i = 0; i < TM; ++i)
 #pragma unroll
           for (int j = 0; j < TN; ++j) { c0[i][j] = 0.0; c1[i][j] = 0.0; }
-      }
-      // m-tiles of this warp that intersect the operator's triangle inside this panel: [imin, imax). The rest of the
-      // panel is zero for them, so whole (panel, m-tile) pairs are skipped with a real (warp-uniform) branch.
-      int imin = 0, imax = TM;
-      if (e.flags & kPanelClip) {
-        const int krel = e.k0 - e.i * BM;   // k of the panel relative to the diagonal block
-        if (e.kind == 0) {                  // lower operator: row r needs k <= r  ->  rt + 7 >= krel
-          const int num = krel - 7 - wm * 8;
-          imin = num > 0 ? (num + 8 * WM - 1) / (8 * WM) : 0;
-        } else {                            // upper operator: k >= r  ->  krel + 15 >= rt
-          const int num = krel + kPanelK - 1 - wm * 8;
-          imax = num >= 0 ? min(TM, num / (8 * WM) + 1) : 0;
-        }
       }
       const double* bt = tile + (e.k0 + t4) * LDT + col0 + g8;
       const double* pan = pbuf + cst * PANEL;
