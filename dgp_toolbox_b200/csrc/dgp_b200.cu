@@ -137,19 +137,28 @@ GemmArgs gargs(const double* A, long lda, const double* B, long ldb, double* C, 
   return g;
 }
 
-// largest split count <= target that keeps K / splitk a multiple of 16
+// Split-K count for a contraction over the point-samples: the count (<= 64, >= 8 k-tiles per chunk, partial tiles within
+// the scratch budget) whose CTA total fills whole waves best; ties go to the smaller count (less reduction traffic).
 constexpr size_t kSplitkPartDoubles = (size_t)96 << 20;   // 768 MB of split-K partial tiles at most
-int pick_splitk(long K, long tiles, size_t out_doubles, int target_blocks = 148 * 4) {
-  long units = K / 16;
-  long want = (target_blocks + tiles - 1) / tiles;
-  if (want < 1) want = 1;
-  if (want > 64) want = 64;
-  if ((size_t)want * out_doubles > kSplitkPartDoubles) want = (long)(kSplitkPartDoubles / out_doubles);
-  if (want < 1) want = 1;
-  if (want > units) want = units;
-  for (long s = want; s >= 1; --s)
-    if (units % s == 0) return (int)s;
-  return 1;
+int pick_splitk(dgp_ctx* c, const GemmArgs& g, bool nt) {
+  const GemmPlan p = gemm_plan(g, nt, c->num_sms);
+  const size_t out_doubles = (size_t)g.batch * g.M * g.N;
+  long smax = 64;
+  if ((size_t)smax * out_doubles > kSplitkPartDoubles) smax = (long)(kSplitkPartDoubles / out_doubles);
+  const long ktiles = g.K / 16;
+  if (smax > ktiles / 8) smax = ktiles / 8;
+  if (smax < 1) smax = 1;
+  int best = 1;
+  double best_eff = -1.0;
+  for (long s = 1; s <= smax; ++s) {
+    const long chunk = (ktiles + s - 1) / s;
+    if ((s - 1) * chunk >= ktiles) continue;   // an empty last chunk
+    const long ctas = p.tiles * s;
+    const long waves = (ctas + p.slots - 1) / p.slots;
+    const double eff = (double)ctas / (double)(waves * p.slots);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = (int)s; }
+  }
+  return best;
 }
 
 template <typename F>
@@ -467,23 +476,22 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
   }));
   LAUNCH(reduce_partials_kernel, w.D_in + 1, 256, 0, rbf_part, nb, w.D_in + 1, w.rbf_red, first_chunk ? 0 : 1);
   LAUNCH(reduce_partials_kernel, 3, 256, 0, up.part, up.nblocks, 3, w.sgv, first_chunk ? 0 : 1);
-  const long mt = Mp / 64;
   CAT(DGP_CAT_GEMM_BWD_PARAM);
   // dKu (data part) = -Wg A^T
   g = gargs(W, Pp, cl.A, Pp, w.dKu, Mp, Mp, Mp, (int)Pp);
-  g.alpha = -1.0; g.beta = beta; g.splitk = pick_splitk(Pp, mt * mt, (size_t)Mp * Mp); g.part = splitk_part;
+  g.alpha = -1.0; g.beta = beta; g.splitk = pick_splitk(c, g, true); g.part = splitk_part;
   RC(gemm(c, g, true));
   // dq_sqrt_d (data part) = tril(A diag(2 Gv_d) T_d^T)
   g = gargs(cl.A, Pp, cl.T, Pp, w.dR, Mp, Mp, Mp, (int)Pp);
   g.alpha = 2.0; g.beta = beta; g.batch = D; g.sA = 0; g.sB = (long)Mp * Pp; g.sC = (long)Mp * Mp; g.c_lower = 1;
-  g.kscale = up.GvT; g.sScale = Pp; g.splitk = pick_splitk(Pp, mt * (mt + 1) / 2 * D, (size_t)D * Mp * Mp); g.part = splitk_part;
+  g.kscale = up.GvT; g.sScale = Pp; g.splitk = pick_splitk(c, g, true); g.part = splitk_part;
   RC(gemm(c, g, true));
   // dq_mu (data part) = A Gm ;  H = Gbar [X, 1]
   g = gargs(cl.A, Pp, up.GmPad, 32, w.dqmu, 32, Mp, 32, (int)Pp);
-  g.beta = beta; g.splitk = pick_splitk(Pp, mt, (size_t)Mp * 32); g.part = splitk_part;
+  g.beta = beta; g.splitk = pick_splitk(c, g, false); g.part = splitk_part;
   RC(gemm(c, g, false));
   g = gargs(Gbar, Pp, XaugPad, 32, w.H, 32, Mp, 32, (int)Pp);
-  g.beta = beta; g.splitk = pick_splitk(Pp, mt, (size_t)Mp * 32); g.part = splitk_part;
+  g.beta = beta; g.splitk = pick_splitk(c, g, false); g.part = splitk_part;
   RC(gemm(c, g, false));
   return DGP_OK;
 }

@@ -68,8 +68,10 @@ __global__ void __launch_bounds__(WM* WN * 32) gemm_kernel(GemmArgs g) {
   const int m0 = mt * BM, n0 = nt * BN;
   if (g.c_lower && n0 >= m0 + BM) return;
 
-  const int kchunk = g.K / g.splitk;
-  int kbeg = split * kchunk, kend = kbeg + kchunk;
+  // split-K: chunks of whole k-tiles, the last one may be shorter (any split count works, so the launcher can pick the
+  // count that fills whole waves of CTAs)
+  const int kchunk = ((g.K / BK + g.splitk - 1) / g.splitk) * BK;
+  int kbeg = min(split * kchunk, g.K), kend = min(kbeg + kchunk, g.K);
   if (g.a_tri == 1) kend = min(kend, m0 + BM);
   if (g.a_tri == 2) kbeg = max(kbeg, (m0 / BK) * BK);
   int ktiles = kend > kbeg ? (kend - kbeg) / BK : 0;
@@ -233,14 +235,58 @@ inline cudaError_t gemm_launch_cfg(const GemmArgs& g, cudaStream_t st) {
   return e;
 }
 
+// Tile shape the launcher will use and how many CTAs of it fit on the device at once (for wave-aware split-K choices).
+struct GemmPlan { int BM, BN; long tiles; int slots; };
+
+template <int BM, int BN, int BK, int WM, int WN, bool NT, int STAGES>
+inline int gemm_ctas_per_sm() {
+  using Cfg = GemmCfg<BM, BN, BK, WM, WN, NT, STAGES>;
+  static int cached = 0;
+  if (!cached) {
+    auto kern = gemm_kernel<BM, BN, BK, WM, WN, NT, STAGES>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, Cfg::THREADS, Cfg::SMEM) != cudaSuccess || n < 1) n = 1;
+    cached = n;
+  }
+  return cached;
+}
+
+inline bool gemm_uses_big_tiles(const GemmArgs& g) {
+  return (g.M % 128 == 0) && (g.N % 128 == 0) && g.a_tri == 0 && ((long)g.M * g.N * g.batch >= 128L * 128 * 64);
+}
+
+inline GemmPlan gemm_plan(const GemmArgs& g, bool nt, int num_sms) {
+  GemmPlan p;
+  int per_sm;
+  if (g.N == 32 && !nt) { p.BM = 64; p.BN = 32; per_sm = gemm_ctas_per_sm<64, 32, 16, 2, 1, false, 3>(); }
+  else if (gemm_uses_big_tiles(g)) {
+    p.BM = 128; p.BN = 128;
+    per_sm = nt ? gemm_ctas_per_sm<128, 128, 16, 4, 4, true, 3>() : gemm_ctas_per_sm<128, 128, 16, 4, 4, false, 3>();
+  } else {
+    p.BM = 64; p.BN = 64;
+    per_sm = nt ? gemm_ctas_per_sm<64, 64, 16, 2, 2, true, 3>() : gemm_ctas_per_sm<64, 64, 16, 2, 2, false, 3>();
+  }
+  const long mt = g.M / p.BM, ntl = g.N / p.BN;
+  long tiles = mt * ntl;
+  if (g.c_lower) {
+    tiles = 0;
+    for (long i = 0; i < mt; ++i)
+      for (long j = 0; j < ntl; ++j)
+        if (j * p.BN < i * p.BM + p.BM) ++tiles;
+  }
+  p.tiles = tiles * g.batch;
+  p.slots = per_sm * num_sms;
+  return p;
+}
+
 // Picks a tile configuration. Returns cudaErrorInvalidValue when the shape is not tile-aligned.
 inline cudaError_t gemm_launch(const GemmArgs& g, bool nt, cudaStream_t st) {
-  if (g.M % 64 || g.K % 16 || g.splitk < 1 || (g.K / g.splitk) % 16 || (g.splitk > 1 && !g.part)) return cudaErrorInvalidValue;
+  if (g.M % 64 || g.K % 16 || g.splitk < 1 || (g.splitk > 1 && !g.part)) return cudaErrorInvalidValue;
   if (g.kblocks > 1 && (nt || g.splitk != 1 || g.kblk % 16 || g.kblocks * g.kblk != g.K || g.a_tri == 2)) return cudaErrorInvalidValue;
   if (g.N == 32 && !nt) return gemm_launch_cfg<64, 32, 16, 2, 1, false, 3>(g, st);
   if (g.N % 64) return cudaErrorInvalidValue;
-  bool big = (g.M % 128 == 0) && (g.N % 128 == 0) && g.a_tri == 0 && ((long)g.M * g.N * g.batch >= 128L * 128 * 64);
-  if (big) {
+  if (gemm_uses_big_tiles(g)) {
     return nt ? gemm_launch_cfg<128, 128, 16, 4, 4, true, 3>(g, st) : gemm_launch_cfg<128, 128, 16, 4, 4, false, 3>(g, st);
   }
   return nt ? gemm_launch_cfg<64, 64, 16, 2, 2, true, 3>(g, st) : gemm_launch_cfg<64, 64, 16, 2, 2, false, 3>(g, st);
