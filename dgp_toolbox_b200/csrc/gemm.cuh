@@ -11,6 +11,8 @@
 //   splitk > 1: K is cut into splitk chunks, partial tiles go to `part` and are summed in a fixed order
 //               (deterministic, no atomics) by gemm_splitk_reduce.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace dgp {
@@ -145,27 +147,34 @@ __global__ void __launch_bounds__(WM* WN * 32) gemm_kernel(GemmArgs g) {
 #pragma unroll
       for (int j = 0; j < TN; ++j) bsc[j] = g.bscale_mul * bp[j * 8];
     }
+    // Two straight-line copies of the k-tile, with and without the operand scales: a predicated-off DMUL still queues on
+    // the FP64 pipe the DMMAs use, so the unscaled products must not carry them at all.
+    auto compute = [&](auto scaled) {
+      constexpr bool SC = decltype(scaled)::value;
 #pragma unroll
-    for (int kk = 0; kk < BK / 4; ++kk) {
-      double a[TM], bb[TN];
+      for (int kk = 0; kk < BK / 4; ++kk) {
+        double a[TM], bb[TN];
 #pragma unroll
-      for (int i = 0; i < TM; ++i) a[i] = as[i * 8 * LDA + kk * 4];
-      if (Sb) {
-        double s = ss[kk * 4];
+        for (int i = 0; i < TM; ++i) a[i] = as[i * 8 * LDA + kk * 4];
+        if (SC && Sb) {
+          double s = ss[kk * 4];
 #pragma unroll
-        for (int i = 0; i < TM; ++i) a[i] *= s;
+          for (int i = 0; i < TM; ++i) a[i] *= s;
+        }
+#pragma unroll
+        for (int j = 0; j < TN; ++j) bb[j] = NT ? bs[j * 8 * LDB + kk * 4] : bs[kk * 4 * LDB + j * 8];
+        if (SC && !NT && g.bscale) {
+#pragma unroll
+          for (int j = 0; j < TN; ++j) bb[j] *= bsc[j];
+        }
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) dmma884(c0[i][j], c1[i][j], a[i], bb[j]);
       }
-#pragma unroll
-      for (int j = 0; j < TN; ++j) bb[j] = NT ? bs[j * 8 * LDB + kk * 4] : bs[kk * 4 * LDB + j * 8];
-      if (!NT && g.bscale) {
-#pragma unroll
-        for (int j = 0; j < TN; ++j) bb[j] *= bsc[j];
-      }
-#pragma unroll
-      for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) dmma884(c0[i][j], c1[i][j], a[i], bb[j]);
-    }
+    };
+    if (Sb || (!NT && g.bscale)) compute(std::true_type());
+    else compute(std::false_type());
   }
   cp_async_wait<0>();
 

@@ -11,15 +11,16 @@ cases = [  # name, nt, M, N, K, tri, clower, batch, splitk
     ("A=LinvT V     (NN tri upper)", 0, 256, P, 256, 2, 0, 1, 1),
     ("T=RpT A  x8   (NN tri upper batched)", 0, 256, P, 256, 2, 0, 8, 1),
     ("W=Kinv dA     (NN dense)", 0, 256, P, 256, 0, 0, 1, 1),
-    ("dKu=-Wg A^T   (NT, split-K)", 1, 256, 256, P, 0, 0, 1, 16),
-    ("dR=A s T^T x8 (NT c_lower, kscale, split-K)", 1, 256, 256, P, 0, 1, 8, 4),
+    ("dKu=-Wg A^T   (NT, split-K)", 1, 256, 256, P, 0, 0, 1, 27),
+    ("dR=A s T^T x8 (NT c_lower, kscale, split-K)", 1, 256, 256, P, 0, 1, 8, 11),
+    ("dR no kscale  (NT c_lower, split-K)", 1, 256, 256, P, 0, 1, 8, 11),
     ("dqmu=A Gm     (NN N=32 split-K)", 0, 256, 32, P, 0, 0, 1, 32),
 ]
 for name, nt, M, N, K, tri, clow, batch, sk in cases:
     A = torch.randn(batch, M, K, dtype=torch.float64, device="cuda")
     B = torch.randn(batch, N, K, dtype=torch.float64, device="cuda") if nt else torch.randn(batch, K, N, dtype=torch.float64, device="cuda")
     C = torch.zeros(batch, M, N, dtype=torch.float64, device="cuda")
-    ks = torch.randn(batch, K, dtype=torch.float64, device="cuda") if (nt and clow) else None
+    ks = torch.randn(batch, K, dtype=torch.float64, device="cuda") if (nt and clow and "no kscale" not in name) else None
     def run():
         ctx.call("dgp_debug_gemm", nt, M, N, K, 1.0, D._lib.ptr(A), D._lib.ptr(B), 0.0, D._lib.ptr(C), tri, clow, batch, sk, D._lib.ptr(ks))
     for _ in range(3): run()
