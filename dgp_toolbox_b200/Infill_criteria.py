@@ -36,7 +36,7 @@ class EI(Infill_criteria):
         (:43-47); otherwise mean_s max(y_min - F, 0) on propagated samples (:49-51). One C-ABI call (dgp_ei)."""
         if getattr(model, "name", None) != 'dgp':
             raise NotImplementedError("only model.name == 'dgp' is on the accelerated path")
-        X = _lib.as_device(x, model.device)
+        X = model._check_X(_lib.as_device(x, model.device))
         N, D = X.shape[0], model.layers[-1].num_outputs
         out = torch.empty((N, D), dtype=torch.float64, device=X.device)
         if N == 0:

@@ -59,6 +59,18 @@ class DGP_Base(_Module):
         keep.append(arr)
         return m, keep
 
+    def _check_X(self, X):
+        D0 = self.layers[0].feature.Z.shape[1]
+        if X.dim() != 2 or X.shape[1] != D0:
+            raise ValueError(f"X has shape {tuple(X.shape)}, the first layer expects [N, {D0}]")
+        return X
+
+    def _check_XY(self, X, Y):
+        self._check_X(X)
+        DL = self.layers[-1].num_outputs
+        if Y.dim() != 2 or tuple(Y.shape) != (X.shape[0], DL):
+            raise ValueError(f"Y has shape {tuple(Y.shape)}, expected [{X.shape[0]}, {DL}]")
+
     def _next_seed(self, seed):
         if seed is not None:
             return int(seed)
@@ -78,7 +90,7 @@ class DGP_Base(_Module):
         """dgp.py:34-63 -> (Fs, Fmeans, Fvars), lists of [S,N,D_l] tensors."""
         if full_cov:
             raise NotImplementedError("full_cov=True is out of scope of the accelerated path (SURVEY §8 f4)")
-        X = _lib.as_device(X, self.device)
+        X = self._check_X(_lib.as_device(X, self.device))
         N = X.shape[0]
         mk = lambda: [torch.empty((S, N, l.num_outputs), dtype=torch.float64, device=X.device) for l in self.layers]
         Fs, Fmeans, Fvars = mk(), mk(), mk()
@@ -94,7 +106,7 @@ class DGP_Base(_Module):
         """dgp.py:66-77: last layer's mean and variance [S,N,D_L]."""
         if full_cov:
             raise NotImplementedError("full_cov=True is out of scope of the accelerated path (SURVEY §8 f4)")
-        X = _lib.as_device(X, self.device)
+        X = self._check_X(_lib.as_device(X, self.device))
         N, L = X.shape[0], len(self.layers)
         D = self.layers[-1].num_outputs
         Fmean = torch.empty((S, N, D), dtype=torch.float64, device=X.device)
@@ -126,7 +138,10 @@ class DGP_Base(_Module):
         X, Y = data
         X = _lib.as_device(X, self.device)
         Y = _lib.as_device(Y, self.device)
+        self._check_XY(X, Y)
         N, S = X.shape[0], self.num_samples
+        if N == 0:
+            raise ValueError("empty minibatch")
         m, keep = self._model_desc()
         n = int(_lib.lib.dgp_grad_size(C.byref(m))) if want_grad else 3
         if out is None:
@@ -141,6 +156,7 @@ class DGP_Base(_Module):
         """dgp_elbo_grad_host: HOST numpy in, HOST numpy out; the host<->device copies are part of the call."""
         X_host = np.ascontiguousarray(X_host, dtype=np.float64)
         Y_host = np.ascontiguousarray(Y_host, dtype=np.float64)
+        self._check_XY(torch.from_numpy(X_host), torch.from_numpy(Y_host))
         m, keep = self._model_desc()
         n = int(_lib.lib.dgp_grad_size(C.byref(m))) if want_grad else 3
         if out_host is None:
@@ -202,7 +218,7 @@ class DGP_Base(_Module):
 
     def predict_moments(self, Xnew, num_samples, add_lik_var=True, zs=None, seed=None):
         """Mixture moments over the S samples reduced on the device (dgp.py:362-366; Infill_criteria.py:39-41)."""
-        X = _lib.as_device(Xnew, self.device)
+        X = self._check_X(_lib.as_device(Xnew, self.device))
         N, D = X.shape[0], self.layers[-1].num_outputs
         mean = torch.empty((N, D), dtype=torch.float64, device=X.device)
         var = torch.empty_like(mean)
@@ -213,6 +229,10 @@ class DGP_Base(_Module):
         _lib.get_context(X.device).call("dgp_predict_moments", C.byref(m), _lib.ptr(X), N, num_samples, zp, self._next_seed(seed), 0,
                                         1 if add_lik_var else 0, _lib.ptr(mean), _lib.ptr(var))
         return mean, var
+
+    def predict(self, Xnew, num_samples, zs=None, seed=None):
+        """dgp.py:362-366 (DGP.predict: mixture moments of predict_y), reduced on the device."""
+        return self.predict_moments(Xnew, num_samples, add_lik_var=True, zs=zs, seed=seed)
 
     # ------------------------------------------------------------------ optimisers (callers of the hot path, SURVEY §8 f1)
     def _adam_state(self, params):
@@ -261,6 +281,3 @@ class DGP(DGP_Base):
             layer.q_sqrt.assign(layer.q_sqrt.value * 1e-3)
         DGP_Base.optimize_adam(self, self.data, iterations, lr, beta_1, beta_2, epsilon, messages)
 
-    def predict(self, Xnew, num_samples, zs=None, seed=None):
-        """dgp.py:362-366 (mixture moments of predict_y), reduced on the device."""
-        return self.predict_moments(Xnew, num_samples, add_lik_var=True, zs=zs, seed=seed)

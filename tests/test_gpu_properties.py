@@ -112,8 +112,10 @@ def test_empty_inputs_and_error_behaviour():
         model.propagate(np.zeros((4, 8)), full_cov=True)
     with pytest.raises(NotImplementedError):
         D.SVGP_Layer(D.RBF(lengthscales=[1.0]), np.zeros((4, 1)), 1, D.Zero(), white=True)
-    with pytest.raises(D._lib.DGPError):      # input width does not match the first layer
+    with pytest.raises(ValueError):           # Y width does not match the last layer
         model.elbo_flat((np.zeros((4, 8)), np.zeros((4, 3))))
+    with pytest.raises(ValueError):           # X width does not match the first layer
+        model.propagate(np.zeros((4, 5)))
     bad = D.SVGP_Layer(D.RBF(lengthscales=[1.0], variance=1.0), np.linspace(0, 1, 5)[:, None], 1, D.Zero())
     bad.kern.variance.assign(-1.0)            # Kuu + jitter I is no longer positive definite
     with pytest.raises(D._lib.DGPError):
