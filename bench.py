@@ -147,6 +147,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import dgp_toolbox_b200 as D
     from dgp_toolbox_b200.distributed import ShardedELBO
@@ -270,7 +272,7 @@ def main():
         val, dt, cores = cpu_reference_throughput(cfg, args.nb_cpu, 3, 1)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"N_b={args.nb_cpu} points x S={S} samples, 3 steps after 1 warm-up ({dt:.2f} s/step)"}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

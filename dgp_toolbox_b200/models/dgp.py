@@ -260,6 +260,63 @@ class DGP_Base(_Module):
             if step % messages == 0:
                 print(f"ELBO: {(flat[0] - flat[1]).item()}")
 
+    def natgrad_step(self, data, gamma, variational_params, scale=1.0, seed=None, zs=None):
+        """One GPflow NaturalGradient(gamma).minimize(-ELBO, var_list=[(q_mu, q_sqrt), ...]) step with the default XiNat
+        parameterisation (dgp.py:188,218,312,343): theta <- theta - gamma * d(-ELBO)/d eta with natural parameters
+        theta = (S^-1 mu, -S^-1/2) and expectation parameters eta = (mu, S + mu mu^T), S = q_sqrt q_sqrt^T, per output column.
+        The ELBO gradient comes from one dgp_elbo_grad call; the O(D_out M^3) re-parameterisation is host-side glue
+        (torch.linalg on the device), like the optimiser math of the reference."""
+        flat = self.elbo_flat(data, want_grad=True, scale=scale, seed=seed, zs=zs)
+        grads = self.unpack_grads(flat)
+        for q_mu, q_sqrt in variational_params:
+            mu = q_mu.value                                    # [M, D]
+            R = torch.tril(q_sqrt.value)                       # [D, M, M]
+            Gmu = -grads[q_mu]                                 # d loss / d mu, loss = -ELBO
+            GR = -torch.tril(grads[q_sqrt])                    # d loss / d R
+            # Cholesky adjoint: dS = R^-T sym(Phi(R^T GR)) R^-1, Phi = lower triangle with halved diagonal
+            P = torch.tril(R.transpose(1, 2) @ GR)
+            P = P - 0.5 * torch.diag_embed(torch.diagonal(P, dim1=1, dim2=2))
+            P = 0.5 * (P + P.transpose(1, 2))
+            tmp = torch.linalg.solve_triangular(R.transpose(1, 2), P, upper=True)                  # R^-T P
+            dS = torch.linalg.solve_triangular(R.transpose(1, 2), tmp.transpose(1, 2), upper=True).transpose(1, 2)  # (R^-T tmp^T)^T = tmp R^-1
+            mu_c = mu.T.unsqueeze(-1)                          # [D, M, 1]
+            d_eta1 = Gmu.T.unsqueeze(-1) - 2.0 * dS @ mu_c     # eta2 = S + mu mu^T  =>  S = eta2 - eta1 eta1^T
+            d_eta2 = dS
+            Sinv = torch.cholesky_inverse(R)                   # S^-1
+            theta1 = Sinv @ mu_c - gamma * d_eta1
+            theta2 = -0.5 * Sinv - gamma * d_eta2
+            S_new = torch.linalg.inv(-2.0 * theta2)
+            S_new = 0.5 * (S_new + S_new.transpose(1, 2))
+            q_mu.assign((S_new @ theta1).squeeze(-1).T.contiguous())
+            q_sqrt.assign(torch.linalg.cholesky(S_new))
+        return flat[0] - flat[1]
+
+    def optimize_nat_adam(self, data, iterations1=100, iterations2=5000, lr_adam=0.01, lr_gamma=0.01, beta_1=0.9, beta_2=0.999,
+                          epsilon=1e-07, ng_all=True, messages=100):
+        """dgp.py:155-220: part 1 Adam on the kernel / inducing-input / likelihood parameters with q fixed; part 2 alternates
+        one Adam step with one natural-gradient step on the (q_mu, q_sqrt) pairs (all layers, or the last one only)."""
+        nat_layers = self.layers if ng_all else self.layers[-1:]
+        for layer in nat_layers:
+            gpflow.set_trainable(layer.q_mu, False)
+            gpflow.set_trainable(layer.q_sqrt, False)
+        variational_params = [(layer.q_mu, layer.q_sqrt) for layer in nat_layers]
+        params = self.trainable_parameters
+        state = self._adam_state(params)
+        t = 0
+        for step in range(iterations1):
+            flat = self.elbo_flat(data, want_grad=True)
+            t += 1
+            self._adam_step(params, self.unpack_grads(flat), state, t, lr_adam, beta_1, beta_2, epsilon)
+            if step % messages == 0:
+                print(f"ELBO: {(flat[0] - flat[1]).item()}")
+        for step in range(iterations2):
+            flat = self.elbo_flat(data, want_grad=True)
+            t += 1
+            self._adam_step(params, self.unpack_grads(flat), state, t, lr_adam, beta_1, beta_2, epsilon)
+            self.natgrad_step(data, lr_gamma, variational_params)
+            if step % messages == 0:
+                print(f"ELBO: {(flat[0] - flat[1]).item()}")
+
     def number_parameters(self, trainable=True):
         """dgp.py:348-360."""
         ps = self.trainable_parameters if trainable else self.parameters
@@ -280,4 +337,12 @@ class DGP(DGP_Base):
         for layer in self.layers[:-1]:
             layer.q_sqrt.assign(layer.q_sqrt.value * 1e-3)
         DGP_Base.optimize_adam(self, self.data, iterations, lr, beta_1, beta_2, epsilon, messages)
+
+    def optimize_nat_adam(self, iterations1=100, iterations2=5000, lr_adam=0.01, lr_gamma=0.01, beta_1=0.9, beta_2=0.999,
+                          epsilon=1e-07, ng_all=True, messages=100):
+        """dgp.py:281-345: as DGP_Base.optimize_nat_adam on self.data after the hidden layers' q_sqrt *= 1e-3 (:323-324)."""
+        for layer in self.layers[:-1]:
+            layer.q_sqrt.assign(layer.q_sqrt.value * 1e-3)
+        DGP_Base.optimize_nat_adam(self, self.data, iterations1, iterations2, lr_adam, lr_gamma, beta_1, beta_2, epsilon,
+                                   ng_all, messages)
 

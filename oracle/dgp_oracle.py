@@ -420,6 +420,44 @@ def ehvi_exact(m0, v0, m1, v1, ynd0, ynd1):
 
 
 # --------------------------------------------------------------------------------------
+# GPflow NaturalGradient (XiNat) step on (q_mu, q_sqrt) pairs — models/dgp.py:188,218,312,343
+# --------------------------------------------------------------------------------------
+def natgrad_step(model: OModel, X, Y, zs, gamma: float, layer_indices: Sequence[int], scale: float = 1.0):
+    """theta <- theta - gamma * d(-ELBO)/d eta, theta = (S^-1 mu, -S^-1/2), eta = (mu, S + mu mu^T), S = q_sqrt q_sqrt^T
+    (GPflow 2.0 optimizers/natgrad.py, default XiNat). The gradient w.r.t. the expectation parameters is taken by autograd
+    through eta -> (mu, chol(eta2 - mu mu^T)), i.e. by a different route than the product's closed-form Cholesky adjoint.
+    Returns the new [(q_mu, q_sqrt)] for the given layers (the model is not modified)."""
+    etas = []
+    layers = []
+    for i, l in enumerate(model.layers):
+        if i in layer_indices:
+            mu = l.q_mu.detach().T.unsqueeze(-1)                                   # [D, M, 1]
+            S = l.q_sqrt.detach() @ l.q_sqrt.detach().transpose(1, 2)
+            e1 = mu.clone().requires_grad_(True)
+            e2 = (S + mu @ mu.transpose(1, 2)).clone().requires_grad_(True)
+            etas.append((i, e1, e2))
+            Sfrom = e2 - e1 @ e1.transpose(1, 2)
+            layers.append(OLayer(Z=l.Z, lengthscales=l.lengthscales, variance=l.variance, q_mu=e1.squeeze(-1).T,
+                                 q_sqrt=torch.linalg.cholesky(Sfrom), mean_kind=l.mean_kind, mf_W=l.mf_W, mf_b=l.mf_b, white=l.white))
+        else:
+            layers.append(l)
+    loss = -elbo(OModel(layers=layers, lik_var=model.lik_var, num_samples=model.num_samples), X, Y, zs, scale)
+    loss.backward()
+    out = []
+    for i, e1, e2 in etas:
+        l = model.layers[i]
+        mu = l.q_mu.detach().T.unsqueeze(-1)
+        Sinv = torch.cholesky_inverse(l.q_sqrt.detach())
+        g2 = 0.5 * (e2.grad + e2.grad.transpose(1, 2))
+        theta1 = Sinv @ mu - gamma * e1.grad
+        theta2 = -0.5 * Sinv - gamma * g2
+        S_new = torch.linalg.inv(-2.0 * theta2)
+        S_new = 0.5 * (S_new + S_new.transpose(1, 2))
+        out.append(((S_new @ theta1).squeeze(-1).T.contiguous(), torch.linalg.cholesky(S_new)))
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # parameter transforms kept host-side (SURVEY §9)
 # --------------------------------------------------------------------------------------
 def softplus(u):

@@ -209,3 +209,16 @@ def test_gemm_engine_against_torch():
         if clow:
             ref, out = torch.tril(ref), torch.tril(out)
         assert rel_err(out, ref) < 1e-12, (nt, M, N, K, tri, clow, batch, splitk)
+
+
+def test_natural_gradient_step_matches_oracle():
+    """GPflow NaturalGradient (XiNat) step on every layer's (q_mu, q_sqrt): product (closed-form Cholesky adjoint on the CUDA
+    gradients) against the oracle (autograd through the expectation parameters)."""
+    prob, om, pm = both_models(3, [3], 24, 40, 4)
+    zs = oracle_zs(om, 40, 4, 9)
+    X, Y = torch.as_tensor(prob["X"]), torch.as_tensor(prob["Y"])
+    new = O.natgrad_step(om, X, Y, zs, 1e-3, [0, 1])
+    pm.natgrad_step((prob["X"], prob["Y"]), 1e-3, [(l.q_mu, l.q_sqrt) for l in pm.layers], zs=zs)
+    for (mu_o, R_o), layer in zip(new, pm.layers):
+        assert rel_err(layer.q_mu.value, mu_o) < 1e-8
+        assert rel_err(layer.q_sqrt.value, R_o) < 1e-8

@@ -172,3 +172,17 @@ def test_ei_and_ehvi_basic():
     imp = np.mean([max(hv(list(zip(y0, y1)) + [(f0[i], f1[i])]) - base, 0.0)
                    for i in range(n)])
     assert abs(val - imp) < 0.02, (val, imp)
+
+
+def test_oracle_natural_gradient_step():
+    """XiNat step: gamma = 0 is a no-op (theta -> (mu, S) round trip), a small gamma increases the ELBO."""
+    prob = O.synthetic_problem(3, [3], 12, 30)
+    om = O.model_from_problem(prob, 3)
+    zs = [torch.randn(3, 30, l.D_out, dtype=torch.float64, generator=torch.Generator().manual_seed(1)) for l in om.layers]
+    X, Y = torch.as_tensor(prob["X"]), torch.as_tensor(prob["Y"])
+    e0 = float(O.elbo(om, X, Y, zs))
+    for (mu, R), l in zip(O.natgrad_step(om, X, Y, zs, 0.0, [0, 1]), om.layers):
+        assert float((mu - l.q_mu).abs().max()) < 1e-12 and float((R - l.q_sqrt).abs().max()) < 1e-12
+    for (mu, R), l in zip(O.natgrad_step(om, X, Y, zs, 1e-3, [0, 1]), om.layers):
+        l.q_mu, l.q_sqrt = mu, R
+    assert float(O.elbo(om, X, Y, zs)) > e0 + 100.0
