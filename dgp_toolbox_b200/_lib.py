@@ -55,6 +55,7 @@ _SIG = {
     "dgp_launch_count": (_i64, [_vp, _i]),
     "dgp_set_profiling": (C.c_int, [_vp, _i]),
     "dgp_set_fused": (C.c_int, [_vp, _i]),
+    "dgp_set_share_first_layer": (C.c_int, [_vp, _i]),
     "dgp_get_profile": (C.c_int, [_vp, _vp, _vp, _i]),
     "dgp_philox_normal": (C.c_int, [_vp, _u64, _i, _i64, _i64, _i, _i64, _vp]),
     "dgp_kernel_K": (C.c_int, [_vp, _i, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
@@ -123,6 +124,9 @@ class Context:
         cnt = (C.c_int64 * n)()
         lib.dgp_get_profile(self.h, C.cast(ms, _vp), C.cast(cnt, _vp), 1 if reset else 0)
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_CATEGORIES)}
+
+    def set_share_first_layer(self, on: bool):
+        lib.dgp_set_share_first_layer(self.h, 1 if on else 0)
 
     def set_fused(self, on: bool):
         lib.dgp_set_fused(self.h, 1 if on else 0)

@@ -35,6 +35,7 @@ struct dgp_ctx {
   size_t h_pinned_bytes = 0;
   double* d_stage = nullptr;            // device side of that staging (outside the arena, which may be re-grown)
   size_t d_stage_bytes = 0;
+  bool share_first_layer = true;        // evaluate the first layer once per point instead of once per point-sample
   bool use_fused = true;                // fused conditional kernel (fused.cuh); false -> unfused GEMM pipeline
   long launches = 0;                    // kernels launched since the last dgp_reset_launch_count
   // optional per-category device timing (CUDA event pairs around every launch, on the ctx's stream)
@@ -525,6 +526,8 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
   for (int l = 1; l < nl; ++l)
     if (model->layers[l].D_in != model->layers[l - 1].D_out) { c->err = "layer widths do not chain"; return DGP_ERR_ARG; }
   const bool grad = o.want_grad;
+  // first-layer sharing (see expand_first_layer_kernel): needs a later layer to consume the per-sample draws
+  const bool share0 = c->share_first_layer && S > 1 && nl >= 2;
   if ((grad || o.want_elbo) && model->layers[nl - 1].D_out != o.Dy) { c->err = "Y width must equal the last layer's D_out"; return DGP_ERR_ARG; }
   if ((grad || o.want_elbo) && !model->lik_variance) { c->err = "lik_variance is null"; return DGP_ERR_ARG; }
 
@@ -612,6 +615,21 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
       else { cl.Xin = cls[l - 1].F; cl.xmod = P; }
       const bool last = l == nl - 1;
       const bool need_sample = !last || o.need_last_sample || (o.io.Fs && o.io.Fs[l]);
+      if (l == 0 && share0) {
+        // the first layer sees the same X row for every sample: one conditional per point, expanded to the S samples
+        RC(forward_layer(c, d, lw[0], cl, tmp, grad, Tshared, 0, Nc, 1, Nc, 0, seed, n_offset, ChunkIO(), false));
+        CAT(DGP_CAT_MOMENTS);
+        ExpandArgs e;
+        memset(&e, 0, sizeof(e));
+        e.mean0 = cl.Fmean; e.var0 = cl.Fvar; e.z_in = (o.io.zs && o.io.zs[0]) ? o.io.zs[0] : nullptr;
+        e.seed = seed; e.layer = 0; e.Nc = Nc; e.N_total = N; e.n0 = n0; e.n_offset = n_offset; e.S = S; e.D = d.D_out;
+        e.jitter = d.jitter; e.F = cl.F; e.z = cl.z;
+        e.xFmean = (o.io.Fmeans && o.io.Fmeans[0]) ? o.io.Fmeans[0] : nullptr;
+        e.xFvar = (o.io.Fvars && o.io.Fvars[0]) ? o.io.Fvars[0] : nullptr;
+        e.xF = (o.io.Fs && o.io.Fs[0]) ? o.io.Fs[0] : nullptr;
+        LAUNCH(expand_first_layer_kernel, (unsigned)((P * d.D_out + 255) / 256), 256, 0, e);
+        continue;
+      }
       RC(forward_layer(c, d, lw[l], cl, tmp, grad, Tshared, l, Nc, S, N, n0, seed, n_offset, o.io, need_sample));
     }
     const ChunkLayer& clL = cls[nl - 1];
@@ -646,6 +664,16 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
         for (int l = nl - 1; l >= 0; --l) {
           const dgp_layer_desc& d = model->layers[l];
           CAT(DGP_CAT_OTHER);
+          if (l == 0 && share0) {
+            // first-layer sharing: per-point upstream gradients = sums over the S samples, then a P = Nc adjoint
+            const long Pp0 = round_up(Nc, kTileP), nb0 = Pp0 / 128;
+            UpstreamOut uh{up.Gm, up.GvT, up.GmPad, up.gq, lik_part};
+            LAUNCH(upstream_reduce_kernel, (unsigned)nb0, 128, 0, dX_next, cls[0].z, cls[0].Fvar, Nc, S, Pp0, d.D_out, d.jitter, uh);
+            Upstream up0 = up;
+            up0.part = lik_part; up0.nblocks = nb0;
+            RC(backward_layer(c, d, lw[0], cls[0], tmp, up0, nullptr, XaugPad, rbf_part, skpart, Nc, 1, first));
+            continue;
+          }
           if (l < nl - 1) {
             // Gm = G_F, Gv = G_F z / (2 sqrt(var + jitter))                          (adjoint of utils/utils.py:40-41)
             UpstreamOut uh{up.Gm, up.GvT, up.GmPad, up.gq, lik_part};
@@ -778,6 +806,12 @@ int64_t dgp_workspace_bytes(dgp_ctx* c) { return c ? (int64_t)c->cap : 0; }
 int dgp_set_workspace_limit(dgp_ctx* c, int64_t bytes) {
   if (!c || bytes < ((int64_t)64 << 20)) return DGP_ERR_ARG;
   c->ws_limit = (size_t)bytes;
+  return DGP_OK;
+}
+
+int dgp_set_share_first_layer(dgp_ctx* c, int on) {
+  if (!c) return DGP_ERR_ARG;
+  c->share_first_layer = on != 0;
   return DGP_OK;
 }
 

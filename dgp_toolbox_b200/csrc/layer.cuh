@@ -119,6 +119,38 @@ __global__ void __launch_bounds__(128) moments_kernel(MomentsArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// First-layer sharing. The first layer's input is X tiled over the S samples (models/dgp.py:49), so its conditional is
+// the same for every sample: it is evaluated once per POINT (mean0, var0 [Nc][D]) and expanded here to the S samples,
+// where the reparameterised draw F = mean + z sqrt(var + jitter) does differ per sample (utils/utils.py:40-41).
+// ---------------------------------------------------------------------------------------------------------
+struct ExpandArgs {
+  const double* mean0; const double* var0;     // [Nc][D]
+  const double* z_in;                          // caller [S][N_total][D] or null -> Philox
+  unsigned long long seed; int layer; long Nc; long N_total; long n0; long n_offset; long S; int D;
+  double jitter;
+  double* F; double* z;                        // chunk-local [S*Nc][D]
+  double* xFmean; double* xFvar; double* xF;   // caller-visible, any may be null
+};
+
+__global__ void __launch_bounds__(256) expand_first_layer_kernel(ExpandArgs a) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.S * a.Nc * a.D) return;
+  const int d = (int)(idx % a.D);
+  const long p = idx / a.D;
+  const long s = p / a.Nc, n = p % a.Nc;
+  const double mu = a.mean0[n * a.D + d], var = a.var0[n * a.D + d];
+  const long xrow = s * a.N_total + a.n0 + n;
+  const double z = a.z_in ? a.z_in[xrow * a.D + d]
+                          : philox_normal(a.seed, (uint32_t)a.layer, (uint32_t)s, (uint32_t)(a.n0 + n + a.n_offset), (uint32_t)d);
+  const double f = mu + z * sqrt(var + a.jitter);
+  a.F[idx] = f;
+  a.z[idx] = z;
+  if (a.xFmean) a.xFmean[xrow * a.D + d] = mu;
+  if (a.xFvar) a.xFvar[xrow * a.D + d] = var;
+  if (a.xF) a.xF[xrow * a.D + d] = f;
+}
+
 // Philox draws written out for the oracle / explicit-z callers.
 __global__ void philox_normal_kernel(unsigned long long seed, int layer, long S, long N, int D, long n_offset, double* z) {
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -210,6 +242,44 @@ __global__ void __launch_bounds__(128) upstream_kernel(const double* __restrict_
     }
     for (int d = D; d < 32; ++d) o.GmPad[p * 32 + d] = 0.0;
     o.gq[p] = gq;
+  }
+  double t2 = block_sum(sgv, red);
+  if (threadIdx.x == 0) {
+    o.part[(long)blockIdx.x * 3 + 0] = 0.0;
+    o.part[(long)blockIdx.x * 3 + 1] = 0.0;
+    o.part[(long)blockIdx.x * 3 + 2] = t2;
+  }
+}
+
+// First-layer sharing, adjoint side: the per-point upstream gradients are the sums over the S samples,
+//   Gm[n] = sum_s G_F[s,n],  Gv[n] = sum_s G_F[s,n] z[s,n] / (2 sqrt(var0[n] + jitter)).
+__global__ void __launch_bounds__(128) upstream_reduce_kernel(const double* __restrict__ GF, const double* __restrict__ z,
+                                                              const double* __restrict__ var0, long Nc, long S, long Pp0, int D,
+                                                              double jitter, UpstreamOut o) {
+  __shared__ double red[32];
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  double sgv = 0.0;
+  if (n < Pp0) {
+    double gq = 0.0;
+    for (int d = 0; d < D; ++d) {
+      double gm = 0.0, gv = 0.0;
+      if (n < Nc) {
+        double gz = 0.0;
+        for (long s = 0; s < S; ++s) {
+          const double g = GF[(s * Nc + n) * D + d];
+          gm += g;
+          gz = fma(g, z[(s * Nc + n) * D + d], gz);
+        }
+        gv = gz / (2.0 * sqrt(var0[n * D + d] + jitter));
+      }
+      o.Gm[n * D + d] = gm;
+      o.GvT[(long)d * Pp0 + n] = gv;
+      o.GmPad[n * 32 + d] = gm;
+      gq -= gv;
+      sgv += gv;
+    }
+    for (int d = D; d < 32; ++d) o.GmPad[n * 32 + d] = 0.0;
+    o.gq[n] = gq;
   }
   double t2 = block_sum(sgv, red);
   if (threadIdx.x == 0) {

@@ -70,6 +70,10 @@ enum { DGP_CAT_PREP = 0,            /* Kuu build, Cholesky + inverse, KL, replic
 int dgp_set_profiling(dgp_ctx* ctx, int on);
 /* on = 0 routes the conditional through the unfused GEMM pipeline (debug / A-B measurement); default 1 */
 int dgp_set_fused(dgp_ctx* ctx, int on);
+/* The first layer's input is X tiled over the S samples (models/dgp.py:49), so its conditional (and the adjoint's contractions)
+ * are identical for every sample; on = 1 (default) evaluates them once per point and expands / reduces over S around them,
+ * on = 0 evaluates every point-sample like the reference does. Results agree to summation order. */
+int dgp_set_share_first_layer(dgp_ctx* ctx, int on);
 int dgp_get_profile(dgp_ctx* ctx, double* ms_out, int64_t* launches_out, int reset);
 
 /* kern.K(X, X2) of the GPflow SquaredExponential the reference layers hold (utils/layers.py:221,230,243):

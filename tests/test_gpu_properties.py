@@ -134,3 +134,27 @@ def test_optimize_adam_increases_elbo():
     D.DGP_Base.optimize_adam(model, model.data, iterations=150, lr=0.01, messages=10 ** 9)   # no q_sqrt rescaling (dgp.py:268)
     after = float(model.ELBO((X, Y), seed=123))
     assert after > before + 50.0, (before, after)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_first_layer_sharing_equals_per_sample_evaluation(fused):
+    """The first layer is evaluated once per point and expanded over the S samples; switching that off evaluates every
+    point-sample like the reference. Values, gradients and propagated samples must agree to summation order."""
+    import dgp_toolbox_b200 as D
+    from dgp_toolbox_b200 import synthetic
+    model, cfg = _c2_model(S=8)
+    X, Y = synthetic.minibatch(cfg["D0"], 700, 4)
+    ctx = D._lib.get_context(0)
+    ctx.set_fused(fused)
+    try:
+        a = model.elbo_flat((X, Y), want_grad=True, seed=21).clone()
+        Fa = [t.clone() for t in sum(model.propagate(X, S=8, seed=22), [])]
+        ctx.set_share_first_layer(False)
+        b = model.elbo_flat((X, Y), want_grad=True, seed=21).clone()
+        Fb = [t.clone() for t in sum(model.propagate(X, S=8, seed=22), [])]
+    finally:
+        ctx.set_share_first_layer(True)
+        ctx.set_fused(True)
+    assert float((a - b).abs().max()) <= 1e-10 * float(b.abs().max())
+    for x, y in zip(Fa, Fb):
+        assert float((x - y).abs().max()) <= 1e-11 * max(float(y.abs().max()), 1.0)
