@@ -230,18 +230,22 @@ def main():
     all_ms = sum(v[0] for v in prof.values())
     n_grad, _ = model.grad_layout()
 
-    def kernel_entry(name, cats, flops_per_ps):
+    def kernel_entry(name, cats, flops_per_ps, traffic=None):
         ms = sum(prof[k][0] for k in cats)
         n = sum(prof[k][1] for k in cats)
         ach = flops_per_ps * nb * S * args.steps / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": None, "algorithmic_flops_per_point_sample": flops_per_ps, "launches_in_region": n,
+                "traffic": traffic, "algorithmic_flops_per_point_sample": flops_per_ps, "launches_in_region": n,
                 "kernel_ms_per_step": ms / args.steps, "share_of_step": ms / all_ms if all_ms > 0 else None}
 
     fwd_cats = [k for k in ("fused_fwd", "gemm_fwd") if prof[k][0] > 0]
     k_fwd = kernel_entry("dgp::fused_forward_kernel (Kuf tile -> Lu^-1 -> Lu^-T -> q_sqrt^T contraction -> moments/sample, FP64 DMMA, "
                          "TMA bulk-copy operand ring)" if prof["fused_fwd"][0] > 0 else "dgp::gemm_kernel (forward contractions)",
-                         fwd_cats, f_fwd)
+                         fwd_cats, f_fwd,
+                         # ncu --set full capture profiles/r01c_fused_forward_ncu.txt: dram read+write 1.2027 GB for one launch over
+                         # 65 536 point-samples of an 8->8 layer (= the 18.4 KB A/T_d stash per point-sample, no re-reads), scaled
+                         # to this run's launch size
+                         traffic=(1.2027e9 / 65536) * nb * S if prof["fused_fwd"][0] > 0 and args.config == "c2" else None)
     k_bwd = kernel_entry("dgp::gemm_kernel (FP64 DMMA adjoint contractions: sum_d q_sqrt_d dT_d, Ku^-1 dA', -Wg A^T, A diag(2Gv_d) T_d^T, "
                          "A Gm, Gbar [X,1])", ["gemm_bwd_data", "gemm_bwd_param"], 2 * f_fwd)
     main, other = (k_bwd, k_fwd) if k_bwd["kernel_ms_per_step"] >= k_fwd["kernel_ms_per_step"] else (k_fwd, k_bwd)
