@@ -38,6 +38,47 @@ __global__ void ei_analytic_kernel(const double* __restrict__ mean, const double
   out[i] = -(t1 + t2);
 }
 
+// -EI and its upstream adjoints w.r.t. the last layer's per-sample moments (for d(-EI)/dx, the gradient the reference's
+// Adam-on-x acquisition search differentiates, Infill_criteria.py:79-84). With mbar = mean_s mu, vbar = mean_s(v + mu^2) - mbar^2,
+// sigma = sqrt(vbar), u = (y_min - mbar)/sigma:  d(-EI)/d mbar = Phi(u),  d(-EI)/d vbar = -phi(u) / (2 sigma), hence
+//   Gm[s] = Phi(u)/S - phi(u) (mu_s - mbar) / (sigma S),   Gv[s] = -phi(u) / (2 sigma S).
+// One thread per candidate point; chunk-local p = s * Nc + n. Gm / GvT / GmPad / gq must be zero-filled beforehand.
+__global__ void ei_upstream_kernel(const double* __restrict__ Fmean, const double* __restrict__ Fvar, long Nc, long S, long Pp, int D,
+                                   double y_min, double* __restrict__ neg_ei, double* __restrict__ Gm, double* __restrict__ GvT,
+                                   double* __restrict__ GmPad, double* __restrict__ gq) {
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= Nc) return;
+  for (int d = 0; d < D; ++d) {
+    double sm = 0.0, sq = 0.0;
+    for (long s = 0; s < S; ++s) {
+      const double m = Fmean[(s * Nc + n) * D + d], v = Fvar[(s * Nc + n) * D + d];
+      sm += m;
+      sq += v + m * m;
+    }
+    const double mbar = sm / (double)S, vbar = sq / (double)S - mbar * mbar, sig = sqrt(vbar);
+    const double u = (y_min - mbar) / sig, cdf = norm_cdf(u), pdf = norm_pdf(u);
+    neg_ei[n * D + d] = -((y_min - mbar) * cdf + vbar * (pdf / sig));
+    const double gv = -pdf / (2.0 * sig * (double)S);
+    for (long s = 0; s < S; ++s) {
+      const long p = s * Nc + n;
+      const double gm = cdf / (double)S - pdf * (Fmean[p * D + d] - mbar) / (sig * (double)S);
+      Gm[p * D + d] = gm;
+      GmPad[p * 32 + d] = gm;
+      GvT[(long)d * Pp + p] = gv;
+      gq[p] -= gv;
+    }
+  }
+}
+
+// out[n][j] = sum_s in[(s * Nc + n)][j]
+__global__ void sum_samples_kernel(const double* __restrict__ in, long Nc, long S, int D, double* __restrict__ out) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Nc * D) return;
+  double acc = 0.0;
+  for (long s = 0; s < S; ++s) acc += in[s * Nc * D + idx];
+  out[idx] = acc;
+}
+
 // -EI by Monte-Carlo: mean_s where(F - y_min < 0, y_min - F, 0)     (F [S,N,D])
 __global__ void ei_mc_kernel(const double* __restrict__ F, long S, long ND, double y_min, double* __restrict__ out) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -442,7 +442,7 @@ struct Upstream { double *Gm, *GvT, *GmPad, *gq, *part; long nblocks; };
 
 int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const ChunkLayer& cl, const Temps& tmp,
                    const Upstream& up, double* dXin, double* XaugPad, double* rbf_part, double* splitk_part, long Nc, long S,
-                   bool first_chunk) {
+                   bool first_chunk, bool params = true) {
   const long P = Nc * S, Pp = round_up(P, kTileP);
   const int Mp = w.Mp, D = w.D_out;
   const double beta = first_chunk ? 0.0 : 1.0;
@@ -475,6 +475,7 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
     LAUNCH(rbf_bwd_kernel<DM>, (unsigned)nb, 128, smem, r);
     return DGP_OK;
   }));
+  if (!params) return DGP_OK;   // input gradient only (acquisition): the contractions over the point-samples are not needed
   LAUNCH(reduce_partials_kernel, w.D_in + 1, 256, 0, rbf_part, nb, w.D_in + 1, w.rbf_red, first_chunk ? 0 : 1);
   LAUNCH(reduce_partials_kernel, 3, 256, 0, up.part, up.nblocks, 3, w.sgv, first_chunk ? 0 : 1);
   CAT(DGP_CAT_GEMM_BWD_PARAM);
@@ -507,6 +508,7 @@ struct RunOpts {
   double* pm = nullptr; double* pv = nullptr; int add_lik = 0;   // mixture moments [N][D_L]
   double* ei = nullptr; double y_min = 0.0; int ei_analytic = 1; // -EI [N][D_L]
   bool need_last_sample = false;
+  double* dx = nullptr;                                          // d sum(-EI) / dX [N][D0] (analytic EI only)
 };
 
 size_t max_splitk_part(const std::vector<LayerWs>& lw) {
@@ -526,13 +528,14 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
   for (int l = 1; l < nl; ++l)
     if (model->layers[l].D_in != model->layers[l - 1].D_out) { c->err = "layer widths do not chain"; return DGP_ERR_ARG; }
   const bool grad = o.want_grad;
+  const bool adj = grad || o.dx;   // the adjoint chain runs (needs the A / T_d stash and Ku^-1)
   // first-layer sharing (see expand_first_layer_kernel): needs a later layer to consume the per-sample draws
   const bool share0 = c->share_first_layer && S > 1 && nl >= 2;
   if ((grad || o.want_elbo) && model->layers[nl - 1].D_out != o.Dy) { c->err = "Y width must equal the last layer's D_out"; return DGP_ERR_ARG; }
   if ((grad || o.want_elbo) && !model->lik_variance) { c->err = "lik_variance is null"; return DGP_ERR_ARG; }
 
   std::vector<LayerWs> lw;
-  RC(prep_layers(c, model, lw, grad ? PREP_GRAD : (o.want_elbo ? PREP_KL : PREP_FWD)));
+  RC(prep_layers(c, model, lw, adj ? PREP_GRAD : (o.want_elbo ? PREP_KL : PREP_FWD)));
   const size_t base_used = c->used;
 
   int maxMp = 0, maxD = 1;
@@ -542,12 +545,12 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
     if (w.Mp > maxMp) maxMp = w.Mp;
     if (w.D_out > maxD) maxD = w.D_out;
     pp_doubles += 4 * (size_t)w.D_out;                              // F, Fmean, Fvar, z
-    if (grad) pp_doubles += (size_t)(1 + w.D_out) * w.Mp;            // A, T stash
+    if (adj) pp_doubles += (size_t)(1 + w.D_out) * w.Mp;             // A, T stash
   }
   pp_doubles += 3 * (size_t)maxMp;                                   // temps
-  if (!grad) pp_doubles += (size_t)maxD * maxMp;                     // shared T
-  if (grad) pp_doubles += 2 * (size_t)maxD + 32 + 1 + 32 + 2 * 32;   // Gm, GvT, GmPad, gq, XaugPad, dX ping-pong
-  size_t fixed = base_used + (grad ? max_splitk_part(lw) * sizeof(double) : 0) + ((size_t)8 << 20);
+  if (!adj) pp_doubles += (size_t)maxD * maxMp;                      // shared T
+  if (adj) pp_doubles += 2 * (size_t)maxD + 32 + 1 + 32 + 2 * 32;    // Gm, GvT, GmPad, gq, XaugPad, dX ping-pong
+  size_t fixed = base_used + (adj ? max_splitk_part(lw) * sizeof(double) : 0) + ((size_t)8 << 20);
   long Nc_max;
   {
     size_t avail = c->ws_limit > fixed ? c->ws_limit - fixed : 0;
@@ -570,7 +573,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
     cls[l].Fmean = walloc(c, (size_t)Ppmax * w.D_out);
     cls[l].Fvar = walloc(c, (size_t)Ppmax * w.D_out);
     cls[l].z = walloc(c, (size_t)Ppmax * w.D_out);
-    if (grad) {
+    if (adj) {
       cls[l].A = walloc(c, (size_t)w.Mp * Ppmax);
       cls[l].T = walloc(c, (size_t)w.D_out * w.Mp * Ppmax);
     }
@@ -579,16 +582,16 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
   tmp.t0 = walloc(c, (size_t)maxMp * Ppmax);
   tmp.t1 = walloc(c, (size_t)maxMp * Ppmax);
   tmp.t2 = walloc(c, (size_t)maxMp * Ppmax);
-  double* Tshared = grad ? nullptr : walloc(c, (size_t)maxD * maxMp * Ppmax);
+  double* Tshared = adj ? nullptr : walloc(c, (size_t)maxD * maxMp * Ppmax);
   Upstream up{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   double *XaugPad = nullptr, *dXa = nullptr, *dXb = nullptr, *rbf_part = nullptr, *skpart = nullptr, *lik_part = nullptr;
   double* acc = nullptr;   // [0] data term, [1] d/d lik variance (accumulated over chunks)
   const long nbmax = Ppmax / 128;
-  if (grad || o.want_elbo) {
+  if (adj || o.want_elbo) {
     lik_part = walloc(c, (size_t)nbmax * 3);
     acc = walloc(c, 4);
   }
-  if (grad) {
+  if (adj) {
     up.Gm = walloc(c, (size_t)Ppmax * maxD);
     up.GvT = walloc(c, (size_t)Ppmax * maxD);
     up.GmPad = walloc(c, (size_t)Ppmax * 32);
@@ -617,7 +620,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
       const bool need_sample = !last || o.need_last_sample || (o.io.Fs && o.io.Fs[l]);
       if (l == 0 && share0) {
         // the first layer sees the same X row for every sample: one conditional per point, expanded to the S samples
-        RC(forward_layer(c, d, lw[0], cl, tmp, grad, Tshared, 0, Nc, 1, Nc, 0, seed, n_offset, ChunkIO(), false));
+        RC(forward_layer(c, d, lw[0], cl, tmp, adj, Tshared, 0, Nc, 1, Nc, 0, seed, n_offset, ChunkIO(), false));
         CAT(DGP_CAT_MOMENTS);
         ExpandArgs e;
         memset(&e, 0, sizeof(e));
@@ -630,9 +633,43 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
         LAUNCH(expand_first_layer_kernel, (unsigned)((P * d.D_out + 255) / 256), 256, 0, e);
         continue;
       }
-      RC(forward_layer(c, d, lw[l], cl, tmp, grad, Tshared, l, Nc, S, N, n0, seed, n_offset, o.io, need_sample));
+      RC(forward_layer(c, d, lw[l], cl, tmp, adj, Tshared, l, Nc, S, N, n0, seed, n_offset, o.io, need_sample));
     }
     const ChunkLayer& clL = cls[nl - 1];
+    // adjoint chain over the layers, last to first; params = false stops at the input gradient (o.dx)
+    auto run_backward = [&](bool params) -> int {
+      const long nb = Pp / 128;
+      const int D0 = model->layers[0].D_in;
+      double* dX_next = dXa;
+      for (int l = nl - 1; l >= 0; --l) {
+        const dgp_layer_desc& d = model->layers[l];
+        CAT(DGP_CAT_OTHER);
+        if (l == 0 && share0) {
+          // first-layer sharing: per-point upstream gradients = sums over the S samples, then a P = Nc adjoint
+          const long Pp0 = round_up(Nc, kTileP), nb0 = Pp0 / 128;
+          UpstreamOut uh{up.Gm, up.GvT, up.GmPad, up.gq, lik_part};
+          LAUNCH(upstream_reduce_kernel, (unsigned)nb0, 128, 0, dX_next, cls[0].z, cls[0].Fvar, Nc, S, Pp0, d.D_out, d.jitter, uh);
+          Upstream up0 = up;
+          up0.part = lik_part; up0.nblocks = nb0;
+          RC(backward_layer(c, d, lw[0], cls[0], tmp, up0, o.dx ? o.dx + n0 * D0 : nullptr, XaugPad, rbf_part, skpart, Nc, 1, first, params));
+          continue;
+        }
+        if (l < nl - 1) {
+          // Gm = G_F, Gv = G_F z / (2 sqrt(var + jitter))                          (adjoint of utils/utils.py:40-41)
+          UpstreamOut uh{up.Gm, up.GvT, up.GmPad, up.gq, lik_part};
+          LAUNCH(upstream_kernel, (unsigned)nb, 128, 0, dX_next, cls[l].z, cls[l].Fvar, P, Pp, d.D_out, d.jitter, uh);
+        }
+        double* dXin = (l > 0 || o.dx) ? (dX_next == dXa ? dXb : dXa) : nullptr;
+        if (l == 0 && o.dx && S == 1) dXin = o.dx + n0 * D0;   // one sample: the per-point-sample gradient is the answer
+        RC(backward_layer(c, d, lw[l], cls[l], tmp, up, dXin, XaugPad, rbf_part, skpart, Nc, S, first, params));
+        if (l == 0 && o.dx && S > 1) {
+          CAT(DGP_CAT_OTHER);
+          LAUNCH(sum_samples_kernel, (unsigned)((Nc * D0 + 255) / 256), 256, 0, dXin, Nc, S, D0, o.dx + n0 * D0);
+        }
+        if (dXin) dX_next = dXin;
+      }
+      return DGP_OK;
+    };
     CAT(DGP_CAT_OTHER);
     // ---- prediction epilogues ----
     if (o.pm) {
@@ -640,7 +677,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
       LAUNCH(mixture_moments_kernel, (unsigned)((ND + 255) / 256), 256, 0, clL.Fmean, clL.Fvar, S, ND, model->lik_variance,
              o.add_lik, o.pm + n0 * DL, o.pv + n0 * DL);
     }
-    if (o.ei) {
+    if (o.ei && !o.dx) {
       const long ND = Nc * DL;
       if (o.ei_analytic) {
         double* m = tmp.t0;
@@ -660,30 +697,20 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
       LAUNCH(reduce_partials_kernel, 2, 256, 0, lik_part, nb, 3, acc, first ? 0 : 1);
       if (grad) {
         up.part = lik_part; up.nblocks = nb;
-        double* dX_next = dXa;
-        for (int l = nl - 1; l >= 0; --l) {
-          const dgp_layer_desc& d = model->layers[l];
-          CAT(DGP_CAT_OTHER);
-          if (l == 0 && share0) {
-            // first-layer sharing: per-point upstream gradients = sums over the S samples, then a P = Nc adjoint
-            const long Pp0 = round_up(Nc, kTileP), nb0 = Pp0 / 128;
-            UpstreamOut uh{up.Gm, up.GvT, up.GmPad, up.gq, lik_part};
-            LAUNCH(upstream_reduce_kernel, (unsigned)nb0, 128, 0, dX_next, cls[0].z, cls[0].Fvar, Nc, S, Pp0, d.D_out, d.jitter, uh);
-            Upstream up0 = up;
-            up0.part = lik_part; up0.nblocks = nb0;
-            RC(backward_layer(c, d, lw[0], cls[0], tmp, up0, nullptr, XaugPad, rbf_part, skpart, Nc, 1, first));
-            continue;
-          }
-          if (l < nl - 1) {
-            // Gm = G_F, Gv = G_F z / (2 sqrt(var + jitter))                          (adjoint of utils/utils.py:40-41)
-            UpstreamOut uh{up.Gm, up.GvT, up.GmPad, up.gq, lik_part};
-            LAUNCH(upstream_kernel, (unsigned)nb, 128, 0, dX_next, cls[l].z, cls[l].Fvar, P, Pp, d.D_out, d.jitter, uh);
-          }
-          double* dXin = (l > 0) ? (dX_next == dXa ? dXb : dXa) : nullptr;
-          RC(backward_layer(c, d, lw[l], cls[l], tmp, up, dXin, XaugPad, rbf_part, skpart, Nc, S, first));
-          if (dXin) dX_next = dXin;
-        }
+        RC(run_backward(true));
       }
+    }
+    if (o.dx) {
+      // ---- d sum(-EI) / dX: EI upstream adjoints, then the data path of the adjoint chain (no parameter contractions) ----
+      const long nb = Pp / 128;
+      CK(cudaMemsetAsync(up.Gm, 0, (size_t)Pp * DL * sizeof(double), c->stream));
+      CK(cudaMemsetAsync(up.GvT, 0, (size_t)Pp * DL * sizeof(double), c->stream));
+      CK(cudaMemsetAsync(up.GmPad, 0, (size_t)Pp * 32 * sizeof(double), c->stream));
+      CK(cudaMemsetAsync(up.gq, 0, (size_t)Pp * sizeof(double), c->stream));
+      LAUNCH(ei_upstream_kernel, (unsigned)((Nc + 127) / 128), 128, 0, clL.Fmean, clL.Fvar, Nc, S, Pp, DL, o.y_min, o.ei + n0 * DL,
+             up.Gm, up.GvT, up.GmPad, up.gq);
+      up.part = lik_part; up.nblocks = nb;
+      RC(run_backward(false));
     }
     n0 += Nc;
     first = false;
@@ -1008,6 +1035,14 @@ int dgp_ei(dgp_ctx* c, const dgp_model_desc* model, const double* X, int64_t N, 
   if (!c || !model || !X || !neg_ei) return DGP_ERR_ARG;
   RunOpts o;
   o.io.zs = zs_host; o.ei = neg_ei; o.y_min = y_min; o.ei_analytic = analytic; o.need_last_sample = !analytic;
+  return run_model_planned(c, model, X, N, S, seed, n_offset, o);
+}
+
+int dgp_ei_grad(dgp_ctx* c, const dgp_model_desc* model, const double* X, int64_t N, int64_t S, const double* const* zs_host,
+                uint64_t seed, int64_t n_offset, double y_min, double* neg_ei, double* d_neg_ei_dX) {
+  if (!c || !model || !X || !neg_ei || !d_neg_ei_dX) return DGP_ERR_ARG;
+  RunOpts o;
+  o.io.zs = zs_host; o.ei = neg_ei; o.y_min = y_min; o.ei_analytic = 1; o.dx = d_neg_ei_dX;
   return run_model_planned(c, model, X, N, S, seed, n_offset, o);
 }
 

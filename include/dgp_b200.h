@@ -129,6 +129,12 @@ int dgp_predict_moments(dgp_ctx* ctx, const dgp_model_desc* model, const double*
 int dgp_ei(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, int64_t N, int64_t S,
            const double* const* zs_host, uint64_t seed, int64_t n_offset, double y_min, int analytic, double* neg_ei);
 
+/* EI.run (analytic) together with d sum(-EI) / dX [N, D_0]: what tape.gradient(loss, x) gives the reference's Adam-on-x search
+ * (Infill_criteria.py:79-84). Runs the forward chain, the EI adjoints and the data path of the adjoint chain (no parameter
+ * contractions). */
+int dgp_ei_grad(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, int64_t N, int64_t S, const double* const* zs_host,
+                uint64_t seed, int64_t n_offset, double y_min, double* neg_ei, double* d_neg_ei_dX);
+
 /* EHVI exact 2-objective strip sum (EHVI.py:102-104,154-157) from per-objective moments [N]; ynd0/ynd1: padded
  * Pareto front (EHVI.py:90-100), n entries each, DEVICE pointers. */
 int dgp_ehvi2d(dgp_ctx* ctx, const double* m0, const double* v0, const double* m1, const double* v1, int64_t N,

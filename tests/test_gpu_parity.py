@@ -222,3 +222,20 @@ def test_natural_gradient_step_matches_oracle():
     for (mu_o, R_o), layer in zip(new, pm.layers):
         assert rel_err(layer.q_mu.value, mu_o) < 1e-8
         assert rel_err(layer.q_sqrt.value, R_o) < 1e-8
+
+
+@pytest.mark.parametrize("D0,units,M,N,S", [(4, [4], 48, 60, 8), (3, [2, 3], 30, 25, 1), (2, [], 20, 30, 5)])
+def test_ei_input_gradient_matches_oracle_autograd(D0, units, M, N, S):
+    """d sum(-EI) / dx (the gradient of the reference's Adam-on-x acquisition search, Infill_criteria.py:79-84) against
+    autograd through the oracle chain; covers first-layer sharing (S > 1, L >= 2), S = 1 and a single-layer model."""
+    import dgp_toolbox_b200 as D
+    prob, om, pm = both_models(D0, units, M, N, S)
+    zs = oracle_zs(om, N, S, 4)
+    X = torch.as_tensor(prob["X"]).clone().requires_grad_(True)
+    _, Fm_o, Fv_o = O.propagate(om.layers, X, S, zs)
+    y_min = float(prob["Y"].min())
+    neg_ei_o = O.ei_analytic(Fm_o[-1], Fv_o[-1], y_min)
+    neg_ei_o.sum().backward()
+    neg_ei, dx = D.EI(y_min, D0).run_with_grad(pm, prob["X"], num_samples=S, zs=zs)
+    assert rel_err(neg_ei, neg_ei_o.detach()) < 1e-8
+    assert rel_err(dx, X.grad) < 1e-8
