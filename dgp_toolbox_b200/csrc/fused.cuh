@@ -412,11 +412,14 @@ __global__ void __launch_bounds__(288, 1) fused_forward_kernel(FusedFwdArgs a) {
       const double* tc = tile + col0 + c;
       const double* qd = a.qmu + d;
       int m = 0;
-      for (; m + 4 <= a.M; m += 4) {
-        m0 = fma(tc[(m + 0) * LDT], qd[(m + 0) * a.D_out], m0);
-        m1 = fma(tc[(m + 1) * LDT], qd[(m + 1) * a.D_out], m1);
-        m2 = fma(tc[(m + 2) * LDT], qd[(m + 2) * a.D_out], m2);
-        m3 = fma(tc[(m + 3) * LDT], qd[(m + 3) * a.D_out], m3);
+      for (; m + 8 <= a.M; m += 8) {   // eight independent q_mu loads in flight: they come from L2 (L1 is ~12 KB here)
+        double qv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) qv[u] = qd[(m + u) * a.D_out];
+        m0 = fma(tc[(m + 0) * LDT], qv[0], m0); m1 = fma(tc[(m + 1) * LDT], qv[1], m1);
+        m2 = fma(tc[(m + 2) * LDT], qv[2], m2); m3 = fma(tc[(m + 3) * LDT], qv[3], m3);
+        m0 = fma(tc[(m + 4) * LDT], qv[4], m0); m1 = fma(tc[(m + 5) * LDT], qv[5], m1);
+        m2 = fma(tc[(m + 6) * LDT], qv[6], m2); m3 = fma(tc[(m + 7) * LDT], qv[7], m3);
       }
       for (; m < a.M; ++m) m0 = fma(tc[m * LDT], qd[m * a.D_out], m0);
       const double mean = (m0 + m1) + (m2 + m3);

@@ -144,3 +144,18 @@ def test_parameter_transforms_round_trip():
     assert np.array_equal(O.fill_triangular_inverse(L), x)
     th = np.array([1e-3, 0.5, 3.0, 40.0])
     assert np.allclose(O.softplus(O.softplus_inv(th)), th, rtol=1e-12)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference runs on host cores only (no GPU, no /root/reference) and prints the contract's JSON line."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--nb-cpu", "32"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "point-samples/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
