@@ -5,7 +5,7 @@ not been built. There is no CPU fallback.
 """
 from . import _lib  # noqa: F401  (fails loudly when the CUDA library is missing)
 from . import gpflow_shim as gpflow  # noqa: F401
-from .gpflow_shim import RBF, Gaussian, Identity, Linear, Parameter, SquaredExponential, Zero  # noqa: F401
+from .gpflow_shim import RBF, Gaussian, Identity, Linear, Matern32, Matern52, Parameter, SquaredExponential, Zero  # noqa: F401
 from .models.dgp import DGP, DGP_Base  # noqa: F401
 from .utils.layers import Layer, SVGP_Layer  # noqa: F401
 from .utils.layer_initializations import init_layers_linear  # noqa: F401

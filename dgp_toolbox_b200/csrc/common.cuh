@@ -37,6 +37,35 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
+// Stationary kernels of the layers, as functions of the scaled squared distance r2 = sum_j ((x_j - x'_j) / l_j)^2
+// (GPflow semantics; call sites dgp_dace/utils/layers.py:221,230,243 and BO/SO_BO.py:190-197,237-244):
+//   kind 0 SquaredExponential: s2 exp(-r2 / 2)
+//   kind 1 Matern32:           s2 (1 + sqrt3 r) exp(-sqrt3 r),               r = sqrt(max(r2, 1e-36))
+//   kind 2 Matern52:           s2 (1 + sqrt5 r + 5/3 r^2) exp(-sqrt5 r)
+// kernel_gfac = -2 dk/d(r2), the factor the adjoint multiplies K-bar with (for the SquaredExponential it equals k itself);
+// it is finite at r = 0 and the coordinate differences it multiplies vanish there, matching autodiff through the clamp.
+__device__ __forceinline__ void kernel_eval(int kind, double r2, double s2, double& k, double& gfac) {
+  if (kind == 0) {
+    k = s2 * exp(-0.5 * r2);
+    gfac = k;
+  } else if (kind == 1) {
+    const double a = 1.7320508075688772935;
+    const double r = sqrt(fmax(r2, 1e-36)), e = exp(-a * r);
+    k = s2 * (1.0 + a * r) * e;
+    gfac = 3.0 * s2 * e;
+  } else {
+    const double a = 2.2360679774997896964;
+    const double r = sqrt(fmax(r2, 1e-36)), e = exp(-a * r);
+    k = s2 * (1.0 + a * r + (5.0 / 3.0) * r * r) * e;
+    gfac = (5.0 / 3.0) * s2 * (1.0 + a * r) * e;
+  }
+}
+__device__ __forceinline__ double kernel_value(int kind, double r2, double s2) {
+  double k, g;
+  kernel_eval(kind, r2, s2, k, g);
+  return k;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

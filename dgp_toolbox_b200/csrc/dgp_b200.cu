@@ -179,7 +179,7 @@ int check_layer(dgp_ctx* c, const dgp_layer_desc& L) {
   }
   if (round_up(L.M, kTileM) > 768) { c->err = "M > 768 is not supported by the single-CTA Cholesky"; return DGP_ERR_UNSUPPORTED; }
   if (L.white) { c->err = "white=True layers are not implemented (reference default is white=False, dgp.py:248)"; return DGP_ERR_UNSUPPORTED; }
-  if (L.kernel_kind != 0) { c->err = "only the SquaredExponential/RBF kernel is implemented"; return DGP_ERR_UNSUPPORTED; }
+  if (L.kernel_kind < 0 || L.kernel_kind > 2) { c->err = "kernel_kind must be 0 (SquaredExponential), 1 (Matern32) or 2 (Matern52)"; return DGP_ERR_UNSUPPORTED; }
   if (L.mean_kind < 0 || L.mean_kind > 2) { c->err = "mean_kind must be 0 (Zero), 1 (Identity) or 2 (Linear)"; return DGP_ERR_ARG; }
   if (L.mean_kind == 1 && L.D_in != L.D_out) { c->err = "Identity mean function needs D_in == D_out"; return DGP_ERR_ARG; }
   if (L.mean_kind == 2 && !L.mf_W) { c->err = "Linear mean function needs mf_W"; return DGP_ERR_ARG; }
@@ -220,6 +220,8 @@ size_t fused_smem(int cfg, int Mp, int D_in, int D_out) {
 }
 
 int pick_fused_cfg(int Mp, int D_in, int D_out) {
+  static const char* force = getenv("DGP_B200_FUSED_CFG");   // experiment hook: force one configuration
+  if (force) { const int cfg = atoi(force); if (cfg >= 0 && cfg < 4 && Mp % kFusedChoices[cfg].BM == 0 && fused_smem(cfg, Mp, D_in, D_out) <= kMaxSmem) return cfg; }
   for (int cfg = 0; cfg < 4; ++cfg) {
     if (Mp % kFusedChoices[cfg].BM) continue;
     if (fused_smem(cfg, Mp, D_in, D_out) <= kMaxSmem) return cfg;
@@ -293,7 +295,7 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
     const dgp_layer_desc& d = model->layers[l];
     LayerWs& w = lw[l];
     const long mm = (long)w.Mp * w.Mp;
-    LAUNCH(kuu_build_kernel, (unsigned)((mm + 255) / 256), 256, 0, d.Z, d.lengthscales, d.variance, w.M, w.Mp, w.D_in, d.jitter, w.Ku, w.Knj);
+    LAUNCH(kuu_build_kernel, (unsigned)((mm + 255) / 256), 256, 0, d.Z, d.lengthscales, d.variance, w.M, w.Mp, w.D_in, d.jitter, w.Ku, w.Knj, d.kernel_kind);
     const long np = mm * w.D_out > (long)w.Mp * 32 ? mm * w.D_out : (long)w.Mp * 32;
     LAUNCH(pad_params_kernel, (unsigned)((np + 255) / 256), 256, 0, d.q_sqrt, d.q_mu, w.M, w.Mp, w.D_out, w.RpT, w.Rcat, w.qmuP);
   }
@@ -370,7 +372,7 @@ int forward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, ChunkLa
     FusedFwdArgs f;
     memset(&f, 0, sizeof(f));
     f.stream = w.stream; f.sched = w.sched; f.NP = w.NP; f.Zs = w.Zs; f.ls = d.lengthscales; f.var = d.variance; f.qmu = d.q_mu;
-    f.Xin = cl.Xin; f.xmod = cl.xmod; f.D_in = w.D_in; f.mfW = d.mf_W; f.mfb = d.mf_b; f.mean_kind = d.mean_kind;
+    f.Xin = cl.Xin; f.xmod = cl.xmod; f.D_in = w.D_in; f.mfW = d.mf_W; f.mfb = d.mf_b; f.mean_kind = d.mean_kind; f.kind = d.kernel_kind;
     f.z_in = (io.zs && io.zs[layer]) ? io.zs[layer] : nullptr;
     f.seed = seed; f.layer = layer; f.Nc = Nc; f.N_total = N_total; f.n0 = n0; f.n_offset = n_offset;
     f.M = w.M; f.Mp = w.Mp; f.D_out = w.D_out; f.P = P; f.Pp = Pp; f.jitter = d.jitter;
@@ -381,7 +383,8 @@ int forward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, ChunkLa
     f.stashA = stash ? cl.A : nullptr; f.stashT = stash ? cl.T : nullptr;
     const size_t smem = fused_smem(w.fcfg, w.Mp, w.D_in, w.D_out);
     const long ntiles = Pp / kFusedChoices[w.fcfg].PT;
-    const unsigned grid = (unsigned)(ntiles < c->num_sms ? ntiles : c->num_sms);
+    const long slots = (long)c->num_sms * ((w.fcfg == 3 && smem <= 112 * 1024) ? 2 : 1);   // the small configuration fits two CTAs per SM
+    const unsigned grid = (unsigned)(ntiles < slots ? ntiles : slots);
 #define FUSED_LAUNCH(BM_, PT_, WM_, WN_)                                                                                   \
     do {                                                                                                                   \
       if (!c->dry) CK(cudaFuncSetAttribute(fused_forward_kernel<BM_, PT_, WM_, WN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem)); \
@@ -402,7 +405,7 @@ int forward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, ChunkLa
   double* T = stash ? cl.T : Tshared;
   CAT(DGP_CAT_KUF);
   LAUNCH(kuf_kernel, dim3((unsigned)(Pp / kKufCols), (unsigned)(Mp / kKufRows)), 256, 0, cl.Xin, cl.xmod, d.Z, d.lengthscales,
-         d.variance, w.M, Mp, w.D_in, P, Pp, K);
+         d.variance, w.M, Mp, w.D_in, P, Pp, K, d.kernel_kind);
   CAT(DGP_CAT_GEMM_FWD);
   GemmArgs g = gargs(w.Linv, Mp, K, Pp, V, Pp, Mp, (int)Pp, Mp);    // V = Lu^-1 Kuf            (layers.py:245)
   g.a_tri = 1;
@@ -466,7 +469,7 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
   memset(&r, 0, sizeof(r));
   r.W = W; r.A = cl.A; r.gq = up.gq; r.Gbar = Gbar; r.Xin = cl.Xin; r.xmod = cl.xmod; r.Z = d.Z; r.ls = d.lengthscales;
   r.var = d.variance; r.M = w.M; r.Mp = Mp; r.D_in = w.D_in; r.P = P; r.Pp = Pp; r.Gm = up.Gm; r.D_out = D;
-  r.mean_kind = d.mean_kind; r.mfW = d.mf_W; r.dXin = dXin; r.XaugPad = XaugPad; r.part = rbf_part;
+  r.mean_kind = d.mean_kind; r.mfW = d.mf_W; r.kind = d.kernel_kind; r.dXin = dXin; r.XaugPad = XaugPad; r.part = rbf_part;
   const long nb = Pp / 128;
   const size_t smem = ((size_t)w.M * w.D_in + kMaxD + 32) * sizeof(double);
   RC(dispatch_dmax(w.D_in, [&](auto dm) -> int {
@@ -738,7 +741,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
         const long mm = (long)w.Mp * w.Mp;
         LAUNCH(dku_assemble_kernel, (unsigned)((mm + 255) / 256), 256, 0, w.dKu, w.Kinv, w.KSK, w.alpha, w.Knj, w.M, w.Mp, w.D_out,
                o.kl_weight, 1);
-        LAUNCH(kuu_bwd_kernel, w.M, 128, 0, w.dKu, d.Z, d.lengthscales, d.variance, w.M, w.Mp, w.D_in, w.dZk, w.kuu_part);
+        LAUNCH(kuu_bwd_kernel, w.M, 128, 0, w.dKu, d.Z, d.lengthscales, d.variance, w.M, w.Mp, w.D_in, w.dZk, w.kuu_part, d.kernel_kind);
         LAUNCH(reduce_partials_kernel, w.D_in + 1, 256, 0, w.kuu_part, (long)w.M, w.D_in + 1, w.kuu_red, 0);
         FinalizeArgs f;
         memset(&f, 0, sizeof(f));
@@ -888,13 +891,13 @@ int dgp_philox_normal(dgp_ctx* c, uint64_t seed, int layer, int64_t S, int64_t N
   return DGP_OK;
 }
 
-int dgp_kernel_K(dgp_ctx* c, int D, const double* lengthscales, const double* variance, const double* X, int64_t n1,
+int dgp_kernel_K(dgp_ctx* c, int kernel_kind, int D, const double* lengthscales, const double* variance, const double* X, int64_t n1,
                  const double* X2, int64_t n2, double* K_out) {
-  if (!c || !X || !X2 || !K_out || D < 1 || D > kMaxD || n1 < 1 || n2 < 1) return DGP_ERR_ARG;
+  if (!c || !X || !X2 || !K_out || D < 1 || D > kMaxD || n1 < 1 || n2 < 1 || kernel_kind < 0 || kernel_kind > 2) return DGP_ERR_ARG;
   if (n1 > 2147483647LL) return DGP_ERR_ARG;
   CK(cudaSetDevice(c->device));
   LAUNCH(kuf_kernel, dim3((unsigned)((n2 + kKufCols - 1) / kKufCols), (unsigned)((n1 + kKufRows - 1) / kKufRows)), 256, 0, X2,
-         (long)n2, X, lengthscales, variance, (int)n1, (int)n1, D, (long)n2, (long)n2, K_out);
+         (long)n2, X, lengthscales, variance, (int)n1, (int)n1, D, (long)n2, (long)n2, K_out, kernel_kind);
   return DGP_OK;
 }
 

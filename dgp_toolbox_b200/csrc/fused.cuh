@@ -104,6 +104,7 @@ struct FusedFwdArgs {
   const double* qmu;                                    // [M][D_out]
   const double* Xin; long xmod; int D_in;               // layer input
   const double* mfW; const double* mfb; int mean_kind;
+  int kind;                                             // kernel kind (common.cuh: kernel_eval)
   const double* z_in;                                   // caller [S][N_total][D_out] or null -> Philox
   unsigned long long seed; int layer; long Nc; long N_total; long n0; long n_offset;
   int M, Mp, D_out; long P, Pp;
@@ -202,7 +203,7 @@ struct FusedCfg {
 };
 
 template <int BM, int PT, int WM, int WN>
-__global__ void __launch_bounds__(288, 1) fused_forward_kernel(FusedFwdArgs a) {
+__global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_forward_kernel(FusedFwdArgs a) {
   using Cfg = FusedCfg<BM, PT, WM, WN>;
   constexpr int TM = Cfg::TM, TN = Cfg::TN, LDT = Cfg::LDT, PANEL = Cfg::PANEL, STAGES = Cfg::STAGES, GT = Cfg::GT, GC = Cfg::GC;
   extern __shared__ __align__(128) double fsmem[];
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(288, 1) fused_forward_kernel(FusedFwdArgs a) {
             const double t = zg[j] - xs[j * GC + c];
             r2 = fma(t, t, r2);
           }
-          trow[c] = (p0 + c < a.P) ? s2 * exp(-0.5 * r2) : 0.0;
+          trow[c] = (p0 + c < a.P) ? kernel_value(a.kind, r2, s2) : 0.0;
         }
       } else {
         for (int c = 0; c < GC; ++c) trow[c] = 0.0;

@@ -14,7 +14,7 @@ namespace dgp {
 constexpr int kKufCols = 128, kKufRows = 32;
 __global__ void __launch_bounds__(256) kuf_kernel(const double* __restrict__ X, long xmod, const double* __restrict__ Z,
                                                   const double* __restrict__ ls, const double* __restrict__ var, int M, int Mp,
-                                                  int D, long P, long Pp, double* __restrict__ K) {
+                                                  int D, long P, long Pp, double* __restrict__ K, int kind) {
   __shared__ double xs[kMaxD][kKufCols];
   __shared__ double zs[kKufRows][kMaxD + 1];
   __shared__ double il[kMaxD];
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) kuf_kernel(const double* __restrict__ X, 
       double t = zs[r][j] - xs[j][c];
       r2 = fma(t, t, r2);
     }
-    double k = (m0 + r < M && p < P) ? s2 * exp(-0.5 * r2) : 0.0;
+    double k = (m0 + r < M && p < P) ? kernel_value(kind, r2, s2) : 0.0;
     if (m0 + r < Mp && p < Pp) K[(long)(m0 + r) * Pp + p] = k;
   }
 }
@@ -303,6 +303,7 @@ struct RbfBwdArgs {
   const double* Xin; long xmod; const double* Z; const double* ls; const double* var;
   int M, Mp, D_in; long P, Pp;
   const double* Gm; int D_out; int mean_kind; const double* mfW;   // mean-function path
+  int kind;             // kernel kind (common.cuh: kernel_eval)
   double* dXin;         // [P][D_in] or null (layer 0)
   double* XaugPad;      // [Pp][32]: [x, 1, 0...]
   double* part;         // [blocks][D_in + 1]
@@ -338,11 +339,13 @@ __global__ void __launch_bounds__(128) rbf_bwd_kernel(RbfBwdArgs a) {
         t[j] = (zs[m * a.D_in + j] - x[j]) * il[j];
         r2 = fma(t[j], t[j], r2);
       }
-    const double k = live ? s2 * exp(-0.5 * r2) : 0.0;
-    const double gb = (w + 2.0 * am * g) * k;
+    double k = 0.0, gf = 0.0;
+    if (live) kernel_eval(a.kind, r2, s2, k, gf);
+    const double kbar = w + 2.0 * am * g;   // dELBO / dKuf[m][p]
+    const double gb = kbar * gf;            // K-bar times -2 dk/d(r2): drives dX, dZ, dl
     a.W[off] = w + am * g;
     a.Gbar[off] = gb;
-    ds2 += gb;
+    ds2 += kbar * k;                        // d/d s2 = sum K-bar K / s2
 #pragma unroll
     for (int j = 0; j < DMAX; ++j)
       if (j < a.D_in) {

@@ -9,7 +9,7 @@ namespace dgp {
 // Ku[i][j] = s2 * exp(-0.5 * sum_j ((z_i - z_j)/l)^2) + jitter * (i==j) for i,j < M; identity on the padding.
 // Knj receives the same matrix without jitter (zero on the padding) for the RBF backward of Kuu.
 __global__ void kuu_build_kernel(const double* __restrict__ Z, const double* __restrict__ ls, const double* __restrict__ var,
-                                 int M, int Mp, int D, double jitter, double* __restrict__ Ku, double* __restrict__ Knj) {
+                                 int M, int Mp, int D, double jitter, double* __restrict__ Ku, double* __restrict__ Knj, int kind) {
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)Mp * Mp) return;
   int i = (int)(idx / Mp), j = (int)(idx % Mp);
@@ -20,7 +20,7 @@ __global__ void kuu_build_kernel(const double* __restrict__ Z, const double* __r
       double t = (Z[(long)i * D + d] - Z[(long)j * D + d]) / ls[d];
       r2 = fma(t, t, r2);
     }
-    k = var[0] * exp(-0.5 * r2);
+    k = kernel_value(kind, r2, var[0]);
     kj = k + (i == j ? jitter : 0.0);
   } else {
     kj = (i == j) ? 1.0 : 0.0;

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(1024) kl_kernel(const double* __restrict__ L, 
   if (threadIdx.x == 0) kl[0] = r - 0.5 * (double)D * (double)M;
 }
 
-// dKu = dKu_data - klw * (0.5 D Kinv - 0.5 Kinv Ssum Kinv - 0.5 alpha alpha^T); Gbar = dKu o Knj (in place into dKu)
+// dKu = dKu_data - klw * (0.5 D Kinv - 0.5 Kinv Ssum Kinv - 0.5 alpha alpha^T), zero on the padding (in place)
 __global__ void dku_assemble_kernel(double* __restrict__ dKu, const double* __restrict__ Kinv, const double* __restrict__ KSK,
                                     const double* __restrict__ alpha, const double* __restrict__ Knj, int M, int Mp, int D,
                                     double klw, int have_data) {
@@ -54,23 +54,32 @@ __global__ void dku_assemble_kernel(double* __restrict__ dKu, const double* __re
     double aa = 0.0;
     for (int d = 0; d < D; ++d) aa = fma(alpha[i * 32 + d], alpha[j * 32 + d], aa);
     v = (have_data ? dKu[idx] : 0.0) - klw * (0.5 * D * Kinv[idx] - 0.5 * KSK[idx] - 0.5 * aa);
-    v *= Knj[idx];
   }
   dKu[idx] = v;
 }
 
-// RBF adjoint on Kuu, one block per inducing row a:
-//   dZ[a][j] = -sum_b (G[a][b] + G[b][a]) (z_a - z_b)_j / l_j^2 ; part[a][j] = sum_b G[a][b] (z_a - z_b)_j^2 / l_j^3 ; part[a][D] = sum_b G[a][b]/s2
+// Kernel adjoint on Kuu, one block per inducing row a, with Kbar = dKu, k and g = -2 dk/d(r2) re-evaluated per pair:
+//   dZ[a][j] = -sum_b (Kbar[a][b] + Kbar[b][a]) g_ab (z_a - z_b)_j / l_j^2 ; part[a][j] = sum_b Kbar[a][b] g_ab (z_a - z_b)_j^2 / l_j^3 ;
+//   part[a][D] = sum_b Kbar[a][b] k_ab / s2
 __global__ void __launch_bounds__(128) kuu_bwd_kernel(const double* __restrict__ G, const double* __restrict__ Z,
                                                       const double* __restrict__ ls, const double* __restrict__ var, int M, int Mp,
-                                                      int D, double* __restrict__ dZk, double* __restrict__ part) {
+                                                      int D, double* __restrict__ dZk, double* __restrict__ part, int kind) {
   __shared__ double red[32];
   const int a = blockIdx.x;
   double accz[kMaxD], accl[kMaxD], accs = 0.0;
   for (int j = 0; j < D; ++j) { accz[j] = 0.0; accl[j] = 0.0; }
+  const double s2 = var[0];
   for (int b = threadIdx.x; b < M; b += blockDim.x) {
-    const double gab = G[(long)a * Mp + b], gba = G[(long)b * Mp + a];
-    accs += gab;
+    double r2 = 0.0;
+    for (int j = 0; j < D; ++j) {
+      const double t = (Z[(long)a * D + j] - Z[(long)b * D + j]) / ls[j];
+      r2 = fma(t, t, r2);
+    }
+    double k, gf;
+    kernel_eval(kind, r2, s2, k, gf);
+    const double kab = G[(long)a * Mp + b], kba = G[(long)b * Mp + a];
+    const double gab = kab * gf, gba = kba * gf;
+    accs += kab * k;
     for (int j = 0; j < D; ++j) {
       const double il = 1.0 / ls[j];
       const double t = (Z[(long)a * D + j] - Z[(long)b * D + j]) * il;
@@ -83,7 +92,7 @@ __global__ void __launch_bounds__(128) kuu_bwd_kernel(const double* __restrict__
     double rl = block_sum(accl[j], red);
     if (threadIdx.x == 0) { dZk[(long)a * D + j] = rz; part[(long)a * (D + 1) + j] = rl; }
   }
-  double rs = block_sum(accs / var[0], red);
+  double rs = block_sum(accs / s2, red);
   if (threadIdx.x == 0) part[(long)a * (D + 1) + D] = rs;
 }
 

@@ -157,7 +157,7 @@ class SquaredExponential(_Module):
         out = torch.empty((X.shape[0], X2.shape[0]), dtype=torch.float64, device=X.device)
         ls = self.lengthscales_vector(D)
         var = self.variance.value.reshape(1)
-        ctx.call("dgp_kernel_K", D, _lib.ptr(ls), _lib.ptr(var), _lib.ptr(X), X.shape[0], _lib.ptr(X2), X2.shape[0], _lib.ptr(out))
+        ctx.call("dgp_kernel_K", self.kernel_kind, D, _lib.ptr(ls), _lib.ptr(var), _lib.ptr(X), X.shape[0], _lib.ptr(X2), X2.shape[0], _lib.ptr(out))
         return out
 
     def K_diag(self, X):
@@ -168,6 +168,22 @@ class SquaredExponential(_Module):
 
 
 RBF = SquaredExponential
+
+
+class Matern32(SquaredExponential):
+    """GPflow kernels.Matern32: variance (1 + sqrt3 r) exp(-sqrt3 r), r = sqrt(max(r2, 1e-36)) (BO/SO_BO.py:194,241)."""
+    kernel_kind = 1
+
+    def __init__(self, variance=1.0, lengthscales=1.0, active_dims=None, name=None):
+        SquaredExponential.__init__(self, variance, lengthscales, active_dims, name or "matern32")
+
+
+class Matern52(SquaredExponential):
+    """GPflow kernels.Matern52: variance (1 + sqrt5 r + 5/3 r^2) exp(-sqrt5 r) (BO/SO_BO.py:196,243)."""
+    kernel_kind = 2
+
+    def __init__(self, variance=1.0, lengthscales=1.0, active_dims=None, name=None):
+        SquaredExponential.__init__(self, variance, lengthscales, active_dims, name or "matern52")
 
 
 class Gaussian(_Module):

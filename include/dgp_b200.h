@@ -23,7 +23,7 @@ typedef struct {
   int32_t D_in, D_out, M;
   int32_t white;              /* reference `white` flag; only 0 (the reference default, dgp.py:248) is implemented */
   int32_t mean_kind;          /* 0 Zero, 1 Identity, 2 Linear (utils/layer_initializations.py:27,42,52) */
-  int32_t kernel_kind;        /* 0 SquaredExponential / RBF (ARD) */
+  int32_t kernel_kind;        /* 0 SquaredExponential / RBF, 1 Matern32, 2 Matern52 (ARD; the kernels BO/SO_BO.py:190-197,237-244 offers) */
   const double* Z;            /* [M, D_in]   feature.Z */
   const double* lengthscales; /* [D_in]      kern.lengthscales (host side broadcasts an isotropic value) */
   const double* variance;     /* [1]         kern.variance */
@@ -76,9 +76,10 @@ int dgp_set_fused(dgp_ctx* ctx, int on);
 int dgp_set_share_first_layer(dgp_ctx* ctx, int on);
 int dgp_get_profile(dgp_ctx* ctx, double* ms_out, int64_t* launches_out, int reset);
 
-/* kern.K(X, X2) of the GPflow SquaredExponential the reference layers hold (utils/layers.py:221,230,243):
- * K_out [n1, n2] = variance * exp(-0.5 * sum_j ((X[i,j] - X2[k,j]) / lengthscales[j])^2). */
-int dgp_kernel_K(dgp_ctx* ctx, int D, const double* lengthscales, const double* variance, const double* X, int64_t n1,
+/* kern.K(X, X2) of the GPflow stationary kernel the reference layers hold (utils/layers.py:221,230,243), K_out [n1, n2]:
+ * kind 0: variance * exp(-r2 / 2); 1: variance (1 + sqrt3 r) exp(-sqrt3 r); 2: variance (1 + sqrt5 r + 5/3 r^2) exp(-sqrt5 r),
+ * r2 = sum_j ((X[i,j] - X2[k,j]) / lengthscales[j])^2, r = sqrt(max(r2, 1e-36)). */
+int dgp_kernel_K(dgp_ctx* ctx, int kernel_kind, int D, const double* lengthscales, const double* variance, const double* X, int64_t n1,
                  const double* X2, int64_t n2, double* K_out);
 
 /* z[s,n,d] for one layer: the Philox-4x32-10 stream the fused path consumes when zs == NULL

@@ -57,6 +57,31 @@ def rbf_K(X, X2, lengthscales, variance):
     return variance * torch.exp(-0.5 * dist)
 
 
+def _scaled_sqdist(X, X2, lengthscales):
+    """gpflow/utilities/ops.py square_distance on inputs divided by the lengthscales (expanded form, unclamped)."""
+    Xs = X / lengthscales
+    if X2 is None:
+        sq = (Xs * Xs).sum(-1, keepdim=True)
+        return -2.0 * Xs @ Xs.T + (sq + sq.T)
+    X2s = X2 / lengthscales
+    return -2.0 * Xs @ X2s.T + ((Xs * Xs).sum(-1)[:, None] + (X2s * X2s).sum(-1)[None, :])
+
+
+def kernel_K(X, X2, lengthscales, variance, kind="rbf"):
+    """GPflow stationary kernels: SquaredExponential (K_r2), Matern32 / Matern52 (K_r with r = sqrt(max(r2, 1e-36)),
+    gpflow/kernels/stationaries.py) — the three kernels BO/SO_BO.py:190-197,237-244 offers."""
+    if kind == "rbf":
+        return rbf_K(X, X2, lengthscales, variance)
+    r = torch.sqrt(torch.clamp(_scaled_sqdist(X, X2, lengthscales), min=1e-36))
+    if kind == "matern32":
+        a = math.sqrt(3.0)
+        return variance * (1.0 + a * r) * torch.exp(-a * r)
+    if kind == "matern52":
+        a = math.sqrt(5.0)
+        return variance * (1.0 + a * r + 5.0 / 3.0 * r * r) * torch.exp(-a * r)
+    raise ValueError(kind)
+
+
 def rbf_K_diag(X, variance):
     return variance * torch.ones(X.shape[0], dtype=DTYPE)
 
@@ -76,6 +101,7 @@ class OLayer:
     mf_W: Optional[torch.Tensor] = None  # [D_in, D_out]
     mf_b: Optional[torch.Tensor] = None  # [D_out]
     white: bool = False
+    kernel_kind: str = "rbf"    # rbf | matern32 | matern52
 
     @property
     def M(self):
@@ -95,7 +121,7 @@ class OLayer:
 
 
 def make_layer(Z, lengthscales, variance, D_out, mean_kind="zero", mf_W=None, mf_b=None, white=False,
-               q_mu=None, q_sqrt=None) -> OLayer:
+               q_mu=None, q_sqrt=None, kernel_kind="rbf") -> OLayer:
     """SVGP_Layer.__init__ (utils/layers.py:181-224): q_mu = 0; q_sqrt = I, or chol(K(Z)+jitter I) when not white."""
     Z = _t(Z).clone()
     ls = _t(lengthscales).clone()
@@ -107,12 +133,12 @@ def make_layer(Z, lengthscales, variance, D_out, mean_kind="zero", mf_W=None, mf
         if white:
             q_sqrt = torch.eye(M, dtype=DTYPE)[None].repeat(D_out, 1, 1)
         else:
-            Ku = rbf_K(Z, None, ls, var)  # utils/layers.py:221
+            Ku = kernel_K(Z, None, ls, var, kernel_kind)  # utils/layers.py:221
             Lu = torch.linalg.cholesky(Ku + torch.eye(M, dtype=DTYPE) * JITTER)  # :222
             q_sqrt = Lu[None].repeat(D_out, 1, 1)  # :223
     return OLayer(Z=Z, lengthscales=ls, variance=var, q_mu=_t(q_mu).clone(), q_sqrt=_t(q_sqrt).clone(),
                   mean_kind=mean_kind, mf_W=None if mf_W is None else _t(mf_W).clone(),
-                  mf_b=None if mf_b is None else _t(mf_b).clone(), white=white)
+                  mf_b=None if mf_b is None else _t(mf_b).clone(), white=white, kernel_kind=kernel_kind)
 
 
 def mean_function(layer: OLayer, X):
@@ -135,7 +161,7 @@ def mean_function(layer: OLayer, X):
 def kuu_chol(layer: OLayer):
     """utils/layers.py:227-234."""
     M = layer.M
-    Ku = rbf_K(layer.Z, None, layer.lengthscales, layer.variance) + JITTER * torch.eye(M, dtype=DTYPE)
+    Ku = kernel_K(layer.Z, None, layer.lengthscales, layer.variance, layer.kernel_kind) + JITTER * torch.eye(M, dtype=DTYPE)
     Lu = torch.linalg.cholesky(Ku)
     return Ku, Lu
 
@@ -147,7 +173,7 @@ def conditional_ND(layer: OLayer, X):
     Ku, Lu = kuu_chol(layer)
     D_out = layer.D_out
     M = layer.M
-    Kuf = rbf_K(layer.Z, X, layer.lengthscales, layer.variance)                    # :243  [M, P]
+    Kuf = kernel_K(layer.Z, X, layer.lengthscales, layer.variance, layer.kernel_kind)   # :243  [M, P]
     A = torch.linalg.solve_triangular(Lu, Kuf, upper=False)                        # :245
     if not layer.white:
         A = torch.linalg.solve_triangular(Lu.T, A, upper=True)                     # :247
@@ -268,7 +294,7 @@ def elbo_and_grads(model: OModel, X, Y, zs, scale: float = 1.0, wrt_X: bool = Fa
         layers.append(OLayer(Z=leaves[f"layers.{i}.Z"], lengthscales=leaves[f"layers.{i}.lengthscales"],
                              variance=leaves[f"layers.{i}.variance"], q_mu=leaves[f"layers.{i}.q_mu"],
                              q_sqrt=leaves[f"layers.{i}.q_sqrt"], mean_kind=l.mean_kind, mf_W=l.mf_W, mf_b=l.mf_b,
-                             white=l.white))
+                             white=l.white, kernel_kind=l.kernel_kind))
     m2 = OModel(layers=layers, lik_var=leaves["lik_var"], num_samples=model.num_samples)
     Xl = X.detach().clone().requires_grad_(wrt_X)
     val = elbo(m2, Xl, Y, zs, scale)
@@ -438,7 +464,8 @@ def natgrad_step(model: OModel, X, Y, zs, gamma: float, layer_indices: Sequence[
             etas.append((i, e1, e2))
             Sfrom = e2 - e1 @ e1.transpose(1, 2)
             layers.append(OLayer(Z=l.Z, lengthscales=l.lengthscales, variance=l.variance, q_mu=e1.squeeze(-1).T,
-                                 q_sqrt=torch.linalg.cholesky(Sfrom), mean_kind=l.mean_kind, mf_W=l.mf_W, mf_b=l.mf_b, white=l.white))
+                                 q_sqrt=torch.linalg.cholesky(Sfrom), mean_kind=l.mean_kind, mf_W=l.mf_W, mf_b=l.mf_b, white=l.white,
+                                 kernel_kind=l.kernel_kind))
         else:
             layers.append(l)
     loss = -elbo(OModel(layers=layers, lik_var=model.lik_var, num_samples=model.num_samples), X, Y, zs, scale)
@@ -574,5 +601,5 @@ def synthetic_problem(D0, num_units, M, N, seed_shift=0, lik_var=0.1, ls_scale=1
 
 def model_from_problem(prob, num_samples) -> OModel:
     layers = [make_layer(l["Z"], l["lengthscales"], l["variance"], l["q_mu"].shape[1], l["mean_kind"], l["mf_W"],
-                         l["mf_b"], False, l["q_mu"], l["q_sqrt"]) for l in prob["layers"]]
+                         l["mf_b"], False, l["q_mu"], l["q_sqrt"], l.get("kernel", "rbf")) for l in prob["layers"]]
     return OModel(layers=layers, lik_var=_t(prob["lik_var"]).reshape(()), num_samples=num_samples)

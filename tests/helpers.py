@@ -10,7 +10,8 @@ def product_model_from_problem(prob, num_samples, seed=1234, device=None):
     import dgp_toolbox_b200 as D
     layers = []
     for l in prob["layers"]:
-        kern = D.SquaredExponential(variance=l["variance"], lengthscales=l["lengthscales"])
+        Kern = {"rbf": D.SquaredExponential, "matern32": D.Matern32, "matern52": D.Matern52}[l.get("kernel", "rbf")]
+        kern = Kern(variance=l["variance"], lengthscales=l["lengthscales"])
         if l["mean_kind"] == "zero":
             mf = D.Zero()
         elif l["mean_kind"] == "identity":
@@ -35,15 +36,18 @@ def _condition(prob, target=2e3):
             l["Z"] = (np.linspace(-2.0, 2.0, M) + 0.01 * np.sin(np.arange(M)))[:, None]
             l["lengthscales"] = np.full(1, 0.3)
         for _ in range(60):
-            Ku = O.rbf_K(torch.as_tensor(l["Z"]), None, torch.as_tensor(l["lengthscales"]), torch.tensor(float(l["variance"])))
+            Ku = O.kernel_K(torch.as_tensor(l["Z"]), None, torch.as_tensor(l["lengthscales"]), torch.tensor(float(l["variance"])),
+                            l.get("kernel", "rbf"))
             if float(torch.linalg.cond(Ku + 1e-6 * torch.eye(M, dtype=torch.float64))) <= target:
                 break
             l["lengthscales"] = l["lengthscales"] * 0.85
     return prob
 
 
-def both_models(D0, num_units, M, N, S, seed_shift=0, lik_var=0.1, condition=True):
+def both_models(D0, num_units, M, N, S, seed_shift=0, lik_var=0.1, condition=True, kernels=None):
     prob = O.synthetic_problem(D0, num_units, M, N, seed_shift=seed_shift, lik_var=lik_var)
+    for l, k in zip(prob["layers"], kernels or []):
+        l["kernel"] = k
     if condition:
         prob = _condition(prob)
     om = O.model_from_problem(prob, S)

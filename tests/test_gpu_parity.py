@@ -239,3 +239,22 @@ def test_ei_input_gradient_matches_oracle_autograd(D0, units, M, N, S):
     neg_ei, dx = D.EI(y_min, D0).run_with_grad(pm, prob["X"], num_samples=S, zs=zs)
     assert rel_err(neg_ei, neg_ei_o.detach()) < 1e-8
     assert rel_err(dx, X.grad) < 1e-8
+
+
+@pytest.mark.parametrize("kernels", [["matern32", "matern52", "rbf"], ["matern52", "matern32", "matern32"]])
+def test_matern_kernels_match_oracle(kernels, conditional_path):
+    """Matern32 / Matern52 layers (the kernel options of BO/SO_BO.py:190-197,237-244): chain, ELBO, every gradient, K()."""
+    prob, om, pm = both_models(3, [3, 2], 40, 45, 4, kernels=kernels)
+    zs = oracle_zs(om, 45, 4, 8)
+    X, Y = torch.as_tensor(prob["X"]), torch.as_tensor(prob["Y"])
+    Fs_o, Fm_o, Fv_o = O.propagate(om.layers, X, 4, zs)
+    Fs, Fm, Fv = pm.propagate(prob["X"], S=4, zs=zs)
+    for l in range(3):
+        assert rel_err(Fm[l], Fm_o[l]) < TOL and rel_err(Fv[l], Fv_o[l], scale=1.0) < TOL and rel_err(Fs[l], Fs_o[l]) < TOL
+    val_o, g_o = O.elbo_and_grads(om, X, Y, zs)
+    val, g = pm.ELBO_and_grads((prob["X"], prob["Y"]), zs=zs)
+    assert abs(float(val) - float(val_o)) <= TOL * abs(float(val_o))
+    for k, go in g_o.items():
+        assert rel_err(g[k].reshape(go.shape), go) < TOL, k
+    lo, lp = om.layers[0], pm.layers[0]
+    assert rel_err(lp.kern.K(lp.feature.Z.value, prob["X"]), O.kernel_K(lo.Z, X, lo.lengthscales, lo.variance, lo.kernel_kind)) < TOL
