@@ -70,6 +70,45 @@ __global__ void ei_upstream_kernel(const double* __restrict__ Fmean, const doubl
   }
 }
 
+// Moment-based criteria of dgp_dace/Infill_criteria.py on (mean, var) [n] (mixture moments of predict_y over the samples):
+//   kind 0  -EI(y)                      (EI.run, :43-47,52)
+//   kind 1  -(EI(y) - mean)             (WB2.run, :124-133)
+//   kind 2  EV(c) = (mean - c) Phi((mean - c)/s) + s phi((mean - c)/s)   (EV_one_constraint.run analytic, :249-257)
+//   kind 3  -(sigmoid(x[n][j]) EI(y) - mean)   -> out [n][d]            (WB2S.run, :187-198; S = 1/(1 + 1/exp(x)) elementwise in x)
+__global__ void acq_moments_kernel(int kind, const double* __restrict__ mean, const double* __restrict__ var, long n, double y,
+                                   const double* __restrict__ x, int d, double* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double m = mean[i], v = var[i], s = sqrt(v);
+  if (kind == 2) {
+    const double u = (m - y) / s;
+    out[i] = (m - y) * norm_cdf(u) + v * (norm_pdf(u) / s);
+    return;
+  }
+  const double u = (y - m) / s;
+  const double ei = (y - m) * norm_cdf(u) + v * (norm_pdf(u) / s);
+  if (kind == 0) out[i] = -ei;
+  else if (kind == 1) out[i] = -(ei - m);
+  else {
+    for (int j = 0; j < d; ++j) {
+      const double sg = 1.0 / (1.0 + 1.0 / exp(x[i * d + j]));
+      out[i * d + j] = -(sg * ei - m);
+    }
+  }
+}
+
+// Monte-Carlo expected violation: mean_s where(F - c < 0, 0, F - c)     (EV_one_constraint.run, :259-262; F [S,N,D])
+__global__ void ev_mc_kernel(const double* __restrict__ F, long S, long ND, double c, double* __restrict__ out) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ND) return;
+  double acc = 0.0;
+  for (long s = 0; s < S; ++s) {
+    const double f = F[s * ND + i];
+    acc += (f - c) < 0.0 ? 0.0 : (f - c);
+  }
+  out[i] = acc / (double)S;
+}
+
 // out[n][j] = sum_s in[(s * Nc + n)][j]
 __global__ void sum_samples_kernel(const double* __restrict__ in, long Nc, long S, int D, double* __restrict__ out) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -1049,6 +1049,21 @@ int dgp_ei_grad(dgp_ctx* c, const dgp_model_desc* model, const double* X, int64_
   return run_model_planned(c, model, X, N, S, seed, n_offset, o);
 }
 
+int dgp_acq_moments(dgp_ctx* c, int kind, const double* mean, const double* var, int64_t n, double y, const double* x, int d,
+                    double* out) {
+  if (!c || !mean || !var || !out || n < 1 || kind < 0 || kind > 3 || (kind == 3 && (!x || d < 1))) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  LAUNCH(acq_moments_kernel, (unsigned)((n + 255) / 256), 256, 0, kind, mean, var, (long)n, y, x, d, out);
+  return DGP_OK;
+}
+
+int dgp_ev_mc(dgp_ctx* c, const double* F, int64_t S, int64_t ND, double zero_c, double* out) {
+  if (!c || !F || !out || S < 1 || ND < 1) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  LAUNCH(ev_mc_kernel, (unsigned)((ND + 255) / 256), 256, 0, F, (long)S, (long)ND, zero_c, out);
+  return DGP_OK;
+}
+
 int dgp_ehvi2d(dgp_ctx* c, const double* m0, const double* v0, const double* m1, const double* v1, int64_t N, const double* ynd0,
                const double* ynd1, int n, double* out) {
   if (!c || !m0 || !v0 || !m1 || !v1 || !ynd0 || !ynd1 || !out || N < 1 || n < 2 || n > 2048) return DGP_ERR_ARG;

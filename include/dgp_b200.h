@@ -136,6 +136,14 @@ int dgp_ei(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, int64_t N
 int dgp_ei_grad(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, int64_t N, int64_t S, const double* const* zs_host,
                 uint64_t seed, int64_t n_offset, double y_min, double* neg_ei, double* d_neg_ei_dX);
 
+/* The other moment-based criteria of dgp_dace/Infill_criteria.py, evaluated on mixture moments (mean, var) [n] (DEVICE):
+ * kind 0: -EI(y) (:43-47); 1: WB2 -(EI(y) - mean) (:124-133); 2: EV_one_constraint analytic with zero_c = y (:249-257);
+ * 3: WB2S -(sigmoid(x) EI(y) - mean) with x [n, d] -> out [n, d] (:187-198). out [n] except for kind 3. */
+int dgp_acq_moments(dgp_ctx* ctx, int kind, const double* mean, const double* var, int64_t n, double y, const double* x, int d,
+                    double* out);
+/* EV_one_constraint Monte-Carlo branch (:259-262): out [ND] = mean_s max(F[s] - zero_c, 0), F [S, ND]. */
+int dgp_ev_mc(dgp_ctx* ctx, const double* F, int64_t S, int64_t ND, double zero_c, double* out);
+
 /* EHVI exact 2-objective strip sum (EHVI.py:102-104,154-157) from per-objective moments [N]; ynd0/ynd1: padded
  * Pareto front (EHVI.py:90-100), n entries each, DEVICE pointers. */
 int dgp_ehvi2d(dgp_ctx* ctx, const double* m0, const double* v0, const double* m1, const double* v1, int64_t N,

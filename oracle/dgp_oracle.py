@@ -411,6 +411,38 @@ def ei_mc(F_last, y_min):
     return -imp.mean(0)
 
 
+def _ei_from_moments(m, v, y):
+    s = torch.sqrt(v)
+    u = (y - m) / s
+    return (y - m) * _Phi(u) + v * (_phi(u) / s)
+
+
+def wb2(Ymean, Yvar, y_min):
+    """Infill_criteria.py:124-133: -(EI - mean) on predict_y mixture moments."""
+    m, v = mixture_moments(Ymean, Yvar)
+    return -(_ei_from_moments(m, v, y_min) - m)
+
+
+def wb2s(Ymean, Yvar, y_min, x):
+    """Infill_criteria.py:187-198: -(S * EI - mean), S = 1 / (1 + 1 / exp(x))."""
+    m, v = mixture_moments(Ymean, Yvar)
+    S = 1.0 / (1.0 + 1.0 / torch.exp(x))
+    return -(S * _ei_from_moments(m, v, y_min) - m)
+
+
+def ev_analytic(Ymean, Yvar, zero_c):
+    """Infill_criteria.py:249-257: Normal(-mean, sqrt(var)); t1 = (-c + mean) cdf(-c); t2 = var * pdf(-c)."""
+    m, v = mixture_moments(Ymean, Yvar)
+    s = torch.sqrt(v)
+    u = (m - zero_c) / s
+    return (m - zero_c) * _Phi(u) + v * (_phi(u) / s)
+
+
+def ev_mc(F_last, zero_c):
+    """Infill_criteria.py:259-262."""
+    return torch.where((F_last - zero_c) < 0, torch.zeros_like(F_last), F_last - zero_c).mean(0)
+
+
 def Y_ND(Y0, Y1, nadir, ideal=(0.0, 0.0)):
     """EHVI.py:90-100: pad the sorted Pareto front with nadir/ideal."""
     n = len(Y0)

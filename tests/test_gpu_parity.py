@@ -258,3 +258,27 @@ def test_matern_kernels_match_oracle(kernels, conditional_path):
         assert rel_err(g[k].reshape(go.shape), go) < TOL, k
     lo, lp = om.layers[0], pm.layers[0]
     assert rel_err(lp.kern.K(lp.feature.Z.value, prob["X"]), O.kernel_K(lo.Z, X, lo.lengthscales, lo.variance, lo.kernel_kind)) < TOL
+
+
+def test_wb2_wb2s_ev_match_oracle():
+    """The other moment-based criteria of Infill_criteria.py (WB2, WB2S, EV analytic / Monte-Carlo, EV.run_with_IC)."""
+    import dgp_toolbox_b200 as D
+    prob, om, pm = both_models(3, [3], 32, 50, 6)
+    prob2, om2, pm2 = both_models(3, [3], 32, 50, 6, seed_shift=50)
+    S, N = 6, 50
+    zs, zs2 = oracle_zs(om, N, S, 1), oracle_zs(om2, N, S, 2)
+    X = torch.as_tensor(prob["X"])
+    ym, yv = O.predict_y(om, X, S, zs)
+    y_min = float(prob["Y"].min())
+    assert rel_err(D.WB2(y_min, 3).run(pm, prob["X"], num_samples=S, zs=zs), O.wb2(ym, yv, y_min)) < 1e-8
+    assert rel_err(D.WB2S(y_min, 3).run(pm, prob["X"], num_samples=S, zs=zs), O.wb2s(ym, yv, y_min, X)) < 1e-8
+    c = 0.2
+    assert rel_err(D.EV_one_constraint(c, 3).run(pm, prob["X"], analytic=True, num_samples=S, zs=zs), O.ev_analytic(ym, yv, c)) < 1e-8
+    Fs_o, _, _ = O.propagate(om.layers, X, S, zs)
+    assert rel_err(D.EV_one_constraint(c, 3).run(pm, prob["X"], analytic=False, num_samples=S, zs=zs), O.ev_mc(Fs_o[-1], c)) < TOL
+    ym2, yv2 = O.predict_y(om2, X, S, zs2)
+    ev = D.EV([c, -0.1], 3).run([pm, pm2], prob["X"], analytic=True, num_samples=S, zs=[zs, zs2])
+    ev_o = torch.cat([O.ev_analytic(ym, yv, c), O.ev_analytic(ym2, yv2, -0.1)], 1)
+    assert rel_err(ev, ev_o) < 1e-8
+    with pytest.raises(NotImplementedError):
+        D.PoF(0.0, 3).run(pm, prob["X"])
