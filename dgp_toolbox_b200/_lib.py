@@ -50,6 +50,7 @@ _SIG = {
     "dgp_ctx_destroy": (None, [_vp]),
     "dgp_last_error": (C.c_char_p, [_vp]),
     "dgp_set_stream": (C.c_int, [_vp, _vp]),
+    "dgp_check": (C.c_int, [_vp]),
     "dgp_workspace_bytes": (_i64, [_vp]),
     "dgp_set_workspace_limit": (C.c_int, [_vp, _i64]),
     "dgp_launch_count": (_i64, [_vp, _i]),
@@ -111,6 +112,12 @@ class Context:
         rc = getattr(lib, name)(self.h, *args)
         if rc != 0:
             raise DGPError(f"{name} failed ({rc}): {lib.dgp_last_error(self.h).decode()}")
+
+    def check(self):
+        """Synchronise and raise if an asynchronous call hit a non-positive-definite Kuu."""
+        rc = lib.dgp_check(self.h)
+        if rc != 0:
+            raise DGPError(f"dgp_check ({rc}): {lib.dgp_last_error(self.h).decode()}")
 
     def launch_count(self, reset=False) -> int:
         return int(lib.dgp_launch_count(self.h, 1 if reset else 0))

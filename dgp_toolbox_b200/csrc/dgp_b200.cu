@@ -30,6 +30,7 @@ struct dgp_ctx {
   bool dry = false;
   size_t ws_limit = (size_t)24 << 30;   // chunks of the minibatch are sized to stay under this
   int num_sms = 148;
+  bool chol_configured = false;
   int* d_info = nullptr;                // Cholesky failure flag
   double* h_pinned = nullptr;           // staging for the *_host entry points
   size_t h_pinned_bytes = 0;
@@ -300,11 +301,9 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
     LAUNCH(pad_params_kernel, (unsigned)((np + 255) / 256), 256, 0, d.q_sqrt, d.q_mu, w.M, w.Mp, w.D_out, w.RpT, w.Rcat, w.qmuP);
   }
   {
-    static bool configured = false;
-    const size_t smem = chol_smem_bytes(768);
-    if (!configured) {
-      CK(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = true;
+    if (!c->chol_configured) {   // per device (= per ctx)
+      CK(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem_bytes(768)));
+      c->chol_configured = true;
     }
     LAUNCH(chol_inv_kernel, nl, kCholThreads, chol_smem_bytes(maxMp), dargs);
   }
@@ -837,6 +836,12 @@ int dgp_set_workspace_limit(dgp_ctx* c, int64_t bytes) {
   if (!c || bytes < ((int64_t)64 << 20)) return DGP_ERR_ARG;
   c->ws_limit = (size_t)bytes;
   return DGP_OK;
+}
+
+int dgp_check(dgp_ctx* c) {
+  if (!c) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  return check_chol(c);
 }
 
 int dgp_set_share_first_layer(dgp_ctx* c, int on) {

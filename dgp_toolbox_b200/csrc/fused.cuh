@@ -283,6 +283,10 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
   const double s2 = a.var[0];
   int cst = 0;
   unsigned cph = 0;
+#ifdef DGP_DEBUG_WAITCLK
+  long long wait_clk = 0;
+  const long long t_k0 = clock64();
+#endif
   for (int idx = tg; idx < WM * GC; idx += GT) part[idx] = 0.0;
 
   for (int tl = 0; tl < my_tiles; ++tl) {
@@ -344,7 +348,13 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
       }
       const double* bt = tile + (e.k0 + t4) * LDT + col0 + g8;
       const double* pan = pbuf + cst * PANEL;
+#ifdef DGP_DEBUG_WAITCLK
+      const long long t_w0 = clock64();
+#endif
       mbar_wait(full + cst, cph);           // the panel's bytes have landed
+#ifdef DGP_DEBUG_WAITCLK
+      wait_clk += clock64() - t_w0;
+#endif
       static_assert(TM <= 4, "panel_dispatch covers TM <= 4");
       panel_dispatch<TM, TN, WM, LDT>(c0, c1, pan, bt, wm, g8, t4, imin, imax);
       __syncwarp();
@@ -449,6 +459,9 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
       }
     }
   }
+#ifdef DGP_DEBUG_WAITCLK
+  if (lane == 0 && blockIdx.x < 2 && my_tiles > 10) printf("cta %d warp %d: waited %.1f%% of %lld clk for operator panels\n", blockIdx.x, warp, 100.0 * wait_clk / (double)(clock64() - t_k0), clock64() - t_k0);
+#endif
 }
 
 }  // namespace dgp

@@ -225,11 +225,13 @@ template <int BM, int BN, int BK, int WM, int WN, bool NT, int STAGES>
 inline cudaError_t gemm_launch_cfg(const GemmArgs& g, cudaStream_t st) {
   using Cfg = GemmCfg<BM, BN, BK, WM, WN, NT, STAGES>;
   auto kern = gemm_kernel<BM, BN, BK, WM, WN, NT, STAGES>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};   // the opt-in shared-memory size is a per-device function attribute
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) return e;
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   long blocks = (long)(g.M / BM) * (g.N / BN) * g.batch * g.splitk;
   kern<<<(unsigned)blocks, Cfg::THREADS, Cfg::SMEM, st>>>(g);

@@ -170,6 +170,7 @@ class DGP_Base(_Module):
     def ELBO(self, data, zs=None, seed=None):
         """dgp.py:89-100 -> 0-d tensor. The reference's minibatch scale is identically 1 (dgp.py:95-99)."""
         flat = self.elbo_flat(data, want_grad=False, zs=zs, seed=seed)
+        _lib.get_context(self.device).check()   # the value path reports a failed Cholesky; the training loop stays asynchronous
         return flat[0] - flat[1]
 
     def ELBO_closure(self, data, zs=None, seed=None):

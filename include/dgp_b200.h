@@ -48,6 +48,10 @@ void dgp_ctx_destroy(dgp_ctx* ctx);
 const char* dgp_last_error(dgp_ctx* ctx);
 int dgp_version(void);
 int dgp_set_stream(dgp_ctx* ctx, void* cuda_stream);
+/* Synchronises the ctx's stream and reports asynchronous numerical failures of the calls issued so far: DGP_ERR_NUMERIC (-4)
+ * when a Kuu + jitter I was not positive definite (the asynchronous entry points dgp_elbo_grad / dgp_predict_moments / dgp_ei*
+ * do not synchronise themselves). */
+int dgp_check(dgp_ctx* ctx);
 /* bytes of device workspace currently held by the ctx; the minibatch is processed in chunks of points sized so that the
  * workspace stays under the limit (default 24 GiB, env DGP_B200_WS_GB) */
 int64_t dgp_workspace_bytes(dgp_ctx* ctx);

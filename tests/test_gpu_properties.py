@@ -120,6 +120,11 @@ def test_empty_inputs_and_error_behaviour():
     bad.kern.variance.assign(-1.0)            # Kuu + jitter I is no longer positive definite
     with pytest.raises(D._lib.DGPError):
         bad.build_cholesky_if_needed()
+    # the asynchronous ELBO path reports the same failure through dgp_check on the value path
+    bad_model = D.DGP_Base(D.Gaussian(0.1), [bad], num_samples=2)
+    with pytest.raises(D._lib.DGPError):
+        bad_model.ELBO((np.linspace(0, 1, 7)[:, None], np.zeros((7, 1))))
+    model.ELBO((np.zeros((4, 8)), np.zeros((4, 1))))   # the flag does not stick to later calls
 
 
 def test_optimize_adam_increases_elbo():
