@@ -329,29 +329,44 @@ __global__ void __launch_bounds__(128) rbf_bwd_kernel(RbfBwdArgs a) {
   }
   const double s2 = a.var[0];
   const double g = a.gq[p];
-  for (int m = 0; m < a.M; ++m) {
-    const long off = (long)m * a.Pp + p;
-    const double w = a.W[off], am = a.A[off];
-    double r2 = 0.0, t[DMAX];
+  // rows in groups of 4 with all eight plane loads of a group issued up front: W is updated in place, so the compiler
+  // cannot hoist the next rows' loads above the stores on its own, and one row at a time is latency-bound
+  for (int m0 = 0; m0 < a.M; m0 += 4) {
+    double wv[4], av[4];
 #pragma unroll
-    for (int j = 0; j < DMAX; ++j)
-      if (j < a.D_in) {
-        t[j] = (zs[m * a.D_in + j] - x[j]) * il[j];
-        r2 = fma(t[j], t[j], r2);
-      }
-    double k = 0.0, gf = 0.0;
-    if (live) kernel_eval(a.kind, r2, s2, k, gf);
-    const double kbar = w + 2.0 * am * g;   // dELBO / dKuf[m][p]
-    const double gb = kbar * gf;            // K-bar times -2 dk/d(r2): drives dX, dZ, dl
-    a.W[off] = w + am * g;
-    a.Gbar[off] = gb;
-    ds2 += kbar * k;                        // d/d s2 = sum K-bar K / s2
+    for (int u = 0; u < 4; ++u) {
+      const long off = (long)(m0 + u) * a.Pp + p;
+      wv[u] = (m0 + u < a.M) ? a.W[off] : 0.0;
+      av[u] = (m0 + u < a.M) ? a.A[off] : 0.0;
+    }
 #pragma unroll
-    for (int j = 0; j < DMAX; ++j)
-      if (j < a.D_in) {
-        dx[j] = fma(gb * t[j], il[j], dx[j]);       // Gbar (z-x)/l^2
-        dl[j] = fma(gb * t[j] * t[j], il[j], dl[j]);  // Gbar (z-x)^2/l^3
+    for (int u = 0; u < 4; ++u) {
+      const int m = m0 + u;
+      if (m < a.M) {
+        const long off = (long)m * a.Pp + p;
+        const double w = wv[u], am = av[u];
+        double r2 = 0.0, t[DMAX];
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j)
+          if (j < a.D_in) {
+            t[j] = (zs[m * a.D_in + j] - x[j]) * il[j];
+            r2 = fma(t[j], t[j], r2);
+          }
+        double k = 0.0, gf = 0.0;
+        if (live) kernel_eval(a.kind, r2, s2, k, gf);
+        const double kbar = w + 2.0 * am * g;   // dELBO / dKuf[m][p]
+        const double gb = kbar * gf;            // K-bar times -2 dk/d(r2): drives dX, dZ, dl
+        a.W[off] = w + am * g;
+        a.Gbar[off] = gb;
+        ds2 += kbar * k;                        // d/d s2 = sum K-bar K / s2
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j)
+          if (j < a.D_in) {
+            dx[j] = fma(gb * t[j], il[j], dx[j]);       // Gbar (z-x)/l^2
+            dl[j] = fma(gb * t[j] * t[j], il[j], dl[j]);  // Gbar (z-x)^2/l^3
+          }
       }
+    }
   }
   if (p < a.Pp) {
 #pragma unroll
