@@ -36,6 +36,7 @@ struct dgp_ctx {
   size_t h_pinned_bytes = 0;
   double* d_stage = nullptr;            // device side of that staging (outside the arena, which may be re-grown)
   size_t d_stage_bytes = 0;
+  bool use_vform = true;                // forward-only calls fold q_sqrt_d^T Lu^-T once per step and skip the A pass
   bool share_first_layer = true;        // evaluate the first layer once per point instead of once per point-sample
   bool use_fused = true;                // fused conditional kernel (fused.cuh); false -> unfused GEMM pipeline
   long launches = 0;                    // kernels launched since the last dgp_reset_launch_count
@@ -204,6 +205,9 @@ struct LayerWs {
   double *Zs = nullptr, *stream = nullptr;
   PanelDesc* sched = nullptr;
   int NP = 0, fcfg = -1;   // fcfg: index into the fused configurations, -1 = not available
+  // V-form of the conditional (forward-only calls): C_d = q_sqrt_d^T Lu^-T [D][Mp][Mp] and beta = Lu^-1 q_mu [Mp][32]
+  bool vform = false;
+  double *Cmat = nullptr, *betaP = nullptr;
 };
 
 // ---- fused kernel configurations ----
@@ -230,7 +234,7 @@ int pick_fused_cfg(int Mp, int D_in, int D_out) {
   return -1;
 }
 
-std::vector<PanelDesc> build_schedule(int Mp, int BM, int D_out) {
+std::vector<PanelDesc> build_schedule(int Mp, int BM, int D_out, bool vform) {
   std::vector<PanelDesc> v;
   const int nb = Mp / BM, kpb = BM / kPanelK, kt = Mp / kPanelK;
   for (int i = nb - 1; i >= 0; --i)
@@ -239,7 +243,7 @@ std::vector<PanelDesc> build_schedule(int Mp, int BM, int D_out) {
       if ((fl & kPanelLast) && i == 0) fl |= kPanelStageEnd;
       v.push_back(PanelDesc{0, 0, i, ks * kPanelK, fl, 0});
     }
-  for (int pass = 0; pass <= D_out; ++pass)
+  for (int pass = vform ? 1 : 0; pass <= D_out; ++pass)
     for (int i = 0; i < nb; ++i)
       for (int ks = i * kpb; ks < kt; ++ks) {
         int fl = (ks == i * kpb ? kPanelFirst : 0) | (ks == kt - 1 ? kPanelLast : 0) | (ks * kPanelK < (i + 1) * BM ? kPanelClip : 0);
@@ -280,7 +284,9 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
     if (w.fcfg >= 0) {
       const int BM = kFusedChoices[w.fcfg].BM;
       const int nb = w.Mp / BM, kpb = BM / kPanelK;
-      w.NP = (2 + w.D_out) * kpb * nb * (nb + 1) / 2;
+      w.vform = c->use_vform && level == PREP_FWD;
+      w.NP = ((w.vform ? 1 : 2) + w.D_out) * kpb * nb * (nb + 1) / 2;
+      if (w.vform) { w.Cmat = walloc(c, mm * w.D_out); w.betaP = walloc(c, (size_t)w.Mp * 32); }
       w.Zs = walloc(c, (size_t)w.M * w.D_in);
       w.stream = walloc(c, (size_t)w.NP * BM * kPanelK);
       w.sched = reinterpret_cast<PanelDesc*>(walloc(c, ((size_t)w.NP * sizeof(PanelDesc) + 7) / 8));
@@ -312,12 +318,21 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
     if (w.fcfg < 0) continue;
     const dgp_layer_desc& d = model->layers[l];
     const int BM = kFusedChoices[w.fcfg].BM;
-    std::vector<PanelDesc> sch = build_schedule(w.Mp, BM, w.D_out);
+    if (w.vform) {
+      GemmArgs g = gargs(w.RpT, w.Mp, w.LinvT, w.Mp, w.Cmat, w.Mp, w.Mp, w.Mp, w.Mp);   // C_d = q_sqrt_d^T Lu^-T (upper x upper)
+      g.a_tri = 2; g.batch = w.D_out; g.sA = (long)w.Mp * w.Mp; g.sB = 0; g.sC = (long)w.Mp * w.Mp;
+      RC(gemm(c, g, false));
+      g = gargs(w.Linv, w.Mp, w.qmuP, 32, w.betaP, 32, w.Mp, 32, w.Mp);                   // beta = Lu^-1 q_mu
+      g.a_tri = 1;
+      RC(gemm(c, g, false));
+    }
+    std::vector<PanelDesc> sch = build_schedule(w.Mp, BM, w.D_out, w.vform);
     if ((int)sch.size() != w.NP) { c->err = "internal: panel schedule size mismatch"; return DGP_ERR_ARG; }
     CK(cudaMemcpyAsync(w.sched, sch.data(), sch.size() * sizeof(PanelDesc), cudaMemcpyHostToDevice, c->stream));
     LAUNCH(scale_z_kernel, (unsigned)((w.M * w.D_in + 255) / 256), 256, 0, d.Z, d.lengthscales, w.M, w.D_in, w.Zs);
-    if (BM == 128) LAUNCH(pack_stream_kernel<128>, w.NP, 256, 0, w.sched, w.Linv, w.LinvT, w.RpT, w.Mp, w.stream);
-    else LAUNCH(pack_stream_kernel<64>, w.NP, 256, 0, w.sched, w.Linv, w.LinvT, w.RpT, w.Mp, w.stream);
+    const double* tsrc = w.vform ? w.Cmat : w.RpT;   // operator of the T_d passes
+    if (BM == 128) LAUNCH(pack_stream_kernel<128>, w.NP, 256, 0, w.sched, w.Linv, w.LinvT, tsrc, w.Mp, w.stream);
+    else LAUNCH(pack_stream_kernel<64>, w.NP, 256, 0, w.sched, w.Linv, w.LinvT, tsrc, w.Mp, w.stream);
   }
   if (level >= PREP_KL) {
     for (int l = 0; l < nl; ++l) {
@@ -370,7 +385,8 @@ int forward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, ChunkLa
     CAT(DGP_CAT_FUSED_FWD);
     FusedFwdArgs f;
     memset(&f, 0, sizeof(f));
-    f.stream = w.stream; f.sched = w.sched; f.NP = w.NP; f.Zs = w.Zs; f.ls = d.lengthscales; f.var = d.variance; f.qmu = d.q_mu;
+    f.stream = w.stream; f.sched = w.sched; f.NP = w.NP; f.Zs = w.Zs; f.ls = d.lengthscales; f.var = d.variance;
+    f.vform = w.vform ? 1 : 0; f.qmu = w.vform ? w.betaP : d.q_mu; f.qmu_ld = w.vform ? 32 : w.D_out;
     f.Xin = cl.Xin; f.xmod = cl.xmod; f.D_in = w.D_in; f.mfW = d.mf_W; f.mfb = d.mf_b; f.mean_kind = d.mean_kind; f.kind = d.kernel_kind;
     f.z_in = (io.zs && io.zs[layer]) ? io.zs[layer] : nullptr;
     f.seed = seed; f.layer = layer; f.Nc = Nc; f.N_total = N_total; f.n0 = n0; f.n_offset = n_offset;
@@ -835,6 +851,12 @@ int64_t dgp_workspace_bytes(dgp_ctx* c) { return c ? (int64_t)c->cap : 0; }
 int dgp_set_workspace_limit(dgp_ctx* c, int64_t bytes) {
   if (!c || bytes < ((int64_t)64 << 20)) return DGP_ERR_ARG;
   c->ws_limit = (size_t)bytes;
+  return DGP_OK;
+}
+
+int dgp_set_vform(dgp_ctx* c, int on) {
+  if (!c) return DGP_ERR_ARG;
+  c->use_vform = on != 0;
   return DGP_OK;
 }
 

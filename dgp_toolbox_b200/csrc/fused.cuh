@@ -8,6 +8,8 @@
 //   5. mean = A^T q_mu + mf(x), var = s2 - |V|^2 + |T_d|^2, z (Philox or supplied), F = mean + z sqrt(var + jitter)
 //      written as [P][D_out]                                                     (layers.py:249,272-278; utils/utils.py:40-41)
 // Kuf, V never touch HBM; A and T_d are written to HBM only when the adjoint will need them (training stash).
+// V-form (forward-only paths): T_d = C_d V with C_d = q_sqrt_d^T Lu^-T folded once per step, mean = V^T (Lu^-1 q_mu); the A
+// pass disappears ((1 + D_out) M^2 instead of (2 + D_out) M^2 flops per point-sample, same values to rounding).
 //
 // The triangular operators (Lu^-1 lower, Lu^-T upper, q_sqrt_d^T upper) are pre-packed once per step by
 // pack_stream_kernel into ONE linear stream of [BM x 16] panels in exactly the order the tile loop consumes them, each panel
@@ -101,7 +103,8 @@ struct FusedFwdArgs {
   const double* stream; const PanelDesc* sched; int NP;
   const double* Zs;                                     // [M][D_in] inducing inputs / lengthscales
   const double* ls; const double* var;                  // [D_in], [1]
-  const double* qmu;                                    // [M][D_out]
+  const double* qmu; int qmu_ld;                        // [M][qmu_ld] weights of the mean: q_mu (ld = D_out), or beta = Lu^-1 q_mu in V-form
+  int vform;                                            // 1: skip the A pass, T_d = C_d V with C_d = q_sqrt_d^T Lu^-T packed in the stream
   const double* Xin; long xmod; int D_in;               // layer input
   const double* mfW; const double* mfb; int mean_kind;
   int kind;                                             // kernel kind (common.cuh: kernel_eval)
@@ -339,7 +342,7 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
       e.d = pass - 2;
       e.k0 = tq.x & 0xfff; e.i = (tq.x >> 12) & 63; e.flags = (tq.x >> 18) & 15;
       const int imin = (tq.y >> (6 * wm)) & 7, imax = (tq.y >> (6 * wm + 3)) & 7;   // this warp's active m-tiles [imin, imax)
-      if (++qq == (pass == 0 ? NPv : NPa)) { qq = 0; ++pass; }
+      if (++qq == (pass == 0 ? NPv : NPa)) { qq = 0; ++pass; if (pass == 1 && a.vform) pass = 2; }
       if (e.flags & kPanelFirst) {
 #pragma unroll
         for (int i = 0; i < TM; ++i)
@@ -390,7 +393,8 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
               *reinterpret_cast<double2*>(tile + row * LDT + col) = make_double2(c0[i][j], c1[i][j]);
             }
         }
-        double* st = e.kind == 1 ? a.stashA : (e.kind == 2 && a.stashT ? a.stashT + (long)e.d * a.Mp * a.Pp : nullptr);
+        // stash of the resident operand the T_d passes read (A, or V in V-form) and of T_d itself
+        double* st = e.kind == (a.vform ? 0 : 1) ? a.stashA : (e.kind == 2 && a.stashT ? a.stashT + (long)e.d * a.Mp * a.Pp : nullptr);
         if (st) {
 #pragma unroll
           for (int i = 0; i < TM; ++i)
@@ -426,13 +430,13 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
       for (; m + 8 <= a.M; m += 8) {   // eight independent q_mu loads in flight: they come from L2 (L1 is ~12 KB here)
         double qv[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) qv[u] = qd[(m + u) * a.D_out];
+        for (int u = 0; u < 8; ++u) qv[u] = qd[(m + u) * a.qmu_ld];
         m0 = fma(tc[(m + 0) * LDT], qv[0], m0); m1 = fma(tc[(m + 1) * LDT], qv[1], m1);
         m2 = fma(tc[(m + 2) * LDT], qv[2], m2); m3 = fma(tc[(m + 3) * LDT], qv[3], m3);
         m0 = fma(tc[(m + 4) * LDT], qv[4], m0); m1 = fma(tc[(m + 5) * LDT], qv[5], m1);
         m2 = fma(tc[(m + 6) * LDT], qv[6], m2); m3 = fma(tc[(m + 7) * LDT], qv[7], m3);
       }
-      for (; m < a.M; ++m) m0 = fma(tc[m * LDT], qd[m * a.D_out], m0);
+      for (; m < a.M; ++m) m0 = fma(tc[m * LDT], qd[m * a.qmu_ld], m0);
       const double mean = (m0 + m1) + (m2 + m3);
       const double* x = a.Xin + (p % a.xmod) * a.D_in;
       double mf = 0.0;

@@ -78,6 +78,10 @@ int dgp_set_fused(dgp_ctx* ctx, int on);
  * are identical for every sample; on = 1 (default) evaluates them once per point and expands / reduces over S around them,
  * on = 0 evaluates every point-sample like the reference does. Results agree to summation order. */
 int dgp_set_share_first_layer(dgp_ctx* ctx, int on);
+/* Forward-only calls (propagate / predict / acquisition) by default use the V-form of the conditional: C_d = q_sqrt_d^T Lu^-T and
+ * beta = Lu^-1 q_mu are folded once per call, T_d = C_d V, mean = V^T beta, and the A = Lu^-T V pass disappears
+ * ((1 + D_out) M^2 instead of (2 + D_out) M^2 flops per point-sample). on = 0 keeps the reference's operation order. */
+int dgp_set_vform(dgp_ctx* ctx, int on);
 int dgp_get_profile(dgp_ctx* ctx, double* ms_out, int64_t* launches_out, int reset);
 
 /* kern.K(X, X2) of the GPflow stationary kernel the reference layers hold (utils/layers.py:221,230,243), K_out [n1, n2]:

@@ -182,3 +182,23 @@ def test_notebook_regression_schedule_learns_the_step():
     assert elbo > -60.0, elbo
     m, _ = model.predict(np.array([[0.1], [0.9]]), 50, seed=3)
     assert float(m[0]) < 0.3 and float(m[1]) > 0.7
+
+
+def test_vform_forward_equals_reference_operation_order():
+    """Forward-only calls fold C_d = q_sqrt_d^T Lu^-T and beta = Lu^-1 q_mu once and skip the A = Lu^-T V pass; switching
+    that off keeps the reference's operation order. Same values to rounding."""
+    import dgp_toolbox_b200 as D
+    from dgp_toolbox_b200 import synthetic
+    model, cfg = _c2_model(S=4)
+    X, _ = synthetic.minibatch(cfg["D0"], 300, 6)
+    ctx = D._lib.get_context(0)
+    a = [t.clone() for t in sum(model.propagate(X, S=4, seed=5), [])]
+    ma, va = model.predict(X, 4, seed=6)
+    ctx.set_vform(False)
+    try:
+        b = [t.clone() for t in sum(model.propagate(X, S=4, seed=5), [])]
+        mb, vb = model.predict(X, 4, seed=6)
+    finally:
+        ctx.set_vform(True)
+    for x, y in zip(a + [ma, va], b + [mb, vb]):
+        assert float((x - y).abs().max()) <= 1e-10 * max(float(y.abs().max()), 1.0)
