@@ -57,7 +57,7 @@ _SIG = {
     "dgp_set_profiling": (C.c_int, [_vp, _i]),
     "dgp_set_fused": (C.c_int, [_vp, _i]),
     "dgp_set_share_first_layer": (C.c_int, [_vp, _i]),
-    "dgp_set_vform": (C.c_int, [_vp, _i]),
+    "dgp_set_vform": (C.c_int, [_vp, _i, _i]),
     "dgp_get_profile": (C.c_int, [_vp, _vp, _vp, _i]),
     "dgp_philox_normal": (C.c_int, [_vp, _u64, _i, _i64, _i64, _i, _i64, _vp]),
     "dgp_kernel_K": (C.c_int, [_vp, _i, _i, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
@@ -139,8 +139,9 @@ class Context:
     def set_share_first_layer(self, on: bool):
         lib.dgp_set_share_first_layer(self.h, 1 if on else 0)
 
-    def set_vform(self, on: bool):
-        lib.dgp_set_vform(self.h, 1 if on else 0)
+    def set_vform(self, forward: bool = True, grad=True):
+        """grad: False (A-form adjoint), True (V-form adjoint for calls with >= 32768 point-samples), "always"."""
+        lib.dgp_set_vform(self.h, 1 if forward else 0, 2 if grad == "always" else (1 if grad else 0))
 
     def set_fused(self, on: bool):
         lib.dgp_set_fused(self.h, 1 if on else 0)

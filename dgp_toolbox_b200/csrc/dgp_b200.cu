@@ -36,6 +36,9 @@ struct dgp_ctx {
   size_t h_pinned_bytes = 0;
   double* d_stage = nullptr;            // device side of that staging (outside the arena, which may be re-grown)
   size_t d_stage_bytes = 0;
+  bool use_vform_grad = true;           // ... and so does the ELBO+gradient path (V-form adjoint in backward_layer)
+  bool vform_forward_calls = true;
+  long vform_grad_min_ps = 32768;       // fewer point-samples than this: keep the A-form adjoint (no Cholesky-adjoint glue)
   bool use_vform = true;                // forward-only calls fold q_sqrt_d^T Lu^-T once per step and skip the A pass
   bool share_first_layer = true;        // evaluate the first layer once per point instead of once per point-sample
   bool use_fused = true;                // fused conditional kernel (fused.cuh); false -> unfused GEMM pipeline
@@ -208,6 +211,10 @@ struct LayerWs {
   // V-form of the conditional (forward-only calls): C_d = q_sqrt_d^T Lu^-T [D][Mp][Mp] and beta = Lu^-1 q_mu [Mp][32]
   bool vform = false;
   double *Cmat = nullptr, *betaP = nullptr;
+  // V-form adjoint: C_d^T side by side, L^T, accumulators over the chunks (G1 = tril(dV V^T), DCt = [tril(V dT_d^T)]_d, dbeta = V Gm)
+  // and scratch of the once-per-step re-parameterisation back to (q_mu, q_sqrt, Ku)
+  double *CTcat = nullptr, *LT = nullptr, *G1 = nullptr, *DCt = nullptr, *dbeta = nullptr, *dqmu2 = nullptr, *dRcat = nullptr;
+  double *dLinv = nullptr, *sq1 = nullptr, *sq2 = nullptr;
 };
 
 // ---- fused kernel configurations ----
@@ -255,7 +262,7 @@ std::vector<PanelDesc> build_schedule(int Mp, int BM, int D_out, bool vform) {
 
 enum PrepLevel { PREP_FWD = 0, PREP_KL = 1, PREP_GRAD = 2 };
 
-int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& lw, PrepLevel level) {
+int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& lw, PrepLevel level, bool vform_grad_ok = true) {
   const int nl = model->num_layers;
   lw.assign(nl, LayerWs());
   std::vector<CholArgs> hargs(nl);
@@ -284,9 +291,14 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
     if (w.fcfg >= 0) {
       const int BM = kFusedChoices[w.fcfg].BM;
       const int nb = w.Mp / BM, kpb = BM / kPanelK;
-      w.vform = c->use_vform && level == PREP_FWD;
+      w.vform = (level == PREP_FWD && c->use_vform && c->vform_forward_calls) || (level == PREP_GRAD && c->use_vform_grad && vform_grad_ok);
       w.NP = ((w.vform ? 1 : 2) + w.D_out) * kpb * nb * (nb + 1) / 2;
       if (w.vform) { w.Cmat = walloc(c, mm * w.D_out); w.betaP = walloc(c, (size_t)w.Mp * 32); }
+      if (w.vform && level == PREP_GRAD) {
+        w.CTcat = walloc(c, mm * w.D_out); w.LT = walloc(c, mm); w.G1 = walloc(c, mm); w.DCt = walloc(c, mm * w.D_out);
+        w.dbeta = walloc(c, (size_t)w.Mp * 32); w.dqmu2 = walloc(c, (size_t)w.Mp * 32); w.dRcat = walloc(c, mm * w.D_out);
+        w.dLinv = walloc(c, mm); w.sq1 = walloc(c, mm); w.sq2 = walloc(c, mm);
+      }
       w.Zs = walloc(c, (size_t)w.M * w.D_in);
       w.stream = walloc(c, (size_t)w.NP * BM * kPanelK);
       w.sched = reinterpret_cast<PanelDesc*>(walloc(c, ((size_t)w.NP * sizeof(PanelDesc) + 7) / 8));
@@ -325,6 +337,13 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
       g = gargs(w.Linv, w.Mp, w.qmuP, 32, w.betaP, 32, w.Mp, 32, w.Mp);                   // beta = Lu^-1 q_mu
       g.a_tri = 1;
       RC(gemm(c, g, false));
+    }
+    if (w.vform && level == PREP_GRAD) {
+      const long nct = (long)w.D_out * w.Mp * w.Mp;
+      LAUNCH(vform_transpose_kernel, (unsigned)((nct + 255) / 256), 256, 0, w.Cmat, w.L, w.Mp, w.D_out, w.CTcat, w.LT);
+      // c_lower products leave the tiles above the diagonal unwritten: start the accumulators from zero
+      CK(cudaMemsetAsync(w.G1, 0, (size_t)w.Mp * w.Mp * sizeof(double), c->stream));
+      CK(cudaMemsetAsync(w.DCt, 0, (size_t)nct * sizeof(double), c->stream));
     }
     std::vector<PanelDesc> sch = build_schedule(w.Mp, BM, w.D_out, w.vform);
     if ((int)sch.size() != w.NP) { c->err = "internal: panel schedule size mismatch"; return DGP_ERR_ARG; }
@@ -467,6 +486,60 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
   double* dA = tmp.t0;
   double* W = tmp.t1;
   double* Gbar = tmp.t2;
+  if (w.vform) {
+    // ---- V-form adjoint: cl.A holds V = Lu^-1 Kuf, T_d = C_d V, mean = V^T beta ----
+    const double* V = cl.A;
+    double* dV = dA;
+    double* Kbar = W;
+    CAT(DGP_CAT_GEMM_BWD_DATA);
+    // dV = beta Gm^T + sum_d C_d^T (2 Gv_d o T_d) - 2 V diag(sum_d Gv_d)          (gq = -sum_d Gv_d)
+    GemmArgs g = gargs(w.betaP, 32, up.GmPad, 32, dV, Pp, Mp, (int)Pp, 32);
+    RC(gemm(c, g, true));
+    g = gargs(w.CTcat, (long)D * Mp, cl.T, Pp, dV, Pp, Mp, (int)Pp, D * Mp);
+    g.a_tri = 1; g.kblocks = D; g.kblk = Mp; g.bscale = up.GvT; g.ld_bscale = Pp; g.bscale_mul = 2.0; g.beta = 1.0;
+    if (D == 1) g.kblocks = 1;
+    g.epi_plane = V; g.ld_epi = Pp; g.epi_col = up.gq; g.epi_mul = 2.0;
+    RC(gemm(c, g, false));
+    // K-bar = dELBO/dKuf = Lu^-T dV
+    g = gargs(w.LinvT, Mp, dV, Pp, Kbar, Pp, Mp, (int)Pp, Mp);
+    g.a_tri = 2;
+    RC(gemm(c, g, false));
+    CAT(DGP_CAT_RBF_BWD);
+    RbfBwdArgs r;
+    memset(&r, 0, sizeof(r));
+    r.W = Kbar; r.A = nullptr; r.gq = up.gq; r.Gbar = Gbar; r.Xin = cl.Xin; r.xmod = cl.xmod; r.Z = d.Z; r.ls = d.lengthscales;
+    r.var = d.variance; r.M = w.M; r.Mp = Mp; r.D_in = w.D_in; r.P = P; r.Pp = Pp; r.Gm = up.Gm; r.D_out = D;
+    r.mean_kind = d.mean_kind; r.mfW = d.mf_W; r.kind = d.kernel_kind; r.dXin = dXin; r.XaugPad = XaugPad; r.part = rbf_part;
+    const long nbv = Pp / 128;
+    const size_t smemv = ((size_t)w.M * w.D_in + kMaxD + 32) * sizeof(double);
+    RC(dispatch_dmax(w.D_in, [&](auto dm) -> int {
+      constexpr int DM = decltype(dm)::value;
+      if (!c->dry) CK(cudaFuncSetAttribute((rbf_bwd_kernel<DM, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      LAUNCH((rbf_bwd_kernel<DM, true>), (unsigned)nbv, 128, smemv, r);
+      return DGP_OK;
+    }));
+    if (!params) return DGP_OK;
+    LAUNCH(reduce_partials_kernel, w.D_in + 1, 256, 0, rbf_part, nbv, w.D_in + 1, w.rbf_red, first_chunk ? 0 : 1);
+    LAUNCH(reduce_partials_kernel, 3, 256, 0, up.part, up.nblocks, 3, w.sgv, first_chunk ? 0 : 1);
+    CAT(DGP_CAT_GEMM_BWD_PARAM);
+    // G1 = tril(dV V^T)  (-> dLu^-1 through Kuf = Lu V)
+    g = gargs(dV, Pp, V, Pp, w.G1, Mp, Mp, Mp, (int)Pp);
+    g.beta = beta; g.c_lower = 1; g.splitk = pick_splitk(c, g, true); g.part = splitk_part;
+    RC(gemm(c, g, true));
+    // DCt_d = tril(V diag(2 Gv_d) T_d^T) = (dC_d)^T, blocks side by side
+    g = gargs(V, Pp, cl.T, Pp, w.DCt, (long)D * Mp, Mp, Mp, (int)Pp);
+    g.alpha = 2.0; g.beta = beta; g.batch = D; g.sA = 0; g.sB = (long)Mp * Pp; g.sC = Mp; g.c_lower = 1;
+    g.kscale = up.GvT; g.sScale = Pp; g.splitk = pick_splitk(c, g, true); g.part = splitk_part;
+    RC(gemm(c, g, true));
+    // dbeta = V Gm ;  H = Gbar [X, 1]
+    g = gargs(V, Pp, up.GmPad, 32, w.dbeta, 32, Mp, 32, (int)Pp);
+    g.beta = beta; g.splitk = pick_splitk(c, g, false); g.part = splitk_part;
+    RC(gemm(c, g, false));
+    g = gargs(Gbar, Pp, XaugPad, 32, w.H, 32, Mp, 32, (int)Pp);
+    g.beta = beta; g.splitk = pick_splitk(c, g, false); g.part = splitk_part;
+    RC(gemm(c, g, false));
+    return DGP_OK;
+  }
   // dA' = q_mu Gm^T + sum_d R_d (2 Gv_d o T_d)                                       
   CAT(DGP_CAT_GEMM_BWD_DATA);
   GemmArgs g = gargs(w.qmuP, 32, up.GmPad, 32, dA, Pp, Mp, (int)Pp, 32);
@@ -489,8 +562,8 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
   const size_t smem = ((size_t)w.M * w.D_in + kMaxD + 32) * sizeof(double);
   RC(dispatch_dmax(w.D_in, [&](auto dm) -> int {
     constexpr int DM = decltype(dm)::value;
-    if (!c->dry) CK(cudaFuncSetAttribute(rbf_bwd_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    LAUNCH(rbf_bwd_kernel<DM>, (unsigned)nb, 128, smem, r);
+    if (!c->dry) CK(cudaFuncSetAttribute((rbf_bwd_kernel<DM, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LAUNCH((rbf_bwd_kernel<DM, false>), (unsigned)nb, 128, smem, r);
     return DGP_OK;
   }));
   if (!params) return DGP_OK;   // input gradient only (acquisition): the contractions over the point-samples are not needed
@@ -553,7 +626,8 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
   if ((grad || o.want_elbo) && !model->lik_variance) { c->err = "lik_variance is null"; return DGP_ERR_ARG; }
 
   std::vector<LayerWs> lw;
-  RC(prep_layers(c, model, lw, adj ? PREP_GRAD : (o.want_elbo ? PREP_KL : PREP_FWD)));
+  // the V-form adjoint pays ~8 extra M^3-class products per layer and step: worth it only when there are enough point-samples
+  RC(prep_layers(c, model, lw, adj ? PREP_GRAD : (o.want_elbo ? PREP_KL : PREP_FWD), N * S >= c->vform_grad_min_ps));
   const size_t base_used = c->used;
 
   int maxMp = 0, maxD = 1;
@@ -754,13 +828,47 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
         const dgp_layer_desc& d = model->layers[l];
         LayerWs& w = lw[l];
         const long mm = (long)w.Mp * w.Mp;
+        if (w.vform) {
+          // V-form accumulators (G1, DCt, dbeta) -> gradients w.r.t. q_mu, q_sqrt and Ku = Lu Lu^T
+          const int Mp = w.Mp, D = w.D_out;
+          const long nct = (long)D * mm;
+          LAUNCH(tril_scale_kernel, (unsigned)((mm + 255) / 256), 256, 0, w.G1, Mp, (long)Mp, 1, 1.0);
+          LAUNCH(tril_scale_kernel, (unsigned)((nct + 255) / 256), 256, 0, w.DCt, Mp, (long)D * Mp, D, 1.0);
+          GemmArgs g = gargs(w.LinvT, Mp, w.dbeta, 32, w.dqmu2, 32, Mp, 32, Mp);              // dq_mu = Lu^-T dbeta
+          g.a_tri = 2;
+          RC(gemm(c, g, false));
+          g = gargs(w.LinvT, Mp, w.DCt, (long)D * Mp, w.dRcat, (long)D * Mp, Mp, D * Mp, Mp);   // dq_sqrt_d = tril(Lu^-T dC_d^T)
+          g.a_tri = 2;
+          RC(gemm(c, g, false));
+          // dLu^-1 = tril(G1 Lu^T + sum_d dC_d^T q_sqrt_d^T + dbeta q_mu^T)
+          g = gargs(w.G1, Mp, w.L, Mp, w.dLinv, Mp, Mp, Mp, Mp);
+          RC(gemm(c, g, true));
+          g = gargs(w.DCt, (long)D * Mp, w.RpT, Mp, w.dLinv, Mp, Mp, Mp, D * Mp);
+          g.beta = 1.0;
+          RC(gemm(c, g, false));
+          g = gargs(w.dbeta, 32, w.qmuP, 32, w.dLinv, Mp, Mp, Mp, 32);
+          g.beta = 1.0;
+          RC(gemm(c, g, true));
+          LAUNCH(tril_scale_kernel, (unsigned)((mm + 255) / 256), 256, 0, w.dLinv, Mp, (long)Mp, 1, 1.0);
+          // Lu^-1 = X is a function of Ku = Lu Lu^T: dX = -Phi(X dKu X^T) X, hence (Phi is self-adjoint)
+          //   dKu = -X^T sym(Phi(Xbar X^T)) X,  Xbar = dLu^-1,  Phi = lower triangle with halved diagonal
+          g = gargs(w.dLinv, Mp, w.Linv, Mp, w.sq1, Mp, Mp, Mp, Mp);          // Q = Xbar X^T
+          RC(gemm(c, g, true));
+          LAUNCH(phi_sym_kernel, (unsigned)((mm + 255) / 256), 256, 0, w.sq1, Mp, w.sq2);
+          g = gargs(w.LinvT, Mp, w.sq2, Mp, w.sq1, Mp, Mp, Mp, Mp);
+          g.a_tri = 2;
+          RC(gemm(c, g, false));
+          g = gargs(w.sq1, Mp, w.Linv, Mp, w.dKu, Mp, Mp, Mp, Mp);
+          g.alpha = -1.0;
+          RC(gemm(c, g, false));
+        }
         LAUNCH(dku_assemble_kernel, (unsigned)((mm + 255) / 256), 256, 0, w.dKu, w.Kinv, w.KSK, w.alpha, w.Knj, w.M, w.Mp, w.D_out,
                o.kl_weight, 1);
         LAUNCH(kuu_bwd_kernel, w.M, 128, 0, w.dKu, d.Z, d.lengthscales, d.variance, w.M, w.Mp, w.D_in, w.dZk, w.kuu_part, d.kernel_kind);
         LAUNCH(reduce_partials_kernel, w.D_in + 1, 256, 0, w.kuu_part, (long)w.M, w.D_in + 1, w.kuu_red, 0);
         FinalizeArgs f;
         memset(&f, 0, sizeof(f));
-        f.Gd = w.dR; f.KR = w.KRcat; f.Rcat = w.Rcat; f.dqmu = w.dqmu; f.alpha = w.alpha; f.H = w.H; f.dZk = w.dZk;
+        f.Gd = w.vform ? w.dRcat : w.dR; f.gd_cat = w.vform ? 1 : 0; f.KR = w.KRcat; f.Rcat = w.Rcat; f.dqmu = w.vform ? w.dqmu2 : w.dqmu; f.alpha = w.alpha; f.H = w.H; f.dZk = w.dZk;
         f.rbf_red = w.rbf_red; f.kuu_red = w.kuu_red; f.sgv = w.sgv; f.Z = d.Z; f.ls = d.lengthscales;
         f.M = w.M; f.Mp = w.Mp; f.D_in = w.D_in; f.D_out = w.D_out; f.klw = o.kl_weight;
         f.dZ = out + offs[l].dZ; f.dls = out + offs[l].dlengthscales; f.dvar = out + offs[l].dvariance;
@@ -854,9 +962,12 @@ int dgp_set_workspace_limit(dgp_ctx* c, int64_t bytes) {
   return DGP_OK;
 }
 
-int dgp_set_vform(dgp_ctx* c, int on) {
+int dgp_set_vform(dgp_ctx* c, int forward_calls, int gradient_calls) {
   if (!c) return DGP_ERR_ARG;
-  c->use_vform = on != 0;
+  c->use_vform = forward_calls != 0 || gradient_calls != 0;
+  c->use_vform_grad = gradient_calls != 0;
+  c->vform_grad_min_ps = gradient_calls == 2 ? 0 : 32768;   // 2: always, 1: only with enough point-samples to amortise the glue
+  c->vform_forward_calls = forward_calls != 0;
   return DGP_OK;
 }
 

@@ -35,6 +35,8 @@ struct GemmArgs {
   int kblocks; int kblk;
   // Optional column scale of B in NN mode: B[k][n] *= bscale_mul * bscale[(k / kblk) * ld_bscale + n].
   const double* bscale; long ld_bscale; double bscale_mul;
+  // Optional epilogue term (non-split-K only): C[m][n] += epi_mul * epi_col[n] * epi_plane[m * ld_epi + n]
+  const double* epi_plane; long ld_epi; const double* epi_col; double epi_mul;
 };
 
 template <int BM, int BN, int BK, int WM, int WN, bool NT, int STAGES>
@@ -198,6 +200,11 @@ __global__ void __launch_bounds__(WM* WN * 32) gemm_kernel(GemmArgs g) {
         double2* p = reinterpret_cast<double2*>(Cb + (long)row * g.ldc + col);
         double2 v = make_double2(g.alpha * c0[i][j], g.alpha * c1[i][j]);
         if (g.beta != 0.0) { double2 o = *p; v.x += g.beta * o.x; v.y += g.beta * o.y; }
+        if (g.epi_plane) {
+          const double2 e = *reinterpret_cast<const double2*>(g.epi_plane + (long)row * g.ld_epi + col);
+          v.x += g.epi_mul * g.epi_col[col] * e.x;
+          v.y += g.epi_mul * g.epi_col[col + 1] * e.y;
+        }
         *p = v;
       }
   }
@@ -307,6 +314,7 @@ inline GemmPlan gemm_plan(const GemmArgs& g, bool nt, int num_sms) {
 // Picks a tile configuration. Returns cudaErrorInvalidValue when the shape is not tile-aligned.
 inline cudaError_t gemm_launch(const GemmArgs& g, bool nt, cudaStream_t st) {
   if (g.M % 64 || g.K % 16 || g.splitk < 1 || (g.splitk > 1 && !g.part)) return cudaErrorInvalidValue;
+  if (g.epi_plane && (g.splitk != 1 || g.batch != 1)) return cudaErrorInvalidValue;
   if (g.kblocks > 1 && (nt || g.splitk != 1 || g.kblk % 16 || g.kblocks * g.kblk != g.K || g.a_tri == 2)) return cudaErrorInvalidValue;
   if (g.N == 32 && !nt) return gemm_launch_cfg<64, 32, 16, 2, 1, false, 3>(g, st);
   if (g.N % 64) return cudaErrorInvalidValue;

@@ -296,8 +296,8 @@ __global__ void __launch_bounds__(128) upstream_reduce_kernel(const double* __re
 // One thread per point-sample column, all inducing rows in a loop; per-block partials [blocks][D_in + 1].
 // ---------------------------------------------------------------------------------------------------------
 struct RbfBwdArgs {
-  double* W;            // [Mp][Pp] in: W, out: Wg
-  const double* A;      // [Mp][Pp]
+  double* W;            // [Mp][Pp] in: W, out: Wg      (V-form, A == null: in: K-bar = dELBO/dKuf, left untouched)
+  const double* A;      // [Mp][Pp] or null
   const double* gq;     // [Pp]
   double* Gbar;         // [Mp][Pp] out
   const double* Xin; long xmod; const double* Z; const double* ls; const double* var;
@@ -309,7 +309,7 @@ struct RbfBwdArgs {
   double* part;         // [blocks][D_in + 1]
 };
 
-template <int DMAX>
+template <int DMAX, bool VF>   // VF: V-form (no A plane, K-bar read-only)
 __global__ void __launch_bounds__(128) rbf_bwd_kernel(RbfBwdArgs a) {
   extern __shared__ double sh[];
   double* zs = sh;                         // [M][D_in]  (unscaled)
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(128) rbf_bwd_kernel(RbfBwdArgs a) {
     for (int u = 0; u < 4; ++u) {
       const long off = (long)(m0 + u) * a.Pp + p;
       wv[u] = (m0 + u < a.M) ? a.W[off] : 0.0;
-      av[u] = (m0 + u < a.M) ? a.A[off] : 0.0;
+      av[u] = (!VF && m0 + u < a.M) ? a.A[off] : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -354,9 +354,9 @@ __global__ void __launch_bounds__(128) rbf_bwd_kernel(RbfBwdArgs a) {
           }
         double k = 0.0, gf = 0.0;
         if (live) kernel_eval(a.kind, r2, s2, k, gf);
-        const double kbar = w + 2.0 * am * g;   // dELBO / dKuf[m][p]
+        const double kbar = VF ? w : w + 2.0 * am * g;   // dELBO / dKuf[m][p]
         const double gb = kbar * gf;            // K-bar times -2 dk/d(r2): drives dX, dZ, dl
-        a.W[off] = w + am * g;
+        if (!VF) a.W[off] = w + am * g;
         a.Gbar[off] = gb;
         ds2 += kbar * k;                        // d/d s2 = sum K-bar K / s2
 #pragma unroll

@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(128) kuu_bwd_kernel(const double* __restrict__
 
 struct FinalizeArgs {
   // inputs
-  const double* Gd;       // [D_out][Mp][Mp]  tril(A dT_d^T)     (null when no data term)
+  const double* Gd;       // [D_out][Mp][Mp]  tril(A dT_d^T), or [Mp][D_out*Mp] when gd_cat (null when no data term)
+  int gd_cat;
   const double* KR;       // [Mp][D_out*Mp]   Kinv Rcat
   const double* Rcat;     // [Mp][D_out*Mp]
   const double* dqmu;     // [Mp][32] data part (null when no data term)
@@ -126,7 +127,7 @@ __global__ void finalize_layer_kernel(FinalizeArgs a) {
     if (j <= i) {
       const long off = ((long)d * a.Mp + i) * a.Mp + j;
       const long offc = (long)i * a.D_out * a.Mp + (long)d * a.Mp + j;
-      v = (a.Gd ? a.Gd[off] : 0.0) - a.klw * (a.KR[offc] - (i == j ? 1.0 / a.Rcat[offc] : 0.0));
+      v = (a.Gd ? a.Gd[a.gd_cat ? offc : off] : 0.0) - a.klw * (a.KR[offc] - (i == j ? 1.0 / a.Rcat[offc] : 0.0));
     }
     a.dq_sqrt[idx] = v;
   }
@@ -145,6 +146,44 @@ __global__ void finalize_layer_kernel(FinalizeArgs a) {
   }
   if (idx < a.D_in) a.dls[idx] = (a.rbf_red ? a.rbf_red[idx] : 0.0) + a.kuu_red[idx];
   if (idx == 0) a.dvar[0] = (a.rbf_red ? a.rbf_red[a.D_in] : 0.0) + a.kuu_red[a.D_in] + (a.sgv ? a.sgv[2] : 0.0);
+}
+
+// ---- V-form adjoint glue (M^2-class, once per step and layer) ----
+// CTcat[i][d*Mp + j] = Cmat[d][j][i]  (C_d^T, lower-triangular blocks side by side); LT = L^T.
+__global__ void vform_transpose_kernel(const double* __restrict__ Cmat, const double* __restrict__ L, int Mp, int D,
+                                       double* __restrict__ CTcat, double* __restrict__ LT) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < (long)D * Mp * Mp) {
+    const int j = (int)(idx % Mp);
+    const long r = idx / Mp;
+    const int i = (int)(r % Mp), d = (int)(r / Mp);
+    CTcat[(long)i * D * Mp + (long)d * Mp + j] = Cmat[((long)d * Mp + j) * Mp + i];
+  }
+  if (idx < (long)Mp * Mp) {
+    const int i = (int)(idx / Mp), j = (int)(idx % Mp);
+    LT[idx] = L[(long)j * Mp + i];
+  }
+}
+
+// In place on `nblk` square blocks laid side by side in a [Mp][ld] matrix: keep the lower triangle (scaled), zero the rest.
+__global__ void tril_scale_kernel(double* __restrict__ X, int Mp, long ld, int nblk, double scale) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)nblk * Mp * Mp) return;
+  const int j = (int)(idx % Mp);
+  const long r = idx / Mp;
+  const int i = (int)(r % Mp), b = (int)(r / Mp);
+  double* p = X + (long)i * ld + (long)b * Mp + j;
+  *p = (j <= i) ? scale * *p : 0.0;
+}
+
+// Cholesky adjoint core: out = sym(Phi(P)), Phi = lower triangle with halved diagonal, sym(Q) = (Q + Q^T) / 2.
+__global__ void phi_sym_kernel(const double* __restrict__ P, int Mp, double* __restrict__ out) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)Mp * Mp) return;
+  const int i = (int)(idx / Mp), j = (int)(idx % Mp);
+  const int a = max(i, j), b = min(i, j);
+  const double v = P[(long)a * Mp + b];
+  out[idx] = 0.5 * v;   // off-diagonal: (Phi + Phi^T)/2 = P_lower / 2; diagonal: (P/2 + P/2) / 2 = P / 2
 }
 
 __global__ void scale_copy_kernel(const double* in, double s, double* out) {

@@ -78,10 +78,14 @@ int dgp_set_fused(dgp_ctx* ctx, int on);
  * are identical for every sample; on = 1 (default) evaluates them once per point and expands / reduces over S around them,
  * on = 0 evaluates every point-sample like the reference does. Results agree to summation order. */
 int dgp_set_share_first_layer(dgp_ctx* ctx, int on);
-/* Forward-only calls (propagate / predict / acquisition) by default use the V-form of the conditional: C_d = q_sqrt_d^T Lu^-T and
- * beta = Lu^-1 q_mu are folded once per call, T_d = C_d V, mean = V^T beta, and the A = Lu^-T V pass disappears
- * ((1 + D_out) M^2 instead of (2 + D_out) M^2 flops per point-sample). on = 0 keeps the reference's operation order. */
-int dgp_set_vform(dgp_ctx* ctx, int on);
+/* V-form of the conditional (default on for both kinds of call): C_d = q_sqrt_d^T Lu^-T and beta = Lu^-1 q_mu are folded once per
+ * call, T_d = C_d V, mean = V^T beta, var = s2 - |V|^2 + |T_d|^2, so the A = Lu^-T V pass disappears ((1 + D_out) M^2 instead of
+ * (2 + D_out) M^2 flops per point-sample); the adjoint works on V as well (dV, K-bar = Lu^-T dV, contractions G1 = tril(dV V^T),
+ * tril(V dT_d^T), V Gm) and maps back to (q_mu, q_sqrt, Ku) once per step through the Cholesky adjoint. 0 keeps the reference's
+ * operation order (A = Ku^-1 Kuf explicitly) for the forward-only calls / for the ELBO+gradient calls. gradient_calls = 1 uses the
+ * V-form adjoint when the call has >= 32768 point-samples (below that the ~8 extra M^3-class products per layer cost more than
+ * they save), 2 always. Same results to rounding. */
+int dgp_set_vform(dgp_ctx* ctx, int forward_calls, int gradient_calls);
 int dgp_get_profile(dgp_ctx* ctx, double* ms_out, int64_t* launches_out, int reset);
 
 /* kern.K(X, X2) of the GPflow stationary kernel the reference layers hold (utils/layers.py:221,230,243), K_out [n1, n2]:

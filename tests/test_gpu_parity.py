@@ -13,14 +13,17 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-9
 
 
-@pytest.fixture(params=["fused", "unfused"])
+@pytest.fixture(params=["fused", "fused-aform", "unfused"])
 def conditional_path(request):
-    """Both implementations of the conditional: the fused kernel (default) and the unfused GEMM pipeline."""
+    """The implementations of the conditional: the fused kernel in V-form (default), the fused kernel in the reference's
+    operation order (A = Ku^-1 Kuf explicit), and the unfused GEMM pipeline."""
     import dgp_toolbox_b200 as D
     ctx = D._lib.get_context(0)
-    ctx.set_fused(request.param == "fused")
+    ctx.set_fused(request.param != "unfused")
+    ctx.set_vform(request.param == "fused", "always" if request.param == "fused" else False)
     yield request.param
     ctx.set_fused(True)
+    ctx.set_vform(True, True)
 
 
 SHAPES = [

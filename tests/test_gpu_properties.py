@@ -194,11 +194,20 @@ def test_vform_forward_equals_reference_operation_order():
     ctx = D._lib.get_context(0)
     a = [t.clone() for t in sum(model.propagate(X, S=4, seed=5), [])]
     ma, va = model.predict(X, 4, seed=6)
-    ctx.set_vform(False)
+    Y = np.sin(X.sum(1, keepdims=True))
+    ctx.set_vform(True, "always")
+    ga = model.elbo_flat((X, Y), want_grad=True, seed=7).clone()
+    ctx.set_vform(False, False)
     try:
         b = [t.clone() for t in sum(model.propagate(X, S=4, seed=5), [])]
         mb, vb = model.predict(X, 4, seed=6)
+        gb = model.elbo_flat((X, Y), want_grad=True, seed=7).clone()
     finally:
-        ctx.set_vform(True)
+        ctx.set_vform(True, True)
     for x, y in zip(a + [ma, va], b + [mb, vb]):
         assert float((x - y).abs().max()) <= 1e-10 * max(float(y.abs().max()), 1.0)
+    # gradients: same adjoint through two different parameterisations (V-form maps back through the Cholesky adjoint)
+    _, offs = model.grad_layout()
+    bounds = [0, 3] + [o.dZ for o in offs[1:]] + [ga.numel()]
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        assert float((ga[lo:hi] - gb[lo:hi]).abs().max()) <= 1e-8 * max(float(gb[lo:hi].abs().max()), 1e-12)
