@@ -58,6 +58,7 @@ _SIG = {
     "dgp_set_fused": (C.c_int, [_vp, _i]),
     "dgp_set_share_first_layer": (C.c_int, [_vp, _i]),
     "dgp_set_vform": (C.c_int, [_vp, _i, _i]),
+    "dgp_set_parallel_layers": (C.c_int, [_vp, _i]),
     "dgp_get_profile": (C.c_int, [_vp, _vp, _vp, _i]),
     "dgp_philox_normal": (C.c_int, [_vp, _u64, _i, _i64, _i64, _i, _i64, _vp]),
     "dgp_kernel_K": (C.c_int, [_vp, _i, _i, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),

@@ -42,6 +42,12 @@ struct dgp_ctx {
   bool use_vform = true;                // forward-only calls fold q_sqrt_d^T Lu^-T once per step and skip the A pass
   bool share_first_layer = true;        // evaluate the first layer once per point instead of once per point-sample
   bool use_fused = true;                // fused conditional kernel (fused.cuh); false -> unfused GEMM pipeline
+  // the layers' replicated per-step work (Kuu build, operator packing, KL, M^3 glue, gradient assembly) is independent per
+  // layer and made of tiny launches: it runs on per-layer side streams forked from / joined to the caller's stream
+  static constexpr int kAux = 8;
+  cudaStream_t aux[kAux] = {nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr};
+  bool parallel_layers = true;
   long launches = 0;                    // kernels launched since the last dgp_reset_launch_count
   // optional per-category device timing (CUDA event pairs around every launch, on the ctx's stream)
   bool profiling = false;
@@ -103,6 +109,32 @@ double* walloc(dgp_ctx* c, size_t n_doubles) {
   if (c->dry) return nullptr;
   return reinterpret_cast<double*>(c->ws + off);
 }
+
+struct LayerFork {   // fork the ctx's stream into per-layer side streams for a loop over layers, join afterwards
+  dgp_ctx* c; cudaStream_t main; int n; bool active = false;
+  LayerFork(dgp_ctx* ctx, int nlayers) : c(ctx), main(ctx->stream), n(nlayers < dgp_ctx::kAux ? nlayers : dgp_ctx::kAux) {
+    if (c->dry || nlayers < 2 || !c->parallel_layers) return;
+    if (!c->ev_fork) {
+      if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) return;
+      for (int i = 0; i < dgp_ctx::kAux; ++i) {
+        if (cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking) != cudaSuccess) return;
+        if (cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) != cudaSuccess) return;
+      }
+    }
+    if (cudaEventRecord(c->ev_fork, main) != cudaSuccess) return;
+    for (int i = 0; i < n; ++i) cudaStreamWaitEvent(c->aux[i], c->ev_fork, 0);
+    active = true;
+  }
+  void use(int l) { if (active) c->stream = c->aux[l % n]; }
+  void join() {
+    if (active) {
+      for (int i = 0; i < n; ++i) { cudaEventRecord(c->ev_join[i], c->aux[i]); cudaStreamWaitEvent(main, c->ev_join[i], 0); }
+      active = false;
+    }
+    c->stream = main;
+  }
+  ~LayerFork() { join(); }
+};
 
 int ensure_ws(dgp_ctx* c, size_t need) {
   if (need <= c->cap) return DGP_OK;
@@ -310,7 +342,9 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
   CAT(DGP_CAT_PREP);
   CK(cudaMemsetAsync(c->d_info, 0, sizeof(int), c->stream));
   CK(cudaMemcpyAsync(dargs, hargs.data(), sizeof(CholArgs) * nl, cudaMemcpyHostToDevice, c->stream));
+  LayerFork forkA(c, nl);
   for (int l = 0; l < nl; ++l) {
+    forkA.use(l);
     const dgp_layer_desc& d = model->layers[l];
     LayerWs& w = lw[l];
     const long mm = (long)w.Mp * w.Mp;
@@ -318,6 +352,7 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
     const long np = mm * w.D_out > (long)w.Mp * 32 ? mm * w.D_out : (long)w.Mp * 32;
     LAUNCH(pad_params_kernel, (unsigned)((np + 255) / 256), 256, 0, d.q_sqrt, d.q_mu, w.M, w.Mp, w.D_out, w.RpT, w.Rcat, w.qmuP);
   }
+  forkA.join();
   {
     if (!c->chol_configured) {   // per device (= per ctx)
       CK(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem_bytes(768)));
@@ -325,7 +360,9 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
     }
     LAUNCH(chol_inv_kernel, nl, kCholThreads, chol_smem_bytes(maxMp), dargs);
   }
+  LayerFork forkB(c, nl);
   for (int l = 0; l < nl; ++l) {   // operator stream of the fused conditional kernel
+    forkB.use(l);
     LayerWs& w = lw[l];
     if (w.fcfg < 0) continue;
     const dgp_layer_desc& d = model->layers[l];
@@ -355,6 +392,7 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
   }
   if (level >= PREP_KL) {
     for (int l = 0; l < nl; ++l) {
+      forkB.use(l);
       LayerWs& w = lw[l];
       const int Mp = w.Mp, D = w.D_out;
       GemmArgs g = gargs(w.LinvT, Mp, w.Linv, Mp, w.Kinv, Mp, Mp, Mp, Mp);   // Kinv = Linv^T Linv
@@ -824,7 +862,9 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
     for (int l = 0; l < nl; ++l) LAUNCH(reduce_partials_kernel, 1, 256, 0, lw[l].kl, 1, 1, klsum, 1);
     LAUNCH(scale_copy_kernel, 1, 32, 0, klsum, o.kl_weight, out + 1);
     if (grad) {
+      LayerFork forkE(c, nl);
       for (int l = 0; l < nl; ++l) {
+        forkE.use(l);
         const dgp_layer_desc& d = model->layers[l];
         LayerWs& w = lw[l];
         const long mm = (long)w.Mp * w.Mp;
@@ -943,6 +983,10 @@ void dgp_ctx_destroy(dgp_ctx* c) {
   if (c->d_stage) cudaFree(c->d_stage);
   for (auto& s : c->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
+  if (c->ev_fork) {
+    cudaEventDestroy(c->ev_fork);
+    for (int i = 0; i < dgp_ctx::kAux; ++i) { if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); if (c->aux[i]) cudaStreamDestroy(c->aux[i]); }
+  }
   delete c;
 }
 
@@ -959,6 +1003,12 @@ int64_t dgp_workspace_bytes(dgp_ctx* c) { return c ? (int64_t)c->cap : 0; }
 int dgp_set_workspace_limit(dgp_ctx* c, int64_t bytes) {
   if (!c || bytes < ((int64_t)64 << 20)) return DGP_ERR_ARG;
   c->ws_limit = (size_t)bytes;
+  return DGP_OK;
+}
+
+int dgp_set_parallel_layers(dgp_ctx* c, int on) {
+  if (!c) return DGP_ERR_ARG;
+  c->parallel_layers = on != 0;
   return DGP_OK;
 }
 

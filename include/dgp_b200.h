@@ -78,6 +78,9 @@ int dgp_set_fused(dgp_ctx* ctx, int on);
  * are identical for every sample; on = 1 (default) evaluates them once per point and expands / reduces over S around them,
  * on = 0 evaluates every point-sample like the reference does. Results agree to summation order. */
 int dgp_set_share_first_layer(dgp_ctx* ctx, int on);
+/* The layers' replicated per-step work (Kuu build, operator packing, KL, M^3 glue, gradient assembly) runs on per-layer side
+ * streams forked from and joined to the ctx's stream (default 1); 0 keeps every launch on the ctx's stream. */
+int dgp_set_parallel_layers(dgp_ctx* ctx, int on);
 /* V-form of the conditional (default on for both kinds of call): C_d = q_sqrt_d^T Lu^-T and beta = Lu^-1 q_mu are folded once per
  * call, T_d = C_d V, mean = V^T beta, var = s2 - |V|^2 + |T_d|^2, so the A = Lu^-T V pass disappears ((1 + D_out) M^2 instead of
  * (2 + D_out) M^2 flops per point-sample); the adjoint works on V as well (dV, K-bar = Lu^-T dV, contractions G1 = tril(dV V^T),
