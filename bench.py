@@ -123,7 +123,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     f_fwd_ref, f_step_ref = synthetic.flops_per_point_sample(cfg["D0"], cfg["num_units"], cfg["M"])            # reference formulation
-    f_fwd, f_step = synthetic.flops_per_point_sample(cfg["D0"], cfg["num_units"], cfg["M"], S=cfg["S"])      # with first-layer sharing
+    f_fwd, f_step = synthetic.flops_per_point_sample(cfg["D0"], cfg["num_units"], cfg["M"], S=cfg["S"])      # V-form + first-layer sharing
     workload = (f"{len(cfg['num_units'])}-layer DGP ({len(cfg['num_units']) + 1} SVGP layers), ARD-RBF, D={cfg['D0']}, "
                 f"M={cfg['M']}, S={cfg['S']}, minibatch ELBO+grad, float64")
 
@@ -239,15 +239,15 @@ def main():
                 "kernel_ms_per_step": ms / args.steps, "share_of_step": ms / all_ms if all_ms > 0 else None}
 
     fwd_cats = [k for k in ("fused_fwd", "gemm_fwd") if prof[k][0] > 0]
-    k_fwd = kernel_entry("dgp::fused_forward_kernel (Kuf tile -> Lu^-1 -> Lu^-T -> q_sqrt^T contraction -> moments/sample, FP64 DMMA, "
+    k_fwd = kernel_entry("dgp::fused_forward_kernel (Kuf tile -> V = Lu^-1 Kuf -> T_d = (q_sqrt_d^T Lu^-T) V -> moments/sample, FP64 DMMA, "
                          "TMA bulk-copy operand ring)" if prof["fused_fwd"][0] > 0 else "dgp::gemm_kernel (forward contractions)",
                          fwd_cats, f_fwd,
                          # ncu --set full capture profiles/r01c_fused_forward_ncu.txt: dram read+write 1.2027 GB for one launch over
                          # 65 536 point-samples of an 8->8 layer (= the 18.4 KB A/T_d stash per point-sample, no re-reads), scaled
                          # to this run's launch size
                          traffic=(1.2027e9 / 65536) * nb * S if prof["fused_fwd"][0] > 0 and args.config == "c2" else None)
-    k_bwd = kernel_entry("dgp::gemm_kernel (FP64 DMMA adjoint contractions: sum_d q_sqrt_d dT_d, Ku^-1 dA', -Wg A^T, A diag(2Gv_d) T_d^T, "
-                         "A Gm, Gbar [X,1])", ["gemm_bwd_data", "gemm_bwd_param"], 2 * f_fwd)
+    k_bwd = kernel_entry("dgp::gemm_kernel (FP64 DMMA adjoint contractions: dV = sum_d C_d^T dT_d, Lu^-T dV, tril(dV V^T), "
+                         "tril(V diag(2Gv_d) T_d^T), V Gm, Gbar [X,1])", ["gemm_bwd_data", "gemm_bwd_param"], 2 * f_fwd)
     main, other = (k_bwd, k_fwd) if k_bwd["kernel_ms_per_step"] >= k_fwd["kernel_ms_per_step"] else (k_fwd, k_bwd)
     flops_rank_step = f_step * nb * S
     roofline = dict(main)
@@ -256,8 +256,9 @@ def main():
         "whole_step_frac": flops_rank_step / (ms_step * 1e-3) / 1e12 / peak,
         "reference_formulation": {
             "flops_per_point_sample": f_step_ref,
-            "note": "the reference tiles X over the S samples and evaluates the first layer S times per point (models/dgp.py:49); "
-                    "this implementation evaluates it once per point (identical results), so the kernels need "
+            "note": "the reference tiles X over the S samples, evaluates the first layer S times per point (models/dgp.py:49) and forms "
+                    "A = Ku^-1 Kuf explicitly (utils/layers.py:245-247); this implementation evaluates the first layer once per point "
+                    "and folds q_sqrt_d^T Lu^-T once per step (V-form, no A pass) - identical results - so the kernels need "
                     f"{f_step:.0f} flops per point-sample instead of {f_step_ref}. `achieved`/`frac` use the smaller figure "
                     "(work the kernels actually have to do); this entry says what rate the reference's formulation would need "
                     "for the same throughput.",

@@ -66,17 +66,19 @@ def minibatch(D0, N, index):
     return X, Y
 
 
-def flops_per_layer(D0, num_units, M):
+def flops_per_layer(D0, num_units, M, vform=False):
     """Algorithmic (triangular-aware, useful) forward FP64 flops of each SVGP layer for ONE evaluation of its conditional
-    (SURVEY §8d): (2 + D_out) M^2 + 2 M D_in + 2 M (2 D_out + 1)."""
+    (SURVEY §8d): (2 + D_out) M^2 + 2 M D_in + 2 M (2 D_out + 1) in the reference's operation order (V, A = Lu^-T V, T_d);
+    the V-form (C_d = q_sqrt_d^T Lu^-T folded once per step, no A pass) needs (1 + D_out) M^2 + the same lower-order terms."""
     dims = [D0] + list(num_units) + [1]
-    return [(2 + dout) * M * M + 2 * M * din + 2 * M * (2 * dout + 1) for din, dout in zip(dims[:-1], dims[1:])]
+    lead = 1 if vform else 2
+    return [(lead + dout) * M * M + 2 * M * din + 2 * M * (2 * dout + 1) for din, dout in zip(dims[:-1], dims[1:])]
 
 
 def flops_per_point_sample(D0, num_units, M, S=None):
     """(forward, ELBO+grad = 3x forward) flops per point-sample. S = None: the reference's formulation, every layer evaluated
-    for every point-sample. S given: what this implementation needs — the first layer's input is shared by the
-    S samples of a point, so that layer is evaluated once per point (1/S per point-sample)."""
-    fl = flops_per_layer(D0, num_units, M)
+    for every point-sample in the reference's operation order. S given: what this implementation needs — V-form
+    layers, and the first layer (whose input is shared by the S samples of a point) evaluated once per point."""
+    fl = flops_per_layer(D0, num_units, M, vform=S is not None)
     f = sum(fl) if S is None or len(fl) < 2 else fl[0] / S + sum(fl[1:])
     return f, 3 * f

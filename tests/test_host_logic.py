@@ -62,6 +62,10 @@ def test_product_synthetic_generator_equals_oracle_generator():
                 assert np.array_equal(la["mf_W"], lb["mf_W"])
     f_fwd, f_step = synthetic.flops_per_point_sample(8, [8, 8, 8], 256)
     assert f_fwd == 3 * (10 * 65536 + 4096 + 8704) + (3 * 65536 + 4096 + 1536) and f_step == 3 * f_fwd   # 2.207 MFLOP
+    fl = synthetic.flops_per_layer(8, [8, 8, 8], 256, vform=True)
+    assert fl[0] == 9 * 65536 + 4096 + 8704 and fl[-1] == 2 * 65536 + 4096 + 1536
+    f_v, _ = synthetic.flops_per_point_sample(8, [8, 8, 8], 256, S=32)
+    assert abs(f_v - (fl[0] / 32 + sum(fl[1:]))) < 1e-9
 
 
 def test_shard_bounds_cover_and_are_contiguous():

@@ -37,7 +37,7 @@ cfg = synthetic.CONFIGS["c3"]
 model = synthetic.model_from_problem(synthetic.synthetic_problem(cfg["D0"], cfg["num_units"], cfg["M"], 8), cfg["S"])
 pool = [torch.from_numpy(synthetic.minibatch(cfg["D0"], args.nb, i)[0]).cuda() for i in range(4)]
 ms = timed(lambda i: model.predict(pool[i % 4], cfg["S"], seed=100 + i), args.steps)
-f_fwd, _ = synthetic.flops_per_point_sample(cfg["D0"], cfg["num_units"], cfg["M"])
+f_fwd, _ = synthetic.flops_per_point_sample(cfg["D0"], cfg["num_units"], cfg["M"], S=cfg["S"])
 ps = args.nb * cfg["S"]
 print(json.dumps({"metric": "DGP predict point-samples/s", "value": ps / (ms * 1e-3), "unit": "point-samples/s", "ms_per_step": ms,
                   "config": {"workload": "5-layer DGP (6 SVGP layers), D=20, M=512, S=64, predict (mixture moments of predict_y), float64",
@@ -63,7 +63,7 @@ def acq(i):
 
 
 ms = timed(acq, args.steps)
-f_fwd, _ = synthetic.flops_per_point_sample(cfg["D0"], cfg["num_units"], cfg["M"])
+f_fwd, _ = synthetic.flops_per_point_sample(cfg["D0"], cfg["num_units"], cfg["M"], S=cfg["S"])
 flops = 3 * f_fwd * nb * cfg["S"]   # three propagations per candidate batch: EI on model 0, EHVI on models 0 and 1
 print(json.dumps({"metric": "DGP EI+EHVI candidates/s", "value": nb / (ms * 1e-3), "unit": "candidates/s", "ms_per_step": ms,
                   "config": {"workload": "EI (analytic) + exact 2-objective EHVI, two 3-layer DGPs (D=8, M=256), S=32, 32-point Pareto front, float64",
