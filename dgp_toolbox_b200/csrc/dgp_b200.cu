@@ -245,7 +245,7 @@ struct LayerWs {
   double *Cmat = nullptr, *betaP = nullptr;
   // V-form adjoint: C_d^T side by side, L^T, accumulators over the chunks (G1 = tril(dV V^T), DCt = [tril(V dT_d^T)]_d, dbeta = V Gm)
   // and scratch of the once-per-step re-parameterisation back to (q_mu, q_sqrt, Ku)
-  double *CTcat = nullptr, *LT = nullptr, *G1 = nullptr, *DCt = nullptr, *dbeta = nullptr, *dqmu2 = nullptr, *dRcat = nullptr;
+  double *CTcat = nullptr, *G1 = nullptr, *DCt = nullptr, *dbeta = nullptr, *dqmu2 = nullptr, *dRcat = nullptr;
   double *dLinv = nullptr, *sq1 = nullptr, *sq2 = nullptr;
 };
 
@@ -327,7 +327,7 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
       w.NP = ((w.vform ? 1 : 2) + w.D_out) * kpb * nb * (nb + 1) / 2;
       if (w.vform) { w.Cmat = walloc(c, mm * w.D_out); w.betaP = walloc(c, (size_t)w.Mp * 32); }
       if (w.vform && level == PREP_GRAD) {
-        w.CTcat = walloc(c, mm * w.D_out); w.LT = walloc(c, mm); w.G1 = walloc(c, mm); w.DCt = walloc(c, mm * w.D_out);
+        w.CTcat = walloc(c, mm * w.D_out); w.G1 = walloc(c, mm); w.DCt = walloc(c, mm * w.D_out);
         w.dbeta = walloc(c, (size_t)w.Mp * 32); w.dqmu2 = walloc(c, (size_t)w.Mp * 32); w.dRcat = walloc(c, mm * w.D_out);
         w.dLinv = walloc(c, mm); w.sq1 = walloc(c, mm); w.sq2 = walloc(c, mm);
       }
@@ -377,7 +377,7 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
     }
     if (w.vform && level == PREP_GRAD) {
       const long nct = (long)w.D_out * w.Mp * w.Mp;
-      LAUNCH(vform_transpose_kernel, (unsigned)((nct + 255) / 256), 256, 0, w.Cmat, w.L, w.Mp, w.D_out, w.CTcat, w.LT);
+      LAUNCH(vform_transpose_kernel, (unsigned)((nct + 255) / 256), 256, 0, w.Cmat, w.Mp, w.D_out, w.CTcat);
       // c_lower products leave the tiles above the diagonal unwritten: start the accumulators from zero
       CK(cudaMemsetAsync(w.G1, 0, (size_t)w.Mp * w.Mp * sizeof(double), c->stream));
       CK(cudaMemsetAsync(w.DCt, 0, (size_t)nct * sizeof(double), c->stream));

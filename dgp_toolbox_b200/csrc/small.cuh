@@ -149,20 +149,14 @@ __global__ void finalize_layer_kernel(FinalizeArgs a) {
 }
 
 // ---- V-form adjoint glue (M^2-class, once per step and layer) ----
-// CTcat[i][d*Mp + j] = Cmat[d][j][i]  (C_d^T, lower-triangular blocks side by side); LT = L^T.
-__global__ void vform_transpose_kernel(const double* __restrict__ Cmat, const double* __restrict__ L, int Mp, int D,
-                                       double* __restrict__ CTcat, double* __restrict__ LT) {
+// CTcat[i][d*Mp + j] = Cmat[d][j][i]  (C_d^T, lower-triangular blocks side by side).
+__global__ void vform_transpose_kernel(const double* __restrict__ Cmat, int Mp, int D, double* __restrict__ CTcat) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < (long)D * Mp * Mp) {
-    const int j = (int)(idx % Mp);
-    const long r = idx / Mp;
-    const int i = (int)(r % Mp), d = (int)(r / Mp);
-    CTcat[(long)i * D * Mp + (long)d * Mp + j] = Cmat[((long)d * Mp + j) * Mp + i];
-  }
-  if (idx < (long)Mp * Mp) {
-    const int i = (int)(idx / Mp), j = (int)(idx % Mp);
-    LT[idx] = L[(long)j * Mp + i];
-  }
+  if (idx >= (long)D * Mp * Mp) return;
+  const int j = (int)(idx % Mp);
+  const long r = idx / Mp;
+  const int i = (int)(r % Mp), d = (int)(r / Mp);
+  CTcat[(long)i * D * Mp + (long)d * Mp + j] = Cmat[((long)d * Mp + j) * Mp + i];
 }
 
 // In place on `nblk` square blocks laid side by side in a [Mp][ld] matrix: keep the lower triangle (scaled), zero the rest.
