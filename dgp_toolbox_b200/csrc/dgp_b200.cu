@@ -318,7 +318,7 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
       w.dZk = walloc(c, (size_t)w.M * w.D_in); w.kuu_part = walloc(c, (size_t)w.M * (w.D_in + 1)); w.kuu_red = walloc(c, 32);
     }
     if (w.Mp > maxMp) maxMp = w.Mp;
-    hargs[l] = CholArgs{w.Ku, w.L, w.Linv, w.LinvT, w.Mp, c->d_info};
+    hargs[l] = CholArgs{w.Ku, w.L, nullptr, nullptr, w.Mp, c->d_info};   // inverse: tri_inv_kernel
     w.fcfg = c->use_fused ? pick_fused_cfg(w.Mp, w.D_in, w.D_out) : -1;
     if (w.fcfg >= 0) {
       const int BM = kFusedChoices[w.fcfg].BM;
@@ -337,7 +337,13 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
     }
   }
   CholArgs* dargs = reinterpret_cast<CholArgs*>(walloc(c, (sizeof(CholArgs) * nl + 7) / 8));
+  double** dinv = reinterpret_cast<double**>(walloc(c, (size_t)nl));
+  double** dinvT = reinterpret_cast<double**>(walloc(c, (size_t)nl));
   if (c->dry) return DGP_OK;
+  std::vector<double*> hinv(nl), hinvT(nl);
+  for (int l = 0; l < nl; ++l) { hinv[l] = lw[l].Linv; hinvT[l] = lw[l].LinvT; }
+  CK(cudaMemcpyAsync(dinv, hinv.data(), sizeof(double*) * nl, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(dinvT, hinvT.data(), sizeof(double*) * nl, cudaMemcpyHostToDevice, c->stream));
 
   CAT(DGP_CAT_PREP);
   CK(cudaMemsetAsync(c->d_info, 0, sizeof(int), c->stream));
@@ -359,6 +365,8 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
       c->chol_configured = true;
     }
     LAUNCH(chol_inv_kernel, nl, kCholThreads, chol_smem_bytes(maxMp), dargs);
+    CK(cudaFuncSetAttribute(tri_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_inv_smem_bytes(768)));
+    LAUNCH(tri_inv_kernel, dim3((unsigned)(maxMp / 32), (unsigned)nl), 256, tri_inv_smem_bytes(maxMp), dargs, dinv, dinvT);
   }
   LayerFork forkB(c, nl);
   for (int l = 0; l < nl; ++l) {   // operator stream of the fused conditional kernel
