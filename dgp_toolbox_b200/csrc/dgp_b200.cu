@@ -247,6 +247,7 @@ struct LayerWs {
   // and scratch of the once-per-step re-parameterisation back to (q_mu, q_sqrt, Ku)
   double *CTcat = nullptr, *G1 = nullptr, *DCt = nullptr, *dbeta = nullptr, *dqmu2 = nullptr, *dRcat = nullptr;
   double *dLinv = nullptr, *sq1 = nullptr, *sq2 = nullptr;
+  double* part_small = nullptr;   // split-K partials of this layer's long-K M^3-class products (per layer: the layers run concurrently)
 };
 
 // ---- fused kernel configurations ----
@@ -312,7 +313,7 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
       w.LRcat = walloc(c, mm * w.D_out); w.kl = walloc(c, 1);
     }
     if (level >= PREP_GRAD) {
-      w.KRcat = walloc(c, mm * w.D_out); w.KSK = walloc(c, mm);
+      w.KRcat = walloc(c, mm * w.D_out); w.KSK = walloc(c, mm); w.part_small = walloc(c, mm * 16);
       w.dKu = walloc(c, mm); w.dR = walloc(c, mm * w.D_out); w.dqmu = walloc(c, (size_t)w.Mp * 32);
       w.H = walloc(c, (size_t)w.Mp * 32); w.rbf_red = walloc(c, 32); w.sgv = walloc(c, 4);
       w.dZk = walloc(c, (size_t)w.M * w.D_in); w.kuu_part = walloc(c, (size_t)w.M * (w.D_in + 1)); w.kuu_red = walloc(c, 32);
@@ -416,6 +417,7 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
         g = gargs(w.Kinv, Mp, w.Rcat, (long)D * Mp, w.KRcat, (long)D * Mp, Mp, D * Mp, Mp);  // Kinv [R_1 .. R_D]
         RC(gemm(c, g, false));
         g = gargs(w.KRcat, (long)D * Mp, w.KRcat, (long)D * Mp, w.KSK, Mp, Mp, Mp, D * Mp);   // sum_d (Kinv R_d)(Kinv R_d)^T
+        g.splitk = D >= 16 ? 16 : (D >= 2 ? D : 1); g.part = w.part_small;   // few output tiles, long K: split it
         RC(gemm(c, g, true));
       }
     }
@@ -893,6 +895,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
           RC(gemm(c, g, true));
           g = gargs(w.DCt, (long)D * Mp, w.RpT, Mp, w.dLinv, Mp, Mp, Mp, D * Mp);
           g.beta = 1.0;
+          g.splitk = D >= 16 ? 16 : (D >= 2 ? D : 1); g.part = w.part_small;
           RC(gemm(c, g, false));
           g = gargs(w.dbeta, 32, w.qmuP, 32, w.dLinv, Mp, Mp, Mp, 32);
           g.beta = 1.0;
