@@ -50,6 +50,8 @@ struct GemmCfg {
   static constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE + BK) * sizeof(double);
 };
 
+__device__ __forceinline__ bool gemm_tri_skip_enabled() { return true; }
+
 template <int BM, int BN, int BK, int WM, int WN, bool NT, int STAGES>
 __global__ void __launch_bounds__(WM* WN * 32) gemm_kernel(GemmArgs g) {
   using Cfg = GemmCfg<BM, BN, BK, WM, WN, NT, STAGES>;
@@ -60,7 +62,11 @@ __global__ void __launch_bounds__(WM* WN * 32) gemm_kernel(GemmArgs g) {
   double* Bs = As + STAGES * A_STAGE;
   double* Ss = Bs + STAGES * B_STAGE;
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // Triangular A: inside a diagonal block a warp whose rows lie entirely above (lower A) / below (upper A) the k-tile has only
+  // zeros to multiply and skips it. Warp w always runs on SM sub-partition w % 4, so the warp -> row-slot role rotates with the
+  // CTA index to spread the lighter roles over the sub-partitions.
+  const int warp = g.a_tri ? (int)(((tid >> 5) + blockIdx.x) % (WM * WN)) : (tid >> 5);
   const int g8 = lane >> 2, t4 = lane & 3;
   const int wm = warp / WN, wn = warp % WN;
 
@@ -176,6 +182,13 @@ __global__ void __launch_bounds__(WM* WN * 32) gemm_kernel(GemmArgs g) {
           for (int j = 0; j < TN; ++j) dmma884(c0[i][j], c1[i][j], a[i], bb[j]);
       }
     };
+    bool skip = false;
+    if (g.a_tri && gemm_tri_skip_enabled()) {
+      const int kin = koff(kt) - (kt / tpb) * kblk;   // k inside the (possibly concatenated) triangular block
+      const int r0w = m0 + wm * TM * 8;               // first row of the warp
+      skip = g.a_tri == 1 ? (kin > r0w + TM * 8 - 1) : (kin + BK - 1 < r0w);
+    }
+    if (skip) continue;
     if (Sb || (!NT && g.bscale)) compute(std::true_type());
     else compute(std::false_type());
   }
