@@ -36,6 +36,8 @@ SHAPES = [
     (1, [1, 1], 25, 50, 10, True),        # KAT-1 shape
     (6, [6], 128, 150, 3, True),          # Mp = 128: BM=128 fused configuration with one row block
     (4, [4], 320, 70, 2, True),           # Mp = 320: BM=64 fused configuration, 5 row blocks
+    (20, [20, 20], 512, 24, 2, True),     # config-3 layer shape: D=20, M=512 -> BM=128, PT=32 fused configuration, 4 row blocks
+    (12, [16], 130, 40, 3, True),         # Mp = 192 (padding rows), D_out = 16 > 8, widening Linear mean function
 ]
 
 
