@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
               const int row = e.i * BM + i * 8 * WM + wm * 8 + g8, col = j * 8 + 2 * t4;
-              *reinterpret_cast<double2*>(st + (long)row * a.Pp + p0 + col) = make_double2(c0[i][j], c1[i][j]);
+              __stcs(reinterpret_cast<double2*>(st + (long)row * a.Pp + p0 + col), make_double2(c0[i][j], c1[i][j]));   // streaming: read back only by the adjoint
             }
         }
         if (e.kind != 2) group_sync(bar_id, GT);   // the new rows are visible before the next block reads them
