@@ -7,15 +7,18 @@
 //   4. T_d = q_sqrt_d^T A for every output d: only column sums of squares are kept                         (layers.py:257-271)
 //   5. mean = A^T q_mu + mf(x), var = s2 - |V|^2 + |T_d|^2, z (Philox or supplied), F = mean + z sqrt(var + jitter)
 //      written as [P][D_out]                                                     (layers.py:249,272-278; utils/utils.py:40-41)
-// Kuf, V never touch HBM; A and T_d are written to HBM only when the adjoint will need them (training stash).
-// V-form (forward-only paths): T_d = C_d V with C_d = q_sqrt_d^T Lu^-T folded once per step, mean = V^T (Lu^-1 q_mu); the A
-// pass disappears ((1 + D_out) M^2 instead of (2 + D_out) M^2 flops per point-sample, same values to rounding).
+// Kuf never touches HBM; the operand of the T_d passes and T_d itself are written to HBM only when the adjoint will need them
+// (training stash, streaming stores).
+// V-form (default): C_d = q_sqrt_d^T Lu^-T and beta = Lu^-1 q_mu are folded once per step, T_d = C_d V, mean = V^T beta, and pass 3
+// disappears ((1 + D_out) M^2 instead of (2 + D_out) M^2 flops per point-sample, same values to rounding); V is stashed.
 //
-// The triangular operators (Lu^-1 lower, Lu^-T upper, q_sqrt_d^T upper) are pre-packed once per step by
+// The triangular operators (Lu^-1 lower, Lu^-T upper, q_sqrt_d^T or C_d upper) are pre-packed once per step by
 // pack_stream_kernel into ONE linear stream of [BM x 16] panels in exactly the order the tile loop consumes them, each panel
-// already in the XOR-swizzled shared-memory layout, so the producer side is a linear cp.async copy through a STAGES-deep
-// ring and the consumer side is a flat loop over a small panel schedule. Inside diagonal blocks each warp skips the
-// k-steps above/below its own 8-row m-tiles, so executed DMMA work stays within a few percent of the triangular minimum.
+// already in the XOR-swizzled shared-memory layout. A producer warp moves one panel per bulk copy (cp.async.bulk -> SASS
+// UBLKCP, completion on an mbarrier) through a STAGES-deep ring; 8 consumer warps in WN column groups wait on the full
+// barriers, run straight-line DMMA blocks specialised on the active m-tile range, and release the stage on the empty
+// barriers. Inside diagonal blocks whole (panel, m-tile) pairs that hold only zeros are skipped with warp-uniform
+// branches (a predicated-off DMMA still occupies the pipe), so executed DMMA work stays within ~6% of the triangular minimum.
 #pragma once
 #include "common.cuh"
 #include "philox.cuh"
