@@ -61,6 +61,7 @@ _SIG = {
     "dgp_set_parallel_layers": (C.c_int, [_vp, _i]),
     "dgp_get_profile": (C.c_int, [_vp, _vp, _vp, _i]),
     "dgp_philox_normal": (C.c_int, [_vp, _u64, _i, _i64, _i64, _i, _i64, _vp]),
+    "dgp_philox_raw": (C.c_int, [_vp, _u64, _i, _i64, _i64, _i, _i64, _vp]),
     "dgp_kernel_K": (C.c_int, [_vp, _i, _i, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "dgp_kuu_chol": (C.c_int, [_vp, C.POINTER(LayerDesc), _vp, _vp]),
     "dgp_conditional_nd": (C.c_int, [_vp, C.POINTER(LayerDesc), _vp, _i64, _vp, _vp]),

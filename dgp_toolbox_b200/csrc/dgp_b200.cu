@@ -1090,6 +1090,15 @@ int dgp_philox_normal(dgp_ctx* c, uint64_t seed, int layer, int64_t S, int64_t N
   return DGP_OK;
 }
 
+int dgp_philox_raw(dgp_ctx* c, uint64_t seed, int layer, int64_t S, int64_t N, int D, int64_t n_offset, uint32_t* words_out) {
+  if (!c || !words_out || S < 1 || N < 1 || D < 1) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  const long total = S * N * D;
+  LAUNCH(philox_raw_kernel, (unsigned)((total + 255) / 256), 256, 0, (unsigned long long)seed, layer, (long)S, (long)N, D, (long)n_offset,
+         words_out);
+  return DGP_OK;
+}
+
 int dgp_kernel_K(dgp_ctx* c, int kernel_kind, int D, const double* lengthscales, const double* variance, const double* X, int64_t n1,
                  const double* X2, int64_t n2, double* K_out) {
   if (!c || !X || !X2 || !K_out || D < 1 || D > kMaxD || n1 < 1 || n2 < 1 || kernel_kind < 0 || kernel_kind > 2) return DGP_ERR_ARG;

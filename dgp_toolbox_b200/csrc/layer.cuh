@@ -151,6 +151,18 @@ __global__ void __launch_bounds__(256) expand_first_layer_kernel(ExpandArgs a) {
   if (a.xF) a.xF[xrow * a.D + d] = f;
 }
 
+// Raw Philox-4x32-10 words of element (layer, s, n, d): the integer plumbing under the normal draws (bit-exact contract).
+__global__ void philox_raw_kernel(unsigned long long seed, int layer, long S, long N, int D, long n_offset, uint32_t* out) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * N * D) return;
+  int d = (int)(idx % D);
+  long r = idx / D;
+  long n = r % N, s = r / N;
+  uint32_t w[4];
+  philox4x32_10((uint32_t)(n + n_offset), (uint32_t)s, (uint32_t)d, (uint32_t)layer, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+  for (int k = 0; k < 4; ++k) out[idx * 4 + k] = w[k];
+}
+
 // Philox draws written out for the oracle / explicit-z callers.
 __global__ void philox_normal_kernel(unsigned long long seed, int layer, long S, long N, int D, long n_offset, double* z) {
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;

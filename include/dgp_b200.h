@@ -101,6 +101,10 @@ int dgp_kernel_K(dgp_ctx* ctx, int kernel_kind, int D, const double* lengthscale
  * (replaces tf.random.normal at utils/layers.py:113; counter = (n + n_offset, s, d, layer)). */
 int dgp_philox_normal(dgp_ctx* ctx, uint64_t seed, int layer, int64_t S, int64_t N, int D, int64_t n_offset, double* z_out);
 
+/* The raw Philox-4x32-10 words behind dgp_philox_normal, words_out [S, N, D, 4] uint32 (DEVICE): key = (seed_lo, seed_hi),
+ * counter = (n + n_offset, s, d, layer). Integer plumbing, bit-exact against oracle.philox_uint32. */
+int dgp_philox_raw(dgp_ctx* ctx, uint64_t seed, int layer, int64_t S, int64_t N, int D, int64_t n_offset, uint32_t* words_out);
+
 /* SVGP_Layer.build_cholesky_if_needed (utils/layers.py:227-234): Ku [M,M] = Kuu + jitter I, Lu [M,M] = chol(Ku). */
 int dgp_kuu_chol(dgp_ctx* ctx, const dgp_layer_desc* layer, double* Ku_out, double* Lu_out);
 

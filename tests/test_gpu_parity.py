@@ -120,6 +120,18 @@ def test_kat1_notebook_elbo_through_cuda():
     assert abs(val - (-406.37591174470)) <= 1e-9 * 406.37591174470, val
 
 
+def test_philox_words_are_bit_exact():
+    """Seed / counter plumbing: the raw Philox-4x32-10 words of every (layer, s, n, d) equal the oracle's, bit for bit, including
+    a shard offset and a seed with high bits."""
+    import dgp_toolbox_b200 as D
+    ctx = D._lib.get_context(0)
+    for seed, layer, S, N, Dd, off in [(1234, 0, 3, 17, 2, 0), (0xDEADBEEFCAFEF00D, 3, 5, 9, 4, 1000003)]:
+        w = torch.empty((S, N, Dd, 4), dtype=torch.int32, device="cuda")
+        ctx.call("dgp_philox_raw", seed, layer, S, N, Dd, off, D._lib.ptr(w))
+        got = w.cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, O.philox_uint32(seed, layer, S, N, Dd, n_offset=off))
+
+
 def test_philox_stream_is_bit_exact_and_drives_the_chain(conditional_path):
     import dgp_toolbox_b200 as D
     prob, om, pm = both_models(3, [2], 20, 33, 6)
