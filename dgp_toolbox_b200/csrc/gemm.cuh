@@ -126,6 +126,97 @@ __global__ void __launch_bounds__(WM* WN * 32) gemm_kernel(GemmArgs g) {
     }
   };
 
+  // ---- diagonal tile of a lower-only NT product (contractions over the point-samples: tril(dV V^T), tril(V dT_d^T)) ----
+  // Only the 36 of 64 accumulator units (8 x 8 each) on or below the diagonal are needed. Giving each warp a 32 x 32 quadrant
+  // would leave one warp idle and two half-used while the CTA still takes the full time, so instead every warp computes ALL
+  // 36 units for a quarter of each k-tile's k-steps; the four partial sums are added through shared memory at the end.
+  // The CTA then takes 36/64 of the time of an off-diagonal tile.
+  if constexpr (NT && BM == 64 && BN == 64 && BK == 32 && WM * WN == 4) {
+    if (g.c_lower && n0 == m0 && g.a_tri == 0 && g.kblocks <= 1) {
+      const int w = tid >> 5;
+      double d0[8][8], d1[8][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { d0[i][j] = 0.0; d1[i][j] = 0.0; }
+#pragma unroll
+      for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < ktiles) load_stage(s, koff(s));
+        cp_async_commit();
+      }
+      for (int kt = 0; kt < ktiles; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+          int nk = kt + STAGES - 1;
+          if (nk < ktiles) load_stage(nk % STAGES, koff(nk));
+          cp_async_commit();
+        }
+        const int st = kt % STAGES;
+        const double* as = As + st * A_STAGE + g8 * LDA + t4;
+        const double* bs = Bs + st * B_STAGE + g8 * LDB + t4;
+        const double* ss = Ss + st * BK + t4;
+#pragma unroll
+        for (int q = 0; q < BK / 16; ++q) {
+          const int kk = w * (BK / 16) + q;   // this warp's k-steps of the tile
+          double a[8], bb[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] = as[i * 8 * LDA + kk * 4];
+          if (Sb) {
+            const double sc = ss[kk * 4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] *= sc;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bb[j] = bs[j * 8 * LDB + kk * 4];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j <= i) dmma884(d0[i][j], d1[i][j], a[i], bb[j]);
+        }
+      }
+      cp_async_wait<0>();
+      __syncthreads();
+      // cross-warp sum in a fixed order through shared memory: red[w][unit][64]
+      double* red = smem;
+      static_assert((size_t)4 * 36 * 64 * sizeof(double) <= Cfg::SMEM, "reduction scratch fits in the operand ring");
+      {
+        int u = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j <= i) {
+              *reinterpret_cast<double2*>(red + ((size_t)(w * 36 + u) * 64) + g8 * 8 + 2 * t4) = make_double2(d0[i][j], d1[i][j]);
+              ++u;
+            }
+      }
+      __syncthreads();
+      double* Pp = g.splitk > 1 ? g.part + ((long)split * g.batch + b) * (long)g.M * g.N : nullptr;
+      double* Cb = g.C + (long)b * g.sC;
+      for (int idx = tid; idx < 64 * 64; idx += THREADS) {
+        const int r = idx >> 6, cc = idx & 63;
+        const int i = r >> 3, j = cc >> 3;
+        double v = 0.0;
+        if (j <= i) {
+          const int u = i * (i + 1) / 2 + j;
+          const int e = (r & 7) * 8 + (cc & 7);
+          v = ((red[(size_t)(0 * 36 + u) * 64 + e] + red[(size_t)(1 * 36 + u) * 64 + e]) + red[(size_t)(2 * 36 + u) * 64 + e]) +
+              red[(size_t)(3 * 36 + u) * 64 + e];
+        }
+        if (Pp) Pp[(long)(m0 + r) * g.N + n0 + cc] = v;
+        else {
+          double* p = Cb + (long)(m0 + r) * g.ldc + n0 + cc;
+          double o = g.alpha * v;
+          if (g.beta != 0.0) o += g.beta * *p;
+          *p = o;
+        }
+      }
+      return;
+    }
+  }
+
   double c0[TM][TN], c1[TM][TN];
 #pragma unroll
   for (int i = 0; i < TM; ++i)

@@ -14,13 +14,18 @@ cases = [  # name, nt, M, N, K, tri, clower, batch, splitk
     ("dKu=-Wg A^T   (NT, split-K)", 1, 256, 256, P, 0, 0, 1, 27),
     ("dR=A s T^T x8 (NT c_lower, kscale, split-K)", 1, 256, 256, P, 0, 1, 8, 11),
     ("dR no kscale  (NT c_lower, split-K)", 1, 256, 256, P, 0, 1, 8, 11),
+    ("dR splitk 14", 1, 256, 256, P, 0, 1, 8, 14),
+    ("dR splitk 18", 1, 256, 256, P, 0, 1, 8, 18),
+    ("dR splitk 22", 1, 256, 256, P, 0, 1, 8, 22),
+    ("dR splitk 33", 1, 256, 256, P, 0, 1, 8, 33),
+    ("dR splitk 44", 1, 256, 256, P, 0, 1, 8, 44),
     ("dqmu=A Gm     (NN N=32 split-K)", 0, 256, 32, P, 0, 0, 1, 32),
 ]
 for name, nt, M, N, K, tri, clow, batch, sk in cases:
     A = torch.randn(batch, M, K, dtype=torch.float64, device="cuda")
     B = torch.randn(batch, N, K, dtype=torch.float64, device="cuda") if nt else torch.randn(batch, K, N, dtype=torch.float64, device="cuda")
     C = torch.zeros(batch, M, N, dtype=torch.float64, device="cuda")
-    ks = torch.randn(batch, K, dtype=torch.float64, device="cuda") if (nt and clow and "no kscale" not in name) else None
+    ks = torch.randn(batch, K, dtype=torch.float64, device="cuda") if (nt and clow and "x8" in name) else None
     def run():
         ctx.call("dgp_debug_gemm", nt, M, N, K, 1.0, D._lib.ptr(A), D._lib.ptr(B), 0.0, D._lib.ptr(C), tri, clow, batch, sk, D._lib.ptr(ks))
     for _ in range(3): run()
