@@ -242,10 +242,10 @@ def main():
     k_fwd = kernel_entry("dgp::fused_forward_kernel (Kuf tile -> V = Lu^-1 Kuf -> T_d = (q_sqrt_d^T Lu^-T) V -> moments/sample, FP64 DMMA, "
                          "TMA bulk-copy operand ring)" if prof["fused_fwd"][0] > 0 else "dgp::gemm_kernel (forward contractions)",
                          fwd_cats, f_fwd,
-                         # ncu --set full capture profiles/r01c_fused_forward_ncu.txt: dram read+write 1.2027 GB for one launch over
+                         # ncu --set full capture profiles/r01e_fused_forward_ncu.txt: dram read+write 1.1754 GB for one launch over
                          # 65 536 point-samples of an 8->8 layer (= the 18.4 KB A/T_d stash per point-sample, no re-reads), scaled
                          # to this run's launch size
-                         traffic=(1.2027e9 / 65536) * nb * S if prof["fused_fwd"][0] > 0 and args.config == "c2" else None)
+                         traffic=(1.1754e9 / 65536) * nb * S if prof["fused_fwd"][0] > 0 and args.config == "c2" else None)
     k_bwd = kernel_entry("dgp::gemm_kernel (FP64 DMMA adjoint contractions: dV = sum_d C_d^T dT_d, Lu^-T dV, tril(dV V^T), "
                          "tril(V diag(2Gv_d) T_d^T), V Gm, Gbar [X,1])", ["gemm_bwd_data", "gemm_bwd_param"], 2 * f_fwd)
     main, other = (k_bwd, k_fwd) if k_bwd["kernel_ms_per_step"] >= k_fwd["kernel_ms_per_step"] else (k_fwd, k_bwd)
