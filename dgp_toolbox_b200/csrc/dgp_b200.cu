@@ -565,12 +565,18 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
     r.W = Kbar; r.A = nullptr; r.gq = up.gq; r.Gbar = Gbar; r.Xin = cl.Xin; r.xmod = cl.xmod; r.Z = d.Z; r.ls = d.lengthscales;
     r.var = d.variance; r.M = w.M; r.Mp = Mp; r.D_in = w.D_in; r.P = P; r.Pp = Pp; r.Gm = up.Gm; r.D_out = D;
     r.mean_kind = d.mean_kind; r.mfW = d.mf_W; r.kind = d.kernel_kind; r.dXin = dXin; r.XaugPad = XaugPad; r.part = rbf_part;
-    const long nbv = Pp / 128;
-    const size_t smemv = ((size_t)w.M * w.D_in + kMaxD + 32) * sizeof(double);
+    const bool small = Pp / 128 < 2L * c->num_sms;   // latency-bound launch: 64-column blocks with 4 row groups
+    const long nbv = small ? Pp / kRbfCols : Pp / 128;
+    const size_t smemv = small ? rbf_bwd_smem_bytes(w.M, w.D_in) : ((size_t)w.M * w.D_in + kMaxD + 32) * sizeof(double);
     RC(dispatch_dmax(w.D_in, [&](auto dm) -> int {
       constexpr int DM = decltype(dm)::value;
-      if (!c->dry) CK(cudaFuncSetAttribute((rbf_bwd_kernel<DM, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      LAUNCH((rbf_bwd_kernel<DM, true>), (unsigned)nbv, 128, smemv, r);
+      if (small) {
+        if (!c->dry) CK(cudaFuncSetAttribute((rbf_bwd2d_kernel<DM, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        LAUNCH((rbf_bwd2d_kernel<DM, true>), (unsigned)nbv, 256, smemv, r);
+      } else {
+        if (!c->dry) CK(cudaFuncSetAttribute((rbf_bwd_kernel<DM, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        LAUNCH((rbf_bwd_kernel<DM, true>), (unsigned)nbv, 128, smemv, r);
+      }
       return DGP_OK;
     }));
     if (!params) return DGP_OK;
@@ -613,12 +619,18 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
   r.W = W; r.A = cl.A; r.gq = up.gq; r.Gbar = Gbar; r.Xin = cl.Xin; r.xmod = cl.xmod; r.Z = d.Z; r.ls = d.lengthscales;
   r.var = d.variance; r.M = w.M; r.Mp = Mp; r.D_in = w.D_in; r.P = P; r.Pp = Pp; r.Gm = up.Gm; r.D_out = D;
   r.mean_kind = d.mean_kind; r.mfW = d.mf_W; r.kind = d.kernel_kind; r.dXin = dXin; r.XaugPad = XaugPad; r.part = rbf_part;
-  const long nb = Pp / 128;
-  const size_t smem = ((size_t)w.M * w.D_in + kMaxD + 32) * sizeof(double);
+  const bool small = Pp / 128 < 2L * c->num_sms;   // latency-bound launch: 64-column blocks with 4 row groups
+  const long nb = small ? Pp / kRbfCols : Pp / 128;
+  const size_t smem = small ? rbf_bwd_smem_bytes(w.M, w.D_in) : ((size_t)w.M * w.D_in + kMaxD + 32) * sizeof(double);
   RC(dispatch_dmax(w.D_in, [&](auto dm) -> int {
     constexpr int DM = decltype(dm)::value;
-    if (!c->dry) CK(cudaFuncSetAttribute((rbf_bwd_kernel<DM, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    LAUNCH((rbf_bwd_kernel<DM, false>), (unsigned)nb, 128, smem, r);
+    if (small) {
+      if (!c->dry) CK(cudaFuncSetAttribute((rbf_bwd2d_kernel<DM, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      LAUNCH((rbf_bwd2d_kernel<DM, false>), (unsigned)nb, 256, smem, r);
+    } else {
+      if (!c->dry) CK(cudaFuncSetAttribute((rbf_bwd_kernel<DM, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      LAUNCH((rbf_bwd_kernel<DM, false>), (unsigned)nb, 128, smem, r);
+    }
     return DGP_OK;
   }));
   if (!params) return DGP_OK;   // input gradient only (acquisition): the contractions over the point-samples are not needed
@@ -746,7 +758,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
     XaugPad = walloc(c, (size_t)Ppmax * 32);
     dXa = walloc(c, (size_t)Ppmax * 32);
     dXb = walloc(c, (size_t)Ppmax * 32);
-    rbf_part = walloc(c, (size_t)nbmax * 32);
+    rbf_part = walloc(c, (size_t)nbmax * 2 * 32);   // one row of partials per 64-column block of rbf_bwd_kernel
     skpart = walloc(c, max_splitk_part(lw));
   }
   if (c->dry) return DGP_OK;

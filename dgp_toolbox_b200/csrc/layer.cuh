@@ -321,6 +321,121 @@ struct RbfBwdArgs {
   double* part;         // [blocks][D_in + 1]
 };
 
+constexpr int kRbfCols = 64, kRbfRowGroups = 4;   // 256 threads: 64 point-sample columns x 4 interleaved row groups
+inline size_t rbf_bwd_smem_bytes(int M, int D_in) {
+  return ((size_t)M * D_in + kMaxD + 32 + (size_t)kRbfRowGroups * kRbfCols * D_in) * sizeof(double);
+}
+
+// Small launches (fewer blocks than two waves of the one-thread-per-column kernel below): latency-bound, so each thread walks
+// every 4th inducing row of its column and the row groups' partial input gradients are summed through shared memory.
+template <int DMAX, bool VF>   // VF: V-form (no A plane, K-bar read-only)
+__global__ void __launch_bounds__(256) rbf_bwd2d_kernel(RbfBwdArgs a) {
+  extern __shared__ double sh[];
+  double* zs = sh;                         // [M][D_in]  (unscaled)
+  double* il = zs + (long)a.M * a.D_in;    // [D_in] 1/l
+  double* red = il + kMaxD;                // [32]
+  double* dxs = red + 32;                  // [row groups][cols][D_in] partial input gradients
+  for (int i = threadIdx.x; i < a.M * a.D_in; i += blockDim.x) zs[i] = a.Z[i];
+  if (threadIdx.x < a.D_in) il[threadIdx.x] = 1.0 / a.ls[threadIdx.x];
+  __syncthreads();
+  const int cl = threadIdx.x & (kRbfCols - 1), rg = threadIdx.x / kRbfCols;
+  const long p = (long)blockIdx.x * kRbfCols + cl;  // < Pp
+  const bool live = p < a.P;
+  double x[DMAX], dx[DMAX], dl[DMAX], ds2 = 0.0;
+#pragma unroll
+  for (int j = 0; j < DMAX; ++j) {
+    x[j] = (live && j < a.D_in) ? a.Xin[(p % a.xmod) * a.D_in + j] : 0.0;
+    dx[j] = 0.0;
+    dl[j] = 0.0;
+  }
+  const double s2 = a.var[0];
+  const double g = a.gq[p];
+  // each thread walks every 4th inducing row of its column (4x the parallelism of one thread per column: the loop is
+  // latency-bound), in groups of 4 rows with all plane loads of a group issued up front (W is updated in place, so the
+  // compiler cannot hoist the next rows' loads above the stores on its own)
+  for (int mb = 0; mb < a.M; mb += 4 * kRbfRowGroups) {
+    double wv[4], av[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int m = mb + u * kRbfRowGroups + rg;
+      const long off = (long)m * a.Pp + p;
+      wv[u] = (m < a.M) ? a.W[off] : 0.0;
+      av[u] = (!VF && m < a.M) ? a.A[off] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int m = mb + u * kRbfRowGroups + rg;
+      if (m < a.M) {
+        const long off = (long)m * a.Pp + p;
+        const double w = wv[u], am = av[u];
+        double r2 = 0.0, t[DMAX];
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j)
+          if (j < a.D_in) {
+            t[j] = (zs[m * a.D_in + j] - x[j]) * il[j];
+            r2 = fma(t[j], t[j], r2);
+          }
+        double k = 0.0, gf = 0.0;
+        if (live) kernel_eval(a.kind, r2, s2, k, gf);
+        const double kbar = VF ? w : w + 2.0 * am * g;   // dELBO / dKuf[m][p]
+        const double gb = kbar * gf;            // K-bar times -2 dk/d(r2): drives dX, dZ, dl
+        if (!VF) a.W[off] = w + am * g;
+        a.Gbar[off] = gb;
+        ds2 += kbar * k;                        // d/d s2 = sum K-bar K / s2
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j)
+          if (j < a.D_in) {
+            dx[j] = fma(gb * t[j], il[j], dx[j]);       // Gbar (z-x)/l^2
+            dl[j] = fma(gb * t[j] * t[j], il[j], dl[j]);  // Gbar (z-x)^2/l^3
+          }
+      }
+    }
+  }
+  // input gradient of the column: sum of the row groups' partials in a fixed order
+#pragma unroll
+  for (int j = 0; j < DMAX; ++j)
+    if (j < a.D_in) dxs[((size_t)rg * kRbfCols + cl) * a.D_in + j] = dx[j];
+  __syncthreads();
+  if (rg == 0) {
+#pragma unroll
+    for (int j = 0; j < DMAX; ++j)
+      if (j < a.D_in) {
+        double v = 0.0;
+        for (int q = 0; q < kRbfRowGroups; ++q) v += dxs[((size_t)q * kRbfCols + cl) * a.D_in + j];
+        dx[j] = v;
+      }
+    if (p < a.Pp) {
+#pragma unroll
+      for (int j = 0; j < DMAX; ++j)
+        if (j < a.D_in) a.XaugPad[p * 32 + j] = x[j];
+      for (int j = a.D_in; j < 32; ++j) a.XaugPad[p * 32 + j] = (j == a.D_in && live) ? 1.0 : 0.0;
+    }
+    if (a.dXin && live) {
+#pragma unroll
+      for (int j = 0; j < DMAX; ++j)
+        if (j < a.D_in) {
+          double v = dx[j];
+          if (a.mean_kind == 1) v += a.Gm[p * a.D_out + j];
+          else if (a.mean_kind == 2) {
+            for (int d = 0; d < a.D_out; ++d) v = fma(a.Gm[p * a.D_out + d], a.mfW[j * a.D_out + d], v);
+          }
+          a.dXin[p * a.D_in + j] = v;
+        }
+    }
+  }
+  for (int j = 0; j < a.D_in; ++j) {
+    double v = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < DMAX; ++jj)
+      if (jj == j) v = dl[jj];
+    double r = block_sum(v, red);
+    if (threadIdx.x == 0) a.part[(long)blockIdx.x * (a.D_in + 1) + j] = r;
+  }
+  double r = block_sum(ds2 / s2, red);
+  if (threadIdx.x == 0) a.part[(long)blockIdx.x * (a.D_in + 1) + a.D_in] = r;
+}
+
+// Large launches: one thread per point-sample column (bandwidth-friendlier 1 KB row segments per block).
 template <int DMAX, bool VF>   // VF: V-form (no A plane, K-bar read-only)
 __global__ void __launch_bounds__(128) rbf_bwd_kernel(RbfBwdArgs a) {
   extern __shared__ double sh[];
