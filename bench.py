@@ -113,7 +113,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2")
     ap.add_argument("--nb", type=int, default=16384, help="minibatch points per GPU per step")
-    ap.add_argument("--nb-cpu", type=int, default=256, help="points of the bounded CPU-baseline sample")
+    ap.add_argument("--nb-cpu", type=int, default=512, help="points of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -283,9 +283,9 @@ def main():
         "elbo_last_step": elbo,
     }
     if world == 1 and not args.no_cpu_baseline:
-        val, dt, cores = cpu_reference_throughput(cfg, args.nb_cpu, 3, 1)
+        val, dt, cores = cpu_reference_throughput(cfg, args.nb_cpu, 10, 2)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"N_b={args.nb_cpu} points x S={S} samples, 3 steps after 1 warm-up ({dt:.2f} s/step)"}
+                                "sample": f"N_b={args.nb_cpu} points x S={S} samples, 10 steps after 2 warm-ups ({dt:.2f} s/step)"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
