@@ -43,6 +43,11 @@ class GradOffsets(C.Structure):
                 ("dq_mu", C.c_int64), ("dq_sqrt", C.c_int64)]
 
 
+class AdamParam(C.Structure):
+    _fields_ = [("value", C.c_void_p), ("count", C.c_int64), ("grad_offset", C.c_int64), ("grad_count", C.c_int64),
+                ("transform", C.c_int32), ("M", C.c_int32), ("mirror", C.c_void_p), ("mirror_count", C.c_int64)]
+
+
 _vp, _i, _i64, _u64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_double
 _SIG = {
     "dgp_version": (C.c_int, []),
@@ -56,6 +61,7 @@ _SIG = {
     "dgp_launch_count": (_i64, [_vp, _i]),
     "dgp_set_profiling": (C.c_int, [_vp, _i]),
     "dgp_set_fused": (C.c_int, [_vp, _i]),
+    "dgp_set_graph": (C.c_int, [_vp, _i]),
     "dgp_set_share_first_layer": (C.c_int, [_vp, _i]),
     "dgp_set_vform": (C.c_int, [_vp, _i, _i]),
     "dgp_set_parallel_layers": (C.c_int, [_vp, _i]),
@@ -73,6 +79,9 @@ _SIG = {
     "dgp_elbo_grad": (C.c_int, [_vp, C.POINTER(ModelDesc), _vp, _vp, _i64, _i64, _d, _d, C.POINTER(_vp), _u64, _i64,
                                 _i, _vp]),
     "dgp_elbo_grad_host": (C.c_int, [_vp, C.POINTER(ModelDesc), _vp, _vp, _i64, _i64, _d, _d, _u64, _i64, _i, _vp]),
+    "dgp_adam_step": (C.c_int, [_vp, C.POINTER(AdamParam), _i, _vp, _vp, _vp, _i64, _d, _d, _d, _d]),
+    "dgp_train_adam": (C.c_int, [_vp, C.POINTER(ModelDesc), _vp, _vp, _i64, _i64, _d, _d, _u64, _u64, _i64, C.POINTER(AdamParam), _i,
+                                 _vp, _vp, _i64, _i64, _d, _d, _d, _d, _vp, _vp]),
     "dgp_predict_moments": (C.c_int, [_vp, C.POINTER(ModelDesc), _vp, _i64, _i64, C.POINTER(_vp), _u64, _i64, _i,
                                       _vp, _vp]),
     "dgp_ei": (C.c_int, [_vp, C.POINTER(ModelDesc), _vp, _i64, _i64, C.POINTER(_vp), _u64, _i64, _d, _i, _vp]),
@@ -147,6 +156,13 @@ class Context:
 
     def set_fused(self, on: bool):
         lib.dgp_set_fused(self.h, 1 if on else 0)
+
+    def set_graph(self, on: bool):
+        """CUDA-graph replay of the model-level calls (dgp_set_graph): for launch-bound, BO-sized problems whose buffers stay
+        in place from call to call. Turning it off drops the cached graphs."""
+        rc = lib.dgp_set_graph(self.h, 1 if on else 0)
+        if rc != 0:
+            raise DGPError(f"dgp_set_graph ({rc}): {lib.dgp_last_error(self.h).decode()}")
 
     def set_workspace_limit(self, nbytes: int):
         rc = lib.dgp_set_workspace_limit(self.h, int(nbytes))

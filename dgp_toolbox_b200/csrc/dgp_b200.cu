@@ -4,6 +4,7 @@
 // and acq.cuh (acquisition epilogues). There is no CPU fallback: without a CUDA device every call fails.
 #include "../../include/dgp_b200.h"
 
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -32,6 +33,22 @@ struct dgp_ctx {
   int num_sms = 148;
   bool chol_configured = false;
   int* d_info = nullptr;                // Cholesky failure flag
+  // CUDA-graph replay of the ELBO+gradient step (dgp_set_graph): the step's launch sequence depends only on shapes, pointers
+  // and flags, so it is captured once per distinct call signature and replayed; the Philox key is read from d_seed
+  unsigned long long* d_seed = nullptr; // device slot holding the seed of a replayed step
+  const unsigned long long* seed_ptr = nullptr;   // non-null while capturing: kernels read the seed from it
+  bool use_graph = false;
+  cudaStream_t cap_stream = nullptr;    // capture happens on a private stream (the caller's may be the legacy default stream)
+  struct GraphEntry {
+    std::vector<unsigned char> key;
+    cudaGraphExec_t exec = nullptr;
+    long launches = 0;
+    std::vector<void*> pinned;          // host tables the captured copies read at every replay
+    unsigned long last_use = 0;
+  };
+  std::vector<GraphEntry> graphs;
+  unsigned long graph_tick = 0;
+  std::vector<void*>* keep = nullptr;   // non-null while capturing
   double* h_pinned = nullptr;           // staging for the *_host entry points
   size_t h_pinned_bytes = 0;
   double* d_stage = nullptr;            // device side of that staging (outside the arena, which may be re-grown)
@@ -110,6 +127,23 @@ double* walloc(dgp_ctx* c, size_t n_doubles) {
   return reinterpret_cast<double*>(c->ws + off);
 }
 
+// Source pointer for a host->device table upload. While a step is being captured into a CUDA graph the copy node re-reads its
+// source at every replay, so the table is moved into pinned memory owned by the graph entry.
+const void* host_src(dgp_ctx* c, const void* p, size_t bytes) {
+  if (!c->keep) return p;
+  void* h = nullptr;
+  if (cudaMallocHost(&h, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  memcpy(h, p, bytes);
+  c->keep->push_back(h);
+  return h;
+}
+#define H2D(dst, src, bytes)                                                                       \
+  do {                                                                                             \
+    const void* s__ = host_src(c, (src), (bytes));                                                 \
+    if (!s__) { c->err = "cudaMallocHost failed while capturing a graph"; return DGP_ERR_CUDA; }   \
+    CK(cudaMemcpyAsync((dst), s__, (bytes), cudaMemcpyHostToDevice, c->stream));                   \
+  } while (0)
+
 struct LayerFork {   // fork the ctx's stream into per-layer side streams for a loop over layers, join afterwards
   dgp_ctx* c; cudaStream_t main; int n; bool active = false;
   LayerFork(dgp_ctx* ctx, int nlayers) : c(ctx), main(ctx->stream), n(nlayers < dgp_ctx::kAux ? nlayers : dgp_ctx::kAux) {
@@ -136,9 +170,12 @@ struct LayerFork {   // fork the ctx's stream into per-layer side streams for a 
   ~LayerFork() { join(); }
 };
 
+void drop_graphs(dgp_ctx* c);
+
 int ensure_ws(dgp_ctx* c, size_t need) {
   if (need <= c->cap) return DGP_OK;
   CK(cudaStreamSynchronize(c->stream));
+  drop_graphs(c);   // captured steps point into the arena being replaced
   if (c->ws) CK(cudaFree(c->ws));
   c->ws = nullptr;
   c->cap = 0;
@@ -186,6 +223,16 @@ int pick_splitk(dgp_ctx* c, const GemmArgs& g, bool nt) {
   const long ktiles = g.K / 16;
   if (smax > ktiles / 8) smax = ktiles / 8;
   if (smax < 1) smax = 1;
+  if (p.tiles * smax < p.slots) {
+    // Even the finest regular split leaves SMs idle: the product is latency-bound (one serial k-loop per CTA), not
+    // throughput-bound. Cut K down to two k-steps per CTA, as far as the CTAs still fit in one wave.
+    long s = ktiles / 4;
+    if (s > 64) s = 64;
+    if (s * p.tiles > p.slots) s = p.slots / p.tiles;
+    if ((size_t)s * out_doubles > kSplitkPartDoubles) s = (long)(kSplitkPartDoubles / out_doubles);
+    while (s > 1 && (s - 1) * ((ktiles + s - 1) / s) >= ktiles) --s;   // no empty last chunk
+    return (int)(s < 1 ? 1 : s);
+  }
   if (nt && g.c_lower && p.BM == 64 && gemm_small_bk32(g, nt)) {
     // lower-only NT product: its diagonal tiles run the 36-of-64-unit path and finish in ~0.56 of the time of the others, so
     // the CTAs are not uniform and many short CTAs pack better than whole waves of long ones (measured: 11 -> 33 splits, -10%)
@@ -350,12 +397,12 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
   if (c->dry) return DGP_OK;
   std::vector<double*> hinv(nl), hinvT(nl);
   for (int l = 0; l < nl; ++l) { hinv[l] = lw[l].Linv; hinvT[l] = lw[l].LinvT; }
-  CK(cudaMemcpyAsync(dinv, hinv.data(), sizeof(double*) * nl, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(dinvT, hinvT.data(), sizeof(double*) * nl, cudaMemcpyHostToDevice, c->stream));
+  H2D(dinv, hinv.data(), sizeof(double*) * nl);
+  H2D(dinvT, hinvT.data(), sizeof(double*) * nl);
 
   CAT(DGP_CAT_PREP);
   CK(cudaMemsetAsync(c->d_info, 0, sizeof(int), c->stream));
-  CK(cudaMemcpyAsync(dargs, hargs.data(), sizeof(CholArgs) * nl, cudaMemcpyHostToDevice, c->stream));
+  H2D(dargs, hargs.data(), sizeof(CholArgs) * nl);
   LayerFork forkA(c, nl);
   for (int l = 0; l < nl; ++l) {
     forkA.use(l);
@@ -400,7 +447,7 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
     }
     std::vector<PanelDesc> sch = build_schedule(w.Mp, BM, w.D_out, w.vform);
     if ((int)sch.size() != w.NP) { c->err = "internal: panel schedule size mismatch"; return DGP_ERR_ARG; }
-    CK(cudaMemcpyAsync(w.sched, sch.data(), sch.size() * sizeof(PanelDesc), cudaMemcpyHostToDevice, c->stream));
+    H2D(w.sched, sch.data(), sch.size() * sizeof(PanelDesc));
     LAUNCH(scale_z_kernel, (unsigned)((w.M * w.D_in + 255) / 256), 256, 0, d.Z, d.lengthscales, w.M, w.D_in, w.Zs);
     const double* tsrc = w.vform ? w.Cmat : w.RpT;   // operator of the T_d passes
     if (BM == 128) LAUNCH(pack_stream_kernel<128>, w.NP, 256, 0, w.sched, w.Linv, w.LinvT, tsrc, w.Mp, w.stream);
@@ -463,7 +510,7 @@ int forward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, ChunkLa
     f.vform = w.vform ? 1 : 0; f.qmu = w.vform ? w.betaP : d.q_mu; f.qmu_ld = w.vform ? 32 : w.D_out;
     f.Xin = cl.Xin; f.xmod = cl.xmod; f.D_in = w.D_in; f.mfW = d.mf_W; f.mfb = d.mf_b; f.mean_kind = d.mean_kind; f.kind = d.kernel_kind;
     f.z_in = (io.zs && io.zs[layer]) ? io.zs[layer] : nullptr;
-    f.seed = seed; f.layer = layer; f.Nc = Nc; f.N_total = N_total; f.n0 = n0; f.n_offset = n_offset;
+    f.seed = seed; f.seed_ptr = c->seed_ptr; f.layer = layer; f.Nc = Nc; f.N_total = N_total; f.n0 = n0; f.n_offset = n_offset;
     f.M = w.M; f.Mp = w.Mp; f.D_out = w.D_out; f.P = P; f.Pp = Pp; f.jitter = d.jitter;
     f.Fmean = cl.Fmean; f.Fvar = cl.Fvar; f.F = need_sample ? cl.F : nullptr; f.z = need_sample ? cl.z : nullptr;
     f.xFmean = (io.Fmeans && io.Fmeans[layer]) ? io.Fmeans[layer] : nullptr;
@@ -513,7 +560,7 @@ int forward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, ChunkLa
   a.Xin = cl.Xin; a.xmod = cl.xmod; a.D_in = w.D_in;
   a.mfW = d.mf_W; a.mfb = d.mf_b; a.mean_kind = d.mean_kind;
   a.z_in = (io.zs && io.zs[layer]) ? io.zs[layer] : nullptr;
-  a.seed = seed; a.layer = layer; a.Nc = Nc; a.N_total = N_total; a.n0 = n0; a.n_offset = n_offset;
+  a.seed = seed; a.seed_ptr = c->seed_ptr; a.layer = layer; a.Nc = Nc; a.N_total = N_total; a.n0 = n0; a.n_offset = n_offset;
   a.M = w.M; a.Mp = Mp; a.D_out = D; a.P = P; a.Pp = Pp; a.jitter = d.jitter;
   a.Fmean = cl.Fmean; a.Fvar = cl.Fvar; a.F = need_sample ? cl.F : nullptr; a.z = need_sample ? cl.z : nullptr;
   a.xFmean = (io.Fmeans && io.Fmeans[layer]) ? io.Fmeans[layer] : nullptr;
@@ -784,7 +831,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
         ExpandArgs e;
         memset(&e, 0, sizeof(e));
         e.mean0 = cl.Fmean; e.var0 = cl.Fvar; e.z_in = (o.io.zs && o.io.zs[0]) ? o.io.zs[0] : nullptr;
-        e.seed = seed; e.layer = 0; e.Nc = Nc; e.N_total = N; e.n0 = n0; e.n_offset = n_offset; e.S = S; e.D = d.D_out;
+        e.seed = seed; e.seed_ptr = c->seed_ptr; e.layer = 0; e.Nc = Nc; e.N_total = N; e.n0 = n0; e.n_offset = n_offset; e.S = S; e.D = d.D_out;
         e.jitter = d.jitter; e.F = cl.F; e.z = cl.z;
         e.xFmean = (o.io.Fmeans && o.io.Fmeans[0]) ? o.io.Fmeans[0] : nullptr;
         e.xFvar = (o.io.Fvars && o.io.Fvars[0]) ? o.io.Fvars[0] : nullptr;
@@ -951,10 +998,110 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
   return DGP_OK;
 }
 
+void drop_graphs(dgp_ctx* c) {
+  for (auto& g : c->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (void* h : g.pinned) cudaFreeHost(h);
+  }
+  c->graphs.clear();
+}
+
+__global__ void set_seed_kernel(unsigned long long* slot, unsigned long long seed) { *slot = seed; }
+
+template <typename T>
+void key_put(std::vector<unsigned char>& k, const T& v) {
+  const unsigned char* p = reinterpret_cast<const unsigned char*>(&v);
+  k.insert(k.end(), p, p + sizeof(T));
+}
+
+// Everything the launch sequence of a step depends on, except the seed (read from c->d_seed by a replayed step).
+std::vector<unsigned char> graph_key(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, long S, long n_offset,
+                                     const RunOpts& o) {
+  std::vector<unsigned char> k;
+  k.reserve(512);
+  key_put(k, model->num_layers); key_put(k, model->lik_variance);
+  for (int l = 0; l < model->num_layers; ++l) {
+    const dgp_layer_desc& d = model->layers[l];
+    key_put(k, d.D_in); key_put(k, d.D_out); key_put(k, d.M); key_put(k, d.white); key_put(k, d.mean_kind); key_put(k, d.kernel_kind);
+    key_put(k, d.Z); key_put(k, d.lengthscales); key_put(k, d.variance); key_put(k, d.q_mu); key_put(k, d.q_sqrt);
+    key_put(k, d.mf_W); key_put(k, d.mf_b); key_put(k, d.jitter);
+  }
+  key_put(k, X); key_put(k, N); key_put(k, S); key_put(k, n_offset);
+  key_put(k, o.want_grad); key_put(k, o.want_elbo); key_put(k, o.Y); key_put(k, o.Dy); key_put(k, o.scale); key_put(k, o.kl_weight);
+  key_put(k, o.out_flat); key_put(k, o.pm); key_put(k, o.pv); key_put(k, o.add_lik); key_put(k, o.ei); key_put(k, o.y_min);
+  key_put(k, o.ei_analytic); key_put(k, o.need_last_sample); key_put(k, o.dx);
+  key_put(k, c->use_fused); key_put(k, c->use_vform); key_put(k, c->use_vform_grad); key_put(k, c->vform_forward_calls);
+  key_put(k, c->vform_grad_min_ps); key_put(k, c->share_first_layer); key_put(k, c->parallel_layers); key_put(k, c->ws_limit);
+  return k;
+}
+
+constexpr size_t kMaxGraphs = 16;
+
+// Replay path of run_model_planned: capture the step once per call signature, then one seed store + one graph launch per call.
+int run_model_graphed(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, long S, unsigned long long seed,
+                      long n_offset, RunOpts& o) {
+  std::vector<unsigned char> key = graph_key(c, model, X, N, S, n_offset, o);
+  dgp_ctx::GraphEntry* hit = nullptr;
+  for (auto& g : c->graphs)
+    if (g.key == key) { hit = &g; break; }
+  if (!hit) {
+    c->dry = true; c->used = 0;
+    int rc = run_model(c, model, X, N, S, seed, n_offset, o);
+    c->dry = false;
+    if (rc != DGP_OK) return rc;
+    RC(ensure_ws(c, c->used));   // may drop every cached graph (their nodes point into the old arena)
+    c->used = 0;
+    if (!c->cap_stream) CK(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
+    if (!c->d_seed) CK(cudaMalloc(&c->d_seed, sizeof(unsigned long long)));
+    if (c->graphs.size() >= kMaxGraphs) {   // evict the least recently used entry
+      size_t lru = 0;
+      for (size_t i = 1; i < c->graphs.size(); ++i)
+        if (c->graphs[i].last_use < c->graphs[lru].last_use) lru = i;
+      CK(cudaStreamSynchronize(c->stream));
+      if (c->graphs[lru].exec) cudaGraphExecDestroy(c->graphs[lru].exec);
+      for (void* h : c->graphs[lru].pinned) cudaFreeHost(h);
+      c->graphs.erase(c->graphs.begin() + (long)lru);
+    }
+    dgp_ctx::GraphEntry e;
+    e.key = std::move(key);
+    cudaStream_t user = c->stream;
+    const long launches0 = c->launches;
+    CK(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeRelaxed));
+    c->stream = c->cap_stream; c->seed_ptr = c->d_seed; c->keep = &e.pinned;
+    rc = run_model(c, model, X, N, S, seed, n_offset, o);
+    c->stream = user; c->seed_ptr = nullptr; c->keep = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(c->cap_stream, &graph);
+    e.launches = c->launches - launches0;
+    c->launches = launches0;
+    if (rc == DGP_OK && ce != cudaSuccess) { c->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); rc = DGP_ERR_CUDA; }
+    if (rc == DGP_OK) {
+      ce = cudaGraphInstantiate(&e.exec, graph, 0);
+      if (ce != cudaSuccess) { c->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce); rc = DGP_ERR_CUDA; }
+    }
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != DGP_OK) {
+      cudaGetLastError();
+      for (void* h : e.pinned) cudaFreeHost(h);
+      return rc;
+    }
+    c->graphs.push_back(std::move(e));
+    hit = &c->graphs.back();
+  }
+  hit->last_use = ++c->graph_tick;
+  set_seed_kernel<<<1, 1, 0, c->stream>>>(c->d_seed, seed);
+  CK(cudaGetLastError());
+  CK(cudaGraphLaunch(hit->exec, c->stream));
+  c->launches += hit->launches + 1;
+  return DGP_OK;
+}
+
 // plan (dry) pass to size the arena, then the real pass
 int run_model_planned(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, long S, unsigned long long seed,
                       long n_offset, RunOpts& o) {
   CK(cudaSetDevice(c->device));
+  if (c->use_graph && !c->profiling && !o.io.zs && !o.io.Fs && !o.io.Fmeans && !o.io.Fvars)
+    return run_model_graphed(c, model, X, N, S, seed, n_offset, o);
   c->dry = true; c->used = 0;
   int rc = run_model(c, model, X, N, S, seed, n_offset, o);
   c->dry = false;
@@ -1007,6 +1154,9 @@ void dgp_ctx_destroy(dgp_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  drop_graphs(c);
+  if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+  if (c->d_seed) cudaFree(c->d_seed);
   if (c->ws) cudaFree(c->ws);
   if (c->d_info) cudaFree(c->d_info);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -1060,6 +1210,17 @@ int dgp_check(dgp_ctx* c) {
 int dgp_set_share_first_layer(dgp_ctx* c, int on) {
   if (!c) return DGP_ERR_ARG;
   c->share_first_layer = on != 0;
+  return DGP_OK;
+}
+
+int dgp_set_graph(dgp_ctx* c, int on) {
+  if (!c) return DGP_ERR_ARG;
+  c->use_graph = on != 0;
+  if (!on) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    drop_graphs(c);
+  }
   return DGP_OK;
 }
 
@@ -1215,6 +1376,63 @@ int dgp_elbo_grad(dgp_ctx* c, const dgp_model_desc* model, const double* X, cons
   o.Y = Y; o.Dy = model->layers[model->num_layers - 1].D_out;
   o.scale = scale; o.kl_weight = kl_weight; o.out_flat = out_flat; o.io.zs = zs_host;
   return run_model_planned(c, model, X, N, S, seed, n_offset, o);
+}
+
+namespace {
+int adam_table(dgp_ctx* c, const dgp_adam_param* params, int n_params, AdamTable& t) {
+  if (!params || n_params < 1) { c->err = "no parameters to optimise"; return DGP_ERR_ARG; }
+  if (n_params > kAdamMaxParams) { c->err = "more than 48 parameters in one Adam launch"; return DGP_ERR_UNSUPPORTED; }
+  memset(&t, 0, sizeof(t));
+  t.n = n_params;
+  long start = 0;
+  for (int i = 0; i < n_params; ++i) {
+    const dgp_adam_param& p = params[i];
+    if (!p.value || p.count < 1 || p.grad_offset < 0 || p.transform < 0 || p.transform > 3 ||
+        (p.grad_count != p.count && p.count != 1) || p.grad_count < 1 ||
+        (p.transform == 3 && (p.M < 1 || p.count % ((int64_t)p.M * p.M) != 0)) || (p.mirror && p.mirror_count < 1)) {
+      c->err = "invalid dgp_adam_param";
+      return DGP_ERR_ARG;
+    }
+    AdamSeg& sg = t.seg[i];
+    sg.value = p.value; sg.mirror = p.mirror; sg.start = start; sg.count = p.count; sg.grad_offset = p.grad_offset;
+    sg.grad_count = p.grad_count; sg.mirror_count = p.mirror ? p.mirror_count : 0; sg.transform = p.transform; sg.M = p.M > 0 ? p.M : 1;
+    start += p.count;
+  }
+  t.total = start;
+  return DGP_OK;
+}
+
+int adam_launch(dgp_ctx* c, const AdamTable& t, const double* grad, double* m, double* v, int64_t step, double lr, double b1,
+                double b2, double eps, double* trace) {
+  const double lr_t = lr * sqrt(1.0 - pow(b2, (double)step)) / (1.0 - pow(b1, (double)step));
+  CAT(DGP_CAT_OTHER);
+  LAUNCH(adam_kernel, (unsigned)((t.total + 255) / 256), 256, 0, t, grad, m, v, lr_t, b1, b2, eps, trace);
+  return DGP_OK;
+}
+}  // namespace
+
+int dgp_adam_step(dgp_ctx* c, const dgp_adam_param* params, int n_params, const double* grad_flat, double* m_state,
+                  double* v_state, int64_t t, double lr, double beta1, double beta2, double epsilon) {
+  if (!c || !grad_flat || !m_state || !v_state || t < 1) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  AdamTable tab;
+  RC(adam_table(c, params, n_params, tab));
+  return adam_launch(c, tab, grad_flat, m_state, v_state, t, lr, beta1, beta2, epsilon, nullptr);
+}
+
+int dgp_train_adam(dgp_ctx* c, const dgp_model_desc* model, const double* X, const double* Y, int64_t N, int64_t S, double scale,
+                   double kl_weight, uint64_t seed0, uint64_t seed_stride, int64_t n_offset, const dgp_adam_param* params,
+                   int n_params, double* m_state, double* v_state, int64_t t0, int64_t steps, double lr, double beta1,
+                   double beta2, double epsilon, double* out_flat, double* elbo_trace) {
+  if (!c || !model || !X || !Y || !out_flat || !m_state || !v_state || t0 < 1 || steps < 0) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  AdamTable tab;
+  RC(adam_table(c, params, n_params, tab));
+  for (int64_t k = 0; k < steps; ++k) {
+    RC(dgp_elbo_grad(c, model, X, Y, N, S, scale, kl_weight, nullptr, seed0 + (uint64_t)k * seed_stride, n_offset, 1, out_flat));
+    RC(adam_launch(c, tab, out_flat, m_state, v_state, t0 + k, lr, beta1, beta2, epsilon, elbo_trace ? elbo_trace + k : nullptr));
+  }
+  return DGP_OK;
 }
 
 int dgp_elbo_grad_host(dgp_ctx* c, const dgp_model_desc* model, const double* X_host, const double* Y_host, int64_t N,

@@ -112,7 +112,7 @@ struct FusedFwdArgs {
   const double* mfW; const double* mfb; int mean_kind;
   int kind;                                             // kernel kind (common.cuh: kernel_eval)
   const double* z_in;                                   // caller [S][N_total][D_out] or null -> Philox
-  unsigned long long seed; int layer; long Nc; long N_total; long n0; long n_offset;
+  unsigned long long seed; const unsigned long long* seed_ptr; int layer; long Nc; long N_total; long n0; long n_offset;
   int M, Mp, D_out; long P, Pp;
   double jitter;
   double* Fmean; double* Fvar; double* F; double* z;    // chunk-local [P][D_out]; F / z may be null
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
       if (a.xFvar) a.xFvar[xrow * a.D_out + d] = var;
       if (a.F) {
         const double z = a.z_in ? a.z_in[xrow * a.D_out + d]
-                                : philox_normal(a.seed, (uint32_t)a.layer, (uint32_t)s, (uint32_t)(a.n0 + n + a.n_offset), (uint32_t)d);
+                                : philox_normal(a.seed_ptr ? *a.seed_ptr : a.seed, (uint32_t)a.layer, (uint32_t)s, (uint32_t)(a.n0 + n + a.n_offset), (uint32_t)d);
         if (a.z) a.z[p * a.D_out + d] = z;
         const double f = mu + z * sqrt(var + a.jitter);
         a.F[p * a.D_out + d] = f;

@@ -59,7 +59,7 @@ struct MomentsArgs {
   const double* Xin; long xmod; int D_in;              // layer input (for the mean function)
   const double* mfW; const double* mfb; int mean_kind; // 0 zero, 1 identity, 2 linear
   const double* z_in;                                  // caller [S][N_total][D_out] or null -> Philox
-  unsigned long long seed; int layer; long Nc; long N_total; long n0; long n_offset;
+  unsigned long long seed; const unsigned long long* seed_ptr; int layer; long Nc; long N_total; long n0; long n_offset;
   int M, Mp, D_out; long P, Pp;
   double jitter;
   double* Fmean; double* Fvar; double* F; double* z;       // chunk-local [P][D_out]; F / z may be null
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(128) moments_kernel(MomentsArgs a) {
       if (a.xFvar) a.xFvar[xrow * a.D_out + d] = var;
       if (a.F) {
         const double z = a.z_in ? a.z_in[xrow * a.D_out + d]
-                                : philox_normal(a.seed, (uint32_t)a.layer, (uint32_t)s, (uint32_t)(a.n0 + n + a.n_offset), (uint32_t)d);
+                                : philox_normal(a.seed_ptr ? *a.seed_ptr : a.seed, (uint32_t)a.layer, (uint32_t)s, (uint32_t)(a.n0 + n + a.n_offset), (uint32_t)d);
         if (a.z) a.z[p * a.D_out + d] = z;
         const double f = mu + z * sqrt(var + a.jitter);
         a.F[p * a.D_out + d] = f;
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(128) moments_kernel(MomentsArgs a) {
 struct ExpandArgs {
   const double* mean0; const double* var0;     // [Nc][D]
   const double* z_in;                          // caller [S][N_total][D] or null -> Philox
-  unsigned long long seed; int layer; long Nc; long N_total; long n0; long n_offset; long S; int D;
+  unsigned long long seed; const unsigned long long* seed_ptr; int layer; long Nc; long N_total; long n0; long n_offset; long S; int D;
   double jitter;
   double* F; double* z;                        // chunk-local [S*Nc][D]
   double* xFmean; double* xFvar; double* xF;   // caller-visible, any may be null
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) expand_first_layer_kernel(ExpandArgs a) {
   const double mu = a.mean0[n * a.D + d], var = a.var0[n * a.D + d];
   const long xrow = s * a.N_total + a.n0 + n;
   const double z = a.z_in ? a.z_in[xrow * a.D + d]
-                          : philox_normal(a.seed, (uint32_t)a.layer, (uint32_t)s, (uint32_t)(a.n0 + n + a.n_offset), (uint32_t)d);
+                          : philox_normal(a.seed_ptr ? *a.seed_ptr : a.seed, (uint32_t)a.layer, (uint32_t)s, (uint32_t)(a.n0 + n + a.n_offset), (uint32_t)d);
   const double f = mu + z * sqrt(var + a.jitter);
   a.F[idx] = f;
   a.z[idx] = z;

@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(kCholThreads) chol_inv_kernel(const CholArgs* 
   extern __shared__ __align__(16) double sm[];
   double* D = sm;              // [32][33]
   double* Pn = sm + 32 * 33;   // [n][33]
+  double* Dinv = Pn + (size_t)n * 33;   // [32] reciprocals of the current diagonal block's pivots
   double* L = a.L;
 
   for (long idx = tid; idx < (long)n * n; idx += nth) {
@@ -68,23 +69,30 @@ __global__ void __launch_bounds__(kCholThreads) chol_inv_kernel(const CholArgs* 
     }
     __syncthreads();
     if (tid < 32) {
+      // lane r keeps row r of the block in registers; column j: the pivot and the multipliers l_cj travel by shuffle, so the
+      // 32-step dependency chain has no shared-memory round trips or barriers in it
       const int r = tid;
+      double row[32];
+#pragma unroll
+      for (int cc = 0; cc < 32; ++cc) row[cc] = D[r * 33 + cc];
+      bool bad = false;
+#pragma unroll
       for (int j = 0; j < 32; ++j) {
-        double djj = D[j * 33 + j];
-        if (r == j) {
-          if (!(djj > 0.0)) *a.info = 1;
-          D[j * 33 + j] = sqrt(djj);
+        const double djj = __shfl_sync(0xffffffffu, row[j], j);
+        bad |= !(djj > 0.0);
+        const double piv = sqrt(djj);
+        const double inv = 1.0 / piv;
+        row[j] = (r == j) ? piv : row[j] * inv;
+        if (r == j) Dinv[j] = inv;
+#pragma unroll
+        for (int cc = j + 1; cc < 32; ++cc) {
+          const double lcj = __shfl_sync(0xffffffffu, row[j], cc);
+          if (r >= cc) row[cc] = fma(-row[j], lcj, row[cc]);
         }
-        __syncwarp();
-        double piv = D[j * 33 + j];
-        if (r > j) D[r * 33 + j] = D[r * 33 + j] / piv;
-        __syncwarp();
-        if (r > j) {
-          double lrj = D[r * 33 + j];
-          for (int c = j + 1; c <= r; ++c) D[r * 33 + c] -= lrj * D[c * 33 + j];
-        }
-        __syncwarp();
       }
+      if (bad && r == 0) *a.info = 1;
+#pragma unroll
+      for (int cc = 0; cc < 32; ++cc) D[r * 33 + cc] = row[cc];
     }
     __syncthreads();
     for (int idx = tid; idx < 1024; idx += nth) {
@@ -103,7 +111,7 @@ __global__ void __launch_bounds__(kCholThreads) chol_inv_kernel(const CholArgs* 
         double s = x[c];
 #pragma unroll
         for (int k = 0; k < c; ++k) s -= x[k] * D[c * 33 + k];
-        x[c] = s / D[c * 33 + c];
+        x[c] = s * Dinv[c];
       }
       double* orow = L + (long)(k0 + kCholNB + r) * n + k0;
 #pragma unroll

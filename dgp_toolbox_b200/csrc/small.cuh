@@ -192,4 +192,57 @@ __global__ void unpad_square_kernel(const double* __restrict__ in, int M, int Mp
   out[idx] = in[(long)i * Mp + j];
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Adam on the unconstrained variables (models/dgp.py:132-154: tf.optimizers.Adam applied to the GPflow variables).
+// The model keeps constrained values, so one thread per entry maps value -> unconstrained u through the parameter's
+// bijector, applies the chain rule to the constrained-space ELBO gradient, updates (m, v, u) and writes bijector(u) back.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kAdamMaxParams = 48;
+struct AdamSeg {
+  double* value; double* mirror;   // parameter [count]; optional broadcast copy [mirror_count] (scalar lengthscale -> [D_in])
+  long start;                      // prefix offset into the (m, v) state
+  long count, grad_offset, grad_count, mirror_count;
+  int transform, M;                // 0 identity, 1 softplus, 2 softplus + 1e-6, 3 lower triangles of [count / M^2][M][M]
+};
+struct AdamTable { int n; long total; AdamSeg seg[kAdamMaxParams]; };
+
+__global__ void __launch_bounds__(256) adam_kernel(AdamTable t, const double* __restrict__ grad, double* __restrict__ m_state,
+                                                   double* __restrict__ v_state, double lr_t, double beta1, double beta2, double eps,
+                                                   double* __restrict__ trace) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0 && trace) *trace = grad[0] - grad[1];   // the step's ELBO estimate: data term - KL
+  if (idx >= t.total) return;
+  int k = 0;
+  while (k + 1 < t.n && idx >= t.seg[k + 1].start) ++k;
+  const AdamSeg& sg = t.seg[k];
+  const long i = idx - sg.start;
+  if (sg.transform == 3) {
+    const long r = (i / sg.M) % sg.M, col = i % sg.M;
+    if (col > r) return;   // FillTriangular has no variable above the diagonal
+  }
+  double g = 0.0;   // d ELBO / d value
+  if (sg.grad_count == sg.count) g = grad[sg.grad_offset + i];
+  else for (long j = 0; j < sg.grad_count; ++j) g += grad[sg.grad_offset + j];   // one scalar shared by grad_count entries
+  g = -g;           // the optimiser minimises -ELBO
+  const double c = sg.value[i];
+  double u = c;
+  const double lower = sg.transform == 2 ? 1e-6 : 0.0;
+  if (sg.transform == 1 || sg.transform == 2) {
+    const double y = c - lower;
+    const double sig = -expm1(-y);   // sigmoid(u) = 1 - exp(-softplus(u))
+    u = y + log(sig);                // softplus^-1
+    g *= sig;
+  }
+  const double m = beta1 * m_state[idx] + (1.0 - beta1) * g;
+  const double v = beta2 * v_state[idx] + (1.0 - beta2) * g * g;
+  m_state[idx] = m;
+  v_state[idx] = v;
+  u -= lr_t * m / (sqrt(v) + eps);
+  double out = u;
+  if (sg.transform == 1 || sg.transform == 2) out = (u > 0.0 ? u + log1p(exp(-u)) : log1p(exp(u))) + lower;
+  sg.value[i] = out;
+  if (sg.mirror)
+    for (long j = 0; j < sg.mirror_count; ++j) sg.mirror[j] = out;
+}
+
 }  // namespace dgp

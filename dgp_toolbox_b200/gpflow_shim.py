@@ -144,7 +144,13 @@ class SquaredExponential(_Module):
     def lengthscales_vector(self, D):
         ls = self.lengthscales.value.reshape(-1)
         if ls.numel() == 1:
-            return ls.expand(D).contiguous()
+            # the C ABI takes one lengthscale per input column; the expansion lives in one buffer per kernel object so that
+            # its address is stable from call to call (graph replay, dgp_adam_param.mirror)
+            buf = getattr(self, "_ls_vec", None)
+            if buf is None or buf.numel() != D or buf.device != ls.device:
+                buf = self._ls_vec = torch.empty(D, dtype=torch.float64, device=ls.device)
+            buf.copy_(ls.expand(D))
+            return buf
         if ls.numel() != D:
             raise ValueError(f"lengthscales has {ls.numel()} entries, input has {D} columns")
         return ls.contiguous()

@@ -236,30 +236,93 @@ class DGP_Base(_Module):
         return self.predict_moments(Xnew, num_samples, add_lik_var=True, zs=zs, seed=seed)
 
     # ------------------------------------------------------------------ optimisers (callers of the hot path)
-    def _adam_state(self, params):
-        return {p: (torch.zeros_like(p.value), torch.zeros_like(p.value)) for p in params}
+    _TRANSFORM_CODE = {None: 0, "positive": 1, "positive_shift": 2, "triangular": 3}
 
-    def _adam_step(self, params, grads, state, t, lr, beta_1, beta_2, epsilon):
-        """Keras/TF Adam on the unconstrained variables; `grads` are constrained-space d ELBO (we minimise -ELBO)."""
-        lr_t = lr * np.sqrt(1.0 - beta_2 ** t) / (1.0 - beta_1 ** t)
-        for p in params:
-            g = -p.grad_to_unconstrained(grads[p])
-            m, v = state[p]
-            m.mul_(beta_1).add_(g, alpha=1.0 - beta_1)
-            v.mul_(beta_2).addcmul_(g, g, value=1.0 - beta_2)
-            u = p.unconstrained()
-            u.sub_(lr_t * m / (v.sqrt() + epsilon))
-            p.set_unconstrained(u)
+    def _adam_params(self, params):
+        """Parameter list -> (dgp_adam_param array, keep-alive list): where each trainable Parameter lives, where its gradient sits
+        in the dgp_elbo_grad buffer and which GPflow bijector maps it to the variable tf.optimizers.Adam updates."""
+        _, offs = self.grad_layout()
+        where = {}
+        for l, o in zip(self.layers, offs):
+            M, D_in = l.feature.Z.shape
+            where[id(l.feature.Z)] = (o.dZ, M * D_in, None, 0)
+            ls = l.kern.lengthscales
+            if ls.value.numel() == D_in and ls.value.dim() > 0:
+                where[id(ls)] = (o.dlengthscales, D_in, None, 0)
+            else:   # one lengthscale shared by all inputs: gradient summed, value re-broadcast into the [D_in] vector of the ABI
+                where[id(ls)] = (o.dlengthscales, D_in, l.kern.lengthscales_vector(D_in), 0)
+            where[id(l.kern.variance)] = (o.dvariance, 1, None, 0)
+            where[id(l.q_mu)] = (o.dq_mu, M * l.num_outputs, None, 0)
+            where[id(l.q_sqrt)] = (o.dq_sqrt, l.num_outputs * M * M, None, M)
+        where[id(self.likelihood.likelihood.variance)] = (2, 1, None, 0)
+        arr = (_lib.AdamParam * len(params))()
+        keep = []
+        for i, p in enumerate(params):
+            if id(p) not in where:
+                raise NotImplementedError(f"{p!r} has no gradient on the accelerated path (SURVEY §8 f2): set_trainable(p, False)")
+            off, gcount, mirror, M = where[id(p)]
+            v = p.value
+            if not v.is_contiguous():
+                raise ValueError(f"{p!r} must be contiguous")
+            arr[i].value, arr[i].count = v.data_ptr(), v.numel()
+            arr[i].grad_offset, arr[i].grad_count = off, gcount
+            arr[i].transform, arr[i].M = self._TRANSFORM_CODE[p.transform], M
+            if mirror is not None:
+                arr[i].mirror, arr[i].mirror_count = mirror.data_ptr(), mirror.numel()
+                keep.append(mirror)
+            keep.append(v)
+        return arr, keep
+
+    def _adam_state(self, params):
+        """(m, v) of tf.optimizers.Adam, flat in `params` order."""
+        n = sum(p.value.numel() for p in params)
+        return (torch.zeros(n, dtype=torch.float64, device=self.device), torch.zeros(n, dtype=torch.float64, device=self.device))
+
+    def _adam_step(self, params, flat, state, t, lr, beta_1, beta_2, epsilon):
+        """One dgp_adam_step: Keras/TF Adam on the unconstrained variables from the constrained-space gradients in `flat`."""
+        arr, keep = self._adam_params(params)
+        _lib.get_context(self.device).call("dgp_adam_step", arr, len(params), _lib.ptr(flat), _lib.ptr(state[0]), _lib.ptr(state[1]),
+                                           int(t), float(lr), float(beta_1), float(beta_2), float(epsilon))
+
+    def _train_adam(self, data, params, state, t0, steps, lr, beta_1, beta_2, epsilon, scale=1.0, kl_weight=1.0):
+        """`steps` iterations of (ELBO gradient, Adam update) in one dgp_train_adam call; returns the per-step ELBO estimates
+        (device tensor [steps]). Seeds continue the model's draw sequence exactly like `steps` elbo_flat calls would."""
+        X, Y = data
+        X = _lib.as_device(X, self.device)
+        Y = _lib.as_device(Y, self.device)
+        self._check_XY(X, Y)
+        if X.shape[0] == 0:
+            raise ValueError("empty minibatch")
+        m, keep = self._model_desc()
+        arr, keep2 = self._adam_params(params)
+        n = int(_lib.lib.dgp_grad_size(C.byref(m)))
+        if getattr(self, "_train_flat", None) is None or self._train_flat.numel() != n or self._train_flat.device != X.device:
+            self._train_flat = torch.empty(n, dtype=torch.float64, device=X.device)   # one address across calls: graph replay
+        trace = torch.empty(max(steps, 1), dtype=torch.float64, device=X.device)
+        seed0 = self._next_seed(None)
+        self._draw += steps - 1
+        _lib.get_context(X.device).call("dgp_train_adam", C.byref(m), _lib.ptr(X), _lib.ptr(Y), X.shape[0], self.num_samples,
+                                        float(scale), float(kl_weight), seed0, 0x9E3779B97F4A7C15, 0, arr, len(params),
+                                        _lib.ptr(state[0]), _lib.ptr(state[1]), int(t0), int(steps), float(lr), float(beta_1),
+                                        float(beta_2), float(epsilon), _lib.ptr(self._train_flat), _lib.ptr(trace))
+        return trace[:steps]
+
+    def _adam_loop(self, data, params, state, t0, iterations, lr, beta_1, beta_2, epsilon, messages):
+        """The reference's loop (dgp.py:146-154) in blocks that end on the steps it prints at (step % messages == 0)."""
+        step = 0
+        while step < iterations:
+            n = 1 if step == 0 else min(messages, iterations - step)
+            trace = self._train_adam(data, params, state, t0 + step, n, lr, beta_1, beta_2, epsilon)
+            step += n
+            if (step - 1) % messages == 0:
+                print(f"ELBO: {trace[-1].item()}")
+        _lib.get_context(self.device).check()
 
     def optimize_adam(self, data, iterations=5000, lr=0.01, beta_1=0.9, beta_2=0.999, epsilon=1e-07, messages=100):
-        """dgp.py:132-154."""
+        """dgp.py:132-154. The whole loop runs in the library (dgp_train_adam); the host only prints."""
         params = self.trainable_parameters
         state = self._adam_state(params)
-        for step in range(iterations):
-            flat = self.elbo_flat(data, want_grad=True)
-            self._adam_step(params, self.unpack_grads(flat), state, step + 1, lr, beta_1, beta_2, epsilon)
-            if step % messages == 0:
-                print(f"ELBO: {(flat[0] - flat[1]).item()}")
+        self._adam_loop(data, params, state, 1, iterations, lr, beta_1, beta_2, epsilon, messages)
 
     def natgrad_step(self, data, gamma, variational_params, scale=1.0, seed=None, zs=None):
         """One GPflow NaturalGradient(gamma).minimize(-ELBO, var_list=[(q_mu, q_sqrt), ...]) step with the default XiNat
@@ -303,17 +366,12 @@ class DGP_Base(_Module):
         variational_params = [(layer.q_mu, layer.q_sqrt) for layer in nat_layers]
         params = self.trainable_parameters
         state = self._adam_state(params)
-        t = 0
-        for step in range(iterations1):
-            flat = self.elbo_flat(data, want_grad=True)
-            t += 1
-            self._adam_step(params, self.unpack_grads(flat), state, t, lr_adam, beta_1, beta_2, epsilon)
-            if step % messages == 0:
-                print(f"ELBO: {(flat[0] - flat[1]).item()}")
+        self._adam_loop(data, params, state, 1, iterations1, lr_adam, beta_1, beta_2, epsilon, messages)
+        t = iterations1
         for step in range(iterations2):
             flat = self.elbo_flat(data, want_grad=True)
             t += 1
-            self._adam_step(params, self.unpack_grads(flat), state, t, lr_adam, beta_1, beta_2, epsilon)
+            self._adam_step(params, flat, state, t, lr_adam, beta_1, beta_2, epsilon)
             self.natgrad_step(data, lr_gamma, variational_params)
             if step % messages == 0:
                 print(f"ELBO: {(flat[0] - flat[1]).item()}")

@@ -72,6 +72,13 @@ enum { DGP_CAT_PREP = 0,            /* Kuu build, Cholesky + inverse, KL, replic
        DGP_CAT_OTHER = 7,           /* likelihood, upstream adjoints, acquisition epilogues */
        DGP_CAT_FUSED_FWD = 8 };     /* fused conditional + sample kernel (Kuf, both solves, q_sqrt contraction, moments in one launch) */
 int dgp_set_profiling(dgp_ctx* ctx, int on);
+/* CUDA-graph replay (default 0). With on = 1 the model-level calls that draw their own Philox samples (dgp_elbo_grad,
+ * dgp_predict_moments, dgp_ei, dgp_ei_grad; zs_host == NULL) capture their launch sequence -- ~70-130 small launches over the
+ * per-layer side streams for a BO-sized problem -- into a CUDA graph the first time a call signature (every pointer, shape,
+ * scalar and ctx flag; not the seed) is seen, and replay it afterwards: one seed store + one graph launch per call. The caller
+ * keeps the buffers of a signature alive and in place (parameters updated in place, as dgp_adam_step does). Up to 16 signatures
+ * are cached (LRU); growing the workspace or on = 0 drops them. Same kernels, same results bit for bit. */
+int dgp_set_graph(dgp_ctx* ctx, int on);
 /* on = 0 routes the conditional through the unfused GEMM pipeline (debug / A-B measurement); default 1 */
 int dgp_set_fused(dgp_ctx* ctx, int on);
 /* The first layer's input is X tiled over the S samples (models/dgp.py:49), so its conditional (and the adjoint's contractions)
@@ -137,6 +144,36 @@ int dgp_elbo_grad(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, co
 int dgp_elbo_grad_host(dgp_ctx* ctx, const dgp_model_desc* model, const double* X_host, const double* Y_host, int64_t N,
                        int64_t S, double scale, double kl_weight, uint64_t seed, int64_t n_offset, int want_grad,
                        double* out_flat_host);
+
+/* One trainable parameter of the optimiser entry points below. */
+typedef struct {
+  double* value;          /* device, constrained space, updated in place (the array the layer descriptors point at) */
+  int64_t count;          /* entries of value */
+  int64_t grad_offset;    /* its gradient inside the dgp_elbo_grad buffer (dgp_grad_layout) */
+  int64_t grad_count;     /* == count; or > count == 1: one scalar shared by grad_count gradient entries (non-ARD lengthscale) */
+  int transform;          /* GPflow bijector: 0 identity, 1 softplus (positive()), 2 softplus + 1e-6 (likelihood variance),
+                             3 FillTriangular over [count / M^2][M][M] (q_sqrt: entries above the diagonal are not variables) */
+  int M;                  /* transform 3 only */
+  double* mirror;         /* optional [mirror_count] broadcast of the updated scalar (the [D_in] vector a non-ARD lengthscale is */
+  int64_t mirror_count;   /* expanded to for dgp_layer_desc.lengthscales), else NULL / 0 */
+} dgp_adam_param;
+
+/* tf.optimizers.Adam(lr, beta_1, beta_2, epsilon).apply_gradients on the unconstrained GPflow variables, minimising -ELBO
+ * (models/dgp.py:132-154, 190-204): u = bijector^-1(value), g_u = -dELBO/dvalue * dvalue/du, m = b1 m + (1-b1) g_u,
+ * v = b2 v + (1-b2) g_u^2, u -= lr sqrt(1-b2^t)/(1-b1^t) m / (sqrt(v) + epsilon), value = bijector(u); one launch for all
+ * parameters. m_state / v_state: device [sum count] in params order, zero before the first step; t counts from 1.
+ * params is a HOST array, n_params <= 48. */
+int dgp_adam_step(dgp_ctx* ctx, const dgp_adam_param* params, int n_params, const double* grad_flat, double* m_state,
+                  double* v_state, int64_t t, double lr, double beta1, double beta2, double epsilon);
+
+/* `steps` iterations of the reference's training loop (models/dgp.py:146-154) without returning to the host: step k runs
+ * dgp_elbo_grad(seed = seed0 + k * seed_stride mod 2^64) into out_flat and then dgp_adam_step(t = t0 + k). elbo_trace (device
+ * [steps], or NULL) receives each step's ELBO estimate out[0] - out[1] (what the reference prints every `messages` steps). With
+ * dgp_set_graph(1) a step is three launches: seed store, graph replay, Adam. */
+int dgp_train_adam(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, const double* Y, int64_t N, int64_t S, double scale,
+                   double kl_weight, uint64_t seed0, uint64_t seed_stride, int64_t n_offset, const dgp_adam_param* params,
+                   int n_params, double* m_state, double* v_state, int64_t t0, int64_t steps, double lr, double beta1,
+                   double beta2, double epsilon, double* out_flat, double* elbo_trace);
 
 /* DGP_Base.predict_f / predict_y + DGP.predict mixture moments (models/dgp.py:66-77,113-124,362-366; also
  * Infill_criteria.py:39-41, EHVI.py:112-119): mean [N, D_L], var [N, D_L]; add_lik_var != 0 adds sigma_n^2 (predict_y). */

@@ -516,6 +516,74 @@ def natgrad_step(model: OModel, X, Y, zs, gamma: float, layer_indices: Sequence[
     return out
 
 
+class AdamOracle:
+    """tf.optimizers.Adam(lr, beta_1, beta_2, epsilon) on the GPflow variables of a model, minimising -ELBO (reference
+    models/dgp.py:132-154: optimizer.apply_gradients(zip(tape.gradient(-ELBO, trainable_variables), trainable_variables))).
+    GPflow stores UNCONSTRAINED variables: softplus^-1(value) for kernel lengthscales / variance (positive()),
+    softplus^-1(value - 1e-6) for the Gaussian likelihood variance, the lower-triangle entries of q_sqrt (FillTriangular; kept
+    here as a full matrix whose upper triangle never receives gradient), identity for Z and q_mu. The variables persist across
+    steps, constrained values are rebuilt from them, and the gradient w.r.t. the variables is taken by autograd THROUGH the
+    bijectors -- the product instead inverts the bijector every step and applies the chain rule in closed form.
+    Keras Adam: lr_t = lr sqrt(1 - b2^t) / (1 - b1^t); m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; u -= lr_t m / (sqrt(v) + eps)."""
+
+    BIJECTOR = {"Z": "identity", "lengthscales": "positive", "variance": "positive", "q_mu": "identity", "q_sqrt": "triangular",
+                "lik_var": "positive_shift"}
+
+    def __init__(self, model: OModel, lr=0.01, beta_1=0.9, beta_2=0.999, epsilon=1e-7, names: Optional[Sequence[str]] = None):
+        self.lr, self.b1, self.b2, self.eps, self.t = lr, beta_1, beta_2, epsilon, 0
+        params = model.named_params()
+        self.names = list(params) if names is None else list(names)
+        self.u = {k: self._inverse(k, params[k].detach().clone()) for k in self.names}
+        self.m = {k: torch.zeros_like(v) for k, v in self.u.items()}
+        self.v = {k: torch.zeros_like(v) for k, v in self.u.items()}
+
+    @classmethod
+    def _kind(cls, name):
+        return cls.BIJECTOR[name.split(".")[-1]]
+
+    @classmethod
+    def _inverse(cls, name, value):
+        kind = cls._kind(name)
+        if kind in ("positive", "positive_shift"):
+            y = value - (1e-6 if kind == "positive_shift" else 0.0)
+            return y + torch.log(-torch.expm1(-y))
+        return value
+
+    @classmethod
+    def _forward(cls, name, u):
+        kind = cls._kind(name)
+        if kind in ("positive", "positive_shift"):
+            return torch.logaddexp(u, torch.zeros_like(u)) + (1e-6 if kind == "positive_shift" else 0.0)
+        if kind == "triangular":
+            return torch.tril(u)
+        return u
+
+    def step(self, model: OModel, X, Y, zs, scale: float = 1.0):
+        """One apply_gradients; returns (the step's ELBO, a new OModel holding the updated constrained values)."""
+        params = model.named_params()
+        leaves = {k: self.u[k].detach().clone().requires_grad_(True) for k in self.names}
+        val = {k: (self._forward(k, leaves[k]) if k in leaves else params[k].detach()) for k in params}
+        layers = [OLayer(Z=val[f"layers.{i}.Z"], lengthscales=val[f"layers.{i}.lengthscales"], variance=val[f"layers.{i}.variance"],
+                         q_mu=val[f"layers.{i}.q_mu"], q_sqrt=val[f"layers.{i}.q_sqrt"], mean_kind=l.mean_kind, mf_W=l.mf_W,
+                         mf_b=l.mf_b, white=l.white, kernel_kind=l.kernel_kind) for i, l in enumerate(model.layers)]
+        value = elbo(OModel(layers=layers, lik_var=val["lik_var"], num_samples=model.num_samples), X, Y, zs, scale)
+        (-value).backward()
+        self.t += 1
+        lr_t = self.lr * np.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
+        for k in self.names:
+            g = leaves[k].grad
+            self.m[k] = self.b1 * self.m[k] + (1.0 - self.b1) * g
+            self.v[k] = self.b2 * self.v[k] + (1.0 - self.b2) * g * g
+            self.u[k] = self.u[k] - lr_t * self.m[k] / (torch.sqrt(self.v[k]) + self.eps)
+        new = {k: (self._forward(k, self.u[k]).detach() if k in self.u else params[k].detach()) for k in params}
+        out = OModel(layers=[OLayer(Z=new[f"layers.{i}.Z"], lengthscales=new[f"layers.{i}.lengthscales"],
+                                    variance=new[f"layers.{i}.variance"], q_mu=new[f"layers.{i}.q_mu"],
+                                    q_sqrt=new[f"layers.{i}.q_sqrt"], mean_kind=l.mean_kind, mf_W=l.mf_W, mf_b=l.mf_b,
+                                    white=l.white, kernel_kind=l.kernel_kind) for i, l in enumerate(model.layers)],
+                     lik_var=new["lik_var"], num_samples=model.num_samples)
+        return value.detach(), out
+
+
 # --------------------------------------------------------------------------------------
 # parameter transforms kept host-side (SURVEY §9)
 # --------------------------------------------------------------------------------------

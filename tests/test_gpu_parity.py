@@ -241,6 +241,39 @@ def test_natural_gradient_step_matches_oracle():
         assert rel_err(layer.q_sqrt.value, R_o) < 1e-8
 
 
+@pytest.mark.parametrize("isotropic", [False, True])
+def test_adam_steps_match_oracle_tf_adam(isotropic):
+    """dgp_adam_step (one launch: bijector inverse, chain rule, Adam, bijector) against the oracle's tf.optimizers.Adam on
+    persistent unconstrained variables with autograd through the bijectors (reference models/dgp.py:132-154). Four steps on
+    fixed draws; `isotropic` uses one shared lengthscale per kernel (summed gradient, broadcast value)."""
+    from oracle.dgp_oracle import synthetic_problem, model_from_problem
+    from tests.helpers import product_model_from_problem, _condition
+    prob = _condition(synthetic_problem(3, [3], 24, 40, lik_var=0.5))
+    if isotropic:
+        for l in prob["layers"]:
+            l["lengthscales"] = np.asarray(float(np.min(l["lengthscales"])))
+    om, pm = model_from_problem(prob, 4), product_model_from_problem(prob, 4)
+    zs = oracle_zs(om, 40, 4, 9)
+    X, Y = torch.as_tensor(prob["X"]), torch.as_tensor(prob["Y"])
+    opt = O.AdamOracle(om, lr=0.01, beta_1=0.9, beta_2=0.999, epsilon=1e-7)
+    params = pm.trainable_parameters
+    state = pm._adam_state(params)
+    m = om
+    for t in range(1, 5):
+        v_o, m = opt.step(m, X, Y, zs)
+        flat = pm.elbo_flat((prob["X"], prob["Y"]), zs=zs)
+        assert rel_err(flat[0] - flat[1], v_o) < 1e-8
+        pm._adam_step(params, flat, state, t, 0.01, 0.9, 0.999, 1e-7)
+    for lo, lp in zip(m.layers, pm.layers):
+        assert rel_err(lp.feature.Z.value, lo.Z) < 1e-8
+        assert rel_err(lp.kern.lengthscales.value, lo.lengthscales) < 1e-8
+        assert rel_err(lp.kern.variance.value, lo.variance) < 1e-8
+        assert rel_err(lp.q_mu.value, lo.q_mu, scale=1e-2) < 1e-8
+        assert rel_err(lp.q_sqrt.value, lo.q_sqrt) < 1e-8
+        assert float(torch.triu(lp.q_sqrt.value, 1).abs().max()) == 0.0
+    assert rel_err(pm.likelihood.likelihood.variance.value, m.lik_var) < 1e-8
+
+
 @pytest.mark.parametrize("D0,units,M,N,S", [(4, [4], 48, 60, 8), (3, [2, 3], 30, 25, 1), (2, [], 20, 30, 5)])
 def test_ei_input_gradient_matches_oracle_autograd(D0, units, M, N, S):
     """d sum(-EI) / dx (the gradient of the reference's Adam-on-x acquisition search, Infill_criteria.py:79-84) against

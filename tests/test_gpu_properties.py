@@ -141,6 +141,82 @@ def test_optimize_adam_increases_elbo():
     assert after > before + 50.0, (before, after)
 
 
+def _bo_model(seed=1):
+    import dgp_toolbox_b200 as D
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-1, 1, (60, 2))
+    Y = np.sin(3 * X[:, :1]) * np.cos(2 * X[:, 1:]) + 0.05 * rng.standard_normal((60, 1))
+    kernels = [D.RBF(lengthscales=[0.7, 0.7], variance=1.0) for _ in range(3)]
+    return D.DGP(X, Y, X[:20].copy(), kernels, [2, 2], D.Gaussian(0.1), num_samples=5, seed=seed), X, Y
+
+
+def test_graph_replay_is_bit_exact():
+    """dgp_set_graph(1) replays the captured launch sequence with the seed read from device memory: ELBO + gradients, mixture
+    moments and EI must equal the directly launched calls bit for bit, for every seed, after in-place parameter updates
+    (same buffers -> same graph) and for a second call signature held in the cache at the same time."""
+    import dgp_toolbox_b200 as D
+    model, X, Y = _bo_model()
+    ctx = D._lib.get_context(0)
+    Xd, Yd = model.data
+    Xs = Xd[:25].contiguous()
+    out_a = torch.empty(model.grad_layout()[0], dtype=torch.float64, device="cuda")
+    out_b = torch.empty_like(out_a)
+    try:
+        for rnd in range(2):
+            for seed in (3, 4, 2 ** 63 + 11):
+                ctx.set_graph(False)
+                ref = model.elbo_flat((Xd, Yd), seed=seed, out=out_a).clone()
+                ref_small = model.elbo_flat((Xs, Yd[:25].contiguous()), seed=seed).clone()
+                pm_ref = [t.clone() for t in model.predict_moments(Xd, 5, seed=seed)]
+                ctx.set_graph(True)
+                n0 = ctx.launch_count(reset=True)
+                got = model.elbo_flat((Xd, Yd), seed=seed, out=out_b)
+                assert torch.equal(got, ref)
+                got2 = model.elbo_flat((Xd, Yd), seed=seed, out=out_b)      # replay of the entry captured above
+                assert torch.equal(got2, ref)
+                assert ctx.launch_count() > 20                               # replays count the launches of the captured step
+                Ys = Yd[:25].contiguous()
+                assert torch.equal(model.elbo_flat((Xs, Ys), seed=seed), ref_small)   # fresh buffers: a new signature (LRU cache)
+                pm_got = model.predict_moments(Xd, 5, seed=seed)
+                assert all(torch.equal(a, b) for a, b in zip(pm_got, pm_ref))
+            # move the parameters in place: the cached graphs must see the new values
+            model.layers[0].kern.lengthscales.assign(model.layers[0].kern.lengthscales.value * 1.1)
+            model.layers[-1].q_mu.assign(model.layers[-1].q_mu.value + 0.05)
+    finally:
+        ctx.set_graph(False)
+
+
+def test_train_adam_equals_stepwise_calls_and_graph_replay():
+    """dgp_train_adam (loop in the library) == elbo_flat + dgp_adam_step called step by step with the model's seed sequence,
+    bit for bit, with and without graph replay."""
+    import dgp_toolbox_b200 as D
+    ctx = D._lib.get_context(0)
+    results = []
+    for mode in ("stepwise", "library", "library+graph"):
+        model, X, Y = _bo_model(seed=7)
+        params = model.trainable_parameters
+        state = model._adam_state(params)
+        try:
+            ctx.set_graph(mode == "library+graph")
+            if mode == "stepwise":
+                trace = []
+                for t in range(1, 13):
+                    flat = model.elbo_flat(model.data)
+                    trace.append((flat[0] - flat[1]).reshape(1))
+                    model._adam_step(params, flat, state, t, 0.02, 0.9, 0.999, 1e-7)
+                trace = torch.cat(trace)
+            else:
+                trace = torch.cat([model._train_adam(model.data, params, state, 1, 5, 0.02, 0.9, 0.999, 1e-7),
+                                   model._train_adam(model.data, params, state, 6, 7, 0.02, 0.9, 0.999, 1e-7)])
+        finally:
+            ctx.set_graph(False)
+        results.append((trace.clone(), [p.value.clone() for p in params], model._draw))
+    for trace, values, draw in results[1:]:
+        assert draw == results[0][2]
+        assert torch.equal(trace, results[0][0])
+        assert all(torch.equal(a, b) for a, b in zip(values, results[0][1]))
+
+
 @pytest.mark.parametrize("fused", [True, False])
 def test_first_layer_sharing_equals_per_sample_evaluation(fused):
     """The first layer is evaluated once per point and expanded over the S samples; switching that off evaluates every
