@@ -579,9 +579,33 @@ int forward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, ChunkLa
 
 struct Upstream { double *Gm, *GvT, *GmPad, *gq, *part; long nblocks; };
 
+// The contractions over the point-samples that produce a layer's parameter gradients are independent of each other. On
+// latency-bound (sub-wave) calls they run side by side on the ctx's side streams, each with its own slice of the split-K scratch;
+// `on_main` is issued on the caller's stream while they run.
+template <typename F>
+int param_gemms(dgp_ctx* c, GemmArgs* gs, const bool* nts, int n, double* part, size_t part_cap, bool small, F&& on_main) {
+  size_t off[8], total = 0;
+  for (int i = 0; i < n; ++i) {
+    gs[i].splitk = pick_splitk(c, gs[i], nts[i]);
+    off[i] = total;
+    if (gs[i].splitk > 1) total += (((size_t)gs[i].splitk * gs[i].batch * gs[i].M * gs[i].N) + 31) & ~(size_t)31;
+  }
+  const bool par = small && total <= part_cap;
+  LayerFork fk(c, par ? n : 0);
+  for (int i = 0; i < n; ++i) {
+    fk.use(i);
+    gs[i].part = part + (fk.active ? off[i] : 0);
+    RC(gemm(c, gs[i], nts[i]));
+  }
+  if (fk.active) c->stream = fk.main;
+  RC(on_main());
+  fk.join();
+  return DGP_OK;
+}
+
 int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const ChunkLayer& cl, const Temps& tmp,
-                   const Upstream& up, double* dXin, double* XaugPad, double* rbf_part, double* splitk_part, long Nc, long S,
-                   bool first_chunk, bool params = true) {
+                   const Upstream& up, double* dXin, double* XaugPad, double* rbf_part, double* splitk_part, size_t splitk_cap, long Nc,
+                   long S, bool first_chunk, bool params = true) {
   const long P = Nc * S, Pp = round_up(P, kTileP);
   const int Mp = w.Mp, D = w.D_out;
   const double beta = first_chunk ? 0.0 : 1.0;
@@ -627,25 +651,26 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
       return DGP_OK;
     }));
     if (!params) return DGP_OK;
-    LAUNCH(reduce_partials_kernel, w.D_in + 1, 256, 0, rbf_part, nbv, w.D_in + 1, w.rbf_red, first_chunk ? 0 : 1);
-    LAUNCH(reduce_partials_kernel, 3, 256, 0, up.part, up.nblocks, 3, w.sgv, first_chunk ? 0 : 1);
     CAT(DGP_CAT_GEMM_BWD_PARAM);
+    GemmArgs pg[4];
+    const bool pnt[4] = {true, true, false, false};
     // G1 = tril(dV V^T)  (-> dLu^-1 through Kuf = Lu V)
-    g = gargs(dV, Pp, V, Pp, w.G1, Mp, Mp, Mp, (int)Pp);
-    g.beta = beta; g.c_lower = 1; g.splitk = pick_splitk(c, g, true); g.part = splitk_part;
-    RC(gemm(c, g, true));
+    pg[0] = gargs(dV, Pp, V, Pp, w.G1, Mp, Mp, Mp, (int)Pp);
+    pg[0].beta = beta; pg[0].c_lower = 1;
     // DCt_d = tril(V diag(2 Gv_d) T_d^T) = (dC_d)^T, blocks side by side
-    g = gargs(V, Pp, cl.T, Pp, w.DCt, (long)D * Mp, Mp, Mp, (int)Pp);
-    g.alpha = 2.0; g.beta = beta; g.batch = D; g.sA = 0; g.sB = (long)Mp * Pp; g.sC = Mp; g.c_lower = 1;
-    g.kscale = up.GvT; g.sScale = Pp; g.splitk = pick_splitk(c, g, true); g.part = splitk_part;
-    RC(gemm(c, g, true));
+    pg[1] = gargs(V, Pp, cl.T, Pp, w.DCt, (long)D * Mp, Mp, Mp, (int)Pp);
+    pg[1].alpha = 2.0; pg[1].beta = beta; pg[1].batch = D; pg[1].sA = 0; pg[1].sB = (long)Mp * Pp; pg[1].sC = Mp; pg[1].c_lower = 1;
+    pg[1].kscale = up.GvT; pg[1].sScale = Pp;
     // dbeta = V Gm ;  H = Gbar [X, 1]
-    g = gargs(V, Pp, up.GmPad, 32, w.dbeta, 32, Mp, 32, (int)Pp);
-    g.beta = beta; g.splitk = pick_splitk(c, g, false); g.part = splitk_part;
-    RC(gemm(c, g, false));
-    g = gargs(Gbar, Pp, XaugPad, 32, w.H, 32, Mp, 32, (int)Pp);
-    g.beta = beta; g.splitk = pick_splitk(c, g, false); g.part = splitk_part;
-    RC(gemm(c, g, false));
+    pg[2] = gargs(V, Pp, up.GmPad, 32, w.dbeta, 32, Mp, 32, (int)Pp);
+    pg[2].beta = beta;
+    pg[3] = gargs(Gbar, Pp, XaugPad, 32, w.H, 32, Mp, 32, (int)Pp);
+    pg[3].beta = beta;
+    RC(param_gemms(c, pg, pnt, 4, splitk_part, splitk_cap, small, [&]() -> int {
+      LAUNCH(reduce_partials_kernel, w.D_in + 1, 256, 0, rbf_part, nbv, w.D_in + 1, w.rbf_red, first_chunk ? 0 : 1);
+      LAUNCH(reduce_partials_kernel, 3, 256, 0, up.part, up.nblocks, 3, w.sgv, first_chunk ? 0 : 1);
+      return DGP_OK;
+    }));
     return DGP_OK;
   }
   // dA' = q_mu Gm^T + sum_d R_d (2 Gv_d o T_d)                                       
@@ -681,25 +706,26 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
     return DGP_OK;
   }));
   if (!params) return DGP_OK;   // input gradient only (acquisition): the contractions over the point-samples are not needed
-  LAUNCH(reduce_partials_kernel, w.D_in + 1, 256, 0, rbf_part, nb, w.D_in + 1, w.rbf_red, first_chunk ? 0 : 1);
-  LAUNCH(reduce_partials_kernel, 3, 256, 0, up.part, up.nblocks, 3, w.sgv, first_chunk ? 0 : 1);
   CAT(DGP_CAT_GEMM_BWD_PARAM);
+  GemmArgs pg[4];
+  const bool pnt[4] = {true, true, false, false};
   // dKu (data part) = -Wg A^T
-  g = gargs(W, Pp, cl.A, Pp, w.dKu, Mp, Mp, Mp, (int)Pp);
-  g.alpha = -1.0; g.beta = beta; g.splitk = pick_splitk(c, g, true); g.part = splitk_part;
-  RC(gemm(c, g, true));
+  pg[0] = gargs(W, Pp, cl.A, Pp, w.dKu, Mp, Mp, Mp, (int)Pp);
+  pg[0].alpha = -1.0; pg[0].beta = beta;
   // dq_sqrt_d (data part) = tril(A diag(2 Gv_d) T_d^T)
-  g = gargs(cl.A, Pp, cl.T, Pp, w.dR, Mp, Mp, Mp, (int)Pp);
-  g.alpha = 2.0; g.beta = beta; g.batch = D; g.sA = 0; g.sB = (long)Mp * Pp; g.sC = (long)Mp * Mp; g.c_lower = 1;
-  g.kscale = up.GvT; g.sScale = Pp; g.splitk = pick_splitk(c, g, true); g.part = splitk_part;
-  RC(gemm(c, g, true));
+  pg[1] = gargs(cl.A, Pp, cl.T, Pp, w.dR, Mp, Mp, Mp, (int)Pp);
+  pg[1].alpha = 2.0; pg[1].beta = beta; pg[1].batch = D; pg[1].sA = 0; pg[1].sB = (long)Mp * Pp; pg[1].sC = (long)Mp * Mp; pg[1].c_lower = 1;
+  pg[1].kscale = up.GvT; pg[1].sScale = Pp;
   // dq_mu (data part) = A Gm ;  H = Gbar [X, 1]
-  g = gargs(cl.A, Pp, up.GmPad, 32, w.dqmu, 32, Mp, 32, (int)Pp);
-  g.beta = beta; g.splitk = pick_splitk(c, g, false); g.part = splitk_part;
-  RC(gemm(c, g, false));
-  g = gargs(Gbar, Pp, XaugPad, 32, w.H, 32, Mp, 32, (int)Pp);
-  g.beta = beta; g.splitk = pick_splitk(c, g, false); g.part = splitk_part;
-  RC(gemm(c, g, false));
+  pg[2] = gargs(cl.A, Pp, up.GmPad, 32, w.dqmu, 32, Mp, 32, (int)Pp);
+  pg[2].beta = beta;
+  pg[3] = gargs(Gbar, Pp, XaugPad, 32, w.H, 32, Mp, 32, (int)Pp);
+  pg[3].beta = beta;
+  RC(param_gemms(c, pg, pnt, 4, splitk_part, splitk_cap, small, [&]() -> int {
+    LAUNCH(reduce_partials_kernel, w.D_in + 1, 256, 0, rbf_part, nb, w.D_in + 1, w.rbf_red, first_chunk ? 0 : 1);
+    LAUNCH(reduce_partials_kernel, 3, 256, 0, up.part, up.nblocks, 3, w.sgv, first_chunk ? 0 : 1);
+    return DGP_OK;
+  }));
   return DGP_OK;
 }
 
@@ -719,7 +745,8 @@ struct RunOpts {
 size_t max_splitk_part(const std::vector<LayerWs>& lw) {
   size_t m = 0;
   for (const LayerWs& w : lw) {
-    size_t v = (size_t)64 * w.D_out * w.Mp * w.Mp;
+    // room for the four parameter contractions of a layer side by side (param_gemms)
+    size_t v = (size_t)64 * (w.D_out + 1) * w.Mp * w.Mp + (size_t)128 * w.Mp * 32 + 1024;
     if (v > m) m = v;
   }
   return m < kSplitkPartDoubles ? m : kSplitkPartDoubles + ((size_t)32 * 1024 * 1024 / 8);
@@ -791,6 +818,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
   double* Tshared = adj ? nullptr : walloc(c, (size_t)maxD * maxMp * Ppmax);
   Upstream up{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   double *XaugPad = nullptr, *dXa = nullptr, *dXb = nullptr, *rbf_part = nullptr, *skpart = nullptr, *lik_part = nullptr;
+  size_t skcap = 0;
   double* acc = nullptr;   // [0] data term, [1] d/d lik variance (accumulated over chunks)
   const long nbmax = Ppmax / 128;
   if (adj || o.want_elbo) {
@@ -806,7 +834,8 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
     dXa = walloc(c, (size_t)Ppmax * 32);
     dXb = walloc(c, (size_t)Ppmax * 32);
     rbf_part = walloc(c, (size_t)nbmax * 2 * 32);   // one row of partials per 64-column block of rbf_bwd_kernel
-    skpart = walloc(c, max_splitk_part(lw));
+    skcap = max_splitk_part(lw);
+    skpart = walloc(c, skcap);
   }
   if (c->dry) return DGP_OK;
 
@@ -857,7 +886,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
           LAUNCH(upstream_reduce_kernel, (unsigned)nb0, 128, 0, dX_next, cls[0].z, cls[0].Fvar, Nc, S, Pp0, d.D_out, d.jitter, uh);
           Upstream up0 = up;
           up0.part = lik_part; up0.nblocks = nb0;
-          RC(backward_layer(c, d, lw[0], cls[0], tmp, up0, o.dx ? o.dx + n0 * D0 : nullptr, XaugPad, rbf_part, skpart, Nc, 1, first, params));
+          RC(backward_layer(c, d, lw[0], cls[0], tmp, up0, o.dx ? o.dx + n0 * D0 : nullptr, XaugPad, rbf_part, skpart, skcap, Nc, 1, first, params));
           continue;
         }
         if (l < nl - 1) {
@@ -867,7 +896,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
         }
         double* dXin = (l > 0 || o.dx) ? (dX_next == dXa ? dXb : dXa) : nullptr;
         if (l == 0 && o.dx && S == 1) dXin = o.dx + n0 * D0;   // one sample: the per-point-sample gradient is the answer
-        RC(backward_layer(c, d, lw[l], cls[l], tmp, up, dXin, XaugPad, rbf_part, skpart, Nc, S, first, params));
+        RC(backward_layer(c, d, lw[l], cls[l], tmp, up, dXin, XaugPad, rbf_part, skpart, skcap, Nc, S, first, params));
         if (l == 0 && o.dx && S > 1) {
           CAT(DGP_CAT_OTHER);
           LAUNCH(sum_samples_kernel, (unsigned)((Nc * D0 + 255) / 256), 256, 0, dXin, Nc, S, D0, o.dx + n0 * D0);

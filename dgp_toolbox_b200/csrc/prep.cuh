@@ -62,37 +62,31 @@ __global__ void __launch_bounds__(kCholThreads) chol_inv_kernel(const CholArgs* 
   const int nb = n / kCholNB;
   for (int kb = 0; kb < nb; ++kb) {
     const int k0 = kb * kCholNB;
-    // 1. diagonal block -> smem, unblocked Cholesky by warp 0
+    // 1. diagonal block -> smem, unblocked Cholesky
     for (int idx = tid; idx < 1024; idx += nth) {
       int r = idx >> 5, c = idx & 31;
       D[r * 33 + c] = L[(long)(k0 + r) * n + k0 + c];
     }
     __syncthreads();
-    if (tid < 32) {
-      // lane r keeps row r of the block in registers; column j: the pivot and the multipliers l_cj travel by shuffle, so the
-      // 32-step dependency chain has no shared-memory round trips or barriers in it
-      const int r = tid;
-      double row[32];
-#pragma unroll
-      for (int cc = 0; cc < 32; ++cc) row[cc] = D[r * 33 + cc];
-      bool bad = false;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const double djj = __shfl_sync(0xffffffffu, row[j], j);
-        bad |= !(djj > 0.0);
-        const double piv = sqrt(djj);
-        const double inv = 1.0 / piv;
-        row[j] = (r == j) ? piv : row[j] * inv;
-        if (r == j) Dinv[j] = inv;
-#pragma unroll
-        for (int cc = j + 1; cc < 32; ++cc) {
-          const double lcj = __shfl_sync(0xffffffffu, row[j], cc);
-          if (r >= cc) row[cc] = fma(-row[j], lcj, row[cc]);
-        }
+    // right-looking, all threads on the block in shared memory: column j applies its rank-1 update
+    // a_rc -= a_rj a_cj / d_jj to the columns right of it (one barrier per column), the scaling by 1 / sqrt(d_jj) comes last
+    for (int j = 0; j < 32; ++j) {
+      const double djj = D[j * 33 + j];
+      const double inv = rsqrt(djj);
+      if (tid == 0) {
+        if (!(djj > 0.0)) *a.info = 1;
+        Dinv[j] = inv;
       }
-      if (bad && r == 0) *a.info = 1;
-#pragma unroll
-      for (int cc = 0; cc < 32; ++cc) D[r * 33 + cc] = row[cc];
+      const double w = inv * inv;
+      for (int e = tid; e < 1024; e += nth) {
+        const int r = e >> 5, c = e & 31;
+        if (c > j && r >= c) D[r * 33 + c] = fma(-(D[r * 33 + j] * w), D[c * 33 + j], D[r * 33 + c]);
+      }
+      __syncthreads();
+    }
+    for (int e = tid; e < 1024; e += nth) {
+      const int r = e >> 5, c = e & 31;
+      D[r * 33 + c] = (r >= c) ? D[r * 33 + c] * Dinv[c] : 0.0;
     }
     __syncthreads();
     for (int idx = tid; idx < 1024; idx += nth) {
@@ -107,11 +101,11 @@ __global__ void __launch_bounds__(kCholThreads) chol_inv_kernel(const CholArgs* 
 #pragma unroll
       for (int c = 0; c < 32; ++c) x[c] = arow[c];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        double s = x[c];
+      for (int c = 0; c < 32; ++c) {   // right-looking: the dependency chain is one multiply + one fma per column
+        x[c] *= Dinv[c];
 #pragma unroll
-        for (int k = 0; k < c; ++k) s -= x[k] * D[c * 33 + k];
-        x[c] = s * Dinv[c];
+        for (int c2 = 0; c2 < 32; ++c2)
+          if (c2 > c) x[c2] = fma(-x[c], D[c2 * 33 + c], x[c2]);
       }
       double* orow = L + (long)(k0 + kCholNB + r) * n + k0;
 #pragma unroll
@@ -244,13 +238,18 @@ __global__ void __launch_bounds__(256) tri_inv_kernel(const CholArgs* __restrict
     for (int q = 0; q < 4; ++q) G[r * 33 + cs + q] = (ib == jb) ? ((r == cs + q) ? 1.0 : 0.0) : acc[q];
     __syncthreads();
     if (tid < 32) {                              // forward substitution, one column per thread
+      // right-looking with the pivots' reciprocals: the dependency chain is one multiply + one fma per row, and the constant
+      // loop bounds let both loops unroll completely (x[] in registers)
+      const double myinv = 1.0 / Ld[tid * 33 + tid];
       double x[32];
 #pragma unroll
-      for (int rr = 0; rr < 32; ++rr) {
-        double s = G[rr * 33 + tid];
+      for (int rr = 0; rr < 32; ++rr) x[rr] = G[rr * 33 + tid];
 #pragma unroll
-        for (int k = 0; k < rr; ++k) s = fma(-Ld[rr * 33 + k], x[k], s);
-        x[rr] = s / Ld[rr * 33 + rr];
+      for (int rr = 0; rr < 32; ++rr) {
+        x[rr] *= __shfl_sync(0xffffffffu, myinv, rr);
+#pragma unroll
+        for (int r2 = 0; r2 < 32; ++r2)
+          if (r2 > rr) x[r2] = fma(-Ld[r2 * 33 + rr], x[rr], x[r2]);
       }
 #pragma unroll
       for (int rr = 0; rr < 32; ++rr) Xc[(size_t)(i0 + rr) * 33 + tid] = x[rr];

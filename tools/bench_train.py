@@ -11,10 +11,14 @@ import dgp_toolbox_b200 as D
 from dgp_toolbox_b200 import synthetic
 
 ctx = D._lib.get_context(0)
-K = 200
+K = int(os.environ.get("K", "200"))
+CASES = os.environ.get("CASES", "c1,bo,c2_small").split(",")
+MODES = os.environ.get("MODES", "stepwise,library,library+graph").split(",")
 for name, (D0, units, M, S, N) in {"c1": (2, [2], 50, 10, 1000), "bo": (1, [1, 1], 25, 10, 50), "c2_small": (8, [8, 8, 8], 256, 32, 256)}.items():
+    if name not in CASES:
+        continue
     row = {"case": name, "iterations": K}
-    for mode in ("stepwise", "library", "library+graph"):
+    for mode in MODES:
         model = synthetic.model_from_problem(synthetic.synthetic_problem(D0, units, M, 8, ls_scale=0.3), S)
         X, Y = synthetic.minibatch(D0, N, 0)
         data = (torch.from_numpy(X).cuda(), torch.from_numpy(Y).cuda())
