@@ -517,16 +517,19 @@ int forward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, ChunkLa
     f.xFvar = (io.Fvars && io.Fvars[layer]) ? io.Fvars[layer] : nullptr;
     f.xF = (io.Fs && io.Fs[layer]) ? io.Fs[layer] : nullptr;
     f.stashA = stash ? cl.A : nullptr; f.stashT = stash ? cl.T : nullptr;
-    const size_t smem = fused_smem(w.fcfg, w.Mp, w.D_in, w.D_out);
-    const long ntiles = Pp / kFusedChoices[w.fcfg].PT;
-    const long slots = (long)c->num_sms * ((w.fcfg == 3 && smem <= 112 * 1024) ? 2 : 1);   // the small configuration fits two CTAs per SM
+    // few point-samples (a shared first layer, a BO-sized batch): halve the tile so that twice as many SMs share the launch;
+    // the packed operator stream depends on BM only
+    const int cfg = ((w.fcfg == 0 || w.fcfg == 2) && Pp / 64 <= c->num_sms / 2) ? w.fcfg + 1 : w.fcfg;
+    const size_t smem = fused_smem(cfg, w.Mp, w.D_in, w.D_out);
+    const long ntiles = Pp / kFusedChoices[cfg].PT;
+    const long slots = (long)c->num_sms * ((cfg == 3 && smem <= 112 * 1024) ? 2 : 1);   // the small configuration fits two CTAs per SM
     const unsigned grid = (unsigned)(ntiles < slots ? ntiles : slots);
 #define FUSED_LAUNCH(BM_, PT_, WM_, WN_)                                                                                   \
     do {                                                                                                                   \
       if (!c->dry) CK(cudaFuncSetAttribute(fused_forward_kernel<BM_, PT_, WM_, WN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem)); \
       LAUNCH((fused_forward_kernel<BM_, PT_, WM_, WN_>), grid, 288, smem, f);                                              \
     } while (0)
-    switch (w.fcfg) {
+    switch (cfg) {
       case 0: FUSED_LAUNCH(128, 64, 4, 2); break;
       case 1: FUSED_LAUNCH(128, 32, 4, 2); break;
       case 2: FUSED_LAUNCH(64, 64, 2, 4); break;
@@ -680,6 +683,13 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
   g = gargs(w.Rcat, (long)D * Mp, cl.T, Pp, dA, Pp, Mp, (int)Pp, D * Mp);
   g.a_tri = 1; g.kblocks = D; g.kblk = Mp; g.bscale = up.GvT; g.ld_bscale = Pp; g.bscale_mul = 2.0; g.beta = 1.0;
   if (D == 1) { g.kblocks = 1; }
+  if (D > 1) {
+    // few point-samples (a shared first layer): too few output tiles to occupy the GPU, so deal the D blocks out to splits
+    const GemmPlan p = gemm_plan(g, false, c->num_sms);
+    long s = p.tiles > 0 ? p.slots / (2 * p.tiles) : 1;
+    if (s > D) s = D;
+    if (s >= 2 && (size_t)s * Mp * Pp <= splitk_cap) { g.splitk = (int)s; g.part = splitk_part; }
+  }
   RC(gemm(c, g, false));
   // W = Ku^-1 dA'
   g = gargs(w.Kinv, Mp, dA, Pp, W, Pp, Mp, (int)Pp, Mp);

@@ -31,6 +31,7 @@ struct GemmArgs {
   int splitk;
   double* part;
   // K-concatenation: K = kblocks * kblk; A is [M][kblocks*kblk], B is the row-stacked [kblocks*kblk][N] (NN only).
+  // splitk > 1 (<= kblocks) deals whole blocks out to the splits.
   // With a_tri = 1 every block is lower triangular (its k-range is clipped at the row block). kblocks <= 1: plain GEMM.
   int kblocks; int kblk;
   // Optional column scale of B in NN mode: B[k][n] *= bscale_mul * bscale[(k / kblk) * ld_bscale + n].
@@ -88,13 +89,20 @@ __global__ void __launch_bounds__(WM* WN * 32) gemm_kernel(GemmArgs g) {
   int ktiles = kend > kbeg ? (kend - kbeg) / BK : 0;
   int tpb = ktiles > 0 ? ktiles : 1;   // k-tiles per concatenated block
   const int kblk = g.kblocks > 1 ? g.kblk : 0;
+  int blk0 = 0;   // first concatenated block of this CTA: with splitk > 1 the blocks (not the k-range) are dealt out to the splits
   if (g.kblocks > 1) {
     const int hi = g.a_tri == 1 ? min(g.kblk, m0 + BM) : g.kblk;
+    int nblk = g.kblocks;
+    if (g.splitk > 1) {
+      const int bps = (g.kblocks + g.splitk - 1) / g.splitk;
+      blk0 = split * bps;
+      nblk = max(0, min(bps, g.kblocks - blk0));
+    }
     kbeg = 0;
     tpb = hi / BK;
-    ktiles = g.kblocks * tpb;
+    ktiles = nblk * tpb;
   }
-  auto koff = [&](int kt) { const int blk = kt / tpb; return blk * kblk + kbeg + (kt - blk * tpb) * BK; };
+  auto koff = [&](int kt) { const int blk = kt / tpb; return (blk0 + blk) * kblk + kbeg + (kt - blk * tpb) * BK; };
 
   const double* Ab = g.A + (long)b * g.sA;
   const double* Bb = g.B + (long)b * g.sB;
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(WM* WN * 32) gemm_kernel(GemmArgs g) {
     const double* ss = Ss + st * BK + t4;
     double bsc[TN];
     if (!NT && g.bscale) {
-      const double* bp = g.bscale + (long)(kt / tpb) * g.ld_bscale + n0 + wn * TN * 8 + g8;
+      const double* bp = g.bscale + (long)(blk0 + kt / tpb) * g.ld_bscale + n0 + wn * TN * 8 + g8;
 #pragma unroll
       for (int j = 0; j < TN; ++j) bsc[j] = g.bscale_mul * bp[j * 8];
     }
@@ -275,7 +283,7 @@ __global__ void __launch_bounds__(WM* WN * 32) gemm_kernel(GemmArgs g) {
     };
     bool skip = false;
     if (g.a_tri && gemm_tri_skip_enabled()) {
-      const int kin = koff(kt) - (kt / tpb) * kblk;   // k inside the (possibly concatenated) triangular block
+      const int kin = koff(kt) - (blk0 + kt / tpb) * kblk;   // k inside the (possibly concatenated) triangular block
       const int r0w = m0 + wm * TM * 8;               // first row of the warp
       skip = g.a_tri == 1 ? (kin > r0w + TM * 8 - 1) : (kin + BK - 1 < r0w);
     }
@@ -419,7 +427,7 @@ inline GemmPlan gemm_plan(const GemmArgs& g, bool nt, int num_sms) {
 inline cudaError_t gemm_launch(const GemmArgs& g, bool nt, cudaStream_t st) {
   if (g.M % 64 || g.K % 16 || g.splitk < 1 || (g.splitk > 1 && !g.part)) return cudaErrorInvalidValue;
   if (g.epi_plane && (g.splitk != 1 || g.batch != 1)) return cudaErrorInvalidValue;
-  if (g.kblocks > 1 && (nt || g.splitk != 1 || g.kblk % 16 || g.kblocks * g.kblk != g.K || g.a_tri == 2)) return cudaErrorInvalidValue;
+  if (g.kblocks > 1 && (nt || g.splitk > g.kblocks || g.kblk % 16 || g.kblocks * g.kblk != g.K || g.a_tri == 2)) return cudaErrorInvalidValue;
   if (g.N == 32 && !nt) return gemm_launch_cfg<64, 32, 16, 2, 1, false, 3>(g, st);
   if (g.N % 64) return cudaErrorInvalidValue;
   if (gemm_uses_big_tiles(g)) {
