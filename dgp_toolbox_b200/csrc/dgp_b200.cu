@@ -64,6 +64,10 @@ struct dgp_ctx {
   static constexpr int kAux = 8;
   cudaStream_t aux[kAux] = {nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr};
+  // per-layer work that only the adjoint / the KL sum consume (Kuu^-1, KL, its adjoint's products) keeps running on the side
+  // streams while the forward chain starts; join_late() makes the ctx's stream wait for it
+  cudaEvent_t ev_late[kAux] = {nullptr};
+  int late_pending = 0;
   bool parallel_layers = true;
   long launches = 0;                    // kernels launched since the last dgp_reset_launch_count
   // optional per-category device timing (CUDA event pairs around every launch, on the ctx's stream)
@@ -153,6 +157,7 @@ struct LayerFork {   // fork the ctx's stream into per-layer side streams for a 
       for (int i = 0; i < dgp_ctx::kAux; ++i) {
         if (cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking) != cudaSuccess) return;
         if (cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) != cudaSuccess) return;
+        if (cudaEventCreateWithFlags(&c->ev_late[i], cudaEventDisableTiming) != cudaSuccess) return;
       }
     }
     if (cudaEventRecord(c->ev_fork, main) != cudaSuccess) return;
@@ -167,7 +172,24 @@ struct LayerFork {   // fork the ctx's stream into per-layer side streams for a 
     }
     c->stream = main;
   }
+  void detach() {   // leave the side streams running; join_late() waits for them
+    if (active) {
+      for (int i = 0; i < n; ++i) cudaEventRecord(c->ev_late[i], c->aux[i]);
+      c->late_pending = n;
+      active = false;
+    }
+    c->stream = main;
+  }
   ~LayerFork() { join(); }
+};
+
+void join_late(dgp_ctx* c) {
+  for (int i = 0; i < c->late_pending; ++i) cudaStreamWaitEvent(c->stream, c->ev_late[i], 0);
+  c->late_pending = 0;
+}
+struct LateGuard {   // no exit from a model-level call leaves side-stream work unjoined (the next call reuses the arena)
+  dgp_ctx* c;
+  ~LateGuard() { join_late(c); }
 };
 
 void drop_graphs(dgp_ctx* c);
@@ -349,7 +371,8 @@ std::vector<PanelDesc> build_schedule(int Mp, int BM, int D_out, bool vform) {
 
 enum PrepLevel { PREP_FWD = 0, PREP_KL = 1, PREP_GRAD = 2 };
 
-int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& lw, PrepLevel level, bool vform_grad_ok = true) {
+int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& lw, PrepLevel level, bool vform_grad_ok = true,
+                bool defer_late = false) {
   const int nl = model->num_layers;
   lw.assign(nl, LayerWs());
   std::vector<CholArgs> hargs(nl);
@@ -453,9 +476,12 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
     if (BM == 128) LAUNCH(pack_stream_kernel<128>, w.NP, 256, 0, w.sched, w.Linv, w.LinvT, tsrc, w.Mp, w.stream);
     else LAUNCH(pack_stream_kernel<64>, w.NP, 256, 0, w.sched, w.Linv, w.LinvT, tsrc, w.Mp, w.stream);
   }
+  forkB.join();
   if (level >= PREP_KL) {
+    // consumed by the adjoint / the final KL sum only: with defer_late the forward chain does not wait for these
+    LayerFork forkC(c, nl);
     for (int l = 0; l < nl; ++l) {
-      forkB.use(l);
+      forkC.use(l);
       LayerWs& w = lw[l];
       const int Mp = w.Mp, D = w.D_out;
       GemmArgs g = gargs(w.LinvT, Mp, w.Linv, Mp, w.Kinv, Mp, Mp, Mp, Mp);   // Kinv = Linv^T Linv
@@ -475,6 +501,7 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
         RC(gemm(c, g, true));
       }
     }
+    if (defer_late) forkC.detach();
   }
   return DGP_OK;
 }
@@ -778,7 +805,8 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
 
   std::vector<LayerWs> lw;
   // the V-form adjoint pays ~8 extra M^3-class products per layer and step: worth it only when there are enough point-samples
-  RC(prep_layers(c, model, lw, adj ? PREP_GRAD : (o.want_elbo ? PREP_KL : PREP_FWD), N * S >= c->vform_grad_min_ps));
+  LateGuard late_guard{c};
+  RC(prep_layers(c, model, lw, adj ? PREP_GRAD : (o.want_elbo ? PREP_KL : PREP_FWD), N * S >= c->vform_grad_min_ps, true));
   const size_t base_used = c->used;
 
   int maxMp = 0, maxD = 1;
@@ -883,6 +911,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
     const ChunkLayer& clL = cls[nl - 1];
     // adjoint chain over the layers, last to first; params = false stops at the input gradient (o.dx)
     auto run_backward = [&](bool params) -> int {
+      join_late(c);   // Kuu^-1 and the other products deferred by prep_layers
       const long nb = Pp / 128;
       const int D0 = model->layers[0].D_in;
       double* dX_next = dXa;
@@ -962,6 +991,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
   }
 
   // ---- replicated epilogue: KL, its adjoint, RBF adjoint on Kuu, gradient assembly ----
+  join_late(c);
   CAT(DGP_CAT_PREP);
   if (grad || o.want_elbo) {
     double* out = o.out_flat;
@@ -1204,7 +1234,7 @@ void dgp_ctx_destroy(dgp_ctx* c) {
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->ev_fork) {
     cudaEventDestroy(c->ev_fork);
-    for (int i = 0; i < dgp_ctx::kAux; ++i) { if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); if (c->aux[i]) cudaStreamDestroy(c->aux[i]); }
+    for (int i = 0; i < dgp_ctx::kAux; ++i) { if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); if (c->ev_late[i]) cudaEventDestroy(c->ev_late[i]); if (c->aux[i]) cudaStreamDestroy(c->aux[i]); }
   }
   delete c;
 }
