@@ -501,7 +501,8 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
         RC(gemm(c, g, true));
       }
     }
-    if (defer_late) forkC.detach();
+    // (not while profiling: an event pair around a launch that waits for SMs behind the forward chain would time the wait)
+    if (defer_late && !c->profiling) forkC.detach();
   }
   return DGP_OK;
 }

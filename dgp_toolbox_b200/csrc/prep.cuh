@@ -41,16 +41,17 @@ struct CholArgs {
 constexpr int kCholNB = 32;
 constexpr int kCholThreads = 512;
 
-// dynamic shared memory: D[32][33] + panel[(Mp)][33]  (panel reused as the G block [32][Mp+1] of the inverse)
-inline size_t chol_smem_bytes(int Mp) { return (size_t)(32 * 33 + (size_t)Mp * 33 + 64) * sizeof(double); }
+// dynamic shared memory: D[32][33] + Dinv[32] + panel (transposed [32][Mp+4]; reused as the G block [32][Mp+1] of the inverse)
+inline size_t chol_smem_bytes(int Mp) { return (size_t)(32 * 33 + 32 + (size_t)Mp * 33 + 128) * sizeof(double); }
 
 __global__ void __launch_bounds__(kCholThreads) chol_inv_kernel(const CholArgs* __restrict__ args) {
   const CholArgs a = args[blockIdx.x];
   const int n = a.Mp, tid = threadIdx.x, nth = blockDim.x;
   extern __shared__ __align__(16) double sm[];
   double* D = sm;              // [32][33]
-  double* Pn = sm + 32 * 33;   // [n][33]
-  double* Dinv = Pn + (size_t)n * 33;   // [32] reciprocals of the current diagonal block's pivots
+  double* Dinv = sm + 32 * 33; // [32] reciprocals of the current diagonal block's pivots
+  double* Pn = Dinv + 32;      // panel, transposed: [32][n + 4]  (the inverse path reuses it as [32][n + 1])
+  const int ldp = n + 4;
   double* L = a.L;
 
   for (long idx = tid; idx < (long)n * n; idx += nth) {
@@ -109,25 +110,30 @@ __global__ void __launch_bounds__(kCholThreads) chol_inv_kernel(const CholArgs* 
       }
       double* orow = L + (long)(k0 + kCholNB + r) * n + k0;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) { orow[c] = x[c]; Pn[r * 33 + c] = x[c]; }
+      for (int c = 0; c < 32; ++c) { orow[c] = x[c]; Pn[c * ldp + r] = x[c]; }
     }
     __syncthreads();
-    // 3. trailing update on the lower triangle, 4x4 micro-tiles
+    // 3. trailing update on the lower triangle, 4x4 micro-tiles dealt out over the triangle (consecutive threads: same row
+    // strip, consecutive column strips, so the transposed panel is read as one broadcast + one contiguous run per k)
     const int nt4 = nt / 4;
-    for (int tix = tid; tix < nt4 * nt4; tix += nth) {
-      int ti = tix / nt4, tj = tix % nt4;
-      if (tj > ti) continue;
+    const int ntri = nt4 * (nt4 + 1) / 2;
+    for (int tix = tid; tix < ntri; tix += nth) {
+      int ti = (int)((sqrtf(8.f * (float)tix + 1.f) - 1.f) * 0.5f);
+      while (ti * (ti + 1) / 2 > tix) --ti;
+      while ((ti + 1) * (ti + 2) / 2 <= tix) ++ti;
+      const int tj = tix - ti * (ti + 1) / 2;
       double acc[4][4];
 #pragma unroll
       for (int p = 0; p < 4; ++p)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[p][q] = 0.0;
-      const double* pi = Pn + (ti * 4) * 33;
-      const double* pj = Pn + (tj * 4) * 33;
+      const double* pi = Pn + ti * 4;
+      const double* pj = Pn + tj * 4;
+#pragma unroll 4
       for (int c = 0; c < 32; ++c) {
-        double ai[4], bj[4];
-#pragma unroll
-        for (int p = 0; p < 4; ++p) { ai[p] = pi[p * 33 + c]; bj[p] = pj[p * 33 + c]; }
+        const double2 a01 = *reinterpret_cast<const double2*>(pi + c * ldp), a23 = *reinterpret_cast<const double2*>(pi + c * ldp + 2);
+        const double2 b01 = *reinterpret_cast<const double2*>(pj + c * ldp), b23 = *reinterpret_cast<const double2*>(pj + c * ldp + 2);
+        const double ai[4] = {a01.x, a01.y, a23.x, a23.y}, bj[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
         for (int p = 0; p < 4; ++p)
 #pragma unroll
@@ -220,10 +226,20 @@ __global__ void __launch_bounds__(256) tri_inv_kernel(const CholArgs* __restrict
   for (int ib = jb; ib < nb; ++ib) {
     const int i0 = ib * 32;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    // the 32 x 32 chunks of L travel global -> registers -> shared memory, one chunk ahead of the products that consume them
+    double pre[4], preD[4];
+    auto fetch = [&](double* dst, int col0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int idx = tid + u * 256; dst[u] = L[(long)(i0 + (idx >> 5)) * n + col0 + (idx & 31)]; }
+    };
+    fetch(preD, i0);
+    if (jb < ib) fetch(pre, jb * 32);
     for (int kb = jb; kb < ib; ++kb) {          // G = - sum_k L_ik X_kj
       __syncthreads();
-      for (int idx = tid; idx < 1024; idx += 256) Lc[(idx >> 5) * 33 + (idx & 31)] = L[(long)(i0 + (idx >> 5)) * n + kb * 32 + (idx & 31)];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int idx = tid + u * 256; Lc[(idx >> 5) * 33 + (idx & 31)] = pre[u]; }
       __syncthreads();
+      if (kb + 1 < ib) fetch(pre, (kb + 1) * 32);
       const double* xk = Xc + (size_t)(kb * 32) * 33 + cs;
 #pragma unroll 8
       for (int k = 0; k < 32; ++k) {
@@ -233,7 +249,8 @@ __global__ void __launch_bounds__(256) tri_inv_kernel(const CholArgs* __restrict
       }
     }
     __syncthreads();
-    for (int idx = tid; idx < 1024; idx += 256) Ld[(idx >> 5) * 33 + (idx & 31)] = L[(long)(i0 + (idx >> 5)) * n + i0 + (idx & 31)];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int idx = tid + u * 256; Ld[(idx >> 5) * 33 + (idx & 31)] = preD[u]; }
 #pragma unroll
     for (int q = 0; q < 4; ++q) G[r * 33 + cs + q] = (ib == jb) ? ((r == cs + q) ? 1.0 : 0.0) : acc[q];
     __syncthreads();
