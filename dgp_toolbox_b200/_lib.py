@@ -118,6 +118,7 @@ class Context:
             raise DGPError(f"dgp_ctx_create(device={device}) failed with code {rc} "
                            "(-3: device is not sm_100; -1: CUDA error)")
         self.h = h
+        self.graph = False
 
     def call(self, name, *args):
         lib.dgp_set_stream(self.h, _vp(torch.cuda.current_stream(self.device).cuda_stream))
@@ -163,6 +164,7 @@ class Context:
         rc = lib.dgp_set_graph(self.h, 1 if on else 0)
         if rc != 0:
             raise DGPError(f"dgp_set_graph ({rc}): {lib.dgp_last_error(self.h).decode()}")
+        self.graph = bool(on)
 
     def set_workspace_limit(self, nbytes: int):
         rc = lib.dgp_set_workspace_limit(self.h, int(nbytes))

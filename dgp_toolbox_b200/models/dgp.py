@@ -309,14 +309,25 @@ class DGP_Base(_Module):
 
     def _adam_loop(self, data, params, state, t0, iterations, lr, beta_1, beta_2, epsilon, messages):
         """The reference's loop (dgp.py:146-154) in blocks that end on the steps it prints at (step % messages == 0)."""
-        step = 0
-        while step < iterations:
-            n = 1 if step == 0 else min(messages, iterations - step)
-            trace = self._train_adam(data, params, state, t0 + step, n, lr, beta_1, beta_2, epsilon)
-            step += n
-            if (step - 1) % messages == 0:
-                print(f"ELBO: {trace[-1].item()}")
-        _lib.get_context(self.device).check()
+        ctx = _lib.get_context(self.device)
+        X = _lib.as_device(data[0], self.device)
+        data = (X, _lib.as_device(data[1], self.device))   # one device copy for the whole loop: stable addresses
+        # launch-bound problems (the library's own threshold for its sub-wave paths): replay the step as a CUDA graph
+        auto_graph = not ctx.graph and X.shape[0] * self.num_samples <= 32768
+        if auto_graph:
+            ctx.set_graph(True)
+        try:
+            step = 0
+            while step < iterations:
+                n = 1 if step == 0 else min(messages, iterations - step)
+                trace = self._train_adam(data, params, state, t0 + step, n, lr, beta_1, beta_2, epsilon)
+                step += n
+                if (step - 1) % messages == 0:
+                    print(f"ELBO: {trace[-1].item()}")
+            ctx.check()
+        finally:
+            if auto_graph:
+                ctx.set_graph(False)
 
     def optimize_adam(self, data, iterations=5000, lr=0.01, beta_1=0.9, beta_2=0.999, epsilon=1e-07, messages=100):
         """dgp.py:132-154. The whole loop runs in the library (dgp_train_adam); the host only prints."""
