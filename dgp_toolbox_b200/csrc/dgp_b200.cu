@@ -610,8 +610,9 @@ int forward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, ChunkLa
 
 struct Upstream { double *Gm, *GvT, *GmPad, *gq, *part; long nblocks; };
 
-// The contractions over the point-samples that produce a layer's parameter gradients are independent of each other. On
-// latency-bound (sub-wave) calls they run side by side on the ctx's side streams, each with its own slice of the split-K scratch;
+// The contractions over the point-samples that produce a layer's parameter gradients are independent of each other: they run
+// side by side on the ctx's side streams, each with its own slice of the split-K scratch. On sub-wave calls that multiplies the
+// occupied SMs; on full-size calls each kernel's tail wave is filled by the next kernel's CTAs (config 2: 100.9 -> 98.8 ms/step).
 // `on_main` is issued on the caller's stream while they run.
 template <typename F>
 int param_gemms(dgp_ctx* c, GemmArgs* gs, const bool* nts, int n, double* part, size_t part_cap, bool small, F&& on_main) {
@@ -621,7 +622,8 @@ int param_gemms(dgp_ctx* c, GemmArgs* gs, const bool* nts, int n, double* part, 
     off[i] = total;
     if (gs[i].splitk > 1) total += (((size_t)gs[i].splitk * gs[i].batch * gs[i].M * gs[i].N) + 31) & ~(size_t)31;
   }
-  const bool par = small && total <= part_cap;
+  (void)small;
+  const bool par = total <= part_cap;
   LayerFork fk(c, par ? n : 0);
   for (int i = 0; i < n; ++i) {
     fk.use(i);
