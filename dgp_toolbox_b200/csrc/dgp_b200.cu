@@ -68,6 +68,10 @@ struct dgp_ctx {
   // streams while the forward chain starts; join_late() makes the ctx's stream wait for it
   cudaEvent_t ev_late[kAux] = {nullptr};
   int late_pending = 0;
+  // a layer's parameter contractions keep running on the side streams while the next layer's data path of the adjoint chain
+  // runs on the ctx's stream (two sets of adjoint temporaries alternate between the layers); join_param() waits for a set
+  cudaEvent_t ev_param[2][4] = {{nullptr}};
+  int param_pending[2] = {0, 0};
   bool parallel_layers = true;
   long launches = 0;                    // kernels launched since the last dgp_reset_launch_count
   // optional per-category device timing (CUDA event pairs around every launch, on the ctx's stream)
@@ -159,6 +163,9 @@ struct LayerFork {   // fork the ctx's stream into per-layer side streams for a 
         if (cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) != cudaSuccess) return;
         if (cudaEventCreateWithFlags(&c->ev_late[i], cudaEventDisableTiming) != cudaSuccess) return;
       }
+      for (int k = 0; k < 2; ++k)
+        for (int i = 0; i < 4; ++i)
+          if (cudaEventCreateWithFlags(&c->ev_param[k][i], cudaEventDisableTiming) != cudaSuccess) return;
     }
     if (cudaEventRecord(c->ev_fork, main) != cudaSuccess) return;
     for (int i = 0; i < n; ++i) cudaStreamWaitEvent(c->aux[i], c->ev_fork, 0);
@@ -180,8 +187,21 @@ struct LayerFork {   // fork the ctx's stream into per-layer side streams for a 
     }
     c->stream = main;
   }
+  void detach_param(int set) {   // leave the (<= 4) side streams running; join_param(set) waits for them
+    if (active) {
+      for (int i = 0; i < n; ++i) cudaEventRecord(c->ev_param[set][i], c->aux[i]);
+      c->param_pending[set] = n;
+      active = false;
+    }
+    c->stream = main;
+  }
   ~LayerFork() { join(); }
 };
+
+void join_param(dgp_ctx* c, int set) {
+  for (int i = 0; i < c->param_pending[set]; ++i) cudaStreamWaitEvent(c->stream, c->ev_param[set][i], 0);
+  c->param_pending[set] = 0;
+}
 
 void join_late(dgp_ctx* c) {
   for (int i = 0; i < c->late_pending; ++i) cudaStreamWaitEvent(c->stream, c->ev_late[i], 0);
@@ -189,7 +209,7 @@ void join_late(dgp_ctx* c) {
 }
 struct LateGuard {   // no exit from a model-level call leaves side-stream work unjoined (the next call reuses the arena)
   dgp_ctx* c;
-  ~LateGuard() { join_late(c); }
+  ~LateGuard() { join_late(c); join_param(c, 0); join_param(c, 1); }
 };
 
 void drop_graphs(dgp_ctx* c);
@@ -614,31 +634,42 @@ struct Upstream { double *Gm, *GvT, *GmPad, *gq, *part; long nblocks; };
 // side by side on the ctx's side streams, each with its own slice of the split-K scratch. On sub-wave calls that multiplies the
 // occupied SMs; on full-size calls each kernel's tail wave is filled by the next kernel's CTAs (config 2: 100.9 -> 98.8 ms/step).
 // `on_main` is issued on the caller's stream while they run.
+struct ParamScratch {
+  double* part = nullptr; size_t cap = 0;
+  bool fixed = false; size_t off[4] = {0, 0, 0, 0}, room[4] = {0, 0, 0, 0};   // per-contraction regions that hold for every layer
+  int defer_set = -1;   // >= 0: leave the contractions running and record their completion for join_param(defer_set)
+};
+
 template <typename F>
-int param_gemms(dgp_ctx* c, GemmArgs* gs, const bool* nts, int n, double* part, size_t part_cap, bool small, F&& on_main) {
+int param_gemms(dgp_ctx* c, GemmArgs* gs, const bool* nts, int n, const ParamScratch& ps, F&& on_main) {
   size_t off[8], total = 0;
+  bool fixed = ps.fixed && n <= 4;
   for (int i = 0; i < n; ++i) {
     gs[i].splitk = pick_splitk(c, gs[i], nts[i]);
     off[i] = total;
-    if (gs[i].splitk > 1) total += (((size_t)gs[i].splitk * gs[i].batch * gs[i].M * gs[i].N) + 31) & ~(size_t)31;
+    const size_t need = gs[i].splitk > 1 ? (size_t)gs[i].splitk * gs[i].batch * gs[i].M * gs[i].N : 0;
+    total += (need + 31) & ~(size_t)31;
+    if (fixed && need > ps.room[i]) fixed = false;
   }
-  (void)small;
-  const bool par = total <= part_cap;
+  const bool par = fixed || total <= ps.cap;
   LayerFork fk(c, par ? n : 0);
   for (int i = 0; i < n; ++i) {
     fk.use(i);
-    gs[i].part = part + (fk.active ? off[i] : 0);
+    gs[i].part = ps.part + (fk.active ? (fixed ? ps.off[i] : off[i]) : 0);
     RC(gemm(c, gs[i], nts[i]));
   }
   if (fk.active) c->stream = fk.main;
   RC(on_main());
-  fk.join();
+  // two layers' contractions may be in flight only with regions that do not depend on the layer; not while profiling (an event
+  // pair around a launch that shares the SMs with another stream would time the sharing)
+  if (fk.active && fixed && ps.defer_set >= 0 && !c->profiling) fk.detach_param(ps.defer_set);
+  else fk.join();
   return DGP_OK;
 }
 
 int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const ChunkLayer& cl, const Temps& tmp,
-                   const Upstream& up, double* dXin, double* XaugPad, double* rbf_part, double* splitk_part, size_t splitk_cap, long Nc,
-                   long S, bool first_chunk, bool params = true) {
+                   const Upstream& up, double* dXin, double* XaugPad, double* rbf_part, const ParamScratch& ps, long Nc, long S, bool first_chunk,
+                   bool params = true) {
   const long P = Nc * S, Pp = round_up(P, kTileP);
   const int Mp = w.Mp, D = w.D_out;
   const double beta = first_chunk ? 0.0 : 1.0;
@@ -699,7 +730,7 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
     pg[2].beta = beta;
     pg[3] = gargs(Gbar, Pp, XaugPad, 32, w.H, 32, Mp, 32, (int)Pp);
     pg[3].beta = beta;
-    RC(param_gemms(c, pg, pnt, 4, splitk_part, splitk_cap, small, [&]() -> int {
+    RC(param_gemms(c, pg, pnt, 4, ps, [&]() -> int {
       LAUNCH(reduce_partials_kernel, w.D_in + 1, 256, 0, rbf_part, nbv, w.D_in + 1, w.rbf_red, first_chunk ? 0 : 1);
       LAUNCH(reduce_partials_kernel, 3, 256, 0, up.part, up.nblocks, 3, w.sgv, first_chunk ? 0 : 1);
       return DGP_OK;
@@ -718,7 +749,10 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
     const GemmPlan p = gemm_plan(g, false, c->num_sms);
     long s = p.tiles > 0 ? p.slots / (2 * p.tiles) : 1;
     if (s > D) s = D;
-    if (s >= 2 && (size_t)s * Mp * Pp <= splitk_cap) { g.splitk = (int)s; g.part = splitk_part; }
+    if (s >= 2 && (size_t)s * Mp * Pp <= ps.cap) {
+      join_param(c, 0); join_param(c, 1);   // the scratch is shared with the parameter contractions still in flight
+      g.splitk = (int)s; g.part = ps.part;
+    }
   }
   RC(gemm(c, g, false));
   // W = Ku^-1 dA'
@@ -761,7 +795,7 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
   pg[2].beta = beta;
   pg[3] = gargs(Gbar, Pp, XaugPad, 32, w.H, 32, Mp, 32, (int)Pp);
   pg[3].beta = beta;
-  RC(param_gemms(c, pg, pnt, 4, splitk_part, splitk_cap, small, [&]() -> int {
+  RC(param_gemms(c, pg, pnt, 4, ps, [&]() -> int {
     LAUNCH(reduce_partials_kernel, w.D_in + 1, 256, 0, rbf_part, nb, w.D_in + 1, w.rbf_red, first_chunk ? 0 : 1);
     LAUNCH(reduce_partials_kernel, 3, 256, 0, up.part, up.nblocks, 3, w.sgv, first_chunk ? 0 : 1);
     return DGP_OK;
@@ -782,13 +816,20 @@ struct RunOpts {
   double* dx = nullptr;                                          // d sum(-EI) / dX [N][D0] (analytic EI only)
 };
 
-size_t max_splitk_part(const std::vector<LayerWs>& lw) {
-  size_t m = 0;
+// Split-K scratch of the adjoint: four regions (the parameter contractions of a layer run side by side), sized for the widest
+// layer so that the same layout serves every layer.
+void splitk_regions(const std::vector<LayerWs>& lw, size_t room[4]) {
+  size_t Mp = 0, D = 1;
   for (const LayerWs& w : lw) {
-    // room for the four parameter contractions of a layer side by side (param_gemms)
-    size_t v = (size_t)64 * (w.D_out + 1) * w.Mp * w.Mp + (size_t)128 * w.Mp * 32 + 1024;
-    if (v > m) m = v;
+    if ((size_t)w.Mp > Mp) Mp = w.Mp;
+    if ((size_t)w.D_out > D) D = w.D_out;
   }
+  room[0] = 64 * Mp * Mp; room[1] = 64 * D * Mp * Mp; room[2] = 64 * Mp * 32; room[3] = 64 * Mp * 32;
+}
+size_t max_splitk_part(const std::vector<LayerWs>& lw) {
+  size_t room[4];
+  splitk_regions(lw, room);
+  const size_t m = room[0] + room[1] + room[2] + room[3] + 1024;
   return m < kSplitkPartDoubles ? m : kSplitkPartDoubles + ((size_t)32 * 1024 * 1024 / 8);
 }
 
@@ -824,6 +865,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
   pp_doubles += 3 * (size_t)maxMp;                                   // temps
   if (!adj) pp_doubles += (size_t)maxD * maxMp;                      // shared T
   if (adj) pp_doubles += 2 * (size_t)maxD + 32 + 1 + 32 + 2 * 32;    // Gm, GvT, GmPad, gq, XaugPad, dX ping-pong
+  if (adj && nl > 1) pp_doubles += 3 * (size_t)maxMp + 2 * (size_t)maxD + 32 + 1 + 32;   // second set of adjoint temporaries
   size_t fixed = base_used + (adj ? max_splitk_part(lw) * sizeof(double) : 0) + ((size_t)8 << 20);
   long Nc_max;
   {
@@ -857,7 +899,9 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
   tmp.t1 = walloc(c, (size_t)maxMp * Ppmax);
   tmp.t2 = walloc(c, (size_t)maxMp * Ppmax);
   double* Tshared = adj ? nullptr : walloc(c, (size_t)maxD * maxMp * Ppmax);
-  Upstream up{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+  Upstream up{nullptr, nullptr, nullptr, nullptr, nullptr, 0}, up1{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+  Temps tmp1;
+  double* XaugPad1 = nullptr;
   double *XaugPad = nullptr, *dXa = nullptr, *dXb = nullptr, *rbf_part = nullptr, *skpart = nullptr, *lik_part = nullptr;
   size_t skcap = 0;
   double* acc = nullptr;   // [0] data term, [1] d/d lik variance (accumulated over chunks)
@@ -877,6 +921,23 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
     rbf_part = walloc(c, (size_t)nbmax * 2 * 32);   // one row of partials per 64-column block of rbf_bwd_kernel
     skcap = max_splitk_part(lw);
     skpart = walloc(c, skcap);
+    if (nl > 1) {   // second set: layer l's parameter contractions read theirs while layer l-1's data path fills the other
+      tmp1.t0 = walloc(c, (size_t)maxMp * Ppmax);
+      tmp1.t1 = walloc(c, (size_t)maxMp * Ppmax);
+      tmp1.t2 = walloc(c, (size_t)maxMp * Ppmax);
+      up1.Gm = walloc(c, (size_t)Ppmax * maxD);
+      up1.GvT = walloc(c, (size_t)Ppmax * maxD);
+      up1.GmPad = walloc(c, (size_t)Ppmax * 32);
+      up1.gq = walloc(c, (size_t)Ppmax);
+      XaugPad1 = walloc(c, (size_t)Ppmax * 32);
+    }
+  }
+  ParamScratch ps;
+  ps.part = skpart; ps.cap = skcap;
+  if (adj) {
+    splitk_regions(lw, ps.room);
+    ps.off[0] = 0; ps.off[1] = ps.room[0]; ps.off[2] = ps.off[1] + ps.room[1]; ps.off[3] = ps.off[2] + ps.room[2];
+    ps.fixed = ps.off[3] + ps.room[3] <= skcap;
   }
   if (c->dry) return DGP_OK;
 
@@ -921,30 +982,41 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
       for (int l = nl - 1; l >= 0; --l) {
         const dgp_layer_desc& d = model->layers[l];
         CAT(DGP_CAT_OTHER);
+        // the two sets of adjoint temporaries alternate: this layer's data path may start while the previous layer's parameter
+        // contractions still read the other set; the contractions that read THIS set two layers ago must be done
+        const int set = (nl > 1 && tmp1.t0) ? ((nl - 1 - l) & 1) : 0;
+        const Temps& tm = set ? tmp1 : tmp;
+        Upstream& us = set ? up1 : up;
+        double* Xaug = set ? XaugPad1 : XaugPad;
+        join_param(c, set);
+        ParamScratch psl = ps;
+        psl.defer_set = (params && l > 0 && tmp1.t0) ? set : -1;   // the first layer is the last one processed: nothing to overlap with
         if (l == 0 && share0) {
           // first-layer sharing: per-point upstream gradients = sums over the S samples, then a P = Nc adjoint
           const long Pp0 = round_up(Nc, kTileP), nb0 = Pp0 / 128;
-          UpstreamOut uh{up.Gm, up.GvT, up.GmPad, up.gq, lik_part};
+          UpstreamOut uh{us.Gm, us.GvT, us.GmPad, us.gq, lik_part};
           LAUNCH(upstream_reduce_kernel, (unsigned)nb0, 128, 0, dX_next, cls[0].z, cls[0].Fvar, Nc, S, Pp0, d.D_out, d.jitter, uh);
-          Upstream up0 = up;
+          Upstream up0 = us;
           up0.part = lik_part; up0.nblocks = nb0;
-          RC(backward_layer(c, d, lw[0], cls[0], tmp, up0, o.dx ? o.dx + n0 * D0 : nullptr, XaugPad, rbf_part, skpart, skcap, Nc, 1, first, params));
+          RC(backward_layer(c, d, lw[0], cls[0], tm, up0, o.dx ? o.dx + n0 * D0 : nullptr, Xaug, rbf_part, psl, Nc, 1, first, params));
           continue;
         }
         if (l < nl - 1) {
           // Gm = G_F, Gv = G_F z / (2 sqrt(var + jitter))                          (adjoint of utils/utils.py:40-41)
-          UpstreamOut uh{up.Gm, up.GvT, up.GmPad, up.gq, lik_part};
+          UpstreamOut uh{us.Gm, us.GvT, us.GmPad, us.gq, lik_part};
           LAUNCH(upstream_kernel, (unsigned)nb, 128, 0, dX_next, cls[l].z, cls[l].Fvar, P, Pp, d.D_out, d.jitter, uh);
         }
+        us.part = lik_part; us.nblocks = nb;
         double* dXin = (l > 0 || o.dx) ? (dX_next == dXa ? dXb : dXa) : nullptr;
         if (l == 0 && o.dx && S == 1) dXin = o.dx + n0 * D0;   // one sample: the per-point-sample gradient is the answer
-        RC(backward_layer(c, d, lw[l], cls[l], tmp, up, dXin, XaugPad, rbf_part, skpart, skcap, Nc, S, first, params));
+        RC(backward_layer(c, d, lw[l], cls[l], tm, us, dXin, Xaug, rbf_part, psl, Nc, S, first, params));
         if (l == 0 && o.dx && S > 1) {
           CAT(DGP_CAT_OTHER);
           LAUNCH(sum_samples_kernel, (unsigned)((Nc * D0 + 255) / 256), 256, 0, dXin, Nc, S, D0, o.dx + n0 * D0);
         }
         if (dXin) dX_next = dXin;
       }
+      join_param(c, 0); join_param(c, 1);   // the next chunk's forward chain reuses the temporaries
       return DGP_OK;
     };
     CAT(DGP_CAT_OTHER);
@@ -1237,6 +1309,7 @@ void dgp_ctx_destroy(dgp_ctx* c) {
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->ev_fork) {
     cudaEventDestroy(c->ev_fork);
+    for (int k = 0; k < 2; ++k) for (int i = 0; i < 4; ++i) if (c->ev_param[k][i]) cudaEventDestroy(c->ev_param[k][i]);
     for (int i = 0; i < dgp_ctx::kAux; ++i) { if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); if (c->ev_late[i]) cudaEventDestroy(c->ev_late[i]); if (c->aux[i]) cudaStreamDestroy(c->aux[i]); }
   }
   delete c;
