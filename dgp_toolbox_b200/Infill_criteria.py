@@ -1,13 +1,15 @@
-"""Expected-improvement evaluation with the reference's interface (dgp_dace/Infill_criteria.py:12-52). Only the
-*evaluation* (EI.run on a DGP) is on the accelerated path; the DE/Adam search loops of the reference
-(Infill_criteria.py:61-87) are host-side callers and out of scope."""
+"""The reference's infill criteria with their interface (dgp_dace/Infill_criteria.py): evaluation on the accelerated path
+(dgp_ei, dgp_ei_grad, dgp_predict_moments + dgp_acq_moments) and the `optimize` searches (differential evolution, then Adam on
+the sigmoid-reparameterised x; Infill_criteria.py:61-87,142-168,207-233) with the search state on the device (search.py,
+SURVEY §8 f3)."""
 from __future__ import annotations
 
 import ctypes as C
 
+import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, search
 
 
 class Infill_criteria(object):
@@ -31,14 +33,16 @@ class EI(Infill_criteria):
         self.IC_optimized = None
         self.x_opt = None
 
-    def run(self, model, x, analytic=True, num_samples=1000, zs=None, seed=None):
+    def run(self, model, x, analytic=True, num_samples=1000, zs=None, seed=None, out=None):
         """Returns -EI [N, D_L]. analytic: moment-match predict_f over the S samples (:39-41) then the closed form
-        (:43-47); otherwise mean_s max(y_min - F, 0) on propagated samples (:49-51). One C-ABI call (dgp_ei)."""
+        (:43-47); otherwise mean_s max(y_min - F, 0) on propagated samples (:49-51). One C-ABI call (dgp_ei).
+        `out`: result buffer to reuse (search loops keep every address fixed so that the call replays as a graph)."""
         if getattr(model, "name", None) != 'dgp':
             raise NotImplementedError("only model.name == 'dgp' is on the accelerated path")
         X = model._check_X(_lib.as_device(x, model.device))
         N, D = X.shape[0], model.layers[-1].num_outputs
-        out = torch.empty((N, D), dtype=torch.float64, device=X.device)
+        if out is None:
+            out = torch.empty((N, D), dtype=torch.float64, device=X.device)
         if N == 0:
             return out
         m, keep = model._model_desc()
@@ -48,15 +52,17 @@ class EI(Infill_criteria):
                                         y_min, 1 if analytic else 0, _lib.ptr(out))
         return out
 
-    def run_with_grad(self, model, x, num_samples=1000, zs=None, seed=None):
+    def run_with_grad(self, model, x, num_samples=1000, zs=None, seed=None, out=None, dx=None):
         """(-EI [N, D_L], d sum(-EI) / dx [N, d]): the value and the gradient the reference's Adam-on-x loop takes with
         tape.gradient(loss, x) (Infill_criteria.py:79-84), analytic EI. One C-ABI call (dgp_ei_grad)."""
         if getattr(model, "name", None) != 'dgp':
             raise NotImplementedError("only model.name == 'dgp' is on the accelerated path")
         X = model._check_X(_lib.as_device(x, model.device))
         N, D = X.shape[0], model.layers[-1].num_outputs
-        out = torch.empty((N, D), dtype=torch.float64, device=X.device)
-        dx = torch.zeros_like(X)
+        if out is None:
+            out = torch.empty((N, D), dtype=torch.float64, device=X.device)
+        if dx is None:
+            dx = torch.zeros_like(X)
         if N == 0:
             return out, dx
         m, keep = model._model_desc()
@@ -69,6 +75,40 @@ class EI(Infill_criteria):
     def loss(self, model, x, analytic):
         """Infill_criteria.py:53-60."""
         return self.run(model, x, analytic)
+
+    def optimize(self, model, bounds, popsize_DE=300, popstd_DE=1.5, iterations_DE=400, init_adam=None, iterations_adam=1000,
+                 method='DE', analytic=True, num_samples=1000, seed=None):
+        """Infill_criteria.py:61-87: minimise -EI over the box `bounds = (lw, up)`; 'DE' (differential evolution, population
+        popsize_DE around u = 0 with spread popstd_DE, iterations_DE generations, one dgp_ei call per generation), 'Adam'
+        (iterations_adam steps of lr 0.01 on u from init_adam, one dgp_ei_grad call per step) or 'DE+Adam'. Sets and returns
+        x_opt [d, 1] (numpy, like the reference); IC_optimized is the criterion there. Every evaluation draws fresh samples,
+        as the reference's tf.random.normal does."""
+        lw = np.broadcast_to(np.asarray(bounds[0], dtype=np.float64).reshape(-1), (self.d,)).copy()
+        up = np.broadcast_to(np.asarray(bounds[1], dtype=np.float64).reshape(-1), (self.d,)).copy()
+        if method not in ('DE', 'Adam', 'DE+Adam'):
+            raise ValueError(f"unknown method {method!r}")
+        de_seed = model._next_seed(seed)
+        with search.GraphScope(model.device):
+            if method in ('DE', 'DE+Adam'):
+                res = search.de_minimize(lambda X, out: self.run(model, X, analytic, num_samples, out=out), lw, up, self.d,
+                                         model.device, popsize_DE, popstd_DE, iterations_DE, seed=de_seed)
+                self.x_opt = res["x"].cpu().numpy().reshape(self.d, 1)
+                self.de_iterations = res["iterations"]      # < iterations_DE when the population collapsed (TFP position_tolerance)
+                self.IC_optimized = self.run(model, self.x_opt.reshape(1, self.d), analytic, num_samples)
+            if method in ('Adam', 'DE+Adam'):
+                if not analytic:
+                    raise NotImplementedError("the input gradient exists for the analytic EI only")
+                if init_adam is None:
+                    init_adam = np.zeros(self.d) if self.x_opt is None else self.x_opt
+                init_adam = np.asarray(init_adam, dtype=np.float64).reshape(self.d)
+                u0 = _lib.as_device(np.log((up - init_adam + 1e-3) / (init_adam - lw + 1e-3)).reshape(1, self.d), model.device)
+                out = torch.empty((1, model.layers[-1].num_outputs), dtype=torch.float64, device=u0.device)
+                dx = torch.zeros_like(u0)
+                u, X, val = search.adam_box_minimize(
+                    lambda X: self.run_with_grad(model, X, num_samples, out=out, dx=dx), lw, up, u0, iterations_adam, lr=0.01)
+                self.x_opt = X.cpu().numpy().reshape(self.d, 1)
+                self.IC_optimized = val.clone()
+        return self.x_opt
 
 
 def _scalar(v):
@@ -92,6 +132,28 @@ def _moment_criterion(kind, model, x, y, num_samples, zs, seed, with_x=False):
     return out
 
 
+def _optimize_de(crit, run, model, bounds, popsize_DE, popstd_DE, iterations_DE, method, seed):
+    """The DE stage of the reference's `optimize` for the moment-based criteria (Infill_criteria.py:142-168,207-233); their Adam
+    stage needs d criterion / dx, which the accelerated path provides for EI only."""
+    if method != 'DE':
+        raise NotImplementedError("method 'Adam' / 'DE+Adam' needs the input gradient, available for EI only (dgp_ei_grad)")
+    lw = np.broadcast_to(np.asarray(bounds[0], dtype=np.float64).reshape(-1), (crit.d,)).copy()
+    up = np.broadcast_to(np.asarray(bounds[1], dtype=np.float64).reshape(-1), (crit.d,)).copy()
+    with search.GraphScope(model.device):
+        def objective(X, out):
+            v = run(X)
+            if out is None:
+                return v
+            out.copy_(v)
+            return out
+        res = search.de_minimize(objective, lw, up, crit.d, model.device, popsize_DE, popstd_DE, iterations_DE,
+                                 seed=model._next_seed(seed))
+        crit.x_opt = res["x"].cpu().numpy().reshape(crit.d, 1)
+        crit.de_iterations = res["iterations"]
+        crit.IC_optimized = run(crit.x_opt.reshape(1, crit.d))
+    return crit.x_opt
+
+
 class WB2(Infill_criteria):
     """Infill_criteria.py:106-141: -(EI - mean) on predict_y moments."""
 
@@ -100,12 +162,18 @@ class WB2(Infill_criteria):
         self.y_min = y_min
         self.d = d
         self.IC_optimized = None
+        self.x_opt = None
 
     def run(self, model, x, num_samples=500, zs=None, seed=None):
         return _moment_criterion(1, model, x, self.y_min, num_samples, zs, seed)
 
     def loss(self, model, x):
         return self.run(model, x)
+
+    def optimize(self, model, bounds, popsize_DE=300, popstd_DE=1.5, iterations_DE=400, init_adam=None, iterations_adam=1000,
+                 method='DE', seed=None):
+        """Infill_criteria.py:142-168 (DE stage)."""
+        return _optimize_de(self, lambda X: self.run(model, X), model, bounds, popsize_DE, popstd_DE, iterations_DE, method, seed)
 
 
 class WB2S(Infill_criteria):
@@ -116,12 +184,18 @@ class WB2S(Infill_criteria):
         self.y_min = y_min
         self.d = d
         self.IC_optimized = None
+        self.x_opt = None
 
     def run(self, model, x, num_samples=500, zs=None, seed=None):
         return _moment_criterion(3, model, x, self.y_min, num_samples, zs, seed, with_x=True)
 
     def loss(self, model, x):
         return self.run(model, x)
+
+    def optimize(self, model, bounds, popsize_DE=300, popstd_DE=1.5, iterations_DE=400, init_adam=None, iterations_adam=1000,
+                 method='DE', seed=None):
+        """Infill_criteria.py:207-233 (DE stage; the [N, d] criterion is summed over its columns per candidate)."""
+        return _optimize_de(self, lambda X: self.run(model, X), model, bounds, popsize_DE, popstd_DE, iterations_DE, method, seed)
 
 
 class EV_one_constraint(Infill_criteria):

@@ -87,6 +87,10 @@ _SIG = {
     "dgp_ei": (C.c_int, [_vp, C.POINTER(ModelDesc), _vp, _i64, _i64, C.POINTER(_vp), _u64, _i64, _d, _i, _vp]),
     "dgp_ei_grad": (C.c_int, [_vp, C.POINTER(ModelDesc), _vp, _i64, _i64, C.POINTER(_vp), _u64, _i64, _d, _vp, _vp]),
     "dgp_acq_moments": (C.c_int, [_vp, _i, _vp, _vp, _i64, _d, _vp, _i, _vp]),
+    "dgp_de_propose": (C.c_int, [_vp, _vp, _i64, _i, _vp, _vp, _u64, _i64, _d, _d, _vp, _vp]),
+    "dgp_de_select": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i]),
+    "dgp_box_from_u": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
+    "dgp_adam_box_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i64, _d, _d, _d, _d, _vp]),
     "dgp_ev_mc": (C.c_int, [_vp, _vp, _i64, _i64, _d, _vp]),
     "dgp_ehvi2d": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp]),
     "dgp_debug_gemm": (C.c_int, [_vp, _i, _i, _i, _i, _d, _vp, _vp, _d, _vp, _i, _i, _i, _i, _vp]),

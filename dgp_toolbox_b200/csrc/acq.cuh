@@ -2,6 +2,7 @@
 // Reference: dgp_dace/models/dgp.py:362-366, dgp_dace/Infill_criteria.py:36-52, dgp_dace/EHVI.py:102-104,154-157.
 #pragma once
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace dgp {
 
@@ -155,6 +156,91 @@ __global__ void ehvi2d_kernel(const double* __restrict__ m0, const double* __res
     t2 += (psi_fn(y0[i - 1], y0[i - 1], mu0, s0) - psi_fn(y0[i - 1], y0[i], mu0, s0)) * d1;
   }
   out[c] = t1 + t2;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Acquisition search on the device (reference Infill_criteria.py:61-87 and its copies for the other criteria):
+// tfp.optimizer.differential_evolution_minimize ("rand/1/bin", differential weight 0.5, crossover probability 0.9) followed by
+// tf.optimizers.Adam, both on u with x = lw + (up - lw) / (1 + exp(u)).
+// Random choices come from Philox-4x32-10 with key = seed and counter = (member, generation, slot, 0xDE):
+//   slot 0: words (w0, w1, w2, w3) -> three distinct partners a, b, c != member (w_k mod (pop-1-k), then skipping the excluded
+//           indices in ascending order) and the forced crossover dimension w3 mod d;
+//   slot 1 + j/4: word j%4 -> uniform (w + 0.5) / 2^32 of dimension j; the dimension takes the mutant when it is < crossover.
+// ---------------------------------------------------------------------------------------------------------
+__device__ inline int de_skip(int v, int e0, int e1, int e2, int n_excl) {   // v-th index not in the sorted exclusion list
+  if (n_excl > 0 && v >= e0) ++v;
+  if (n_excl > 1 && v >= e1) ++v;
+  if (n_excl > 2 && v >= e2) ++v;
+  return v;
+}
+
+__global__ void de_propose_kernel(const double* __restrict__ pop_u, long pop, int d, const double* __restrict__ lw,
+                                  const double* __restrict__ up, unsigned long long seed, const unsigned long long* seed_ptr,
+                                  long generation, double weight, double crossover, double* __restrict__ cand_u,
+                                  double* __restrict__ cand_x) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= pop * d) return;
+  const int i = (int)(idx / d), j = (int)(idx % d);
+  const unsigned long long sd = seed_ptr ? *seed_ptr : seed;
+  uint32_t w[4];
+  philox4x32_10((uint32_t)i, (uint32_t)generation, 0u, 0xDEu, (uint32_t)sd, (uint32_t)(sd >> 32), w);
+  const int a = de_skip((int)(w[0] % (uint32_t)(pop - 1)), i, 0, 0, 1);
+  const int lo1 = min(i, a), hi1 = max(i, a);
+  const int b = de_skip((int)(w[1] % (uint32_t)(pop - 2)), lo1, hi1, 0, 2);
+  int e0 = lo1, e1 = hi1, e2 = b;   // sort {i, a, b}
+  if (e2 < e1) { const int t = e1; e1 = e2; e2 = t; }
+  if (e1 < e0) { const int t = e0; e0 = e1; e1 = t; }
+  const int c = de_skip((int)(w[2] % (uint32_t)(pop - 3)), e0, e1, e2, 3);
+  const int forced = (int)(w[3] % (uint32_t)d);
+  uint32_t r[4];
+  philox4x32_10((uint32_t)i, (uint32_t)generation, (uint32_t)(1 + j / 4), 0xDEu, (uint32_t)sd, (uint32_t)(sd >> 32), r);
+  const double uni = ((double)r[j % 4] + 0.5) * (1.0 / 4294967296.0);
+  const double mutant = pop_u[(long)a * d + j] + weight * (pop_u[(long)b * d + j] - pop_u[(long)c * d + j]);
+  const double u = (uni < crossover || j == forced) ? mutant : pop_u[(long)i * d + j];
+  cand_u[idx] = u;
+  cand_x[idx] = lw[j] + (up[j] - lw[j]) / (1.0 + exp(u));
+}
+
+// Member i takes the candidate when it is strictly better (minimisation); values are summed over the ncol output columns.
+__global__ void de_select_kernel(double* __restrict__ pop_u, double* __restrict__ pop_val, const double* __restrict__ cand_u,
+                                 const double* __restrict__ cand_val, long pop, int d, int ncol, int first) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pop) return;
+  double v = 0.0;
+  for (int k = 0; k < ncol; ++k) v += cand_val[i * ncol + k];
+  if (first || v < pop_val[i]) {
+    pop_val[i] = v;
+    for (int j = 0; j < d; ++j) pop_u[i * d + j] = cand_u[i * d + j];
+  }
+}
+
+__global__ void box_from_u_kernel(const double* __restrict__ u, const double* __restrict__ lw, const double* __restrict__ up,
+                                  long n, int d, double* __restrict__ x) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * d) return;
+  const int j = (int)(idx % d);
+  x[idx] = lw[j] + (up[j] - lw[j]) / (1.0 + exp(u[idx]));
+}
+
+// One tf.optimizers.Adam step on u from dL/dx (Infill_criteria.py:79-84): dx/du = -(up - lw) e^u / (1 + e^u)^2; the new x is
+// written back so that the next criterion evaluation reads it.
+__global__ void adam_box_kernel(double* __restrict__ u, double* __restrict__ m_state, double* __restrict__ v_state,
+                                const double* __restrict__ dx, const double* __restrict__ lw, const double* __restrict__ up, long n,
+                                int d, double lr_t, double beta1, double beta2, double eps, double* __restrict__ x) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * d) return;
+  const int j = (int)(idx % d);
+  const double span = up[j] - lw[j];
+  double uu = u[idx];
+  const double sg = 1.0 / (1.0 + exp(uu));              // x = lw + span * sg
+  const double g = dx[idx] * (-span * sg * (1.0 - sg));
+  const double m = beta1 * m_state[idx] + (1.0 - beta1) * g;
+  const double v = beta2 * v_state[idx] + (1.0 - beta2) * g * g;
+  m_state[idx] = m;
+  v_state[idx] = v;
+  uu -= lr_t * m / (sqrt(v) + eps);
+  u[idx] = uu;
+  x[idx] = lw[j] + span / (1.0 + exp(uu));
 }
 
 }  // namespace dgp

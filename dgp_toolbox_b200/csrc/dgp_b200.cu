@@ -1647,6 +1647,45 @@ int dgp_acq_moments(dgp_ctx* c, int kind, const double* mean, const double* var,
   return DGP_OK;
 }
 
+int dgp_de_propose(dgp_ctx* c, const double* pop_u, int64_t pop, int d, const double* lw, const double* up, uint64_t seed,
+                   int64_t generation, double weight, double crossover, double* cand_u, double* cand_x) {
+  if (!c || !pop_u || !lw || !up || !cand_u || !cand_x || d < 1 || generation < 0) return DGP_ERR_ARG;
+  if (pop < 4) { c->err = "differential evolution needs a population of at least 4"; return DGP_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  CAT(DGP_CAT_OTHER);
+  LAUNCH(de_propose_kernel, (unsigned)((pop * d + 127) / 128), 128, 0, pop_u, (long)pop, d, lw, up, (unsigned long long)seed,
+         (const unsigned long long*)nullptr, (long)generation, weight, crossover, cand_u, cand_x);
+  return DGP_OK;
+}
+
+int dgp_de_select(dgp_ctx* c, double* pop_u, double* pop_val, const double* cand_u, const double* cand_val, int64_t pop, int d,
+                  int ncol, int first) {
+  if (!c || !pop_u || !pop_val || !cand_u || !cand_val || pop < 1 || d < 1 || ncol < 1) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  CAT(DGP_CAT_OTHER);
+  LAUNCH(de_select_kernel, (unsigned)((pop + 127) / 128), 128, 0, pop_u, pop_val, cand_u, cand_val, (long)pop, d, ncol, first);
+  return DGP_OK;
+}
+
+int dgp_box_from_u(dgp_ctx* c, const double* u, const double* lw, const double* up, int64_t n, int d, double* x) {
+  if (!c || !u || !lw || !up || !x || n < 1 || d < 1) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  CAT(DGP_CAT_OTHER);
+  LAUNCH(box_from_u_kernel, (unsigned)((n * d + 127) / 128), 128, 0, u, lw, up, (long)n, d, x);
+  return DGP_OK;
+}
+
+int dgp_adam_box_step(dgp_ctx* c, double* u, double* m_state, double* v_state, const double* dx, const double* lw,
+                      const double* up, int64_t n, int d, int64_t t, double lr, double beta1, double beta2, double epsilon, double* x) {
+  if (!c || !u || !m_state || !v_state || !dx || !lw || !up || !x || n < 1 || d < 1 || t < 1) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  CAT(DGP_CAT_OTHER);
+  const double lr_t = lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t));
+  LAUNCH(adam_box_kernel, (unsigned)((n * d + 127) / 128), 128, 0, u, m_state, v_state, dx, lw, up, (long)n, d, lr_t, beta1, beta2,
+         epsilon, x);
+  return DGP_OK;
+}
+
 int dgp_ev_mc(dgp_ctx* c, const double* F, int64_t S, int64_t ND, double zero_c, double* out) {
   if (!c || !F || !out || S < 1 || ND < 1) return DGP_ERR_ARG;
   CK(cudaSetDevice(c->device));

@@ -175,6 +175,26 @@ int dgp_train_adam(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, c
                    int n_params, double* m_state, double* v_state, int64_t t0, int64_t steps, double lr, double beta1,
                    double beta2, double epsilon, double* out_flat, double* elbo_trace);
 
+/* ---- acquisition search: the reference's `optimize` methods (Infill_criteria.py:61-87,142-168,207-233,290-316) run
+ * tfp.optimizer.differential_evolution_minimize and then tf.optimizers.Adam on u, x = lw + (up - lw) / (1 + exp(u)). The criterion
+ * itself is evaluated by the entry points below (dgp_ei, dgp_ei_grad, dgp_predict_moments + dgp_acq_moments); these four keep the
+ * search state on the device between evaluations. All arrays are device pointers; lw / up have d entries. ----
+ * dgp_de_propose: one "rand/1/bin" generation (TFP defaults: weight 0.5, crossover 0.9): candidate_i = pop[a] + weight (pop[b] -
+ *   pop[c]) on the dimensions drawn with probability `crossover` (one dimension always), pop_i elsewhere; a, b, c distinct and != i.
+ *   Random choices: Philox-4x32-10, key = seed, counter = (i, generation, slot, 0xDE) (csrc/acq.cuh states the word layout; the
+ *   oracle reproduces it bit for bit). Writes the candidates in u-space and mapped into the box (the criterion's input). pop >= 4.
+ * dgp_de_select: pop_i <- candidate_i where sum_k cand_val[i, k] < pop_val[i] (first != 0: take every candidate, initial evaluation).
+ * dgp_box_from_u: x = lw + (up - lw) / (1 + exp(u)) for n rows.
+ * dgp_adam_box_step: one tf.optimizers.Adam(lr, beta1, beta2, epsilon) step on u [n, d] from dx = d criterion / d x [n, d]
+ *   (dx/du = -(up - lw) e^u / (1 + e^u)^2), t counts from 1; writes the new x [n, d]. n > 1 runs n searches side by side. */
+int dgp_de_propose(dgp_ctx* ctx, const double* pop_u, int64_t pop, int d, const double* lw, const double* up, uint64_t seed,
+                   int64_t generation, double weight, double crossover, double* cand_u, double* cand_x);
+int dgp_de_select(dgp_ctx* ctx, double* pop_u, double* pop_val, const double* cand_u, const double* cand_val, int64_t pop, int d,
+                  int ncol, int first);
+int dgp_box_from_u(dgp_ctx* ctx, const double* u, const double* lw, const double* up, int64_t n, int d, double* x);
+int dgp_adam_box_step(dgp_ctx* ctx, double* u, double* m_state, double* v_state, const double* dx, const double* lw,
+                      const double* up, int64_t n, int d, int64_t t, double lr, double beta1, double beta2, double epsilon, double* x);
+
 /* DGP_Base.predict_f / predict_y + DGP.predict mixture moments (models/dgp.py:66-77,113-124,362-366; also
  * Infill_criteria.py:39-41, EHVI.py:112-119): mean [N, D_L], var [N, D_L]; add_lik_var != 0 adds sigma_n^2 (predict_y). */
 int dgp_predict_moments(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, int64_t N, int64_t S,

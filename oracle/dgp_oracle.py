@@ -668,6 +668,80 @@ def philox_normal(seed: int, layer: int, S: int, N: int, D: int, n_offset: int =
 
 
 # --------------------------------------------------------------------------------------
+# acquisition search (reference Infill_criteria.py:61-87): differential evolution, then Adam, on u with
+# x = lw + (up - lw) / (1 + exp(u))
+# --------------------------------------------------------------------------------------
+def box_from_u(u, lw, up):
+    return lw + (up - lw) / (1.0 + np.exp(u))
+
+
+def de_choices(seed: int, generation: int, pop: int, d: int):
+    """Random choices of one generation, the word layout of csrc/acq.cuh: Philox key = seed, counter = (member, generation,
+    slot, 0xDE). Slot 0 -> partners a, b, c (distinct, != member: w_k mod (pop-1-k), then skipping the excluded indices in
+    ascending order) and the forced dimension w3 mod d; slot 1 + j // 4, word j % 4 -> uniform (w + 0.5) / 2^32 of dimension j.
+    Returns (a, b, c, forced) int arrays [pop] and uniforms [pop, d]."""
+    i = np.arange(pop, dtype=np.uint32)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    w = philox4x32_10(i, np.uint32(generation), np.uint32(0), np.uint32(0xDE), k0, k1)
+
+    def skip(v, excl):
+        v = v.copy()
+        for e in excl:            # ascending per member
+            v = v + (v >= e)
+        return v
+
+    ii = np.arange(pop)
+    a = skip((w[0] % np.uint32(pop - 1)).astype(np.int64), [ii])
+    lo, hi = np.minimum(ii, a), np.maximum(ii, a)
+    b = skip((w[1] % np.uint32(pop - 2)).astype(np.int64), [lo, hi])
+    e = np.sort(np.stack([ii, a, b], 1), axis=1)
+    c = skip((w[2] % np.uint32(pop - 3)).astype(np.int64), [e[:, 0], e[:, 1], e[:, 2]])
+    forced = (w[3] % np.uint32(d)).astype(np.int64)
+    uni = np.empty((pop, d))
+    for j in range(d):
+        r = philox4x32_10(i, np.uint32(generation), np.uint32(1 + j // 4), np.uint32(0xDE), k0, k1)
+        uni[:, j] = (r[j % 4].astype(np.float64) + 0.5) / 4294967296.0
+    return a, b, c, forced, uni
+
+
+def de_minimize(objective, lw, up, pop_u0, iterations: int, seed: int, weight: float = 0.5, crossover: float = 0.9):
+    """tfp.optimizer.differential_evolution_minimize restated ("rand/1/bin", TFP defaults weight 0.5 / crossover 0.9; TFP itself
+    is not in this image -- published algorithm: Storn & Price 1997, TFP API docs): every generation builds one candidate per
+    member, pop[a] + weight (pop[b] - pop[c]) on the crossed-over dimensions, evaluates the whole candidate population at once and
+    keeps the strictly better of (member, candidate). objective(x [pop, d], generation) -> [pop] values; generation 0 is the
+    evaluation of the initial population. Returns (population_u, values)."""
+    lw, up = np.asarray(lw, dtype=np.float64), np.asarray(up, dtype=np.float64)
+    pop_u = np.array(pop_u0, dtype=np.float64)
+    pop, d = pop_u.shape
+    vals = np.asarray(objective(box_from_u(pop_u, lw, up), 0), dtype=np.float64).reshape(pop)
+    for g in range(1, iterations + 1):
+        a, b, c, forced, uni = de_choices(seed, g, pop, d)
+        mutant = pop_u[a] + weight * (pop_u[b] - pop_u[c])
+        take = uni < crossover
+        take[np.arange(pop), forced] = True
+        cand = np.where(take, mutant, pop_u)
+        cv = np.asarray(objective(box_from_u(cand, lw, up), g), dtype=np.float64).reshape(pop)
+        better = cv < vals
+        pop_u[better] = cand[better]
+        vals[better] = cv[better]
+    return pop_u, vals
+
+
+def adam_box_minimize(value_and_grad, lw, up, u0, iterations: int, lr=0.01, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+    """tf.optimizers.Adam on u (Infill_criteria.py:72-86); value_and_grad(u, step) -> (value, d value / d u) with the gradient
+    taken by autograd through x = lw + (up - lw) / (1 + exp(u)). Returns (u, last value)."""
+    u = np.array(u0, dtype=np.float64)
+    m, v = np.zeros_like(u), np.zeros_like(u)
+    val = None
+    for t in range(1, iterations + 1):
+        val, g = value_and_grad(u, t - 1)
+        m = beta_1 * m + (1.0 - beta_1) * g
+        v = beta_2 * v + (1.0 - beta_2) * g * g
+        u = u - lr * np.sqrt(1.0 - beta_2 ** t) / (1.0 - beta_1 ** t) * m / (np.sqrt(v) + epsilon)
+    return u, val
+
+
+# --------------------------------------------------------------------------------------
 # synthetic benchmark inputs (SURVEY §8d) shared by tests and bench.py's cpu_baseline leg
 # --------------------------------------------------------------------------------------
 def synthetic_problem(D0, num_units, M, N, seed_shift=0, lik_var=0.1, ls_scale=1.0):

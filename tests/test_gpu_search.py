@@ -1,0 +1,123 @@
+"""Acquisition search on the device (reference Infill_criteria.py:61-87): differential evolution and Adam on the
+sigmoid-reparameterised candidate, against the oracle's numpy restatement driven by the same Philox choices and draws."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dgp_oracle as O
+from tests.helpers import both_models, rel_err
+
+pytestmark = pytest.mark.gpu
+GOLDEN = 0x9E3779B97F4A7C15
+
+
+def _seeds(model, n):
+    """The next n seeds the model's draw sequence will hand out."""
+    return [(model.seed + GOLDEN * (model._draw + k)) & 0xFFFFFFFFFFFFFFFF for k in range(n)]
+
+
+def _oracle_neg_ei(om, x, S, seed, y_min):
+    zs = [torch.as_tensor(O.philox_normal(seed, l, S, x.shape[0], layer.D_out)) for l, layer in enumerate(om.layers)]
+    _, Fm, Fv = O.propagate(om.layers, x, S, zs)
+    return O.ei_analytic(Fm[-1], Fv[-1], y_min)
+
+
+@pytest.mark.parametrize("pop,d", [(4, 1), (12, 3), (301, 6)])
+def test_de_generation_matches_oracle_choices(pop, d):
+    import dgp_toolbox_b200 as D
+    ctx = D._lib.get_context(0)
+    rng = np.random.default_rng(pop)
+    pop_u = rng.standard_normal((pop, d))
+    lw, up = -1.0 - rng.random(d), 1.0 + rng.random(d)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    pu, lwt, upt = t(pop_u), t(lw), t(up)
+    cu, cx = torch.empty_like(pu), torch.empty_like(pu)
+    for gen in (1, 2, 77):
+        ctx.call("dgp_de_propose", D._lib.ptr(pu), pop, d, D._lib.ptr(lwt), D._lib.ptr(upt), 2 ** 63 + 5, gen, 0.5, 0.9,
+                 D._lib.ptr(cu), D._lib.ptr(cx))
+        a, b, c, forced, uni = O.de_choices(2 ** 63 + 5, gen, pop, d)
+        take = uni < 0.9
+        take[np.arange(pop), forced] = True
+        want = np.where(take, pop_u[a] + 0.5 * (pop_u[b] - pop_u[c]), pop_u)
+        got = cu.cpu().numpy()
+        assert np.array_equal(got == pop_u, ~take | (want == pop_u))          # the same dimensions crossed over
+        assert np.max(np.abs(got - want)) <= 1e-15 * max(1.0, np.max(np.abs(want)))
+        assert rel_err(cx, O.box_from_u(want, lw, up)) < 1e-14
+
+
+def test_de_search_on_dgp_ei_matches_oracle():
+    """Six generations of the whole loop (propose -> dgp_ei on the candidate population with fresh draws -> select) against the
+    oracle's de_minimize fed with the oracle's EI on the same Philox draws: same survivors, same values."""
+    import dgp_toolbox_b200 as D
+    from dgp_toolbox_b200 import search
+    prob, om, pm = both_models(3, [3], 24, 40, 8)
+    pop, d, S, gens = 12, 3, 8, 6
+    y_min = float(prob["Y"].min())
+    lw, up = np.full(d, -2.0), np.full(d, 2.0)
+    ei = D.EI(y_min, d)
+    seeds = _seeds(pm, gens + 1)
+    pop0 = search.initial_population(d, pop, 1.5, 99, 0)
+    assert float(pop0[0].abs().max()) == 0.0
+    z = O.philox_normal(99, search.DE_INIT_LAYER, 1, pop, d)[0]
+    assert rel_err(pop0[1:], 1.5 * z[1:]) < 1e-14
+    res = search.de_minimize(lambda X, out: ei.run(pm, X, True, S, out=out), lw, up, d, 0, pop, 1.5, gens, seed=4242,
+                             initial_population_u=pop0)
+    pu, vals = O.de_minimize(lambda x, g: _oracle_neg_ei(om, torch.as_tensor(x), S, seeds[g], y_min).numpy().reshape(-1),
+                             lw, up, pop0.cpu().numpy(), gens, 4242)
+    assert rel_err(res["population_u"], pu) < 1e-8
+    assert rel_err(res["values"], vals) < 1e-8
+    assert res["best"] == int(np.argmin(vals)) and res["iterations"] == gens
+    assert rel_err(res["x"], O.box_from_u(pu[np.argmin(vals)], lw, up)) < 1e-8
+
+
+def test_adam_on_box_matches_oracle_autograd():
+    """Adam on u with d(-EI)/dx from dgp_ei_grad and the closed-form dx/du, against the oracle's Adam with autograd through
+    x = lw + (up - lw) / (1 + exp(u)) and the oracle EI; two searches side by side."""
+    import dgp_toolbox_b200 as D
+    from dgp_toolbox_b200 import search
+    prob, om, pm = both_models(3, [3], 24, 40, 8)
+    d, S, steps, n = 3, 8, 5, 2
+    y_min = float(prob["Y"].min())
+    lw, up = np.array([-2.0, -1.5, -1.0]), np.array([2.0, 1.0, 3.0])
+    ei = D.EI(y_min, d)
+    seeds = _seeds(pm, steps)
+    u0 = np.array([[0.3, -0.2, 0.1], [-0.5, 0.4, 0.0]])
+
+    def vg(u, step):
+        ut = torch.as_tensor(u).clone().requires_grad_(True)
+        x = torch.as_tensor(lw) + torch.as_tensor(up - lw) / (1.0 + torch.exp(ut))
+        val = _oracle_neg_ei(om, x, S, seeds[step], y_min).sum()
+        val.backward()
+        return float(val.detach()), ut.grad.numpy()
+
+    u_o, _ = O.adam_box_minimize(vg, lw, up, u0, steps, lr=0.05)
+    out = torch.empty((n, 1), dtype=torch.float64, device="cuda")
+    dx = torch.zeros((n, d), dtype=torch.float64, device="cuda")
+    u, X, val = search.adam_box_minimize(lambda X: ei.run_with_grad(pm, X, S, out=out, dx=dx), lw, up,
+                                         torch.from_numpy(u0).cuda(), steps, lr=0.05)
+    assert rel_err(u, u_o) < 1e-8
+    assert rel_err(X, O.box_from_u(u_o, lw, up)) < 1e-8
+
+
+def test_ei_optimize_de_then_adam_improves_on_a_dense_grid():
+    """EI.optimize('DE+Adam') on a 1-D problem: the optimum it returns is inside the box and (on common draws) at least as good
+    as the best point of a 400-point grid, up to the Monte-Carlo noise of the criterion."""
+    import dgp_toolbox_b200 as D
+    rng = np.random.default_rng(3)
+    X = np.linspace(-1.0, 1.0, 14)[:, None]
+    Y = np.sin(4.0 * X) + 0.3 * X + 0.02 * rng.standard_normal(X.shape)
+    model = D.DGP(X, Y, X.copy(), [D.RBF(lengthscales=[0.4], variance=1.0) for _ in range(2)], [1], D.Gaussian(0.01),
+                  num_samples=8, seed=5)
+    D.DGP_Base.optimize_adam(model, model.data, iterations=300, lr=0.02, messages=10 ** 9)
+    crit = D.EI(float(Y.min()), 1)
+    x_opt = crit.optimize(model, (np.array([-1.0]), np.array([1.0])), popsize_DE=24, iterations_DE=25, iterations_adam=60,
+                          method='DE+Adam', num_samples=64, seed=11)
+    assert x_opt.shape == (1, 1) and -1.0 <= x_opt.item() <= 1.0
+    grid = np.linspace(-1.0, 1.0, 400)[:, None]
+    g = crit.run(model, grid, True, 256, seed=77).cpu().numpy().reshape(-1)
+    at_opt = float(crit.run(model, x_opt.reshape(1, 1), True, 256, seed=77))
+    assert at_opt <= g.min() + 0.05 * abs(g.min()) + 1e-6, (at_opt, g.min(), x_opt.item(), grid[np.argmin(g)])
+    with pytest.raises(NotImplementedError):
+        D.WB2(float(Y.min()), 1).optimize(model, (np.array([-1.0]), np.array([1.0])), method='Adam')
+    xw = D.WB2(float(Y.min()), 1).optimize(model, (np.array([-1.0]), np.array([1.0])), popsize_DE=12, iterations_DE=5, seed=2)
+    assert xw.shape == (1, 1) and -1.0 <= xw.item() <= 1.0

@@ -186,3 +186,32 @@ def test_oracle_natural_gradient_step():
     for (mu, R), l in zip(O.natgrad_step(om, X, Y, zs, 1e-3, [0, 1]), om.layers):
         l.q_mu, l.q_sqrt = mu, R
     assert float(O.elbo(om, X, Y, zs)) > e0 + 100.0
+
+
+def test_oracle_search_restatement_de_and_adam_on_a_quadratic():
+    """The oracle's differential evolution / box-Adam (restating tfp.optimizer.differential_evolution_minimize and
+    tf.optimizers.Adam as Infill_criteria.py:61-87 uses them): partner indices are distinct and never the member itself, one
+    dimension always crosses over, and both stages find the minimum of a separable quadratic inside the box."""
+    for pop, d in [(4, 1), (7, 2), (33, 5)]:
+        for gen in (1, 9):
+            a, b, c, forced, uni = O.de_choices(2 ** 40 + 3, gen, pop, d)
+            ii = np.arange(pop)
+            for v in (a, b, c):
+                assert v.min() >= 0 and v.max() < pop and (v != ii).all()
+            assert (a != b).all() and (a != c).all() and (b != c).all()
+            assert forced.min() >= 0 and forced.max() < d and 0.0 < uni.min() and uni.max() < 1.0
+    lw, up = np.array([-1.0, 0.0]), np.array([2.0, 1.0])
+    target = np.array([0.5, 0.25])
+    rng = np.random.default_rng(0)
+    pop0 = np.r_[np.zeros((1, 2)), 1.5 * rng.standard_normal((19, 2))]
+    pu, vals = O.de_minimize(lambda x, g: ((x - target) ** 2).sum(1), lw, up, pop0, 80, 11)
+    assert np.allclose(O.box_from_u(pu[np.argmin(vals)], lw, up), target, atol=1e-6)
+    assert (np.diff(np.sort(vals)) >= 0).all() and vals.max() < 1e-6      # selection only ever keeps improvements
+
+    def vg(u, step):
+        e = np.exp(u)
+        x = lw + (up - lw) / (1.0 + e)
+        return float(((x - target) ** 2).sum()), 2.0 * (x - target) * (-(up - lw) * e / (1.0 + e) ** 2)
+
+    u, val = O.adam_box_minimize(vg, lw, up, np.zeros(2), 2000, lr=0.01)
+    assert np.allclose(O.box_from_u(u, lw, up), target, atol=1e-3) and val < 1e-5
