@@ -155,7 +155,9 @@ const void* host_src(dgp_ctx* c, const void* p, size_t bytes) {
 struct LayerFork {   // fork the ctx's stream into per-layer side streams for a loop over layers, join afterwards
   dgp_ctx* c; cudaStream_t main; int n; bool active = false;
   LayerFork(dgp_ctx* ctx, int nlayers) : c(ctx), main(ctx->stream), n(nlayers < dgp_ctx::kAux ? nlayers : dgp_ctx::kAux) {
-    if (c->dry || nlayers < 2 || !c->parallel_layers) return;
+    // while profiling everything stays on one stream: an event pair around a launch that shares the SMs with launches of other
+    // streams would time the sharing, not the kernel
+    if (c->dry || nlayers < 2 || !c->parallel_layers || c->profiling) return;
     if (!c->ev_fork) {
       if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) return;
       for (int i = 0; i < dgp_ctx::kAux; ++i) {
