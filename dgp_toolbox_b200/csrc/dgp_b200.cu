@@ -313,7 +313,6 @@ int check_layer(dgp_ctx* c, const dgp_layer_desc& L) {
     return DGP_ERR_ARG;
   }
   if (round_up(L.M, kTileM) > 768) { c->err = "M > 768 is not supported by the single-CTA Cholesky"; return DGP_ERR_UNSUPPORTED; }
-  if (L.white) { c->err = "white=True layers are not implemented (reference default is white=False, dgp.py:248)"; return DGP_ERR_UNSUPPORTED; }
   if (L.kernel_kind < 0 || L.kernel_kind > 2) { c->err = "kernel_kind must be 0 (SquaredExponential), 1 (Matern32) or 2 (Matern52)"; return DGP_ERR_UNSUPPORTED; }
   if (L.mean_kind < 0 || L.mean_kind > 2) { c->err = "mean_kind must be 0 (Zero), 1 (Identity) or 2 (Linear)"; return DGP_ERR_ARG; }
   if (L.mean_kind == 1 && L.D_in != L.D_out) { c->err = "Identity mean function needs D_in == D_out"; return DGP_ERR_ARG; }
@@ -340,6 +339,7 @@ struct LayerWs {
   int NP = 0, fcfg = -1;   // fcfg: index into the fused configurations, -1 = not available
   // V-form of the conditional (forward-only calls): C_d = q_sqrt_d^T Lu^-T [D][Mp][Mp] and beta = Lu^-1 q_mu [Mp][32]
   bool vform = false;
+  bool white = false;   // whitened representation (utils/layers.py:246,254-255,296-303): C_d = q_sqrt_d^T, beta = q_mu, KL against N(0, I)
   double *Cmat = nullptr, *betaP = nullptr;
   // V-form adjoint: C_d^T side by side, L^T, accumulators over the chunks (G1 = tril(dV V^T), DCt = [tril(V dT_d^T)]_d, dbeta = V Gm)
   // and scratch of the once-per-step re-parameterisation back to (q_mu, q_sqrt, Ku)
@@ -403,7 +403,7 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
     const dgp_layer_desc& d = model->layers[l];
     RC(check_layer(c, d));
     LayerWs& w = lw[l];
-    w.M = d.M; w.Mp = (int)round_up(d.M, kTileM); w.D_in = d.D_in; w.D_out = d.D_out;
+    w.M = d.M; w.Mp = (int)round_up(d.M, kTileM); w.D_in = d.D_in; w.D_out = d.D_out; w.white = d.white != 0;
     const size_t mm = (size_t)w.Mp * w.Mp;
     w.Ku = walloc(c, mm); w.Knj = walloc(c, mm); w.L = walloc(c, mm); w.Linv = walloc(c, mm); w.LinvT = walloc(c, mm);
     w.RpT = walloc(c, mm * w.D_out); w.Rcat = walloc(c, mm * w.D_out); w.qmuP = walloc(c, (size_t)w.Mp * 32);
@@ -420,10 +420,14 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
     if (w.Mp > maxMp) maxMp = w.Mp;
     hargs[l] = CholArgs{w.Ku, w.L, nullptr, nullptr, w.Mp, c->d_info};   // inverse: tri_inv_kernel
     w.fcfg = c->use_fused ? pick_fused_cfg(w.Mp, w.D_in, w.D_out) : -1;
+    if (w.white && w.fcfg < 0) {
+      c->err = "white=True layers run on the fused conditional kernel only (dgp_set_fused(1), and a layer shape it supports)";
+      return DGP_ERR_UNSUPPORTED;
+    }
     if (w.fcfg >= 0) {
       const int BM = kFusedChoices[w.fcfg].BM;
       const int nb = w.Mp / BM, kpb = BM / kPanelK;
-      w.vform = (level == PREP_FWD && c->use_vform && c->vform_forward_calls) || (level == PREP_GRAD && c->use_vform_grad && vform_grad_ok);
+      w.vform = w.white || (level == PREP_FWD && c->use_vform && c->vform_forward_calls) || (level == PREP_GRAD && c->use_vform_grad && vform_grad_ok);
       w.NP = ((w.vform ? 1 : 2) + w.D_out) * kpb * nb * (nb + 1) / 2;
       if (w.vform) { w.Cmat = walloc(c, mm * w.D_out); w.betaP = walloc(c, (size_t)w.Mp * 32); }
       if (w.vform && level == PREP_GRAD) {
@@ -475,7 +479,10 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
     if (w.fcfg < 0) continue;
     const dgp_layer_desc& d = model->layers[l];
     const int BM = kFusedChoices[w.fcfg].BM;
-    if (w.vform) {
+    if (w.white) {   // whitened: q(v) is given in the basis the solve already works in
+      w.Cmat = w.RpT;
+      w.betaP = w.qmuP;
+    } else if (w.vform) {
       GemmArgs g = gargs(w.RpT, w.Mp, w.LinvT, w.Mp, w.Cmat, w.Mp, w.Mp, w.Mp, w.Mp);   // C_d = q_sqrt_d^T Lu^-T (upper x upper)
       g.a_tri = 2; g.batch = w.D_out; g.sA = (long)w.Mp * w.Mp; g.sB = 0; g.sC = (long)w.Mp * w.Mp;
       RC(gemm(c, g, false));
@@ -506,6 +513,10 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
       forkC.use(l);
       LayerWs& w = lw[l];
       const int Mp = w.Mp, D = w.D_out;
+      if (w.white) {   // KL(q(v) || N(0, I)) needs no product with Ku
+        LAUNCH(kl_white_kernel, 1, 1024, 0, w.Rcat, w.qmuP, w.M, Mp, D, w.kl);
+        continue;
+      }
       GemmArgs g = gargs(w.LinvT, Mp, w.Linv, Mp, w.Kinv, Mp, Mp, Mp, Mp);   // Kinv = Linv^T Linv
       g.a_tri = 2;
       RC(gemm(c, g, false));
@@ -1096,22 +1107,27 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
           const long nct = (long)D * mm;
           LAUNCH(tril_scale_kernel, (unsigned)((mm + 255) / 256), 256, 0, w.G1, Mp, (long)Mp, 1, 1.0);
           LAUNCH(tril_scale_kernel, (unsigned)((nct + 255) / 256), 256, 0, w.DCt, Mp, (long)D * Mp, D, 1.0);
-          GemmArgs g = gargs(w.LinvT, Mp, w.dbeta, 32, w.dqmu2, 32, Mp, 32, Mp);              // dq_mu = Lu^-T dbeta
-          g.a_tri = 2;
-          RC(gemm(c, g, false));
-          g = gargs(w.LinvT, Mp, w.DCt, (long)D * Mp, w.dRcat, (long)D * Mp, Mp, D * Mp, Mp);   // dq_sqrt_d = tril(Lu^-T dC_d^T)
-          g.a_tri = 2;
-          RC(gemm(c, g, false));
-          // dLu^-1 = tril(G1 Lu^T + sum_d dC_d^T q_sqrt_d^T + dbeta q_mu^T)
+          GemmArgs g;
+          if (!w.white) {
+            g = gargs(w.LinvT, Mp, w.dbeta, 32, w.dqmu2, 32, Mp, 32, Mp);              // dq_mu = Lu^-T dbeta
+            g.a_tri = 2;
+            RC(gemm(c, g, false));
+            g = gargs(w.LinvT, Mp, w.DCt, (long)D * Mp, w.dRcat, (long)D * Mp, Mp, D * Mp, Mp);   // dq_sqrt_d = tril(Lu^-T dC_d^T)
+            g.a_tri = 2;
+            RC(gemm(c, g, false));
+          }
+          // dLu^-1 = tril(G1 Lu^T + sum_d dC_d^T q_sqrt_d^T + dbeta q_mu^T); whitened: C_d and beta do not involve Lu, G1 term only
           g = gargs(w.G1, Mp, w.L, Mp, w.dLinv, Mp, Mp, Mp, Mp);
           RC(gemm(c, g, true));
-          g = gargs(w.DCt, (long)D * Mp, w.RpT, Mp, w.dLinv, Mp, Mp, Mp, D * Mp);
-          g.beta = 1.0;
-          g.splitk = D >= 16 ? 16 : (D >= 2 ? D : 1); g.part = w.part_small;
-          RC(gemm(c, g, false));
-          g = gargs(w.dbeta, 32, w.qmuP, 32, w.dLinv, Mp, Mp, Mp, 32);
-          g.beta = 1.0;
-          RC(gemm(c, g, true));
+          if (!w.white) {
+            g = gargs(w.DCt, (long)D * Mp, w.RpT, Mp, w.dLinv, Mp, Mp, Mp, D * Mp);
+            g.beta = 1.0;
+            g.splitk = D >= 16 ? 16 : (D >= 2 ? D : 1); g.part = w.part_small;
+            RC(gemm(c, g, false));
+            g = gargs(w.dbeta, 32, w.qmuP, 32, w.dLinv, Mp, Mp, Mp, 32);
+            g.beta = 1.0;
+            RC(gemm(c, g, true));
+          }
           LAUNCH(tril_scale_kernel, (unsigned)((mm + 255) / 256), 256, 0, w.dLinv, Mp, (long)Mp, 1, 1.0);
           // Lu^-1 = X is a function of Ku = Lu Lu^T: dX = -Phi(X dKu X^T) X, hence (Phi is self-adjoint)
           //   dKu = -X^T sym(Phi(Xbar X^T)) X,  Xbar = dLu^-1,  Phi = lower triangle with halved diagonal
@@ -1126,12 +1142,14 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
           RC(gemm(c, g, false));
         }
         LAUNCH(dku_assemble_kernel, (unsigned)((mm + 255) / 256), 256, 0, w.dKu, w.Kinv, w.KSK, w.alpha, w.Knj, w.M, w.Mp, w.D_out,
-               o.kl_weight, 1);
+               w.white ? 0.0 : o.kl_weight, 1);
         LAUNCH(kuu_bwd_kernel, w.M, 128, 0, w.dKu, d.Z, d.lengthscales, d.variance, w.M, w.Mp, w.D_in, w.dZk, w.kuu_part, d.kernel_kind);
         LAUNCH(reduce_partials_kernel, w.D_in + 1, 256, 0, w.kuu_part, (long)w.M, w.D_in + 1, w.kuu_red, 0);
         FinalizeArgs f;
         memset(&f, 0, sizeof(f));
-        f.Gd = w.vform ? w.dRcat : w.dR; f.gd_cat = w.vform ? 1 : 0; f.KR = w.KRcat; f.Rcat = w.Rcat; f.dqmu = w.vform ? w.dqmu2 : w.dqmu; f.alpha = w.alpha; f.H = w.H; f.dZk = w.dZk;
+        f.Gd = w.white ? w.DCt : (w.vform ? w.dRcat : w.dR); f.gd_cat = w.vform ? 1 : 0; f.KR = w.KRcat; f.Rcat = w.Rcat;
+        f.dqmu = w.white ? w.dbeta : (w.vform ? w.dqmu2 : w.dqmu); f.alpha = w.alpha; f.H = w.H; f.dZk = w.dZk;
+        f.white = w.white ? 1 : 0; f.qmuP = w.qmuP;
         f.rbf_red = w.rbf_red; f.kuu_red = w.kuu_red; f.sgv = w.sgv; f.Z = d.Z; f.ls = d.lengthscales;
         f.M = w.M; f.Mp = w.Mp; f.D_in = w.D_in; f.D_out = w.D_out; f.klw = o.kl_weight;
         f.dZ = out + offs[l].dZ; f.dls = out + offs[l].dlengthscales; f.dvar = out + offs[l].dvariance;

@@ -42,6 +42,20 @@ __global__ void __launch_bounds__(1024) kl_kernel(const double* __restrict__ L, 
   if (threadIdx.x == 0) kl[0] = r - 0.5 * (double)D * (double)M;
 }
 
+// Whitened layer: KL(N(q_mu, R R^T) || N(0, I)) = -0.5 D M - sum log|R_ii| + 0.5 |R|_F^2 + 0.5 |q_mu|_F^2   (layers.py:296-303)
+__global__ void __launch_bounds__(1024) kl_white_kernel(const double* __restrict__ Rcat, const double* __restrict__ qmuP, int M, int Mp,
+                                                        int D, double* __restrict__ kl) {
+  __shared__ double red[32];
+  double s = 0.0;
+  const long nR = (long)D * Mp * Mp;
+  for (long i = threadIdx.x; i < nR; i += blockDim.x) { double v = Rcat[i]; s = fma(0.5 * v, v, s); }
+  for (long i = threadIdx.x; i < (long)Mp * 32; i += blockDim.x) s = fma(0.5 * qmuP[i], qmuP[i], s);
+  for (int i = threadIdx.x; i < M; i += blockDim.x)
+    for (int d = 0; d < D; ++d) { double r = Rcat[(long)i * D * Mp + (long)d * Mp + i]; s -= 0.5 * log(r * r); }
+  double r = block_sum(s, red);
+  if (threadIdx.x == 0) kl[0] = r - 0.5 * (double)D * (double)M;
+}
+
 // dKu = dKu_data - klw * (0.5 D Kinv - 0.5 Kinv Ssum Kinv - 0.5 alpha alpha^T), zero on the padding (in place)
 __global__ void dku_assemble_kernel(double* __restrict__ dKu, const double* __restrict__ Kinv, const double* __restrict__ KSK,
                                     const double* __restrict__ alpha, const double* __restrict__ Knj, int M, int Mp, int D,
@@ -52,8 +66,10 @@ __global__ void dku_assemble_kernel(double* __restrict__ dKu, const double* __re
   double v = 0.0;
   if (i < M && j < M) {
     double aa = 0.0;
-    for (int d = 0; d < D; ++d) aa = fma(alpha[i * 32 + d], alpha[j * 32 + d], aa);
-    v = (have_data ? dKu[idx] : 0.0) - klw * (0.5 * D * Kinv[idx] - 0.5 * KSK[idx] - 0.5 * aa);
+    if (klw != 0.0)   // klw == 0: a whitened layer, whose KL does not depend on Ku (Kinv / KSK / alpha are not computed)
+      for (int d = 0; d < D; ++d) aa = fma(alpha[i * 32 + d], alpha[j * 32 + d], aa);
+    v = (have_data ? dKu[idx] : 0.0);
+    if (klw != 0.0) v -= klw * (0.5 * D * Kinv[idx] - 0.5 * KSK[idx] - 0.5 * aa);
   }
   dKu[idx] = v;
 }
@@ -112,6 +128,7 @@ struct FinalizeArgs {
   const double* Z; const double* ls;
   int M, Mp, D_in, D_out;
   double klw;
+  int white; const double* qmuP;   // whitened layer: d KL / d q_sqrt = R - diag(1 / R_ii), d KL / d q_mu = q_mu
   // outputs (unpadded, inside the flat gradient buffer)
   double* dZ; double* dls; double* dvar; double* dq_mu; double* dq_sqrt;
 };
@@ -127,13 +144,13 @@ __global__ void finalize_layer_kernel(FinalizeArgs a) {
     if (j <= i) {
       const long off = ((long)d * a.Mp + i) * a.Mp + j;
       const long offc = (long)i * a.D_out * a.Mp + (long)d * a.Mp + j;
-      v = (a.Gd ? a.Gd[a.gd_cat ? offc : off] : 0.0) - a.klw * (a.KR[offc] - (i == j ? 1.0 / a.Rcat[offc] : 0.0));
+      v = (a.Gd ? a.Gd[a.gd_cat ? offc : off] : 0.0) - a.klw * ((a.white ? a.Rcat[offc] : a.KR[offc]) - (i == j ? 1.0 / a.Rcat[offc] : 0.0));
     }
     a.dq_sqrt[idx] = v;
   }
   if (idx < (long)a.M * a.D_out) {
     int d = (int)(idx % a.D_out), m = (int)(idx / a.D_out);
-    a.dq_mu[idx] = (a.dqmu ? a.dqmu[m * 32 + d] : 0.0) - a.klw * a.alpha[m * 32 + d];
+    a.dq_mu[idx] = (a.dqmu ? a.dqmu[m * 32 + d] : 0.0) - a.klw * (a.white ? a.qmuP[m * 32 + d] : a.alpha[m * 32 + d]);
   }
   if (idx < (long)a.M * a.D_in) {
     int j = (int)(idx % a.D_in), m = (int)(idx / a.D_in);

@@ -63,15 +63,14 @@ class Layer(_Module):
 
 
 class SVGP_Layer(Layer):
-    """dgp_dace/utils/layers.py:180-308 (augmented=False; non-white, the reference default)."""
+    """dgp_dace/utils/layers.py:180-308 (augmented=False). white=True is the whitened representation q(v) = N(q_mu, q_sqrt q_sqrt^T),
+    u = Lu v (:246,254-255,296-303); the reference default is white=False."""
 
     def __init__(self, kern, Z, num_outputs, mean_function, augmented=False, layers=None, white=False,
                  input_prop_dim=None, **kwargs):
         Layer.__init__(self, input_prop_dim)
         if augmented:
             raise NotImplementedError("augmented inducing inputs belong to the MF/MO models (SURVEY §8 f2)")
-        if white:
-            raise NotImplementedError("white=True is not on the accelerated path (reference default is False, dgp.py:248)")
         Z = np.asarray(Z.detach().cpu().numpy() if hasattr(Z, "detach") else Z, dtype=np.float64)
         self.num_inducing = Z.shape[0]
         self.num_outputs = int(num_outputs)
@@ -80,9 +79,12 @@ class SVGP_Layer(Layer):
         self.mean_function = mean_function
         self.feature = InducingPoints(Z)
         self.q_mu = Parameter(np.zeros((self.num_inducing, self.num_outputs)), name="q_mu")
-        # non-white: q(u) initialised to the prior, q_sqrt = chol(K(Z) + jitter I)   (:219-223)
-        _, Lu = self._kuu_chol()
-        self.q_sqrt = Parameter(Lu[None].repeat(self.num_outputs, 1, 1), transform="triangular", name="q_sqrt")
+        if white:      # q(v) = N(0, I)   (:203-206)
+            self.q_sqrt = Parameter(np.tile(np.eye(self.num_inducing)[None], (self.num_outputs, 1, 1)), transform="triangular",
+                                    name="q_sqrt")
+        else:          # q(u) initialised to the prior, q_sqrt = chol(K(Z) + jitter I)   (:219-223)
+            _, Lu = self._kuu_chol()
+            self.q_sqrt = Parameter(Lu[None].repeat(self.num_outputs, 1, 1), transform="triangular", name="q_sqrt")
         self.needs_build_cholesky = True
 
     # ---- descriptor handed to the C ABI (pointers into the Parameter tensors) ----

@@ -775,5 +775,5 @@ def synthetic_problem(D0, num_units, M, N, seed_shift=0, lik_var=0.1, ls_scale=1
 
 def model_from_problem(prob, num_samples) -> OModel:
     layers = [make_layer(l["Z"], l["lengthscales"], l["variance"], l["q_mu"].shape[1], l["mean_kind"], l["mf_W"],
-                         l["mf_b"], False, l["q_mu"], l["q_sqrt"], l.get("kernel", "rbf")) for l in prob["layers"]]
+                         l["mf_b"], bool(l.get("white", False)), l["q_mu"], l["q_sqrt"], l.get("kernel", "rbf")) for l in prob["layers"]]
     return OModel(layers=layers, lik_var=_t(prob["lik_var"]).reshape(()), num_samples=num_samples)

@@ -18,7 +18,7 @@ def product_model_from_problem(prob, num_samples, seed=1234, device=None):
             mf = D.Identity()
         else:
             mf = D.Linear(l["mf_W"], l["mf_b"])
-        layer = D.SVGP_Layer(kern, l["Z"], l["q_mu"].shape[1], mf)
+        layer = D.SVGP_Layer(kern, l["Z"], l["q_mu"].shape[1], mf, white=bool(l.get("white", False)))
         layer.q_mu.assign(l["q_mu"])
         layer.q_sqrt.assign(l["q_sqrt"])
         layers.append(layer)
@@ -44,10 +44,12 @@ def _condition(prob, target=2e3):
     return prob
 
 
-def both_models(D0, num_units, M, N, S, seed_shift=0, lik_var=0.1, condition=True, kernels=None):
+def both_models(D0, num_units, M, N, S, seed_shift=0, lik_var=0.1, condition=True, kernels=None, white=None):
     prob = O.synthetic_problem(D0, num_units, M, N, seed_shift=seed_shift, lik_var=lik_var)
     for l, k in zip(prob["layers"], kernels or []):
         l["kernel"] = k
+    for l, w in zip(prob["layers"], white or []):
+        l["white"] = bool(w)
     if condition:
         prob = _condition(prob)
     om = O.model_from_problem(prob, S)

@@ -310,6 +310,69 @@ def test_matern_kernels_match_oracle(kernels, conditional_path):
     assert rel_err(lp.kern.K(lp.feature.Z.value, prob["X"]), O.kernel_K(lo.Z, X, lo.lengthscales, lo.variance, lo.kernel_kind)) < TOL
 
 
+@pytest.mark.parametrize("white", [[True, True, True], [True, False, True], [False, True, False]])
+@pytest.mark.parametrize("S", [4, 1])
+def test_whitened_layers_match_oracle(white, S):
+    """white=True layers (utils/layers.py:246,254-255,296-303): q(v) = N(q_mu, q_sqrt q_sqrt^T) with u = Lu v, so the
+    conditional stops after the first triangular solve and the KL is taken against N(0, I). Chain, layer methods, ELBO, every
+    gradient (the V-form adjoint with C_d = q_sqrt_d^T, beta = q_mu), EI input gradient; mixed with non-white layers."""
+    import dgp_toolbox_b200 as D
+    prob, om, pm = both_models(3, [3, 2], 40, 45, S, white=white)
+    assert [l.white for l in om.layers] == white and [l.white for l in pm.layers] == white
+    zs = oracle_zs(om, 45, S, 8)
+    X, Y = torch.as_tensor(prob["X"]), torch.as_tensor(prob["Y"])
+    Fs_o, Fm_o, Fv_o = O.propagate(om.layers, X, S, zs)
+    Fs, Fm, Fv = pm.propagate(prob["X"], S=S, zs=zs)
+    for l in range(3):
+        assert rel_err(Fm[l], Fm_o[l]) < TOL and rel_err(Fv[l], Fv_o[l], scale=1.0) < TOL and rel_err(Fs[l], Fs_o[l]) < TOL
+    for lo, lp in zip(om.layers, pm.layers):
+        Xl = torch.as_tensor(np.random.default_rng(1).standard_normal((17, lo.D_in)))
+        m_o, v_o = O.conditional_ND(lo, Xl)
+        m, v = lp.conditional_ND(Xl)
+        assert rel_err(m, m_o) < TOL and rel_err(v, v_o, scale=1.0) < TOL
+        assert rel_err(lp.KL(), O.layer_KL(lo)) < TOL
+    val_o, g_o = O.elbo_and_grads(om, X, Y, zs)
+    val, g = pm.ELBO_and_grads((prob["X"], prob["Y"]), zs=zs)
+    assert abs(float(val) - float(val_o)) <= TOL * abs(float(val_o))
+    for k, go in g_o.items():
+        assert rel_err(g[k].reshape(go.shape), go) < TOL, k
+    assert abs(float(pm.ELBO((prob["X"], prob["Y"]), zs=zs)) - float(val_o)) <= TOL * abs(float(val_o))
+    Xg = X.clone().requires_grad_(True)
+    _, Fm2, Fv2 = O.propagate(om.layers, Xg, S, zs)
+    y_min = float(prob["Y"].min())
+    O.ei_analytic(Fm2[-1], Fv2[-1], y_min).sum().backward()
+    _, dx = D.EI(y_min, 3).run_with_grad(pm, prob["X"], num_samples=S, zs=zs)
+    assert rel_err(dx, Xg.grad) < 1e-8
+
+
+def test_whitened_dgp_constructor_and_training_step():
+    """DGP(..., white=True) (models/dgp.py:248-252): q_sqrt starts at the identity, the initial ELBO equals the oracle's, an Adam
+    run raises it, and the unfused debug pipeline refuses whitened layers instead of computing the non-white formulas."""
+    import dgp_toolbox_b200 as D
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-1, 1, (60, 2))
+    Y = np.sin(3 * X[:, :1]) * np.cos(2 * X[:, 1:]) + 0.05 * rng.standard_normal((60, 1))
+    Z = X[:20].copy()
+    model = D.DGP(X, Y, Z, [D.RBF(lengthscales=[0.7, 0.7], variance=1.0) for _ in range(2)], [2], D.Gaussian(0.1), num_samples=4,
+                  seed=1, white=True)
+    om = O.make_dgp(X, Y, Z, [(np.array([0.7, 0.7]), 1.0) for _ in range(2)], [2], lik_var=0.1, num_samples=4, white=True)
+    for l in model.layers:
+        assert torch.equal(l.q_sqrt.value, torch.eye(20, dtype=torch.float64, device="cuda")[None].repeat(l.num_outputs, 1, 1))
+    zs = oracle_zs(om, 60, 4, 3)
+    val_o = O.elbo(om, torch.as_tensor(X), torch.as_tensor(Y), zs)
+    assert abs(float(model.ELBO((X, Y), zs=zs)) - float(val_o)) <= TOL * abs(float(val_o))
+    before = float(model.ELBO((X, Y), seed=123))
+    D.DGP_Base.optimize_adam(model, model.data, iterations=150, lr=0.01, messages=10 ** 9)
+    assert float(model.ELBO((X, Y), seed=123)) > before + 50.0
+    ctx = D._lib.get_context(0)
+    ctx.set_fused(False)
+    try:
+        with pytest.raises(D._lib.DGPError, match="white"):
+            model.ELBO((X, Y), seed=1)
+    finally:
+        ctx.set_fused(True)
+
+
 def test_wb2_wb2s_ev_match_oracle():
     """The other moment-based criteria of Infill_criteria.py (WB2, WB2S, EV analytic / Monte-Carlo, EV.run_with_IC)."""
     import dgp_toolbox_b200 as D

@@ -111,7 +111,7 @@ def test_empty_inputs_and_error_behaviour():
     with pytest.raises(NotImplementedError):
         model.propagate(np.zeros((4, 8)), full_cov=True)
     with pytest.raises(NotImplementedError):
-        D.SVGP_Layer(D.RBF(lengthscales=[1.0]), np.zeros((4, 1)), 1, D.Zero(), white=True)
+        D.SVGP_Layer(D.RBF(lengthscales=[1.0]), np.zeros((4, 1)), 1, D.Zero(), augmented=True)
     with pytest.raises(ValueError):           # Y width does not match the last layer
         model.elbo_flat((np.zeros((4, 8)), np.zeros((4, 3))))
     with pytest.raises(ValueError):           # X width does not match the first layer
