@@ -21,7 +21,7 @@ typedef struct dgp_ctx dgp_ctx;
 /* One SVGP layer = the state of reference SVGP_Layer (dgp_dace/utils/layers.py:181-224). */
 typedef struct {
   int32_t D_in, D_out, M;
-  int32_t white;              /* reference `white` flag; only 0 (the reference default, dgp.py:248) is implemented */
+  int32_t white;              /* reference `white` flag (utils/layers.py:246,254-255,296-303): 1 = q(v) whitened, u = Lu v; 0 = default */
   int32_t mean_kind;          /* 0 Zero, 1 Identity, 2 Linear (utils/layer_initializations.py:27,42,52) */
   int32_t kernel_kind;        /* 0 SquaredExponential / RBF, 1 Matern32, 2 Matern52 (ARD; the kernels BO/SO_BO.py:190-197,237-244 offers) */
   const double* Z;            /* [M, D_in]   feature.Z */
