@@ -32,6 +32,15 @@ class ShardedELBO:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
         return flat
 
+    def train_adam_step(self, X_local, Y_local, n_offset, params, state, t, lr=0.01, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
+                        scale=1.0, seed=None):
+        """One data-parallel training iteration: sharded ELBO gradient, the allreduce, then the same dgp_adam_step on every
+        rank (the reduced buffer is bit-identical across ranks, so the replicated parameters stay in lockstep without a
+        broadcast). `params` / `state` as in DGP_Base._adam_state; t counts from 1. Returns the reduced flat buffer."""
+        flat = self.step(X_local, Y_local, n_offset, scale=scale, want_grad=True, seed=seed)
+        self.model._adam_step(params, flat, state, t, lr, beta_1, beta_2, epsilon)
+        return flat
+
     def step_host(self, X_host: torch.Tensor, Y_host: torch.Tensor, n_offset, scale=1.0, want_grad=True, seed=None):
         """Pinned HOST shard in, HOST result out: H2D copies, the step, the allreduce and the D2H copy of the result."""
         dev = self.model.device

@@ -186,6 +186,32 @@ def test_graph_replay_is_bit_exact():
         ctx.set_graph(False)
 
 
+def test_sharded_training_step_equals_the_unsharded_one():
+    """ShardedELBO.train_adam_step on the two halves of a minibatch in turn (what two ranks do before their allreduce), summed
+    by hand, followed by dgp_adam_step == one unsharded training iteration: same parameters to rounding of the sum order."""
+    import dgp_toolbox_b200 as D
+    from dgp_toolbox_b200.distributed import ShardedELBO, shard_bounds
+    ma, X, Y = _bo_model(seed=3)
+    mb, _, _ = _bo_model(seed=3)
+    Xd, Yd = ma.data
+    pa, pb = ma.trainable_parameters, mb.trainable_parameters
+    sa, sb = ma._adam_state(pa), mb._adam_state(pb)
+    for t in range(1, 4):
+        flat = ma.elbo_flat((Xd, Yd), seed=100 + t)
+        ma._adam_step(pa, flat, sa, t, 0.02, 0.9, 0.999, 1e-7)
+        parts = []
+        for r in range(2):
+            lo, hi = shard_bounds(Xd.shape[0], r, 2)
+            parts.append(mb.elbo_flat((Xd[lo:hi].contiguous(), Yd[lo:hi].contiguous()), kl_weight=0.5, seed=100 + t, n_offset=lo))
+        mb._adam_step(pb, parts[0] + parts[1], sb, t, 0.02, 0.9, 0.999, 1e-7)
+    for a, b in zip(pa, pb):
+        assert float((a.value - b.value).abs().max()) <= 1e-9 * max(1.0, float(a.value.abs().max()))
+    one = ShardedELBO(mb)                      # world 1: the wrapper is the plain step + dgp_adam_step
+    before = [p.value.clone() for p in pb]
+    one.train_adam_step(Xd, Yd, 0, pb, sb, 4, lr=0.02, seed=7)
+    assert any(not torch.equal(p.value, q) for p, q in zip(pb, before))
+
+
 def test_train_adam_equals_stepwise_calls_and_graph_replay():
     """dgp_train_adam (loop in the library) == elbo_flat + dgp_adam_step called step by step with the model's seed sequence,
     bit for bit, with and without graph replay."""
