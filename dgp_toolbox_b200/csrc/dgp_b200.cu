@@ -31,6 +31,8 @@ struct dgp_ctx {
   bool dry = false;
   size_t ws_limit = (size_t)24 << 30;   // chunks of the minibatch are sized to stay under this
   int num_sms = 148;
+  int splitk_max = 64;                  // most splits of a contraction over the point-samples (sizes the split-K scratch)
+  int lower_waves = 9;                  // CTA waves a lower-only NT contraction is cut into (pick_splitk)
   bool chol_configured = false;
   int* d_info = nullptr;                // Cholesky failure flag
   // CUDA-graph replay of the ELBO+gradient step (dgp_set_graph): the step's launch sequence depends only on shapes, pointers
@@ -262,7 +264,7 @@ constexpr size_t kSplitkPartDoubles = (size_t)96 << 20;   // 768 MB of split-K p
 int pick_splitk(dgp_ctx* c, const GemmArgs& g, bool nt) {
   const GemmPlan p = gemm_plan(g, nt, c->num_sms);
   const size_t out_doubles = (size_t)g.batch * g.M * g.N;
-  long smax = 64;
+  long smax = c->splitk_max;
   if ((size_t)smax * out_doubles > kSplitkPartDoubles) smax = (long)(kSplitkPartDoubles / out_doubles);
   const long ktiles = g.K / 16;
   if (smax > ktiles / 8) smax = ktiles / 8;
@@ -280,7 +282,7 @@ int pick_splitk(dgp_ctx* c, const GemmArgs& g, bool nt) {
   if (nt && g.c_lower && p.BM == 64 && gemm_small_bk32(g, nt)) {
     // lower-only NT product: its diagonal tiles run the 36-of-64-unit path and finish in ~0.56 of the time of the others, so
     // the CTAs are not uniform and many short CTAs pack better than whole waves of long ones (measured: 11 -> 33 splits, -10%)
-    long s = (9 * (long)p.slots + p.tiles - 1) / p.tiles;
+    long s = (c->lower_waves * (long)p.slots + p.tiles - 1) / p.tiles;
     if (s > smax) s = smax;
     return (int)(s < 1 ? 1 : s);
   }
@@ -831,17 +833,18 @@ struct RunOpts {
 
 // Split-K scratch of the adjoint: four regions (the parameter contractions of a layer run side by side), sized for the widest
 // layer so that the same layout serves every layer.
-void splitk_regions(const std::vector<LayerWs>& lw, size_t room[4]) {
+void splitk_regions(const dgp_ctx* c, const std::vector<LayerWs>& lw, size_t room[4]) {
   size_t Mp = 0, D = 1;
   for (const LayerWs& w : lw) {
     if ((size_t)w.Mp > Mp) Mp = w.Mp;
     if ((size_t)w.D_out > D) D = w.D_out;
   }
-  room[0] = 64 * Mp * Mp; room[1] = 64 * D * Mp * Mp; room[2] = 64 * Mp * 32; room[3] = 64 * Mp * 32;
+  const size_t sm = (size_t)c->splitk_max;
+  room[0] = sm * Mp * Mp; room[1] = sm * D * Mp * Mp; room[2] = sm * Mp * 32; room[3] = sm * Mp * 32;
 }
-size_t max_splitk_part(const std::vector<LayerWs>& lw) {
+size_t max_splitk_part(const dgp_ctx* c, const std::vector<LayerWs>& lw) {
   size_t room[4];
-  splitk_regions(lw, room);
+  splitk_regions(c, lw, room);
   const size_t m = room[0] + room[1] + room[2] + room[3] + 1024;
   return m < kSplitkPartDoubles ? m : kSplitkPartDoubles + ((size_t)32 * 1024 * 1024 / 8);
 }
@@ -879,7 +882,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
   if (!adj) pp_doubles += (size_t)maxD * maxMp;                      // shared T
   if (adj) pp_doubles += 2 * (size_t)maxD + 32 + 1 + 32 + 2 * 32;    // Gm, GvT, GmPad, gq, XaugPad, dX ping-pong
   if (adj && nl > 1) pp_doubles += 3 * (size_t)maxMp + 2 * (size_t)maxD + 32 + 1 + 32;   // second set of adjoint temporaries
-  size_t fixed = base_used + (adj ? max_splitk_part(lw) * sizeof(double) : 0) + ((size_t)8 << 20);
+  size_t fixed = base_used + (adj ? max_splitk_part(c, lw) * sizeof(double) : 0) + ((size_t)8 << 20);
   long Nc_max;
   {
     size_t avail = c->ws_limit > fixed ? c->ws_limit - fixed : 0;
@@ -932,7 +935,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
     dXa = walloc(c, (size_t)Ppmax * 32);
     dXb = walloc(c, (size_t)Ppmax * 32);
     rbf_part = walloc(c, (size_t)nbmax * 2 * 32);   // one row of partials per 64-column block of rbf_bwd_kernel
-    skcap = max_splitk_part(lw);
+    skcap = max_splitk_part(c, lw);
     skpart = walloc(c, skcap);
     if (nl > 1) {   // second set: layer l's parameter contractions read theirs while layer l-1's data path fills the other
       tmp1.t0 = walloc(c, (size_t)maxMp * Ppmax);
@@ -948,7 +951,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
   ParamScratch ps;
   ps.part = skpart; ps.cap = skcap;
   if (adj) {
-    splitk_regions(lw, ps.room);
+    splitk_regions(c, lw, ps.room);
     ps.off[0] = 0; ps.off[1] = ps.room[0]; ps.off[2] = ps.off[1] + ps.room[1]; ps.off[3] = ps.off[2] + ps.room[2];
     ps.fixed = ps.off[3] + ps.room[3] <= skcap;
   }
@@ -1308,6 +1311,8 @@ int dgp_ctx_create(int device, void* cuda_stream, dgp_ctx** out) {
   if (getenv("DGP_B200_UNFUSED")) c->use_fused = false;
   c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
   if (cudaMalloc(&c->d_info, sizeof(int)) != cudaSuccess) { delete c; return DGP_ERR_CUDA; }
+  if (const char* e = getenv("DGP_B200_SPLITK_MAX")) { const int v = atoi(e); if (v >= 1 && v <= 512) c->splitk_max = v; }
+  if (const char* e = getenv("DGP_B200_LOWER_WAVES")) { const int v = atoi(e); if (v >= 1 && v <= 256) c->lower_waves = v; }
   const char* lim = getenv("DGP_B200_WS_GB");
   if (lim && atof(lim) > 0.0) c->ws_limit = (size_t)(atof(lim) * (double)((size_t)1 << 30));
   *out = c;
