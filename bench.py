@@ -252,7 +252,12 @@ def main():
                          # to this run's launch size
                          traffic=(1.1754e9 / 65536) * nb * S if prof["fused_fwd"][0] > 0 and args.config == "c2" else None)
     k_bwd = kernel_entry("dgp::gemm_kernel (FP64 DMMA adjoint contractions: dV = sum_d C_d^T dT_d, Lu^-T dV, tril(dV V^T), "
-                         "tril(V diag(2Gv_d) T_d^T), V Gm, Gbar [X,1])", ["gemm_bwd_data", "gemm_bwd_param"], 2 * f_fwd)
+                         "tril(V diag(2Gv_d) T_d^T), V Gm, Gbar [X,1])", ["gemm_bwd_data", "gemm_bwd_param"], 2 * f_fwd,
+                         # ncu --set full capture profiles/r01h_top_kernels_ncu.txt, largest launch of the engine
+                         # (tril(V diag(2Gv_d) T_d^T) over one 262 144-point-sample chunk, 4352 CTAs): dram read 19.39 GB + write
+                         # 0.09 GB against 4.8 GB of operands (64x64 tiles re-read V / T_d through an L2 that the K-chunks in
+                         # flight overflow; 1.9 TB/s, not the bound -- DESIGN.md section 8.3)
+                         traffic=19.394378e9 + 0.091298e9 if args.config == "c2" and nb == 16384 else None)
     main, other = (k_bwd, k_fwd) if k_bwd["kernel_ms_per_step"] >= k_fwd["kernel_ms_per_step"] else (k_fwd, k_bwd)
     flops_rank_step = f_step * nb * S
     roofline = dict(main)
