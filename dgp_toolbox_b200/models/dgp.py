@@ -335,35 +335,34 @@ class DGP_Base(_Module):
         state = self._adam_state(params)
         self._adam_loop(data, params, state, 1, iterations, lr, beta_1, beta_2, epsilon, messages)
 
-    def natgrad_step(self, data, gamma, variational_params, scale=1.0, seed=None, zs=None):
+    def natgrad_step(self, data, gamma, variational_params, scale=1.0, seed=None, zs=None, out=None):
         """One GPflow NaturalGradient(gamma).minimize(-ELBO, var_list=[(q_mu, q_sqrt), ...]) step with the default XiNat
         parameterisation (dgp.py:188,218,312,343): theta <- theta - gamma * d(-ELBO)/d eta with natural parameters
-        theta = (S^-1 mu, -S^-1/2) and expectation parameters eta = (mu, S + mu mu^T), S = q_sqrt q_sqrt^T, per output column.
-        The ELBO gradient comes from one dgp_elbo_grad call; the O(D_out M^3) re-parameterisation is host-side glue
-        (torch.linalg on the device), like the optimiser math of the reference."""
-        flat = self.elbo_flat(data, want_grad=True, scale=scale, seed=seed, zs=zs)
+        theta = (S^-1 mu, -S^-1/2) and expectation parameters eta = (mu, S + mu mu^T), S = R R^T, R = q_sqrt, per output column.
+        With G_mu, G_R the loss gradients, dS = R^-T P R^-1 (Cholesky adjoint, P = sym(Phi(R^T G_R))) and d_eta = (G_mu - 2 dS mu,
+        dS), the update collapses to
+            S_new^-1 = S^-1 + 2 gamma dS = R^-T (I + 2 gamma P) R^-1,      mu_new = mu - gamma S_new G_mu,
+        so with the reverse Cholesky I + 2 gamma P = U U^T (U upper) the new factor is q_sqrt_new = R U^-T (lower times lower, positive
+        diagonal: the Cholesky factor of S_new) and mu_new = mu - gamma q_sqrt_new q_sqrt_new^T G_mu -- one triangular product, one
+        M x M Cholesky and one triangular solve per output, no explicit inverse of S. The ELBO gradient comes from one dgp_elbo_grad
+        call; this O(D_out M^3) re-parameterisation is host-side glue (batched torch.linalg on the device), like the optimiser
+        math of the reference. Checked against the oracle, which takes d/d eta by autograd through the expectation parameters."""
+        flat = self.elbo_flat(data, want_grad=True, scale=scale, seed=seed, zs=zs, out=out)
         grads = self.unpack_grads(flat)
         for q_mu, q_sqrt in variational_params:
             mu = q_mu.value                                    # [M, D]
             R = torch.tril(q_sqrt.value)                       # [D, M, M]
             Gmu = -grads[q_mu]                                 # d loss / d mu, loss = -ELBO
             GR = -torch.tril(grads[q_sqrt])                    # d loss / d R
-            # Cholesky adjoint: dS = R^-T sym(Phi(R^T GR)) R^-1, Phi = lower triangle with halved diagonal
-            P = torch.tril(R.transpose(1, 2) @ GR)
-            P = P - 0.5 * torch.diag_embed(torch.diagonal(P, dim1=1, dim2=2))
-            P = 0.5 * (P + P.transpose(1, 2))
-            tmp = torch.linalg.solve_triangular(R.transpose(1, 2), P, upper=True)                  # R^-T P
-            dS = torch.linalg.solve_triangular(R.transpose(1, 2), tmp.transpose(1, 2), upper=True).transpose(1, 2)  # (R^-T tmp^T)^T = tmp R^-1
-            mu_c = mu.T.unsqueeze(-1)                          # [D, M, 1]
-            d_eta1 = Gmu.T.unsqueeze(-1) - 2.0 * dS @ mu_c     # eta2 = S + mu mu^T  =>  S = eta2 - eta1 eta1^T
-            d_eta2 = dS
-            Sinv = torch.cholesky_inverse(R)                   # S^-1
-            theta1 = Sinv @ mu_c - gamma * d_eta1
-            theta2 = -0.5 * Sinv - gamma * d_eta2
-            S_new = torch.linalg.inv(-2.0 * theta2)
-            S_new = 0.5 * (S_new + S_new.transpose(1, 2))
-            q_mu.assign((S_new @ theta1).squeeze(-1).T.contiguous())
-            q_sqrt.assign(torch.linalg.cholesky(S_new))
+            T = torch.tril(R.transpose(1, 2) @ GR)
+            # I + 2 gamma sym(Phi(T)),  Phi = lower triangle with halved diagonal
+            B = gamma * (T + T.transpose(1, 2) - torch.diag_embed(torch.diagonal(T, dim1=1, dim2=2)))
+            B.diagonal(dim1=1, dim2=2).add_(1.0)
+            U = torch.linalg.cholesky_ex(B.flip(-1, -2)).L.flip(-1, -2)          # reverse Cholesky: B = U U^T, U upper
+            C = torch.linalg.solve_triangular(U.transpose(1, 2), R, upper=False, left=False)   # C U^T = R
+            w = C.transpose(1, 2) @ Gmu.T.unsqueeze(-1)        # [D, M, 1]
+            q_mu.assign(mu - gamma * (C @ w).squeeze(-1).T)
+            q_sqrt.assign(torch.tril(C))
         return flat[0] - flat[1]
 
     def optimize_nat_adam(self, data, iterations1=100, iterations2=5000, lr_adam=0.01, lr_gamma=0.01, beta_1=0.9, beta_2=0.999,
@@ -378,14 +377,26 @@ class DGP_Base(_Module):
         params = self.trainable_parameters
         state = self._adam_state(params)
         self._adam_loop(data, params, state, 1, iterations1, lr_adam, beta_1, beta_2, epsilon, messages)
-        t = iterations1
-        for step in range(iterations2):
-            flat = self.elbo_flat(data, want_grad=True)
-            t += 1
-            self._adam_step(params, flat, state, t, lr_adam, beta_1, beta_2, epsilon)
-            self.natgrad_step(data, lr_gamma, variational_params)
-            if step % messages == 0:
-                print(f"ELBO: {(flat[0] - flat[1]).item()}")
+        ctx = _lib.get_context(self.device)
+        X = _lib.as_device(data[0], self.device)
+        data = (X, _lib.as_device(data[1], self.device))      # one device copy and one result buffer: stable addresses
+        buf = torch.empty(self.grad_layout()[0], dtype=torch.float64, device=X.device)
+        auto_graph = not ctx.graph and X.shape[0] * self.num_samples <= 32768
+        if auto_graph:
+            ctx.set_graph(True)
+        try:
+            t = iterations1
+            for step in range(iterations2):
+                flat = self.elbo_flat(data, want_grad=True, out=buf)
+                t += 1
+                self._adam_step(params, flat, state, t, lr_adam, beta_1, beta_2, epsilon)
+                if step % messages == 0:
+                    print(f"ELBO: {(flat[0] - flat[1]).item()}")
+                self.natgrad_step(data, lr_gamma, variational_params, out=buf)
+            ctx.check()
+        finally:
+            if auto_graph:
+                ctx.set_graph(False)
 
     def number_parameters(self, trainable=True):
         """dgp.py:348-360."""
