@@ -159,6 +159,9 @@ class Context:
         """grad: False (A-form adjoint), True (V-form adjoint for calls with >= 32768 point-samples), "always"."""
         lib.dgp_set_vform(self.h, 1 if forward else 0, 2 if grad == "always" else (1 if grad else 0))
 
+    def set_parallel_layers(self, on: bool):
+        lib.dgp_set_parallel_layers(self.h, 1 if on else 0)
+
     def set_fused(self, on: bool):
         lib.dgp_set_fused(self.h, 1 if on else 0)
 

@@ -44,4 +44,25 @@ for i in range(3):
 torch.cuda.synchronize()
 print(f"config-3 ELBO+grad, 2048 points x 64 samples: {(time.time() - t0) / 3 * 1e3:.1f} ms/step, {2048 * 64 * 3 / (time.time() - t0):.0f} point-samples/s")
 ctx.check()
+
+# launch-bound sizes: the side-stream overlap (deferred prep products, parameter contractions in flight behind the next layer's
+# data path) and graph replay must not change a single bit from step to step
+for name, (D0, units, M, S, N) in {"c1": (2, [2], 50, 10, 1000), "bo": (1, [1, 1], 25, 10, 50), "c2_small": (8, [8, 8, 8], 256, 32, 256)}.items():
+    ms = synthetic.model_from_problem(synthetic.synthetic_problem(D0, units, M, 8, ls_scale=0.3), S)
+    Xs, Ys = synthetic.minibatch(D0, N, 0)
+    Xs, Ys = torch.from_numpy(Xs).cuda(), torch.from_numpy(Ys).cuda()
+    buf = torch.empty(ms.grad_layout()[0], dtype=torch.float64, device="cuda")
+    ctx.set_parallel_layers(False)
+    serial = ms.elbo_flat((Xs, Ys), seed=5).clone()
+    ctx.set_parallel_layers(True)
+    for graph in (False, True):
+        ctx.set_graph(graph)
+        bad = 0
+        for i in range(400):
+            out = ms.elbo_flat((Xs, Ys), seed=5, out=buf)
+            if i % 50 == 49:
+                bad += int(not torch.equal(out, serial))
+        ctx.set_graph(False)
+        assert bad == 0, (name, graph, bad)
+    print(f"{name}: 2 x 400 steps (direct / graph replay) bitwise equal to the single-stream result")
 print("stress ok")
