@@ -132,11 +132,32 @@ def _moment_criterion(kind, model, x, y, num_samples, zs, seed, with_x=False):
     return out
 
 
+def _moment_criterion_grad(kind, model, x, y, num_samples, zs, seed, out=None, dx=None):
+    """(criterion [N, 1], d sum(criterion) / dx [N, d]) for kind 1 (WB2) / 2 (EV) on predict_y mixture moments: one dgp_acq_grad
+    call (criterion adjoints, then the data path of the adjoint chain)."""
+    if getattr(model, "name", None) != 'dgp':
+        raise NotImplementedError("only model.name == 'dgp' is on the accelerated path")
+    X = model._check_X(_lib.as_device(x, model.device))
+    N, D = X.shape[0], model.layers[-1].num_outputs
+    if D != 1:
+        raise ValueError("the criterion expects a single-output model")
+    if out is None:
+        out = torch.empty((N, D), dtype=torch.float64, device=X.device)
+    if dx is None:
+        dx = torch.zeros_like(X)
+    if N == 0:
+        return out, dx
+    m, keep = model._model_desc()
+    zt, zp = model._zs(zs, num_samples, N)
+    _lib.get_context(X.device).call("dgp_acq_grad", C.byref(m), kind, _lib.ptr(X), N, num_samples, zp, model._next_seed(seed), 0,
+                                    _scalar(y), _lib.ptr(out), _lib.ptr(dx))
+    return out, dx
+
+
 def _optimize_de(crit, run, model, bounds, popsize_DE, popstd_DE, iterations_DE, method, seed):
-    """The DE stage of the reference's `optimize` for the moment-based criteria (Infill_criteria.py:142-168,207-233); their Adam
-    stage needs d criterion / dx, which the accelerated path provides for EI only."""
+    """The DE stage of the reference's `optimize` for the moment-based criteria (Infill_criteria.py:142-168,207-233)."""
     if method != 'DE':
-        raise NotImplementedError("method 'Adam' / 'DE+Adam' needs the input gradient, available for EI only (dgp_ei_grad)")
+        raise NotImplementedError("method 'Adam' / 'DE+Adam' needs the input gradient, which WB2S does not have on this path")
     lw = np.broadcast_to(np.asarray(bounds[0], dtype=np.float64).reshape(-1), (crit.d,)).copy()
     up = np.broadcast_to(np.asarray(bounds[1], dtype=np.float64).reshape(-1), (crit.d,)).copy()
     with search.GraphScope(model.device):
@@ -170,10 +191,32 @@ class WB2(Infill_criteria):
     def loss(self, model, x):
         return self.run(model, x)
 
+    def run_with_grad(self, model, x, num_samples=500, zs=None, seed=None, out=None, dx=None):
+        """(WB2 [N, 1], d sum(WB2) / dx [N, d]) -- what tape.gradient(loss, x) gives the reference's Adam stage (:160-165)."""
+        return _moment_criterion_grad(1, model, x, self.y_min, num_samples, zs, seed, out, dx)
+
     def optimize(self, model, bounds, popsize_DE=300, popstd_DE=1.5, iterations_DE=400, init_adam=None, iterations_adam=1000,
                  method='DE', seed=None):
-        """Infill_criteria.py:142-168 (DE stage)."""
-        return _optimize_de(self, lambda X: self.run(model, X), model, bounds, popsize_DE, popstd_DE, iterations_DE, method, seed)
+        """Infill_criteria.py:142-168: 'DE', 'Adam' or 'DE+Adam' like EI.optimize."""
+        if method not in ('DE', 'Adam', 'DE+Adam'):
+            raise ValueError(f"unknown method {method!r}")
+        lw = np.broadcast_to(np.asarray(bounds[0], dtype=np.float64).reshape(-1), (self.d,)).copy()
+        up = np.broadcast_to(np.asarray(bounds[1], dtype=np.float64).reshape(-1), (self.d,)).copy()
+        if method in ('DE', 'DE+Adam'):
+            _optimize_de(self, lambda X: self.run(model, X), model, bounds, popsize_DE, popstd_DE, iterations_DE, 'DE', seed)
+        if method in ('Adam', 'DE+Adam'):
+            with search.GraphScope(model.device):
+                if init_adam is None:
+                    init_adam = np.zeros(self.d) if self.x_opt is None else self.x_opt
+                init_adam = np.asarray(init_adam, dtype=np.float64).reshape(self.d)
+                u0 = _lib.as_device(np.log((up - init_adam + 1e-3) / (init_adam - lw + 1e-3)).reshape(1, self.d), model.device)
+                out = torch.empty((1, 1), dtype=torch.float64, device=u0.device)
+                dx = torch.zeros_like(u0)
+                u, X, val = search.adam_box_minimize(lambda X: self.run_with_grad(model, X, out=out, dx=dx), lw, up, u0,
+                                                     iterations_adam, lr=0.01)
+                self.x_opt = X.cpu().numpy().reshape(self.d, 1)
+                self.IC_optimized = val.clone()
+        return self.x_opt
 
 
 class WB2S(Infill_criteria):
@@ -206,6 +249,10 @@ class EV_one_constraint(Infill_criteria):
         self.zero_c = zero_c
         self.d = d
         self.IC_optimized = None
+
+    def run_with_grad(self, model, x, num_samples=500, zs=None, seed=None, out=None, dx=None):
+        """(EV [N, 1], d sum(EV) / dx [N, d]) for the analytic expected violation (constrained searches differentiate it)."""
+        return _moment_criterion_grad(2, model, x, self.zero_c, num_samples, zs, seed, out, dx)
 
     def run(self, model, x, analytic=True, num_samples=100, zs=None, seed=None):
         if analytic:

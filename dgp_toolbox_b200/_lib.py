@@ -86,6 +86,7 @@ _SIG = {
                                       _vp, _vp]),
     "dgp_ei": (C.c_int, [_vp, C.POINTER(ModelDesc), _vp, _i64, _i64, C.POINTER(_vp), _u64, _i64, _d, _i, _vp]),
     "dgp_ei_grad": (C.c_int, [_vp, C.POINTER(ModelDesc), _vp, _i64, _i64, C.POINTER(_vp), _u64, _i64, _d, _vp, _vp]),
+    "dgp_acq_grad": (C.c_int, [_vp, C.POINTER(ModelDesc), _i, _vp, _i64, _i64, C.POINTER(_vp), _u64, _i64, _d, _vp, _vp]),
     "dgp_acq_moments": (C.c_int, [_vp, _i, _vp, _vp, _i64, _d, _vp, _i, _vp]),
     "dgp_de_propose": (C.c_int, [_vp, _vp, _i64, _i, _vp, _vp, _u64, _i64, _d, _d, _vp, _vp]),
     "dgp_de_select": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i]),

@@ -44,9 +44,15 @@ __global__ void ei_analytic_kernel(const double* __restrict__ mean, const double
 // sigma = sqrt(vbar), u = (y_min - mbar)/sigma:  d(-EI)/d mbar = Phi(u),  d(-EI)/d vbar = -phi(u) / (2 sigma), hence
 //   Gm[s] = Phi(u)/S - phi(u) (mu_s - mbar) / (sigma S),   Gv[s] = -phi(u) / (2 sigma S).
 // One thread per candidate point; chunk-local p = s * Nc + n. Gm / GvT / GmPad / gq must be zero-filled beforehand.
+// kind selects the criterion c(mbar, vbar) (and its partial derivatives) evaluated on the mixture moments; lik_var != null adds
+// sigma_n^2 to vbar (predict_y moments, what WB2 / EV use; EI.run works on predict_f moments):
+//   0  -EI(y)          u = (y - mbar)/sigma:  dc/dmbar = Phi(u),      dc/dvbar = -phi(u) / (2 sigma)
+//   1  -(EI(y) - mbar) (WB2):                 dc/dmbar = Phi(u) + 1,  dc/dvbar as above
+//   2  EV(y) = (mbar - y) Phi(t) + sigma phi(t), t = (mbar - y)/sigma:  dc/dmbar = Phi(t),  dc/dvbar = phi(t) / (2 sigma)
+// Per sample: Gm[s] = dc/dmbar / S + 2 dc/dvbar (mu_s - mbar) / S,  Gv[s] = dc/dvbar / S.
 __global__ void ei_upstream_kernel(const double* __restrict__ Fmean, const double* __restrict__ Fvar, long Nc, long S, long Pp, int D,
                                    double y_min, double* __restrict__ neg_ei, double* __restrict__ Gm, double* __restrict__ GvT,
-                                   double* __restrict__ GmPad, double* __restrict__ gq) {
+                                   double* __restrict__ GmPad, double* __restrict__ gq, int kind, const double* __restrict__ lik_var) {
   const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= Nc) return;
   for (int d = 0; d < D; ++d) {
@@ -56,13 +62,25 @@ __global__ void ei_upstream_kernel(const double* __restrict__ Fmean, const doubl
       sm += m;
       sq += v + m * m;
     }
-    const double mbar = sm / (double)S, vbar = sq / (double)S - mbar * mbar, sig = sqrt(vbar);
-    const double u = (y_min - mbar) / sig, cdf = norm_cdf(u), pdf = norm_pdf(u);
-    neg_ei[n * D + d] = -((y_min - mbar) * cdf + vbar * (pdf / sig));
-    const double gv = -pdf / (2.0 * sig * (double)S);
+    const double mbar = sm / (double)S, vbar = sq / (double)S - mbar * mbar + (lik_var ? lik_var[0] : 0.0), sig = sqrt(vbar);
+    double val, dm, dv;
+    if (kind == 2) {
+      const double t = (mbar - y_min) / sig, cdf = norm_cdf(t), pdf = norm_pdf(t);
+      val = (mbar - y_min) * cdf + vbar * (pdf / sig);
+      dm = cdf;
+      dv = pdf / (2.0 * sig);
+    } else {
+      const double u = (y_min - mbar) / sig, cdf = norm_cdf(u), pdf = norm_pdf(u);
+      val = -((y_min - mbar) * cdf + vbar * (pdf / sig));
+      dm = cdf;
+      dv = -pdf / (2.0 * sig);
+      if (kind == 1) { val += mbar; dm += 1.0; }
+    }
+    neg_ei[n * D + d] = val;
+    const double gv = dv / (double)S;
     for (long s = 0; s < S; ++s) {
       const long p = s * Nc + n;
-      const double gm = cdf / (double)S - pdf * (Fmean[p * D + d] - mbar) / (sig * (double)S);
+      const double gm = dm / (double)S + 2.0 * dv * (Fmean[p * D + d] - mbar) / (double)S;
       Gm[p * D + d] = gm;
       GmPad[p * 32 + d] = gm;
       GvT[(long)d * Pp + p] = gv;

@@ -829,6 +829,7 @@ struct RunOpts {
   double* ei = nullptr; double y_min = 0.0; int ei_analytic = 1; // -EI [N][D_L]
   bool need_last_sample = false;
   double* dx = nullptr;                                          // d sum(-EI) / dX [N][D0] (analytic EI only)
+  int acq_kind = 0, acq_add_lik = 0;                             // criterion of the o.dx path (ei_upstream_kernel)
 };
 
 // Split-K scratch of the adjoint: four regions (the parameter contractions of a layer run side by side), sized for the widest
@@ -1073,7 +1074,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
       CK(cudaMemsetAsync(up.GmPad, 0, (size_t)Pp * 32 * sizeof(double), c->stream));
       CK(cudaMemsetAsync(up.gq, 0, (size_t)Pp * sizeof(double), c->stream));
       LAUNCH(ei_upstream_kernel, (unsigned)((Nc + 127) / 128), 128, 0, clL.Fmean, clL.Fvar, Nc, S, Pp, DL, o.y_min, o.ei + n0 * DL,
-             up.Gm, up.GvT, up.GmPad, up.gq);
+             up.Gm, up.GvT, up.GmPad, up.gq, o.acq_kind, o.acq_add_lik ? model->lik_variance : nullptr);
       up.part = lik_part; up.nblocks = nb;
       RC(run_backward(false));
     }
@@ -1196,7 +1197,7 @@ std::vector<unsigned char> graph_key(dgp_ctx* c, const dgp_model_desc* model, co
   key_put(k, X); key_put(k, N); key_put(k, S); key_put(k, n_offset);
   key_put(k, o.want_grad); key_put(k, o.want_elbo); key_put(k, o.Y); key_put(k, o.Dy); key_put(k, o.scale); key_put(k, o.kl_weight);
   key_put(k, o.out_flat); key_put(k, o.pm); key_put(k, o.pv); key_put(k, o.add_lik); key_put(k, o.ei); key_put(k, o.y_min);
-  key_put(k, o.ei_analytic); key_put(k, o.need_last_sample); key_put(k, o.dx);
+  key_put(k, o.ei_analytic); key_put(k, o.need_last_sample); key_put(k, o.dx); key_put(k, o.acq_kind); key_put(k, o.acq_add_lik);
   key_put(k, c->use_fused); key_put(k, c->use_vform); key_put(k, c->use_vform_grad); key_put(k, c->vform_forward_calls);
   key_put(k, c->vform_grad_min_ps); key_put(k, c->share_first_layer); key_put(k, c->parallel_layers); key_put(k, c->ws_limit);
   return k;
@@ -1661,6 +1662,16 @@ int dgp_ei_grad(dgp_ctx* c, const dgp_model_desc* model, const double* X, int64_
   if (!c || !model || !X || !neg_ei || !d_neg_ei_dX) return DGP_ERR_ARG;
   RunOpts o;
   o.io.zs = zs_host; o.ei = neg_ei; o.y_min = y_min; o.ei_analytic = 1; o.dx = d_neg_ei_dX;
+  return run_model_planned(c, model, X, N, S, seed, n_offset, o);
+}
+
+int dgp_acq_grad(dgp_ctx* c, const dgp_model_desc* model, int kind, const double* X, int64_t N, int64_t S,
+                 const double* const* zs_host, uint64_t seed, int64_t n_offset, double y, double* value, double* d_value_dX) {
+  if (!c || !model || !X || !value || !d_value_dX || kind < 0 || kind > 2) return DGP_ERR_ARG;
+  if (kind > 0 && !model->lik_variance) { c->err = "lik_variance is null"; return DGP_ERR_ARG; }
+  RunOpts o;
+  o.io.zs = zs_host; o.ei = value; o.y_min = y; o.ei_analytic = 1; o.dx = d_value_dX;
+  o.acq_kind = kind; o.acq_add_lik = kind > 0 ? 1 : 0;
   return run_model_planned(c, model, X, N, S, seed, n_offset, o);
 }
 

@@ -175,6 +175,13 @@ int dgp_train_adam(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, c
                    int n_params, double* m_state, double* v_state, int64_t t0, int64_t steps, double lr, double beta1,
                    double beta2, double epsilon, double* out_flat, double* elbo_trace);
 
+/* Value and input gradient of a moment-based criterion (the gradient the reference's Adam-on-x stage takes with tape.gradient,
+ * Infill_criteria.py:79-84,160-165): kind 0 = -EI on predict_f moments (== dgp_ei_grad), 1 = WB2 = -(EI - mean) and 2 = EV =
+ * (mean - y) Phi + s phi, both on predict_y moments (+ sigma_n^2, Infill_criteria.py:124-133,249-257). value [N, D_L],
+ * d_value_dX [N, D0] = d sum(value) / dX. The adjoint chain runs without the parameter contractions. */
+int dgp_acq_grad(dgp_ctx* ctx, const dgp_model_desc* model, int kind, const double* X, int64_t N, int64_t S,
+                 const double* const* zs_host, uint64_t seed, int64_t n_offset, double y, double* value, double* d_value_dX);
+
 /* ---- acquisition search: the reference's `optimize` methods (Infill_criteria.py:61-87,142-168,207-233,290-316) run
  * tfp.optimizer.differential_evolution_minimize and then tf.optimizers.Adam on u, x = lw + (up - lw) / (1 + exp(u)). The criterion
  * itself is evaluated by the entry points below (dgp_ei, dgp_ei_grad, dgp_predict_moments + dgp_acq_moments); these four keep the

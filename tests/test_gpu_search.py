@@ -118,6 +118,28 @@ def test_ei_optimize_de_then_adam_improves_on_a_dense_grid():
     at_opt = float(crit.run(model, x_opt.reshape(1, 1), True, 256, seed=77))
     assert at_opt <= g.min() + 0.05 * abs(g.min()) + 1e-6, (at_opt, g.min(), x_opt.item(), grid[np.argmin(g)])
     with pytest.raises(NotImplementedError):
-        D.WB2(float(Y.min()), 1).optimize(model, (np.array([-1.0]), np.array([1.0])), method='Adam')
-    xw = D.WB2(float(Y.min()), 1).optimize(model, (np.array([-1.0]), np.array([1.0])), popsize_DE=12, iterations_DE=5, seed=2)
+        D.WB2S(float(Y.min()), 1).optimize(model, (np.array([-1.0]), np.array([1.0])), method='Adam')
+    wb2 = D.WB2(float(Y.min()), 1)
+    xw = wb2.optimize(model, (np.array([-1.0]), np.array([1.0])), popsize_DE=12, iterations_DE=5, iterations_adam=20,
+                      method='DE+Adam', seed=2)
     assert xw.shape == (1, 1) and -1.0 <= xw.item() <= 1.0
+    gw = wb2.run(model, grid, num_samples=256, seed=78).cpu().numpy().reshape(-1)
+    assert float(wb2.run(model, xw.reshape(1, 1), num_samples=256, seed=78)) <= gw.min() + 0.25 * (gw.max() - gw.min())
+
+
+@pytest.mark.parametrize("D0,units,M,N,S", [(4, [4], 48, 60, 8), (3, [2, 3], 30, 25, 1), (2, [], 20, 30, 5)])
+def test_wb2_and_ev_input_gradients_match_oracle_autograd(D0, units, M, N, S):
+    """dgp_acq_grad: WB2 = -(EI - mean) and the analytic expected violation on predict_y moments, value and d/dx, against
+    autograd through the oracle chain (Infill_criteria.py:124-133,249-257; the gradient of the Adam stage, :160-165)."""
+    import dgp_toolbox_b200 as D
+    prob, om, pm = both_models(D0, units, M, N, S)
+    zs = [torch.randn(S, N, l.D_out, dtype=torch.float64, generator=torch.Generator().manual_seed(4 + i)) for i, l in enumerate(om.layers)]
+    y = float(prob["Y"].min()) + 0.1
+    for name, crit, ofun in (("wb2", D.WB2(y, D0), O.wb2), ("ev", D.EV_one_constraint(y, D0), O.ev_analytic)):
+        X = torch.as_tensor(prob["X"]).clone().requires_grad_(True)
+        ym, yv = O.predict_y(om, X, S, zs)
+        val_o = ofun(ym, yv, y)
+        val_o.sum().backward()
+        val, dx = crit.run_with_grad(pm, prob["X"], num_samples=S, zs=zs)
+        assert rel_err(val, val_o.detach()) < 1e-8, name
+        assert rel_err(dx, X.grad) < 1e-8, name
