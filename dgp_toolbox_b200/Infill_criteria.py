@@ -290,6 +290,60 @@ class EV(Infill_criteria):
         return torch.where(ev.max(dim=1, keepdim=True).values > threshold, ev.sum(dim=1, keepdim=True) + 10000.0, ic)
 
 
+def _ev_optimize_with_IC(self, IC, model_Y, model_C, bounds, threshold=0.1, analytic=True, num_samples=100, popsize_DE=300,
+                         popstd_DE=1.5, iterations_DE=400, init_adam=None, iterations_adam=1000, method='DE', seed=None):
+    """Infill_criteria.py:290-316: minimise `run_with_IC` (the criterion where every constraint's expected violation is below
+    `threshold`, sum of violations + 10000 elsewhere) over the box. 'DE' evaluates the whole population per generation; the
+    'Adam' stage differentiates the branch tf.cond takes at the current point: sum_j dEV_j/dx where a violation exceeds the
+    threshold, dIC/dx otherwise (analytic EV; IC needs run_with_grad: EI or WB2). The reference passes the literal 0.1 to the
+    objective regardless of `threshold` (:292); the argument is honoured here."""
+    if method not in ('DE', 'Adam', 'DE+Adam'):
+        raise ValueError(f"unknown method {method!r}")
+    d = self.d
+    lw = np.broadcast_to(np.asarray(bounds[0], dtype=np.float64).reshape(-1), (d,)).copy()
+    up = np.broadcast_to(np.asarray(bounds[1], dtype=np.float64).reshape(-1), (d,)).copy()
+    dev = model_Y.device
+    if getattr(self, "x_opt", None) is None:
+        self.x_opt = None
+    with search.GraphScope(dev):
+        if method in ('DE', 'DE+Adam'):
+            def objective(X, out):
+                v = self.run_with_IC(IC, model_Y, model_C, X, threshold, analytic, num_samples)
+                if out is None:
+                    return v.contiguous()
+                out.copy_(v)
+                return out
+            res = search.de_minimize(objective, lw, up, d, dev, popsize_DE, popstd_DE, iterations_DE, seed=model_Y._next_seed(seed))
+            self.x_opt = res["x"].cpu().numpy().reshape(d, 1)
+            self.de_iterations = res["iterations"]
+            self.IC_optimized = self.run_with_IC(IC, model_Y, model_C, self.x_opt.reshape(1, d), threshold, analytic, num_samples)
+        if method in ('Adam', 'DE+Adam'):
+            if not analytic or not hasattr(IC, "run_with_grad"):
+                raise NotImplementedError("the Adam stage needs the analytic EV and a criterion with run_with_grad (EI, WB2)")
+            if init_adam is None:
+                init_adam = np.zeros(d) if self.x_opt is None else self.x_opt
+            init_adam = np.asarray(init_adam, dtype=np.float64).reshape(d)
+            u0 = _lib.as_device(np.log((up - init_adam + 1e-3) / (init_adam - lw + 1e-3)).reshape(1, d), dev)
+            ones = [EV_one_constraint(self.zero_c[i], d) for i in range(len(model_C))]
+
+            def value_and_grad(X):
+                evs = [c.run_with_grad(m, X) for c, m in zip(ones, model_C)]
+                ev = torch.cat([v for v, _ in evs], 1)
+                ic, dic = IC.run_with_grad(model_Y, X)
+                bad = ev.max(dim=1, keepdim=True).values > threshold
+                val = torch.where(bad, ev.sum(dim=1, keepdim=True) + 10000.0, ic.sum(dim=1, keepdim=True))
+                dx = torch.where(bad, sum(g for _, g in evs), dic)
+                return val, dx.contiguous()
+
+            u, X, val = search.adam_box_minimize(value_and_grad, lw, up, u0, iterations_adam, lr=0.01)
+            self.x_opt = X.cpu().numpy().reshape(d, 1)
+            self.IC_optimized = val.clone()
+    return self.x_opt
+
+
+EV.optimize_with_IC = _ev_optimize_with_IC
+
+
 class PoF(Infill_criteria):
     """Infill_criteria.py:318-345 computes the EI-style terms but never returns them and `run_with_IC` references an undefined
     name: there is no reference behaviour to reproduce."""

@@ -143,3 +143,40 @@ def test_wb2_and_ev_input_gradients_match_oracle_autograd(D0, units, M, N, S):
         val, dx = crit.run_with_grad(pm, prob["X"], num_samples=S, zs=zs)
         assert rel_err(val, val_o.detach()) < 1e-8, name
         assert rel_err(dx, X.grad) < 1e-8, name
+
+
+def _exact_gp_model(X, T, noise, seed):
+    """One SVGP layer with Z = X and q(u) set to the exact GP-regression posterior at the inducing points: the model's
+    predictions are the GP posterior without any training."""
+    import dgp_toolbox_b200 as D
+    kern = D.RBF(lengthscales=[0.4], variance=1.0)
+    model = D.DGP(X, T, X.copy(), [kern], [], D.Gaussian(noise), num_samples=4, seed=seed)
+    K = kern.K(X).cpu().numpy()
+    A = K @ np.linalg.inv(K + noise * np.eye(len(X)))
+    Spost = K - A @ K
+    Spost = 0.5 * (Spost + Spost.T) + 1e-9 * np.eye(len(X))
+    model.layers[0].q_mu.assign(A @ T)
+    model.layers[0].q_sqrt.assign(np.linalg.cholesky(Spost)[None])
+    return model
+
+
+def test_constrained_search_with_expected_violation():
+    """EV.optimize_with_IC (Infill_criteria.py:290-316): EI on the objective model where the constraint model's expected violation
+    stays under the threshold, violation + 10000 elsewhere. The DE stage must land in the feasible part of the box; the Adam
+    stage follows the gradient of the active branch and stays there."""
+    import dgp_toolbox_b200 as D
+    rng = np.random.default_rng(5)
+    X = np.linspace(-1.0, 1.0, 16)[:, None]
+    Y = np.sin(4.0 * X) + 0.3 * X + 0.02 * rng.standard_normal(X.shape)
+    Cc = X + 0.02 * rng.standard_normal(X.shape)            # constraint c(x) = x <= 0: the right half of the box is infeasible
+    mY, mC = _exact_gp_model(X, Y, 1e-3, 5), _exact_gp_model(X, Cc, 1e-3, 6)
+    ev = D.EV([0.0], 1)
+    ei = D.EI(float(Y.min()), 1)
+    grid = np.linspace(-1.0, 1.0, 101)[:, None]
+    vals = ev.run_with_IC(ei, mY, [mC], grid, threshold=0.1, num_samples=64, seed=3).cpu().numpy().reshape(-1)
+    assert (vals[grid[:, 0] > 0.5] > 9000.0).all() and (vals[grid[:, 0] < -0.5] < 1.0).all()
+    x_opt = ev.optimize_with_IC(ei, mY, [mC], (np.array([-1.0]), np.array([1.0])), threshold=0.1, num_samples=64, popsize_DE=24,
+                                iterations_DE=20, iterations_adam=30, method='DE+Adam', seed=9)
+    assert x_opt.shape == (1, 1) and -1.0 <= x_opt.item() <= 0.3
+    at = float(ev.run_with_IC(ei, mY, [mC], x_opt.reshape(1, 1), threshold=0.1, num_samples=256, seed=4))
+    assert at < 1.0 and at <= vals[vals < 9000.0].min() + 0.1 * abs(vals[vals < 9000.0].min()) + 1e-3, (at, x_opt.item())
