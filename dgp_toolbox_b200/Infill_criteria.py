@@ -77,12 +77,14 @@ class EI(Infill_criteria):
         return self.run(model, x, analytic)
 
     def optimize(self, model, bounds, popsize_DE=300, popstd_DE=1.5, iterations_DE=400, init_adam=None, iterations_adam=1000,
-                 method='DE', analytic=True, num_samples=1000, seed=None):
+                 method='DE', analytic=True, num_samples=1000, seed=None, adam_starts=1):
         """Infill_criteria.py:61-87: minimise -EI over the box `bounds = (lw, up)`; 'DE' (differential evolution, population
         popsize_DE around u = 0 with spread popstd_DE, iterations_DE generations, one dgp_ei call per generation), 'Adam'
         (iterations_adam steps of lr 0.01 on u from init_adam, one dgp_ei_grad call per step) or 'DE+Adam'. Sets and returns
         x_opt [d, 1] (numpy, like the reference); IC_optimized is the criterion there. Every evaluation draws fresh samples,
-        as the reference's tf.random.normal does."""
+        as the reference's tf.random.normal does. adam_starts > 1 (an extension; the reference refines one point) starts the
+        Adam stage of 'DE+Adam' from the best `adam_starts` members of the final population side by side -- the same number
+        of launches, one dgp_ei_grad call over adam_starts candidates per step -- and keeps the best end point."""
         lw = np.broadcast_to(np.asarray(bounds[0], dtype=np.float64).reshape(-1), (self.d,)).copy()
         up = np.broadcast_to(np.asarray(bounds[1], dtype=np.float64).reshape(-1), (self.d,)).copy()
         if method not in ('DE', 'Adam', 'DE+Adam'):
@@ -93,6 +95,7 @@ class EI(Infill_criteria):
                 res = search.de_minimize(lambda X, out: self.run(model, X, analytic, num_samples, out=out), lw, up, self.d,
                                          model.device, popsize_DE, popstd_DE, iterations_DE, seed=de_seed)
                 self.x_opt = res["x"].cpu().numpy().reshape(self.d, 1)
+                starts_u = res["population_u"][torch.argsort(res["values"])[:max(1, int(adam_starts))]].contiguous()
                 self.de_iterations = res["iterations"]      # < iterations_DE when the population collapsed (TFP position_tolerance)
                 self.IC_optimized = self.run(model, self.x_opt.reshape(1, self.d), analytic, num_samples)
             if method in ('Adam', 'DE+Adam'):
@@ -102,12 +105,16 @@ class EI(Infill_criteria):
                     init_adam = np.zeros(self.d) if self.x_opt is None else self.x_opt
                 init_adam = np.asarray(init_adam, dtype=np.float64).reshape(self.d)
                 u0 = _lib.as_device(np.log((up - init_adam + 1e-3) / (init_adam - lw + 1e-3)).reshape(1, self.d), model.device)
-                out = torch.empty((1, model.layers[-1].num_outputs), dtype=torch.float64, device=u0.device)
+                if method == 'DE+Adam' and int(adam_starts) > 1:
+                    u0 = starts_u            # the population is already in u-space
+                n = u0.shape[0]
+                out = torch.empty((n, model.layers[-1].num_outputs), dtype=torch.float64, device=u0.device)
                 dx = torch.zeros_like(u0)
                 u, X, val = search.adam_box_minimize(
                     lambda X: self.run_with_grad(model, X, num_samples, out=out, dx=dx), lw, up, u0, iterations_adam, lr=0.01)
-                self.x_opt = X.cpu().numpy().reshape(self.d, 1)
-                self.IC_optimized = val.clone()
+                best = int(torch.argmin(val.sum(dim=1))) if n > 1 else 0
+                self.x_opt = X[best].cpu().numpy().reshape(self.d, 1)
+                self.IC_optimized = val[best:best + 1].clone()
         return self.x_opt
 
 
