@@ -215,3 +215,31 @@ def test_oracle_search_restatement_de_and_adam_on_a_quadratic():
 
     u, val = O.adam_box_minimize(vg, lw, up, np.zeros(2), 2000, lr=0.01)
     assert np.allclose(O.box_from_u(u, lw, up), target, atol=1e-3) and val < 1e-5
+
+
+def test_adam_oracle_first_step_closed_form():
+    """tf.optimizers.Adam's first step is u -= lr * g / (|g| + eps / sqrt(1 - beta_2)) for every variable, with g the gradient
+    w.r.t. the UNCONSTRAINED variable. The oracle takes g by autograd through the bijectors; here it is rebuilt from the
+    constrained-space gradients with the closed-form chain rules the product's kernel uses (softplus: d theta / d u =
+    1 - exp(-(theta - lower)); FillTriangular: lower triangle only) -- the two routes must give the same update."""
+    prob = O.synthetic_problem(3, [2], 12, 20, lik_var=0.3)
+    om = O.model_from_problem(prob, 3)
+    X, Y = torch.as_tensor(prob["X"]), torch.as_tensor(prob["Y"])
+    g0 = torch.Generator().manual_seed(0)
+    zs = [torch.randn(3, 20, l.D_out, dtype=torch.float64, generator=g0) for l in om.layers]
+    lr, b2, eps = 0.01, 0.999, 1e-7
+    _, grads = O.elbo_and_grads(om, X, Y, zs)
+    opt = O.AdamOracle(om, lr=lr, beta_2=b2, epsilon=eps)
+    u_before = {k: v.clone() for k, v in opt.u.items()}
+    opt.step(om, X, Y, zs)
+    for name, theta in om.named_params().items():
+        kind = O.AdamOracle._kind(name)
+        gl = -grads[name]                                            # d(-ELBO) / d theta
+        if kind in ("positive", "positive_shift"):
+            gu = gl * (-torch.expm1(-(theta - (1e-6 if kind == "positive_shift" else 0.0))))
+        elif kind == "triangular":
+            gu = torch.tril(gl)
+        else:
+            gu = gl
+        want = u_before[name] - lr * gu / (gu.abs() + eps / np.sqrt(1.0 - b2))
+        assert torch.allclose(opt.u[name], want, rtol=1e-10, atol=1e-13), name
