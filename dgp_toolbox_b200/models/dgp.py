@@ -293,6 +293,8 @@ class DGP_Base(_Module):
         self._check_XY(X, Y)
         if X.shape[0] == 0:
             raise ValueError("empty minibatch")
+        if steps <= 0:
+            return torch.empty(0, dtype=torch.float64, device=X.device)
         m, keep = self._model_desc()
         arr, keep2 = self._adam_params(params)
         n = int(_lib.lib.dgp_grad_size(C.byref(m)))
