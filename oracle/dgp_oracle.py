@@ -246,6 +246,45 @@ def propagate(layers: Sequence[OLayer], X, S: int, zs: Sequence[torch.Tensor]):
     return Fs, Fmeans, Fvars
 
 
+# ---- full_cov=True branches (not on the accelerated path yet: the oracle states them for the next round) ----
+def conditional_ND_full(layer: OLayer, X):
+    """utils/layers.py:237-278 with full_cov=True: mean [N, D_out], cov [N, N, D_out] = transpose(K(X, X)[None] + A^T SK_d A)."""
+    Ku, Lu = kuu_chol(layer)
+    M = layer.M
+    Kuf = kernel_K(layer.Z, X, layer.lengthscales, layer.variance, layer.kernel_kind)
+    A = torch.linalg.solve_triangular(Lu, Kuf, upper=False)
+    if not layer.white:
+        A = torch.linalg.solve_triangular(Lu.T, A, upper=True)
+    mean = A.T @ layer.q_mu
+    SK = -(torch.eye(M, dtype=DTYPE) if layer.white else Ku)[None] + layer.q_sqrt @ layer.q_sqrt.transpose(1, 2)
+    delta = A.T[None] @ (SK @ A[None])                                            # :265  [D_out, N, N]
+    Kff = kernel_K(X, None, layer.lengthscales, layer.variance, layer.kernel_kind)   # :266
+    return mean + mean_function(layer, X), (Kff[None] + delta).permute(2, 1, 0)       # tf.transpose reverses the axes (:276)
+
+
+def reparameterize_full(mean, var, z):
+    """utils/utils.py:43-52: mean [S,N,D], var [S,N,N,D], z [S,N,D] -> mean + chol(var_sd + jitter I) z_sd per sample and output."""
+    S, N, D = mean.shape
+    v = var.permute(0, 3, 1, 2) + JITTER * torch.eye(N, dtype=DTYPE)
+    f = mean.permute(0, 2, 1) + (torch.linalg.cholesky(v) @ z.permute(0, 2, 1)[..., None])[..., 0]
+    return f.permute(0, 2, 1)
+
+
+def propagate_full_cov(layers: Sequence[OLayer], X, S: int, zs: Sequence[torch.Tensor]):
+    """models/dgp.py:34-63 with full_cov=True: every layer's conditional is evaluated per sample (conditional_SND's map_fn,
+    utils/layers.py:76-79) and sampled with the full N x N covariance. Returns Fs, Fmeans [S,N,D_l], Fvars [S,N,N,D_l]."""
+    F = X[None].expand(S, -1, -1)
+    Fs, Fmeans, Fvars = [], [], []
+    for layer, z in zip(layers, zs):
+        mv = [conditional_ND_full(layer, F[s]) for s in range(S)]
+        mean, var = torch.stack([m for m, _ in mv]), torch.stack([v for _, v in mv])
+        F = reparameterize_full(mean, var, z)
+        Fs.append(F)
+        Fmeans.append(mean)
+        Fvars.append(var)
+    return Fs, Fmeans, Fvars
+
+
 # --------------------------------------------------------------------------------------
 # a8-a11: Gaussian likelihood, ELBO, predict
 # --------------------------------------------------------------------------------------

@@ -243,3 +243,32 @@ def test_adam_oracle_first_step_closed_form():
             gu = gl
         want = u_before[name] - lr * gu / (gu.abs() + eps / np.sqrt(1.0 - b2))
         assert torch.allclose(opt.u[name], want, rtol=1e-10, atol=1e-13), name
+
+
+def test_oracle_full_cov_branches_are_consistent_with_the_diagonal_ones():
+    """full_cov=True restatement (utils/layers.py:264-266, utils/utils.py:43-52): the diagonal of the full
+    covariance is the diagonal-branch variance, the covariance is symmetric and positive semi-definite, one point reduces the
+    full-covariance sample to the diagonal reparameterisation, and whitened / non-whitened layers agree as they do on the diagonal."""
+    prob = O.synthetic_problem(3, [3], 14, 9)
+    om = O.model_from_problem(prob, 2)
+    X = torch.as_tensor(prob["X"])
+    for layer in om.layers:
+        Xl = torch.as_tensor(np.random.default_rng(0).standard_normal((9, layer.D_in)))
+        m_d, v_d = O.conditional_ND(layer, Xl)
+        m_f, v_f = O.conditional_ND_full(layer, Xl)
+        assert v_f.shape == (9, 9, layer.D_out) and torch.allclose(m_f, m_d, rtol=1e-12, atol=1e-12)
+        assert torch.allclose(torch.diagonal(v_f, dim1=0, dim2=1).T, v_d, rtol=1e-10, atol=1e-12)
+        assert torch.allclose(v_f, v_f.transpose(0, 1), rtol=1e-12, atol=1e-13)
+        assert float(torch.linalg.eigvalsh(v_f[:, :, 0]).min()) > -1e-9
+    g = torch.Generator().manual_seed(1)
+    zs = [torch.randn(2, 9, l.D_out, dtype=torch.float64, generator=g) for l in om.layers]
+    Fs, Fm, Fv = O.propagate_full_cov(om.layers, X, 2, zs)
+    assert Fs[-1].shape == (2, 9, 1) and Fv[-1].shape == (2, 9, 9, 1)
+    _, Fm_d, Fv_d = O.propagate(om.layers, X, 2, zs)
+    assert torch.allclose(Fm[0], Fm_d[0], rtol=1e-12, atol=1e-12)                    # first layer: same inputs either way
+    assert torch.allclose(torch.diagonal(Fv[0], dim1=1, dim2=2).permute(0, 2, 1), Fv_d[0], rtol=1e-10, atol=1e-12)
+    one = X[:1]
+    z1 = [z[:, :1] for z in zs]
+    Fs1, _, _ = O.propagate_full_cov(om.layers, one, 2, z1)
+    Fs1_d, _, _ = O.propagate(om.layers, one, 2, z1)
+    assert torch.allclose(Fs1[-1], Fs1_d[-1], rtol=1e-10, atol=1e-12)
