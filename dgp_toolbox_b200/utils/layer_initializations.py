@@ -1,4 +1,5 @@
-"""Layer-list construction, mirroring dgp_dace/utils/layer_initializations.py:24-68 (pure host set-up, numpy)."""
+"""Layer-list construction with the behaviour of dgp_dace/utils/layer_initializations.py:24-68 (pure host set-up, numpy):
+which mean function each hidden layer gets and how the inducing inputs follow the width changes."""
 from __future__ import annotations
 
 import numpy as np
@@ -11,30 +12,37 @@ def _np(x):
     return np.asarray(x.detach().cpu().numpy() if hasattr(x, "detach") else x, dtype=np.float64)
 
 
+def width_change_map(inputs, d_in, d_out):
+    """The fixed [d_in, d_out] linear map between two layer widths, or None when they are equal (Identity mean function,
+    :41-42). Narrowing projects on the leading principal directions of the layer's inputs (:45-47); widening copies the
+    coordinates and pads with zeros (:49-50)."""
+    if d_in == d_out:
+        return None
+    if d_out < d_in:
+        principal = np.linalg.svd(inputs, full_matrices=False)[2]     # rows: right singular vectors
+        return principal[:d_out].T
+    pad = np.zeros((d_in, d_out))
+    pad[np.arange(d_in), np.arange(d_in)] = 1.0
+    return pad
+
+
 def init_layers_linear(X, Y, Z, kernels, num_units, num_outputs=None, mean_function=None, Layer=SVGP_Layer, white=False):
-    """Hidden layers get an Identity mean function when widths match (:41-42), a PCA projection when narrowing (:45-47)
-    or identity-plus-zero-padding when widening (:49-50), both as non-trainable Linear (:52-55); Z (and the running X)
-    are projected with the same W (:59-61). The last layer gets `mean_function` (Zero by default) (:64-67)."""
-    X, Z = _np(X), _np(Z)
-    num_outputs = num_outputs or _np(Y).shape[1]
-    mean_function = gpflow.Zero() if mean_function is None else mean_function
+    """One SVGP layer per kernel. A hidden layer whose width changes gets the non-trainable Linear mean function of
+    width_change_map (:52-55), and the inducing inputs (and the data used for the next projection) are pushed through the same
+    map (:59-61); the last layer gets `mean_function` (Zero by default) and `num_outputs` columns (:64-67)."""
+    running_X, running_Z = _np(X).copy(), _np(Z).copy()
+    widths = [running_X.shape[1], *num_units]
     layers = []
-    dims = [X.shape[1]] + list(num_units)
-    X_running, Z_running = X.copy(), Z.copy()
-    for dim_in, dim_out, kern in zip(dims[:-1], dims[1:], kernels[:-1]):
-        if dim_in == dim_out:
-            mf = gpflow.Identity()
+    for (d_in, d_out), kern in zip(zip(widths[:-1], widths[1:]), kernels[:-1]):   # as many hidden layers as both lists allow
+        W = width_change_map(running_X, d_in, d_out)
+        if W is None:
+            mean = gpflow.Identity()
         else:
-            if dim_in > dim_out:
-                _, _, V = np.linalg.svd(X_running, full_matrices=False)
-                W = V[:dim_out, :].T
-            else:
-                W = np.concatenate([np.eye(dim_in), np.zeros((dim_in, dim_out - dim_in))], 1)
-            mf = gpflow.Linear(W)
-            gpflow.set_trainable(mf, False)
-        layers.append(Layer(kern, Z_running, dim_out, mf, white=white))
-        if dim_in != dim_out:
-            Z_running = Z_running.dot(W)
-            X_running = X_running.dot(W)
-    layers.append(Layer(kernels[-1], Z_running, num_outputs, mean_function, white=white))
+            mean = gpflow.Linear(W)
+            gpflow.set_trainable(mean, False)
+        layers.append(Layer(kern, running_Z, d_out, mean, white=white))
+        if W is not None:
+            running_Z, running_X = running_Z @ W, running_X @ W
+    last_mean = gpflow.Zero() if mean_function is None else mean_function
+    layers.append(Layer(kernels[-1], running_Z, num_outputs or _np(Y).shape[1], last_mean, white=white))
     return layers
