@@ -27,6 +27,20 @@ UNIT = "point-samples/s"
 FP64_PEAK_FALLBACK_TFLOPS = 37.07   # profiles/r01_fp64_peaks.json (DMMA.8x8x4 register-resident loop, this pool's B200)
 
 
+def load_synthetic(package):
+    """The numpy-only module with the benchmark configurations and flop counts. Our arm imports it as part of the package;
+    the reference arm must not import `dgp_toolbox_b200` (its __init__ maps libdgp_b200.so into the process), so there the
+    file is loaded by path under another name."""
+    if package:
+        from dgp_toolbox_b200 import synthetic
+        return synthetic
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_bench_synthetic", os.path.join(ROOT, "dgp_toolbox_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def fp64_peak():
     """MEASURED_PEAKS.json has no FP64 figure (bf16 + HBM only), so the denominator is this repo's own calibration
     (tools/fp64_peaks.cu run on this pool's B200, committed as profiles/r01_fp64_peaks.json)."""
@@ -118,7 +132,7 @@ def main():
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
-    from dgp_toolbox_b200 import synthetic  # numpy-only module; does not need a GPU
+    synthetic = load_synthetic(package=args.impl == "ours")
     cfg = synthetic.CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -141,6 +155,7 @@ def main():
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "TensorFlow/GPflow absent from the image: oracle/ float64 torch-CPU restatement of the reference op sequence",
         }))
+        assert "dgp_toolbox_b200" not in sys.modules, "the reference arm must not load the product library"
         return
 
     import torch

@@ -22,6 +22,45 @@ def Y_ND(Y, ND, nadir, ideal=[0, 0]):
     return Y_
 
 
+def NDC(Y, C, obj1_ascending=True):
+    """EHVI.py:38-81: indices of the feasible (every constraint value <= 0), non-dominated points of the two-objective
+    DoE `Y = [y0 [n,1], y1 [n,1]]`, ordered by objective 0 (ascending, ties in DoE order; descending when
+    `obj1_ascending=False`). Host numpy over the DoE (tens of points): one pairwise dominance table instead of the
+    reference's double loop and bubble sort."""
+    y = np.concatenate((np.asarray(Y[0], dtype=np.float64).reshape(-1, 1), np.asarray(Y[1], dtype=np.float64).reshape(-1, 1)), axis=1)
+    C = np.asarray(C, dtype=np.float64).reshape(len(y), -1)
+    feasible = np.flatnonzero(C.max(axis=1) <= 0)
+    if feasible.size == 0:
+        return []
+    f = y[feasible]
+    le = (f[:, None, :] <= f[None, :, :]).all(-1)          # le[j, i]: point j is no worse than point i in both objectives
+    lt = (f[:, None, :] < f[None, :, :]).any(-1)           # ... and strictly better in at least one
+    dominated = (le & lt).any(axis=0)
+    front = feasible[~dominated]
+    front = front[np.argsort(y[front, 0], kind="stable")]
+    nd = [int(i) for i in front]
+    return nd if obj1_ascending else nd[::-1]
+
+
+def HV_calcul(ND, Y, bounds):
+    """EHVI.py:8-36: hypervolume (minimisation) of the front `ND` (sorted by objective 0 ascending) w.r.t. the reference
+    point (U1, U2); strips are added front point by front point exactly as the reference does, including its treatment
+    of points beyond the reference point."""
+    _, _, U1, U2 = bounds
+    if len(ND) == 0:
+        return 0
+    y1 = np.asarray(Y[0], dtype=np.float64).reshape(-1)[list(ND)]
+    y2 = np.asarray(Y[1], dtype=np.float64).reshape(-1)[list(ND)]
+    if np.any((y1 > U1) & (y2 > U2)):
+        return 0
+    hv = max((U1 - y1[0]) * (U2 - y2[0]), 0.0)
+    nxt1, nxt2, prev2 = y1[1:], y2[1:], y2[:-1]
+    outside = (nxt1 > U1) | (nxt2 > U2)
+    first_inside = (nxt2 <= U2) & (prev2 > U2)
+    height = np.where(first_inside, U2 - nxt2, prev2 - nxt2)
+    return float(hv + np.sum(np.where(outside, 0.0, height * (U1 - nxt1))))
+
+
 def psi(a, b, mu, sigma):
     """EHVI.py:102-104 on tensors (helper for callers; the EHVI kernel evaluates it in-kernel)."""
     u = (b - mu) / sigma

@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the reference's docstrings contain "\\s" / "\\i"; importing its unmodified source (tests/refexec.py) warns about them
+    config.addinivalue_line("filterwarnings", "ignore:invalid escape sequence:SyntaxWarning")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -24,3 +26,4 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
