@@ -41,6 +41,7 @@ class EI(Infill_criteria):
             raise NotImplementedError("only model.name == 'dgp' is on the accelerated path")
         X = model._check_X(_lib.as_device(x, model.device))
         N, D = X.shape[0], model.layers[-1].num_outputs
+        own_out = out is None
         if out is None:
             out = torch.empty((N, D), dtype=torch.float64, device=X.device)
         if N == 0:
@@ -48,8 +49,11 @@ class EI(Infill_criteria):
         m, keep = model._model_desc()
         zt, zp = model._zs(zs, num_samples, N)
         y_min = float(self.y_min.item() if hasattr(self.y_min, "item") else self.y_min)
-        _lib.get_context(X.device).call("dgp_ei", C.byref(m), _lib.ptr(X), N, num_samples, zp, model._next_seed(seed), 0,
-                                        y_min, 1 if analytic else 0, _lib.ptr(out))
+        ctx = _lib.get_context(X.device)
+        ctx.call("dgp_ei", C.byref(m), _lib.ptr(X), N, num_samples, zp, model._next_seed(seed), 0,
+                 y_min, 1 if analytic else 0, _lib.ptr(out))
+        if own_out:
+            ctx.check()   # a user call: raise on a non-positive-definite Kuu instead of returning NaN (search loops pass `out`)
         return out
 
     def run_with_grad(self, model, x, num_samples=1000, zs=None, seed=None, out=None, dx=None):

@@ -61,6 +61,7 @@ struct dgp_ctx {
   bool use_vform = true;                // forward-only calls fold q_sqrt_d^T Lu^-T once per step and skip the A pass
   bool share_first_layer = true;        // evaluate the first layer once per point instead of once per point-sample
   bool use_fused = true;                // fused conditional kernel (fused.cuh); false -> unfused GEMM pipeline
+  bool warp_major_groups = true;        // fused kernels: the two warps of an SM sub-partition sit in different column groups
   // the layers' replicated per-step work (Kuu build, operator packing, KL, M^3 glue, gradient assembly) is independent per
   // layer and made of tiny launches: it runs on per-layer side streams forked from / joined to the caller's stream
   static constexpr int kAux = 8;
@@ -452,7 +453,7 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
   H2D(dinvT, hinvT.data(), sizeof(double*) * nl);
 
   CAT(DGP_CAT_PREP);
-  CK(cudaMemsetAsync(c->d_info, 0, sizeof(int), c->stream));
+  // d_info is sticky: a failed factorisation stays flagged (and freezes the optimiser kernels) until dgp_check reads and clears it
   H2D(dargs, hargs.data(), sizeof(CholArgs) * nl);
   LayerFork forkA(c, nl);
   for (int l = 0; l < nl; ++l) {
@@ -580,6 +581,7 @@ int forward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, ChunkLa
     f.xFvar = (io.Fvars && io.Fvars[layer]) ? io.Fvars[layer] : nullptr;
     f.xF = (io.Fs && io.Fs[layer]) ? io.Fs[layer] : nullptr;
     f.stashA = stash ? cl.A : nullptr; f.stashT = stash ? cl.T : nullptr;
+    f.warp_major_groups = c->warp_major_groups ? 1 : 0;
     // few point-samples (a shared first layer, a BO-sized batch): halve the tile so that twice as many SMs share the launch;
     // the packed operator stream depends on BM only
     const int cfg = ((w.fcfg == 0 || w.fcfg == 2) && Pp / 64 <= c->num_sms / 2) ? w.fcfg + 1 : w.fcfg;
@@ -1284,7 +1286,11 @@ int check_chol(dgp_ctx* c) {
   int info = 0;
   CK(cudaMemcpyAsync(&info, c->d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  if (info) { c->err = "Kuu + jitter I is not positive definite (Cholesky pivot <= 0)"; return DGP_ERR_NUMERIC; }
+  if (info) {
+    CK(cudaMemsetAsync(c->d_info, 0, sizeof(int), c->stream));   // reported once; later steps start clean
+    c->err = "Kuu + jitter I is not positive definite (Cholesky pivot <= 0); parameter updates were suspended from that step on";
+    return DGP_ERR_NUMERIC;
+  }
   return DGP_OK;
 }
 
@@ -1310,8 +1316,9 @@ int dgp_ctx_create(int device, void* cuda_stream, dgp_ctx** out) {
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   if (getenv("DGP_B200_UNFUSED")) c->use_fused = false;
+  if (const char* e = getenv("DGP_B200_WARPMAP")) c->warp_major_groups = atoi(e) != 0;   // measurement hook
   c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
-  if (cudaMalloc(&c->d_info, sizeof(int)) != cudaSuccess) { delete c; return DGP_ERR_CUDA; }
+  if (cudaMalloc(&c->d_info, sizeof(int)) != cudaSuccess || cudaMemset(c->d_info, 0, sizeof(int)) != cudaSuccess) { delete c; return DGP_ERR_CUDA; }
   if (const char* e = getenv("DGP_B200_SPLITK_MAX")) { const int v = atoi(e); if (v >= 1 && v <= 512) c->splitk_max = v; }
   if (const char* e = getenv("DGP_B200_LOWER_WAVES")) { const int v = atoi(e); if (v >= 1 && v <= 256) c->lower_waves = v; }
   const char* lim = getenv("DGP_B200_WS_GB");
@@ -1577,7 +1584,7 @@ int adam_launch(dgp_ctx* c, const AdamTable& t, const double* grad, double* m, d
                 double b2, double eps, double* trace) {
   const double lr_t = lr * sqrt(1.0 - pow(b2, (double)step)) / (1.0 - pow(b1, (double)step));
   CAT(DGP_CAT_OTHER);
-  LAUNCH(adam_kernel, (unsigned)((t.total + 255) / 256), 256, 0, t, grad, m, v, lr_t, b1, b2, eps, trace);
+  LAUNCH(adam_kernel, (unsigned)((t.total + 255) / 256), 256, 0, t, grad, m, v, lr_t, b1, b2, eps, trace, c->d_info);
   return DGP_OK;
 }
 }  // namespace

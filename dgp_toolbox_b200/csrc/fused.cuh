@@ -118,6 +118,7 @@ struct FusedFwdArgs {
   double* Fmean; double* Fvar; double* F; double* z;    // chunk-local [P][D_out]; F / z may be null
   double* xFmean; double* xFvar; double* xF;            // caller-visible, any may be null
   double* stashA; double* stashT;                       // [Mp][Pp], [D_out][Mp][Pp] or null
+  int warp_major_groups;                                // 1: warps [g*WM, (g+1)*WM) form column group g (default); 0: group = warp % WN
 };
 
 // ---- mbarrier / bulk-copy primitives (sm_90+; SASS: SYNCS.*, UBLKCP) ----
@@ -279,7 +280,10 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
 
   // ---- consumers ----
   const int g8 = lane >> 2, t4 = lane & 3;
-  const int wm = warp / WN, wn = warp % WN;       // group = wn
+  // Warps w and w + 4 share an SM sub-partition (and its FP64 pipe). With group = warp / WM the two warps of a sub-partition belong
+  // to DIFFERENT column groups, which run decoupled (they share only the panel ring): while one group is in a block-end phase
+  // (barriers, write-back, stash stores) or in the Kuf / epilogue stages, the other keeps that sub-partition's DMMA pipe busy.
+  const int wm = a.warp_major_groups ? warp % WM : warp / WN, wn = a.warp_major_groups ? warp / WM : warp % WN;       // group = wn
   const int tg = wm * 32 + lane;                  // thread index inside the group
   const int col0 = wn * GC;                       // first tile column of the group
   double* xs = xs_all + wn * a.D_in * GC;

@@ -225,10 +225,13 @@ struct AdamTable { int n; long total; AdamSeg seg[kAdamMaxParams]; };
 
 __global__ void __launch_bounds__(256) adam_kernel(AdamTable t, const double* __restrict__ grad, double* __restrict__ m_state,
                                                    double* __restrict__ v_state, double lr_t, double beta1, double beta2, double eps,
-                                                   double* __restrict__ trace) {
+                                                   double* __restrict__ trace, const int* __restrict__ chol_failed) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx == 0 && trace) *trace = grad[0] - grad[1];   // the step's ELBO estimate: data term - KL
   if (idx >= t.total) return;
+  // a non-positive-definite Kuu makes this step's gradient NaN: keep the parameters at their last good values (the flag is sticky
+  // until dgp_check reports it), as the reference does by raising at the failing step
+  if (chol_failed && *chol_failed) return;
   int k = 0;
   while (k + 1 < t.n && idx >= t.seg[k + 1].start) ++k;
   const AdamSeg& sg = t.seg[k];

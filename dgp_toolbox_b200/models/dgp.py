@@ -232,8 +232,11 @@ class DGP_Base(_Module):
         return mean, var
 
     def predict(self, Xnew, num_samples, zs=None, seed=None):
-        """dgp.py:362-366 (DGP.predict: mixture moments of predict_y), reduced on the device."""
-        return self.predict_moments(Xnew, num_samples, add_lik_var=True, zs=zs, seed=seed)
+        """dgp.py:362-366 (DGP.predict: mixture moments of predict_y), reduced on the device. Raises on a non-positive-definite
+        Kuu instead of returning NaN (the search loops call predict_moments directly and check once at their end)."""
+        out = self.predict_moments(Xnew, num_samples, add_lik_var=True, zs=zs, seed=seed)
+        _lib.get_context(self.device).check()
+        return out
 
     # ------------------------------------------------------------------ optimisers (callers of the hot path, SURVEY §8 f1)
     _TRANSFORM_CODE = {None: 0, "positive": 1, "positive_shift": 2, "triangular": 3}
@@ -326,6 +329,8 @@ class DGP_Base(_Module):
                 step += n
                 if (step - 1) % messages == 0:
                     print(f"ELBO: {trace[-1].item()}")
+                    ctx.check()   # .item() has synchronised already: a failed Cholesky is raised at the block it happened in,
+                    #               with the parameters frozen at their last good values (adam_kernel skips flagged steps)
             ctx.check()
         finally:
             if auto_graph:
@@ -394,6 +399,7 @@ class DGP_Base(_Module):
                 self._adam_step(params, flat, state, t, lr_adam, beta_1, beta_2, epsilon)
                 if step % messages == 0:
                     print(f"ELBO: {(flat[0] - flat[1]).item()}")
+                    ctx.check()
                 self.natgrad_step(data, lr_gamma, variational_params, out=buf)
             ctx.check()
         finally:

@@ -346,6 +346,37 @@ def elbo_and_grads(model: OModel, X, Y, zs, scale: float = 1.0, wrt_X: bool = Fa
     return val.detach(), grads
 
 
+def elbo_and_grads_chunked(model: OModel, X, Y, seed: int, chunk: int = 256, scale: float = 1.0, n_offset: int = 0):
+    """ELBO and constrained-space gradients of a LARGE minibatch, accumulated over chunks of points: the data term
+    sum_n E_log_p_Y (models/dgp.py:96) is additive over points and the KL terms (:97) are added once, so the reference's value
+    and gradient on the whole minibatch equal the sums below. Draws are the Philox stream of `seed` at the GLOBAL point index
+    (what the CUDA kernels draw for the same seed), so no [S, N, D] array of the whole minibatch is ever materialised."""
+    params = model.named_params()
+    total = {k: torch.zeros_like(v) for k, v in params.items()}
+    value = 0.0
+    N = X.shape[0]
+    for lo in range(0, N, chunk):
+        hi = min(N, lo + chunk)
+        zs = [torch.as_tensor(philox_normal(seed, l, model.num_samples, hi - lo, layer.D_out, n_offset=n_offset + lo))
+              for l, layer in enumerate(model.layers)]
+        leaves = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+        layers = [OLayer(Z=leaves[f"layers.{i}.Z"], lengthscales=leaves[f"layers.{i}.lengthscales"], variance=leaves[f"layers.{i}.variance"],
+                         q_mu=leaves[f"layers.{i}.q_mu"], q_sqrt=leaves[f"layers.{i}.q_sqrt"], mean_kind=l.mean_kind, mf_W=l.mf_W,
+                         mf_b=l.mf_b, white=l.white, kernel_kind=l.kernel_kind) for i, l in enumerate(model.layers)]
+        m2 = OModel(layers=layers, lik_var=leaves["lik_var"], num_samples=model.num_samples)
+        term = E_log_p_Y(m2, X[lo:hi], Y[lo:hi], zs).sum() * scale
+        if lo == 0:
+            term = term - sum(layer_KL(l) for l in layers)
+        term.backward()
+        value += float(term.detach())
+        for k, v in leaves.items():
+            if v.grad is not None:
+                total[k] += v.grad
+    for i in range(len(model.layers)):
+        total[f"layers.{i}.q_sqrt"] = torch.tril(total[f"layers.{i}.q_sqrt"])
+    return value, total
+
+
 def predict_f(model: OModel, X, S, zs):
     """models/dgp.py:66-77."""
     _, Fmeans, Fvars = propagate(model.layers, X, S, zs)

@@ -313,3 +313,30 @@ def test_vform_forward_equals_reference_operation_order():
     bounds = [0, 3] + [o.dZ for o in offs[1:]] + [ga.numel()]
     for lo, hi in zip(bounds[:-1], bounds[1:]):
         assert float((ga[lo:hi] - gb[lo:hi]).abs().max()) <= 1e-8 * max(float(gb[lo:hi].abs().max()), 1e-12)
+
+
+def test_failed_cholesky_is_raised_at_the_failing_block_and_freezes_the_parameters(capsys):
+    """A non-positive-definite Kuu (here: a negative kernel variance written behind the bijector's back) must not destroy
+    the model: the flag is sticky until reported, the fused Adam launch skips flagged steps, and the training loop raises at
+    the message block the failure happened in (the reference raises at the failing step, models/dgp.py:142-146)."""
+    import dgp_toolbox_b200 as D
+    from oracle import dgp_oracle as O
+    from tests.helpers import product_model_from_problem
+    prob = O.synthetic_problem(3, [3], 16, 40)
+    pm = product_model_from_problem(prob, 4)
+    data = (prob["X"], prob["Y"])
+    pm.optimize_adam(data, iterations=2, messages=1)          # healthy steps first
+    before = [p.value.clone() for p in pm.trainable_parameters]
+    good_var = pm.layers[1].kern.variance.value.clone()
+    pm.layers[1].kern.variance.value.fill_(-1.0)
+    before[[id(p) for p in pm.trainable_parameters].index(id(pm.layers[1].kern.variance))].fill_(-1.0)
+    with pytest.raises(D._lib.DGPError, match="positive definite"):
+        pm.optimize_adam(data, iterations=5, messages=1)
+    for p, b in zip(pm.trainable_parameters, before):
+        assert torch.equal(p.value, b), p                      # nothing was overwritten with NaN
+    with pytest.raises(D._lib.DGPError, match="positive definite"):
+        pm.predict(prob["X"], 4)
+    pm.layers[1].kern.variance.value.copy_(good_var)
+    m, v = pm.predict(prob["X"], 4)                            # reported once: the next call starts clean
+    assert bool(torch.isfinite(m).all()) and bool(torch.isfinite(v).all())
+    capsys.readouterr()

@@ -163,3 +163,18 @@ def test_bench_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "point-samples/s" and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
+
+
+def test_chunked_oracle_equals_single_pass():
+    """oracle.elbo_and_grads_chunked (used by the full-size GPU parity tests) == oracle.elbo_and_grads on the same Philox draws."""
+    import torch
+    from oracle import dgp_oracle as O
+    prob = O.synthetic_problem(3, [3], 16, 50)
+    om = O.model_from_problem(prob, 4)
+    X, Y = torch.as_tensor(prob["X"]), torch.as_tensor(prob["Y"])
+    zs = [torch.as_tensor(O.philox_normal(9, l, 4, 50, layer.D_out)) for l, layer in enumerate(om.layers)]
+    v, g = O.elbo_and_grads(om, X, Y, zs, scale=2.0)
+    v2, g2 = O.elbo_and_grads_chunked(om, X, Y, 9, chunk=16, scale=2.0)
+    assert abs(float(v) - v2) <= 1e-12 * abs(v2)
+    for k in g:
+        assert float((g[k] - g2[k]).abs().max()) <= 1e-10 * float(g[k].abs().max() + 1e-300), k

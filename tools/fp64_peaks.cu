@@ -79,6 +79,54 @@ __global__ void dmma_smem_kernel(double* out, int iters, double seed){
   if(s==123.456) out[0]=s;
 }
 
+// Mixed issue: every warp carries NM independent DMMA chains and NF independent DFMA chains, interleaved in program order.
+// If DMMA and DFMA ran on separate pipes the loop would take max(t_dmma, t_dfma); if they share the FP64 pipe, the sum.
+template<int NM,int NF>
+__global__ void mixed_kernel(double* out, int iters, double seed){
+  double c0[NM>0?NM:1], c1[NM>0?NM:1], f[NF>0?NF:1];
+  double a = seed*1e-3 + threadIdx.x*1e-6, b = 1e-3, c = 1.0 - seed*1e-9;
+#pragma unroll
+  for(int i=0;i<NM;i++){ c0[i]=i; c1[i]=-i; }
+#pragma unroll
+  for(int i=0;i<NF;i++) f[i]=seed+i+threadIdx.x;
+  for(int it=0; it<iters; ++it){
+#pragma unroll
+    for(int i=0;i<(NM>NF?NM:NF);i++){
+      if(i<NM) dmma(c0[i],c1[i],a,b);
+      if(i<NF) f[i]=fma(f[i],c,b);
+    }
+  }
+  double s=0;
+#pragma unroll
+  for(int i=0;i<NM;i++) s+=c0[i]+c1[i];
+#pragma unroll
+  for(int i=0;i<NF;i++) s+=f[i];
+  if(s==123.456) out[0]=s;
+}
+// Same question with warp specialisation: even warps issue only DMMA, odd warps only DFMA.
+template<int ILP>
+__global__ void split_kernel(double* out, int iters, double seed){
+  double c0[ILP], c1[ILP];
+  double a = seed*1e-3 + threadIdx.x*1e-6, b = 1e-3, c = 1.0 - seed*1e-9;
+#pragma unroll
+  for(int i=0;i<ILP;i++){ c0[i]=i+threadIdx.x; c1[i]=-i; }
+  if((threadIdx.x>>5)&1){
+    for(int it=0; it<iters; ++it){
+#pragma unroll
+      for(int i=0;i<ILP;i++){ c0[i]=fma(c0[i],c,b); c1[i]=fma(c1[i],c,b); }   // 2*ILP DFMA per iteration
+    }
+  } else {
+    for(int it=0; it<iters; ++it){
+#pragma unroll
+      for(int i=0;i<ILP;i++) dmma(c0[i],c1[i],a,b);
+    }
+  }
+  double s=0;
+#pragma unroll
+  for(int i=0;i<ILP;i++) s+=c0[i]+c1[i];
+  if(s==123.456) out[0]=s;
+}
+
 template<typename F> float time_ms(F f, int reps=5){
   cudaEvent_t e0,e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   f(); f(); CK(cudaDeviceSynchronize());
@@ -129,6 +177,22 @@ int main(){
     printf(" \"dmma_dep_chain_ns_per_instr\":%.2f,\n", ms*1e6/iters);
     float ms2=time_ms([&]{dfma_kernel<1><<<1,32>>>(out,iters,1.0);});
     printf(" \"dfma_dep_chain_ns_per_instr\":%.2f,\n", ms2*1e6/iters);
+  }
+  // DMMA + DFMA mixed in one instruction stream / in neighbouring warps: do they co-issue?
+  {
+    int grid=sms*2, th=256;   // 16 warps per SM
+    double warps=(double)grid*(th/32);
+    float tm=time_ms([&]{mixed_kernel<8,0><<<grid,th>>>(out,iters,1.0);});
+    float tf=time_ms([&]{mixed_kernel<0,8><<<grid,th>>>(out,iters,1.0);});
+    float tx=time_ms([&]{mixed_kernel<8,8><<<grid,th>>>(out,iters,1.0);});
+    float tx2=time_ms([&]{mixed_kernel<8,2><<<grid,th>>>(out,iters,1.0);});
+    double fm=2.0*256*8*iters*warps, ff=2.0*32*8*iters*warps;
+    printf(" \"mixed_same_warp\":{\"dmma_only_ms\":%.3f,\"dfma_only_ms\":%.3f,\"both_ms\":%.3f,\"dmma_only_tflops\":%.2f,\"dfma_only_tflops\":%.2f,"
+           "\"both_total_tflops\":%.2f,\"dmma8_dfma2_ms\":%.3f,\"dmma8_dfma2_total_tflops\":%.2f,\"co_issue\":%s},\n",
+           tm,tf,tx,fm/tm/1e9,ff/tf/1e9,(fm+ff)/tx/1e9,tx2,(fm+ff/4)/tx2/1e9, tx < 0.9f*(tm+tf) ? "true":"false");
+    float ts=time_ms([&]{split_kernel<8><<<grid,th>>>(out,iters,1.0);});
+    double fsm=2.0*256*8*iters*warps/2, fsf=2.0*32*16*iters*warps/2;
+    printf(" \"mixed_warp_specialised\":{\"ms\":%.3f,\"dmma_tflops\":%.2f,\"dfma_tflops\":%.2f,\"total_tflops\":%.2f},\n",ts,fsm/ts/1e9,fsf/ts/1e9,(fsm+fsf)/ts/1e9);
   }
   // smem-fed DMMA
   printf(" \"dmma_smem\":[");
