@@ -140,7 +140,7 @@ class Context:
     def launch_count(self, reset=False) -> int:
         return int(lib.dgp_launch_count(self.h, 1 if reset else 0))
 
-    PROFILE_CATEGORIES = ("prep", "kuf", "gemm_fwd", "moments", "gemm_bwd_data", "rbf_bwd", "gemm_bwd_param", "other", "fused_fwd")
+    PROFILE_CATEGORIES = ("prep", "kuf", "gemm_fwd", "moments", "gemm_bwd_data", "rbf_bwd", "gemm_bwd_param", "other", "fused_fwd", "fused_bwd")
 
     def set_profiling(self, on: bool):
         lib.dgp_set_profiling(self.h, 1 if on else 0)

@@ -13,6 +13,7 @@
 #include "acq.cuh"
 #include "common.cuh"
 #include "fused.cuh"
+#include "fused_bwd.cuh"
 #include "gemm.cuh"
 #include "layer.cuh"
 #include "philox.cuh"
@@ -61,7 +62,8 @@ struct dgp_ctx {
   bool use_vform = true;                // forward-only calls fold q_sqrt_d^T Lu^-T once per step and skip the A pass
   bool share_first_layer = true;        // evaluate the first layer once per point instead of once per point-sample
   bool use_fused = true;                // fused conditional kernel (fused.cuh); false -> unfused GEMM pipeline
-  bool warp_major_groups = true;        // fused kernels: the two warps of an SM sub-partition sit in different column groups
+  bool use_fused_bwd = true;            // fused data-path adjoint (fused_bwd.cuh) for V-form layers it supports
+  bool warp_major_groups = false;       // fused kernels: the two warps of an SM sub-partition sit in different column groups
   // the layers' replicated per-step work (Kuu build, operator packing, KL, M^3 glue, gradient assembly) is independent per
   // layer and made of tiny launches: it runs on per-layer side streams forked from / joined to the caller's stream
   static constexpr int kAux = 8;
@@ -348,6 +350,8 @@ struct LayerWs {
   // and scratch of the once-per-step re-parameterisation back to (q_mu, q_sqrt, Ku)
   double *CTcat = nullptr, *G1 = nullptr, *DCt = nullptr, *dbeta = nullptr, *dqmu2 = nullptr, *dRcat = nullptr;
   double *dLinv = nullptr, *sq1 = nullptr, *sq2 = nullptr;
+  // fused data-path adjoint (fused_bwd.cuh): packed C_d^T / Lu^-T panel stream; bcfg: 0 = BM 256, 1 = BM 128, -1 = unfused GEMM pipeline
+  double* bstream = nullptr; int bcfg = -1, NPb = 0;
   double* part_small = nullptr;   // split-K partials of this layer's long-K M^3-class products (per layer: the layers run concurrently)
 };
 
@@ -371,6 +375,21 @@ int pick_fused_cfg(int Mp, int D_in, int D_out) {
   for (int cfg = 0; cfg < 4; ++cfg) {
     if (Mp % kFusedChoices[cfg].BM) continue;
     if (fused_smem(cfg, Mp, D_in, D_out) <= kMaxSmem) return cfg;
+  }
+  return -1;
+}
+
+// ---- fused data-path adjoint configurations ----
+constexpr int kFusedBwdBM[2] = {256, 128};
+size_t fused_bwd_smem(int cfg, int Mp, int D_in, int D_out) {
+  return cfg == 0 ? FusedBwdCfg<256, 64, 4, 2>::smem_bytes(Mp, D_in, D_out) : FusedBwdCfg<128, 64, 4, 2>::smem_bytes(Mp, D_in, D_out);
+}
+int pick_fused_bwd_cfg(int Mp, int D_in, int D_out) {
+  if (D_in > 16) return -1;
+  static const char* force = getenv("DGP_B200_FUSED_BWD_CFG");
+  for (int cfg = force ? atoi(force) : 0; cfg < 2; ++cfg) {
+    if (cfg < 0 || Mp % kFusedBwdBM[cfg]) continue;
+    if (fused_bwd_smem(cfg, Mp, D_in, D_out) <= kMaxSmem) return cfg;
   }
   return -1;
 }
@@ -437,6 +456,12 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
         w.CTcat = walloc(c, mm * w.D_out); w.G1 = walloc(c, mm); w.DCt = walloc(c, mm * w.D_out);
         w.dbeta = walloc(c, (size_t)w.Mp * 32); w.dqmu2 = walloc(c, (size_t)w.Mp * 32); w.dRcat = walloc(c, mm * w.D_out);
         w.dLinv = walloc(c, mm); w.sq1 = walloc(c, mm); w.sq2 = walloc(c, mm);
+        w.bcfg = c->use_fused_bwd ? pick_fused_bwd_cfg(w.Mp, w.D_in, w.D_out) : -1;
+        if (w.bcfg >= 0) {
+          const int BMb = kFusedBwdBM[w.bcfg], nbb = w.Mp / BMb;
+          w.NPb = (w.D_out + 1) * (BMb / kPanelK) * nbb * (nbb + 1) / 2;
+          w.bstream = walloc(c, (size_t)w.NPb * BMb * kPanelK);
+        }
       }
       w.Zs = walloc(c, (size_t)w.M * w.D_in);
       w.stream = walloc(c, (size_t)w.NP * BM * kPanelK);
@@ -496,6 +521,8 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
     if (w.vform && level == PREP_GRAD) {
       const long nct = (long)w.D_out * w.Mp * w.Mp;
       LAUNCH(vform_transpose_kernel, (unsigned)((nct + 255) / 256), 256, 0, w.Cmat, w.Mp, w.D_out, w.CTcat);
+      if (w.bcfg == 0) LAUNCH(pack_bwd_stream_kernel<256>, w.NPb, 256, 0, w.Cmat, w.LinvT, w.Mp, w.D_out, w.bstream);
+      else if (w.bcfg == 1) LAUNCH(pack_bwd_stream_kernel<128>, w.NPb, 256, 0, w.Cmat, w.LinvT, w.Mp, w.D_out, w.bstream);
       // c_lower products leave the tiles above the diagonal unwritten: start the accumulators from zero
       CK(cudaMemsetAsync(w.G1, 0, (size_t)w.Mp * w.Mp * sizeof(double), c->stream));
       CK(cudaMemsetAsync(w.DCt, 0, (size_t)nct * sizeof(double), c->stream));
@@ -698,6 +725,30 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
     const double* V = cl.A;
     double* dV = dA;
     double* Kbar = W;
+    const bool fused_bwd = w.bcfg >= 0;
+    const long ntile64 = Pp / 64;
+    long nbv = 0;
+    if (fused_bwd) {
+      // ---- one launch: dV, K-bar = Lu^-T dV and the kernel adjoint on resident tiles (fused_bwd.cuh) ----
+      CAT(DGP_CAT_FUSED_BWD);
+      FusedBwdArgs f;
+      memset(&f, 0, sizeof(f));
+      f.stream = w.bstream; f.V = V; f.T = cl.T; f.GvT = up.GvT; f.gq = up.gq; f.Gm = up.GmPad; f.gm_ld = 32; f.beta = w.betaP;
+      f.Zs = w.Zs; f.ls = d.lengthscales; f.var = d.variance; f.Xin = cl.Xin; f.xmod = cl.xmod; f.D_in = w.D_in;
+      f.mfW = d.mf_W; f.mean_kind = d.mean_kind; f.kind = d.kernel_kind; f.M = w.M; f.Mp = Mp; f.D_out = D; f.P = P; f.Pp = Pp;
+      f.dV = dV; f.Gbar = Gbar; f.dXin = dXin; f.XaugPad = XaugPad; f.part = rbf_part;
+      nbv = ntile64 * 2;
+      const size_t smem = fused_bwd_smem(w.bcfg, Mp, w.D_in, D);
+      const unsigned grid = (unsigned)(ntile64 < c->num_sms ? ntile64 : c->num_sms);
+#define FUSED_BWD_LAUNCH(BM_, DM_)                                                                                          \
+      do {                                                                                                                  \
+        if (!c->dry) CK(cudaFuncSetAttribute((fused_backward_kernel<BM_, 64, 4, 2, DM_>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem)); \
+        LAUNCH((fused_backward_kernel<BM_, 64, 4, 2, DM_>), grid, 288, smem, f);                                            \
+      } while (0)
+      if (w.bcfg == 0) { if (w.D_in <= 8) FUSED_BWD_LAUNCH(256, 8); else FUSED_BWD_LAUNCH(256, 16); }
+      else { if (w.D_in <= 8) FUSED_BWD_LAUNCH(128, 8); else FUSED_BWD_LAUNCH(128, 16); }
+#undef FUSED_BWD_LAUNCH
+    } else {
     CAT(DGP_CAT_GEMM_BWD_DATA);
     // dV = beta Gm^T + sum_d C_d^T (2 Gv_d o T_d) - 2 V diag(sum_d Gv_d)          (gq = -sum_d Gv_d)
     GemmArgs g = gargs(w.betaP, 32, up.GmPad, 32, dV, Pp, Mp, (int)Pp, 32);
@@ -718,7 +769,7 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
     r.var = d.variance; r.M = w.M; r.Mp = Mp; r.D_in = w.D_in; r.P = P; r.Pp = Pp; r.Gm = up.Gm; r.D_out = D;
     r.mean_kind = d.mean_kind; r.mfW = d.mf_W; r.kind = d.kernel_kind; r.dXin = dXin; r.XaugPad = XaugPad; r.part = rbf_part;
     const bool small = Pp / 128 < 2L * c->num_sms;   // latency-bound launch: 64-column blocks with 4 row groups
-    const long nbv = small ? Pp / kRbfCols : Pp / 128;
+    nbv = small ? Pp / kRbfCols : Pp / 128;
     const size_t smemv = small ? rbf_bwd_smem_bytes(w.M, w.D_in) : ((size_t)w.M * w.D_in + kMaxD + 32) * sizeof(double);
     RC(dispatch_dmax(w.D_in, [&](auto dm) -> int {
       constexpr int DM = decltype(dm)::value;
@@ -731,6 +782,7 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
       }
       return DGP_OK;
     }));
+    }
     if (!params) return DGP_OK;
     CAT(DGP_CAT_GEMM_BWD_PARAM);
     GemmArgs pg[4];
@@ -937,7 +989,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
     XaugPad = walloc(c, (size_t)Ppmax * 32);
     dXa = walloc(c, (size_t)Ppmax * 32);
     dXb = walloc(c, (size_t)Ppmax * 32);
-    rbf_part = walloc(c, (size_t)nbmax * 2 * 32);   // one row of partials per 64-column block of rbf_bwd_kernel
+    rbf_part = walloc(c, (size_t)nbmax * 2 * 40);   // one row of partials per 64-column block of rbf_bwd_kernel
     skcap = max_splitk_part(c, lw);
     skpart = walloc(c, skcap);
     if (nl > 1) {   // second set: layer l's parameter contractions read theirs while layer l-1's data path fills the other
@@ -1316,7 +1368,8 @@ int dgp_ctx_create(int device, void* cuda_stream, dgp_ctx** out) {
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   if (getenv("DGP_B200_UNFUSED")) c->use_fused = false;
-  if (const char* e = getenv("DGP_B200_WARPMAP")) c->warp_major_groups = atoi(e) != 0;   // measurement hook
+  if (const char* e = getenv("DGP_B200_WARPMAP")) c->warp_major_groups = atoi(e) != 0;   // measurement hooks
+  if (const char* e = getenv("DGP_B200_FUSED_BWD")) c->use_fused_bwd = atoi(e) != 0;
   c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
   if (cudaMalloc(&c->d_info, sizeof(int)) != cudaSuccess || cudaMemset(c->d_info, 0, sizeof(int)) != cudaSuccess) { delete c; return DGP_ERR_CUDA; }
   if (const char* e = getenv("DGP_B200_SPLITK_MAX")) { const int v = atoi(e); if (v >= 1 && v <= 512) c->splitk_max = v; }

@@ -299,8 +299,18 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
 #endif
   for (int idx = tg; idx < WM * GC; idx += GT) part[idx] = 0.0;
 
+#ifdef DGP_DEBUG_PHASECLK
+  long long ph_kuf = 0, ph_loop = 0, ph_end = 0, ph_epi = 0, ph_wait = 0;
+  const long long ph_t0 = clock64();
+#define PH_MARK(var) const long long var = clock64()
+#define PH_ADD(acc, from) acc += clock64() - (from)
+#else
+#define PH_MARK(var)
+#define PH_ADD(acc, from)
+#endif
   for (int tl = 0; tl < my_tiles; ++tl) {
     const long p0 = (long)(blockIdx.x + tl * gridDim.x) * PT + col0;   // first point-sample of this group's columns
+    PH_MARK(ph_a);
     group_sync(bar_id, GT);   // previous tile's epilogue is done with the group's columns / colsum
     // ---- stage 1: scaled inputs, then the Kuf tile ----
     for (int idx = tg; idx < a.D_in * GC; idx += GT) {
@@ -339,6 +349,8 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
       }
     }
     group_sync(bar_id, GT);
+    PH_ADD(ph_kuf, ph_a);
+    PH_MARK(ph_b);
     // ---- stages 2-4: flat loop over the operator panels ----
     double c0[TM][TN], c1[TM][TN];
     int pass = 0, qq = 0;   // pass 0: V, 1: A, 2 + d: T_d; qq: panel index inside the pass
@@ -361,7 +373,9 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
 #ifdef DGP_DEBUG_WAITCLK
       const long long t_w0 = clock64();
 #endif
+      PH_MARK(ph_w);
       mbar_wait(full + cst, cph);           // the panel's bytes have landed
+      PH_ADD(ph_wait, ph_w);
 #ifdef DGP_DEBUG_WAITCLK
       wait_clk += clock64() - t_w0;
 #endif
@@ -372,6 +386,7 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
       if (++cst == STAGES) { cst = 0; cph ^= 1; }
 
       if (e.flags & kPanelLast) {
+        PH_MARK(ph_e);
         if (e.kind != 1) {   // column sums of squares of V / T_d: reduce over this warp's rows, accumulate in part[wm][col]
 #pragma unroll
           for (int j = 0; j < TN; ++j) {
@@ -423,8 +438,11 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
           }
           group_sync(bar_id, GT);
         }
+        PH_ADD(ph_end, ph_e);
       }
     }
+    PH_ADD(ph_loop, ph_b);
+    PH_MARK(ph_c);
     // ---- stage 5: moments, sample, outputs ----
     for (int idx = tg; idx < GC * a.D_out; idx += GT) {
       const int c = idx / a.D_out, d = idx % a.D_out;
@@ -469,7 +487,15 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
         if (a.xF) a.xF[xrow * a.D_out + d] = f;
       }
     }
+    PH_ADD(ph_epi, ph_c);
   }
+#ifdef DGP_DEBUG_PHASECLK
+  if (lane == 0 && blockIdx.x == 1 && my_tiles > 10 && (warp == 0 || warp == 5)) {
+    const double tot = (double)(clock64() - ph_t0);
+    printf("fused_fwd cta %d warp %d (D_out %d, tiles %d): total %.0f clk/tile | kuf %.1f%% loop %.1f%% (of which block-ends %.1f%%, panel waits %.1f%%) epilogue %.1f%%\n",
+           blockIdx.x, warp, a.D_out, my_tiles, tot / my_tiles, 100.0 * ph_kuf / tot, 100.0 * ph_loop / tot, 100.0 * ph_end / tot, 100.0 * ph_wait / tot, 100.0 * ph_epi / tot);
+  }
+#endif
 #ifdef DGP_DEBUG_WAITCLK
   if (lane == 0 && blockIdx.x < 2 && my_tiles > 10) printf("cta %d warp %d: waited %.1f%% of %lld clk for operator panels\n", blockIdx.x, warp, 100.0 * wait_clk / (double)(clock64() - t_k0), clock64() - t_k0);
 #endif

@@ -61,7 +61,7 @@ int64_t dgp_launch_count(dgp_ctx* ctx, int reset);
 
 /* Per-category device time of the ctx's launches, measured with CUDA event pairs on the ctx's stream (bench.py's
  * live roofline figure). dgp_get_profile synchronises the stream; ms_out / launches_out have DGP_PROFILE_CATEGORIES entries. */
-#define DGP_PROFILE_CATEGORIES 9
+#define DGP_PROFILE_CATEGORIES 10
 enum { DGP_CAT_PREP = 0,            /* Kuu build, Cholesky + inverse, KL, replicated M^3-class products, gradient assembly */
        DGP_CAT_KUF = 1,             /* Kuf tiles (covs.Kuf) */
        DGP_CAT_GEMM_FWD = 2,        /* V = Lu^-1 Kuf, A = Lu^-T V, T_d = q_sqrt_d^T A  (DMMA) */
@@ -70,7 +70,8 @@ enum { DGP_CAT_PREP = 0,            /* Kuu build, Cholesky + inverse, KL, replic
        DGP_CAT_RBF_BWD = 5,         /* RBF adjoint on the Kuf block */
        DGP_CAT_GEMM_BWD_PARAM = 6,  /* dKu, dq_sqrt, dq_mu, dZ contractions over the point-samples (DMMA) */
        DGP_CAT_OTHER = 7,           /* likelihood, upstream adjoints, acquisition epilogues */
-       DGP_CAT_FUSED_FWD = 8 };     /* fused conditional + sample kernel (Kuf, both solves, q_sqrt contraction, moments in one launch) */
+       DGP_CAT_FUSED_FWD = 8,       /* fused conditional + sample kernel (Kuf, both solves, q_sqrt contraction, moments in one launch) */
+       DGP_CAT_FUSED_BWD = 9 };     /* fused data-path adjoint (dV, K-bar = Lu^-T dV, kernel adjoint in one launch; V-form layers) */
 int dgp_set_profiling(dgp_ctx* ctx, int on);
 /* CUDA-graph replay (default 0). With on = 1 the model-level calls that draw their own Philox samples (dgp_elbo_grad,
  * dgp_predict_moments, dgp_ei, dgp_ei_grad; zs_host == NULL) capture their launch sequence -- ~70-130 small launches over the

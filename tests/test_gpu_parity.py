@@ -38,6 +38,8 @@ SHAPES = [
     (4, [4], 320, 70, 2, True),           # Mp = 320: BM=64 fused configuration, 5 row blocks
     (20, [20, 20], 512, 24, 2, True),     # config-3 layer shape: D=20, M=512 -> BM=128, PT=32 fused configuration, 4 row blocks
     (12, [16], 130, 40, 3, True),         # Mp = 192 (padding rows), D_out = 16 > 8, widening Linear mean function
+    (5, [3, 6], 250, 77, 3, True),        # Mp = 256 with 6 padding rows, ragged widths, Linear mean functions, P = 231 (fused adjoint, BM = 256)
+    (12, [16], 120, 90, 2, True),         # Mp = 128 with padding rows, D_in = 12 / 16 > 8 (fused adjoint, BM = 128, DMAX = 16)
 ]
 
 
