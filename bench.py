@@ -41,6 +41,17 @@ def load_synthetic(package):
     return mod
 
 
+def load_traffic():
+    """Measured DRAM bytes per launch of the dominant kernels (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum),
+    read from the profile summary committed with this build (profiles/r02_traffic.json, written by tools/ncu_traffic.py from the
+    .ncu-rep of the SAME bench command; its header names the commit). No file -> traffic stays null: never a pasted literal."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 def fp64_peak():
     """MEASURED_PEAKS.json has no FP64 figure (bf16 + HBM only), so the denominator is this repo's own calibration
     (tools/fp64_peaks.cu run on this pool's B200, committed as profiles/r01_fp64_peaks.json)."""
@@ -259,21 +270,21 @@ def main():
                 "kernel_ms_per_step": ms / args.steps, "share_of_step": ms / all_ms if all_ms > 0 else None}
 
     fwd_cats = [k for k in ("fused_fwd", "gemm_fwd") if prof[k][0] > 0]
+    traffic = load_traffic()
     k_fwd = kernel_entry("dgp::fused_forward_kernel (Kuf tile -> V = Lu^-1 Kuf -> T_d = (q_sqrt_d^T Lu^-T) V -> moments/sample, FP64 DMMA, "
-                         "TMA bulk-copy operand ring)" if prof["fused_fwd"][0] > 0 else "dgp::gemm_kernel (forward contractions)",
-                         fwd_cats, f_fwd,
-                         # ncu --set full capture profiles/r01e_fused_forward_ncu.txt: dram read+write 1.1754 GB for one launch over
-                         # 65 536 point-samples of an 8->8 layer (= the 18.4 KB A/T_d stash per point-sample, no re-reads), scaled
-                         # to this run's launch size
-                         traffic=(1.1754e9 / 65536) * nb * S if prof["fused_fwd"][0] > 0 and args.config == "c2" else None)
-    k_bwd = kernel_entry("dgp::gemm_kernel (FP64 DMMA adjoint contractions: dV = sum_d C_d^T dT_d, Lu^-T dV, tril(dV V^T), "
-                         "tril(V diag(2Gv_d) T_d^T), V Gm, Gbar [X,1])", ["gemm_bwd_data", "gemm_bwd_param"], 2 * f_fwd,
-                         # ncu --set full capture profiles/r01h_top_kernels_ncu.txt, largest launch of the engine
-                         # (tril(V diag(2Gv_d) T_d^T) over one 262 144-point-sample chunk, 4352 CTAs): dram read 19.39 GB + write
-                         # 0.09 GB against 4.8 GB of operands (64x64 tiles re-read V / T_d through an L2 that the K-chunks in
-                         # flight overflow; 1.9 TB/s, not the bound -- DESIGN.md section 8.3)
-                         traffic=19.394378e9 + 0.091298e9 if args.config == "c2" and nb == 16384 else None)
-    main, other = (k_bwd, k_fwd) if k_bwd["kernel_ms_per_step"] >= k_fwd["kernel_ms_per_step"] else (k_fwd, k_bwd)
+                         "bulk-copy (UBLKCP) operand ring)" if prof["fused_fwd"][0] > 0 else "dgp::gemm_kernel (forward contractions)",
+                         fwd_cats, f_fwd, traffic=traffic.get("fused_forward_kernel"))
+    # adjoint = data path (fused_backward_kernel, or the unfused GEMMs + rbf_bwd when DGP_B200_FUSED_BWD=0) + parameter contractions;
+    # algorithmic flops: F_fwd each (the adjoint is exactly twice the forward)
+    data_cats = [k for k in ("fused_bwd", "gemm_bwd_data", "rbf_bwd") if prof[k][0] > 0]
+    k_data = kernel_entry("dgp::fused_backward_kernel (dV = sum_d C_d^T (2Gv_d o T_d) + ..., K-bar = Lu^-T dV, kernel adjoint on resident "
+                          "tiles; panels + T_d slabs through one bulk-copy ring, FP64 DMMA)" if prof["fused_bwd"][0] > 0
+                          else "dgp::gemm_kernel + rbf_bwd_kernel (unfused data adjoint)", data_cats, f_fwd,
+                          traffic=traffic.get("fused_backward_kernel"))
+    k_param = kernel_entry("dgp::gemm_kernel (FP64 DMMA contractions over the point-samples: tril(dV V^T), tril(V diag(2Gv_d) T_d^T), "
+                           "V Gm, Gbar [X,1])", ["gemm_bwd_param"], f_fwd, traffic=traffic.get("gemm_kernel_param"))
+    kernels = sorted([k_fwd, k_data, k_param], key=lambda k: -k["kernel_ms_per_step"])
+    main, others = kernels[0], kernels[1:]
     flops_rank_step = f_step * nb * S
     roofline = dict(main)
     roofline.update({
@@ -288,7 +299,8 @@ def main():
                     "(work the kernels actually have to do); this entry says what rate the reference's formulation would need "
                     "for the same throughput.",
             "equivalent_tflops": f_step_ref * nb * S / (ms_step * 1e-3) / 1e12},
-        "other_kernels": [other],
+        "other_kernels": others,
+        "traffic_source": traffic.get("source"),
         "categories_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
         "profiled_pass_ms_per_step": ms_profiled / args.steps,
         "note": "achieved = algorithmic (triangular-aware, useful) FP64 flops of SURVEY.md §8d / CUDA-event time of the kernel's launches, "

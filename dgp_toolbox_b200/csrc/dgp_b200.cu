@@ -64,6 +64,7 @@ struct dgp_ctx {
   bool use_fused = true;                // fused conditional kernel (fused.cuh); false -> unfused GEMM pipeline
   bool use_fused_bwd = true;            // fused data-path adjoint (fused_bwd.cuh) for V-form layers it supports
   bool warp_major_groups = false;       // fused kernels: the two warps of an SM sub-partition sit in different column groups
+  int group_skew = 0;                   // ... which start this many clocks apart       // fused kernels: the two warps of an SM sub-partition sit in different column groups
   // the layers' replicated per-step work (Kuu build, operator packing, KL, M^3 glue, gradient assembly) is independent per
   // layer and made of tiny launches: it runs on per-layer side streams forked from / joined to the caller's stream
   static constexpr int kAux = 8;
@@ -380,9 +381,9 @@ int pick_fused_cfg(int Mp, int D_in, int D_out) {
 }
 
 // ---- fused data-path adjoint configurations ----
-constexpr int kFusedBwdBM[2] = {256, 128};
+constexpr int kFusedBwdBM[2] = {128, 64};   // 128-row blocks (4 m-tiles per warp); 64-row blocks for Mp = 64, 192, ...
 size_t fused_bwd_smem(int cfg, int Mp, int D_in, int D_out) {
-  return cfg == 0 ? FusedBwdCfg<256, 64, 4, 2>::smem_bytes(Mp, D_in, D_out) : FusedBwdCfg<128, 64, 4, 2>::smem_bytes(Mp, D_in, D_out);
+  return cfg == 0 ? FusedBwdCfg<128, 64, 4, 2>::smem_bytes(Mp, D_in, D_out) : FusedBwdCfg<64, 64, 2, 4>::smem_bytes(Mp, D_in, D_out);
 }
 int pick_fused_bwd_cfg(int Mp, int D_in, int D_out) {
   if (D_in > 16) return -1;
@@ -521,8 +522,8 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
     if (w.vform && level == PREP_GRAD) {
       const long nct = (long)w.D_out * w.Mp * w.Mp;
       LAUNCH(vform_transpose_kernel, (unsigned)((nct + 255) / 256), 256, 0, w.Cmat, w.Mp, w.D_out, w.CTcat);
-      if (w.bcfg == 0) LAUNCH(pack_bwd_stream_kernel<256>, w.NPb, 256, 0, w.Cmat, w.LinvT, w.Mp, w.D_out, w.bstream);
-      else if (w.bcfg == 1) LAUNCH(pack_bwd_stream_kernel<128>, w.NPb, 256, 0, w.Cmat, w.LinvT, w.Mp, w.D_out, w.bstream);
+      if (w.bcfg == 0) LAUNCH(pack_bwd_stream_kernel<128>, w.NPb, 256, 0, w.Cmat, w.LinvT, w.Mp, w.D_out, w.bstream);
+      else if (w.bcfg == 1) LAUNCH(pack_bwd_stream_kernel<64>, w.NPb, 256, 0, w.Cmat, w.LinvT, w.Mp, w.D_out, w.bstream);
       // c_lower products leave the tiles above the diagonal unwritten: start the accumulators from zero
       CK(cudaMemsetAsync(w.G1, 0, (size_t)w.Mp * w.Mp * sizeof(double), c->stream));
       CK(cudaMemsetAsync(w.DCt, 0, (size_t)nct * sizeof(double), c->stream));
@@ -608,7 +609,7 @@ int forward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, ChunkLa
     f.xFvar = (io.Fvars && io.Fvars[layer]) ? io.Fvars[layer] : nullptr;
     f.xF = (io.Fs && io.Fs[layer]) ? io.Fs[layer] : nullptr;
     f.stashA = stash ? cl.A : nullptr; f.stashT = stash ? cl.T : nullptr;
-    f.warp_major_groups = c->warp_major_groups ? 1 : 0;
+    f.warp_major_groups = c->warp_major_groups ? 1 : 0; f.group_skew = c->group_skew;
     // few point-samples (a shared first layer, a BO-sized batch): halve the tile so that twice as many SMs share the launch;
     // the packed operator stream depends on BM only
     const int cfg = ((w.fcfg == 0 || w.fcfg == 2) && Pp / 64 <= c->num_sms / 2) ? w.fcfg + 1 : w.fcfg;
@@ -737,16 +738,17 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
       f.Zs = w.Zs; f.ls = d.lengthscales; f.var = d.variance; f.Xin = cl.Xin; f.xmod = cl.xmod; f.D_in = w.D_in;
       f.mfW = d.mf_W; f.mean_kind = d.mean_kind; f.kind = d.kernel_kind; f.M = w.M; f.Mp = Mp; f.D_out = D; f.P = P; f.Pp = Pp;
       f.dV = dV; f.Gbar = Gbar; f.dXin = dXin; f.XaugPad = XaugPad; f.part = rbf_part;
-      nbv = ntile64 * 2;
+      f.warp_major_groups = c->warp_major_groups ? 1 : 0; f.group_skew = c->group_skew;
+      nbv = ntile64 * (w.bcfg == 0 ? 2 : 4);   // one row of partial sums per tile and column group
       const size_t smem = fused_bwd_smem(w.bcfg, Mp, w.D_in, D);
       const unsigned grid = (unsigned)(ntile64 < c->num_sms ? ntile64 : c->num_sms);
-#define FUSED_BWD_LAUNCH(BM_, DM_)                                                                                          \
+#define FUSED_BWD_LAUNCH(BM_, WM_, WN_, DM_)                                                                                \
       do {                                                                                                                  \
-        if (!c->dry) CK(cudaFuncSetAttribute((fused_backward_kernel<BM_, 64, 4, 2, DM_>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem)); \
-        LAUNCH((fused_backward_kernel<BM_, 64, 4, 2, DM_>), grid, 288, smem, f);                                            \
+        if (!c->dry) CK(cudaFuncSetAttribute((fused_backward_kernel<BM_, 64, WM_, WN_, DM_>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem)); \
+        LAUNCH((fused_backward_kernel<BM_, 64, WM_, WN_, DM_>), grid, 288, smem, f);                                        \
       } while (0)
-      if (w.bcfg == 0) { if (w.D_in <= 8) FUSED_BWD_LAUNCH(256, 8); else FUSED_BWD_LAUNCH(256, 16); }
-      else { if (w.D_in <= 8) FUSED_BWD_LAUNCH(128, 8); else FUSED_BWD_LAUNCH(128, 16); }
+      if (w.bcfg == 0) { if (w.D_in <= 8) FUSED_BWD_LAUNCH(128, 4, 2, 8); else FUSED_BWD_LAUNCH(128, 4, 2, 16); }
+      else { if (w.D_in <= 8) FUSED_BWD_LAUNCH(64, 2, 4, 8); else FUSED_BWD_LAUNCH(64, 2, 4, 16); }
 #undef FUSED_BWD_LAUNCH
     } else {
     CAT(DGP_CAT_GEMM_BWD_DATA);
@@ -989,7 +991,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
     XaugPad = walloc(c, (size_t)Ppmax * 32);
     dXa = walloc(c, (size_t)Ppmax * 32);
     dXb = walloc(c, (size_t)Ppmax * 32);
-    rbf_part = walloc(c, (size_t)nbmax * 2 * 40);   // one row of partials per 64-column block of rbf_bwd_kernel
+    rbf_part = walloc(c, (size_t)nbmax * 8 * 20);   // one row of partials per 64-column block of rbf_bwd_kernel
     skcap = max_splitk_part(c, lw);
     skpart = walloc(c, skcap);
     if (nl > 1) {   // second set: layer l's parameter contractions read theirs while layer l-1's data path fills the other
@@ -1370,6 +1372,7 @@ int dgp_ctx_create(int device, void* cuda_stream, dgp_ctx** out) {
   if (getenv("DGP_B200_UNFUSED")) c->use_fused = false;
   if (const char* e = getenv("DGP_B200_WARPMAP")) c->warp_major_groups = atoi(e) != 0;   // measurement hooks
   if (const char* e = getenv("DGP_B200_FUSED_BWD")) c->use_fused_bwd = atoi(e) != 0;
+  if (const char* e = getenv("DGP_B200_SKEW")) c->group_skew = atoi(e);
   c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
   if (cudaMalloc(&c->d_info, sizeof(int)) != cudaSuccess || cudaMemset(c->d_info, 0, sizeof(int)) != cudaSuccess) { delete c; return DGP_ERR_CUDA; }
   if (const char* e = getenv("DGP_B200_SPLITK_MAX")) { const int v = atoi(e); if (v >= 1 && v <= 512) c->splitk_max = v; }

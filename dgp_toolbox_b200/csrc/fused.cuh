@@ -118,7 +118,8 @@ struct FusedFwdArgs {
   double* Fmean; double* Fvar; double* F; double* z;    // chunk-local [P][D_out]; F / z may be null
   double* xFmean; double* xFvar; double* xF;            // caller-visible, any may be null
   double* stashA; double* stashT;                       // [Mp][Pp], [D_out][Mp][Pp] or null
-  int warp_major_groups;                                // 1: warps [g*WM, (g+1)*WM) form column group g (default); 0: group = warp % WN
+  int warp_major_groups;                                // 1: warps [g*WM, (g+1)*WM) form column group g; 0: group = warp % WN (default)
+  int group_skew;                                       // measurement hook: clocks by which column group g starts late (g * group_skew)
 };
 
 // ---- mbarrier / bulk-copy primitives (sm_90+; SASS: SYNCS.*, UBLKCP) ----
@@ -298,9 +299,13 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
   const long long t_k0 = clock64();
 #endif
   for (int idx = tg; idx < WM * GC; idx += GT) part[idx] = 0.0;
+  if (a.group_skew > 0 && wn > 0) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < (long long)a.group_skew * wn) {}
+  }
 
 #ifdef DGP_DEBUG_PHASECLK
-  long long ph_kuf = 0, ph_loop = 0, ph_end = 0, ph_epi = 0, ph_wait = 0;
+  long long ph_kuf = 0, ph_loop = 0, ph_end = 0, ph_epi = 0, ph_wait = 0, ph_dot = 0;
   const long long ph_t0 = clock64();
 #define PH_MARK(var) const long long var = clock64()
 #define PH_ADD(acc, from) acc += clock64() - (from)
@@ -448,21 +453,28 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
       const int c = idx / a.D_out, d = idx % a.D_out;
       const long p = p0 + c;
       if (p >= a.P) continue;
+#ifdef DGP_DEBUG_PHASECLK
+      const long long ph_c2 = clock64();
+#endif
       double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
       const double* tc = tile + col0 + c;
       const double* qd = a.qmu + d;
       int m = 0;
-      for (; m + 8 <= a.M; m += 8) {   // eight independent q_mu loads in flight: they come from L2 (L1 is ~12 KB here)
-        double qv[8];
+      for (; m + 16 <= a.M; m += 16) {   // sixteen independent weight loads in flight: they come from L2 (L1 is ~12 KB here)
+        double qv[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) qv[u] = qd[(m + u) * a.qmu_ld];
-        m0 = fma(tc[(m + 0) * LDT], qv[0], m0); m1 = fma(tc[(m + 1) * LDT], qv[1], m1);
-        m2 = fma(tc[(m + 2) * LDT], qv[2], m2); m3 = fma(tc[(m + 3) * LDT], qv[3], m3);
-        m0 = fma(tc[(m + 4) * LDT], qv[4], m0); m1 = fma(tc[(m + 5) * LDT], qv[5], m1);
-        m2 = fma(tc[(m + 6) * LDT], qv[6], m2); m3 = fma(tc[(m + 7) * LDT], qv[7], m3);
+        for (int u = 0; u < 16; ++u) qv[u] = qd[(m + u) * a.qmu_ld];
+#pragma unroll
+        for (int u = 0; u < 16; u += 4) {
+          m0 = fma(tc[(m + u + 0) * LDT], qv[u + 0], m0); m1 = fma(tc[(m + u + 1) * LDT], qv[u + 1], m1);
+          m2 = fma(tc[(m + u + 2) * LDT], qv[u + 2], m2); m3 = fma(tc[(m + u + 3) * LDT], qv[u + 3], m3);
+        }
       }
       for (; m < a.M; ++m) m0 = fma(tc[m * LDT], qd[m * a.qmu_ld], m0);
       const double mean = (m0 + m1) + (m2 + m3);
+#ifdef DGP_DEBUG_PHASECLK
+      ph_dot += clock64() - ph_c2;
+#endif
       const double* x = a.Xin + (p % a.xmod) * a.D_in;
       double mf = 0.0;
       if (a.mean_kind == 1) mf = x[d];
@@ -492,8 +504,8 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
 #ifdef DGP_DEBUG_PHASECLK
   if (lane == 0 && blockIdx.x == 1 && my_tiles > 10 && (warp == 0 || warp == 5)) {
     const double tot = (double)(clock64() - ph_t0);
-    printf("fused_fwd cta %d warp %d (D_out %d, tiles %d): total %.0f clk/tile | kuf %.1f%% loop %.1f%% (of which block-ends %.1f%%, panel waits %.1f%%) epilogue %.1f%%\n",
-           blockIdx.x, warp, a.D_out, my_tiles, tot / my_tiles, 100.0 * ph_kuf / tot, 100.0 * ph_loop / tot, 100.0 * ph_end / tot, 100.0 * ph_wait / tot, 100.0 * ph_epi / tot);
+    printf("fused_fwd cta %d warp %d (D_out %d, tiles %d): total %.0f clk/tile | kuf %.1f%% loop %.1f%% (of which block-ends %.1f%%, panel waits %.1f%%) epilogue %.1f%% (dot products %.1f%%)\n",
+           blockIdx.x, warp, a.D_out, my_tiles, tot / my_tiles, 100.0 * ph_kuf / tot, 100.0 * ph_loop / tot, 100.0 * ph_end / tot, 100.0 * ph_wait / tot, 100.0 * ph_epi / tot, 100.0 * ph_dot / tot);
   }
 #endif
 #ifdef DGP_DEBUG_WAITCLK

@@ -33,6 +33,7 @@ struct FusedBwdArgs {
   double* dXin;                         // [P][D_in] out or null
   double* XaugPad;                      // [Pp][32] out: [x, 1, 0...]
   double* part;                         // [tiles * WN][D_in + 1] out: partial sums for dl_j, ds2
+  int warp_major_groups, group_skew;    // see FusedFwdArgs
 };
 
 // Panel order: pass 0: row block i = 0..nb-1, output d = 0..D-1, k-panels 0..(i+1)*BM/16-1 of C_d^T; pass 1: row block i,
@@ -59,6 +60,48 @@ __global__ void __launch_bounds__(256) pack_bwd_stream_kernel(const double* __re
   }
 }
 
+// panel_block of fused.cuh with the B fragments multiplied by a per-column scale as they are loaded (pass 0: 2 Gv_d)
+template <int LO, int HI, int TM, int TN, int WM, int LDT, bool SC>
+__device__ __forceinline__ void bwd_panel_block(double (&c0)[TM][TN], double (&c1)[TM][TN], const double* __restrict__ pan,
+                                                const double* __restrict__ bt, const double (&sc)[TN], int wm, int g8, int t4) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    double bv[TN], av[HI - LO > 0 ? HI - LO : 1];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) bv[j] = bt[kk * 4 * LDT + j * 8];
+#pragma unroll
+    for (int i = LO; i < HI; ++i) {
+      const int row = i * 8 * WM + wm * 8 + g8;
+      av[i - LO] = pan[row * kPanelK + (((kk ^ (row & 3)) << 2) | t4)];
+    }
+    if (SC) {
+#pragma unroll
+      for (int j = 0; j < TN; ++j) bv[j] *= sc[j];
+    }
+#pragma unroll
+    for (int i = LO; i < HI; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) dmma884(c0[i][j], c1[i][j], av[i - LO], bv[j]);
+  }
+}
+template <int TM, int TN, int WM, int LDT, bool SC>
+__device__ __forceinline__ void bwd_panel_dispatch(double (&c0)[TM][TN], double (&c1)[TM][TN], const double* pan, const double* bt,
+                                                   const double (&sc)[TN], int wm, int g8, int t4, int lo, int hi) {
+  static_assert(TM <= 4, "dispatch covers TM <= 4");
+  if (lo == 0) {
+    if (hi == TM) { bwd_panel_block<0, TM, TM, TN, WM, LDT, SC>(c0, c1, pan, bt, sc, wm, g8, t4); return; }
+    if constexpr (TM >= 2) { if (hi == 1) { bwd_panel_block<0, 1, TM, TN, WM, LDT, SC>(c0, c1, pan, bt, sc, wm, g8, t4); return; } }
+    if constexpr (TM >= 3) { if (hi == 2) { bwd_panel_block<0, 2, TM, TN, WM, LDT, SC>(c0, c1, pan, bt, sc, wm, g8, t4); return; } }
+    if constexpr (TM >= 4) { if (hi == 3) { bwd_panel_block<0, 3, TM, TN, WM, LDT, SC>(c0, c1, pan, bt, sc, wm, g8, t4); return; } }
+    return;
+  }
+  if constexpr (TM >= 2) { if (lo == TM - 1) { bwd_panel_block<TM - 1, TM, TM, TN, WM, LDT, SC>(c0, c1, pan, bt, sc, wm, g8, t4); return; } }
+  if constexpr (TM >= 3) { if (lo == TM - 2) { bwd_panel_block<TM - 2, TM, TM, TN, WM, LDT, SC>(c0, c1, pan, bt, sc, wm, g8, t4); return; } }
+  if constexpr (TM >= 4) { if (lo == TM - 3) { bwd_panel_block<TM - 3, TM, TM, TN, WM, LDT, SC>(c0, c1, pan, bt, sc, wm, g8, t4); return; } }
+}
+
+constexpr int kZChunk = 32;   // inducing rows staged per round of the input-gradient sweep
+
 template <int BM, int PT, int WM, int WN>
 struct FusedBwdCfg {
   static_assert(WM * WN == 8, "8 consumer warps");
@@ -67,9 +110,9 @@ struct FusedBwdCfg {
   static constexpr int TM = BM / (8 * WM), TN = GC / 8;
   static constexpr int LDT = PT + 4;
   static constexpr int PANEL = BM * kPanelK, SLAB = kPanelK * LDT, STAGE = PANEL + SLAB;
-  static constexpr int STAGES = BM >= 256 ? 2 : 3;
+  static constexpr int STAGES = 3;
   static size_t smem_bytes(int Mp, int D_in, int D_out) {
-    return ((size_t)STAGES * STAGE + (size_t)Mp * LDT + (size_t)D_in * PT + (size_t)D_out * PT + (size_t)PT + 2 * STAGES + 2 * WN * WM) * sizeof(double);
+    return ((size_t)STAGES * STAGE + (size_t)Mp * LDT + (size_t)D_in * PT + (size_t)D_out * PT + (size_t)PT + 2 * STAGES + 2 + (size_t)WN * WM * (kMaxD + 1) + (size_t)WN * kZChunk * D_in) * sizeof(double);
   }
 };
 
@@ -86,7 +129,9 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
   double* gq_all = gv2_all + a.D_out * PT;                // [WN][GC]
   unsigned long long* full = reinterpret_cast<unsigned long long*>(gq_all + PT);
   unsigned long long* empty = full + STAGES;
-  double* red_all = reinterpret_cast<double*>(empty + STAGES);   // [WN][WM][2] scratch of the per-tile group reductions
+  unsigned long long* vbar = empty + STAGES;                      // the tile's V rows have landed in the resident tile
+  double* red_all = reinterpret_cast<double*>(vbar + 2);          // [WN][WM][kMaxD + 1] scratch of the per-tile group reductions
+  double* zbuf_all = red_all + WN * WM * (kMaxD + 1);             // [WN][kZChunk][D_in] staged rows of the scaled inducing inputs
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = a.Mp / BM, kt = a.Mp / kPanelK;
@@ -95,6 +140,7 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8); }
+    mbar_init(vbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -104,19 +150,49 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
     if (lane == 0) {
       int st = 0;
       unsigned ph = 0;
+      // The T_d slabs come from HBM (the stash is far larger than L2) and the ring is only STAGES deep, so a second iterator runs
+      // kAhead stages ahead of the copies and pulls the slabs into L2 (cp.async.bulk.prefetch.L2): the copy itself then hits L2.
+#ifndef DGP_BWD_AHEAD
+#define DGP_BWD_AHEAD 8
+#endif
+      constexpr int kAhead = DGP_BWD_AHEAD;
+      int f_tl = 0, f_i = 0, f_d = 0, f_ks = 0;
+      auto prefetch_next = [&]() {
+        if (f_tl >= my_tiles) return;
+        const double* trow = a.T + ((long)f_d * a.Mp + (long)f_ks * kPanelK) * a.Pp + (long)(blockIdx.x + f_tl * gridDim.x) * PT;
+#pragma unroll 4
+        for (int r = 0; r < kPanelK; ++r)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(trow + (long)r * a.Pp), "r"(PT * 8) : "memory");
+        if (++f_ks == (f_i + 1) * KPB) { f_ks = 0; if (++f_d == a.D_out) { f_d = 0; if (++f_i == nb) { f_i = 0; ++f_tl; } } }
+      };
+      for (int q = 0; q < kAhead; ++q) prefetch_next();
       for (int tl = 0; tl < my_tiles; ++tl) {
         const long p0 = (long)(blockIdx.x + tl * gridDim.x) * PT;
         const double* src = a.stream;
+        int issued = 0;
         for (int i = 0; i < nb; ++i)
           for (int d = 0; d < a.D_out; ++d)
             for (int ks = 0; ks < (i + 1) * KPB; ++ks) {
               mbar_wait(empty + st, ph ^ 1);
+              if (issued++ == STAGES) {
+                // All 8 consumer warps have released the first panel of THIS tile, so the previous tile's epilogue is over and
+                // the resident tile is write-only until the block ends of pass 0: park the tile's V rows there (the 2 V diag(gq)
+                // term reads them at the block end, just before dV overwrites them).
+                mbar_arrive_expect_tx(vbar, (unsigned)(a.Mp * PT * 8));
+                for (int r = 0; r < a.Mp; ++r) bulk_g2s(tile + r * LDT, a.V + (long)r * a.Pp + p0, PT * 8, vbar);
+              }
               double* dst = pbuf + st * STAGE;
+#ifdef DGP_BWD_EXPERIMENT_NO_SLABS   // measurement only (wrong results): how much of the ring wait is the stash traffic?
+              mbar_arrive_expect_tx(full + st, PANEL * 8);
+              bulk_g2s(dst, src, PANEL * 8, full + st);
+#else
               mbar_arrive_expect_tx(full + st, (PANEL + kPanelK * PT) * 8);
               bulk_g2s(dst, src, PANEL * 8, full + st);
               const double* trow = a.T + ((long)d * a.Mp + (long)ks * kPanelK) * a.Pp + p0;
 #pragma unroll 4
               for (int r = 0; r < kPanelK; ++r) bulk_g2s(dst + PANEL + r * LDT, trow + (long)r * a.Pp, PT * 8, full + st);
+#endif
+              prefetch_next();
               src += PANEL;
               if (++st == STAGES) { st = 0; ph ^= 1; }
             }
@@ -135,47 +211,32 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
 
   // ---- consumers ----
   const int g8 = lane >> 2, t4 = lane & 3;
-  const int wm = warp / WN, wn = warp % WN;
+  const int wm = a.warp_major_groups ? warp % WM : warp / WN, wn = a.warp_major_groups ? warp / WM : warp % WN;
   const int tg = wm * 32 + lane;
   const int col0 = wn * GC;
   double* xs = xs_all + wn * a.D_in * GC;
   double* gv2 = gv2_all + wn * a.D_out * GC;
   double* gqs = gq_all + wn * GC;
-  double* red = red_all + wn * WM * 2;
+  double* red = red_all + wn * WM * (kMaxD + 1);
+  double* zbuf = zbuf_all + wn * kZChunk * a.D_in;
   const int bar_id = 1 + wn;
   const double s2 = a.var[0];
   int cst = 0;
   unsigned cph = 0;
   double c0[TM][TN], c1[TM][TN];
 
-  // one k-panel: A fragments from the swizzled panel, B fragments from `bt` (row stride LDT), m-tiles [lo, hi) only
-  auto run_panel = [&](const double* pan, const double* bt, int lo, int hi, const double* sc) {
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      double bv[TN], av[TM];
-#pragma unroll
-      for (int j = 0; j < TN; ++j) bv[j] = bt[kk * 4 * LDT + j * 8];
-      if (sc) {
-#pragma unroll
-        for (int j = 0; j < TN; ++j) bv[j] *= sc[j];
-      }
-#pragma unroll
-      for (int i = 0; i < TM; ++i) {
-        const int row = i * 8 * WM + wm * 8 + g8;
-        av[i] = pan[row * kPanelK + (((kk ^ (row & 3)) << 2) | t4)];
-      }
-#pragma unroll
-      for (int i = 0; i < TM; ++i)
-        if (i >= lo && i < hi) {   // warp-uniform: a predicated-off DMMA would still occupy the pipe
-#pragma unroll
-          for (int j = 0; j < TN; ++j) dmma884(c0[i][j], c1[i][j], av[i], bv[j]);
-        }
-    }
-  };
-
+  if (a.group_skew > 0 && wn > 0) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < (long long)a.group_skew * wn) {}
+  }
+#ifdef DGP_DEBUG_PHASECLK
+  long long ph_pro = 0, ph_p0 = 0, ph_be = 0, ph_p1 = 0, ph_row = 0, ph_red = 0, ph_out = 0, ph_wait = 0;
+  const long long ph_t0 = clock64();
+#endif
   for (int tl = 0; tl < my_tiles; ++tl) {
     const long tile_index = (long)blockIdx.x + (long)tl * gridDim.x;
     const long p0 = tile_index * PT + col0;
+    PH_MARK(ph_a);
     group_sync(bar_id, GT);   // the previous tile's epilogue is done with the group's columns
     for (int idx = tg; idx < a.D_in * GC; idx += GT) {
       const int j = idx / GC, c = idx % GC;
@@ -189,8 +250,10 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
     if (tg < GC) gqs[tg] = a.gq[p0 + tg];
     group_sync(bar_id, GT);
 
+    PH_ADD(ph_pro, ph_a);
     // ---- pass 0: dV ----
     for (int i = 0; i < nb; ++i) {
+      PH_MARK(ph_b);
 #pragma unroll
       for (int ti = 0; ti < TM; ++ti)
 #pragma unroll
@@ -203,45 +266,60 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
           const int num = ks * kPanelK - i * BM - 7 - wm * 8;   // lower operator: row r needs k <= r
           const int lo = num > 0 ? (num + 8 * WM - 1) / (8 * WM) : 0;
           const double* stage = pbuf + cst * STAGE;
+          PH_MARK(ph_w);
           mbar_wait(full + cst, cph);
-          if (lo < TM) run_panel(stage, stage + PANEL + t4 * LDT + col0 + g8, lo, TM, sc);
+          PH_ADD(ph_wait, ph_w);
+          bwd_panel_dispatch<TM, TN, WM, LDT, true>(c0, c1, stage, stage + PANEL + t4 * LDT + col0 + g8, sc, wm, g8, t4, lo < TM ? lo : 0, lo < TM ? TM : 0);
           __syncwarp();
           if (lane == 0) mbar_arrive(empty + cst);
           if (++cst == STAGES) { cst = 0; cph ^= 1; }
         }
       }
+      PH_ADD(ph_p0, ph_b);
+      PH_MARK(ph_c);
       // block end: + beta Gm^T + 2 V diag(gq); to the resident tile and to HBM
-      for (int d = 0; d < a.D_out; ++d) {
-        double gm0[TN], gm1[TN];
+      for (int d = 0; d < a.D_out; d += 2) {   // two outputs per round: 2 (2 TN + TM) independent loads in flight (L2 hits)
+        const bool two = d + 1 < a.D_out;
+        double gm0[2][TN], gm1[2][TN], bq[2][TM];
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
           const double* g = a.Gm + (p0 + j * 8 + 2 * t4) * a.gm_ld + d;
-          gm0[j] = g[0]; gm1[j] = g[a.gm_ld];
+          gm0[0][j] = g[0]; gm1[0][j] = g[a.gm_ld];
+          gm0[1][j] = two ? g[1] : 0.0; gm1[1][j] = two ? g[a.gm_ld + 1] : 0.0;
         }
 #pragma unroll
         for (int ti = 0; ti < TM; ++ti) {
-          const double b = a.beta[(long)(i * BM + ti * 8 * WM + wm * 8 + g8) * 32 + d];
-#pragma unroll
-          for (int j = 0; j < TN; ++j) { c0[ti][j] = fma(b, gm0[j], c0[ti][j]); c1[ti][j] = fma(b, gm1[j], c1[ti][j]); }
+          const double* b = a.beta + (long)(i * BM + ti * 8 * WM + wm * 8 + g8) * 32 + d;
+          bq[0][ti] = b[0]; bq[1][ti] = two ? b[1] : 0.0;
         }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int ti = 0; ti < TM; ++ti)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) { c0[ti][j] = fma(bq[u][ti], gm0[u][j], c0[ti][j]); c1[ti][j] = fma(bq[u][ti], gm1[u][j], c1[ti][j]); }
       }
+      if (i == 0) mbar_wait(vbar, (unsigned)(tl & 1));   // the V rows parked by the producer
 #pragma unroll
       for (int ti = 0; ti < TM; ++ti) {
         const int row = i * BM + ti * 8 * WM + wm * 8 + g8;
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
           const int cl = j * 8 + 2 * t4;                      // column inside the group
-          const long p = p0 + cl;
-          const double2 v = *reinterpret_cast<const double2*>(a.V + (long)row * a.Pp + p);
+          double2* tp = reinterpret_cast<double2*>(tile + row * LDT + col0 + cl);
+          const double2 v = *tp;
           const double r0 = fma(2.0 * v.x, gqs[cl], c0[ti][j]), r1 = fma(2.0 * v.y, gqs[cl + 1], c1[ti][j]);
-          *reinterpret_cast<double2*>(tile + row * LDT + col0 + cl) = make_double2(r0, r1);
-          *reinterpret_cast<double2*>(a.dV + (long)row * a.Pp + p) = make_double2(r0, r1);
+          *tp = make_double2(r0, r1);
+          *reinterpret_cast<double2*>(a.dV + (long)row * a.Pp + p0 + cl) = make_double2(r0, r1);
         }
       }
+      PH_ADD(ph_be, ph_c);
     }
+    PH_MARK(ph_d);
     group_sync(bar_id, GT);   // the group's columns of dV are complete
 
     // ---- pass 1: K-bar = Lu^-T dV, in place, row blocks ascending ----
+    const double sc1[TN] = {};
     for (int i = 0; i < nb; ++i) {
 #pragma unroll
       for (int ti = 0; ti < TM; ++ti)
@@ -252,7 +330,7 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
         const int hi = num >= 0 ? min(TM, num / (8 * WM) + 1) : 0;
         const double* stage = pbuf + cst * STAGE;
         mbar_wait(full + cst, cph);
-        if (hi > 0) run_panel(stage, tile + (ks * kPanelK + t4) * LDT + col0 + g8, 0, hi, nullptr);
+        bwd_panel_dispatch<TM, TN, WM, LDT, false>(c0, c1, stage, tile + (ks * kPanelK + t4) * LDT + col0 + g8, sc1, wm, g8, t4, 0, hi);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + cst);
         if (++cst == STAGES) { cst = 0; cph ^= 1; }
@@ -268,6 +346,8 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
       group_sync(bar_id, GT);
     }
 
+    PH_ADD(ph_p1, ph_d);
+    PH_MARK(ph_e);
     // ---- kernel adjoint on the resident K-bar tile ----
     // row sweep: one inducing row per thread; Gbar = K-bar * (-2 dk/dr2) in place, row-local sums for dl_j and ds2
     double dl[DMAX], ds2 = 0.0;
@@ -302,55 +382,96 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
         for (int c = 0; c < GC; ++c) trow[c] = 0.0;
       }
     }
+    PH_ADD(ph_row, ph_e);
+    PH_MARK(ph_f);
     // per-tile, per-group partial sums in a fixed order: warp shuffle tree, then the WM warps through shared memory
     {
-      double* pout = a.part + (tile_index * WN + wn) * (a.D_in + 1);
-      for (int j = 0; j <= a.D_in; ++j) {
-        double v = ds2 / s2;
+#pragma unroll
+      for (int j = 0; j < DMAX; ++j)
         if (j < a.D_in) {
-#pragma unroll
-          for (int jj = 0; jj < DMAX; ++jj)
-            if (jj == j) v = dl[jj] * (1.0 / a.ls[jj]);
+          const double v = warp_sum(dl[j] * (1.0 / a.ls[j]));
+          if (lane == 0) red[wm * (kMaxD + 1) + j] = v;
         }
-        v = warp_sum(v);
-        if (lane == 0) red[wm * 2 + (j & 1)] = v;
-        group_sync(bar_id, GT);
-        if (tg == 0) {
-          double s = 0.0;
-#pragma unroll
-          for (int w = 0; w < WM; ++w) s += red[w * 2 + (j & 1)];
-          pout[j] = s;
-        }
-      }
+      const double v = warp_sum(ds2 / s2);
+      if (lane == 0) red[wm * (kMaxD + 1) + a.D_in] = v;
     }
-    group_sync(bar_id, GT);   // Gbar rows of the group's columns are complete
+    group_sync(bar_id, GT);   // Gbar rows of the group's columns are complete; the warps' partial sums are in `red`
+    if (tg <= a.D_in) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < WM; ++w) s += red[w * (kMaxD + 1) + tg];
+      a.part[(tile_index * WN + wn) * (a.D_in + 1) + tg] = s;
+    }
+    PH_ADD(ph_red, ph_f);
+    PH_MARK(ph_g);
     // Gbar tile -> HBM (row segments of GC doubles)
     for (int idx = tg; idx < a.Mp * (GC / 2); idx += GT) {
       const int m = idx / (GC / 2), c2 = (idx % (GC / 2)) * 2;
       *reinterpret_cast<double2*>(a.Gbar + (long)m * a.Pp + p0 + c2) = *reinterpret_cast<const double2*>(tile + m * LDT + col0 + c2);
     }
-    // input gradient: dX[p][j] = (1/l_j) sum_m Gbar[m][p] (zs[m][j] - xs[p][j])  (+ mean-function path)
+    // input gradient: dX[p][j] = (1/l_j) sum_m Gbar[m][p] (zs[m][j] - xs[p][j])  (+ mean-function path).
+    // The scaled inducing inputs are staged through shared memory in chunks of kZChunk rows (a per-thread walk over all M rows
+    // would be bound by the L2 latency of its loads); the next chunk's values are in registers while the current one is used.
     if (a.dXin) {
-      for (int idx = tg; idx < GC * a.D_in; idx += GT) {
-        const int c = idx % GC, j = idx / GC;
-        const long p = p0 + c;
-        const double xv = xs[j * GC + c];
-        const double* tc = tile + col0 + c;
-        const double* zc = a.Zs + j;
-        double s0 = 0.0, s1 = 0.0;
-        int m = 0;
-        for (; m + 2 <= a.M; m += 2) {
-          s0 = fma(tc[m * LDT], zc[(long)m * a.D_in] - xv, s0);
-          s1 = fma(tc[(m + 1) * LDT], zc[(long)(m + 1) * a.D_in] - xv, s1);
+      constexpr int NO = 4;                         // (column, input dimension) outputs per thread and round
+      const int nout = GC * a.D_in;
+      for (int o0 = 0; o0 < nout; o0 += GT * NO) {
+        double acc[NO];
+#pragma unroll
+        for (int u = 0; u < NO; ++u) acc[u] = 0.0;
+        const int zn = kZChunk * a.D_in;            // doubles per chunk
+        double zpre[(kZChunk * kMaxD / 2 + 63) / 64];   // this thread's share of the next chunk (GT >= 64 threads)
+        auto fetch = [&](int m0) {
+#pragma unroll
+          for (int u = 0; u < (int)(sizeof(zpre) / sizeof(double)); ++u) {
+            const int e = tg + u * GT;
+            zpre[u] = (e < zn && m0 * a.D_in + e < a.M * a.D_in) ? a.Zs[(long)m0 * a.D_in + e] : 0.0;
+          }
+        };
+        fetch(0);
+        for (int m0 = 0; m0 < a.M; m0 += kZChunk) {
+          group_sync(bar_id, GT);                   // the previous chunk has been consumed
+#pragma unroll
+          for (int u = 0; u < (int)(sizeof(zpre) / sizeof(double)); ++u) {
+            const int e = tg + u * GT;
+            if (e < zn) zbuf[e] = zpre[u];
+          }
+          group_sync(bar_id, GT);
+          if (m0 + kZChunk < a.M) fetch(m0 + kZChunk);
+          const int rows = min(kZChunk, a.M - m0);
+#pragma unroll
+          for (int u = 0; u < NO; ++u) {
+            const int o = o0 + tg + u * GT;
+            if (o < nout) {
+              const int c = o % GC, j = o / GC;
+              const double xv = xs[j * GC + c];
+              const double* tc = tile + (size_t)m0 * LDT + col0 + c;
+              double s0 = 0.0, s1 = 0.0;
+              int r = 0;
+              for (; r + 2 <= rows; r += 2) {
+                s0 = fma(tc[r * LDT], zbuf[r * a.D_in + j] - xv, s0);
+                s1 = fma(tc[(r + 1) * LDT], zbuf[(r + 1) * a.D_in + j] - xv, s1);
+              }
+              if (r < rows) s0 = fma(tc[r * LDT], zbuf[r * a.D_in + j] - xv, s0);
+              acc[u] += s0 + s1;
+            }
+          }
         }
-        for (; m < a.M; ++m) s0 = fma(tc[m * LDT], zc[(long)m * a.D_in] - xv, s0);
-        if (p < a.P) {
-          double v = (s0 + s1) * (1.0 / a.ls[j]);
-          const double* gm = a.Gm + p * a.gm_ld;
-          if (a.mean_kind == 1) v += gm[j];
-          else if (a.mean_kind == 2)
-            for (int d = 0; d < a.D_out; ++d) v = fma(gm[d], a.mfW[j * a.D_out + d], v);
-          a.dXin[p * a.D_in + j] = v;
+#pragma unroll
+        for (int u = 0; u < NO; ++u) {
+          const int o = o0 + tg + u * GT;
+          if (o < nout) {
+            const int c = o % GC, j = o / GC;
+            const long p = p0 + c;
+            if (p < a.P) {
+              double v = acc[u] * (1.0 / a.ls[j]);
+              const double* gm = a.Gm + p * a.gm_ld;
+              if (a.mean_kind == 1) v += gm[j];
+              else if (a.mean_kind == 2)
+                for (int d = 0; d < a.D_out; ++d) v = fma(gm[d], a.mfW[j * a.D_out + d], v);
+              a.dXin[p * a.D_in + j] = v;
+            }
+          }
         }
       }
     }
@@ -362,7 +483,16 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
       if (p < a.P) v = jj < a.D_in ? a.Xin[(p % a.xmod) * a.D_in + jj] : (jj == a.D_in ? 1.0 : 0.0);
       a.XaugPad[p * 32 + jj] = v;
     }
+    PH_ADD(ph_out, ph_g);
   }
+#ifdef DGP_DEBUG_PHASECLK
+  if (lane == 0 && blockIdx.x == 1 && my_tiles > 10 && (warp == 0 || warp == 5)) {
+    const double tot = (double)(clock64() - ph_t0);
+    printf("fused_bwd cta %d warp %d (D_out %d, BM %d, tiles %d): total %.0f clk/tile | prologue %.1f%% pass0 %.1f%% (slab/panel waits %.1f%%) block-end %.1f%% pass1 %.1f%% row sweep %.1f%% reductions %.1f%% stores+dX %.1f%%\n",
+           blockIdx.x, warp, a.D_out, BM, my_tiles, tot / my_tiles, 100.0 * ph_pro / tot, 100.0 * ph_p0 / tot, 100.0 * ph_wait / tot, 100.0 * ph_be / tot,
+           100.0 * ph_p1 / tot, 100.0 * ph_row / tot, 100.0 * ph_red / tot, 100.0 * ph_out / tot);
+  }
+#endif
 }
 
 }  // namespace dgp
