@@ -882,6 +882,7 @@ struct RunOpts {
   ChunkIO io;
   // prediction outputs
   double* pm = nullptr; double* pv = nullptr; int add_lik = 0;   // mixture moments [N][D_L]
+  double* ve = nullptr;                                          // E_log_p_Y [N][D_L] (needs Y)
   double* ei = nullptr; double y_min = 0.0; int ei_analytic = 1; // -EI [N][D_L]
   bool need_last_sample = false;
   double* dx = nullptr;                                          // d sum(-EI) / dX [N][D0] (analytic EI only)
@@ -1099,6 +1100,11 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
       LAUNCH(mixture_moments_kernel, (unsigned)((ND + 255) / 256), 256, 0, clL.Fmean, clL.Fvar, S, ND, model->lik_variance,
              o.add_lik, o.pm + n0 * DL, o.pv + n0 * DL);
     }
+    if (o.ve) {
+      const long ND = Nc * DL;
+      LAUNCH(ve_mean_kernel, (unsigned)((ND + 255) / 256), 256, 0, clL.Fmean, clL.Fvar, o.Y + n0 * DL, model->lik_variance, Nc, S, DL,
+             o.ve + n0 * DL);
+    }
     if (o.ei && !o.dx) {
       const long ND = Nc * DL;
       if (o.ei_analytic) {
@@ -1252,7 +1258,7 @@ std::vector<unsigned char> graph_key(dgp_ctx* c, const dgp_model_desc* model, co
   }
   key_put(k, X); key_put(k, N); key_put(k, S); key_put(k, n_offset);
   key_put(k, o.want_grad); key_put(k, o.want_elbo); key_put(k, o.Y); key_put(k, o.Dy); key_put(k, o.scale); key_put(k, o.kl_weight);
-  key_put(k, o.out_flat); key_put(k, o.pm); key_put(k, o.pv); key_put(k, o.add_lik); key_put(k, o.ei); key_put(k, o.y_min);
+  key_put(k, o.out_flat); key_put(k, o.ve); key_put(k, o.pm); key_put(k, o.pv); key_put(k, o.add_lik); key_put(k, o.ei); key_put(k, o.y_min);
   key_put(k, o.ei_analytic); key_put(k, o.need_last_sample); key_put(k, o.dx); key_put(k, o.acq_kind); key_put(k, o.acq_add_lik);
   key_put(k, c->use_fused); key_put(k, c->use_vform); key_put(k, c->use_vform_grad); key_put(k, c->vform_forward_calls);
   key_put(k, c->vform_grad_min_ps); key_put(k, c->share_first_layer); key_put(k, c->parallel_layers); key_put(k, c->ws_limit);
@@ -1669,6 +1675,118 @@ int dgp_train_adam(dgp_ctx* c, const dgp_model_desc* model, const double* X, con
   return DGP_OK;
 }
 
+namespace {
+// One natural-gradient step on the listed layers from the gradients in grad_flat; all device work, batched over (layer, d).
+int natgrad_run(dgp_ctx* c, const dgp_model_desc* model, const int* layer_ids, int n_layers, double gamma, const double* grad_flat) {
+  std::vector<dgp_layer_grad_offsets> offs(model->num_layers);
+  dgp_grad_layout(model, offs.data());
+  std::vector<NatOut> outs;
+  int maxMp = 0, maxM = 0;
+  long off = 0;
+  for (int k = 0; k < n_layers; ++k) {
+    const int l = layer_ids[k];
+    if (l < 0 || l >= model->num_layers) { c->err = "natural gradient: layer index out of range"; return DGP_ERR_ARG; }
+    const dgp_layer_desc& d = model->layers[l];
+    RC(check_layer(c, d));
+    const int Mp = (int)round_up(d.M, kTileM);
+    for (int j = 0; j < d.D_out; ++j) {
+      NatOut o;
+      o.q_sqrt = d.q_sqrt + (long)j * d.M * d.M; o.q_sqrt_out = const_cast<double*>(o.q_sqrt);
+      o.g_sqrt = grad_flat + offs[l].dq_sqrt + (long)j * d.M * d.M;
+      o.g_mu = grad_flat + offs[l].dq_mu; o.q_mu = const_cast<double*>(d.q_mu);
+      o.M = d.M; o.Mp = Mp; o.D = d.D_out; o.d = j; o.off = off;
+      off += (long)Mp * Mp;
+      outs.push_back(o);
+    }
+    if (Mp > maxMp) maxMp = Mp;
+    if (d.M > maxM) maxM = d.M;
+  }
+  const int nout = (int)outs.size();
+  if (nout == 0) return DGP_OK;
+  double *R = walloc(c, off), *RT = walloc(c, off), *GR = walloc(c, off), *T = walloc(c, off), *Bf = walloc(c, off);
+  double *Lf = walloc(c, off), *Linv = walloc(c, off), *LinvT = walloc(c, off), *UinvT = walloc(c, off), *Cm = walloc(c, off);
+  NatOut* douts = reinterpret_cast<NatOut*>(walloc(c, (sizeof(NatOut) * nout + 7) / 8));
+  CholArgs* dargs = reinterpret_cast<CholArgs*>(walloc(c, (sizeof(CholArgs) * nout + 7) / 8));
+  double** dinv = reinterpret_cast<double**>(walloc(c, (size_t)nout));
+  double** dinvT = reinterpret_cast<double**>(walloc(c, (size_t)nout));
+  if (c->dry) return DGP_OK;
+  std::vector<CholArgs> hargs(nout);
+  std::vector<double*> hinv(nout), hinvT(nout);
+  for (int i = 0; i < nout; ++i) {
+    hargs[i] = CholArgs{Bf + outs[i].off, Lf + outs[i].off, nullptr, nullptr, outs[i].Mp, c->d_info};
+    hinv[i] = Linv + outs[i].off; hinvT[i] = LinvT + outs[i].off;
+  }
+  CAT(DGP_CAT_PREP);
+  H2D(douts, outs.data(), sizeof(NatOut) * nout);
+  H2D(dargs, hargs.data(), sizeof(CholArgs) * nout);
+  H2D(dinv, hinv.data(), sizeof(double*) * nout);
+  H2D(dinvT, hinvT.data(), sizeof(double*) * nout);
+  const unsigned gx = (unsigned)(((long)maxMp * maxMp + 255) / 256);
+  LAUNCH(natgrad_prep_kernel, dim3(gx, (unsigned)nout), 256, 0, douts, R, RT, GR);
+  for (int i = 0; i < nout; ++i) {   // T = R^T G_R (outputs of one layer share Mp; one launch per output keeps the shapes exact)
+    const NatOut& o = outs[i];
+    GemmArgs g = gargs(RT + o.off, o.Mp, GR + o.off, o.Mp, T + o.off, o.Mp, o.Mp, o.Mp, o.Mp);
+    g.a_tri = 2;
+    RC(gemm(c, g, false));
+  }
+  LAUNCH(natgrad_b_kernel, dim3(gx, (unsigned)nout), 256, 0, douts, T, gamma, Bf);
+  if (!c->chol_configured) {
+    CK(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem_bytes(768)));
+    c->chol_configured = true;
+  }
+  LAUNCH(chol_inv_kernel, nout, kCholThreads, chol_smem_bytes(maxMp), dargs);
+  CK(cudaFuncSetAttribute(tri_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_inv_smem_bytes(768)));
+  LAUNCH(tri_inv_kernel, dim3((unsigned)(maxMp / 32), (unsigned)nout), 256, tri_inv_smem_bytes(maxMp), dargs, dinv, dinvT);
+  LAUNCH(natgrad_flip_kernel, dim3(gx, (unsigned)nout), 256, 0, douts, LinvT, UinvT);
+  for (int i = 0; i < nout; ++i) {   // C = R U^-T (lower x lower)
+    const NatOut& o = outs[i];
+    GemmArgs g = gargs(R + o.off, o.Mp, UinvT + o.off, o.Mp, Cm + o.off, o.Mp, o.Mp, o.Mp, o.Mp);
+    g.a_tri = 1;
+    RC(gemm(c, g, false));
+  }
+  LAUNCH(natgrad_finalize_kernel, nout, 256, 2 * (size_t)maxM * sizeof(double), douts, Cm, gamma, c->d_info);
+  return DGP_OK;
+}
+
+int natgrad_planned(dgp_ctx* c, const dgp_model_desc* model, const int* layer_ids, int n_layers, double gamma, const double* grad_flat) {
+  c->dry = true; c->used = 0;
+  int rc = natgrad_run(c, model, layer_ids, n_layers, gamma, grad_flat);
+  c->dry = false;
+  if (rc != DGP_OK) return rc;
+  RC(ensure_ws(c, c->used));
+  c->used = 0;
+  return natgrad_run(c, model, layer_ids, n_layers, gamma, grad_flat);
+}
+}  // namespace
+
+int dgp_natgrad_step(dgp_ctx* c, const dgp_model_desc* model, const int* layer_ids, int n_layers, double gamma,
+                     const double* grad_flat) {
+  if (!c || !model || !layer_ids || n_layers < 0 || !grad_flat) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  return natgrad_planned(c, model, layer_ids, n_layers, gamma, grad_flat);
+}
+
+int dgp_train_nat_adam(dgp_ctx* c, const dgp_model_desc* model, const double* X, const double* Y, int64_t N, int64_t S, double scale,
+                       double kl_weight, uint64_t seed0, uint64_t seed_stride, int64_t n_offset, const dgp_adam_param* params,
+                       int n_params, double* m_state, double* v_state, int64_t t0, int64_t steps, double lr, double beta1,
+                       double beta2, double epsilon, const int* nat_layers, int n_nat, double gamma, double* out_flat,
+                       double* elbo_trace) {
+  if (!c || !model || !X || !Y || !out_flat || !m_state || !v_state || !nat_layers || t0 < 1 || steps < 0) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  AdamTable tab;
+  const bool have_adam = n_params > 0;
+  if (have_adam) RC(adam_table(c, params, n_params, tab));
+  for (int64_t k = 0; k < steps; ++k) {
+    // models/dgp.py:338-343: Adam step on the non-variational parameters, then NaturalGradient.minimize with a FRESH evaluation
+    RC(dgp_elbo_grad(c, model, X, Y, N, S, scale, kl_weight, nullptr, seed0 + (uint64_t)(2 * k) * seed_stride, n_offset, 1, out_flat));
+    if (have_adam) RC(adam_launch(c, tab, out_flat, m_state, v_state, t0 + k, lr, beta1, beta2, epsilon, elbo_trace ? elbo_trace + k : nullptr));
+    else if (elbo_trace) LAUNCH(scale_copy_diff_kernel, 1, 32, 0, out_flat, elbo_trace + k);
+    RC(dgp_elbo_grad(c, model, X, Y, N, S, scale, kl_weight, nullptr, seed0 + (uint64_t)(2 * k + 1) * seed_stride, n_offset, 1, out_flat));
+    RC(natgrad_planned(c, model, nat_layers, n_nat, gamma, out_flat));
+  }
+  return DGP_OK;
+}
+
 int dgp_elbo_grad_host(dgp_ctx* c, const dgp_model_desc* model, const double* X_host, const double* Y_host, int64_t N,
                        int64_t S, double scale, double kl_weight, uint64_t seed, int64_t n_offset, int want_grad,
                        double* out_flat_host) {
@@ -1709,6 +1827,15 @@ int dgp_predict_moments(dgp_ctx* c, const dgp_model_desc* model, const double* X
   if (add_lik_var && !model->lik_variance) { c->err = "lik_variance is null"; return DGP_ERR_ARG; }
   RunOpts o;
   o.io.zs = zs_host; o.pm = mean; o.pv = var; o.add_lik = add_lik_var;
+  return run_model_planned(c, model, X, N, S, seed, n_offset, o);
+}
+
+int dgp_e_log_p_y(dgp_ctx* c, const dgp_model_desc* model, const double* X, const double* Y, int64_t N, int64_t S,
+                  const double* const* zs_host, uint64_t seed, int64_t n_offset, double* out) {
+  if (!c || !model || !X || !Y || !out) return DGP_ERR_ARG;
+  if (!model->lik_variance) { c->err = "lik_variance is null"; return DGP_ERR_ARG; }
+  RunOpts o;
+  o.io.zs = zs_host; o.ve = out; o.Y = Y; o.Dy = model->layers[model->num_layers - 1].D_out;
   return run_model_planned(c, model, X, N, S, seed, n_offset, o);
 }
 

@@ -230,6 +230,23 @@ __global__ void __launch_bounds__(128) likelihood_kernel(const double* __restric
   }
 }
 
+// DGP_Base.E_log_p_Y (models/dgp.py:79-87): mean over the S samples of the Gaussian variational expectations
+// (utils/utils.py:89-93), one value per point and output. Chunk-local moments [S * Nc][D] with p = s * Nc + n.
+__global__ void __launch_bounds__(256) ve_mean_kernel(const double* __restrict__ Fmean, const double* __restrict__ Fvar,
+                                                      const double* __restrict__ Y, const double* __restrict__ likvar, long Nc,
+                                                      long S, int D, double* __restrict__ out) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Nc * D) return;
+  const double sn2 = likvar[0], y = Y[idx];
+  const double c0 = -0.91893853320467274178 - 0.5 * log(sn2);
+  double acc = 0.0;
+  for (long s = 0; s < S; ++s) {
+    const double r = y - Fmean[s * Nc * D + idx];
+    acc += c0 - 0.5 * fma(r, r, Fvar[s * Nc * D + idx]) / sn2;
+  }
+  out[idx] = acc / (double)S;
+}
+
 // Hidden layer: G_F = d ELBO / d F (the next layer's input gradient); F = mean + z sqrt(var + jitter)
 //   Gm = G_F, Gv = G_F z / (2 sqrt(var + jitter))          (adjoint of utils/utils.py:40-41)
 __global__ void __launch_bounds__(128) upstream_kernel(const double* __restrict__ GF, const double* __restrict__ z,

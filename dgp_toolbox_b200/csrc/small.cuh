@@ -201,6 +201,10 @@ __global__ void scale_copy_kernel(const double* in, double s, double* out) {
   if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = s * in[0];
 }
 
+__global__ void scale_copy_diff_kernel(const double* flat, double* out) {   // ELBO estimate = data term - KL
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = flat[0] - flat[1];
+}
+
 // Copies the leading [M][M] block of a padded [Mp][Mp] matrix.
 __global__ void unpad_square_kernel(const double* __restrict__ in, int M, int Mp, double* __restrict__ out) {
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -263,6 +267,94 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamTable t, const double* __
   sg.value[i] = out;
   if (sg.mirror)
     for (long j = 0; j < sg.mirror_count; ++j) sg.mirror[j] = out;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// GPflow NaturalGradient(gamma) step on (q_mu, q_sqrt) pairs, XiNat parameterisation (models/dgp.py:188,218,312,343), in
+// collapsed form: with R = q_sqrt_d, G_R / G_mu the gradients of -ELBO, T = tril(R^T G_R),
+//   B = I + gamma (T + T^T - diag T) = U U^T (reverse Cholesky, U upper),  q_sqrt_new = R U^-T,  mu_new = mu - gamma C C^T G_mu.
+// One "output" = one (layer, d) pair; all outputs of a call are batched. The reverse Cholesky is an ordinary one of the
+// flipped matrix: with J the index reversal, J B J = Lf Lf^T, U = J Lf J, U^-T = J Lf^-T J.
+// ---------------------------------------------------------------------------------------------------------
+struct NatOut {              // one (layer, d) pair
+  const double* q_sqrt;      // [M][M] block d of the layer's q_sqrt (lower)
+  const double* g_sqrt;      // [M][M] d ELBO / d q_sqrt_d inside the flat gradient buffer
+  const double* g_mu;        // d ELBO / d q_mu, [M][D] (column d used)
+  double* q_mu;              // [M][D] updated in place (column d)
+  double* q_sqrt_out;        // == q_sqrt, updated in place
+  int M, Mp, D, d;
+  long off;                  // offset of this output's [Mp][Mp] matrices inside the batched work arrays
+};
+
+// RT = R^T (upper, padded), R (lower, padded), GR = -tril(dELBO/dq_sqrt) (padded)
+__global__ void natgrad_prep_kernel(const NatOut* __restrict__ outs, double* __restrict__ R, double* __restrict__ RT,
+                                    double* __restrict__ GR) {
+  const NatOut o = outs[blockIdx.y];
+  const long mm = (long)o.Mp * o.Mp;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < mm; idx += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / o.Mp), j = (int)(idx % o.Mp);
+    const bool in = i < o.M && j < o.M && j <= i;
+    const double r = in ? o.q_sqrt[(long)i * o.M + j] : 0.0;
+    R[o.off + idx] = r;
+    RT[o.off + (long)j * o.Mp + i] = r;
+    GR[o.off + idx] = in ? -o.g_sqrt[(long)i * o.M + j] : 0.0;
+  }
+}
+
+// Bf = J (I + gamma (T_low + T_low^T - diag T)) J on the leading M x M block, identity on the padding
+__global__ void natgrad_b_kernel(const NatOut* __restrict__ outs, const double* __restrict__ T, double gamma, double* __restrict__ Bf) {
+  const NatOut o = outs[blockIdx.y];
+  const long mm = (long)o.Mp * o.Mp;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < mm; idx += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / o.Mp), j = (int)(idx % o.Mp);
+    double v = i == j ? 1.0 : 0.0;
+    if (i < o.M && j < o.M) {
+      const int a = o.M - 1 - i, b = o.M - 1 - j;          // un-flipped indices
+      const int hi = a > b ? a : b, lo = a > b ? b : a;
+      v += gamma * T[o.off + (long)hi * o.Mp + lo];         // lower triangle of T, mirrored; the diagonal once
+    }
+    Bf[o.off + idx] = v;
+  }
+}
+
+// UinvT = J Lf^-T J (lower) on the leading block, zero elsewhere
+__global__ void natgrad_flip_kernel(const NatOut* __restrict__ outs, const double* __restrict__ LfinvT, double* __restrict__ UinvT) {
+  const NatOut o = outs[blockIdx.y];
+  const long mm = (long)o.Mp * o.Mp;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < mm; idx += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / o.Mp), j = (int)(idx % o.Mp);
+    // only the upper triangle of Lf^-T is defined (tri_inv_kernel leaves the rest of the plane untouched)
+    UinvT[o.off + idx] = (i < o.M && j <= i) ? LfinvT[o.off + (long)(o.M - 1 - i) * o.Mp + (o.M - 1 - j)] : 0.0;
+  }
+}
+
+// one CTA per output: w = C^T g (g = -dELBO/dq_mu[:, d]), q_mu[:, d] -= gamma C w, q_sqrt_d = tril(C)
+__global__ void __launch_bounds__(256) natgrad_finalize_kernel(const NatOut* __restrict__ outs, const double* __restrict__ C, double gamma,
+                                                               const int* __restrict__ failed) {
+  extern __shared__ double nsh[];   // g [M], w [M]
+  const NatOut o = outs[blockIdx.x];
+  if (failed && *failed) return;    // a factorisation failed (here or in the ELBO): keep the last good values
+  double* g = nsh;
+  double* w = nsh + o.M;
+  const double* Cm = C + o.off;
+  for (int i = threadIdx.x; i < o.M; i += blockDim.x) g[i] = -o.g_mu[(long)i * o.D + o.d];
+  __syncthreads();
+  for (int j = threadIdx.x; j < o.M; j += blockDim.x) {      // w_j = sum_{i >= j} C[i][j] g_i   (C lower)
+    double s = 0.0;
+    for (int i = j; i < o.M; ++i) s = fma(Cm[(long)i * o.Mp + j], g[i], s);
+    w[j] = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < o.M; i += blockDim.x) {      // (C w)_i = sum_{j <= i} C[i][j] w_j
+    double s = 0.0;
+    for (int j = 0; j <= i; ++j) s = fma(Cm[(long)i * o.Mp + j], w[j], s);
+    o.q_mu[(long)i * o.D + o.d] -= gamma * s;
+  }
+  for (long idx = threadIdx.x; idx < (long)o.M * o.M; idx += blockDim.x) {
+    const int i = (int)(idx / o.M), j = (int)(idx % o.M);
+    o.q_sqrt_out[idx] = j <= i ? Cm[(long)i * o.Mp + j] : 0.0;
+  }
 }
 
 }  // namespace dgp

@@ -143,6 +143,8 @@ class SquaredExponential(_Module):
 
     def lengthscales_vector(self, D):
         ls = self.lengthscales.value.reshape(-1)
+        if ls.numel() == 1 and D == 1 and ls.is_contiguous():
+            return ls      # a view of the parameter itself: in-library optimiser loops update it in place, no mirror needed
         if ls.numel() == 1:
             # the C ABI takes one lengthscale per input column; the expansion lives in one buffer per kernel object so that
             # its address is stable from call to call (graph replay, dgp_adam_param.mirror)

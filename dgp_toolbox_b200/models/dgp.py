@@ -121,10 +121,19 @@ class DGP_Base(_Module):
 
     # ------------------------------------------------------------------ a8-a10: ELBO and its gradient
     def E_log_p_Y(self, X, Y, zs=None, seed=None):
-        """dgp.py:79-87 -> [N, D]."""
-        Fmean, Fvar = self.predict_f(X, S=self.num_samples, zs=zs, seed=seed)
+        """dgp.py:79-87 -> [N, D]: one dgp_e_log_p_y call (chain + Gaussian variational expectations + mean over S in-library)."""
+        X = _lib.as_device(X, self.device)
         Y = _lib.as_device(Y, self.device)
-        return self.likelihood.variational_expectations(Fmean, Fvar, Y).mean(0)
+        self._check_XY(X, Y)
+        N, S = X.shape[0], self.num_samples
+        out = torch.empty((N, self.layers[-1].num_outputs), dtype=torch.float64, device=X.device)
+        if N == 0:
+            return out
+        m, keep = self._model_desc()
+        zt, zp = self._zs(zs, S, N)
+        _lib.get_context(X.device).call("dgp_e_log_p_y", C.byref(m), _lib.ptr(X), _lib.ptr(Y), N, S, zp, self._next_seed(seed), 0,
+                                        _lib.ptr(out))
+        return out
 
     def grad_layout(self):
         m, keep = self._model_desc()
@@ -351,26 +360,50 @@ class DGP_Base(_Module):
             S_new^-1 = S^-1 + 2 gamma dS = R^-T (I + 2 gamma P) R^-1,      mu_new = mu - gamma S_new G_mu,
         so with the reverse Cholesky I + 2 gamma P = U U^T (U upper) the new factor is q_sqrt_new = R U^-T (lower times lower, positive
         diagonal: the Cholesky factor of S_new) and mu_new = mu - gamma q_sqrt_new q_sqrt_new^T G_mu -- one triangular product, one
-        M x M Cholesky and one triangular solve per output, no explicit inverse of S. The ELBO gradient comes from one dgp_elbo_grad
-        call; this O(D_out M^3) re-parameterisation is host-side glue (batched torch.linalg on the device), like the optimiser
-        math of the reference. Checked against the oracle, which takes d/d eta by autograd through the expectation parameters."""
+        M x M Cholesky and one triangular inverse per output, no explicit inverse of S. The ELBO gradient comes from one dgp_elbo_grad
+        call and the update from one dgp_natgrad_step call (batched over layers and outputs in the library's own kernels; no
+        torch.linalg). Checked against the oracle, which takes d/d eta by autograd through the expectation parameters."""
         flat = self.elbo_flat(data, want_grad=True, scale=scale, seed=seed, zs=zs, out=out)
-        grads = self.unpack_grads(flat)
-        for q_mu, q_sqrt in variational_params:
-            mu = q_mu.value                                    # [M, D]
-            R = torch.tril(q_sqrt.value)                       # [D, M, M]
-            Gmu = -grads[q_mu]                                 # d loss / d mu, loss = -ELBO
-            GR = -torch.tril(grads[q_sqrt])                    # d loss / d R
-            T = torch.tril(R.transpose(1, 2) @ GR)
-            # I + 2 gamma sym(Phi(T)),  Phi = lower triangle with halved diagonal
-            B = gamma * (T + T.transpose(1, 2) - torch.diag_embed(torch.diagonal(T, dim1=1, dim2=2)))
-            B.diagonal(dim1=1, dim2=2).add_(1.0)
-            U = torch.linalg.cholesky_ex(B.flip(-1, -2)).L.flip(-1, -2)          # reverse Cholesky: B = U U^T, U upper
-            C = torch.linalg.solve_triangular(U.transpose(1, 2), R, upper=False, left=False)   # C U^T = R
-            w = C.transpose(1, 2) @ Gmu.T.unsqueeze(-1)        # [D, M, 1]
-            q_mu.assign(mu - gamma * (C @ w).squeeze(-1).T)
-            q_sqrt.assign(torch.tril(C))
+        m, keep = self._model_desc()
+        ids = self._nat_layer_ids(variational_params)
+        _lib.get_context(self.device).call("dgp_natgrad_step", C.byref(m), ids, len(ids), float(gamma), _lib.ptr(flat))
         return flat[0] - flat[1]
+
+    def _nat_layer_ids(self, variational_params):
+        """[(q_mu, q_sqrt), ...] (the reference's var_list) -> C int array of layer indices."""
+        idx = []
+        for pair in variational_params:
+            q_mu, q_sqrt = pair[0], pair[1]
+            hit = [i for i, l in enumerate(self.layers) if l.q_mu is q_mu and l.q_sqrt is q_sqrt]
+            if not hit:
+                raise ValueError("natural-gradient pairs must be the (q_mu, q_sqrt) of this model's layers")
+            idx.append(hit[0])
+        return (C.c_int * len(idx))(*idx)
+
+    def _train_nat_adam(self, data, params, state, t0, steps, lr, beta_1, beta_2, epsilon, variational_params, gamma, scale=1.0,
+                        kl_weight=1.0):
+        """`steps` iterations of part 2 of optimize_nat_adam in one dgp_train_nat_adam call; returns the per-iteration ELBO estimates."""
+        X, Y = data
+        X = _lib.as_device(X, self.device)
+        Y = _lib.as_device(Y, self.device)
+        self._check_XY(X, Y)
+        if steps <= 0:
+            return torch.empty(0, dtype=torch.float64, device=X.device)
+        m, keep = self._model_desc()
+        arr, keep2 = self._adam_params(params) if params else (None, [])
+        n = int(_lib.lib.dgp_grad_size(C.byref(m)))
+        if getattr(self, "_train_flat", None) is None or self._train_flat.numel() != n or self._train_flat.device != X.device:
+            self._train_flat = torch.empty(n, dtype=torch.float64, device=X.device)
+        trace = torch.empty(steps, dtype=torch.float64, device=X.device)
+        ids = self._nat_layer_ids(variational_params)
+        seed0 = self._next_seed(None)
+        self._draw += 2 * steps - 1
+        _lib.get_context(X.device).call("dgp_train_nat_adam", C.byref(m), _lib.ptr(X), _lib.ptr(Y), X.shape[0], self.num_samples,
+                                        float(scale), float(kl_weight), seed0, 0x9E3779B97F4A7C15, 0, arr, len(params),
+                                        _lib.ptr(state[0]), _lib.ptr(state[1]), int(t0), int(steps), float(lr), float(beta_1),
+                                        float(beta_2), float(epsilon), ids, len(ids), float(gamma), _lib.ptr(self._train_flat),
+                                        _lib.ptr(trace))
+        return trace
 
     def optimize_nat_adam(self, data, iterations1=100, iterations2=5000, lr_adam=0.01, lr_gamma=0.01, beta_1=0.9, beta_2=0.999,
                           epsilon=1e-07, ng_all=True, messages=100):
@@ -386,21 +419,22 @@ class DGP_Base(_Module):
         self._adam_loop(data, params, state, 1, iterations1, lr_adam, beta_1, beta_2, epsilon, messages)
         ctx = _lib.get_context(self.device)
         X = _lib.as_device(data[0], self.device)
-        data = (X, _lib.as_device(data[1], self.device))      # one device copy and one result buffer: stable addresses
-        buf = torch.empty(self.grad_layout()[0], dtype=torch.float64, device=X.device)
+        data = (X, _lib.as_device(data[1], self.device))      # one device copy: stable addresses for graph replay
         auto_graph = not ctx.graph and X.shape[0] * self.num_samples <= 32768
         if auto_graph:
             ctx.set_graph(True)
         try:
-            t = iterations1
-            for step in range(iterations2):
-                flat = self.elbo_flat(data, want_grad=True, out=buf)
-                t += 1
-                self._adam_step(params, flat, state, t, lr_adam, beta_1, beta_2, epsilon)
-                if step % messages == 0:
-                    print(f"ELBO: {(flat[0] - flat[1]).item()}")
+            # part 2 in blocks that end on the iterations the reference prints at (step % messages == 0); the whole block
+            # (two ELBO+gradient evaluations, Adam and natural-gradient launches per iteration) runs in the library
+            step = 0
+            while step < iterations2:
+                n = 1 if step == 0 else min(messages, iterations2 - step)
+                trace = self._train_nat_adam(data, params, state, iterations1 + 1 + step, n, lr_adam, beta_1, beta_2, epsilon,
+                                             variational_params, lr_gamma)
+                step += n
+                if (step - 1) % messages == 0:
+                    print(f"ELBO: {trace[-1].item()}")
                     ctx.check()
-                self.natgrad_step(data, lr_gamma, variational_params, out=buf)
             ctx.check()
         finally:
             if auto_graph:

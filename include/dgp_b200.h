@@ -176,6 +176,26 @@ int dgp_train_adam(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, c
                    int n_params, double* m_state, double* v_state, int64_t t0, int64_t steps, double lr, double beta1,
                    double beta2, double epsilon, double* out_flat, double* elbo_trace);
 
+/* GPflow NaturalGradient(gamma).minimize on the (q_mu, q_sqrt) pairs of the listed layers (models/dgp.py:188,218,312,343; default
+ * XiNat parameterisation: theta <- theta - gamma d(-ELBO)/d eta, theta = (S^-1 mu, -S^-1/2), eta = (mu, S + mu mu^T), S = q_sqrt
+ * q_sqrt^T), from the gradients a dgp_elbo_grad call left in grad_flat. Collapsed form, per output d: T = tril(q_sqrt_d^T G_R),
+ * I + gamma (T + T^T - diag T) = U U^T (reverse Cholesky), q_sqrt_d <- q_sqrt_d U^-T, q_mu_d <- q_mu_d - gamma q_sqrt_d q_sqrt_d^T G_mu;
+ * all on the device (batched over layers and outputs: triangular DMMA products, the Cholesky / triangular-inverse kernels of a1).
+ * layer_ids: HOST array. The layers' q_mu / q_sqrt arrays are updated in place; nothing is written when a factorisation failed
+ * (dgp_check reports it). */
+int dgp_natgrad_step(dgp_ctx* ctx, const dgp_model_desc* model, const int* layer_ids, int n_layers, double gamma,
+                     const double* grad_flat);
+
+/* `steps` iterations of part 2 of the reference's optimize_nat_adam (models/dgp.py:206-220,331-345) without returning to the host:
+ * iteration k runs dgp_elbo_grad(seed0 + 2k seed_stride) + dgp_adam_step(t0 + k) on `params` (the non-variational parameters; n_params
+ * may be 0), then dgp_elbo_grad(seed0 + (2k+1) seed_stride) + dgp_natgrad_step(nat_layers, gamma) -- two evaluations per iteration,
+ * as NaturalGradient.minimize re-evaluates the objective. elbo_trace[k] = the first evaluation's ELBO estimate. */
+int dgp_train_nat_adam(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, const double* Y, int64_t N, int64_t S, double scale,
+                       double kl_weight, uint64_t seed0, uint64_t seed_stride, int64_t n_offset, const dgp_adam_param* params,
+                       int n_params, double* m_state, double* v_state, int64_t t0, int64_t steps, double lr, double beta1,
+                       double beta2, double epsilon, const int* nat_layers, int n_nat, double gamma, double* out_flat,
+                       double* elbo_trace);
+
 /* Value and input gradient of a moment-based criterion (the gradient the reference's Adam-on-x stage takes with tape.gradient,
  * Infill_criteria.py:79-84,160-165): kind 0 = -EI on predict_f moments (== dgp_ei_grad), 1 = WB2 = -(EI - mean) and 2 = EV =
  * (mean - y) Phi + s phi, both on predict_y moments (+ sigma_n^2, Infill_criteria.py:124-133,249-257). value [N, D_L],
@@ -208,6 +228,11 @@ int dgp_adam_box_step(dgp_ctx* ctx, double* u, double* m_state, double* v_state,
 int dgp_predict_moments(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, int64_t N, int64_t S,
                         const double* const* zs_host, uint64_t seed, int64_t n_offset, int add_lik_var,
                         double* mean, double* var);
+
+/* DGP_Base.E_log_p_Y (models/dgp.py:79-87): out [N, D_L] = mean over the S samples of the Gaussian variational expectations
+ * (-0.5 log 2pi - 0.5 log s_n^2 - 0.5 ((Y - mu)^2 + var) / s_n^2, utils/utils.py:89-93) of the last layer's moments. */
+int dgp_e_log_p_y(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, const double* Y, int64_t N, int64_t S,
+                  const double* const* zs_host, uint64_t seed, int64_t n_offset, double* out);
 
 /* EI.run for a DGP (Infill_criteria.py:36-52): returns -EI [N,1]. analytic != 0: moment-matched closed form;
  * analytic == 0: Monte-Carlo mean_s max(y_min - F, 0) on the propagated samples. */

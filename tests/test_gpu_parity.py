@@ -243,6 +243,75 @@ def test_natural_gradient_step_matches_oracle():
         assert rel_err(layer.q_sqrt.value, R_o) < 1e-8
 
 
+@pytest.mark.parametrize("shape", [(5, [3, 6], 70, 33, 3, 0.05), (2, [2], 130, 21, 2, 1e-3)])
+def test_natural_gradient_step_in_library_wide_and_padded(shape):
+    """dgp_natgrad_step on layers with several outputs, M not a multiple of the 64-row padding, a larger step, and a subset of the
+    layers (ng_all=False of models/dgp.py:198-201 updates the last layer only)."""
+    D0, units, M, N, S, gamma = shape
+    prob, om, pm = both_models(D0, units, M, N, S)
+    zs = oracle_zs(om, N, S, 5)
+    X, Y = torch.as_tensor(prob["X"]), torch.as_tensor(prob["Y"])
+    last = len(om.layers) - 1
+    before = [l.q_sqrt.value.clone() for l in pm.layers]
+    (mu_o, R_o), = O.natgrad_step(om, X, Y, zs, gamma, [last])
+    pm.natgrad_step((prob["X"], prob["Y"]), gamma, [(pm.layers[-1].q_mu, pm.layers[-1].q_sqrt)], zs=zs)
+    assert rel_err(pm.layers[-1].q_mu.value, mu_o) < 1e-8 and rel_err(pm.layers[-1].q_sqrt.value, R_o) < 1e-8
+    for l, b in zip(pm.layers[:-1], before[:-1]):
+        assert torch.equal(l.q_sqrt.value, b)                      # the other layers are untouched
+    new = O.natgrad_step(om, X, Y, zs, gamma, list(range(last + 1)))
+    prob2, om2, pm2 = both_models(D0, units, M, N, S)
+    pm2.natgrad_step((prob["X"], prob["Y"]), gamma, [(l.q_mu, l.q_sqrt) for l in pm2.layers], zs=zs)
+    for (mu_o, R_o), layer in zip(new, pm2.layers):
+        assert rel_err(layer.q_mu.value, mu_o) < 1e-8 and rel_err(layer.q_sqrt.value, R_o) < 1e-8
+
+
+@pytest.mark.parametrize("dims", [(3, [3], 24, 40, 4), (1, [1, 1], 25, 50, 10)])
+def test_nat_adam_loop_in_library_matches_stepwise_calls(dims):
+    """dgp_train_nat_adam (part 2 of optimize_nat_adam, models/dgp.py:331-345, in one call) == the same iterations issued one
+    C-ABI call at a time (elbo_flat + dgp_adam_step, then elbo_flat + dgp_natgrad_step), bit for bit, with and without graph replay.
+    The 1-D case is the notebook's shape (one lengthscale per kernel: the descriptor must point at the parameter itself, not at
+    a broadcast copy that an in-library loop would leave stale)."""
+    import dgp_toolbox_b200 as D
+    results = []
+    gamma = 0.05 if dims[0] == 3 else 1e-3      # the 1-D problem's gradients are large: a bigger step leaves the PD cone
+    for mode in ("stepwise", "library", "library+graph"):
+        prob, om, pm = both_models(*dims)
+        data = (torch.as_tensor(prob["X"]).cuda(), torch.as_tensor(prob["Y"]).cuda())
+        for l in pm.layers:
+            D.gpflow.set_trainable(l.q_mu, False)
+            D.gpflow.set_trainable(l.q_sqrt, False)
+        vp = [(l.q_mu, l.q_sqrt) for l in pm.layers]
+        params = pm.trainable_parameters
+        state = pm._adam_state(params)
+        ctx = D._lib.get_context(0)
+        if mode == "stepwise":
+            for k in range(3):
+                flat = pm.elbo_flat(data, want_grad=True)
+                pm._adam_step(params, flat, state, k + 1, 0.01, 0.9, 0.999, 1e-7)
+                pm.natgrad_step(data, gamma, vp)
+        else:
+            ctx.set_graph(mode.endswith("graph"))
+            try:
+                trace = pm._train_nat_adam(data, params, state, 1, 3, 0.01, 0.9, 0.999, 1e-7, vp, gamma)
+                assert bool(torch.isfinite(trace).all())
+            finally:
+                ctx.set_graph(False)
+        ctx.check()
+        results.append([p.value.clone() for p in pm.parameters])
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            assert torch.equal(a, b)
+
+
+def test_e_log_p_y_matches_oracle():
+    """DGP_Base.E_log_p_Y (models/dgp.py:79-87) through dgp_e_log_p_y."""
+    prob, om, pm = both_models(5, [3, 6], 40, 37, 3)
+    zs = oracle_zs(om, 37, 3, 2)
+    ref = O.E_log_p_Y(om, torch.as_tensor(prob["X"]), torch.as_tensor(prob["Y"]), zs)
+    got = pm.E_log_p_Y(prob["X"], prob["Y"], zs=zs)
+    assert tuple(got.shape) == tuple(ref.shape) and rel_err(got, ref) < TOL
+
+
 @pytest.mark.parametrize("isotropic", [False, True])
 def test_adam_steps_match_oracle_tf_adam(isotropic):
     """dgp_adam_step (one launch: bijector inverse, chain rule, Adam, bijector) against the oracle's tf.optimizers.Adam on
