@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "fused.cuh"
 #include "fused_bwd.cuh"
+#include "fullcov.cuh"
 #include "gemm.cuh"
 #include "layer.cuh"
 #include "philox.cuh"
@@ -1580,6 +1581,104 @@ int dgp_propagate(dgp_ctx* c, const dgp_model_desc* model, const double* X, int6
   RunOpts o;
   o.io.zs = zs_host; o.io.Fs = Fs_host; o.io.Fmeans = Fmeans_host; o.io.Fvars = Fvars_host;
   RC(run_model_planned(c, model, X, N, S, seed, n_offset, o));
+  return check_chol(c);
+}
+
+namespace {
+// propagate(full_cov=True): per layer the fused conditional (V-form, stash on) gives mean, V and T_d for all S samples at once;
+// the S * D_out covariance blocks, their Cholesky factors and the correlated samples follow (fullcov.cuh).
+int run_full_cov(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, long S, const double* const* zs_host,
+                 unsigned long long seed, long n_offset, double* const* Fs_host, double* const* Fmeans_host,
+                 double* const* Fvars_host) {
+  const int nl = model->num_layers;
+  if (nl < 1 || N < 1 || S < 1) { c->err = "need num_layers >= 1, N >= 1, S >= 1"; return DGP_ERR_ARG; }
+  for (int l = 1; l < nl; ++l)
+    if (model->layers[l].D_in != model->layers[l - 1].D_out) { c->err = "layer widths do not chain"; return DGP_ERR_ARG; }
+  const long Np = round_up(N, kTileM);
+  if (Np > 768) { c->err = "full_cov=True: N > 768 is not supported (one CTA factorises an N x N block)"; return DGP_ERR_UNSUPPORTED; }
+  std::vector<LayerWs> lw;
+  const bool vf_saved = c->use_vform, vfc_saved = c->vform_forward_calls;
+  c->use_vform = true; c->vform_forward_calls = true;      // the covariance blocks are built from the V-form planes
+  int rc = prep_layers(c, model, lw, PREP_FWD);
+  c->use_vform = vf_saved; c->vform_forward_calls = vfc_saved;
+  RC(rc);
+  const long P = N * S, Pp = round_up(P, kTileP);
+  int maxD = 1;
+  for (int l = 0; l < nl; ++l) {
+    if (lw[l].fcfg < 0 || !lw[l].vform) { c->err = "full_cov=True needs a layer shape the fused conditional kernel supports"; return DGP_ERR_UNSUPPORTED; }
+    if (lw[l].D_out > maxD) maxD = lw[l].D_out;
+  }
+  std::vector<ChunkLayer> cls(nl);
+  for (int l = 0; l < nl; ++l) {
+    const LayerWs& w = lw[l];
+    cls[l].F = walloc(c, (size_t)Pp * w.D_out); cls[l].Fmean = walloc(c, (size_t)Pp * w.D_out);
+    cls[l].Fvar = walloc(c, (size_t)Pp * w.D_out); cls[l].z = walloc(c, (size_t)Pp * w.D_out);
+  }
+  // one set of planes and factor blocks, reused by every layer
+  int maxMp = 0;
+  for (int l = 0; l < nl; ++l) if (lw[l].Mp > maxMp) maxMp = lw[l].Mp;
+  double* planeV = walloc(c, (size_t)maxMp * Pp);
+  double* planeT = walloc(c, (size_t)maxD * maxMp * Pp);
+  const size_t nblk = (size_t)S * maxD;
+  double* cin = walloc(c, nblk * Np * Np);
+  double* Lf = walloc(c, nblk * Np * Np);
+  CholArgs* dargs = reinterpret_cast<CholArgs*>(walloc(c, (sizeof(CholArgs) * nblk + 7) / 8));
+  Temps tmp;
+  if (c->dry) return DGP_OK;
+  std::vector<CholArgs> hargs(nblk);
+  for (size_t i = 0; i < nblk; ++i) hargs[i] = CholArgs{cin + i * Np * Np, Lf + i * Np * Np, nullptr, nullptr, (int)Np, c->d_info};
+  H2D(dargs, hargs.data(), sizeof(CholArgs) * nblk);
+  if (!c->chol_configured) {
+    CK(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem_bytes(768)));
+    c->chol_configured = true;
+  }
+  for (int l = 0; l < nl; ++l) {
+    const dgp_layer_desc& d = model->layers[l];
+    const LayerWs& w = lw[l];
+    ChunkLayer& cl = cls[l];
+    if (l == 0) { cl.Xin = X; cl.xmod = N; } else { cl.Xin = cls[l - 1].F; cl.xmod = P; }
+    cl.A = planeV; cl.T = planeT;
+    ChunkIO io;   // means go straight to the caller; variances / samples are replaced by the full-covariance ones below
+    std::vector<double*> fm(nl, nullptr);
+    if (Fmeans_host && Fmeans_host[l]) { fm[l] = Fmeans_host[l]; io.Fmeans = fm.data(); }
+    RC(forward_layer(c, d, w, cl, tmp, true, nullptr, l, N, S, N, 0, seed, n_offset, io, false));
+    CAT(DGP_CAT_MOMENTS);
+    FullCovArgs f;
+    memset(&f, 0, sizeof(f));
+    f.V = cl.A; f.T = cl.T; f.Xin = cl.Xin; f.xmod = cl.xmod; f.D_in = w.D_in; f.ls = d.lengthscales; f.var = d.variance;
+    f.kind = d.kernel_kind; f.Mp = w.Mp; f.D = w.D_out; f.N = N; f.Np = Np; f.Pp = Pp; f.S = (int)S; f.jitter = d.jitter;
+    f.var_out = (Fvars_host && Fvars_host[l]) ? Fvars_host[l] : nullptr; f.chol_in = cin;
+    const unsigned nt = (unsigned)(Np / kFcTile), nb = (unsigned)(S * w.D_out);
+    LAUNCH(fullcov_kernel, dim3(nt, nt, nb), 256, 0, f);
+    const bool last = l == nl - 1;
+    const bool want_sample = !last || (Fs_host && Fs_host[l]);
+    if (!want_sample) continue;
+    LAUNCH(chol_inv_kernel, nb, kCholThreads, chol_smem_bytes((int)Np), dargs);
+    const double* z = (zs_host && zs_host[l]) ? zs_host[l] : nullptr;
+    if (!z) {
+      const long total = P * w.D_out;
+      LAUNCH(philox_normal_kernel, (unsigned)((total + 255) / 256), 256, 0, seed, l, (long)S, (long)N, w.D_out, (long)n_offset, cl.z);
+      z = cl.z;
+    }
+    LAUNCH(fullcov_sample_kernel, dim3((unsigned)((N + 127) / 128), nb), 128, 0, Lf, cl.Fmean, z, N, Np, w.D_out, (int)S, cl.F,
+           (Fs_host && Fs_host[l]) ? Fs_host[l] : nullptr);
+  }
+  return DGP_OK;
+}
+}  // namespace
+
+int dgp_propagate_full_cov(dgp_ctx* c, const dgp_model_desc* model, const double* X, int64_t N, int64_t S,
+                           const double* const* zs_host, uint64_t seed, int64_t n_offset, double* const* Fs_host,
+                           double* const* Fmeans_host, double* const* Fvars_host) {
+  if (!c || !model || !X) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  c->dry = true; c->used = 0;
+  int rc = run_full_cov(c, model, X, N, S, zs_host, seed, n_offset, Fs_host, Fmeans_host, Fvars_host);
+  c->dry = false;
+  if (rc != DGP_OK) return rc;
+  RC(ensure_ws(c, c->used));
+  c->used = 0;
+  RC(run_full_cov(c, model, X, N, S, zs_host, seed, n_offset, Fs_host, Fmeans_host, Fvars_host));
   return check_chol(c);
 }
 

@@ -87,25 +87,27 @@ class DGP_Base(_Module):
 
     # ------------------------------------------------------------------ a7: propagate
     def propagate(self, X, full_cov=False, S=1, zs=None, seed=None, n_offset=0):
-        """dgp.py:34-63 -> (Fs, Fmeans, Fvars), lists of [S,N,D_l] tensors."""
-        if full_cov:
-            raise NotImplementedError("full_cov=True is out of scope of the accelerated path (SURVEY §8 f4)")
+        """dgp.py:34-63 -> (Fs, Fmeans, Fvars), lists of [S,N,D_l] tensors; full_cov=True draws samples correlated over the inputs
+        (Fvars then [S,N,N,D_l]: utils/layers.py:76-80,264-268; utils/utils.py:43-52)."""
         X = self._check_X(_lib.as_device(X, self.device))
         N = X.shape[0]
         mk = lambda: [torch.empty((S, N, l.num_outputs), dtype=torch.float64, device=X.device) for l in self.layers]
-        Fs, Fmeans, Fvars = mk(), mk(), mk()
+        Fs, Fmeans = mk(), mk()
+        Fvars = [torch.empty((S, N, N, l.num_outputs), dtype=torch.float64, device=X.device) for l in self.layers] if full_cov else mk()
         if N == 0 or S == 0:
             return Fs, Fmeans, Fvars
         m, keep = self._model_desc()
         zt, zp = self._zs(zs, S, N)
-        _lib.get_context(X.device).call("dgp_propagate", C.byref(m), _lib.ptr(X), N, S, zp, self._next_seed(seed), int(n_offset),
-                                        _lib.ptr_array(Fs), _lib.ptr_array(Fmeans), _lib.ptr_array(Fvars))
+        _lib.get_context(X.device).call("dgp_propagate_full_cov" if full_cov else "dgp_propagate", C.byref(m), _lib.ptr(X), N, S, zp,
+                                        self._next_seed(seed), int(n_offset), _lib.ptr_array(Fs), _lib.ptr_array(Fmeans),
+                                        _lib.ptr_array(Fvars))
         return Fs, Fmeans, Fvars
 
     def predict_f(self, X, full_cov=False, S=1, zs=None, seed=None):
-        """dgp.py:66-77: last layer's mean and variance [S,N,D_L]."""
+        """dgp.py:66-77: last layer's mean [S,N,D_L] and variance [S,N,D_L] (full_cov=True: covariance [S,N,N,D_L])."""
         if full_cov:
-            raise NotImplementedError("full_cov=True is out of scope of the accelerated path (SURVEY §8 f4)")
+            _, Fmeans, Fvars = self.propagate(X, full_cov=True, S=S, zs=zs, seed=seed)
+            return Fmeans[-1], Fvars[-1]
         X = self._check_X(_lib.as_device(X, self.device))
         N, L = X.shape[0], len(self.layers)
         D = self.layers[-1].num_outputs

@@ -30,21 +30,28 @@ class Layer(_Module):
         return torch.zeros((), dtype=torch.float64)
 
     def conditional_SND(self, X, full_cov=False):
-        """:63-85. [S,N,D_in] -> flatten (p = s*N + n) -> conditional_ND -> [S,N,D_out]."""
-        if full_cov:
-            raise NotImplementedError("full_cov=True is out of scope of the accelerated path (SURVEY §8 f4)")
-        X = _lib.as_device(X)
+        """:63-85. [S,N,D_in] -> flatten (p = s*N + n) -> conditional_ND -> [S,N,D_out]; full_cov=True maps conditional_ND over the
+        samples (:76-80) -> mean [S,N,D_out], var [S,N,N,D_out]. Host inputs go to the device the layer's parameters live on."""
+        X = _lib.as_device(X, self.feature.Z.value.device)
         S, N, D = X.shape
+        if full_cov:
+            mv = [self.conditional_ND(X[s].contiguous(), full_cov=True) for s in range(S)]
+            return [torch.stack([m for m, _ in mv]), torch.stack([v for _, v in mv])]
         mean, var = self.conditional_ND(X.reshape(S * N, D))
         return [m.reshape(S, N, self.num_outputs) for m in (mean, var)]
 
     def sample_from_conditional(self, X, z=None, full_cov=False, seed=0, layer_index=0):
         """:87-130. z=None draws from the library's Philox-4x32-10 stream (counter = (n, s, d, layer_index))."""
-        if full_cov:
-            raise NotImplementedError("full_cov=True is out of scope of the accelerated path (SURVEY §8 f4)")
-        X = _lib.as_device(X)
+        X = _lib.as_device(X, self.feature.Z.value.device)
         S, N, _ = X.shape
         D = self.num_outputs
+        if full_cov:
+            # per sample: full N x N covariance per output and the Cholesky reparameterisation (utils/utils.py:43-52)
+            outs = []
+            for s in range(S):
+                zs = None if z is None else [_lib.as_device(z, X.device).reshape(S, N, D)[s:s + 1].contiguous()]
+                outs.append(self._propagate_full(X[s].contiguous(), 1, zs, int(seed) + s, layer_index))
+            return tuple(torch.cat([o[k] for o in outs]) for k in range(3))
         ctx = _lib.get_context(X.device)
         if z is None:
             z = torch.empty((S, N, D), dtype=torch.float64, device=X.device)
@@ -134,11 +141,13 @@ class SVGP_Layer(Layer):
         self.needs_build_cholesky = False
 
     def conditional_ND(self, X, full_cov=False):
-        """:237-278, full_cov=False: X [P, D_in] -> mean, var [P, D_out] (mean includes the mean function)."""
-        if full_cov:
-            raise NotImplementedError("full_cov=True is out of scope of the accelerated path (SURVEY §8 f4)")
+        """:237-278: X [P, D_in] -> mean [P, D_out] (includes the mean function) and var [P, D_out], or with full_cov=True the
+        covariance [P, P, D_out] (:264-268,276)."""
         X = _lib.as_device(X, self.feature.Z.value.device)
         P = X.shape[0]
+        if full_cov:
+            _, mean, var = self._propagate_full(X, 1, None, 0, 0, want_sample=False)
+            return mean[0], var[0]
         mean = torch.empty((P, self.num_outputs), dtype=torch.float64, device=X.device)
         var = torch.empty_like(mean)
         if P == 0:
@@ -146,6 +155,21 @@ class SVGP_Layer(Layer):
         d, keep = self._desc()
         _lib.get_context(X.device).call("dgp_conditional_nd", C.byref(d), _lib.ptr(X), P, _lib.ptr(mean), _lib.ptr(var))
         return mean, var
+
+    def _propagate_full(self, X, S, zs, seed, layer_index, want_sample=True):
+        """One-layer dgp_propagate_full_cov call: X [N, D_in] shared by the S samples -> (F, mean [S,N,D], var [S,N,N,D])."""
+        N, D = X.shape[0], self.num_outputs
+        mean = torch.empty((S, N, D), dtype=torch.float64, device=X.device)
+        var = torch.empty((S, N, N, D), dtype=torch.float64, device=X.device)
+        F = torch.empty((S, N, D), dtype=torch.float64, device=X.device) if want_sample else None
+        if N == 0:
+            return F, mean, var
+        d, keep = self._desc()
+        m = _lib.ModelDesc(1, C.pointer(d), None)
+        zp = _lib.ptr_array(zs) if zs is not None else None
+        _lib.get_context(X.device).call("dgp_propagate_full_cov", C.byref(m), _lib.ptr(X), N, S, zp, int(seed), 0,
+                                        _lib.ptr_array([F]), _lib.ptr_array([mean]), _lib.ptr_array([var]))
+        return F, mean, var
 
     def KL(self):
         """:280-308 -> 0-d tensor."""

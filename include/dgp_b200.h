@@ -229,6 +229,14 @@ int dgp_predict_moments(dgp_ctx* ctx, const dgp_model_desc* model, const double*
                         const double* const* zs_host, uint64_t seed, int64_t n_offset, int add_lik_var,
                         double* mean, double* var);
 
+/* DGP_Base.propagate(X, full_cov=True, S, zs) (models/dgp.py:34-63 with utils/layers.py:76-80,264-268,276 and utils/utils.py:43-52):
+ * every layer's conditional is evaluated per sample with the full N x N covariance, samples are drawn with chol(var + jitter I) per
+ * sample and output. Caller arrays (any may be NULL): Fs[l], Fmeans[l] [S, N, D_l]; Fvars[l] [S, N, N, D_l]. N <= 768 (one CTA
+ * factorises an N x N block); layer shapes must be supported by the fused conditional kernel. zs / seed / n_offset as dgp_propagate. */
+int dgp_propagate_full_cov(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, int64_t N, int64_t S,
+                           const double* const* zs_host, uint64_t seed, int64_t n_offset, double* const* Fs_host,
+                           double* const* Fmeans_host, double* const* Fvars_host);
+
 /* DGP_Base.E_log_p_Y (models/dgp.py:79-87): out [N, D_L] = mean over the S samples of the Gaussian variational expectations
  * (-0.5 log 2pi - 0.5 log s_n^2 - 0.5 ((Y - mu)^2 + var) / s_n^2, utils/utils.py:89-93) of the last layer's moments. */
 int dgp_e_log_p_y(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, const double* Y, int64_t N, int64_t S,

@@ -466,3 +466,44 @@ def test_wb2_wb2s_ev_match_oracle():
     assert rel_err(ev, ev_o) < 1e-8
     with pytest.raises(NotImplementedError):
         D.PoF(0.0, 3).run(pm, prob["X"])
+
+
+@pytest.mark.parametrize("dims", [(3, [3], 14, 11, 3, None), (5, [3, 6], 70, 77, 2, None), (8, [8], 256, 512, 2, None),
+                                  (3, [3, 2], 40, 45, 2, [True, False, True])])
+def test_full_cov_propagate_matches_oracle(dims):
+    """propagate(full_cov=True) (models/dgp.py:34-63): per-sample conditionals with the full N x N covariance
+    (utils/layers.py:76-80,264-268,276) and the Cholesky reparameterisation (utils/utils.py:43-52), up to N = 512."""
+    D0, units, M, N, S, white = dims
+    prob, om, pm = both_models(D0, units, M, N, S, white=white)
+    zs = oracle_zs(om, N, S, 3)
+    with torch.no_grad():
+        Fs_o, Fm_o, Fv_o = O.propagate_full_cov(om.layers, torch.as_tensor(prob["X"]), S, zs)
+    Fs, Fm, Fv = pm.propagate(prob["X"], full_cov=True, S=S, zs=zs)
+    for l in range(len(om.layers)):
+        assert tuple(Fv[l].shape) == (S, N, N, om.layers[l].D_out)
+        assert rel_err(Fm[l], Fm_o[l]) < TOL and rel_err(Fv[l], Fv_o[l], scale=float(om.layers[l].variance)) < TOL
+        assert rel_err(Fs[l], Fs_o[l]) < 1e-8      # through an N x N Cholesky of a covariance with jitter-level eigenvalues
+    m, v = pm.predict_f(prob["X"], full_cov=True, S=S, zs=zs)
+    assert rel_err(m, Fm_o[-1]) < TOL and rel_err(v, Fv_o[-1], scale=1.0) < TOL
+
+
+def test_full_cov_layer_methods_match_oracle():
+    """SVGP_Layer.conditional_ND / conditional_SND / sample_from_conditional with full_cov=True; the diagonal of the covariance is
+    the full_cov=False variance."""
+    prob, om, pm = both_models(4, [4], 30, 25, 3)
+    ol, pl = om.layers[0], pm.layers[0]
+    X = torch.as_tensor(prob["X"])
+    m_o, v_o = O.conditional_ND_full(ol, X)
+    m, v = pl.conditional_ND(prob["X"], full_cov=True)
+    assert tuple(v.shape) == (25, 25, 4) and rel_err(m, m_o) < TOL and rel_err(v, v_o, scale=1.0) < TOL
+    md, vd = pl.conditional_ND(prob["X"])
+    assert rel_err(torch.diagonal(v, dim1=0, dim2=1).T, vd, scale=1.0) < TOL
+    Xs = torch.stack([X, X * 0.9 + 0.1, X - 0.2])
+    ms, vs = pl.conditional_SND(Xs.numpy(), full_cov=True)
+    for s in range(3):
+        m_s, v_s = O.conditional_ND_full(ol, Xs[s])
+        assert rel_err(ms[s], m_s) < TOL and rel_err(vs[s], v_s, scale=1.0) < TOL
+    z = torch.randn(3, 25, 4, dtype=torch.float64, generator=torch.Generator().manual_seed(4))
+    F, mean, var = pl.sample_from_conditional(Xs.numpy(), z=z, full_cov=True)
+    F_o = O.reparameterize_full(ms.cpu(), vs.cpu(), z)
+    assert rel_err(F, F_o) < 1e-8 and rel_err(mean, ms) < 1e-12 and rel_err(var, vs, scale=1.0) < 1e-12
