@@ -92,3 +92,32 @@ def EHVI(model_Y, Xcand, YND, corr=False, approximation='None', S=1000, zs=None,
     _lib.get_context(dev).call("dgp_ehvi2d", _lib.ptr(m0), _lib.ptr(v0), _lib.ptr(m1), _lib.ptr(v1), N, _lib.ptr(y0),
                                _lib.ptr(y1), int(y0.numel()), _lib.ptr(out))
     return out
+
+
+def optimize_EHVI(model, YND, popsize_DE=300, popstd_DE=1.5, iterations_DE=400, init_adam=None, lr_adam=0.01, iterations_adam=1000,
+                  method='DE', corr=False, approximation='None', S=1000, seed=None, bounds=(0.0, 1.0)):
+    """EHVI.py:208-235 for `model` = [dgp0, dgp1] (the two-DGP list path of EHVI()): search the box for the candidate with the
+    largest expected hypervolume improvement. As written the reference (i) passes population_size / population_stddev swapped
+    (:217-218), (ii) MINIMISES the positive EHVI (:212), (iii) reads the input dimension from the MO-DGP object (`model._X`, :210) and
+    (iv) discards the DE result before the Adam stage (`x_opt = np.array([[0]])`, :221). Implemented here is the evident intent:
+    differential evolution (rand/1/bin, TFP defaults) on u with x = lw + (up - lw) / (1 + exp(u)) minimising -EHVI, every
+    generation one EHVI evaluation of the whole population on the device. Returns x_opt [d, 1] like the reference."""
+    from . import search
+    if not isinstance(model, list) or len(model) != 2:
+        raise NotImplementedError("optimize_EHVI is implemented for a list of two DGP models (the MO-DGP object is SURVEY §8 f2)")
+    if method != 'DE':
+        raise NotImplementedError("the Adam stage needs d EHVI / d x, which this path does not provide yet; use method='DE'")
+    d = model[0].layers[0].feature.Z.shape[1]
+    lw = np.broadcast_to(np.asarray(bounds[0], dtype=np.float64).reshape(-1), (d,)).copy()
+    up = np.broadcast_to(np.asarray(bounds[1], dtype=np.float64).reshape(-1), (d,)).copy()
+    dev = model[0].device
+    with search.GraphScope(dev):
+        def objective(X, out):
+            v = -EHVI(model, X, YND, corr=corr, approximation=approximation, S=S)
+            if out is None:
+                return v.contiguous()
+            out.copy_(v)
+            return out
+        res = search.de_minimize(objective, lw, up, d, dev, popsize_DE, popstd_DE, iterations_DE, seed=model[0]._next_seed(seed))
+    _lib.get_context(dev).check()
+    return res["x"].cpu().numpy().reshape(d, 1)

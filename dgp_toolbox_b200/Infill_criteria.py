@@ -144,8 +144,8 @@ def _moment_criterion(kind, model, x, y, num_samples, zs, seed, with_x=False):
 
 
 def _moment_criterion_grad(kind, model, x, y, num_samples, zs, seed, out=None, dx=None):
-    """(criterion [N, 1], d sum(criterion) / dx [N, d]) for kind 1 (WB2) / 2 (EV) on predict_y mixture moments: one dgp_acq_grad
-    call (criterion adjoints, then the data path of the adjoint chain)."""
+    """(criterion [N, 1], d sum(criterion) / dx [N, d]) for kind 1 (WB2) / 2 (EV) / 3 (WB2S: criterion [N, d]) on predict_y mixture
+    moments: one dgp_acq_grad call (criterion adjoints, then the data path of the adjoint chain)."""
     if getattr(model, "name", None) != 'dgp':
         raise NotImplementedError("only model.name == 'dgp' is on the accelerated path")
     X = model._check_X(_lib.as_device(x, model.device))
@@ -153,7 +153,7 @@ def _moment_criterion_grad(kind, model, x, y, num_samples, zs, seed, out=None, d
     if D != 1:
         raise ValueError("the criterion expects a single-output model")
     if out is None:
-        out = torch.empty((N, D), dtype=torch.float64, device=X.device)
+        out = torch.empty((N, X.shape[1] if kind == 3 else D), dtype=torch.float64, device=X.device)
     if dx is None:
         dx = torch.zeros_like(X)
     if N == 0:
@@ -206,28 +206,38 @@ class WB2(Infill_criteria):
         """(WB2 [N, 1], d sum(WB2) / dx [N, d]) -- what tape.gradient(loss, x) gives the reference's Adam stage (:160-165)."""
         return _moment_criterion_grad(1, model, x, self.y_min, num_samples, zs, seed, out, dx)
 
+    @staticmethod
+    def ncol(d):
+        return 1
+
     def optimize(self, model, bounds, popsize_DE=300, popstd_DE=1.5, iterations_DE=400, init_adam=None, iterations_adam=1000,
                  method='DE', seed=None):
         """Infill_criteria.py:142-168: 'DE', 'Adam' or 'DE+Adam' like EI.optimize."""
-        if method not in ('DE', 'Adam', 'DE+Adam'):
-            raise ValueError(f"unknown method {method!r}")
-        lw = np.broadcast_to(np.asarray(bounds[0], dtype=np.float64).reshape(-1), (self.d,)).copy()
-        up = np.broadcast_to(np.asarray(bounds[1], dtype=np.float64).reshape(-1), (self.d,)).copy()
-        if method in ('DE', 'DE+Adam'):
-            _optimize_de(self, lambda X: self.run(model, X), model, bounds, popsize_DE, popstd_DE, iterations_DE, 'DE', seed)
-        if method in ('Adam', 'DE+Adam'):
-            with search.GraphScope(model.device):
-                if init_adam is None:
-                    init_adam = np.zeros(self.d) if self.x_opt is None else self.x_opt
-                init_adam = np.asarray(init_adam, dtype=np.float64).reshape(self.d)
-                u0 = _lib.as_device(np.log((up - init_adam + 1e-3) / (init_adam - lw + 1e-3)).reshape(1, self.d), model.device)
-                out = torch.empty((1, 1), dtype=torch.float64, device=u0.device)
-                dx = torch.zeros_like(u0)
-                u, X, val = search.adam_box_minimize(lambda X: self.run_with_grad(model, X, out=out, dx=dx), lw, up, u0,
-                                                     iterations_adam, lr=0.01)
-                self.x_opt = X.cpu().numpy().reshape(self.d, 1)
-                self.IC_optimized = val.clone()
-        return self.x_opt
+        return _optimize_de_adam(self, model, bounds, popsize_DE, popstd_DE, iterations_DE, init_adam, iterations_adam, method, seed)
+
+
+def _optimize_de_adam(crit, model, bounds, popsize_DE, popstd_DE, iterations_DE, init_adam, iterations_adam, method, seed):
+    """The two stages of the reference's `optimize` for a moment-based criterion with `run` and `run_with_grad` (WB2, WB2S)."""
+    if method not in ('DE', 'Adam', 'DE+Adam'):
+        raise ValueError(f"unknown method {method!r}")
+    d = crit.d
+    lw = np.broadcast_to(np.asarray(bounds[0], dtype=np.float64).reshape(-1), (d,)).copy()
+    up = np.broadcast_to(np.asarray(bounds[1], dtype=np.float64).reshape(-1), (d,)).copy()
+    if method in ('DE', 'DE+Adam'):
+        _optimize_de(crit, lambda X: crit.run(model, X), model, bounds, popsize_DE, popstd_DE, iterations_DE, 'DE', seed)
+    if method in ('Adam', 'DE+Adam'):
+        with search.GraphScope(model.device):
+            if init_adam is None:
+                init_adam = np.zeros(d) if crit.x_opt is None else crit.x_opt
+            init_adam = np.asarray(init_adam, dtype=np.float64).reshape(d)
+            u0 = _lib.as_device(np.log((up - init_adam + 1e-3) / (init_adam - lw + 1e-3)).reshape(1, d), model.device)
+            out = torch.empty((1, crit.ncol(d)), dtype=torch.float64, device=u0.device)
+            dx = torch.zeros_like(u0)
+            u, X, val = search.adam_box_minimize(lambda X: crit.run_with_grad(model, X, out=out, dx=dx), lw, up, u0,
+                                                 iterations_adam, lr=0.01)
+            crit.x_opt = X.cpu().numpy().reshape(d, 1)
+            crit.IC_optimized = val.clone()
+    return crit.x_opt
 
 
 class WB2S(Infill_criteria):
@@ -246,10 +256,18 @@ class WB2S(Infill_criteria):
     def loss(self, model, x):
         return self.run(model, x)
 
+    def run_with_grad(self, model, x, num_samples=500, zs=None, seed=None, out=None, dx=None):
+        """(WB2S [N, d], d sum(WB2S) / dx [N, d]): the chain's input gradient plus the explicit -sig'(x) EI term (:187,198,225-230)."""
+        return _moment_criterion_grad(3, model, x, self.y_min, num_samples, zs, seed, out, dx)
+
+    @staticmethod
+    def ncol(d):
+        return d
+
     def optimize(self, model, bounds, popsize_DE=300, popstd_DE=1.5, iterations_DE=400, init_adam=None, iterations_adam=1000,
                  method='DE', seed=None):
-        """Infill_criteria.py:207-233 (DE stage; the [N, d] criterion is summed over its columns per candidate)."""
-        return _optimize_de(self, lambda X: self.run(model, X), model, bounds, popsize_DE, popstd_DE, iterations_DE, method, seed)
+        """Infill_criteria.py:207-233: 'DE', 'Adam' or 'DE+Adam' (the [N, d] criterion is summed over its columns per candidate)."""
+        return _optimize_de_adam(self, model, bounds, popsize_DE, popstd_DE, iterations_DE, init_adam, iterations_adam, method, seed)
 
 
 class EV_one_constraint(Infill_criteria):
@@ -356,14 +374,41 @@ EV.optimize_with_IC = _ev_optimize_with_IC
 
 
 class PoF(Infill_criteria):
-    """Infill_criteria.py:318-345 computes the EI-style terms but never returns them and `run_with_IC` references an undefined
-    name: there is no reference behaviour to reproduce."""
+    """Infill_criteria.py:318-354, repaired. The reference's `run` computes EI-style terms t1, t2 and returns nothing (:325-341),
+    `run_with_IC` multiplies by the CLASS name (`-1*EI*PoF`, :345) and drops the box bounds when mapping x_opt back (:353). What the
+    name and the use say: PoF(x) = P[c(x) <= zero_c] = Phi((zero_c - mean) / sigma) on the predict_y mixture moments of the
+    constraint model (500 samples like the other criteria), and the constrained criterion to MINIMISE is IC(x) * PoF(x) with
+    IC.run = -EI (so -EI * PoF)."""
 
     def __init__(self, zero_c, d):
         self.name = 'Probability of feasability'
         self.zero_c = zero_c
         self.d = d
         self.IC_optimized = None
+        self.x_opt = None
 
-    def run(self, model_C, x):
-        raise NotImplementedError("PoF.run has no return statement in the reference (Infill_criteria.py:325-341)")
+    def run(self, model_C, x, num_samples=500, zs=None, seed=None):
+        """P[constraint <= zero_c] per candidate -> [N, 1]."""
+        return _moment_criterion(4, model_C, x, self.zero_c, num_samples, zs, seed)
+
+    def run_with_IC(self, IC, model_Y, model_C, x, seed=None):
+        return IC.run(model_Y, x, seed=seed) * self.run(model_C, x, seed=seed)
+
+    def optimize_with_IC(self, IC, model_Y, model_C, bounds, popsize_DE=300, popstd_DE=1.5, iterations_DE=400, seed=None):
+        """:346-354: differential evolution (TFP defaults of the reference: population 300 around u = 0, spread 1.5, 400 generations)
+        on x = lw + (up - lw) / (1 + exp(u)); x_opt is mapped back into the box (the reference forgets lw / up there)."""
+        d = self.d
+        lw = np.broadcast_to(np.asarray(bounds[0], dtype=np.float64).reshape(-1), (d,)).copy()
+        up = np.broadcast_to(np.asarray(bounds[1], dtype=np.float64).reshape(-1), (d,)).copy()
+        with search.GraphScope(model_Y.device):
+            def objective(X, out):
+                v = self.run_with_IC(IC, model_Y, model_C, X)
+                if out is None:
+                    return v.contiguous()
+                out.copy_(v)
+                return out
+            res = search.de_minimize(objective, lw, up, d, model_Y.device, popsize_DE, popstd_DE, iterations_DE,
+                                     seed=model_Y._next_seed(seed))
+            self.x_opt = res["x"].cpu().numpy().reshape(d, 1)
+            self.IC_optimized = self.run_with_IC(IC, model_Y, model_C, self.x_opt.reshape(1, d))
+        return self.x_opt

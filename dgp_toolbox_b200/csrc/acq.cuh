@@ -52,7 +52,11 @@ __global__ void ei_analytic_kernel(const double* __restrict__ mean, const double
 // Per sample: Gm[s] = dc/dmbar / S + 2 dc/dvbar (mu_s - mbar) / S,  Gv[s] = dc/dvbar / S.
 __global__ void ei_upstream_kernel(const double* __restrict__ Fmean, const double* __restrict__ Fvar, long Nc, long S, long Pp, int D,
                                    double y_min, double* __restrict__ neg_ei, double* __restrict__ Gm, double* __restrict__ GvT,
-                                   double* __restrict__ GmPad, double* __restrict__ gq, int kind, const double* __restrict__ lik_var) {
+                                   double* __restrict__ GmPad, double* __restrict__ gq, int kind, const double* __restrict__ lik_var,
+                                   const double* __restrict__ Xc, int d0, double* __restrict__ direct) {
+  // kind 3 (WB2S, Infill_criteria.py:187-198, single-output model): value[n][j] = -(sig(x_nj) EI - mbar), j < d0; the chain receives
+  // the adjoints of sum_j value[n][j] (dc/dmbar = Phi(u) sum_j sig_j + d0, dc/dvbar = -phi(u) sum_j sig_j / (2 sigma)) and
+  // `direct`[n][j] = -sig_j (1 - sig_j) EI is the explicit dependence on x, added to the input gradient by the caller.
   const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= Nc) return;
   for (int d = 0; d < D; ++d) {
@@ -75,8 +79,20 @@ __global__ void ei_upstream_kernel(const double* __restrict__ Fmean, const doubl
       dm = cdf;
       dv = -pdf / (2.0 * sig);
       if (kind == 1) { val += mbar; dm += 1.0; }
+      if (kind == 3) {
+        const double ei = -val;
+        double ssum = 0.0;
+        for (int j = 0; j < d0; ++j) {
+          const double sg = 1.0 / (1.0 + exp(-Xc[n * d0 + j]));
+          ssum += sg;
+          neg_ei[n * d0 + j] = -(sg * ei - mbar);
+          direct[n * d0 + j] = -sg * (1.0 - sg) * ei;
+        }
+        dm = dm * ssum + (double)d0;
+        dv = dv * ssum;
+      }
     }
-    neg_ei[n * D + d] = val;
+    if (kind != 3) neg_ei[n * D + d] = val;
     const double gv = dv / (double)S;
     for (long s = 0; s < S; ++s) {
       const long p = s * Nc + n;
@@ -94,11 +110,14 @@ __global__ void ei_upstream_kernel(const double* __restrict__ Fmean, const doubl
 //   kind 1  -(EI(y) - mean)             (WB2.run, :124-133)
 //   kind 2  EV(c) = (mean - c) Phi((mean - c)/s) + s phi((mean - c)/s)   (EV_one_constraint.run analytic, :249-257)
 //   kind 3  -(sigmoid(x[n][j]) EI(y) - mean)   -> out [n][d]            (WB2S.run, :187-198; S = 1/(1 + 1/exp(x)) elementwise in x)
+//   kind 4  Phi((c - mean) / s): probability that the constraint value is below c     (PoF, :318-341 -- the reference computes the
+//           EI-style terms there and returns nothing; this is the probability its name and its use in run_with_IC call for)
 __global__ void acq_moments_kernel(int kind, const double* __restrict__ mean, const double* __restrict__ var, long n, double y,
                                    const double* __restrict__ x, int d, double* __restrict__ out) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double m = mean[i], v = var[i], s = sqrt(v);
+  if (kind == 4) { out[i] = norm_cdf((y - m) / s); return; }
   if (kind == 2) {
     const double u = (m - y) / s;
     out[i] = (m - y) * norm_cdf(u) + v * (norm_pdf(u) / s);
@@ -261,4 +280,11 @@ __global__ void adam_box_kernel(double* __restrict__ u, double* __restrict__ m_s
   x[idx] = lw[j] + span / (1.0 + exp(uu));
 }
 
+}  // namespace dgp
+
+namespace dgp {
+__global__ void add_inplace_kernel(double* __restrict__ dst, const double* __restrict__ src, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
 }  // namespace dgp

@@ -1007,6 +1007,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
       XaugPad1 = walloc(c, (size_t)Ppmax * 32);
     }
   }
+  double* acq_direct = (o.dx && o.acq_kind == 3) ? walloc(c, (size_t)Nc_max * 32) : nullptr;
   ParamScratch ps;
   ps.part = skpart; ps.cap = skcap;
   if (adj) {
@@ -1136,10 +1137,16 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
       CK(cudaMemsetAsync(up.GvT, 0, (size_t)Pp * DL * sizeof(double), c->stream));
       CK(cudaMemsetAsync(up.GmPad, 0, (size_t)Pp * 32 * sizeof(double), c->stream));
       CK(cudaMemsetAsync(up.gq, 0, (size_t)Pp * sizeof(double), c->stream));
-      LAUNCH(ei_upstream_kernel, (unsigned)((Nc + 127) / 128), 128, 0, clL.Fmean, clL.Fvar, Nc, S, Pp, DL, o.y_min, o.ei + n0 * DL,
-             up.Gm, up.GvT, up.GmPad, up.gq, o.acq_kind, o.acq_add_lik ? model->lik_variance : nullptr);
+      const int D0x = model->layers[0].D_in;
+      const long vstride = o.acq_kind == 3 ? D0x : DL;   // WB2S returns one value per input column
+      LAUNCH(ei_upstream_kernel, (unsigned)((Nc + 127) / 128), 128, 0, clL.Fmean, clL.Fvar, Nc, S, Pp, DL, o.y_min, o.ei + n0 * vstride,
+             up.Gm, up.GvT, up.GmPad, up.gq, o.acq_kind, o.acq_add_lik ? model->lik_variance : nullptr, X + n0 * D0x, D0x, acq_direct);
       up.part = lik_part; up.nblocks = nb;
       RC(run_backward(false));
+      if (o.acq_kind == 3) {
+        CAT(DGP_CAT_OTHER);
+        LAUNCH(add_inplace_kernel, (unsigned)((Nc * D0x + 255) / 256), 256, 0, o.dx + n0 * D0x, acq_direct, Nc * D0x);
+      }
     }
     n0 += Nc;
     first = false;
@@ -1956,8 +1963,9 @@ int dgp_ei_grad(dgp_ctx* c, const dgp_model_desc* model, const double* X, int64_
 
 int dgp_acq_grad(dgp_ctx* c, const dgp_model_desc* model, int kind, const double* X, int64_t N, int64_t S,
                  const double* const* zs_host, uint64_t seed, int64_t n_offset, double y, double* value, double* d_value_dX) {
-  if (!c || !model || !X || !value || !d_value_dX || kind < 0 || kind > 2) return DGP_ERR_ARG;
+  if (!c || !model || !X || !value || !d_value_dX || kind < 0 || kind > 3) return DGP_ERR_ARG;
   if (kind > 0 && !model->lik_variance) { c->err = "lik_variance is null"; return DGP_ERR_ARG; }
+  if (kind == 3 && model->layers[model->num_layers - 1].D_out != 1) { c->err = "WB2S expects a single-output model"; return DGP_ERR_ARG; }
   RunOpts o;
   o.io.zs = zs_host; o.ei = value; o.y_min = y; o.ei_analytic = 1; o.dx = d_value_dX;
   o.acq_kind = kind; o.acq_add_lik = kind > 0 ? 1 : 0;
@@ -1966,7 +1974,7 @@ int dgp_acq_grad(dgp_ctx* c, const dgp_model_desc* model, int kind, const double
 
 int dgp_acq_moments(dgp_ctx* c, int kind, const double* mean, const double* var, int64_t n, double y, const double* x, int d,
                     double* out) {
-  if (!c || !mean || !var || !out || n < 1 || kind < 0 || kind > 3 || (kind == 3 && (!x || d < 1))) return DGP_ERR_ARG;
+  if (!c || !mean || !var || !out || n < 1 || kind < 0 || kind > 4 || (kind == 3 && (!x || d < 1))) return DGP_ERR_ARG;
   CK(cudaSetDevice(c->device));
   LAUNCH(acq_moments_kernel, (unsigned)((n + 255) / 256), 256, 0, kind, mean, var, (long)n, y, x, d, out);
   return DGP_OK;

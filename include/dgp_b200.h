@@ -198,7 +198,8 @@ int dgp_train_nat_adam(dgp_ctx* ctx, const dgp_model_desc* model, const double* 
 
 /* Value and input gradient of a moment-based criterion (the gradient the reference's Adam-on-x stage takes with tape.gradient,
  * Infill_criteria.py:79-84,160-165): kind 0 = -EI on predict_f moments (== dgp_ei_grad), 1 = WB2 = -(EI - mean) and 2 = EV =
- * (mean - y) Phi + s phi, both on predict_y moments (+ sigma_n^2, Infill_criteria.py:124-133,249-257). value [N, D_L],
+ * (mean - y) Phi + s phi, both on predict_y moments (+ sigma_n^2, Infill_criteria.py:124-133,249-257), 3 = WB2S = -(sigmoid(x_j) EI -
+ * mean) per input column j (Infill_criteria.py:187-198; single-output model; value [N, D0]). value [N, D_L] otherwise,
  * d_value_dX [N, D0] = d sum(value) / dX. The adjoint chain runs without the parameter contractions. */
 int dgp_acq_grad(dgp_ctx* ctx, const dgp_model_desc* model, int kind, const double* X, int64_t N, int64_t S,
                  const double* const* zs_host, uint64_t seed, int64_t n_offset, double y, double* value, double* d_value_dX);
@@ -255,7 +256,9 @@ int dgp_ei_grad(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, int6
 
 /* The other moment-based criteria of dgp_dace/Infill_criteria.py, evaluated on mixture moments (mean, var) [n] (DEVICE):
  * kind 0: -EI(y) (:43-47); 1: WB2 -(EI(y) - mean) (:124-133); 2: EV_one_constraint analytic with zero_c = y (:249-257);
- * 3: WB2S -(sigmoid(x) EI(y) - mean) with x [n, d] -> out [n, d] (:187-198). out [n] except for kind 3. */
+ * 3: WB2S -(sigmoid(x) EI(y) - mean) with x [n, d] -> out [n, d] (:187-198); 4: probability of feasibility Phi((y - mean) / s)
+ * (PoF, :318-341: the reference computes EI-style terms there and returns nothing; this is the quantity run_with_IC needs).
+ * out [n] except for kind 3. */
 int dgp_acq_moments(dgp_ctx* ctx, int kind, const double* mean, const double* var, int64_t n, double y, const double* x, int d,
                     double* out);
 /* EV_one_constraint Monte-Carlo branch (:259-262): out [ND] = mean_s max(F[s] - zero_c, 0), F [S, ND]. */

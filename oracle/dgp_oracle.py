@@ -500,6 +500,13 @@ def wb2s(Ymean, Yvar, y_min, x):
     return -(S * _ei_from_moments(m, v, y_min) - m)
 
 
+def pof(Ymean, Yvar, zero_c):
+    """Probability of feasibility P[c <= zero_c] = Phi((zero_c - mean) / sigma) on predict_y mixture moments: the quantity
+    Infill_criteria.py:318-345 (PoF) needs but never returns (its `run` has no return statement)."""
+    m, v = mixture_moments(Ymean, Yvar)
+    return _Phi((zero_c - m) / torch.sqrt(v))
+
+
 def ev_analytic(Ymean, Yvar, zero_c):
     """Infill_criteria.py:249-257: Normal(-mean, sqrt(var)); t1 = (-c + mean) cdf(-c); t2 = var * pdf(-c)."""
     m, v = mixture_moments(Ymean, Yvar)

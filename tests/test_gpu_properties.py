@@ -108,8 +108,9 @@ def test_empty_inputs_and_error_behaviour():
     m, v = model.predict(np.zeros((0, 8)), 2)
     assert m.shape == (0, 1)
     assert model.layers[0].conditional_ND(np.zeros((0, 8)))[0].shape == (0, 8)
-    with pytest.raises(NotImplementedError):
-        model.propagate(np.zeros((4, 8)), full_cov=True)
+    assert model.propagate(np.zeros((4, 8)), full_cov=True, S=2)[2][0].shape == (2, 4, 4, 8)
+    with pytest.raises(D._lib.DGPError, match="N > 768"):
+        model.propagate(np.zeros((800, 8)), full_cov=True, S=1)
     with pytest.raises(NotImplementedError):
         D.SVGP_Layer(D.RBF(lengthscales=[1.0]), np.zeros((4, 1)), 1, D.Zero(), augmented=True)
     with pytest.raises(ValueError):           # Y width does not match the last layer

@@ -122,8 +122,6 @@ def test_ei_optimize_de_then_adam_improves_on_a_dense_grid():
                             method='DE+Adam', num_samples=64, seed=11, adam_starts=4)    # four refinements side by side
     assert x_multi.shape == (1, 1) and crit.IC_optimized.shape == (1, 1)
     assert -1.0 <= x_multi.item() <= 1.0 and float(crit.run(model, x_multi.reshape(1, 1), True, 256, seed=77)) <= 0.5 * (g.min() + g.max())
-    with pytest.raises(NotImplementedError):
-        D.WB2S(float(Y.min()), 1).optimize(model, (np.array([-1.0]), np.array([1.0])), method='Adam')
     wb2 = D.WB2(float(Y.min()), 1)
     xw = wb2.optimize(model, (np.array([-1.0]), np.array([1.0])), popsize_DE=12, iterations_DE=5, iterations_adam=20,
                       method='DE+Adam', seed=2)
@@ -185,3 +183,54 @@ def test_constrained_search_with_expected_violation():
     assert x_opt.shape == (1, 1) and -1.0 <= x_opt.item() <= 0.3
     at = float(ev.run_with_IC(ei, mY, [mC], x_opt.reshape(1, 1), threshold=0.1, num_samples=256, seed=4))
     assert at < 1.0 and at <= vals[vals < 9000.0].min() + 0.1 * abs(vals[vals < 9000.0].min()) + 1e-3, (at, x_opt.item())
+
+
+def test_wb2s_value_and_input_gradient_match_oracle_and_pof():
+    """WB2S.run_with_grad (dgp_acq_grad kind 3: the chain's input gradient + the explicit -sig'(x) EI term, Infill_criteria.py:187-198)
+    against autograd through the oracle; PoF = Phi((c - mean) / sigma) (the repaired Infill_criteria.py:318-345)."""
+    import dgp_toolbox_b200 as D
+    from tests.helpers import both_models
+    prob, om, pm = both_models(3, [3], 20, 15, 6)
+    S, N = 6, 15
+    zs = [torch.as_tensor(O.philox_normal(8, l, S, N, layer.D_out)) for l, layer in enumerate(om.layers)]
+    y_min = float(prob["Y"].min())
+    X = torch.as_tensor(prob["X"]).clone().requires_grad_(True)
+    ym, yv = O.predict_y(om, X, S, zs)
+    val_o = O.wb2s(ym, yv, y_min, X)
+    val_o.sum().backward()
+    crit = D.WB2S(y_min, 3)
+    val, dx = crit.run_with_grad(pm, prob["X"], num_samples=S, seed=8)
+    assert tuple(val.shape) == (N, 3) and rel_err(val, val_o.detach()) < 1e-8 and rel_err(dx, X.grad) < 1e-8
+    assert rel_err(crit.run(pm, prob["X"], num_samples=S, seed=8), val_o.detach()) < 1e-8
+    with torch.no_grad():
+        p_o = O.pof(ym.detach(), yv.detach(), 0.3)
+    p = D.PoF(0.3, 3).run(pm, prob["X"], num_samples=S, seed=8)
+    assert rel_err(p, p_o) < 1e-9 and float(p.min()) >= 0.0 and float(p.max()) <= 1.0
+
+
+def test_wb2s_pof_and_ehvi_searches_run():
+    """WB2S.optimize('DE+Adam'), PoF.optimize_with_IC and optimize_EHVI return points inside the box that are at least as good as
+    the best of a coarse grid (up to Monte-Carlo noise)."""
+    import dgp_toolbox_b200 as D
+    rng = np.random.default_rng(3)
+    X = np.linspace(-1.0, 1.0, 14)[:, None]
+    Y = np.sin(4.0 * X) + 0.3 * X + 0.02 * rng.standard_normal(X.shape)
+    mk = lambda Yv, seed: D.DGP(X, Yv, X.copy(), [D.RBF(lengthscales=[0.4], variance=1.0) for _ in range(2)], [1], D.Gaussian(0.01),
+                                num_samples=8, seed=seed)
+    model, cons, obj2 = mk(Y, 5), mk(np.cos(3.0 * X), 6), mk(np.cos(2.0 * X) + 0.5 * X, 7)
+    for m in (model, cons, obj2):
+        D.DGP_Base.optimize_adam(m, m.data, iterations=150, lr=0.02, messages=10 ** 9)
+    box = (np.array([-1.0]), np.array([1.0]))
+    w = D.WB2S(float(Y.min()), 1)
+    x1 = w.optimize(model, box, popsize_DE=16, iterations_DE=10, iterations_adam=20, method='DE+Adam', seed=2)
+    assert x1.shape == (1, 1) and -1.0 <= x1.item() <= 1.0 and tuple(w.IC_optimized.shape) == (1, 1)
+    pof = D.PoF(0.0, 1)
+    x2 = pof.optimize_with_IC(D.EI(float(Y.min()), 1), model, cons, box, popsize_DE=16, iterations_DE=10, seed=2)
+    assert x2.shape == (1, 1) and -1.0 <= x2.item() <= 1.0 and float(pof.IC_optimized) <= 1e-12     # -EI * PoF <= 0
+    y0 = np.linspace(-0.8, 0.6, 5)
+    ynd = D.Y_ND([y0[:, None], (0.9 - y0)[:, None]], list(np.argsort(-y0)), nadir=[1.5, 1.5], ideal=[-1.5, -1.5])
+    x3 = D.optimize_EHVI([model, obj2], ynd, popsize_DE=16, iterations_DE=8, S=32, seed=4, bounds=box)
+    grid = np.linspace(-1.0, 1.0, 41)[:, None]
+    g = D.EHVI([model, obj2], grid, ynd, S=256, seed=[9, 10]).cpu().numpy().reshape(-1)
+    at = float(D.EHVI([model, obj2], x3.reshape(1, 1), ynd, S=256, seed=[9, 10]))
+    assert x3.shape == (1, 1) and -1.0 <= x3.item() <= 1.0 and at >= 0.7 * g.max()
