@@ -24,7 +24,7 @@ if ROOT not in sys.path:
 
 METRIC = "DGP ELBO+grad point-samples/s"
 UNIT = "point-samples/s"
-FP64_PEAK_FALLBACK_TFLOPS = 37.07   # profiles/r01_fp64_peaks.json (DMMA.8x8x4 register-resident loop, this pool's B200)
+FP64_PEAK_FALLBACK_TFLOPS = 37.07   # profiles/r0*_fp64_peaks.json (DMMA.8x8x4 register-resident loop, this pool's B200)
 
 
 def load_synthetic(package):
@@ -56,8 +56,9 @@ def fp64_peak():
     """MEASURED_PEAKS.json has no FP64 figure (bf16 + HBM only), so the denominator is this repo's own calibration
     (tools/fp64_peaks.cu run on this pool's B200, committed as profiles/r01_fp64_peaks.json)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")) as f:
-            return float(json.load(f)["summary"]["fp64_dmma_tflops"]), "profiles/r01_fp64_peaks.json (own DMMA calibration; MEASURED_PEAKS.json has no FP64 entry)"
+        with open(os.path.join(ROOT, "profiles", "r02_fp64_peaks.json")) as f:
+            return float(json.load(f)["summary"]["fp64_dmma_tflops"]), ("profiles/r02_fp64_peaks.json (own DMMA calibration, tools/fp64_peaks.cu; "
+                                                                        "MEASURED_PEAKS.json has no FP64 entry; DMMA and DFMA share the pipe, so this is the ceiling)")
     except Exception:
         return FP64_PEAK_FALLBACK_TFLOPS, "fallback constant (own r01 DMMA calibration)"
 
@@ -130,6 +131,133 @@ def cpu_reference_throughput(cfg, nb_cpu, steps, warmup):
     return nb_cpu * cfg["S"] / dt, dt, cores
 
 
+def cpu_forward_baseline(kind, cfg, n_cpu, reps=3):
+    """CPU leg of the forward-only configurations (oracle port on all host cores, bounded sample): kind "predict" = DGP.predict
+    (models/dgp.py:362-366); kind "acq" = EI.run analytic + exact EHVI over two DGPs (Infill_criteria.py:36-52, EHVI.py:107-157)."""
+    import numpy as np
+    import torch
+    from oracle import dgp_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    S = cfg["S"]
+    probs = [O.synthetic_problem(cfg["D0"], cfg["num_units"], cfg["M"], n_cpu, seed_shift=k) for k in ((0,) if kind == "predict" else (0, 100))]
+    oms = [O.model_from_problem(p, S) for p in probs]
+    X = torch.as_tensor(probs[0]["X"])
+    g = torch.Generator().manual_seed(0)
+    zss = [[torch.randn(S, n_cpu, l.D_out, dtype=torch.float64, generator=g) for l in om.layers] for om in oms]
+    y0 = np.linspace(0.95, 0.05, 32)
+    ynd = O.Y_ND(y0, 1.0 - np.sqrt(y0), (1.1, 1.1), (-0.1, -0.1))
+
+    def once():
+        with torch.no_grad():
+            if kind == "predict":
+                O.predict(oms[0], X, S, zss[0])
+            else:
+                mom = []
+                for om, zs in zip(oms, zss):
+                    _, Fm, Fv = O.propagate(om.layers, X, S, zs)
+                    mom += list(O.mixture_moments(Fm[-1], Fv[-1]))
+                    if om is oms[0]:
+                        O.ei_analytic(Fm[-1], Fv[-1], 0.0)
+                O.ehvi_exact(*mom, ynd[0], ynd[1])
+    once()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    return (time.perf_counter() - t0) / reps, cores
+
+
+def forward_extras(D, synthetic, torch, steps, peak, with_cpu):
+    """BASELINE configs 3 and 5 (forward-only paths; one GPU): device-resident rate, the same through HOST buffers (H2D of the
+    candidates and D2H of the results inside the timed region), the useful FP64 rate against the peak, and the CPU port on a bounded
+    sample. These ride in `extra.configs` of the JSON line; the headline metric stays config 2."""
+    import numpy as np
+    out = {}
+
+    def timed(fn, k, w=2):
+        for i in range(w):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(w + i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+
+    # ---- config 3: 5-layer DGP (6 SVGP layers), D = 20, M = 512, S = 64: predict (predict_y mixture moments), chunks of 8192 points ----
+    cfg = synthetic.CONFIGS["c3"]
+    nb3 = 8192
+    model = synthetic.model_from_problem(synthetic.synthetic_problem(cfg["D0"], cfg["num_units"], cfg["M"], 8), cfg["S"])
+    host = [torch.from_numpy(synthetic.minibatch(cfg["D0"], nb3, 40 + i)[0]).pin_memory() for i in range(3)]
+    dev = [h.cuda() for h in host]
+    res_host = [torch.empty((nb3, 1), dtype=torch.float64).pin_memory() for _ in range(2)]
+    ms = timed(lambda i: model.predict_moments(dev[i % 3], cfg["S"], seed=100 + i), steps)
+
+    def predict_host(i):
+        x = host[i % 3].to("cuda", non_blocking=True)
+        m, v = model.predict_moments(x, cfg["S"], seed=100 + i)
+        res_host[0].copy_(m, non_blocking=True); res_host[1].copy_(v, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    ms_h = timed(predict_host, steps)
+    D._lib.get_context(0).check()
+    f_fwd, _ = synthetic.flops_per_point_sample(cfg["D0"], cfg["num_units"], cfg["M"], S=cfg["S"])
+    ps = nb3 * cfg["S"]
+    ach = f_fwd * ps / (ms * 1e-3) / 1e12
+    out["c3_predict"] = {
+        "metric": "DGP predict point-samples/s", "value": ps / (ms * 1e-3), "unit": "point-samples/s", "ms_per_step": ms,
+        "config": {"workload": "5-layer DGP (6 SVGP layers), D=20, M=512, S=64, predict (predict_y mixture moments), float64; one step = one "
+                               "8192-point chunk of the N = 10 M sweep", "points_per_step": nb3, "samples": cfg["S"]},
+        "roofline": {"bound": "tensor", "kernel": "dgp::fused_forward_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                     "frac": ach / peak, "algorithmic_flops_per_point_sample": f_fwd, "traffic": None},
+        "e2e": {"value": ps / (ms_h * 1e-3), "unit": "point-samples/s", "ms_per_step": ms_h, "h2d_bytes_per_step": nb3 * cfg["D0"] * 8,
+                "d2h_bytes_per_step": nb3 * 2 * 8}}
+    if with_cpu:
+        dt, cores = cpu_forward_baseline("predict", cfg, 64)
+        out["c3_predict"]["cpu_baseline"] = {"value": 64 * cfg["S"] / dt, "unit": "point-samples/s", "cores": cores, "kind": "port",
+                                             "sample": f"64 points x S={cfg['S']} samples per pass ({dt:.2f} s/pass)"}
+    del model, dev
+    torch.cuda.empty_cache()
+
+    # ---- config 5: EI (analytic) + exact 2-objective EHVI, two 3-layer DGPs (D = 8, M = 256), S = 32, chunks of 16384 candidates ----
+    cfg = synthetic.CONFIGS["c2"]
+    nb5 = 16384
+    m0 = synthetic.model_from_problem(synthetic.synthetic_problem(cfg["D0"], cfg["num_units"], cfg["M"], 8), cfg["S"])
+    m1 = synthetic.model_from_problem(synthetic.synthetic_problem(cfg["D0"], cfg["num_units"], cfg["M"], 8, seed_shift=100), cfg["S"])
+    host = [torch.from_numpy(synthetic.minibatch(cfg["D0"], nb5, 60 + i)[0]).pin_memory() for i in range(3)]
+    dev = [h.cuda() for h in host]
+    y0 = np.linspace(0.95, 0.05, 32)
+    ynd = D.Y_ND([y0, 1.0 - np.sqrt(y0)], np.arange(32), nadir=(1.1, 1.1), ideal=(-0.1, -0.1))
+    ms = timed(lambda i: D.EI_and_EHVI([m0, m1], dev[i % 3], ynd, 0.0, S=cfg["S"], seed=[i, 1000 + i]), steps)
+    res_host = [torch.empty((nb5, 1), dtype=torch.float64).pin_memory() for _ in range(2)]
+
+    def acq_host(i):
+        x = host[i % 3].to("cuda", non_blocking=True)
+        ei, eh = D.EI_and_EHVI([m0, m1], x, ynd, 0.0, S=cfg["S"], seed=[i, 1000 + i])
+        res_host[0].copy_(ei, non_blocking=True); res_host[1].copy_(eh, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    ms_h = timed(acq_host, steps)
+    D._lib.get_context(0).check()
+    f_fwd, _ = synthetic.flops_per_point_sample(cfg["D0"], cfg["num_units"], cfg["M"], S=cfg["S"])
+    flops = 2 * f_fwd * nb5 * cfg["S"]     # one propagation per model and candidate (model 0's moments serve EI and EHVI)
+    ach = flops / (ms * 1e-3) / 1e12
+    out["c5_ei_ehvi"] = {
+        "metric": "DGP EI+EHVI candidates/s", "value": nb5 / (ms * 1e-3), "unit": "candidates/s", "ms_per_step": ms,
+        "config": {"workload": "EI (analytic) + exact 2-objective EHVI, two 3-layer DGPs (D=8, M=256), S=32, 32-point Pareto front, float64; "
+                               "one step = one 16384-candidate chunk of the 4 M sweep; model 0 is propagated once for both criteria",
+                   "candidates_per_step": nb5, "samples": cfg["S"]},
+        "roofline": {"bound": "tensor", "kernel": "dgp::fused_forward_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                     "frac": ach / peak, "traffic": None},
+        "e2e": {"value": nb5 / (ms_h * 1e-3), "unit": "candidates/s", "ms_per_step": ms_h, "h2d_bytes_per_step": nb5 * cfg["D0"] * 8,
+                "d2h_bytes_per_step": nb5 * 2 * 8}}
+    if with_cpu:
+        dt, cores = cpu_forward_baseline("acq", cfg, 128)
+        out["c5_ei_ehvi"]["cpu_baseline"] = {"value": 128 / dt, "unit": "candidates/s", "cores": cores, "kind": "port",
+                                             "sample": f"128 candidates x S={cfg['S']} samples, two models, per pass ({dt:.2f} s/pass)"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -140,6 +268,7 @@ def main():
     ap.add_argument("--nb", type=int, default=16384, help="minibatch points per GPU per step")
     ap.add_argument("--nb-cpu", type=int, default=512, help="points of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip extra.configs (configs 3 and 5) and extra.strong_scaling")
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -245,6 +374,25 @@ def main():
         step_host(i)
     ms_e2e, _ = timed(step_host, args.steps)
 
+    # ---- strong scaling: the SAME 16384-point minibatch split over the ranks (north_star: "minibatch points x samples shard across
+    # the GPUs"); at N = 1 this is the headline measurement itself ----
+    strong = None
+    if world > 1 and not args.no_extras:
+        from dgp_toolbox_b200.distributed import shard_bounds
+        lo, hi = shard_bounds(nb, rank, world)
+        sscale = 1.0e6 / nb
+
+        def step_strong(i):
+            X, Y = pool_dev[i % n_pool]
+            return sharded.step(X[lo:hi], Y[lo:hi], n_offset=i * nb + lo, scale=sscale, seed=1234 + i)
+        for i in range(warmup):
+            step_strong(i)
+        ms_strong, _ = timed(step_strong, args.steps)
+        strong = {"points_per_step_total": nb, "points_per_gpu": hi - lo, "ms_per_step": ms_strong / args.steps,
+                  "value": nb * S / (ms_strong / args.steps * 1e-3), "unit": UNIT,
+                  "note": "efficiency = (ms_per_step of the N = 1 run) / (N x this ms_per_step); replicated per-step work "
+                          "(Kuu, Cholesky, operator packing, KL and its adjoint) and the allreduce do not shrink with N"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -326,6 +474,19 @@ def main():
         val, dt, cores = cpu_reference_throughput(cfg, args.nb_cpu, 10, 2)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"N_b={args.nb_cpu} points x S={S} samples, 10 steps after 2 warm-ups ({dt:.2f} s/step)"}
+    extra = {}
+    if strong is not None:
+        strong["efficiency_vs_weak_step"] = ms_step / (world * strong["ms_per_step"])
+        extra["strong_scaling"] = strong
+    if world == 1 and not args.no_extras:
+        del pool_dev, sharded, model
+        torch.cuda.empty_cache()
+        extra["configs"] = forward_extras(D, synthetic, torch, max(2, min(args.steps, 4)), peak, not args.no_cpu_baseline)
+        extra["fp64_pipe"] = {"dmma_dfma_co_issue": False, "source": "profiles/r02_fp64_peaks.json (tools/fp64_peaks.cu: DMMA-only 37.1, "
+                              "DFMA-only 36.5, both in one warp 35.8, warp-specialised 36.4 TFLOP/s: one shared FP64 pipe, so the DMMA "
+                              "peak is the ceiling of the kernels' mixed DMMA + DFMA instruction stream)"}
+    if extra:
+        line["extra"] = extra
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -94,6 +94,30 @@ def EHVI(model_Y, Xcand, YND, corr=False, approximation='None', S=1000, zs=None,
     return out
 
 
+def EI_and_EHVI(model_Y, Xcand, YND, y_min, S=1000, zs=None, seed=None):
+    """-EI of objective 0 (EI.run analytic, Infill_criteria.py:36-47) and the exact EHVI of both objectives (EHVI.py:107-157) for the
+    same candidates from ONE propagation per model: both criteria moment-match the same predict_f samples of model 0, so a
+    4 M-candidate sweep that wants both (BASELINE config 5) does two chains per chunk instead of three. Returns ([N,1], [N,1])."""
+    if not isinstance(model_Y, list) or len(model_Y) != 2 or any(getattr(m, "name", None) != 'dgp' for m in model_Y):
+        raise NotImplementedError("a list of two DGP models is expected")
+    zs = zs or [None, None]
+    seeds = seed if isinstance(seed, (list, tuple)) else [seed, seed]
+    m0, v0 = model_Y[0].predict_moments(Xcand, S, add_lik_var=False, zs=zs[0], seed=seeds[0])
+    m1, v1 = model_Y[1].predict_moments(Xcand, S, add_lik_var=False, zs=zs[1], seed=seeds[1])
+    N, dev = m0.shape[0], m0.device
+    ei = torch.empty((N, 1), dtype=torch.float64, device=dev)
+    out = torch.empty((N, 1), dtype=torch.float64, device=dev)
+    if N == 0:
+        return ei, out
+    y0 = _lib.as_device(np.asarray(YND[0], dtype=np.float64).reshape(-1), dev)
+    y1 = _lib.as_device(np.asarray(YND[1], dtype=np.float64).reshape(-1), dev)
+    ctx = _lib.get_context(dev)
+    ctx.call("dgp_acq_moments", 0, _lib.ptr(m0), _lib.ptr(v0), N, float(y_min), None, 0, _lib.ptr(ei))
+    ctx.call("dgp_ehvi2d", _lib.ptr(m0), _lib.ptr(v0), _lib.ptr(m1), _lib.ptr(v1), N, _lib.ptr(y0), _lib.ptr(y1), int(y0.numel()),
+             _lib.ptr(out))
+    return ei, out
+
+
 def optimize_EHVI(model, YND, popsize_DE=300, popstd_DE=1.5, iterations_DE=400, init_adam=None, lr_adam=0.01, iterations_adam=1000,
                   method='DE', corr=False, approximation='None', S=1000, seed=None, bounds=(0.0, 1.0)):
     """EHVI.py:208-235 for `model` = [dgp0, dgp1] (the two-DGP list path of EHVI()): search the box for the candidate with the

@@ -10,4 +10,4 @@ from .models.dgp import DGP, DGP_Base  # noqa: F401
 from .utils.layers import Layer, SVGP_Layer  # noqa: F401
 from .utils.layer_initializations import init_layers_linear  # noqa: F401
 from .Infill_criteria import EI, EV, WB2, WB2S, EV_one_constraint, PoF  # noqa: F401
-from .EHVI import EHVI, HV_calcul, NDC, Y_ND, optimize_EHVI, psi  # noqa: F401
+from .EHVI import EHVI, EI_and_EHVI, HV_calcul, NDC, Y_ND, optimize_EHVI, psi  # noqa: F401

@@ -82,6 +82,11 @@ _SIG = {
     "dgp_adam_step": (C.c_int, [_vp, C.POINTER(AdamParam), _i, _vp, _vp, _vp, _i64, _d, _d, _d, _d]),
     "dgp_train_adam": (C.c_int, [_vp, C.POINTER(ModelDesc), _vp, _vp, _i64, _i64, _d, _d, _u64, _u64, _i64, C.POINTER(AdamParam), _i,
                                  _vp, _vp, _i64, _i64, _d, _d, _d, _d, _vp, _vp]),
+    "dgp_comm_unique_id": (C.c_int, [_vp]),
+    "dgp_comm_init": (C.c_int, [_vp, _i, _i, _vp]),
+    "dgp_allreduce_grads": (C.c_int, [_vp, _vp, _i64]),
+    "dgp_comm_destroy": (C.c_int, [_vp]),
+    "dgp_elbo_grad_sharded": (C.c_int, [_vp, C.POINTER(ModelDesc), _vp, _vp, _i64, _i64, _d, _u64, _i64, _i, _vp]),
     "dgp_natgrad_step": (C.c_int, [_vp, C.POINTER(ModelDesc), C.POINTER(C.c_int), _i, _d, _vp]),
     "dgp_train_nat_adam": (C.c_int, [_vp, C.POINTER(ModelDesc), _vp, _vp, _i64, _i64, _d, _d, _u64, _u64, _i64, C.POINTER(AdamParam), _i,
                                      _vp, _vp, _i64, _i64, _d, _d, _d, _d, C.POINTER(C.c_int), _i, _d, _vp, _vp]),

@@ -4,6 +4,8 @@
 // and acq.cuh (acquisition epilogues). There is no CPU fallback: without a CUDA device every call fails.
 #include "../../include/dgp_b200.h"
 
+#include <dlfcn.h>
+
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -80,6 +82,9 @@ struct dgp_ctx {
   cudaEvent_t ev_param[2][4] = {{nullptr}};
   int param_pending[2] = {0, 0};
   bool parallel_layers = true;
+  // NCCL communicator of the data-parallel step (dgp_comm_init); the library is resolved at run time (libnccl.so.2)
+  void* nccl_comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
   long launches = 0;                    // kernels launched since the last dgp_reset_launch_count
   // optional per-category device timing (CUDA event pairs around every launch, on the ctx's stream)
   bool profiling = false;
@@ -1371,6 +1376,95 @@ extern "C" {
 
 int dgp_version(void) { return 100; }
 
+// ---- multi-GPU inside the C ABI: points are sharded over ranks by the caller (n_offset = first global point of
+// the shard, kl_weight = 1 / world); the one exchange step of the path is a sum-allreduce of the flat buffer over NVLink ----
+namespace {
+struct NcclUid { char internal[128]; };
+struct NcclApi {
+  int (*GetUniqueId)(NcclUid*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  const char* names[] = {getenv("DGP_B200_NCCL"), "libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) {
+    if (!n) continue;
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) { api.why = "libnccl.so.2 not found (set DGP_B200_NCCL to its path)"; return api; }
+  api.GetUniqueId = reinterpret_cast<int (*)(NcclUid*)>(dlsym(h, "ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<int (*)(void**, int, NcclUid, int)>(dlsym(h, "ncclCommInitRank"));
+  api.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(dlsym(h, "ncclAllReduce"));
+  api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclCommDestroy"));
+  api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+  api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
+  if (!api.ok) api.why = "libnccl is missing a required symbol";
+  return api;
+}
+constexpr int kNcclDouble = 8, kNcclSum = 0;
+void nccl_comm_free(dgp_ctx* c) {
+  if (c->nccl_comm) { nccl_api().CommDestroy(c->nccl_comm); c->nccl_comm = nullptr; c->comm_world = 1; c->comm_rank = 0; }
+}
+}  // namespace
+
+int dgp_comm_unique_id(void* uid_out_128_bytes) {
+  if (!uid_out_128_bytes) return DGP_ERR_ARG;
+  NcclApi& n = nccl_api();
+  if (!n.ok) return DGP_ERR_UNSUPPORTED;
+  return n.GetUniqueId(reinterpret_cast<NcclUid*>(uid_out_128_bytes)) == 0 ? DGP_OK : DGP_ERR_CUDA;
+}
+
+int dgp_comm_init(dgp_ctx* c, int rank, int world, const void* nccl_uid_128_bytes) {
+  if (!c || !nccl_uid_128_bytes || world < 1 || rank < 0 || rank >= world) return DGP_ERR_ARG;
+  NcclApi& n = nccl_api();
+  if (!n.ok) { c->err = n.why; return DGP_ERR_UNSUPPORTED; }
+  CK(cudaSetDevice(c->device));
+  if (c->nccl_comm) { n.CommDestroy(c->nccl_comm); c->nccl_comm = nullptr; }
+  NcclUid uid;
+  memcpy(&uid, nccl_uid_128_bytes, sizeof(uid));
+  const int rc = n.CommInitRank(&c->nccl_comm, world, uid, rank);
+  if (rc != 0) { c->err = std::string("ncclCommInitRank: ") + n.GetErrorString(rc); c->nccl_comm = nullptr; return DGP_ERR_CUDA; }
+  c->comm_rank = rank; c->comm_world = world;
+  return DGP_OK;
+}
+
+int dgp_allreduce_grads(dgp_ctx* c, double* elbo_and_grads, int64_t n_doubles) {
+  if (!c || !elbo_and_grads || n_doubles < 1) return DGP_ERR_ARG;
+  if (!c->nccl_comm) { c->err = "dgp_comm_init has not been called"; return DGP_ERR_ARG; }
+  NcclApi& n = nccl_api();
+  const int rc = n.AllReduce(elbo_and_grads, elbo_and_grads, (size_t)n_doubles, kNcclDouble, kNcclSum, c->nccl_comm, c->stream);
+  if (rc != 0) { c->err = std::string("ncclAllReduce: ") + n.GetErrorString(rc); return DGP_ERR_CUDA; }
+  return DGP_OK;
+}
+
+int dgp_comm_destroy(dgp_ctx* c) {
+  if (!c) return DGP_ERR_ARG;
+  nccl_comm_free(c);
+  return DGP_OK;
+}
+
+// The data-parallel step in ONE call: this rank's shard of the minibatch (points [n_offset, n_offset + N) of the global batch),
+// KL weighted 1 / world, then the sum-allreduce of the flat buffer on the ctx's stream.
+int dgp_elbo_grad_sharded(dgp_ctx* c, const dgp_model_desc* model, const double* X, const double* Y, int64_t N, int64_t S, double scale,
+                          uint64_t seed, int64_t n_offset, int want_grad, double* out_flat) {
+  if (!c || !model) return DGP_ERR_ARG;
+  const int world = c->nccl_comm ? c->comm_world : 1;
+  RC(dgp_elbo_grad(c, model, X, Y, N, S, scale, 1.0 / world, nullptr, seed, n_offset, want_grad, out_flat));
+  if (world > 1) RC(dgp_allreduce_grads(c, out_flat, want_grad ? dgp_grad_size(model) : 3));
+  return DGP_OK;
+}
+
+
 int dgp_ctx_create(int device, void* cuda_stream, dgp_ctx** out) {
   if (!out) return DGP_ERR_ARG;
   *out = nullptr;
@@ -1402,6 +1496,7 @@ void dgp_ctx_destroy(dgp_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   drop_graphs(c);
+  nccl_comm_free(c);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
   if (c->d_seed) cudaFree(c->d_seed);
   if (c->ws) cudaFree(c->ws);

@@ -17,19 +17,40 @@ def shard_bounds(N, rank, world):
 
 
 class ShardedELBO:
-    def __init__(self, model, group=None):
+    def __init__(self, model, group=None, library_comm=True):
+        """library_comm: the allreduce runs inside libdgp_b200 (dgp_comm_init / dgp_allreduce_grads: the library's own NCCL
+        communicator on the ctx's stream) -- torch.distributed only carries the 128-byte ncclUniqueId to the ranks.
+        False, or a CPU model (gloo tests of the host logic): torch.distributed.all_reduce."""
         self.model = model
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._pinned_out = None
+        self._ctx = None
+        if library_comm and self.world > 1 and torch.cuda.is_available() and model.device.type == "cuda":
+            from . import _lib
+            import ctypes as C
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if self.rank == 0:
+                rc = _lib.lib.dgp_comm_unique_id(C.c_void_p(uid.data_ptr()))
+                if rc != 0:
+                    raise _lib.DGPError(f"dgp_comm_unique_id failed ({rc}): libnccl.so.2 could not be loaded")
+            uid_dev = uid.to(model.device)
+            dist.broadcast(uid_dev, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            uid = uid_dev.cpu()
+            self._ctx = _lib.get_context(model.device)
+            self._ctx.call("dgp_comm_init", self.rank, self.world, C.c_void_p(uid.data_ptr()))
 
     def step(self, X_local, Y_local, n_offset, scale=1.0, want_grad=True, seed=None, zs=None):
         """Device-resident shard in, reduced flat device buffer out."""
         flat = self.model.elbo_flat((X_local, Y_local), want_grad=want_grad, scale=scale, kl_weight=1.0 / self.world,
                                     seed=seed, n_offset=n_offset, zs=zs)
         if self.world > 1:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            if self._ctx is not None:
+                from . import _lib
+                self._ctx.call("dgp_allreduce_grads", _lib.ptr(flat), flat.numel())
+            else:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
         return flat
 
     def train_adam_step(self, X_local, Y_local, n_offset, params, state, t, lr=0.01, beta_1=0.9, beta_2=0.999, epsilon=1e-7,

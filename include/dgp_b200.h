@@ -176,6 +176,21 @@ int dgp_train_adam(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, c
                    int n_params, double* m_state, double* v_state, int64_t t0, int64_t steps, double lr, double beta1,
                    double beta2, double epsilon, double* out_flat, double* elbo_trace);
 
+/* ---- multi-GPU: one process (or thread) and one ctx per GPU. The minibatch's points are sharded over the ranks by
+ * the caller; parameters, Kuu, its Cholesky and the KL term are replicated; the path's only exchange step is ONE sum-allreduce of the
+ * flat [data term, KL, gradients] buffer (NCCL over NVLink / NVSwitch, on the ctx's stream). NCCL is resolved at run time
+ * (libnccl.so.2, or the path in DGP_B200_NCCL); DGP_ERR_UNSUPPORTED when it cannot be loaded.
+ *   dgp_comm_unique_id: rank 0 creates the 128-byte ncclUniqueId and distributes it by any means (MPI, a file, torch.distributed).
+ *   dgp_comm_init: collective over all ranks. dgp_allreduce_grads: in place, asynchronous on the ctx's stream.
+ *   dgp_elbo_grad_sharded: dgp_elbo_grad on this rank's shard (n_offset = global index of its first point, so the Philox draws do
+ *   not depend on the placement; KL weighted 1 / world) followed by the allreduce -- every rank ends with the full-batch buffer. */
+int dgp_comm_unique_id(void* uid_out_128_bytes);
+int dgp_comm_init(dgp_ctx* ctx, int rank, int world, const void* nccl_uid_128_bytes);
+int dgp_allreduce_grads(dgp_ctx* ctx, double* elbo_and_grads, int64_t n_doubles);
+int dgp_comm_destroy(dgp_ctx* ctx);
+int dgp_elbo_grad_sharded(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, const double* Y, int64_t N, int64_t S,
+                          double scale, uint64_t seed, int64_t n_offset, int want_grad, double* out_flat);
+
 /* GPflow NaturalGradient(gamma).minimize on the (q_mu, q_sqrt) pairs of the listed layers (models/dgp.py:188,218,312,343; default
  * XiNat parameterisation: theta <- theta - gamma d(-ELBO)/d eta, theta = (S^-1 mu, -S^-1/2), eta = (mu, S + mu mu^T), S = q_sqrt
  * q_sqrt^T), from the gradients a dgp_elbo_grad call left in grad_flat. Collapsed form, per output d: T = tril(q_sqrt_d^T G_R),
