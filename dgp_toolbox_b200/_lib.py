@@ -82,6 +82,12 @@ _SIG = {
     "dgp_adam_step": (C.c_int, [_vp, C.POINTER(AdamParam), _i, _vp, _vp, _vp, _i64, _d, _d, _d, _d]),
     "dgp_train_adam": (C.c_int, [_vp, C.POINTER(ModelDesc), _vp, _vp, _i64, _i64, _d, _d, _u64, _u64, _i64, C.POINTER(AdamParam), _i,
                                  _vp, _vp, _i64, _i64, _d, _d, _d, _d, _vp, _vp]),
+    "dgp_comp_K": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _vp]),
+    "dgp_comp_Kdiag": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "dgp_comp_K_grad": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "dgp_comp_Kdiag_grad": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "dgp_svgp_from_k": (C.c_int, [_vp, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dgp_svgp_from_k_grad": (C.c_int, [_vp, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _vp, _vp, _vp, _vp]),
     "dgp_comm_unique_id": (C.c_int, [_vp]),
     "dgp_comm_init": (C.c_int, [_vp, _i, _i, _vp]),
     "dgp_allreduce_grads": (C.c_int, [_vp, _vp, _i64]),

@@ -17,6 +17,8 @@
 #include "fused.cuh"
 #include "fused_bwd.cuh"
 #include "fullcov.cuh"
+#include "extk.cuh"
+#include "compkern.cuh"
 #include "gemm.cuh"
 #include "layer.cuh"
 #include "philox.cuh"
@@ -423,7 +425,7 @@ std::vector<PanelDesc> build_schedule(int Mp, int BM, int D_out, bool vform) {
 enum PrepLevel { PREP_FWD = 0, PREP_KL = 1, PREP_GRAD = 2 };
 
 int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& lw, PrepLevel level, bool vform_grad_ok = true,
-                bool defer_late = false) {
+                bool defer_late = false, const double* const* Ku_ext = nullptr) {
   const int nl = model->num_layers;
   lw.assign(nl, LayerWs());
   std::vector<CholArgs> hargs(nl);
@@ -493,7 +495,8 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
     const dgp_layer_desc& d = model->layers[l];
     LayerWs& w = lw[l];
     const long mm = (long)w.Mp * w.Mp;
-    LAUNCH(kuu_build_kernel, (unsigned)((mm + 255) / 256), 256, 0, d.Z, d.lengthscales, d.variance, w.M, w.Mp, w.D_in, d.jitter, w.Ku, w.Knj, d.kernel_kind);
+    if (Ku_ext && Ku_ext[l]) LAUNCH(pad_square_identity_kernel, (unsigned)((mm + 255) / 256), 256, 0, Ku_ext[l], w.M, w.Mp, w.Ku);   // caller's Kuu + jitter I
+    else LAUNCH(kuu_build_kernel, (unsigned)((mm + 255) / 256), 256, 0, d.Z, d.lengthscales, d.variance, w.M, w.Mp, w.D_in, d.jitter, w.Ku, w.Knj, d.kernel_kind);
     const long np = mm * w.D_out > (long)w.Mp * 32 ? mm * w.D_out : (long)w.Mp * 32;
     LAUNCH(pad_params_kernel, (unsigned)((np + 255) / 256), 256, 0, d.q_sqrt, d.q_mu, w.M, w.Mp, w.D_out, w.RpT, w.Rcat, w.qmuP);
   }
@@ -1782,6 +1785,201 @@ int dgp_propagate_full_cov(dgp_ctx* c, const dgp_model_desc* model, const double
   c->used = 0;
   RC(run_full_cov(c, model, X, N, S, zs_host, seed, n_offset, Fs_host, Fmeans_host, Fvars_host));
   return check_chol(c);
+}
+
+namespace {
+CompK comp_view(const dgp_comp_kernel* k) {
+  CompK v;
+  v.D = k->D; v.Da = k->Da; v.has_prod = k->has_prod; v.has_linear = k->has_linear && k->lin_variance; v.in_ard = k->in_ard;
+  v.in_var = k->in_variance; v.in_ls = k->in_lengthscales; v.corr_var = k->corr_variance; v.corr_ls = k->corr_lengthscale;
+  v.prev_var = k->prev_variance; v.prev_ls = k->prev_lengthscale; v.lin_var = k->lin_variance; v.white_var = k->white_variance;
+  return v;
+}
+int comp_check(dgp_ctx* c, const dgp_comp_kernel* k) {
+  if (!k || k->D < 1 || k->D > kCompMaxD || k->Da < 1 || k->Da > k->D || !k->in_variance || !k->in_lengthscales) {
+    c->err = "composite kernel: need 1 <= Da <= D <= 32 and the k_in parameters"; return DGP_ERR_ARG;
+  }
+  if (k->has_prod && (k->Da >= k->D || !k->corr_variance || !k->corr_lengthscale || !k->prev_variance || !k->prev_lengthscale)) {
+    c->err = "composite kernel: the product part needs Da < D and the k_corr / k_prev parameters"; return DGP_ERR_ARG;
+  }
+  return DGP_OK;
+}
+
+// The layer's conditional (and, with Gm, its adjoint) on supplied kernel matrices: A-form GEMM pipeline, one pass over all P.
+int svgp_from_k_run(dgp_ctx* c, int M, int D, long P, const double* Ku, const double* Kuf, const double* Kdiag, const double* q_mu,
+                    const double* q_sqrt, double* mean, double* var, double* kl, const double* Gm, const double* Gv, double gkl,
+                    double* dKu, double* dKuf, double* dKdiag, double* dq_mu, double* dq_sqrt) {
+  const bool grad = Gm != nullptr;
+  // a descriptor that satisfies check_layer: the kernel fields are never read (Ku is supplied, the fused kernels are off)
+  dgp_layer_desc d;
+  memset(&d, 0, sizeof(d));
+  d.D_in = 1; d.D_out = D; d.M = M; d.white = 0; d.mean_kind = 0; d.kernel_kind = 0;
+  d.Z = Ku; d.lengthscales = Ku; d.variance = Ku; d.q_mu = q_mu; d.q_sqrt = q_sqrt; d.jitter = 0.0;
+  dgp_model_desc model{1, &d, nullptr};
+  std::vector<LayerWs> lw;
+  const bool fused_saved = c->use_fused;
+  c->use_fused = false;
+  const double* kext[1] = {Ku};
+  int rc = prep_layers(c, &model, lw, grad ? PREP_GRAD : PREP_KL, false, false, kext);
+  c->use_fused = fused_saved;
+  RC(rc);
+  LayerWs& w = lw[0];
+  const int Mp = w.Mp;
+  const long Pp = round_up(P, kTileP);
+  const size_t plane = (size_t)Mp * Pp;
+  if ((plane * (size_t)(5 + D) + (size_t)Pp * 80) * sizeof(double) + c->used > c->ws_limit) {
+    c->err = "dgp_svgp_from_k: P too large for the workspace limit (dgp_set_workspace_limit); split the points"; return DGP_ERR_UNSUPPORTED;
+  }
+  double *K = walloc(c, plane), *V = walloc(c, plane), *A = walloc(c, plane), *T = walloc(c, plane * D);
+  double *dA = nullptr, *W = nullptr, *GvT = nullptr, *GmPad = nullptr, *gq = nullptr, *part = nullptr, *dummy = nullptr;
+  size_t partcap = 0;
+  if (grad) {
+    dA = walloc(c, plane); W = walloc(c, plane);
+    GvT = walloc(c, (size_t)D * Pp); GmPad = walloc(c, (size_t)Pp * 32); gq = walloc(c, (size_t)Pp);
+    partcap = max_splitk_part(c, lw);
+    part = walloc(c, partcap);
+    dummy = walloc(c, 64);
+  }
+  if (c->dry) return DGP_OK;
+  CAT(DGP_CAT_GEMM_FWD);
+  LAUNCH(pad_plane_kernel, (unsigned)((plane + 255) / 256), 256, 0, Kuf, M, Mp, P, Pp, K);
+  GemmArgs g = gargs(w.Linv, Mp, K, Pp, V, Pp, Mp, (int)Pp, Mp);       // V = Lu^-1 Kuf          (layers.py:245)
+  g.a_tri = 1;
+  RC(gemm(c, g, false));
+  g = gargs(w.LinvT, Mp, V, Pp, A, Pp, Mp, (int)Pp, Mp);               // A = Lu^-T V            (layers.py:247)
+  g.a_tri = 2;
+  RC(gemm(c, g, false));
+  g = gargs(w.RpT, Mp, A, Pp, T, Pp, Mp, (int)Pp, Mp);                 // T_d = q_sqrt_d^T A     (layers.py:257-271)
+  g.a_tri = 2; g.batch = D; g.sA = (long)Mp * Mp; g.sB = 0; g.sC = (long)Mp * Pp;
+  RC(gemm(c, g, false));
+  if (mean) {
+    CAT(DGP_CAT_MOMENTS);
+    LAUNCH(moments_ext_kernel, (unsigned)((P + 127) / 128), 128, 0, V, A, T, w.qmuP, Kdiag, M, Mp, D, P, Pp, mean, var);
+  }
+  if (kl) CK(cudaMemcpyAsync(kl, w.kl, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  if (!grad) return DGP_OK;
+  // ---- adjoint (SURVEY §9, A-form) ----
+  CAT(DGP_CAT_OTHER);
+  LAUNCH(upstream_ext_kernel, (unsigned)(Pp / 128), 128, 0, Gm, Gv, P, Pp, D, GvT, GmPad, gq, dKdiag);
+  CAT(DGP_CAT_GEMM_BWD_DATA);
+  g = gargs(w.qmuP, 32, GmPad, 32, dA, Pp, Mp, (int)Pp, 32);          // dA' = q_mu Gm^T + sum_d R_d (2 Gv_d o T_d)
+  RC(gemm(c, g, true));
+  g = gargs(w.Rcat, (long)D * Mp, T, Pp, dA, Pp, Mp, (int)Pp, D * Mp);
+  g.a_tri = 1; g.kblocks = D; g.kblk = Mp; g.bscale = GvT; g.ld_bscale = Pp; g.bscale_mul = 2.0; g.beta = 1.0;
+  if (D == 1) g.kblocks = 1;
+  RC(gemm(c, g, false));
+  g = gargs(w.Kinv, Mp, dA, Pp, W, Pp, Mp, (int)Pp, Mp);               // W = Ku^-1 dA'
+  RC(gemm(c, g, false));
+  CAT(DGP_CAT_RBF_BWD);
+  LAUNCH(kbar_ext_kernel, (unsigned)(((size_t)M * Pp + 255) / 256), 256, 0, W, A, gq, M, P, Pp, dKuf);
+  CAT(DGP_CAT_GEMM_BWD_PARAM);
+  GemmArgs pg[3];
+  const bool pnt[3] = {true, true, false};
+  pg[0] = gargs(W, Pp, A, Pp, w.dKu, Mp, Mp, Mp, (int)Pp);             // dKu (data part) = -Wg A^T
+  pg[0].alpha = -1.0;
+  pg[1] = gargs(A, Pp, T, Pp, w.dR, Mp, Mp, Mp, (int)Pp);              // dq_sqrt_d (data part) = tril(A diag(2 Gv_d) T_d^T)
+  pg[1].alpha = 2.0; pg[1].batch = D; pg[1].sA = 0; pg[1].sB = (long)Mp * Pp; pg[1].sC = (long)Mp * Mp; pg[1].c_lower = 1;
+  pg[1].kscale = GvT; pg[1].sScale = Pp;
+  pg[2] = gargs(A, Pp, GmPad, 32, w.dqmu, 32, Mp, 32, (int)Pp);        // dq_mu (data part) = A Gm
+  CK(cudaMemsetAsync(w.dR, 0, (size_t)D * Mp * Mp * sizeof(double), c->stream));   // c_lower leaves the upper tiles unwritten
+  for (int i = 0; i < 3; ++i) {
+    pg[i].splitk = pick_splitk(c, pg[i], pnt[i]);
+    if (pg[i].splitk > 1 && (size_t)pg[i].splitk * pg[i].batch * pg[i].M * pg[i].N > partcap) pg[i].splitk = 1;
+    pg[i].part = part;
+    RC(gemm(c, pg[i], pnt[i]));
+  }
+  // ---- KL adjoint (weighted by gkl: the caller's d loss / d kl) and unpadding ----
+  CAT(DGP_CAT_PREP);
+  const long mm = (long)Mp * Mp;
+  LAUNCH(dku_assemble_kernel, (unsigned)((mm + 255) / 256), 256, 0, w.dKu, w.Kinv, w.KSK, w.alpha, w.Knj, M, Mp, D, -gkl, 1);
+  LAUNCH(unpad_square_kernel, (unsigned)(((long)M * M + 255) / 256), 256, 0, w.dKu, M, Mp, dKu);
+  FinalizeArgs f;
+  memset(&f, 0, sizeof(f));
+  f.Gd = w.dR; f.gd_cat = 0; f.KR = w.KRcat; f.Rcat = w.Rcat; f.dqmu = w.dqmu; f.alpha = w.alpha; f.H = nullptr; f.dZk = dummy;
+  f.rbf_red = nullptr; f.kuu_red = dummy; f.sgv = nullptr; f.Z = dummy; f.ls = dummy; f.M = M; f.Mp = Mp; f.D_in = 0; f.D_out = D;
+  f.klw = -gkl; f.white = 0; f.qmuP = w.qmuP;
+  f.dZ = dummy; f.dls = dummy; f.dvar = dummy + 32; f.dq_mu = dq_mu; f.dq_sqrt = dq_sqrt;
+  const long nq = (long)D * M * M;
+  LAUNCH(finalize_layer_kernel, (unsigned)((nq + 255) / 256), 256, 0, f);
+  return DGP_OK;
+}
+}  // namespace
+
+int dgp_comp_K(dgp_ctx* c, const dgp_comp_kernel* k, const double* X, int64_t P, const double* X2, int64_t P2, double* K_out) {
+  if (!c || !X || !K_out || P < 1 || (X2 && P2 < 1)) return DGP_ERR_ARG;
+  RC(comp_check(c, k));
+  CK(cudaSetDevice(c->device));
+  const long n2 = X2 ? P2 : P;
+  CAT(DGP_CAT_KUF);
+  LAUNCH(compk_K_kernel, (unsigned)((P * n2 + 255) / 256), 256, 0, comp_view(k), X, (long)P, X2, n2, K_out);
+  return DGP_OK;
+}
+
+int dgp_comp_Kdiag(dgp_ctx* c, const dgp_comp_kernel* k, const double* X, int64_t P, double* out) {
+  if (!c || !X || !out || P < 1) return DGP_ERR_ARG;
+  RC(comp_check(c, k));
+  CK(cudaSetDevice(c->device));
+  CAT(DGP_CAT_KUF);
+  LAUNCH(compk_Kdiag_kernel, (unsigned)((P + 255) / 256), 256, 0, comp_view(k), X, (long)P, out);
+  return DGP_OK;
+}
+
+int dgp_comp_K_grad(dgp_ctx* c, const dgp_comp_kernel* k, const double* X, int64_t P, const double* X2, int64_t P2,
+                    const double* Kbar, double* dX, double* dX2, double* dtheta) {
+  if (!c || !X || !Kbar || !dX || !dtheta || P < 1 || (X2 && (P2 < 1 || !dX2))) return DGP_ERR_ARG;
+  RC(comp_check(c, k));
+  CK(cudaSetDevice(c->device));
+  const long n2 = X2 ? P2 : P;
+  const int nt = kCompTheta + (k->in_ard ? k->Da : 1);
+  RC(ensure_ws(c, (size_t)P * nt * sizeof(double)));
+  double* part = reinterpret_cast<double*>(c->ws);
+  CAT(DGP_CAT_RBF_BWD);
+  LAUNCH(compk_grad_rows_kernel, (unsigned)P, 128, 0, comp_view(k), X, (long)P, X2, n2, Kbar, dX, part);
+  LAUNCH(reduce_partials_kernel, nt, 256, 0, part, (long)P, nt, dtheta, 0);
+  if (X2) LAUNCH(compk_grad_cols_kernel, (unsigned)((P2 + 127) / 128), 128, 0, comp_view(k), X, (long)P, X2, (long)P2, Kbar, dX2);
+  return DGP_OK;
+}
+
+int dgp_comp_Kdiag_grad(dgp_ctx* c, const dgp_comp_kernel* k, const double* X, int64_t P, const double* g, double* dX, double* dtheta) {
+  if (!c || !X || !g || !dX || !dtheta || P < 1) return DGP_ERR_ARG;
+  RC(comp_check(c, k));
+  CK(cudaSetDevice(c->device));
+  const int nt = kCompTheta + (k->in_ard ? k->Da : 1);
+  const long nb = (P + 127) / 128;
+  RC(ensure_ws(c, (size_t)nb * nt * sizeof(double)));
+  double* part = reinterpret_cast<double*>(c->ws);
+  CAT(DGP_CAT_RBF_BWD);
+  LAUNCH(compk_Kdiag_grad_kernel, (unsigned)nb, 128, 0, comp_view(k), X, (long)P, g, dX, part);
+  LAUNCH(reduce_partials_kernel, nt, 256, 0, part, nb, nt, dtheta, 0);
+  return DGP_OK;
+}
+
+int dgp_svgp_from_k(dgp_ctx* c, int M, int D_out, int64_t P, const double* Ku, const double* Kuf, const double* Kdiag,
+                    const double* q_mu, const double* q_sqrt, double* mean, double* var, double* kl) {
+  if (!c || !Ku || !Kuf || !Kdiag || !q_mu || !q_sqrt || !mean || !var || M < 1 || D_out < 1 || D_out > kMaxD || P < 1) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  c->dry = true; c->used = 0;
+  int rc = svgp_from_k_run(c, M, D_out, P, Ku, Kuf, Kdiag, q_mu, q_sqrt, mean, var, kl, nullptr, nullptr, 0.0, nullptr, nullptr, nullptr, nullptr, nullptr);
+  c->dry = false;
+  if (rc != DGP_OK) return rc;
+  RC(ensure_ws(c, c->used));
+  c->used = 0;
+  return svgp_from_k_run(c, M, D_out, P, Ku, Kuf, Kdiag, q_mu, q_sqrt, mean, var, kl, nullptr, nullptr, 0.0, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+int dgp_svgp_from_k_grad(dgp_ctx* c, int M, int D_out, int64_t P, const double* Ku, const double* Kuf, const double* Kdiag,
+                         const double* q_mu, const double* q_sqrt, const double* Gm, const double* Gv, double gkl,
+                         double* dKu, double* dKuf, double* dKdiag, double* dq_mu, double* dq_sqrt) {
+  if (!c || !Ku || !Kuf || !Kdiag || !q_mu || !q_sqrt || !Gm || !Gv || !dKu || !dKuf || !dKdiag || !dq_mu || !dq_sqrt || M < 1 ||
+      D_out < 1 || D_out > kMaxD || P < 1) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  c->dry = true; c->used = 0;
+  int rc = svgp_from_k_run(c, M, D_out, P, Ku, Kuf, Kdiag, q_mu, q_sqrt, nullptr, nullptr, nullptr, Gm, Gv, gkl, dKu, dKuf, dKdiag, dq_mu, dq_sqrt);
+  c->dry = false;
+  if (rc != DGP_OK) return rc;
+  RC(ensure_ws(c, c->used));
+  c->used = 0;
+  return svgp_from_k_run(c, M, D_out, P, Ku, Kuf, Kdiag, q_mu, q_sqrt, nullptr, nullptr, nullptr, Gm, Gv, gkl, dKu, dKuf, dKdiag, dq_mu, dq_sqrt);
 }
 
 int64_t dgp_grad_size(const dgp_model_desc* model) {

@@ -176,6 +176,41 @@ int dgp_train_adam(dgp_ctx* ctx, const dgp_model_desc* model, const double* X, c
                    int n_params, double* m_state, double* v_state, int64_t t0, int64_t steps, double lr, double beta1,
                    double beta2, double epsilon, double* out_flat, double* elbo_trace);
 
+/* ---- composite kernels and layers on supplied kernel matrices (MF-DGP, MF_DGP.py:262-290) ----
+ * k(x, y) = k_corr(x_a, y_a) (k_prev(x_b, y_b) + s_l^2 <x_b, y_b>) + k_in(x_a, y_a), + s_w^2 on the diagonal of K(X, X) and in K_diag;
+ * a = the first Da of the D input columns, b = the rest. k_corr, k_prev: isotropic SquaredExponential; k_in: SquaredExponential, ARD
+ * (in_ard = 1, Da lengthscales) or isotropic. has_prod = 0: k_in (+ White) alone. All pointers are DEVICE pointers to the parameter
+ * values (scalars unless noted); white_variance / lin_variance may be NULL. */
+typedef struct {
+  int32_t D, Da, has_prod, has_linear, in_ard;
+  const double* in_variance; const double* in_lengthscales;       /* [1], [Da] or [1] */
+  const double* corr_variance; const double* corr_lengthscale;    /* [1], [1] */
+  const double* prev_variance; const double* prev_lengthscale;    /* [1], [1] */
+  const double* lin_variance; const double* white_variance;       /* [1] or NULL */
+} dgp_comp_kernel;
+#define DGP_COMP_THETA 7   /* d/d theta layout: in_var, corr_var, corr_ls, prev_var, prev_ls, lin_var, white_var, then in_ls[Da or 1] */
+
+/* kern.K(X, X2) [P, P2] (X2 = NULL: K(X, X) [P, P] including the White diagonal) and kern.K_diag(X) [P] (gpflow Sum / Product /
+ * SquaredExponential / Linear / White semantics with active_dims). */
+int dgp_comp_K(dgp_ctx* ctx, const dgp_comp_kernel* k, const double* X, int64_t P, const double* X2, int64_t P2, double* K_out);
+int dgp_comp_Kdiag(dgp_ctx* ctx, const dgp_comp_kernel* k, const double* X, int64_t P, double* out);
+/* Adjoints: given Kbar = d loss / d K [P, P2] -> dX [P, D], dX2 [P2, D] (NULL with X2 = NULL: dX then carries both roles) and
+ * dtheta [DGP_COMP_THETA + (in_ard ? Da : 1)]; given g = d loss / d K_diag [P] -> dX, dtheta. Deterministic reductions. */
+int dgp_comp_K_grad(dgp_ctx* ctx, const dgp_comp_kernel* k, const double* X, int64_t P, const double* X2, int64_t P2,
+                    const double* Kbar, double* dX, double* dX2, double* dtheta);
+int dgp_comp_Kdiag_grad(dgp_ctx* ctx, const dgp_comp_kernel* k, const double* X, int64_t P, const double* g, double* dX, double* dtheta);
+
+/* SVGP_Layer.conditional_ND + KL (utils/layers.py:237-308, white = False, no mean function) on supplied matrices: Ku [M, M] =
+ * Kuu + jitter I, Kuf [M, P], Kdiag [P]; q_mu [M, D_out], q_sqrt [D_out, M, M]. -> mean, var [P, D_out], kl [1].
+ * dgp_svgp_from_k_grad: adjoint for upstream gradients Gm = d loss / d mean, Gv = d loss / d var [P, D_out] and gkl = d loss / d kl:
+ * dKu [M, M], dKuf [M, P], dKdiag [P], dq_mu [M, D_out], dq_sqrt [D_out, M, M] (lower triangle). The M^2 P contractions run in
+ * the FP64 DMMA GEMM engine; the kernel matrices and their adjoints are the caller's (dgp_comp_K / dgp_comp_K_grad). */
+int dgp_svgp_from_k(dgp_ctx* ctx, int M, int D_out, int64_t P, const double* Ku, const double* Kuf, const double* Kdiag,
+                    const double* q_mu, const double* q_sqrt, double* mean, double* var, double* kl);
+int dgp_svgp_from_k_grad(dgp_ctx* ctx, int M, int D_out, int64_t P, const double* Ku, const double* Kuf, const double* Kdiag,
+                         const double* q_mu, const double* q_sqrt, const double* Gm, const double* Gv, double gkl,
+                         double* dKu, double* dKuf, double* dKdiag, double* dq_mu, double* dq_sqrt);
+
 /* ---- multi-GPU: one process (or thread) and one ctx per GPU. The minibatch's points are sharded over the ranks by
  * the caller; parameters, Kuu, its Cholesky and the KL term are replicated; the path's only exchange step is ONE sum-allreduce of the
  * flat [data term, KL, gradients] buffer (NCCL over NVLink / NVSwitch, on the ctx's stream). NCCL is resolved at run time
