@@ -14,3 +14,5 @@ from .EHVI import EHVI, EI_and_EHVI, HV_calcul, NDC, Y_ND, optimize_EHVI, psi  #
 from . import composite  # noqa: F401  (composite kernels with active_dims, layers on supplied kernel matrices: SURVEY §8 f2)
 from .models import MF_DGP  # noqa: F401
 from .models.MF_DGP import MultiFidelityDeepGP  # noqa: F401
+from .models import MF_DGP_EM  # noqa: F401
+from .models.MF_DGP_EM import MultiFidelityDeepGP_EM  # noqa: F401

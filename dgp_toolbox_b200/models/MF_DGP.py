@@ -28,7 +28,7 @@ class _Feature(_Module):
 class MFLayer(_Module):
     """SVGP_Layer(kern, Z, num_outputs, Zero(), augmented=…, layers=…) of utils/layers.py:180-224 for composite kernels."""
 
-    def __init__(self, kern, Z, num_outputs, mean_function=None, augmented=False, layers=None, draw=None):
+    def __init__(self, kern, Z, num_outputs, mean_function=None, augmented=False, layers=None, draw=None, layers_red=None):
         Z = np.asarray(Z.numpy() if hasattr(Z, "numpy") else Z, dtype=np.float64)
         self.kern = kern
         self.num_outputs = int(num_outputs)
@@ -43,7 +43,11 @@ class MFLayer(_Module):
         else:
             self.feature.Z_left = Parameter(Z, name="Z_left")
             with torch.no_grad():      # utils/layers.py:210-213: 100 propagated samples of Z_left through the earlier layers
-                self.feature.Z_right = sample_Z_right_array_all_layers(layers, self.feature.Z_left.value, 100, draw)
+                if layers_red is None:
+                    self.feature.Z_right = sample_Z_right_array_all_layers(layers, self.feature.Z_left.value, 100, draw)
+                else:      # embedded mapping: Z_left lives in this fidelity's input space (utils/layers_red.py:110-129)
+                    from .MF_DGP_EM import sample_Z_right as _szr_em
+                    self.feature.Z_right = _szr_em(layers, layers_red, self.feature.Z_left.value, None, draw, 100)
             self.feature.Z = torch.cat([self.feature.Z_left.value, self.feature.Z_right], 1)
             Zfull = self.feature.Z
         self.D = Zfull.shape[1]

@@ -11,14 +11,19 @@ from .base import Module, Parameter
 
 
 class InducingPoints(Module):
-    def __init__(self, Z=None, layers=None, name=None):
+    def __init__(self, Z=None, layers=None, layers_red=None, name=None):
         Module.__init__(self, name=name)
         if layers is None:
             self.Z = Parameter(Z)
         else:
-            from dgp_dace.utils.layers import sample_Z_right_array_all_layers
             self.Z_left = Z if isinstance(Z, Parameter) else Parameter(Z)
-            self.Z_right = tf.convert_to_tensor(sample_Z_right_array_all_layers(layers, self.Z_left.numpy(), 100)).detach()
+            if layers_red is None:
+                from dgp_dace.utils.layers import sample_Z_right_array_all_layers
+                zr = sample_Z_right_array_all_layers(layers, self.Z_left.numpy(), 100)
+            else:      # embedded-mapping variant (utils/layers_red.py:110-129,162-163)
+                from dgp_dace.utils.layers_red import sample_Z_right_array_all_layers
+                zr = sample_Z_right_array_all_layers(layers, layers_red, self.Z_left.numpy(), 100)
+            self.Z_right = tf.convert_to_tensor(zr).detach()
             self.Z = tf.concat([self.Z_left, self.Z_right], 1)
 
     def __len__(self):
