@@ -255,6 +255,42 @@ def forward_extras(D, synthetic, torch, steps, peak, with_cpu):
         dt, cores = cpu_forward_baseline("acq", cfg, 128)
         out["c5_ei_ehvi"]["cpu_baseline"] = {"value": 128 / dt, "unit": "candidates/s", "cores": cores, "kind": "port",
                                              "sample": f"128 candidates x S={cfg['S']} samples, two models, per pass ({dt:.2f} s/pass)"}
+    del m0, m1, dev
+    torch.cuda.empty_cache()
+
+    # ---- config 4: multi-fidelity DGP with embedded mapping (MF_DGP_EM.py), 3 fidelities (input spaces of 2, 3, 4 dimensions), M = 256,
+    # ELBO + every gradient on one minibatch of the N = 500 k data set (the full data set in one evaluation would need the [S, N] planes
+    # of 50 M point-samples; the reference has no minibatching either) ----
+    from dgp_toolbox_b200.models import MF_DGP_EM
+    rng = np.random.default_rng(0)
+    dims, n4, S4 = [2, 3, 4], [32768, 8192, 2048], 10
+    f4 = lambda x: np.sin(3 * x[:, :1]) + 0.5 * x[:, 1:2]
+    X = [rng.uniform(0, 1, (n, d)) for n, d in zip(n4, dims)]
+    Y = [f4(X[0]), 1.2 * f4(X[1]) + 0.3 * X[1][:, :1] ** 2, 1.5 * f4(X[2]) - 0.2 * X[2][:, 1:2]]
+    em = MF_DGP_EM.DGP_Base.make_mf_dgp(X, [rng.uniform(0, 1, (256, d)) for d in dims], [rng.uniform(0, 1, (256, 4)), rng.uniform(0, 1, (256, 3))])
+    em.num_samples = S4
+    Xh = [torch.from_numpy(x).pin_memory() for x in X + Y + [X[1][:, :2].copy(), X[2][:, :2].copy()]]
+    to_dev = lambda: [h.to("cuda", non_blocking=True) for h in Xh]
+    d4 = to_dev()
+    params = em.trainable_parameters
+    ms = timed(lambda i: em.ELBO_and_grads((d4[0:3], d4[3:6], d4[6:8]), params), steps, w=1)
+
+    def em_host(i):
+        d = to_dev()
+        elbo, grads = em.ELBO_and_grads((d[0:3], d[3:6], d[6:8]), params)
+        torch.cat([elbo.reshape(1)] + [grads[p].reshape(-1) for p in params]).cpu()
+    ms_h = timed(em_host, steps, w=1)
+    ps4 = sum(n4) * S4
+    out["c4_mf_dgp_em"] = {
+        "metric": "MF-DGP-EM ELBO+grad point-samples/s", "value": ps4 / (ms * 1e-3), "unit": "point-samples/s", "ms_per_step": ms,
+        "config": {"workload": "multi-fidelity DGP with embedded mapping (MF_DGP_EM.py), 3 fidelities with 2/3/4-D inputs, M=256, S=10, one "
+                               "minibatch of 32768 / 8192 / 2048 points per fidelity, ELBO + every gradient, float64", "point_samples_per_step": ps4},
+        "roofline": None,
+        "e2e": {"value": ps4 / (ms_h * 1e-3), "unit": "point-samples/s", "ms_per_step": ms_h,
+                "h2d_bytes_per_step": int(sum(h.numel() for h in Xh) * 8), "d2h_bytes_per_step": int(sum(p.value.numel() for p in params) * 8 + 8)},
+        "cpu_baseline": None,
+        "note": "composite-kernel layers run the unfused GEMM pipeline on supplied kernel matrices (DESIGN.md §6); no CPU port of this model "
+                "exists in oracle/ (parity is against the reference's own MF_DGP_EM.py executed under tests/ref_shim, tests/golden/mf_dgp_em.npz)"}
     return out
 
 
