@@ -126,17 +126,34 @@ def _scalar(v):
     return float(v.item() if hasattr(v, "item") else v)
 
 
-def _moment_criterion(kind, model, x, y, num_samples, zs, seed, with_x=False):
+def _moment_scratch(model, N, D):
+    """One (mean, var) pair per model and population size, reused by every criterion evaluation of a search: temporaries whose
+    addresses stay put so a captured graph can be replayed."""
+    cache = model.__dict__.setdefault("_moment_bufs", {})
+    key = (N, D, str(model.device))
+    if key not in cache:
+        if len(cache) >= 4:
+            cache.clear()
+        cache[key] = (torch.empty((N, D), dtype=torch.float64, device=model.device),
+                      torch.empty((N, D), dtype=torch.float64, device=model.device))
+    return cache[key]
+
+
+def _moment_criterion(kind, model, x, y, num_samples, zs, seed, with_x=False, out=None):
     """predict_y mixture moments over `num_samples` propagated samples (the reference hard-codes 500), then one
-    dgp_acq_moments launch."""
+    dgp_acq_moments launch. `out` ([N, 1], or [N, d] with `with_x`) receives the values when given."""
     if getattr(model, "name", None) != 'dgp':
         raise NotImplementedError("only model.name == 'dgp' is on the accelerated path")
     X = model._check_X(_lib.as_device(x, model.device))
-    m, v = model.predict_moments(X, num_samples, add_lik_var=True, zs=zs, seed=seed)
-    if m.shape[1] != 1:
-        raise ValueError("the criterion expects a single-output model")
     N, d = X.shape
-    out = torch.empty((N, d if with_x else 1), dtype=torch.float64, device=X.device)
+    D = model.layers[-1].num_outputs
+    if D != 1:
+        raise ValueError("the criterion expects a single-output model")
+    m, v = model.predict_moments(X, num_samples, add_lik_var=True, zs=zs, seed=seed, out=_moment_scratch(model, N, D))
+    if out is None:
+        out = torch.empty((N, d if with_x else 1), dtype=torch.float64, device=X.device)
+    elif tuple(out.shape) != (N, d if with_x else 1):
+        raise ValueError(f"out= must be [{N}, {d if with_x else 1}]")
     if N:
         _lib.get_context(X.device).call("dgp_acq_moments", kind, _lib.ptr(m), _lib.ptr(v), N, _scalar(y),
                                         _lib.ptr(X) if with_x else None, d if with_x else 0, _lib.ptr(out))
@@ -172,17 +189,11 @@ def _optimize_de(crit, run, model, bounds, popsize_DE, popstd_DE, iterations_DE,
     lw = np.broadcast_to(np.asarray(bounds[0], dtype=np.float64).reshape(-1), (crit.d,)).copy()
     up = np.broadcast_to(np.asarray(bounds[1], dtype=np.float64).reshape(-1), (crit.d,)).copy()
     with search.GraphScope(model.device):
-        def objective(X, out):
-            v = run(X)
-            if out is None:
-                return v
-            out.copy_(v)
-            return out
-        res = search.de_minimize(objective, lw, up, crit.d, model.device, popsize_DE, popstd_DE, iterations_DE,
+        res = search.de_minimize(run, lw, up, crit.d, model.device, popsize_DE, popstd_DE, iterations_DE,
                                  seed=model._next_seed(seed))
         crit.x_opt = res["x"].cpu().numpy().reshape(crit.d, 1)
         crit.de_iterations = res["iterations"]
-        crit.IC_optimized = run(crit.x_opt.reshape(1, crit.d))
+        crit.IC_optimized = run(crit.x_opt.reshape(1, crit.d), None)
     return crit.x_opt
 
 
@@ -196,8 +207,8 @@ class WB2(Infill_criteria):
         self.IC_optimized = None
         self.x_opt = None
 
-    def run(self, model, x, num_samples=500, zs=None, seed=None):
-        return _moment_criterion(1, model, x, self.y_min, num_samples, zs, seed)
+    def run(self, model, x, num_samples=500, zs=None, seed=None, out=None):
+        return _moment_criterion(1, model, x, self.y_min, num_samples, zs, seed, out=out)
 
     def loss(self, model, x):
         return self.run(model, x)
@@ -224,7 +235,7 @@ def _optimize_de_adam(crit, model, bounds, popsize_DE, popstd_DE, iterations_DE,
     lw = np.broadcast_to(np.asarray(bounds[0], dtype=np.float64).reshape(-1), (d,)).copy()
     up = np.broadcast_to(np.asarray(bounds[1], dtype=np.float64).reshape(-1), (d,)).copy()
     if method in ('DE', 'DE+Adam'):
-        _optimize_de(crit, lambda X: crit.run(model, X), model, bounds, popsize_DE, popstd_DE, iterations_DE, 'DE', seed)
+        _optimize_de(crit, lambda X, out: crit.run(model, X, out=out), model, bounds, popsize_DE, popstd_DE, iterations_DE, 'DE', seed)
     if method in ('Adam', 'DE+Adam'):
         with search.GraphScope(model.device):
             if init_adam is None:
@@ -250,8 +261,8 @@ class WB2S(Infill_criteria):
         self.IC_optimized = None
         self.x_opt = None
 
-    def run(self, model, x, num_samples=500, zs=None, seed=None):
-        return _moment_criterion(3, model, x, self.y_min, num_samples, zs, seed, with_x=True)
+    def run(self, model, x, num_samples=500, zs=None, seed=None, out=None):
+        return _moment_criterion(3, model, x, self.y_min, num_samples, zs, seed, with_x=True, out=out)
 
     def loss(self, model, x):
         return self.run(model, x)
@@ -283,14 +294,15 @@ class EV_one_constraint(Infill_criteria):
         """(EV [N, 1], d sum(EV) / dx [N, d]) for the analytic expected violation (constrained searches differentiate it)."""
         return _moment_criterion_grad(2, model, x, self.zero_c, num_samples, zs, seed, out, dx)
 
-    def run(self, model, x, analytic=True, num_samples=100, zs=None, seed=None):
+    def run(self, model, x, analytic=True, num_samples=100, zs=None, seed=None, out=None):
         if analytic:
-            return _moment_criterion(2, model, x, self.zero_c, 500 if zs is None else num_samples, zs, seed)
+            return _moment_criterion(2, model, x, self.zero_c, 500 if zs is None else num_samples, zs, seed, out=out)
         if getattr(model, "name", None) != 'dgp':
             raise NotImplementedError("only model.name == 'dgp' is on the accelerated path")
         F = model.propagate(x, S=num_samples, zs=zs, seed=seed)[0][-1]            # [S, N, D_L]
         S, N, D = F.shape
-        out = torch.empty((N, D), dtype=torch.float64, device=F.device)
+        if out is None:
+            out = torch.empty((N, D), dtype=torch.float64, device=F.device)
         if N:
             _lib.get_context(F.device).call("dgp_ev_mc", _lib.ptr(F), S, N * D, _scalar(self.zero_c), _lib.ptr(out))
         return out
@@ -387,9 +399,9 @@ class PoF(Infill_criteria):
         self.IC_optimized = None
         self.x_opt = None
 
-    def run(self, model_C, x, num_samples=500, zs=None, seed=None):
+    def run(self, model_C, x, num_samples=500, zs=None, seed=None, out=None):
         """P[constraint <= zero_c] per candidate -> [N, 1]."""
-        return _moment_criterion(4, model_C, x, self.zero_c, num_samples, zs, seed)
+        return _moment_criterion(4, model_C, x, self.zero_c, num_samples, zs, seed, out=out)
 
     def run_with_IC(self, IC, model_Y, model_C, x, seed=None):
         return IC.run(model_Y, x, seed=seed) * self.run(model_C, x, seed=seed)

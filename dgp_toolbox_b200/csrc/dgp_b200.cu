@@ -672,6 +672,10 @@ int forward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, ChunkLa
   a.xFvar = (io.Fvars && io.Fvars[layer]) ? io.Fvars[layer] : nullptr;
   a.xF = (io.Fs && io.Fs[layer]) ? io.Fs[layer] : nullptr;
   const size_t smem = (size_t)w.M * D * sizeof(double);
+  if (smem > 160 * 1024) {   // q_mu is staged whole in shared memory by the unfused moments kernel
+    c->err = "unfused conditional: M * D_out * 8 bytes of q_mu exceed the 160 KiB staged per CTA (fused path: M <= 256, D_out <= 16)";
+    return DGP_ERR_UNSUPPORTED;
+  }
   return dispatch_dmax(D, [&](auto dm) -> int {
     constexpr int DM = decltype(dm)::value;
     if (!c->dry) {

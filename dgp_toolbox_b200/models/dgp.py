@@ -36,10 +36,11 @@ class DGP_Base(_Module):
 
     @property
     def parameters(self):
-        out = []
-        for l in self.layers:
-            out.extend(l.parameters)
-        out.extend(self.likelihood.likelihood.parameters)
+        out, seen = [], set()
+        for p in [q for l in self.layers for q in l.parameters] + list(self.likelihood.likelihood.parameters):
+            if id(p) not in seen:          # one entry per Parameter object even when a kernel is shared between layers (GPflow semantics)
+                seen.add(id(p))
+                out.append(p)
         return out
 
     @property
@@ -228,12 +229,20 @@ class DGP_Base(_Module):
     def predict_density(self, Xnew, Ynew, num_samples):
         raise NotImplementedError("broken in the reference (tf.log, dgp.py:129); not on the accelerated path")
 
-    def predict_moments(self, Xnew, num_samples, add_lik_var=True, zs=None, seed=None):
-        """Mixture moments over the S samples reduced on the device (dgp.py:362-366; Infill_criteria.py:39-41)."""
+    def predict_moments(self, Xnew, num_samples, add_lik_var=True, zs=None, seed=None, out=None):
+        """Mixture moments over the S samples reduced on the device (dgp.py:362-366; Infill_criteria.py:39-41). `out=(mean, var)`
+        writes into caller-owned [N, D] buffers: the search loops pass the same pair every call so that graph replay
+        (dgp_set_graph) sees addresses that never move, whatever the caching allocator does."""
         X = self._check_X(_lib.as_device(Xnew, self.device))
         N, D = X.shape[0], self.layers[-1].num_outputs
-        mean = torch.empty((N, D), dtype=torch.float64, device=X.device)
-        var = torch.empty_like(mean)
+        if out is not None:
+            mean, var = out
+            for t in (mean, var):
+                if tuple(t.shape) != (N, D) or t.dtype != torch.float64 or t.device != X.device or not t.is_contiguous():
+                    raise ValueError("out= must be two contiguous float64 [N, D] tensors on the model's device")
+        else:
+            mean = torch.empty((N, D), dtype=torch.float64, device=X.device)
+            var = torch.empty_like(mean)
         if N == 0:
             return mean, var
         m, keep = self._model_desc()
@@ -257,6 +266,10 @@ class DGP_Base(_Module):
         in the dgp_elbo_grad buffer and which GPflow bijector maps it to the variable tf.optimizers.Adam updates."""
         _, offs = self.grad_layout()
         where = {}
+        kerns = [id(l.kern) for l in self.layers]
+        if len(set(kerns)) != len(kerns):
+            raise NotImplementedError("one kernel object shared by several layers: its gradient would be the sum over those layers, "
+                                      "which the fused Adam launch does not form -- give every layer its own kernel object")
         for l, o in zip(self.layers, offs):
             M, D_in = l.feature.Z.shape
             where[id(l.feature.Z)] = (o.dZ, M * D_in, None, 0)
@@ -269,6 +282,9 @@ class DGP_Base(_Module):
             where[id(l.q_mu)] = (o.dq_mu, M * l.num_outputs, None, 0)
             where[id(l.q_sqrt)] = (o.dq_sqrt, l.num_outputs * M * M, None, M)
         where[id(self.likelihood.likelihood.variance)] = (2, 1, None, 0)
+        if len(params) > 48:     # kAdamMaxParams (csrc/small.cuh): the table travels as a kernel argument
+            raise ValueError(f"{len(params)} trainable parameters: one fused Adam launch holds at most 48 (9 layers x 5 + likelihood); "
+                             "fix some with set_trainable(p, False) or train in two groups")
         arr = (_lib.AdamParam * len(params))()
         keep = []
         for i, p in enumerate(params):

@@ -341,3 +341,32 @@ def test_failed_cholesky_is_raised_at_the_failing_block_and_freezes_the_paramete
     m, v = pm.predict(prob["X"], 4)                            # reported once: the next call starts clean
     assert bool(torch.isfinite(m).all()) and bool(torch.isfinite(v).all())
     capsys.readouterr()
+
+
+def test_foreign_dlpack_producers_enter_through_as_device():
+    """north_star: tensors are exchanged via DLPack. TensorFlow is absent from the image, so the producer here is a minimal foreign
+    object exposing only `__dlpack__` / `__dlpack_device__` (what an eager tf.Tensor offers), on the host and on the device; both
+    must give the same results as a numpy input through the public API."""
+    import dgp_toolbox_b200 as D
+
+    class Foreign:
+        def __init__(self, backing):
+            self._b = backing
+
+        def __dlpack__(self, *args, **kwargs):
+            return self._b.__dlpack__(*args, **kwargs)
+
+        def __dlpack_device__(self):
+            return self._b.__dlpack_device__()
+
+    model, cfg = _c2_model(S=4)
+    X = np.random.default_rng(0).standard_normal((33, cfg["D0"]))
+    ref_m, ref_v = model.predict(X, 4, seed=9)
+    host = Foreign(X.copy())                                     # kDLCPU capsule
+    dev = Foreign(torch.as_tensor(X).cuda())                     # kDLCUDA capsule: zero-copy path
+    for obj in (host, dev):
+        t = D._lib.as_device(obj)
+        assert t.is_cuda and t.dtype == torch.float64 and torch.equal(t.cpu(), torch.as_tensor(X))
+        m, v = model.predict(obj, 4, seed=9)
+        assert torch.equal(m, ref_m) and torch.equal(v, ref_v)
+    assert D._lib.as_device(dev).data_ptr() == dev._b.data_ptr()  # no copy for a float64 CUDA producer
