@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <type_traits>
 #include <cstdio>
 #include <string>
 

@@ -61,6 +61,7 @@ struct dgp_ctx {
   size_t h_pinned_bytes = 0;
   double* d_stage = nullptr;            // device side of that staging (outside the arena, which may be re-grown)
   size_t d_stage_bytes = 0;
+  bool sync_launches = false;           // DGP_B200_SYNC_LAUNCHES: cudaDeviceSynchronize + error check after every launch (debugging)
   bool use_vform_grad = true;           // ... and so does the ELBO+gradient path (V-form adjoint in backward_layer)
   bool vform_forward_calls = true;
   long vform_grad_min_ps = 32768;       // fewer point-samples than this: keep the A-form adjoint (no Cholesky-adjoint glue)
@@ -137,6 +138,14 @@ struct ProfScope {   // records an event pair around the launches issued during 
       ++c->launches;                                                  \
       ++c->cat_launches[c->cat];                                      \
       CK(cudaGetLastError());                                         \
+      if (c->sync_launches) {   /* DGP_B200_SYNC_LAUNCHES=1: find the launch that faults */ \
+        cudaError_t es__ = cudaDeviceSynchronize();                   \
+        if (es__ != cudaSuccess) {                                    \
+          c->err = std::string(#kern) + " (line " + std::to_string(__LINE__) + "): " + cudaGetErrorString(es__); \
+          fprintf(stderr, "dgp_b200: %s\n", c->err.c_str());          \
+          return DGP_ERR_CUDA;                                        \
+        }                                                             \
+      }                                                               \
     }                                                                 \
   } while (0)
 #define CAT(x) c->cat = (x)
@@ -254,8 +263,12 @@ int gemm(dgp_ctx* c, GemmArgs g, bool nt) {
   cudaError_t e = gemm_launch(g, nt, c->stream);
   c->launches += g.splitk > 1 ? 2 : 1;
   c->cat_launches[c->cat] += g.splitk > 1 ? 2 : 1;
+  if (e == cudaSuccess && c->sync_launches) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     c->err = std::string("gemm_launch: ") + cudaGetErrorString(e);
+    if (c->sync_launches)
+      fprintf(stderr, "dgp_b200: %s (M %d N %d K %d batch %d nt %d splitk %d lower %d tri %d lda %ld ldb %ld ldc %ld)\n", c->err.c_str(), g.M, g.N,
+              g.K, g.batch, (int)nt, g.splitk, g.c_lower, g.a_tri, g.lda, g.ldb, g.ldc);
     return DGP_ERR_CUDA;
   }
   return DGP_OK;
@@ -355,9 +368,9 @@ struct LayerWs {
   bool vform = false;
   bool white = false;   // whitened representation (utils/layers.py:246,254-255,296-303): C_d = q_sqrt_d^T, beta = q_mu, KL against N(0, I)
   double *Cmat = nullptr, *betaP = nullptr;
-  // V-form adjoint: C_d^T side by side, L^T, accumulators over the chunks (G1 = tril(dV V^T), DCt = [tril(V dT_d^T)]_d, dbeta = V Gm)
-  // and scratch of the once-per-step re-parameterisation back to (q_mu, q_sqrt, Ku)
-  double *CTcat = nullptr, *G1 = nullptr, *DCt = nullptr, *dbeta = nullptr, *dqmu2 = nullptr, *dRcat = nullptr;
+  // V-form adjoint: C_d^T side by side, L^T, accumulators over the chunks (Wacc = [tril(V diag(2 Gv_d) V^T)]_d, dbeta = V Gm) and
+  // scratch of the once-per-step re-parameterisation back to (q_mu, q_sqrt, Ku): G1 = tril(dV V^T), DCt = [tril(V dT_d^T)]_d
+  double *CTcat = nullptr, *G1 = nullptr, *DCt = nullptr, *Wacc = nullptr, *dbeta = nullptr, *dqmu2 = nullptr, *dRcat = nullptr;
   double *dLinv = nullptr, *sq1 = nullptr, *sq2 = nullptr;
   // fused data-path adjoint (fused_bwd.cuh): packed C_d^T / Lu^-T panel stream; bcfg: 0 = BM 256, 1 = BM 128, -1 = unfused GEMM pipeline
   double* bstream = nullptr; int bcfg = -1, NPb = 0;
@@ -462,7 +475,7 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
       w.NP = ((w.vform ? 1 : 2) + w.D_out) * kpb * nb * (nb + 1) / 2;
       if (w.vform) { w.Cmat = walloc(c, mm * w.D_out); w.betaP = walloc(c, (size_t)w.Mp * 32); }
       if (w.vform && level == PREP_GRAD) {
-        w.CTcat = walloc(c, mm * w.D_out); w.G1 = walloc(c, mm); w.DCt = walloc(c, mm * w.D_out);
+        w.CTcat = walloc(c, mm * w.D_out); w.G1 = walloc(c, mm); w.DCt = walloc(c, mm * w.D_out); w.Wacc = walloc(c, mm * w.D_out);
         w.dbeta = walloc(c, (size_t)w.Mp * 32); w.dqmu2 = walloc(c, (size_t)w.Mp * 32); w.dRcat = walloc(c, mm * w.D_out);
         w.dLinv = walloc(c, mm); w.sq1 = walloc(c, mm); w.sq2 = walloc(c, mm);
         w.bcfg = c->use_fused_bwd ? pick_fused_bwd_cfg(w.Mp, w.D_in, w.D_out) : -1;
@@ -534,8 +547,7 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
       if (w.bcfg == 0) LAUNCH(pack_bwd_stream_kernel<128>, w.NPb, 256, 0, w.Cmat, w.LinvT, w.Mp, w.D_out, w.bstream);
       else if (w.bcfg == 1) LAUNCH(pack_bwd_stream_kernel<64>, w.NPb, 256, 0, w.Cmat, w.LinvT, w.Mp, w.D_out, w.bstream);
       // c_lower products leave the tiles above the diagonal unwritten: start the accumulators from zero
-      CK(cudaMemsetAsync(w.G1, 0, (size_t)w.Mp * w.Mp * sizeof(double), c->stream));
-      CK(cudaMemsetAsync(w.DCt, 0, (size_t)nct * sizeof(double), c->stream));
+      CK(cudaMemsetAsync(w.Wacc, 0, (size_t)nct * sizeof(double), c->stream));
     }
     std::vector<PanelDesc> sch = build_schedule(w.Mp, BM, w.D_out, w.vform);
     if ((int)sch.size() != w.NP) { c->err = "internal: panel schedule size mismatch"; return DGP_ERR_ARG; }
@@ -699,21 +711,22 @@ struct ParamScratch {
 };
 
 template <typename F>
-int param_gemms(dgp_ctx* c, GemmArgs* gs, const bool* nts, int n, const ParamScratch& ps, F&& on_main) {
+int param_gemms(dgp_ctx* c, GemmArgs* gs, const bool* nts, int n, const ParamScratch& ps, const int* slots, F&& on_main) {
   size_t off[8], total = 0;
   bool fixed = ps.fixed && n <= 4;
+  auto slot = [&](int i) { return slots ? slots[i] : i; };   // which fixed scratch region contraction i uses
   for (int i = 0; i < n; ++i) {
     gs[i].splitk = pick_splitk(c, gs[i], nts[i]);
     off[i] = total;
     const size_t need = gs[i].splitk > 1 ? (size_t)gs[i].splitk * gs[i].batch * gs[i].M * gs[i].N : 0;
     total += (need + 31) & ~(size_t)31;
-    if (fixed && need > ps.room[i]) fixed = false;
+    if (fixed && need > ps.room[slot(i)]) fixed = false;
   }
   const bool par = fixed || total <= ps.cap;
   LayerFork fk(c, par ? n : 0);
   for (int i = 0; i < n; ++i) {
     fk.use(i);
-    gs[i].part = ps.part + (fk.active ? (fixed ? ps.off[i] : off[i]) : 0);
+    gs[i].part = ps.part + (fk.active ? (fixed ? ps.off[slot(i)] : off[i]) : 0);
     RC(gemm(c, gs[i], nts[i]));
   }
   if (fk.active) c->stream = fk.main;
@@ -750,7 +763,8 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
       f.stream = w.bstream; f.V = V; f.T = cl.T; f.GvT = up.GvT; f.gq = up.gq; f.Gm = up.GmPad; f.gm_ld = 32; f.beta = w.betaP;
       f.Zs = w.Zs; f.ls = d.lengthscales; f.var = d.variance; f.Xin = cl.Xin; f.xmod = cl.xmod; f.D_in = w.D_in;
       f.mfW = d.mf_W; f.mean_kind = d.mean_kind; f.kind = d.kernel_kind; f.M = w.M; f.Mp = Mp; f.D_out = D; f.P = P; f.Pp = Pp;
-      f.dV = dV; f.Gbar = Gbar; f.dXin = dXin; f.XaugPad = XaugPad; f.part = rbf_part;
+      f.dV = nullptr;   // dV stays on chip: the parameter contractions below do not read it
+      f.Gbar = Gbar; f.dXin = dXin; f.XaugPad = XaugPad; f.part = rbf_part;
       f.warp_major_groups = c->warp_major_groups ? 1 : 0; f.group_skew = c->group_skew;
       nbv = ntile64 * (w.bcfg == 0 ? 2 : 4);   // one row of partial sums per tile and column group
       const size_t smem = fused_bwd_smem(w.bcfg, Mp, w.D_in, D);
@@ -800,21 +814,23 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
     }
     if (!params) return DGP_OK;
     CAT(DGP_CAT_GEMM_BWD_PARAM);
-    GemmArgs pg[4];
-    const bool pnt[4] = {true, true, false, false};
-    // G1 = tril(dV V^T)  (-> dLu^-1 through Kuf = Lu V)
-    pg[0] = gargs(dV, Pp, V, Pp, w.G1, Mp, Mp, Mp, (int)Pp);
-    pg[0].beta = beta; pg[0].c_lower = 1;
-    // DCt_d = tril(V diag(2 Gv_d) T_d^T) = (dC_d)^T, blocks side by side
-    pg[1] = gargs(V, Pp, cl.T, Pp, w.DCt, (long)D * Mp, Mp, Mp, (int)Pp);
-    pg[1].alpha = 2.0; pg[1].beta = beta; pg[1].batch = D; pg[1].sA = 0; pg[1].sB = (long)Mp * Pp; pg[1].sC = Mp; pg[1].c_lower = 1;
-    pg[1].kscale = up.GvT; pg[1].sScale = Pp;
+    // Contractions over the point-samples. With dT_d = 2 Gv_d o (C_d V) and gq = -sum_d Gv_d both matrix accumulators of the V-form
+    // are functions of the D_out symmetric matrices W_d = V diag(2 Gv_d) V^T:
+    //   (dC_d)^T = V dT_d^T = W_d C_d^T,      dV V^T = beta (V Gm)^T + sum_d (C_d^T C_d - I) W_d,
+    // so only tril(W_d) is accumulated here (D_out lower-only products instead of D_out + 1, and neither dV nor the T_d stash is
+    // read again); the M^3-class products that turn W_d into G1 and DCt run once per step (run_model).
+    GemmArgs pg[3];
+    const bool pnt[3] = {true, false, false};
+    const int slots[3] = {1, 2, 3};
+    pg[0] = gargs(V, Pp, V, Pp, w.Wacc, (long)D * Mp, Mp, Mp, (int)Pp);
+    pg[0].alpha = 2.0; pg[0].beta = beta; pg[0].batch = D; pg[0].sA = 0; pg[0].sB = 0; pg[0].sC = Mp; pg[0].c_lower = 1;
+    pg[0].kscale = up.GvT; pg[0].sScale = Pp;
     // dbeta = V Gm ;  H = Gbar [X, 1]
-    pg[2] = gargs(V, Pp, up.GmPad, 32, w.dbeta, 32, Mp, 32, (int)Pp);
+    pg[1] = gargs(V, Pp, up.GmPad, 32, w.dbeta, 32, Mp, 32, (int)Pp);
+    pg[1].beta = beta;
+    pg[2] = gargs(Gbar, Pp, XaugPad, 32, w.H, 32, Mp, 32, (int)Pp);
     pg[2].beta = beta;
-    pg[3] = gargs(Gbar, Pp, XaugPad, 32, w.H, 32, Mp, 32, (int)Pp);
-    pg[3].beta = beta;
-    RC(param_gemms(c, pg, pnt, 4, ps, [&]() -> int {
+    RC(param_gemms(c, pg, pnt, 3, ps, slots, [&]() -> int {
       LAUNCH(reduce_partials_kernel, w.D_in + 1, 256, 0, rbf_part, nbv, w.D_in + 1, w.rbf_red, first_chunk ? 0 : 1);
       LAUNCH(reduce_partials_kernel, 3, 256, 0, up.part, up.nblocks, 3, w.sgv, first_chunk ? 0 : 1);
       return DGP_OK;
@@ -879,7 +895,7 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
   pg[2].beta = beta;
   pg[3] = gargs(Gbar, Pp, XaugPad, 32, w.H, 32, Mp, 32, (int)Pp);
   pg[3].beta = beta;
-  RC(param_gemms(c, pg, pnt, 4, ps, [&]() -> int {
+  RC(param_gemms(c, pg, pnt, 4, ps, nullptr, [&]() -> int {
     LAUNCH(reduce_partials_kernel, w.D_in + 1, 256, 0, rbf_part, nb, w.D_in + 1, w.rbf_red, first_chunk ? 0 : 1);
     LAUNCH(reduce_partials_kernel, 3, 256, 0, up.part, up.nblocks, 3, w.sgv, first_chunk ? 0 : 1);
     return DGP_OK;
@@ -1191,9 +1207,20 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
           // V-form accumulators (G1, DCt, dbeta) -> gradients w.r.t. q_mu, q_sqrt and Ku = Lu Lu^T
           const int Mp = w.Mp, D = w.D_out;
           const long nct = (long)D * mm;
-          LAUNCH(tril_scale_kernel, (unsigned)((mm + 255) / 256), 256, 0, w.G1, Mp, (long)Mp, 1, 1.0);
-          LAUNCH(tril_scale_kernel, (unsigned)((nct + 255) / 256), 256, 0, w.DCt, Mp, (long)D * Mp, D, 1.0);
+          // W_d = V diag(2 Gv_d) V^T (lower triangles accumulated over the chunks) -> DCt_d = tril(W_d C_d^T),
+          // G1 = tril(sum_d C_d^T (W_d C_d^T)^T + beta dbeta^T - sum_d W_d)                       (see backward_layer)
           GemmArgs g;
+          LAUNCH(sym_fill_kernel, (unsigned)((nct + 255) / 256), 256, 0, w.Wacc, Mp, (long)D * Mp, D);
+          g = gargs(w.Wacc, (long)D * Mp, w.CTcat, (long)D * Mp, w.DCt, (long)D * Mp, Mp, Mp, Mp);
+          g.batch = D; g.sA = Mp; g.sB = Mp; g.sC = Mp;
+          RC(gemm(c, g, false));
+          g = gargs(w.CTcat, (long)D * Mp, w.DCt, (long)D * Mp, w.G1, Mp, Mp, Mp, D * Mp);
+          RC(gemm(c, g, true));
+          g = gargs(w.betaP, 32, w.dbeta, 32, w.G1, Mp, Mp, Mp, 32);
+          g.beta = 1.0;
+          RC(gemm(c, g, true));
+          LAUNCH(g1_finish_kernel, (unsigned)((mm + 255) / 256), 256, 0, w.G1, w.Wacc, Mp, D);
+          LAUNCH(tril_scale_kernel, (unsigned)((nct + 255) / 256), 256, 0, w.DCt, Mp, (long)D * Mp, D, 1.0);
           if (!w.white) {
             g = gargs(w.LinvT, Mp, w.dbeta, 32, w.dqmu2, 32, Mp, 32, Mp);              // dq_mu = Lu^-T dbeta
             g.a_tri = 2;
@@ -1485,6 +1512,7 @@ int dgp_ctx_create(int device, void* cuda_stream, dgp_ctx** out) {
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   if (getenv("DGP_B200_UNFUSED")) c->use_fused = false;
+  if (const char* e = getenv("DGP_B200_SYNC_LAUNCHES")) c->sync_launches = atoi(e) != 0;   // debugging: synchronise and check after every launch
   if (const char* e = getenv("DGP_B200_WARPMAP")) c->warp_major_groups = atoi(e) != 0;   // measurement hooks
   if (const char* e = getenv("DGP_B200_FUSED_BWD")) c->use_fused_bwd = atoi(e) != 0;
   if (const char* e = getenv("DGP_B200_SKEW")) c->group_skew = atoi(e);

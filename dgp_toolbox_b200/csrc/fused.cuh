@@ -206,7 +206,7 @@ struct FusedCfg {
   static constexpr int PANEL = BM * kPanelK;
   static constexpr int STAGES = 4;
   static size_t smem_bytes(int Mp, int D_in, int D_out) {
-    return ((size_t)Mp * LDT + (size_t)STAGES * PANEL + (size_t)D_in * PT + (size_t)(1 + D_out) * PT + (size_t)WM * PT + 2 * STAGES + (size_t)(Mp / BM) * (Mp / BM + 1) * (BM / kPanelK)) * sizeof(double);
+    return ((size_t)Mp * LDT + (size_t)STAGES * PANEL + (size_t)D_in * PT + (size_t)(1 + D_out) * PT + (size_t)WM * PT + (size_t)D_out * PT + 2 * STAGES + (size_t)(Mp / BM) * (Mp / BM + 1) * (BM / kPanelK)) * sizeof(double);
   }
 };
 
@@ -220,7 +220,8 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
   double* xs_all = tile + (size_t)a.Mp * LDT;            // [WN][D_in][GC]  scaled inputs
   double* colsum_all = xs_all + a.D_in * PT;             // [WN][1 + D_out][GC]: |V|^2, |T_d|^2
   double* part_all = colsum_all + (1 + a.D_out) * PT;    // [WN][WM][GC]
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(part_all + WM * PT);   // [STAGES]
+  double* mean_all = part_all + WM * PT;                 // [WN][GC][D_out]  tile^T * weights (stage 5)
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(mean_all + a.D_out * PT);   // [STAGES]
   unsigned long long* empty = full + STAGES;                                               // [STAGES]
   // per-panel descriptors of the V pass and of one upper pass (A and every T_d share it), unpacked with a handful of
   // integer ops per panel instead of re-deriving block / clip state each time
@@ -263,16 +264,27 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
   if (warp == 8) {
     // ---- producer: one bulk copy per panel, in stream order, round after round ----
     if (lane == 0) {
-      int st = 0, q = 0;
+      int st = 0, q = 0, pass = 0, qq = 0;
       unsigned ph = 0;
       const double* src = a.stream;
       const long total = (long)my_tiles * a.NP;
       for (long n = 0; n < total; ++n) {
+        // Inside a diagonal block only the rows on the operator's side of the diagonal are read by the consumers (a suffix for
+        // the lower operator, a prefix for the upper ones; same rule as their m-tile ranges), and a row range is a byte range
+        // of the packed panel: copy just that. 2/3 of the panels are diagonal-block panels, half of whose rows are dead.
+        const unsigned x = ptab[(pass == 0 ? 0 : NPv) + qq].x;
+        int r0 = 0, nr = BM;
+        if ((x >> 18) & kPanelClip) {
+          const int krel = (int)(x & 0xfff) - (int)((x >> 12) & 63) * BM;
+          if (pass == 0) { r0 = krel; nr = BM - krel; }
+          else nr = min(BM, krel + kPanelK);
+        }
+        if (++qq == (pass == 0 ? NPv : NPa)) { qq = 0; ++pass; if (pass == 1 && a.vform) pass = 2; }
         mbar_wait(empty + st, ph ^ 1);
-        mbar_arrive_expect_tx(full + st, PANEL * 8);
-        bulk_g2s(pbuf + st * PANEL, src, PANEL * 8, full + st);
+        mbar_arrive_expect_tx(full + st, (unsigned)(nr * kPanelK * 8));
+        bulk_g2s(pbuf + st * PANEL + r0 * kPanelK, src + r0 * kPanelK, (unsigned)(nr * kPanelK * 8), full + st);
         src += PANEL;
-        if (++q == a.NP) { q = 0; src = a.stream; }
+        if (++q == a.NP) { q = 0; src = a.stream; pass = 0; qq = 0; }
         if (++st == STAGES) { st = 0; ph ^= 1; }
       }
     }
@@ -290,6 +302,7 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
   double* xs = xs_all + wn * a.D_in * GC;
   double* colsum = colsum_all + wn * (1 + a.D_out) * GC;
   double* part = part_all + wn * WM * GC;
+  double* meanbuf = mean_all + wn * a.D_out * GC;
   const int bar_id = 1 + wn;
   const double s2 = a.var[0];
   int cst = 0;
@@ -335,20 +348,43 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
 #pragma unroll
         for (int j = 0; j < ZR; ++j)
           if (j < a.D_in) zr[j] = zg[j];
-        for (int c = 0; c < GC; ++c) {
-          double r2 = 0.0;
+        // four columns at a time: their distance and exp chains are independent, so the FP64 pipe sees 4x the ILP of a plain loop
+        // (the kernel switch is hoisted so that each variant is straight-line code the scheduler can interleave)
+        auto sweep = [&](auto kconst) {
+          constexpr int KIND = decltype(kconst)::value;
+          constexpr int U = 4;
+          static_assert(GC % U == 0, "column unroll");
+          for (int c = 0; c < GC; c += U) {
+            double r2[U];
 #pragma unroll
-          for (int j = 0; j < ZR; ++j)
-            if (j < a.D_in) {
-              const double t = zr[j] - xs[j * GC + c];
-              r2 = fma(t, t, r2);
+            for (int u = 0; u < U; ++u) r2[u] = 0.0;
+#pragma unroll
+            for (int j = 0; j < ZR; ++j)
+              if (j < a.D_in) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                  const double t = zr[j] - xs[j * GC + c + u];
+                  r2[u] = fma(t, t, r2[u]);
+                }
+              }
+            for (int j = ZR; j < a.D_in; ++j) {
+              const double zj = zg[j];
+#pragma unroll
+              for (int u = 0; u < U; ++u) {
+                const double t = zj - xs[j * GC + c + u];
+                r2[u] = fma(t, t, r2[u]);
+              }
             }
-          for (int j = ZR; j < a.D_in; ++j) {
-            const double t = zg[j] - xs[j * GC + c];
-            r2 = fma(t, t, r2);
+            double kv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) kv[u] = kernel_value(KIND, r2[u], s2);
+#pragma unroll
+            for (int u = 0; u < U; ++u) trow[c + u] = (p0 + c + u < a.P) ? kv[u] : 0.0;
           }
-          trow[c] = (p0 + c < a.P) ? kernel_value(a.kind, r2, s2) : 0.0;
-        }
+        };
+        if (a.kind == 0) sweep(std::integral_constant<int, 0>{});
+        else if (a.kind == 1) sweep(std::integral_constant<int, 1>{});
+        else sweep(std::integral_constant<int, 2>{});
       } else {
         for (int c = 0; c < GC; ++c) trow[c] = 0.0;
       }
@@ -449,32 +485,47 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
     PH_ADD(ph_loop, ph_b);
     PH_MARK(ph_c);
     // ---- stage 5: moments, sample, outputs ----
+    // mean^T [D_out x GC] = weights^T [D_out x M] * tile [M x GC] on the tensor pipe: one 8 x 8 output unit per (warp, step), the 64+
+    // k-steps spread over four independent accumulator pairs (a dependent DMMA chain would run at 1/26 of the issue rate)
+    {
+#ifdef DGP_DEBUG_PHASECLK
+      const long long ph_c2 = clock64();
+#endif
+      const int mts = (a.D_out + 7) >> 3;
+      for (int u0 = wm; u0 < mts * (GC / 8); u0 += WM) {
+        const int mt = u0 / (GC / 8), nt = u0 % (GC / 8);
+        const int d = mt * 8 + g8;
+        const bool dlive = d < a.D_out;
+        const double* qa = a.qmu + (dlive ? d : 0);
+        const double* tb = tile + t4 * LDT + col0 + nt * 8 + g8;
+        double e0[4] = {0.0, 0.0, 0.0, 0.0}, e1[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int k0 = 0; k0 < a.Mp; k0 += 32) {
+          double av[8], bv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int k = k0 + u * 4 + t4;
+            av[u] = (dlive && k < a.M) ? qa[(long)k * a.qmu_ld] : 0.0;
+            bv[u] = tb[(k0 + u * 4) * LDT];
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dmma884(e0[u & 3], e1[u & 3], av[u], bv[u]);
+        }
+        if (dlive) {
+          const int col = nt * 8 + 2 * t4;
+          meanbuf[col * a.D_out + d] = (e0[0] + e0[1]) + (e0[2] + e0[3]);
+          meanbuf[(col + 1) * a.D_out + d] = (e1[0] + e1[1]) + (e1[2] + e1[3]);
+        }
+      }
+      group_sync(bar_id, GT);
+#ifdef DGP_DEBUG_PHASECLK
+      ph_dot += clock64() - ph_c2;
+#endif
+    }
     for (int idx = tg; idx < GC * a.D_out; idx += GT) {
       const int c = idx / a.D_out, d = idx % a.D_out;
       const long p = p0 + c;
       if (p >= a.P) continue;
-#ifdef DGP_DEBUG_PHASECLK
-      const long long ph_c2 = clock64();
-#endif
-      double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
-      const double* tc = tile + col0 + c;
-      const double* qd = a.qmu + d;
-      int m = 0;
-      for (; m + 16 <= a.M; m += 16) {   // sixteen independent weight loads in flight: they come from L2 (L1 is ~12 KB here)
-        double qv[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) qv[u] = qd[(m + u) * a.qmu_ld];
-#pragma unroll
-        for (int u = 0; u < 16; u += 4) {
-          m0 = fma(tc[(m + u + 0) * LDT], qv[u + 0], m0); m1 = fma(tc[(m + u + 1) * LDT], qv[u + 1], m1);
-          m2 = fma(tc[(m + u + 2) * LDT], qv[u + 2], m2); m3 = fma(tc[(m + u + 3) * LDT], qv[u + 3], m3);
-        }
-      }
-      for (; m < a.M; ++m) m0 = fma(tc[m * LDT], qd[m * a.qmu_ld], m0);
-      const double mean = (m0 + m1) + (m2 + m3);
-#ifdef DGP_DEBUG_PHASECLK
-      ph_dot += clock64() - ph_c2;
-#endif
+      const double mean = meanbuf[idx];
       const double* x = a.Xin + (p % a.xmod) * a.D_in;
       double mf = 0.0;
       if (a.mean_kind == 1) mf = x[d];

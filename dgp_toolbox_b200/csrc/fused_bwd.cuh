@@ -186,8 +186,10 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
               mbar_arrive_expect_tx(full + st, PANEL * 8);
               bulk_g2s(dst, src, PANEL * 8, full + st);
 #else
-              mbar_arrive_expect_tx(full + st, (PANEL + kPanelK * PT) * 8);
-              bulk_g2s(dst, src, PANEL * 8, full + st);
+              // diagonal block of the lower operator: rows above the panel's k-range are never read (see fused_forward_kernel)
+              const int r0 = max(0, ks * kPanelK - i * BM);
+              mbar_arrive_expect_tx(full + st, (unsigned)(((BM - r0) * kPanelK + kPanelK * PT) * 8));
+              bulk_g2s(dst + r0 * kPanelK, src + r0 * kPanelK, (unsigned)((BM - r0) * kPanelK * 8), full + st);
               const double* trow = a.T + ((long)d * a.Mp + (long)ks * kPanelK) * a.Pp + p0;
 #pragma unroll 4
               for (int r = 0; r < kPanelK; ++r) bulk_g2s(dst + PANEL + r * LDT, trow + (long)r * a.Pp, PT * 8, full + st);
@@ -199,8 +201,9 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
         for (int i = 0; i < nb; ++i)
           for (int ks = i * KPB; ks < kt; ++ks) {
             mbar_wait(empty + st, ph ^ 1);
-            mbar_arrive_expect_tx(full + st, PANEL * 8);
-            bulk_g2s(pbuf + st * STAGE, src, PANEL * 8, full + st);
+            const int nr = min(BM, ks * kPanelK - i * BM + kPanelK);   // upper operator: rows below the panel's k-range are dead
+            mbar_arrive_expect_tx(full + st, (unsigned)(nr * kPanelK * 8));
+            bulk_g2s(pbuf + st * STAGE, src, (unsigned)(nr * kPanelK * 8), full + st);
             src += PANEL;
             if (++st == STAGES) { st = 0; ph ^= 1; }
           }
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
           const double2 v = *tp;
           const double r0 = fma(2.0 * v.x, gqs[cl], c0[ti][j]), r1 = fma(2.0 * v.y, gqs[cl + 1], c1[ti][j]);
           *tp = make_double2(r0, r1);
-          *reinterpret_cast<double2*>(a.dV + (long)row * a.Pp + p0 + cl) = make_double2(r0, r1);
+          if (a.dV) *reinterpret_cast<double2*>(a.dV + (long)row * a.Pp + p0 + cl) = make_double2(r0, r1);
         }
       }
       PH_ADD(ph_be, ph_c);
@@ -360,24 +363,49 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
         const double* zg = a.Zs + (long)m * a.D_in;
 #pragma unroll
         for (int j = 0; j < DMAX; ++j) zr[j] = j < a.D_in ? zg[j] : 0.0;
-        for (int c = 0; c < GC; ++c) {
-          double r2 = 0.0, t[DMAX];
+        // four columns at a time (independent distance / exp chains), kernel switch hoisted: see fused_forward_kernel
+        auto sweep = [&](auto kconst) {
+          constexpr int KIND = decltype(kconst)::value;
+          constexpr int U = 4;
+          static_assert(GC % U == 0, "column unroll");
+          for (int c = 0; c < GC; c += U) {
+            double r2[U];
 #pragma unroll
-          for (int j = 0; j < DMAX; ++j)
-            if (j < a.D_in) {
-              t[j] = zr[j] - xs[j * GC + c];
-              r2 = fma(t[j], t[j], r2);
+            for (int u = 0; u < U; ++u) r2[u] = 0.0;
+#pragma unroll
+            for (int j = 0; j < DMAX; ++j)
+              if (j < a.D_in) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                  const double t = zr[j] - xs[j * GC + c + u];
+                  r2[u] = fma(t, t, r2[u]);
+                }
+              }
+            double k[U], gf[U], gb[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) kernel_eval(KIND, r2[u], s2, k[u], gf[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const double kbar = trow[c + u];
+              gb[u] = kbar * gf[u];
+              ds2 = fma(kbar, k[u], ds2);
             }
-          double k, gf;
-          kernel_eval(a.kind, r2, s2, k, gf);
-          const double kbar = trow[c];
-          const double gb = kbar * gf;
-          trow[c] = gb;
-          ds2 = fma(kbar, k, ds2);
 #pragma unroll
-          for (int j = 0; j < DMAX; ++j)
-            if (j < a.D_in) dl[j] = fma(gb * t[j], t[j], dl[j]);
-        }
+            for (int u = 0; u < U; ++u) trow[c + u] = gb[u];
+#pragma unroll
+            for (int j = 0; j < DMAX; ++j)
+              if (j < a.D_in) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                  const double t = zr[j] - xs[j * GC + c + u];   // recomputed: keeping U x D_in differences live would spill
+                  dl[j] = fma(gb[u] * t, t, dl[j]);
+                }
+              }
+          }
+        };
+        if (a.kind == 0) sweep(std::integral_constant<int, 0>{});
+        else if (a.kind == 1) sweep(std::integral_constant<int, 1>{});
+        else sweep(std::integral_constant<int, 2>{});
       } else {
         for (int c = 0; c < GC; ++c) trow[c] = 0.0;
       }

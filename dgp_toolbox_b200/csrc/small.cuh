@@ -187,6 +187,29 @@ __global__ void tril_scale_kernel(double* __restrict__ X, int Mp, long ld, int n
   *p = (j <= i) ? scale * *p : 0.0;
 }
 
+// In place on `nblk` square blocks laid side by side in a [Mp][ld] matrix: mirror the lower triangle into the upper one.
+__global__ void sym_fill_kernel(double* __restrict__ X, int Mp, long ld, int nblk) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)nblk * Mp * Mp) return;
+  const int j = (int)(idx % Mp);
+  const long r = idx / Mp;
+  const int i = (int)(r % Mp), b = (int)(r / Mp);
+  if (j > i) X[(long)i * ld + (long)b * Mp + j] = X[(long)j * ld + (long)b * Mp + i];
+}
+
+// G1 = tril(G1 - sum_d W_d), W_d side by side in a [Mp][nblk * Mp] matrix (V-form adjoint, see backward_layer).
+__global__ void g1_finish_kernel(double* __restrict__ G1, const double* __restrict__ W, int Mp, int nblk) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)Mp * Mp) return;
+  const int i = (int)(idx / Mp), j = (int)(idx % Mp);
+  double s = 0.0;
+  if (j <= i) {
+    for (int b = 0; b < nblk; ++b) s += W[(long)i * nblk * Mp + (long)b * Mp + j];
+    s = G1[idx] - s;
+  }
+  G1[idx] = s;
+}
+
 // Cholesky adjoint core: out = sym(Phi(P)), Phi = lower triangle with halved diagonal, sym(Q) = (Q + Q^T) / 2.
 __global__ void phi_sym_kernel(const double* __restrict__ P, int Mp, double* __restrict__ out) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -464,8 +464,7 @@ def test_wb2_wb2s_ev_match_oracle():
     ev = D.EV([c, -0.1], 3).run([pm, pm2], prob["X"], analytic=True, num_samples=S, zs=[zs, zs2])
     ev_o = torch.cat([O.ev_analytic(ym, yv, c), O.ev_analytic(ym2, yv2, -0.1)], 1)
     assert rel_err(ev, ev_o) < 1e-8
-    with pytest.raises(NotImplementedError):
-        D.PoF(0.0, 3).run(pm, prob["X"])
+    assert rel_err(D.PoF(c, 3).run(pm, prob["X"], num_samples=S, zs=zs), O.pof(ym, yv, c)) < 1e-8
 
 
 @pytest.mark.parametrize("dims", [(3, [3], 14, 11, 3, None), (5, [3, 6], 70, 77, 2, None), (8, [8], 256, 512, 2, None),

@@ -19,6 +19,10 @@ for (D0, units, M, N, S) in [(3, [3, 2], 70, 150, 3), (8, [8], 128, 200, 4)]:
             model.predict(X, S, seed=3)
             D.EI(0.0, D0).run(model, X, analytic=False, num_samples=S, seed=4)
     ctx.set_fused(True); ctx.set_share_first_layer(True)
+    ctx.set_vform(True, "always")                      # V-form adjoint (fused and, with DGP_B200_FUSED_BWD=0, unfused data path)
+    model.elbo_flat((X, Y), want_grad=True, seed=1)
+    torch.cuda.synchronize()
+    ctx.set_vform(True, True)
     ctx.set_workspace_limit(64 << 20)
     model.elbo_flat((X, Y), want_grad=True, seed=1)
     ctx.set_workspace_limit(24 << 30)
