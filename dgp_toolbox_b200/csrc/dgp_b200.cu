@@ -641,7 +641,7 @@ int forward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, ChunkLa
 #define FUSED_LAUNCH(BM_, PT_, WM_, WN_)                                                                                   \
     do {                                                                                                                   \
       if (!c->dry) CK(cudaFuncSetAttribute(fused_forward_kernel<BM_, PT_, WM_, WN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem)); \
-      LAUNCH((fused_forward_kernel<BM_, PT_, WM_, WN_>), grid, 288, smem, f);                                              \
+      LAUNCH((fused_forward_kernel<BM_, PT_, WM_, WN_>), grid, (FusedCfg<BM_, PT_, WM_, WN_>::THREADS), smem, f);                                              \
     } while (0)
     switch (cfg) {
       case 0: FUSED_LAUNCH(128, 64, 4, 2); break;
@@ -772,7 +772,7 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
 #define FUSED_BWD_LAUNCH(BM_, WM_, WN_, DM_)                                                                                \
       do {                                                                                                                  \
         if (!c->dry) CK(cudaFuncSetAttribute((fused_backward_kernel<BM_, 64, WM_, WN_, DM_>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem)); \
-        LAUNCH((fused_backward_kernel<BM_, 64, WM_, WN_, DM_>), grid, 288, smem, f);                                        \
+        LAUNCH((fused_backward_kernel<BM_, 64, WM_, WN_, DM_>), grid, 384, smem, f);                                        \
       } while (0)
       if (w.bcfg == 0) { if (w.D_in <= 8) FUSED_BWD_LAUNCH(128, 4, 2, 8); else FUSED_BWD_LAUNCH(128, 4, 2, 16); }
       else { if (w.D_in <= 8) FUSED_BWD_LAUNCH(64, 2, 4, 8); else FUSED_BWD_LAUNCH(64, 2, 4, 16); }

@@ -149,6 +149,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// Register re-partitioning between warp groups (setmaxnreg, sm_90a+): a CTA of 12 warps is launched with 168 registers per thread
+// (3 warps per SM sub-partition x 32 x 168 fills its 16 K registers); the warp group that only issues bulk copies shrinks to 40
+// and the two consumer groups grow to 232, which is what lets the straight-line DMMA blocks keep their accumulators, both operand
+// fragment sets and the addressing in registers without spills.
+constexpr int kRegsProducer = 40, kRegsConsumer = 232;
+__device__ __forceinline__ void regs_shrink() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer)); }
+__device__ __forceinline__ void regs_grow() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsConsumer)); }
+
 __device__ __forceinline__ void group_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -198,7 +206,8 @@ __device__ __forceinline__ void panel_dispatch(double (&c0)[TM][TN], double (&c1
 template <int BM, int PT, int WM, int WN>
 struct FusedCfg {
   static_assert(WM * WN == 8, "8 consumer warps");
-  static constexpr int THREADS = 288;
+  static constexpr bool REGSPLIT = !(BM == 64 && PT == 32);   // the 2-CTA/SM configuration keeps 9 warps at equal registers
+  static constexpr int THREADS = REGSPLIT ? 384 : 288;
   static constexpr int GT = WM * 32;          // threads per consumer group
   static constexpr int GC = PT / WN;          // tile columns per group
   static constexpr int TM = BM / (8 * WM), TN = GC / 8;
@@ -211,7 +220,7 @@ struct FusedCfg {
 };
 
 template <int BM, int PT, int WM, int WN>
-__global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_forward_kernel(FusedFwdArgs a) {
+__global__ void __launch_bounds__((FusedCfg<BM, PT, WM, WN>::THREADS), (BM == 64 && PT == 32) ? 2 : 1) fused_forward_kernel(FusedFwdArgs a) {
   using Cfg = FusedCfg<BM, PT, WM, WN>;
   constexpr int TM = Cfg::TM, TN = Cfg::TN, LDT = Cfg::LDT, PANEL = Cfg::PANEL, STAGES = Cfg::STAGES, GT = Cfg::GT, GC = Cfg::GC;
   extern __shared__ __align__(128) double fsmem[];
@@ -261,7 +270,9 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
   }
   __syncthreads();
 
-  if (warp == 8) {
+  if (warp >= 8) {
+    if constexpr (Cfg::REGSPLIT) regs_shrink();
+    if (warp > 8) return;
     // ---- producer: one bulk copy per panel, in stream order, round after round ----
     if (lane == 0) {
       int st = 0, q = 0, pass = 0, qq = 0;
@@ -292,6 +303,7 @@ __global__ void __launch_bounds__(288, (BM == 64 && PT == 32) ? 2 : 1) fused_for
   }
 
   // ---- consumers ----
+  if constexpr (Cfg::REGSPLIT) regs_grow();
   const int g8 = lane >> 2, t4 = lane & 3;
   // Warps w and w + 4 share an SM sub-partition (and its FP64 pipe). With group = warp / WM the two warps of a sub-partition belong
   // to DIFFERENT column groups, which run decoupled (they share only the panel ring): while one group is in a block-end phase

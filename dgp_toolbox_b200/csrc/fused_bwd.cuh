@@ -36,6 +36,11 @@ struct FusedBwdArgs {
   int warp_major_groups, group_skew;    // see FusedFwdArgs
 };
 
+// Inside a row block the k-panels are visited long, short, long, short ...: in natural order the panels of a diagonal block get
+// shorter and shorter (4, 4, 3, 3, 2, 2, 1, 1 active m-tiles per warp) and the last ones hold less DMMA work than one ring refill
+// takes, so the consumers ran dry there (ring waits 11% -> see profiles/). The order of a k-sum only changes rounding.
+__host__ __device__ __forceinline__ int zigzag(int idx, int n) { return (idx & 1) ? n - 1 - (idx >> 1) : (idx >> 1); }
+
 // Panel order: pass 0: row block i = 0..nb-1, output d = 0..D-1, k-panels 0..(i+1)*BM/16-1 of C_d^T; pass 1: row block i,
 // k-panels i*BM/16..Mp/16-1 of Lu^-T. One CTA per panel.
 template <int BM>
@@ -46,11 +51,11 @@ __global__ void __launch_bounds__(256) pack_bwd_stream_kernel(const double* __re
   const int NP0 = D * kpb * nb * (nb + 1) / 2;
   if (q < NP0) {
     for (i = 0;; ++i) { const int cnt = D * (i + 1) * kpb; if (q < cnt) break; q -= cnt; }
-    d = q / ((i + 1) * kpb); ks = q % ((i + 1) * kpb);
+    d = q / ((i + 1) * kpb); ks = zigzag(q % ((i + 1) * kpb), (i + 1) * kpb);
   } else {
     q -= NP0; pass = 1;
     for (i = 0;; ++i) { const int cnt = (nb - i) * kpb; if (q < cnt) break; q -= cnt; }
-    ks = i * kpb + q;
+    ks = i * kpb + zigzag(q, (nb - i) * kpb);
   }
   double* dst = stream + (long)blockIdx.x * BM * kPanelK;
   for (int idx = threadIdx.x; idx < BM * kPanelK; idx += blockDim.x) {
@@ -105,7 +110,7 @@ constexpr int kZChunk = 32;   // inducing rows staged per round of the input-gra
 template <int BM, int PT, int WM, int WN>
 struct FusedBwdCfg {
   static_assert(WM * WN == 8, "8 consumer warps");
-  static constexpr int THREADS = 288;
+  static constexpr int THREADS = 384;   // 8 consumer warps + a warp group whose first warp is the producer (see regs_shrink / regs_grow)
   static constexpr int GT = WM * 32, GC = PT / WN;
   static constexpr int TM = BM / (8 * WM), TN = GC / 8;
   static constexpr int LDT = PT + 4;
@@ -117,7 +122,7 @@ struct FusedBwdCfg {
 };
 
 template <int BM, int PT, int WM, int WN, int DMAX>
-__global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) {
+__global__ void __launch_bounds__(384, 1) fused_backward_kernel(FusedBwdArgs a) {
   using Cfg = FusedBwdCfg<BM, PT, WM, WN>;
   constexpr int TM = Cfg::TM, TN = Cfg::TN, LDT = Cfg::LDT, PANEL = Cfg::PANEL, STAGE = Cfg::STAGE, STAGES = Cfg::STAGES;
   constexpr int GT = Cfg::GT, GC = Cfg::GC, KPB = BM / kPanelK;
@@ -145,7 +150,9 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
   }
   __syncthreads();
 
-  if (warp == 8) {
+  if (warp >= 8) {
+    regs_shrink();
+    if (warp > 8) return;
     // ---- producer: per stage one operator panel, and in pass 0 the 16 row segments of the T_d slab it multiplies ----
     if (lane == 0) {
       int st = 0;
@@ -159,7 +166,7 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
       int f_tl = 0, f_i = 0, f_d = 0, f_ks = 0;
       auto prefetch_next = [&]() {
         if (f_tl >= my_tiles) return;
-        const double* trow = a.T + ((long)f_d * a.Mp + (long)f_ks * kPanelK) * a.Pp + (long)(blockIdx.x + f_tl * gridDim.x) * PT;
+        const double* trow = a.T + ((long)f_d * a.Mp + (long)zigzag(f_ks, (f_i + 1) * KPB) * kPanelK) * a.Pp + (long)(blockIdx.x + f_tl * gridDim.x) * PT;
 #pragma unroll 4
         for (int r = 0; r < kPanelK; ++r)
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(trow + (long)r * a.Pp), "r"(PT * 8) : "memory");
@@ -172,7 +179,8 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
         int issued = 0;
         for (int i = 0; i < nb; ++i)
           for (int d = 0; d < a.D_out; ++d)
-            for (int ks = 0; ks < (i + 1) * KPB; ++ks) {
+            for (int ksi = 0; ksi < (i + 1) * KPB; ++ksi) {
+              const int ks = zigzag(ksi, (i + 1) * KPB);
               mbar_wait(empty + st, ph ^ 1);
               if (issued++ == STAGES) {
                 // All 8 consumer warps have released the first panel of THIS tile, so the previous tile's epilogue is over and
@@ -199,7 +207,8 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
               if (++st == STAGES) { st = 0; ph ^= 1; }
             }
         for (int i = 0; i < nb; ++i)
-          for (int ks = i * KPB; ks < kt; ++ks) {
+          for (int ksi = 0; ksi < kt - i * KPB; ++ksi) {
+            const int ks = i * KPB + zigzag(ksi, kt - i * KPB);
             mbar_wait(empty + st, ph ^ 1);
             const int nr = min(BM, ks * kPanelK - i * BM + kPanelK);   // upper operator: rows below the panel's k-range are dead
             mbar_arrive_expect_tx(full + st, (unsigned)(nr * kPanelK * 8));
@@ -213,6 +222,7 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
   }
 
   // ---- consumers ----
+  regs_grow();
   const int g8 = lane >> 2, t4 = lane & 3;
   const int wm = a.warp_major_groups ? warp % WM : warp / WN, wn = a.warp_major_groups ? warp / WM : warp % WN;
   const int tg = wm * 32 + lane;
@@ -265,7 +275,8 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
         double sc[TN];
 #pragma unroll
         for (int j = 0; j < TN; ++j) sc[j] = gv2[d * GC + j * 8 + g8];
-        for (int ks = 0; ks < (i + 1) * KPB; ++ks) {
+        for (int ksi = 0; ksi < (i + 1) * KPB; ++ksi) {
+          const int ks = zigzag(ksi, (i + 1) * KPB);
           const int num = ks * kPanelK - i * BM - 7 - wm * 8;   // lower operator: row r needs k <= r
           const int lo = num > 0 ? (num + 8 * WM - 1) / (8 * WM) : 0;
           const double* stage = pbuf + cst * STAGE;
@@ -328,7 +339,8 @@ __global__ void __launch_bounds__(288, 1) fused_backward_kernel(FusedBwdArgs a) 
       for (int ti = 0; ti < TM; ++ti)
 #pragma unroll
         for (int j = 0; j < TN; ++j) { c0[ti][j] = 0.0; c1[ti][j] = 0.0; }
-      for (int ks = i * KPB; ks < kt; ++ks) {
+      for (int ksi = 0; ksi < kt - i * KPB; ++ksi) {
+        const int ks = i * KPB + zigzag(ksi, kt - i * KPB);
         const int num = ks * kPanelK - i * BM + kPanelK - 1 - wm * 8;   // upper operator: row r needs k >= r
         const int hi = num >= 0 ? min(TM, num / (8 * WM) + 1) : 0;
         const double* stage = pbuf + cst * STAGE;
