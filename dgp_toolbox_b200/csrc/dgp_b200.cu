@@ -1215,6 +1215,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
           g.batch = D; g.sA = Mp; g.sB = Mp; g.sC = Mp;
           RC(gemm(c, g, false));
           g = gargs(w.CTcat, (long)D * Mp, w.DCt, (long)D * Mp, w.G1, Mp, Mp, Mp, D * Mp);
+          g.splitk = D >= 16 ? 16 : (D >= 2 ? D : 1); g.part = w.part_small;   // few output tiles, long K: split it
           RC(gemm(c, g, true));
           g = gargs(w.betaP, 32, w.dbeta, 32, w.G1, Mp, Mp, Mp, 32);
           g.beta = 1.0;
