@@ -43,8 +43,8 @@ def load_synthetic(package):
 
 def load_traffic():
     """Measured DRAM bytes per launch of the dominant kernels (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum),
-    read from the profile summary committed with this build (profiles/r02_traffic.json, written by tools/ncu_traffic.py from the
-    .ncu-rep of the SAME bench command; its header names the commit). No file -> traffic stays null: never a pasted literal."""
+    read from the profile summary committed with this build (profiles/r02_traffic.json, taken from the summaries tools/ncu_round.sh
+    writes for the SAME bench command; its header names the commit). No file -> traffic stays null: never a pasted literal."""
     try:
         with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             return json.load(f)
@@ -465,8 +465,10 @@ def main():
                           "tiles; panels + T_d slabs through one bulk-copy ring, FP64 DMMA)" if prof["fused_bwd"][0] > 0
                           else "dgp::gemm_kernel + rbf_bwd_kernel (unfused data adjoint)", data_cats, f_fwd,
                           traffic=traffic.get("fused_backward_kernel"))
-    k_param = kernel_entry("dgp::gemm_kernel (FP64 DMMA contractions over the point-samples: tril(dV V^T), tril(V diag(2Gv_d) T_d^T), "
-                           "V Gm, Gbar [X,1])", ["gemm_bwd_param"], f_fwd, traffic=traffic.get("gemm_kernel_param"))
+    f_param = synthetic.param_flops_per_point_sample(cfg["D0"], cfg["num_units"], cfg["M"], cfg["S"])
+    f_step = 2 * f_fwd + f_param   # forward + data adjoint + parameter contractions (W-form: D_out instead of 1 + D_out products)
+    k_param = kernel_entry("dgp::gemm_kernel (FP64 DMMA contractions over the point-samples: tril(V diag(2Gv_d) V^T) per output, "
+                           "V Gm, Gbar [X,1])", ["gemm_bwd_param"], f_param, traffic=traffic.get("gemm_kernel_param"))
     kernels = sorted([k_fwd, k_data, k_param], key=lambda k: -k["kernel_ms_per_step"])
     main, others = kernels[0], kernels[1:]
     flops_rank_step = f_step * nb * S

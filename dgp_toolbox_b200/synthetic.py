@@ -75,6 +75,15 @@ def flops_per_layer(D0, num_units, M, vform=False):
     return [(lead + dout) * M * M + 2 * M * din + 2 * M * (2 * dout + 1) for din, dout in zip(dims[:-1], dims[1:])]
 
 
+def param_flops_per_point_sample(D0, num_units, M, S):
+    """Flops per point-sample of the contractions over the point-samples that the V-form adjoint needs: the D_out lower-only
+    products W_d = V diag(2 Gv_d) V^T (D_out M^2; the reference order and the A-form need (1 + D_out) M^2 — G1 = tril(dV V^T) is
+    derived from the W_d once per step), V Gm (2 M D_out) and Gbar [X, 1] (2 M (D_in + 1)); first layer once per point."""
+    dims = [D0] + list(num_units) + [1]
+    fl = [dout * M * M + 2 * M * dout + 2 * M * (din + 1) for din, dout in zip(dims[:-1], dims[1:])]
+    return sum(fl) if len(fl) < 2 else fl[0] / S + sum(fl[1:])
+
+
 def flops_per_point_sample(D0, num_units, M, S=None):
     """(forward, ELBO+grad = 3x forward) flops per point-sample. S = None: the reference's formulation, every layer evaluated
     for every point-sample in the reference's operation order. S given: what this implementation needs — V-form
