@@ -361,7 +361,7 @@ struct LayerWs {
   double *dKu = nullptr, *dR = nullptr, *dqmu = nullptr, *H = nullptr, *rbf_red = nullptr, *sgv = nullptr;
   double *dZk = nullptr, *kuu_part = nullptr, *kuu_red = nullptr, *kl = nullptr;
   // fused conditional kernel: scaled inducing inputs, packed operator stream, panel schedule
-  double *Zs = nullptr, *stream = nullptr;
+  double *Zs = nullptr, *zz = nullptr, *stream = nullptr;
   PanelDesc* sched = nullptr;
   int NP = 0, fcfg = -1;   // fcfg: index into the fused configurations, -1 = not available
   // V-form of the conditional (forward-only calls): C_d = q_sqrt_d^T Lu^-T [D][Mp][Mp] and beta = Lu^-1 q_mu [Mp][32]
@@ -485,7 +485,7 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
           w.bstream = walloc(c, (size_t)w.NPb * BMb * kPanelK);
         }
       }
-      w.Zs = walloc(c, (size_t)w.M * w.D_in);
+      w.Zs = walloc(c, (size_t)w.M * w.D_in); w.zz = walloc(c, (size_t)w.Mp);
       w.stream = walloc(c, (size_t)w.NP * BM * kPanelK);
       w.sched = reinterpret_cast<PanelDesc*>(walloc(c, ((size_t)w.NP * sizeof(PanelDesc) + 7) / 8));
     }
@@ -553,6 +553,7 @@ int prep_layers(dgp_ctx* c, const dgp_model_desc* model, std::vector<LayerWs>& l
     if ((int)sch.size() != w.NP) { c->err = "internal: panel schedule size mismatch"; return DGP_ERR_ARG; }
     H2D(w.sched, sch.data(), sch.size() * sizeof(PanelDesc));
     LAUNCH(scale_z_kernel, (unsigned)((w.M * w.D_in + 255) / 256), 256, 0, d.Z, d.lengthscales, w.M, w.D_in, w.Zs);
+    LAUNCH(zz_kernel, (unsigned)((w.Mp + 127) / 128), 128, 0, w.Zs, w.M, w.Mp, w.D_in, w.zz);
     const double* tsrc = w.vform ? w.Cmat : w.RpT;   // operator of the T_d passes
     if (BM == 128) LAUNCH(pack_stream_kernel<128>, w.NP, 256, 0, w.sched, w.Linv, w.LinvT, tsrc, w.Mp, w.stream);
     else LAUNCH(pack_stream_kernel<64>, w.NP, 256, 0, w.sched, w.Linv, w.LinvT, tsrc, w.Mp, w.stream);
@@ -619,7 +620,7 @@ int forward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, ChunkLa
     CAT(DGP_CAT_FUSED_FWD);
     FusedFwdArgs f;
     memset(&f, 0, sizeof(f));
-    f.stream = w.stream; f.sched = w.sched; f.NP = w.NP; f.Zs = w.Zs; f.ls = d.lengthscales; f.var = d.variance;
+    f.stream = w.stream; f.sched = w.sched; f.NP = w.NP; f.Zs = w.Zs; f.zz = w.zz; f.ls = d.lengthscales; f.var = d.variance;
     f.vform = w.vform ? 1 : 0; f.qmu = w.vform ? w.betaP : d.q_mu; f.qmu_ld = w.vform ? 32 : w.D_out;
     f.Xin = cl.Xin; f.xmod = cl.xmod; f.D_in = w.D_in; f.mfW = d.mf_W; f.mfb = d.mf_b; f.mean_kind = d.mean_kind; f.kind = d.kernel_kind;
     f.z_in = (io.zs && io.zs[layer]) ? io.zs[layer] : nullptr;

@@ -102,9 +102,20 @@ __global__ void scale_z_kernel(const double* __restrict__ Z, const double* __res
   if (idx < M * D) Zs[idx] = Z[idx] * (1.0 / ls[idx % D]);
 }
 
+// zz[m] = |Zs[m]|^2 (rows >= M: 0), the inducing-point half of the expanded squared distance
+__global__ void zz_kernel(const double* __restrict__ Zs, int M, int Mp, int D, double* __restrict__ zz) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= Mp) return;
+  double s = 0.0;
+  if (m < M)
+    for (int j = 0; j < D; ++j) s = fma(Zs[(long)m * D + j], Zs[(long)m * D + j], s);
+  zz[m] = s;
+}
+
 struct FusedFwdArgs {
   const double* stream; const PanelDesc* sched; int NP;
   const double* Zs;                                     // [M][D_in] inducing inputs / lengthscales
+  const double* zz;                                     // [Mp] |Zs[m]|^2
   const double* ls; const double* var;                  // [D_in], [1]
   const double* qmu; int qmu_ld;                        // [M][qmu_ld] weights of the mean: q_mu (ld = D_out), or beta = Lu^-1 q_mu in V-form
   int vform;                                            // 1: skip the A pass, T_d = C_d V with C_d = q_sqrt_d^T Lu^-T packed in the stream
@@ -330,7 +341,7 @@ __global__ void __launch_bounds__((FusedCfg<BM, PT, WM, WN>::THREADS), (BM == 64
   }
 
 #ifdef DGP_DEBUG_PHASECLK
-  long long ph_kuf = 0, ph_loop = 0, ph_end = 0, ph_epi = 0, ph_wait = 0, ph_dot = 0;
+  long long ph_kuf = 0, ph_loop = 0, ph_end = 0, ph_epi = 0, ph_wait = 0, ph_dot = 0, ph_k0 = 0, ph_k1 = 0, ph_k2 = 0;
   const long long ph_t0 = clock64();
 #define PH_MARK(var) const long long var = clock64()
 #define PH_ADD(acc, from) acc += clock64() - (from)
@@ -342,65 +353,133 @@ __global__ void __launch_bounds__((FusedCfg<BM, PT, WM, WN>::THREADS), (BM == 64
     const long p0 = (long)(blockIdx.x + tl * gridDim.x) * PT + col0;   // first point-sample of this group's columns
     PH_MARK(ph_a);
     group_sync(bar_id, GT);   // previous tile's epilogue is done with the group's columns / colsum
+    PH_ADD(ph_k0, ph_a);
+    PH_MARK(ph_a1);
     // ---- stage 1: scaled inputs, then the Kuf tile ----
+    // xs[j][c] is stored with the 8-column blocks of row j rotated by j & 3 (GC = 32): the B-fragment reads below (four rows j,
+    // eight columns) then touch 32 different banks.
+    constexpr int XSW = GC == 32 ? 1 : 0;
     for (int idx = tg; idx < a.D_in * GC; idx += GT) {
       const int j = idx / GC, c = idx % GC;
       const long p = p0 + c;
-      xs[idx] = (p < a.P) ? a.Xin[(p % a.xmod) * a.D_in + j] * (1.0 / a.ls[j]) : 0.0;
+      xs[j * GC + (c ^ (XSW * ((j & 3) << 3)))] = (p < a.P) ? a.Xin[(p % a.xmod) * a.D_in + j] * (1.0 / a.ls[j]) : 0.0;
     }
     group_sync(bar_id, GT);
-    // one inducing row per thread (its scaled coordinates stay in registers, one global-load latency per row), loop over
-    // the group's columns; xs reads are warp-wide broadcasts
-    for (int m = tg; m < a.Mp; m += GT) {
-      double* trow = tile + m * LDT + col0;
-      if (m < a.M) {
-        constexpr int ZR = 8;   // coordinates kept in registers; wider layers re-read the rest through L1
-        double zr[ZR];
-        const double* zg = a.Zs + (long)m * a.D_in;
+    PH_ADD(ph_k1, ph_a1);
+    PH_MARK(ph_a2);
+    // Kuf through the expanded square (the reference's own form, gpflow square_distance): r2 = |z|^2 + |x|^2 - 2 z.x with the
+    // [Mp x D_in] . [D_in x GC] dot products on the tensor pipe (one 8 x 8 unit per (m-tile, n-tile), D_in / 4 k-steps), then the
+    // kernel function on the accumulator fragments: 8 independent exp chains per m-tile and thread, half the FP64 instructions
+    // of a difference-based sweep.
+    {
+      constexpr int TNG = GC / 8;
+      double xx0[TNG], xx1[TNG];
 #pragma unroll
-        for (int j = 0; j < ZR; ++j)
-          if (j < a.D_in) zr[j] = zg[j];
-        // four columns at a time: their distance and exp chains are independent, so the FP64 pipe sees 4x the ILP of a plain loop
-        // (the kernel switch is hoisted so that each variant is straight-line code the scheduler can interleave)
-        auto sweep = [&](auto kconst) {
-          constexpr int KIND = decltype(kconst)::value;
-          constexpr int U = 4;
-          static_assert(GC % U == 0, "column unroll");
-          for (int c = 0; c < GC; c += U) {
-            double r2[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) r2[u] = 0.0;
-#pragma unroll
-            for (int j = 0; j < ZR; ++j)
-              if (j < a.D_in) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                  const double t = zr[j] - xs[j * GC + c + u];
-                  r2[u] = fma(t, t, r2[u]);
-                }
-              }
-            for (int j = ZR; j < a.D_in; ++j) {
-              const double zj = zg[j];
-#pragma unroll
-              for (int u = 0; u < U; ++u) {
-                const double t = zj - xs[j * GC + c + u];
-                r2[u] = fma(t, t, r2[u]);
-              }
-            }
-            double kv[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) kv[u] = kernel_value(KIND, r2[u], s2);
-#pragma unroll
-            for (int u = 0; u < U; ++u) trow[c + u] = (p0 + c + u < a.P) ? kv[u] : 0.0;
-          }
-        };
-        if (a.kind == 0) sweep(std::integral_constant<int, 0>{});
-        else if (a.kind == 1) sweep(std::integral_constant<int, 1>{});
-        else sweep(std::integral_constant<int, 2>{});
-      } else {
-        for (int c = 0; c < GC; ++c) trow[c] = 0.0;
+      for (int nt = 0; nt < TNG; ++nt) {
+        const int col = nt * 8 + 2 * t4;
+        double q0 = 0.0, q1 = 0.0;
+        for (int j = 0; j < a.D_in; ++j) {
+          const int sw = XSW * ((j & 3) << 3);
+          const double v0 = xs[j * GC + (col ^ sw)], v1 = xs[j * GC + ((col + 1) ^ sw)];
+          q0 = fma(v0, v0, q0); q1 = fma(v1, v1, q1);
+        }
+        xx0[nt] = q0; xx1[nt] = q1;
       }
+      // MB m-tiles per round with all their inducing-input loads issued up front: these come from L2 (the shared-memory carve-out
+      // leaves ~12 KB of L1), and one m-tile at a time the stage was bound by that latency (2.6 k clocks per m-tile, measured)
+      auto sweep = [&](auto kconst, auto ksconst) {
+        constexpr int KIND = decltype(kconst)::value;
+        constexpr int KS = decltype(ksconst)::value;   // k-steps of 4 input dimensions, zero-padded beyond D_in
+        constexpr int MB = 4;                          // operand registers: MB * KS + KS * TNG doubles
+        const int nmt = a.Mp / 8;
+        for (int mt0 = wm; mt0 < nmt; mt0 += WM * MB) {
+          double av[MB][KS], zzv[MB];
+#pragma unroll
+          for (int u = 0; u < MB; ++u) {
+            const int m = (mt0 + u * WM) * 8 + g8;
+            const bool ml = mt0 + u * WM < nmt && m < a.M;
+#pragma unroll
+            for (int kk = 0; kk < KS; ++kk) {
+              const int j = kk * 4 + t4;
+              av[u][kk] = (ml && j < a.D_in) ? a.Zs[(long)m * a.D_in + j] : 0.0;
+            }
+            zzv[u] = ml ? a.zz[m] : 0.0;
+          }
+          double bv[KS][TNG];
+#pragma unroll
+          for (int kk = 0; kk < KS; ++kk) {
+            const int j = kk * 4 + t4;
+#pragma unroll
+            for (int nt = 0; nt < TNG; ++nt) bv[kk][nt] = j < a.D_in ? xs[j * GC + ((nt * 8 + g8) ^ (XSW * (t4 << 3)))] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < MB; ++u) {
+            const int mt = mt0 + u * WM;
+            if (mt >= nmt) break;
+            const int m = mt * 8 + g8;
+            double e0[TNG], e1[TNG];
+#pragma unroll
+            for (int nt = 0; nt < TNG; ++nt) { e0[nt] = 0.0; e1[nt] = 0.0; }
+#pragma unroll
+            for (int kk = 0; kk < KS; ++kk)
+#pragma unroll
+              for (int nt = 0; nt < TNG; ++nt) dmma884(e0[nt], e1[nt], av[u][kk], bv[kk][nt]);
+            const bool ml = m < a.M;
+            double k0[TNG], k1[TNG];
+#pragma unroll
+            for (int nt = 0; nt < TNG; ++nt) {
+              k0[nt] = kernel_value(KIND, fmax(fma(-2.0, e0[nt], zzv[u] + xx0[nt]), 0.0), s2);
+              k1[nt] = kernel_value(KIND, fmax(fma(-2.0, e1[nt], zzv[u] + xx1[nt]), 0.0), s2);
+            }
+#pragma unroll
+            for (int nt = 0; nt < TNG; ++nt) {
+              const int col = nt * 8 + 2 * t4;
+              *reinterpret_cast<double2*>(tile + m * LDT + col0 + col) =
+                  make_double2((ml && p0 + col < a.P) ? k0[nt] : 0.0, (ml && p0 + col + 1 < a.P) ? k1[nt] : 0.0);
+            }
+          }
+        }
+      };
+      // wider layers: one m-tile at a time, k-steps in a run-time loop (keeps the register footprint of this stage small)
+      auto sweep_wide = [&](auto kconst) {
+        constexpr int KIND = decltype(kconst)::value;
+        const int ksteps = (a.D_in + 3) >> 2;
+        for (int mt = wm; mt < a.Mp / 8; mt += WM) {
+          const int m = mt * 8 + g8;
+          const bool ml = m < a.M;
+          double e0[TNG], e1[TNG];
+#pragma unroll
+          for (int nt = 0; nt < TNG; ++nt) { e0[nt] = 0.0; e1[nt] = 0.0; }
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const int j = kk * 4 + t4;
+            const bool jl = j < a.D_in;
+            const double avv = (jl && ml) ? a.Zs[(long)m * a.D_in + j] : 0.0;
+#pragma unroll
+            for (int nt = 0; nt < TNG; ++nt) {
+              const double bvv = jl ? xs[j * GC + ((nt * 8 + g8) ^ (XSW * (t4 << 3)))] : 0.0;
+              dmma884(e0[nt], e1[nt], avv, bvv);
+            }
+          }
+          const double zzm = a.zz[m];
+#pragma unroll
+          for (int nt = 0; nt < TNG; ++nt) {
+            const int col = nt * 8 + 2 * t4;
+            const double ka = kernel_value(KIND, fmax(fma(-2.0, e0[nt], zzm + xx0[nt]), 0.0), s2);
+            const double kb = kernel_value(KIND, fmax(fma(-2.0, e1[nt], zzm + xx1[nt]), 0.0), s2);
+            *reinterpret_cast<double2*>(tile + m * LDT + col0 + col) =
+                make_double2((ml && p0 + col < a.P) ? ka : 0.0, (ml && p0 + col + 1 < a.P) ? kb : 0.0);
+          }
+        }
+      };
+      auto sweep_k = [&](auto kconst) {
+        if (a.D_in <= 8) sweep(kconst, std::integral_constant<int, 2>{});
+        else sweep_wide(kconst);
+      };
+      if (a.kind == 0) sweep_k(std::integral_constant<int, 0>{});
+      else if (a.kind == 1) sweep_k(std::integral_constant<int, 1>{});
+      else sweep_k(std::integral_constant<int, 2>{});
     }
+    PH_ADD(ph_k2, ph_a2);
     group_sync(bar_id, GT);
     PH_ADD(ph_kuf, ph_a);
     PH_MARK(ph_b);
@@ -567,8 +646,8 @@ __global__ void __launch_bounds__((FusedCfg<BM, PT, WM, WN>::THREADS), (BM == 64
 #ifdef DGP_DEBUG_PHASECLK
   if (lane == 0 && blockIdx.x == 1 && my_tiles > 10 && (warp == 0 || warp == 5)) {
     const double tot = (double)(clock64() - ph_t0);
-    printf("fused_fwd cta %d warp %d (D_out %d, tiles %d): total %.0f clk/tile | kuf %.1f%% loop %.1f%% (of which block-ends %.1f%%, panel waits %.1f%%) epilogue %.1f%% (dot products %.1f%%)\n",
-           blockIdx.x, warp, a.D_out, my_tiles, tot / my_tiles, 100.0 * ph_kuf / tot, 100.0 * ph_loop / tot, 100.0 * ph_end / tot, 100.0 * ph_wait / tot, 100.0 * ph_epi / tot, 100.0 * ph_dot / tot);
+    printf("fused_fwd cta %d warp %d (D_out %d, tiles %d): total %.0f clk/tile | kuf %.1f%% loop %.1f%% (of which block-ends %.1f%%, panel waits %.1f%%) epilogue %.1f%% (dot products %.1f%%) | kuf split: first sync %.1f%% inputs %.1f%% compute %.1f%%\n",
+           blockIdx.x, warp, a.D_out, my_tiles, tot / my_tiles, 100.0 * ph_kuf / tot, 100.0 * ph_loop / tot, 100.0 * ph_end / tot, 100.0 * ph_wait / tot, 100.0 * ph_epi / tot, 100.0 * ph_dot / tot, 100.0 * ph_k0 / tot, 100.0 * ph_k1 / tot, 100.0 * ph_k2 / tot);
   }
 #endif
 #ifdef DGP_DEBUG_WAITCLK

@@ -370,3 +370,25 @@ def test_foreign_dlpack_producers_enter_through_as_device():
         m, v = model.predict(obj, 4, seed=9)
         assert torch.equal(m, ref_m) and torch.equal(v, ref_v)
     assert D._lib.as_device(dev).data_ptr() == dev._b.data_ptr()  # no copy for a float64 CUDA producer
+
+
+def test_kernel_exponential_is_accurate_to_ulps():
+    """The kernel functions use a branch-free exp for non-positive arguments (csrc/common.cuh exp_nonpos) so that independent
+    evaluations interleave; it must stay within 2 ulp of the correctly rounded value over the whole argument range, give exp(0) = 1
+    exactly (unit diagonal of Kuu / variance) and clamp below -700 (true value < 1e-304)."""
+    import dgp_toolbox_b200 as D
+    G = D.gpflow_shim
+    x = np.concatenate([np.linspace(0.0, 37.0, 20001), np.random.default_rng(0).uniform(0.0, 37.0, 20000)])[:, None]
+    k = G.SquaredExponential(variance=1.0, lengthscales=1.0)
+    K = k.K(x, np.zeros((1, 1))).cpu().numpy()[:, 0]
+    ref = np.exp(-0.5 * x[:, 0] ** 2)
+    assert K[0] == 1.0
+    rel = np.abs(K - ref) / ref
+    assert rel.max() < 2 * np.finfo(np.float64).eps, rel.max()
+    far = k.K(np.array([[40.0], [1e3]]), np.zeros((1, 1))).cpu().numpy()[:, 0]
+    assert np.all(far >= 0.0) and np.all(far < 1e-300)
+    for cls, f in ((G.Matern32, lambda r: (1 + np.sqrt(3) * r) * np.exp(-np.sqrt(3) * r)),
+                   (G.Matern52, lambda r: (1 + np.sqrt(5) * r + 5.0 / 3.0 * r * r) * np.exp(-np.sqrt(5) * r))):
+        Km = cls(variance=1.0, lengthscales=1.0).K(x[1:], np.zeros((1, 1))).cpu().numpy()[:, 0]
+        refm = f(x[1:, 0])
+        assert (np.abs(Km - refm) / refm).max() < 1e-14
