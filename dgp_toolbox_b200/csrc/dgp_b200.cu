@@ -762,7 +762,7 @@ int backward_layer(dgp_ctx* c, const dgp_layer_desc& d, const LayerWs& w, const 
       FusedBwdArgs f;
       memset(&f, 0, sizeof(f));
       f.stream = w.bstream; f.V = V; f.T = cl.T; f.GvT = up.GvT; f.gq = up.gq; f.Gm = up.GmPad; f.gm_ld = 32; f.beta = w.betaP;
-      f.Zs = w.Zs; f.ls = d.lengthscales; f.var = d.variance; f.Xin = cl.Xin; f.xmod = cl.xmod; f.D_in = w.D_in;
+      f.Zs = w.Zs; f.zz = w.zz; f.ls = d.lengthscales; f.var = d.variance; f.Xin = cl.Xin; f.xmod = cl.xmod; f.D_in = w.D_in;
       f.mfW = d.mf_W; f.mean_kind = d.mean_kind; f.kind = d.kernel_kind; f.M = w.M; f.Mp = Mp; f.D_out = D; f.P = P; f.Pp = Pp;
       f.dV = nullptr;   // dV stays on chip: the parameter contractions below do not read it
       f.Gbar = Gbar; f.dXin = dXin; f.XaugPad = XaugPad; f.part = rbf_part;

@@ -34,6 +34,7 @@ struct FusedBwdArgs {
   double* XaugPad;                      // [Pp][32] out: [x, 1, 0...]
   double* part;                         // [tiles * WN][D_in + 1] out: partial sums for dl_j, ds2
   int warp_major_groups, group_skew;    // see FusedFwdArgs
+  const double* zz;                     // [Mp] |Zs[m]|^2 (zz_kernel)
 };
 
 // Inside a row block the k-panels are visited long, short, long, short ...: in natural order the panels of a diagonal block get
@@ -105,7 +106,7 @@ __device__ __forceinline__ void bwd_panel_dispatch(double (&c0)[TM][TN], double 
   if constexpr (TM >= 4) { if (lo == TM - 3) { bwd_panel_block<TM - 3, TM, TM, TN, WM, LDT, SC>(c0, c1, pan, bt, sc, wm, g8, t4); return; } }
 }
 
-constexpr int kZChunk = 32;   // inducing rows staged per round of the input-gradient sweep
+
 
 template <int BM, int PT, int WM, int WN>
 struct FusedBwdCfg {
@@ -117,7 +118,7 @@ struct FusedBwdCfg {
   static constexpr int PANEL = BM * kPanelK, SLAB = kPanelK * LDT, STAGE = PANEL + SLAB;
   static constexpr int STAGES = 3;
   static size_t smem_bytes(int Mp, int D_in, int D_out) {
-    return ((size_t)STAGES * STAGE + (size_t)Mp * LDT + (size_t)D_in * PT + (size_t)D_out * PT + (size_t)PT + 2 * STAGES + 2 + (size_t)WN * WM * (kMaxD + 1) + (size_t)WN * kZChunk * D_in) * sizeof(double);
+    return ((size_t)STAGES * STAGE + (size_t)Mp * LDT + (size_t)D_in * PT + (size_t)D_out * PT + (size_t)PT + 2 * STAGES + 2 + (size_t)WN * WM * (kMaxD + 1) + (size_t)PT * (D_in + 1)) * sizeof(double);
   }
 };
 
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(384, 1) fused_backward_kernel(FusedBwdArgs a) 
   using Cfg = FusedBwdCfg<BM, PT, WM, WN>;
   constexpr int TM = Cfg::TM, TN = Cfg::TN, LDT = Cfg::LDT, PANEL = Cfg::PANEL, STAGE = Cfg::STAGE, STAGES = Cfg::STAGES;
   constexpr int GT = Cfg::GT, GC = Cfg::GC, KPB = BM / kPanelK;
+  constexpr int XSW = GC == 32 ? 1 : 0;   // 8-column blocks of xs row j rotated by j & 3 (conflict-free B fragments, see fused.cuh)
   extern __shared__ __align__(128) double bsmem[];
   double* pbuf = bsmem;                                   // [STAGES][PANEL | SLAB]
   double* tile = pbuf + STAGES * STAGE;                   // [Mp][LDT]   dV -> K-bar -> Gbar
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(384, 1) fused_backward_kernel(FusedBwdArgs a) 
   unsigned long long* empty = full + STAGES;
   unsigned long long* vbar = empty + STAGES;                      // the tile's V rows have landed in the resident tile
   double* red_all = reinterpret_cast<double*>(vbar + 2);          // [WN][WM][kMaxD + 1] scratch of the per-tile group reductions
-  double* zbuf_all = red_all + WN * WM * (kMaxD + 1);             // [WN][kZChunk][D_in] staged rows of the scaled inducing inputs
+  double* us_all = red_all + WN * WM * (kMaxD + 1);               // [WN][GC][D_in + 1]  U = Gbar^T [Zs, 1] of the group's columns
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = a.Mp / BM, kt = a.Mp / kPanelK;
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(384, 1) fused_backward_kernel(FusedBwdArgs a) 
   double* gv2 = gv2_all + wn * a.D_out * GC;
   double* gqs = gq_all + wn * GC;
   double* red = red_all + wn * WM * (kMaxD + 1);
-  double* zbuf = zbuf_all + wn * kZChunk * a.D_in;
+  double* us = us_all + wn * GC * (a.D_in + 1);
   const int bar_id = 1 + wn;
   const double s2 = a.var[0];
   int cst = 0;
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(384, 1) fused_backward_kernel(FusedBwdArgs a) 
     for (int idx = tg; idx < a.D_in * GC; idx += GT) {
       const int j = idx / GC, c = idx % GC;
       const long p = p0 + c;
-      xs[idx] = (p < a.P) ? a.Xin[(p % a.xmod) * a.D_in + j] * (1.0 / a.ls[j]) : 0.0;
+      xs[j * GC + (c ^ (XSW * ((j & 3) << 3)))] = (p < a.P) ? a.Xin[(p % a.xmod) * a.D_in + j] * (1.0 / a.ls[j]) : 0.0;   // layout: fused.cuh
     }
     for (int idx = tg; idx < a.D_out * GC; idx += GT) {
       const int d = idx / GC, c = idx % GC;
@@ -363,84 +365,205 @@ __global__ void __launch_bounds__(384, 1) fused_backward_kernel(FusedBwdArgs a) 
 
     PH_ADD(ph_p1, ph_d);
     PH_MARK(ph_e);
-    // ---- kernel adjoint on the resident K-bar tile ----
-    // row sweep: one inducing row per thread; Gbar = K-bar * (-2 dk/dr2) in place, row-local sums for dl_j and ds2
-    double dl[DMAX], ds2 = 0.0;
+    // ---- kernel adjoint on the resident K-bar tile, in accumulator-fragment layout ----
+    // The FP64 (non-tensor) pipe runs 64 FMA per clock and SM, and a row-per-thread sweep (distances by differences, dl_j += gb t_j^2,
+    // then a second sweep for the input gradient) needed ~85 FP64 instructions per element of the tile. Here the distances come from
+    // the expanded square with the dot products on the tensor pipe (as in the forward kernel), and everything that is a contraction of
+    // Gbar moves there too:  U = Gbar^T [Zs, 1]  (input gradient and column sums T0),  S = Gbar [Xs, 1]  (row sums S0 and S1), with
+    //   dX[c][j] = (U[c][j] - x_cj T0_c) / l_j,      dl_j = (sum_m z_mj^2 S0_m - 2 z_mj S1_mj + sum_c x_cj^2 T0_c) / l_j.
+    constexpr int TNG = GC / 8, KS = DMAX / 4, NTJ = DMAX / 8 + 1, KC = GC / 4, MB = 4;
+    const int J = a.D_in + 1, nmt = a.Mp / 8;
+    double ds2 = 0.0, dla[NTJ - 1][2];
 #pragma unroll
-    for (int j = 0; j < DMAX; ++j) dl[j] = 0.0;
-    for (int m = tg; m < a.Mp; m += GT) {
-      double* trow = tile + m * LDT + col0;
-      if (m < a.M) {
-        double zr[DMAX];
-        const double* zg = a.Zs + (long)m * a.D_in;
+    for (int jt = 0; jt < NTJ - 1; ++jt) { dla[jt][0] = 0.0; dla[jt][1] = 0.0; }
+    {
+      double xx0[TNG], xx1[TNG], bx[KS][TNG];
 #pragma unroll
-        for (int j = 0; j < DMAX; ++j) zr[j] = j < a.D_in ? zg[j] : 0.0;
-        // four columns at a time (independent distance / exp chains), kernel switch hoisted: see fused_forward_kernel
-        auto sweep = [&](auto kconst) {
-          constexpr int KIND = decltype(kconst)::value;
-          constexpr int U = 4;
-          static_assert(GC % U == 0, "column unroll");
-          for (int c = 0; c < GC; c += U) {
-            double r2[U];
+      for (int nt = 0; nt < TNG; ++nt) {
+        const int col = nt * 8 + 2 * t4;
+        double q0 = 0.0, q1 = 0.0;
+        for (int j = 0; j < a.D_in; ++j) {
+          const int sw = XSW * ((j & 3) << 3);
+          const double v0 = xs[j * GC + (col ^ sw)], v1 = xs[j * GC + ((col + 1) ^ sw)];
+          q0 = fma(v0, v0, q0); q1 = fma(v1, v1, q1);
+        }
+        xx0[nt] = q0; xx1[nt] = q1;
+      }
 #pragma unroll
-            for (int u = 0; u < U; ++u) r2[u] = 0.0;
+      for (int kk = 0; kk < KS; ++kk) {
+        const int j = kk * 4 + t4;
 #pragma unroll
-            for (int j = 0; j < DMAX; ++j)
-              if (j < a.D_in) {
+        for (int nt = 0; nt < TNG; ++nt) bx[kk][nt] = j < a.D_in ? xs[j * GC + ((nt * 8 + g8) ^ (XSW * (t4 << 3)))] : 0.0;
+      }
+      auto sweep = [&](auto kconst) {
+        constexpr int KIND = decltype(kconst)::value;
+        for (int mt0 = wm; mt0 < nmt; mt0 += WM * MB) {
+          double av[MB][KS], zzv[MB];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                  const double t = zr[j] - xs[j * GC + c + u];
-                  r2[u] = fma(t, t, r2[u]);
-                }
-              }
-            double k[U], gf[U], gb[U];
+          for (int u = 0; u < MB; ++u) {
+            const int m = (mt0 + u * WM) * 8 + g8;
+            const bool ml = mt0 + u * WM < nmt && m < a.M;
 #pragma unroll
-            for (int u = 0; u < U; ++u) kernel_eval(KIND, r2[u], s2, k[u], gf[u]);
+            for (int kk = 0; kk < KS; ++kk) {
+              const int j = kk * 4 + t4;
+              av[u][kk] = (ml && j < a.D_in) ? a.Zs[(long)m * a.D_in + j] : 0.0;
+            }
+            zzv[u] = ml ? a.zz[m] : 0.0;
+          }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const double kbar = trow[c + u];
-              gb[u] = kbar * gf[u];
-              ds2 = fma(kbar, k[u], ds2);
+          for (int u = 0; u < MB; ++u) {
+            const int mt = mt0 + u * WM;
+            if (mt >= nmt) break;
+            const int m = mt * 8 + g8;
+            const bool ml = m < a.M;
+            double e0[TNG], e1[TNG];
+#pragma unroll
+            for (int nt = 0; nt < TNG; ++nt) { e0[nt] = 0.0; e1[nt] = 0.0; }
+#pragma unroll
+            for (int kk = 0; kk < KS; ++kk)
+#pragma unroll
+              for (int nt = 0; nt < TNG; ++nt) dmma884(e0[nt], e1[nt], av[u][kk], bx[kk][nt]);
+            double ka[TNG], kb[TNG], ga[TNG], gb[TNG];
+#pragma unroll
+            for (int nt = 0; nt < TNG; ++nt) {
+              kernel_eval(KIND, fmax(fma(-2.0, e0[nt], zzv[u] + xx0[nt]), 0.0), s2, ka[nt], ga[nt]);
+              kernel_eval(KIND, fmax(fma(-2.0, e1[nt], zzv[u] + xx1[nt]), 0.0), s2, kb[nt], gb[nt]);
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) trow[c + u] = gb[u];
-#pragma unroll
-            for (int j = 0; j < DMAX; ++j)
-              if (j < a.D_in) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                  const double t = zr[j] - xs[j * GC + c + u];   // recomputed: keeping U x D_in differences live would spill
-                  dl[j] = fma(gb[u] * t, t, dl[j]);
-                }
-              }
+            for (int nt = 0; nt < TNG; ++nt) {
+              double2* tp = reinterpret_cast<double2*>(tile + m * LDT + col0 + nt * 8 + 2 * t4);
+              const double2 kbar = *tp;
+              if (ml) { ds2 = fma(kbar.x, ka[nt], ds2); ds2 = fma(kbar.y, kb[nt], ds2); }
+              *tp = ml ? make_double2(kbar.x * ga[nt], kbar.y * gb[nt]) : make_double2(0.0, 0.0);
+            }
           }
-        };
-        if (a.kind == 0) sweep(std::integral_constant<int, 0>{});
-        else if (a.kind == 1) sweep(std::integral_constant<int, 1>{});
-        else sweep(std::integral_constant<int, 2>{});
-      } else {
-        for (int c = 0; c < GC; ++c) trow[c] = 0.0;
-      }
+        }
+      };
+      if (a.kind == 0) sweep(std::integral_constant<int, 0>{});
+      else if (a.kind == 1) sweep(std::integral_constant<int, 1>{});
+      else sweep(std::integral_constant<int, 2>{});
     }
     PH_ADD(ph_row, ph_e);
     PH_MARK(ph_f);
-    // per-tile, per-group partial sums in a fixed order: warp shuffle tree, then the WM warps through shared memory
-    {
+    group_sync(bar_id, GT);   // Gbar rows of the group's columns are complete
+    // ---- U = Gbar^T [Zs, 1]: one column tile per warp, 8 k-steps per round (their inducing-input loads in flight together),
+    // even / odd k-steps in separate accumulators (a dependent DMMA chain issues every 26 clocks) ----
+    for (int ct = wm; ct < TNG; ct += WM) {
+      double u0[2][NTJ], u1[2][NTJ];
 #pragma unroll
-      for (int j = 0; j < DMAX; ++j)
-        if (j < a.D_in) {
-          const double v = warp_sum(dl[j] * (1.0 / a.ls[j]));
-          if (lane == 0) red[wm * (kMaxD + 1) + j] = v;
+      for (int jt = 0; jt < NTJ; ++jt) { u0[0][jt] = u0[1][jt] = u1[0][jt] = u1[1][jt] = 0.0; }
+      const double* ta = tile + t4 * LDT + col0 + ct * 8 + g8;
+      for (int m0 = 0; m0 < a.Mp; m0 += 32) {
+        double av[8], bz[8][NTJ];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int m = m0 + q * 4 + t4;
+          av[q] = ta[(m0 + q * 4) * LDT];
+#pragma unroll
+          for (int jt = 0; jt < NTJ; ++jt) {
+            const int j = jt * 8 + g8;
+            bz[q][jt] = m < a.M ? (j < a.D_in ? a.Zs[(long)m * a.D_in + j] : (j == a.D_in ? 1.0 : 0.0)) : 0.0;
+          }
         }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+#pragma unroll
+          for (int jt = 0; jt < NTJ; ++jt) dmma884(u0[q & 1][jt], u1[q & 1][jt], av[q], bz[q][jt]);
+      }
+#pragma unroll
+      for (int jt = 0; jt < NTJ; ++jt) {
+        const int j = jt * 8 + 2 * t4, c = ct * 8 + g8;
+        if (j < J) us[c * J + j] = u0[0][jt] + u0[1][jt];
+        if (j + 1 < J) us[c * J + j + 1] = u1[0][jt] + u1[1][jt];
+      }
+    }
+    // ---- S = Gbar [Xs, 1], contracted on the fly with the inducing inputs ----
+    {
+      double bxs[KC][NTJ];
+#pragma unroll
+      for (int kk = 0; kk < KC; ++kk) {
+        const int c = kk * 4 + t4;
+#pragma unroll
+        for (int jt = 0; jt < NTJ; ++jt) {
+          const int j = jt * 8 + g8;
+          bxs[kk][jt] = j < a.D_in ? xs[j * GC + (c ^ (XSW * ((j & 3) << 3)))] : (j == a.D_in ? 1.0 : 0.0);
+        }
+      }
+      const int jt_one = a.D_in >> 3, src = (lane & ~3) | ((a.D_in & 7) >> 1), comp = a.D_in & 1;   // where column D_in (the ones) lands
+      for (int mt0 = wm; mt0 < nmt; mt0 += WM * MB) {
+        double zv[MB][NTJ - 1][2];
+#pragma unroll
+        for (int u = 0; u < MB; ++u) {
+          const int m = (mt0 + u * WM) * 8 + g8;
+          const bool ml = mt0 + u * WM < nmt && m < a.M;
+#pragma unroll
+          for (int jt = 0; jt < NTJ - 1; ++jt) {
+            const int j = jt * 8 + 2 * t4;
+            zv[u][jt][0] = (ml && j < a.D_in) ? a.Zs[(long)m * a.D_in + j] : 0.0;
+            zv[u][jt][1] = (ml && j + 1 < a.D_in) ? a.Zs[(long)m * a.D_in + j + 1] : 0.0;
+          }
+        }
+        double s0[MB][NTJ], s1[MB][NTJ];
+#pragma unroll
+        for (int u = 0; u < MB; ++u)
+#pragma unroll
+          for (int jt = 0; jt < NTJ; ++jt) { s0[u][jt] = 0.0; s1[u][jt] = 0.0; }
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk)
+#pragma unroll
+          for (int u = 0; u < MB; ++u) {
+            const int mt = mt0 + u * WM;
+            const double avv = mt < nmt ? tile[(mt * 8 + g8) * LDT + col0 + kk * 4 + t4] : 0.0;
+#pragma unroll
+            for (int jt = 0; jt < NTJ; ++jt) dmma884(s0[u][jt], s1[u][jt], avv, bxs[kk][jt]);
+          }
+#pragma unroll
+        for (int u = 0; u < MB; ++u) {
+          double cand = 0.0;
+#pragma unroll
+          for (int jt = 0; jt < NTJ; ++jt)
+            if (jt == jt_one) cand = comp ? s1[u][jt] : s0[u][jt];
+          const double S0 = __shfl_sync(0xffffffffu, cand, src);
+#pragma unroll
+          for (int jt = 0; jt < NTJ - 1; ++jt) {
+            dla[jt][0] = fma(zv[u][jt][0], fma(zv[u][jt][0], S0, -2.0 * s0[u][jt]), dla[jt][0]);
+            dla[jt][1] = fma(zv[u][jt][1], fma(zv[u][jt][1], S0, -2.0 * s1[u][jt]), dla[jt][1]);
+          }
+        }
+      }
+    }
+    // per-tile, per-group partial sums in a fixed order: lanes of equal t4 hold the same j's, so a shuffle tree over g8, then the
+    // WM warps through shared memory
+#pragma unroll
+    for (int jt = 0; jt < NTJ - 1; ++jt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        double v = dla[jt][h];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        const int j = jt * 8 + 2 * lane + h;
+        if (lane < 4 && j < a.D_in) red[wm * (kMaxD + 1) + j] = v;
+      }
+    {
       const double v = warp_sum(ds2 / s2);
       if (lane == 0) red[wm * (kMaxD + 1) + a.D_in] = v;
     }
-    group_sync(bar_id, GT);   // Gbar rows of the group's columns are complete; the warps' partial sums are in `red`
+    group_sync(bar_id, GT);   // U and the warps' partial sums are in shared memory
     if (tg <= a.D_in) {
-      double s = 0.0;
+      double sacc = 0.0;
 #pragma unroll
-      for (int w = 0; w < WM; ++w) s += red[w * (kMaxD + 1) + tg];
-      a.part[(tile_index * WN + wn) * (a.D_in + 1) + tg] = s;
+      for (int w = 0; w < WM; ++w) sacc += red[w * (kMaxD + 1) + tg];
+      if (tg < a.D_in) {
+        double s2j = 0.0;
+        const int sw = XSW * ((tg & 3) << 3);
+        for (int c = 0; c < GC; ++c) {
+          const double xv = xs[tg * GC + (c ^ sw)];
+          s2j = fma(xv * xv, us[c * J + a.D_in], s2j);
+        }
+        sacc = (sacc + s2j) * (1.0 / a.ls[tg]);
+      }
+      a.part[(tile_index * WN + wn) * (a.D_in + 1) + tg] = sacc;
     }
     PH_ADD(ph_red, ph_f);
     PH_MARK(ph_g);
@@ -449,69 +572,19 @@ __global__ void __launch_bounds__(384, 1) fused_backward_kernel(FusedBwdArgs a) 
       const int m = idx / (GC / 2), c2 = (idx % (GC / 2)) * 2;
       *reinterpret_cast<double2*>(a.Gbar + (long)m * a.Pp + p0 + c2) = *reinterpret_cast<const double2*>(tile + m * LDT + col0 + c2);
     }
-    // input gradient: dX[p][j] = (1/l_j) sum_m Gbar[m][p] (zs[m][j] - xs[p][j])  (+ mean-function path).
-    // The scaled inducing inputs are staged through shared memory in chunks of kZChunk rows (a per-thread walk over all M rows
-    // would be bound by the L2 latency of its loads); the next chunk's values are in registers while the current one is used.
+    // input gradient: dX[p][j] = (U[c][j] - x_cj T0_c) / l_j  (+ mean-function path)
     if (a.dXin) {
-      constexpr int NO = 4;                         // (column, input dimension) outputs per thread and round
-      const int nout = GC * a.D_in;
-      for (int o0 = 0; o0 < nout; o0 += GT * NO) {
-        double acc[NO];
-#pragma unroll
-        for (int u = 0; u < NO; ++u) acc[u] = 0.0;
-        const int zn = kZChunk * a.D_in;            // doubles per chunk
-        double zpre[(kZChunk * kMaxD / 2 + 63) / 64];   // this thread's share of the next chunk (GT >= 64 threads)
-        auto fetch = [&](int m0) {
-#pragma unroll
-          for (int u = 0; u < (int)(sizeof(zpre) / sizeof(double)); ++u) {
-            const int e = tg + u * GT;
-            zpre[u] = (e < zn && m0 * a.D_in + e < a.M * a.D_in) ? a.Zs[(long)m0 * a.D_in + e] : 0.0;
-          }
-        };
-        fetch(0);
-        for (int m0 = 0; m0 < a.M; m0 += kZChunk) {
-          group_sync(bar_id, GT);                   // the previous chunk has been consumed
-#pragma unroll
-          for (int u = 0; u < (int)(sizeof(zpre) / sizeof(double)); ++u) {
-            const int e = tg + u * GT;
-            if (e < zn) zbuf[e] = zpre[u];
-          }
-          group_sync(bar_id, GT);
-          if (m0 + kZChunk < a.M) fetch(m0 + kZChunk);
-          const int rows = min(kZChunk, a.M - m0);
-#pragma unroll
-          for (int u = 0; u < NO; ++u) {
-            const int o = o0 + tg + u * GT;
-            if (o < nout) {
-              const int c = o % GC, j = o / GC;
-              const double xv = xs[j * GC + c];
-              const double* tc = tile + (size_t)m0 * LDT + col0 + c;
-              double s0 = 0.0, s1 = 0.0;
-              int r = 0;
-              for (; r + 2 <= rows; r += 2) {
-                s0 = fma(tc[r * LDT], zbuf[r * a.D_in + j] - xv, s0);
-                s1 = fma(tc[(r + 1) * LDT], zbuf[(r + 1) * a.D_in + j] - xv, s1);
-              }
-              if (r < rows) s0 = fma(tc[r * LDT], zbuf[r * a.D_in + j] - xv, s0);
-              acc[u] += s0 + s1;
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < NO; ++u) {
-          const int o = o0 + tg + u * GT;
-          if (o < nout) {
-            const int c = o % GC, j = o / GC;
-            const long p = p0 + c;
-            if (p < a.P) {
-              double v = acc[u] * (1.0 / a.ls[j]);
-              const double* gm = a.Gm + p * a.gm_ld;
-              if (a.mean_kind == 1) v += gm[j];
-              else if (a.mean_kind == 2)
-                for (int d = 0; d < a.D_out; ++d) v = fma(gm[d], a.mfW[j * a.D_out + d], v);
-              a.dXin[p * a.D_in + j] = v;
-            }
-          }
+      for (int o = tg; o < GC * a.D_in; o += GT) {
+        const int c = o % GC, j = o / GC;
+        const long p = p0 + c;
+        if (p < a.P) {
+          const double xv = xs[j * GC + (c ^ (XSW * ((j & 3) << 3)))];
+          double v = (us[c * J + j] - xv * us[c * J + a.D_in]) * (1.0 / a.ls[j]);
+          const double* gm = a.Gm + p * a.gm_ld;
+          if (a.mean_kind == 1) v += gm[j];
+          else if (a.mean_kind == 2)
+            for (int d = 0; d < a.D_out; ++d) v = fma(gm[d], a.mfW[j * a.D_out + d], v);
+          a.dXin[p * a.D_in + j] = v;
         }
       }
     }
