@@ -425,13 +425,19 @@ std::vector<PanelDesc> build_schedule(int Mp, int BM, int D_out, bool vform) {
       if ((fl & kPanelLast) && i == 0) fl |= kPanelStageEnd;
       v.push_back(PanelDesc{0, 0, i, ks * kPanelK, fl, 0});
     }
-  for (int pass = vform ? 1 : 0; pass <= D_out; ++pass)
+  // upper-operator passes: A (A-form only), then the T_d passes two outputs at a time (the panels of d and d + 1 for the same row block
+  // and k-range are adjacent: fused_forward_kernel multiplies both with one set of B fragments), a last single pass when D_out is odd
+  auto upper = [&](int kind, int d0, int nd) {
     for (int i = 0; i < nb; ++i)
       for (int ks = i * kpb; ks < kt; ++ks) {
         int fl = (ks == i * kpb ? kPanelFirst : 0) | (ks == kt - 1 ? kPanelLast : 0) | (ks * kPanelK < (i + 1) * BM ? kPanelClip : 0);
         if ((fl & kPanelLast) && i == nb - 1) fl |= kPanelStageEnd;
-        v.push_back(PanelDesc{pass == 0 ? 1 : 2, pass == 0 ? 0 : pass - 1, i, ks * kPanelK, fl, 0});
+        for (int d = d0; d < d0 + nd; ++d) v.push_back(PanelDesc{kind, d, i, ks * kPanelK, fl, 0});
       }
+  };
+  if (!vform) upper(1, 0, 1);
+  for (int dp = 0; dp < D_out / 2; ++dp) upper(2, 2 * dp, 2);
+  if (D_out & 1) upper(2, D_out - 1, 1);
   return v;
 }
 

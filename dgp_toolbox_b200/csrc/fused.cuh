@@ -210,6 +210,46 @@ __device__ __forceinline__ void panel_dispatch(double (&c0)[TM][TN], double (&c1
   if constexpr (TM >= 4) { if (lo == TM - 3) { panel_block<TM - 3, TM, TM, TN, WM, LDT>(c0, c1, pan, bt, wm, g8, t4); return; } }
 }
 
+// Two panels per iteration that multiply the SAME rows of the resident tile: the T_d passes of outputs d and d + 1 (same row
+// block, same k-range, hence the same active m-tile range). One set of B fragments, one descriptor decode, one dispatch and one
+// block end for twice the DMMAs: the per-panel boundary code (~640 clocks per warp, profiles/r02v_fused_fwd_lines.txt) is paid once
+// per pair. Needs a second set of accumulators, which the 232-register consumer budget allows.
+template <int LO, int HI, int TM, int TN, int WM, int LDT>
+__device__ __forceinline__ void panel_block2(double (&a0)[TM][TN], double (&a1)[TM][TN], double (&b0)[TM][TN], double (&b1)[TM][TN],
+                                             const double* __restrict__ panA, const double* __restrict__ panB,
+                                             const double* __restrict__ bt, int wm, int g8, int t4) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    double bv[TN], avA[HI - LO > 0 ? HI - LO : 1], avB[HI - LO > 0 ? HI - LO : 1];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) bv[j] = bt[kk * 4 * LDT + j * 8];
+#pragma unroll
+    for (int i = LO; i < HI; ++i) {
+      const int row = i * 8 * WM + wm * 8 + g8;
+      const int off = row * kPanelK + (((kk ^ (row & 3)) << 2) | t4);
+      avA[i - LO] = panA[off];
+      avB[i - LO] = panB[off];
+    }
+#pragma unroll
+    for (int i = LO; i < HI; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        dmma884(a0[i][j], a1[i][j], avA[i - LO], bv[j]);
+        dmma884(b0[i][j], b1[i][j], avB[i - LO], bv[j]);
+      }
+  }
+}
+
+template <int TM, int TN, int WM, int LDT>
+__device__ __forceinline__ void panel_dispatch2(double (&a0)[TM][TN], double (&a1)[TM][TN], double (&b0)[TM][TN], double (&b1)[TM][TN],
+                                                const double* panA, const double* panB, const double* bt, int wm, int g8, int t4, int hi) {
+  // upper operators only: the active m-tiles are a prefix [0, hi)
+  if (hi == TM) { panel_block2<0, TM, TM, TN, WM, LDT>(a0, a1, b0, b1, panA, panB, bt, wm, g8, t4); return; }
+  if constexpr (TM >= 2) { if (hi == 1) { panel_block2<0, 1, TM, TN, WM, LDT>(a0, a1, b0, b1, panA, panB, bt, wm, g8, t4); return; } }
+  if constexpr (TM >= 3) { if (hi == 2) { panel_block2<0, 2, TM, TN, WM, LDT>(a0, a1, b0, b1, panA, panB, bt, wm, g8, t4); return; } }
+  if constexpr (TM >= 4) { if (hi == 3) { panel_block2<0, 3, TM, TN, WM, LDT>(a0, a1, b0, b1, panA, panB, bt, wm, g8, t4); return; } }
+}
+
 // Thread layout: WM*WN = 8 consumer warps + 1 producer warp. The WN consumer GROUPS (WM warps each) own disjoint column
 // ranges of the tile and run decoupled from each other: they share only the operator-panel ring, which the producer warp
 // fills with one bulk copy per panel (full/empty mbarriers). While one group is in per-panel bookkeeping, block-end
@@ -226,7 +266,7 @@ struct FusedCfg {
   static constexpr int PANEL = BM * kPanelK;
   static constexpr int STAGES = 4;
   static size_t smem_bytes(int Mp, int D_in, int D_out) {
-    return ((size_t)Mp * LDT + (size_t)STAGES * PANEL + (size_t)D_in * PT + (size_t)(1 + D_out) * PT + (size_t)WM * PT + (size_t)D_out * PT + 2 * STAGES + (size_t)(Mp / BM) * (Mp / BM + 1) * (BM / kPanelK)) * sizeof(double);
+    return ((size_t)Mp * LDT + (size_t)STAGES * PANEL + (size_t)D_in * PT + (size_t)(1 + D_out) * PT + (size_t)2 * WM * PT + (size_t)D_out * PT + 2 * STAGES + (size_t)(Mp / BM) * (Mp / BM + 1) * (BM / kPanelK)) * sizeof(double);
   }
 };
 
@@ -240,7 +280,8 @@ __global__ void __launch_bounds__((FusedCfg<BM, PT, WM, WN>::THREADS), (BM == 64
   double* xs_all = tile + (size_t)a.Mp * LDT;            // [WN][D_in][GC]  scaled inputs
   double* colsum_all = xs_all + a.D_in * PT;             // [WN][1 + D_out][GC]: |V|^2, |T_d|^2
   double* part_all = colsum_all + (1 + a.D_out) * PT;    // [WN][WM][GC]
-  double* mean_all = part_all + WM * PT;                 // [WN][GC][D_out]  tile^T * weights (stage 5)
+  double* part2_all = part_all + WM * PT;                // the same for the second output of a pair of T_d passes
+  double* mean_all = part2_all + WM * PT;                // [WN][GC][D_out]  tile^T * weights (stage 5)
   unsigned long long* full = reinterpret_cast<unsigned long long*>(mean_all + a.D_out * PT);   // [STAGES]
   unsigned long long* empty = full + STAGES;                                               // [STAGES]
   // per-panel descriptors of the V pass and of one upper pass (A and every T_d share it), unpacked with a handful of
@@ -286,28 +327,35 @@ __global__ void __launch_bounds__((FusedCfg<BM, PT, WM, WN>::THREADS), (BM == 64
     if (warp > 8) return;
     // ---- producer: one bulk copy per panel, in stream order, round after round ----
     if (lane == 0) {
-      int st = 0, q = 0, pass = 0, qq = 0;
+      int st = 0;
       unsigned ph = 0;
       const double* src = a.stream;
-      const long total = (long)my_tiles * a.NP;
-      for (long n = 0; n < total; ++n) {
-        // Inside a diagonal block only the rows on the operator's side of the diagonal are read by the consumers (a suffix for
-        // the lower operator, a prefix for the upper ones; same rule as their m-tile ranges), and a row range is a byte range
-        // of the packed panel: copy just that. 2/3 of the panels are diagonal-block panels, half of whose rows are dead.
-        const unsigned x = ptab[(pass == 0 ? 0 : NPv) + qq].x;
+      // Inside a diagonal block only the rows on the operator's side of the diagonal are read by the consumers (a suffix for
+      // the lower operator, a prefix for the upper ones; same rule as their m-tile ranges), and a row range is a byte range
+      // of the packed panel: copy just that. 2/3 of the panels are diagonal-block panels, half of whose rows are dead.
+      auto issue = [&](unsigned x, bool lower) {
         int r0 = 0, nr = BM;
         if ((x >> 18) & kPanelClip) {
           const int krel = (int)(x & 0xfff) - (int)((x >> 12) & 63) * BM;
-          if (pass == 0) { r0 = krel; nr = BM - krel; }
+          if (lower) { r0 = krel; nr = BM - krel; }
           else nr = min(BM, krel + kPanelK);
         }
-        if (++qq == (pass == 0 ? NPv : NPa)) { qq = 0; ++pass; if (pass == 1 && a.vform) pass = 2; }
         mbar_wait(empty + st, ph ^ 1);
         mbar_arrive_expect_tx(full + st, (unsigned)(nr * kPanelK * 8));
         bulk_g2s(pbuf + st * PANEL + r0 * kPanelK, src + r0 * kPanelK, (unsigned)(nr * kPanelK * 8), full + st);
         src += PANEL;
-        if (++q == a.NP) { q = 0; src = a.stream; pass = 0; qq = 0; }
         if (++st == STAGES) { st = 0; ph ^= 1; }
+      };
+      const int pairs = a.D_out >> 1;
+      for (int tl = 0; tl < my_tiles; ++tl) {   // same order as build_schedule() on the host
+        src = a.stream;
+        for (int qq = 0; qq < NPv; ++qq) issue(ptab[qq].x, true);
+        if (!a.vform)
+          for (int qq = 0; qq < NPa; ++qq) issue(ptab[NPv + qq].x, false);
+        for (int dp = 0; dp < pairs; ++dp)
+          for (int qq = 0; qq < NPa; ++qq) { issue(ptab[NPv + qq].x, false); issue(ptab[NPv + qq].x, false); }
+        if (a.D_out & 1)
+          for (int qq = 0; qq < NPa; ++qq) issue(ptab[NPv + qq].x, false);
       }
     }
     return;
@@ -325,6 +373,7 @@ __global__ void __launch_bounds__((FusedCfg<BM, PT, WM, WN>::THREADS), (BM == 64
   double* xs = xs_all + wn * a.D_in * GC;
   double* colsum = colsum_all + wn * (1 + a.D_out) * GC;
   double* part = part_all + wn * WM * GC;
+  double* part2 = part2_all + wn * WM * GC;
   double* meanbuf = mean_all + wn * a.D_out * GC;
   const int bar_id = 1 + wn;
   const double s2 = a.var[0];
@@ -334,7 +383,7 @@ __global__ void __launch_bounds__((FusedCfg<BM, PT, WM, WN>::THREADS), (BM == 64
   long long wait_clk = 0;
   const long long t_k0 = clock64();
 #endif
-  for (int idx = tg; idx < WM * GC; idx += GT) part[idx] = 0.0;
+  for (int idx = tg; idx < WM * GC; idx += GT) { part[idx] = 0.0; part2[idx] = 0.0; }
   if (a.group_skew > 0 && wn > 0) {
     const long long t0 = clock64();
     while (clock64() - t0 < (long long)a.group_skew * wn) {}
@@ -483,96 +532,147 @@ __global__ void __launch_bounds__((FusedCfg<BM, PT, WM, WN>::THREADS), (BM == 64
     group_sync(bar_id, GT);
     PH_ADD(ph_kuf, ph_a);
     PH_MARK(ph_b);
-    // ---- stages 2-4: flat loop over the operator panels ----
-    double c0[TM][TN], c1[TM][TN];
-    int pass = 0, qq = 0;   // pass 0: V, 1: A, 2 + d: T_d; qq: panel index inside the pass
-    for (int q = 0; q < a.NP; ++q) {
-      const uint2 tq = ptab[(pass == 0 ? 0 : NPv) + qq];
-      PanelDesc e;
-      e.kind = pass == 0 ? 0 : (pass == 1 ? 1 : 2);
-      e.d = pass - 2;
-      e.k0 = tq.x & 0xfff; e.i = (tq.x >> 12) & 63; e.flags = (tq.x >> 18) & 15;
-      const int imin = (tq.y >> (6 * wm)) & 7, imax = (tq.y >> (6 * wm + 3)) & 7;   // this warp's active m-tiles [imin, imax)
-      if (++qq == (pass == 0 ? NPv : NPa)) { qq = 0; ++pass; if (pass == 1 && a.vform) pass = 2; }
-      if (e.flags & kPanelFirst) {
+    // ---- stages 2-4: the operator panels: V pass, (A pass), then the T_d passes two outputs at a time ----
+    double c0[TM][TN], c1[TM][TN], f0[TM][TN], f1[TM][TN];
+    static_assert(TM <= 4, "panel_dispatch covers TM <= 4");
+    // end of a row block: column sums of squares, in-place update / stash of the block's rows, stage totals
+    auto block_end = [&](double (&x0)[TM][TN], double (&x1)[TM][TN], int kind, int d, int bi, int flags, double* pt, bool totals = true) {
+      PH_MARK(ph_e);
+      if (kind != 1) {   // column sums of squares of V / T_d: reduce over this warp's rows, accumulate in pt[wm][col]
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+          for (int i = 0; i < TM; ++i) { q0 = fma(x0[i][j], x0[i][j], q0); q1 = fma(x1[i][j], x1[i][j], q1); }
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+            q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+            q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+          }
+          if (g8 == 0) {
+            const int col = j * 8 + 2 * t4;
+            pt[wm * GC + col] += q0;
+            pt[wm * GC + col + 1] += q1;
+          }
+        }
+      }
+      if (kind != 2) {   // in-place update of the resident tile (group-local hazard: same columns, all rows)
+        group_sync(bar_id, GT);   // every warp of the group has finished reading the rows this block overwrites
 #pragma unroll
         for (int i = 0; i < TM; ++i)
 #pragma unroll
-          for (int j = 0; j < TN; ++j) { c0[i][j] = 0.0; c1[i][j] = 0.0; }
+          for (int j = 0; j < TN; ++j) {
+            const int row = bi * BM + i * 8 * WM + wm * 8 + g8, col = col0 + j * 8 + 2 * t4;
+            *reinterpret_cast<double2*>(tile + row * LDT + col) = make_double2(x0[i][j], x1[i][j]);
+          }
       }
-      const double* bt = tile + (e.k0 + t4) * LDT + col0 + g8;
-      const double* pan = pbuf + cst * PANEL;
-#ifdef DGP_DEBUG_WAITCLK
-      const long long t_w0 = clock64();
-#endif
-      PH_MARK(ph_w);
-      mbar_wait(full + cst, cph);           // the panel's bytes have landed
-      PH_ADD(ph_wait, ph_w);
-#ifdef DGP_DEBUG_WAITCLK
-      wait_clk += clock64() - t_w0;
-#endif
-      static_assert(TM <= 4, "panel_dispatch covers TM <= 4");
-      panel_dispatch<TM, TN, WM, LDT>(c0, c1, pan, bt, wm, g8, t4, imin, imax);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty + cst);   // this warp is done with the stage
-      if (++cst == STAGES) { cst = 0; cph ^= 1; }
-
-      if (e.flags & kPanelLast) {
-        PH_MARK(ph_e);
-        if (e.kind != 1) {   // column sums of squares of V / T_d: reduce over this warp's rows, accumulate in part[wm][col]
+      // stash of the resident operand the T_d passes read (A, or V in V-form) and of T_d itself
+      double* st = kind == (a.vform ? 0 : 1) ? a.stashA : (kind == 2 && a.stashT ? a.stashT + (long)d * a.Mp * a.Pp : nullptr);
+      if (st) {
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
 #pragma unroll
           for (int j = 0; j < TN; ++j) {
-            double q0 = 0.0, q1 = 0.0;
-#pragma unroll
-            for (int i = 0; i < TM; ++i) { q0 = fma(c0[i][j], c0[i][j], q0); q1 = fma(c1[i][j], c1[i][j], q1); }
-#pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
-              q0 += __shfl_xor_sync(0xffffffffu, q0, o);
-              q1 += __shfl_xor_sync(0xffffffffu, q1, o);
-            }
-            if (g8 == 0) {
-              const int col = j * 8 + 2 * t4;
-              part[wm * GC + col] += q0;
-              part[wm * GC + col + 1] += q1;
-            }
+            const int row = bi * BM + i * 8 * WM + wm * 8 + g8, col = j * 8 + 2 * t4;
+            __stcs(reinterpret_cast<double2*>(st + (long)row * a.Pp + p0 + col), make_double2(x0[i][j], x1[i][j]));   // streaming: read back only by the adjoint
           }
-        }
-        if (e.kind != 2) {   // in-place update of the resident tile (group-local hazard: same columns, all rows)
-          group_sync(bar_id, GT);   // every warp of the group has finished reading the rows this block overwrites
-#pragma unroll
-          for (int i = 0; i < TM; ++i)
-#pragma unroll
-            for (int j = 0; j < TN; ++j) {
-              const int row = e.i * BM + i * 8 * WM + wm * 8 + g8, col = col0 + j * 8 + 2 * t4;
-              *reinterpret_cast<double2*>(tile + row * LDT + col) = make_double2(c0[i][j], c1[i][j]);
-            }
-        }
-        // stash of the resident operand the T_d passes read (A, or V in V-form) and of T_d itself
-        double* st = e.kind == (a.vform ? 0 : 1) ? a.stashA : (e.kind == 2 && a.stashT ? a.stashT + (long)e.d * a.Mp * a.Pp : nullptr);
-        if (st) {
-#pragma unroll
-          for (int i = 0; i < TM; ++i)
-#pragma unroll
-            for (int j = 0; j < TN; ++j) {
-              const int row = e.i * BM + i * 8 * WM + wm * 8 + g8, col = j * 8 + 2 * t4;
-              __stcs(reinterpret_cast<double2*>(st + (long)row * a.Pp + p0 + col), make_double2(c0[i][j], c1[i][j]));   // streaming: read back only by the adjoint
-            }
-        }
-        if (e.kind != 2) group_sync(bar_id, GT);   // the new rows are visible before the next block reads them
-        if ((e.flags & kPanelStageEnd) && e.kind != 1) {
-          // sum the WM per-warp partials in a fixed order, then clear them for the next stage
-          group_sync(bar_id, GT);
-          if (tg < GC) {
-            double s = 0.0;
-#pragma unroll
-            for (int w = 0; w < WM; ++w) { s += part[w * GC + tg]; part[w * GC + tg] = 0.0; }
-            colsum[(e.kind == 0 ? 0 : 1 + e.d) * GC + tg] = s;
-          }
-          group_sync(bar_id, GT);
-        }
-        PH_ADD(ph_end, ph_e);
       }
-    }
+      if (kind != 2) group_sync(bar_id, GT);   // the new rows are visible before the next block reads them
+      if (totals && (flags & kPanelStageEnd) && kind != 1) {
+        // sum the WM per-warp partials in a fixed order, then clear them for the next stage
+        group_sync(bar_id, GT);
+        if (tg < GC) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int w = 0; w < WM; ++w) { sacc += pt[w * GC + tg]; pt[w * GC + tg] = 0.0; }
+          colsum[(kind == 0 ? 0 : 1 + d) * GC + tg] = sacc;
+        }
+        group_sync(bar_id, GT);
+      }
+      PH_ADD(ph_end, ph_e);
+    };
+    // stage totals of a pair of T_d passes under one pair of group barriers
+    auto pair_totals = [&](int d) {
+      PH_MARK(ph_e);
+      group_sync(bar_id, GT);
+      if (tg < GC) {
+        double sa = 0.0, sb = 0.0;
+#pragma unroll
+        for (int w = 0; w < WM; ++w) {
+          sa += part[w * GC + tg]; part[w * GC + tg] = 0.0;
+          sb += part2[w * GC + tg]; part2[w * GC + tg] = 0.0;
+        }
+        colsum[(1 + d) * GC + tg] = sa;
+        colsum[(2 + d) * GC + tg] = sb;
+      }
+      group_sync(bar_id, GT);
+      PH_ADD(ph_end, ph_e);
+    };
+    // one pass of single panels: descriptors ptab[base .. base + count)
+    auto run_single = [&](int kind, int d, int base, int count) {
+      for (int qq = 0; qq < count; ++qq) {
+        const uint2 tq = ptab[base + qq];
+        const int k0 = tq.x & 0xfff, bi = (tq.x >> 12) & 63, flags = (tq.x >> 18) & 15;
+        const int imin = (tq.y >> (6 * wm)) & 7, imax = (tq.y >> (6 * wm + 3)) & 7;   // this warp's active m-tiles [imin, imax)
+        if (flags & kPanelFirst) {
+#pragma unroll
+          for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) { c0[i][j] = 0.0; c1[i][j] = 0.0; }
+        }
+        const double* bt = tile + (k0 + t4) * LDT + col0 + g8;
+        const double* pan = pbuf + cst * PANEL;
+#ifdef DGP_DEBUG_WAITCLK
+        const long long t_w0 = clock64();
+#endif
+        PH_MARK(ph_w);
+        mbar_wait(full + cst, cph);           // the panel's bytes have landed
+        PH_ADD(ph_wait, ph_w);
+#ifdef DGP_DEBUG_WAITCLK
+        wait_clk += clock64() - t_w0;
+#endif
+        panel_dispatch<TM, TN, WM, LDT>(c0, c1, pan, bt, wm, g8, t4, imin, imax);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + cst);   // this warp is done with the stage
+        if (++cst == STAGES) { cst = 0; cph ^= 1; }
+        if (flags & kPanelLast) block_end(c0, c1, kind, d, bi, flags, part);
+      }
+    };
+    // one pass over the upper-operator descriptors with TWO panels per iteration: outputs d and d + 1 (stream order d, d + 1)
+    auto run_pair = [&](int d) {
+      for (int qq = 0; qq < NPa; ++qq) {
+        const uint2 tq = ptab[NPv + qq];
+        const int k0 = tq.x & 0xfff, bi = (tq.x >> 12) & 63, flags = (tq.x >> 18) & 15;
+        const int imax = (tq.y >> (6 * wm + 3)) & 7;
+        if (flags & kPanelFirst) {
+#pragma unroll
+          for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) { c0[i][j] = 0.0; c1[i][j] = 0.0; f0[i][j] = 0.0; f1[i][j] = 0.0; }
+        }
+        const double* bt = tile + (k0 + t4) * LDT + col0 + g8;
+        const int st1 = cst + 1 == STAGES ? 0 : cst + 1;
+        const unsigned ph1 = cst + 1 == STAGES ? cph ^ 1 : cph;
+        PH_MARK(ph_w);
+        mbar_wait(full + cst, cph);
+        mbar_wait(full + st1, ph1);
+        PH_ADD(ph_wait, ph_w);
+        panel_dispatch2<TM, TN, WM, LDT>(c0, c1, f0, f1, pbuf + cst * PANEL, pbuf + st1 * PANEL, bt, wm, g8, t4, imax);
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(empty + cst); mbar_arrive(empty + st1); }
+        cst = st1; cph = ph1;
+        if (++cst == STAGES) { cst = 0; cph ^= 1; }
+        if (flags & kPanelLast) {
+          block_end(c0, c1, 2, d, bi, flags, part, false);
+          block_end(f0, f1, 2, d + 1, bi, flags, part2, false);
+          if (flags & kPanelStageEnd) pair_totals(d);
+        }
+      }
+    };
+    run_single(0, 0, 0, NPv);
+    if (!a.vform) run_single(1, 0, NPv, NPa);
+    for (int dp = 0; dp < (a.D_out >> 1); ++dp) run_pair(2 * dp);
+    if (a.D_out & 1) run_single(2, a.D_out - 1, NPv, NPa);
     PH_ADD(ph_loop, ph_b);
     PH_MARK(ph_c);
     // ---- stage 5: moments, sample, outputs ----
