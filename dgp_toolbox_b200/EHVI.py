@@ -94,6 +94,42 @@ def EHVI(model_Y, Xcand, YND, corr=False, approximation='None', S=1000, zs=None,
     return out
 
 
+def EHVI_with_grad(model_Y, Xcand, YND, S=1000, zs=None, seed=None):
+    """(-EHVI [N, 1], d sum(-EHVI) / dX [N, d]) for `model_Y` = [dgp0, dgp1]: the value and gradient the Adam stage of optimize_EHVI
+    (EHVI.py:218-234) takes with tf.GradientTape. One propagation per model for the moments, dgp_ehvi2d_grad for the criterion and its
+    partial derivatives w.r.t. the four moments, then one adjoint chain per model (dgp_acq_grad kind 4) with the SAME draws."""
+    import ctypes as C
+    if not isinstance(model_Y, list) or len(model_Y) != 2 or any(getattr(m, "name", None) != 'dgp' for m in model_Y):
+        raise NotImplementedError("a list of two DGP models is expected")
+    dev = model_Y[0].device
+    X = model_Y[0]._check_X(_lib.as_device(Xcand, dev))
+    N = X.shape[0]
+    zs = zs or [None, None]
+    seeds = list(seed) if isinstance(seed, (list, tuple)) else [seed, seed]
+    seeds = [model_Y[k]._next_seed(seeds[k]) for k in range(2)]     # fixed here: the adjoint chain must see the draws of the forward
+    mom = [model_Y[k].predict_moments(X, S, add_lik_var=False, zs=zs[k], seed=seeds[k]) for k in range(2)]
+    if any(m.shape[1] != 1 for m, _ in mom):
+        raise ValueError("each objective model must have one output")
+    val = torch.empty((N, 1), dtype=torch.float64, device=dev)
+    dx = torch.zeros_like(X)
+    if N == 0:
+        return val, dx
+    y0 = _lib.as_device(np.asarray(YND[0], dtype=np.float64).reshape(-1), dev)
+    y1 = _lib.as_device(np.asarray(YND[1], dtype=np.float64).reshape(-1), dev)
+    g = torch.empty((N, 4), dtype=torch.float64, device=dev)
+    ctx = _lib.get_context(dev)
+    ctx.call("dgp_ehvi2d_grad", _lib.ptr(mom[0][0]), _lib.ptr(mom[0][1]), _lib.ptr(mom[1][0]), _lib.ptr(mom[1][1]), N, _lib.ptr(y0),
+             _lib.ptr(y1), int(y0.numel()), _lib.ptr(val), _lib.ptr(g))
+    for k in range(2):
+        ext = (-g[:, 2 * k:2 * k + 2]).contiguous()                 # adjoints of -EHVI w.r.t. (mean, var) of objective k
+        dxk = torch.empty_like(X)
+        m, keep = model_Y[k]._model_desc()
+        zt, zp = model_Y[k]._zs(zs[k], S, N)
+        ctx.call("dgp_acq_grad", C.byref(m), 4, _lib.ptr(X), N, S, zp, seeds[k], 0, 0.0, _lib.ptr(ext), _lib.ptr(dxk))
+        dx += dxk
+    return -val, dx
+
+
 def EI_and_EHVI(model_Y, Xcand, YND, y_min, S=1000, zs=None, seed=None):
     """-EI of objective 0 (EI.run analytic, Infill_criteria.py:36-47) and the exact EHVI of both objectives (EHVI.py:107-157) for the
     same candidates from ONE propagation per model: both criteria moment-match the same predict_f samples of model 0, so a
@@ -125,23 +161,37 @@ def optimize_EHVI(model, YND, popsize_DE=300, popstd_DE=1.5, iterations_DE=400, 
     (:217-218), (ii) MINIMISES the positive EHVI (:212), (iii) reads the input dimension from the MO-DGP object (`model._X`, :210) and
     (iv) discards the DE result before the Adam stage (`x_opt = np.array([[0]])`, :221). Implemented here is the evident intent:
     differential evolution (rand/1/bin, TFP defaults) on u with x = lw + (up - lw) / (1 + exp(u)) minimising -EHVI, every
-    generation one EHVI evaluation of the whole population on the device. Returns x_opt [d, 1] like the reference."""
+    generation one EHVI evaluation of the whole population on the device; then (method 'Adam' / 'DE+Adam') Keras Adam on u started
+    from the DE result (or `init_adam`, or zeros as in the reference), with the gradient of -EHVI w.r.t. the candidate from EHVI_with_grad
+    (fresh draws every step, like the reference's loss). Returns x_opt [d, 1] like the reference."""
     from . import search
     if not isinstance(model, list) or len(model) != 2:
         raise NotImplementedError("optimize_EHVI is implemented for a list of two DGP models (the MO-DGP object is SURVEY §8 f2)")
-    if method != 'DE':
-        raise NotImplementedError("the Adam stage needs d EHVI / d x, which this path does not provide yet; use method='DE'")
+    if method not in ('DE', 'Adam', 'DE+Adam'):
+        raise ValueError(f"unknown method {method!r}")
+    if corr or approximation != 'None':
+        raise NotImplementedError("only the exact uncorrelated EHVI is on the accelerated path")
     d = model[0].layers[0].feature.Z.shape[1]
     lw = np.broadcast_to(np.asarray(bounds[0], dtype=np.float64).reshape(-1), (d,)).copy()
     up = np.broadcast_to(np.asarray(bounds[1], dtype=np.float64).reshape(-1), (d,)).copy()
     dev = model[0].device
-    with search.GraphScope(dev):
-        def objective(X, out):
-            v = -EHVI(model, X, YND, corr=corr, approximation=approximation, S=S)
-            if out is None:
-                return v.contiguous()
-            out.copy_(v)
-            return out
-        res = search.de_minimize(objective, lw, up, d, dev, popsize_DE, popstd_DE, iterations_DE, seed=model[0]._next_seed(seed))
+    x_opt = None
+    if method in ('DE', 'DE+Adam'):
+        with search.GraphScope(dev):
+            def objective(X, out):
+                v = -EHVI(model, X, YND, corr=corr, approximation=approximation, S=S)
+                if out is None:
+                    return v.contiguous()
+                out.copy_(v)
+                return out
+            res = search.de_minimize(objective, lw, up, d, dev, popsize_DE, popstd_DE, iterations_DE, seed=model[0]._next_seed(seed))
+        x_opt = res["x"].cpu().numpy().reshape(d)
+    if method in ('Adam', 'DE+Adam'):
+        if init_adam is None:
+            init_adam = np.zeros(d) if x_opt is None else x_opt     # the reference's default start ([0.] * d, EHVI.py:222)
+        init_adam = np.asarray(init_adam, dtype=np.float64).reshape(d)
+        u0 = _lib.as_device(np.log((up - init_adam + 1e-3) / (init_adam - lw + 1e-3)).reshape(1, d), dev)
+        _, X, _ = search.adam_box_minimize(lambda X: EHVI_with_grad(model, X, YND, S=S), lw, up, u0, iterations_adam, lr=lr_adam)
+        x_opt = X.cpu().numpy().reshape(d)
     _lib.get_context(dev).check()
-    return res["x"].cpu().numpy().reshape(d, 1)
+    return x_opt.reshape(d, 1)

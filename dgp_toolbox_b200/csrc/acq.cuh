@@ -67,8 +67,11 @@ __global__ void ei_upstream_kernel(const double* __restrict__ Fmean, const doubl
       sq += v + m * m;
     }
     const double mbar = sm / (double)S, vbar = sq / (double)S - mbar * mbar + (lik_var ? lik_var[0] : 0.0), sig = sqrt(vbar);
-    double val, dm, dv;
-    if (kind == 2) {
+    double val = 0.0, dm, dv;
+    if (kind == 4) {   // adjoints supplied by the caller (neg_ei holds (dc/dmbar, dc/dvbar) per candidate and output, read only)
+      dm = neg_ei[(n * D + d) * 2];
+      dv = neg_ei[(n * D + d) * 2 + 1];
+    } else if (kind == 2) {
       const double t = (mbar - y_min) / sig, cdf = norm_cdf(t), pdf = norm_pdf(t);
       val = (mbar - y_min) * cdf + vbar * (pdf / sig);
       dm = cdf;
@@ -92,7 +95,7 @@ __global__ void ei_upstream_kernel(const double* __restrict__ Fmean, const doubl
         dv = dv * ssum;
       }
     }
-    if (kind != 3) neg_ei[n * D + d] = val;
+    if (kind != 3 && kind != 4) neg_ei[n * D + d] = val;
     const double gv = dv / (double)S;
     for (long s = 0; s < S; ++s) {
       const long p = s * Nc + n;
@@ -193,6 +196,53 @@ __global__ void ehvi2d_kernel(const double* __restrict__ m0, const double* __res
     t2 += (psi_fn(y0[i - 1], y0[i - 1], mu0, s0) - psi_fn(y0[i - 1], y0[i], mu0, s0)) * d1;
   }
   out[c] = t1 + t2;
+}
+
+// d psi / d mu and d psi / d sigma of psi(a, b, mu, sigma) = sigma phi(u) + (a - mu) Phi(u), u = (b - mu) / sigma
+__device__ __forceinline__ void psi_grad(double a, double b, double mu, double sigma, double& val, double& dmu, double& dsig) {
+  const double u = (b - mu) / sigma, pdf = norm_pdf(u), cdf = norm_cdf(u), q = (a - mu) * pdf / sigma;
+  val = sigma * pdf + (a - mu) * cdf;
+  dmu = u * pdf - cdf - q;
+  dsig = pdf * (1.0 + u * u) - q * u;
+}
+
+// ehvi2d_kernel with its partial derivatives w.r.t. the four moments: grads[c] = (dE/dm0, dE/dv0, dE/dm1, dE/dv1)
+// (the Adam stage of optimize_EHVI, EHVI.py:218-234, differentiates the criterion w.r.t. the candidate through them).
+__global__ void ehvi2d_grad_kernel(const double* __restrict__ m0, const double* __restrict__ v0, const double* __restrict__ m1,
+                                   const double* __restrict__ v1, long N, const double* __restrict__ ynd0,
+                                   const double* __restrict__ ynd1, int n, double* __restrict__ out, double* __restrict__ grads) {
+  extern __shared__ double sh[];
+  double* y0 = sh;
+  double* y1 = sh + n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { y0[i] = ynd0[i]; y1[i] = ynd1[i]; }
+  __syncthreads();
+  long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  const double mu0 = m0[c], s0 = sqrt(v0[c]), mu1 = m1[c], s1 = sqrt(v1[c]);
+  const double ul = (y0[n - 1] - mu0) / s0, cdf_last = norm_cdf(ul), pdf_last = norm_pdf(ul);
+  double e = 0.0, gm0 = 0.0, gs0 = 0.0, gm1 = 0.0, gs1 = 0.0;
+  for (int i = 1; i < n; ++i) {
+    double pa, pam, pas, pb, pbm, pbs;
+    psi_grad(y1[i], y1[i], mu1, s1, pa, pam, pas);
+    psi_grad(y1[i], y1[0], mu1, s1, pb, pbm, pbs);
+    const double d1 = pa - pb, d1m = pam - pbm, d1s = pas - pbs;
+    double f = 0.0, fm = 0.0, fs = 0.0;   // the objective-0 factor of the strip and its derivatives
+    if (i < n - 1) {
+      const double w = y0[i - 1] - y0[i], u = (y0[i] - mu0) / s0, pdf = norm_pdf(u);
+      f += w * (norm_cdf(u) - cdf_last);
+      fm += w * (-pdf + pdf_last) / s0;
+      fs += w * (-u * pdf + ul * pdf_last) / s0;
+    }
+    psi_grad(y0[i - 1], y0[i - 1], mu0, s0, pa, pam, pas);
+    psi_grad(y0[i - 1], y0[i], mu0, s0, pb, pbm, pbs);
+    f += pa - pb; fm += pam - pbm; fs += pas - pbs;
+    e += f * d1;
+    gm0 += fm * d1; gs0 += fs * d1;
+    gm1 += f * d1m; gs1 += f * d1s;
+  }
+  out[c] = e;
+  grads[4 * c + 0] = gm0; grads[4 * c + 1] = gs0 / (2.0 * s0);
+  grads[4 * c + 2] = gm1; grads[4 * c + 3] = gs1 / (2.0 * s1);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -1173,7 +1173,7 @@ int run_model(dgp_ctx* c, const dgp_model_desc* model, const double* X, long N, 
       CK(cudaMemsetAsync(up.GmPad, 0, (size_t)Pp * 32 * sizeof(double), c->stream));
       CK(cudaMemsetAsync(up.gq, 0, (size_t)Pp * sizeof(double), c->stream));
       const int D0x = model->layers[0].D_in;
-      const long vstride = o.acq_kind == 3 ? D0x : DL;   // WB2S returns one value per input column
+      const long vstride = o.acq_kind == 3 ? D0x : (o.acq_kind == 4 ? 2 * DL : DL);   // WB2S: one value per input column; 4: (dm, dv) pairs
       LAUNCH(ei_upstream_kernel, (unsigned)((Nc + 127) / 128), 128, 0, clL.Fmean, clL.Fvar, Nc, S, Pp, DL, o.y_min, o.ei + n0 * vstride,
              up.Gm, up.GvT, up.GmPad, up.gq, o.acq_kind, o.acq_add_lik ? model->lik_variance : nullptr, X + n0 * D0x, D0x, acq_direct);
       up.part = lik_part; up.nblocks = nb;
@@ -2296,12 +2296,13 @@ int dgp_ei_grad(dgp_ctx* c, const dgp_model_desc* model, const double* X, int64_
 
 int dgp_acq_grad(dgp_ctx* c, const dgp_model_desc* model, int kind, const double* X, int64_t N, int64_t S,
                  const double* const* zs_host, uint64_t seed, int64_t n_offset, double y, double* value, double* d_value_dX) {
-  if (!c || !model || !X || !value || !d_value_dX || kind < 0 || kind > 3) return DGP_ERR_ARG;
-  if (kind > 0 && !model->lik_variance) { c->err = "lik_variance is null"; return DGP_ERR_ARG; }
+  if (!c || !model || !X || !value || !d_value_dX || kind < 0 || kind > 4) return DGP_ERR_ARG;
+  const bool add_lik = kind == 4 ? y != 0.0 : kind > 0;
+  if (add_lik && !model->lik_variance) { c->err = "lik_variance is null"; return DGP_ERR_ARG; }
   if (kind == 3 && model->layers[model->num_layers - 1].D_out != 1) { c->err = "WB2S expects a single-output model"; return DGP_ERR_ARG; }
   RunOpts o;
   o.io.zs = zs_host; o.ei = value; o.y_min = y; o.ei_analytic = 1; o.dx = d_value_dX;
-  o.acq_kind = kind; o.acq_add_lik = kind > 0 ? 1 : 0;
+  o.acq_kind = kind; o.acq_add_lik = add_lik ? 1 : 0;
   return run_model_planned(c, model, X, N, S, seed, n_offset, o);
 }
 
@@ -2364,6 +2365,15 @@ int dgp_ehvi2d(dgp_ctx* c, const double* m0, const double* v0, const double* m1,
   if (!c || !m0 || !v0 || !m1 || !v1 || !ynd0 || !ynd1 || !out || N < 1 || n < 2 || n > 2048) return DGP_ERR_ARG;
   CK(cudaSetDevice(c->device));
   LAUNCH(ehvi2d_kernel, (unsigned)((N + 127) / 128), 128, 2 * (size_t)n * sizeof(double), m0, v0, m1, v1, (long)N, ynd0, ynd1, n, out);
+  return DGP_OK;
+}
+
+int dgp_ehvi2d_grad(dgp_ctx* c, const double* m0, const double* v0, const double* m1, const double* v1, int64_t N, const double* ynd0,
+                    const double* ynd1, int n, double* out, double* grads) {
+  if (!c || !m0 || !v0 || !m1 || !v1 || !ynd0 || !ynd1 || !out || !grads || N < 1 || n < 2 || n > 2048) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  LAUNCH(ehvi2d_grad_kernel, (unsigned)((N + 127) / 128), 128, 2 * (size_t)n * sizeof(double), m0, v0, m1, v1, (long)N, ynd0, ynd1, n, out,
+         grads);
   return DGP_OK;
 }
 

@@ -250,7 +250,10 @@ int dgp_train_nat_adam(dgp_ctx* ctx, const dgp_model_desc* model, const double* 
  * Infill_criteria.py:79-84,160-165): kind 0 = -EI on predict_f moments (== dgp_ei_grad), 1 = WB2 = -(EI - mean) and 2 = EV =
  * (mean - y) Phi + s phi, both on predict_y moments (+ sigma_n^2, Infill_criteria.py:124-133,249-257), 3 = WB2S = -(sigmoid(x_j) EI -
  * mean) per input column j (Infill_criteria.py:187-198; single-output model; value [N, D0]). value [N, D_L] otherwise,
- * d_value_dX [N, D0] = d sum(value) / dX. The adjoint chain runs without the parameter contractions. */
+ * d_value_dX [N, D0] = d sum(value) / dX. The adjoint chain runs without the parameter contractions.
+ * kind 4 = adjoints supplied by the caller: `value` is an INPUT [N, D_L, 2] holding (dc/dmean, dc/dvar) of some criterion c w.r.t. the
+ * mixture moments (y != 0: predict_y moments, y == 0: predict_f moments); d_value_dX = dc/dX. The same seed as the call that produced
+ * the moments gives the same draws (EHVI: dgp_ehvi2d_grad, one kind-4 call per objective model). */
 int dgp_acq_grad(dgp_ctx* ctx, const dgp_model_desc* model, int kind, const double* X, int64_t N, int64_t S,
                  const double* const* zs_host, uint64_t seed, int64_t n_offset, double y, double* value, double* d_value_dX);
 
@@ -318,6 +321,11 @@ int dgp_ev_mc(dgp_ctx* ctx, const double* F, int64_t S, int64_t ND, double zero_
  * Pareto front (EHVI.py:90-100), n entries each, DEVICE pointers. */
 int dgp_ehvi2d(dgp_ctx* ctx, const double* m0, const double* v0, const double* m1, const double* v1, int64_t N,
                const double* ynd0, const double* ynd1, int n, double* out);
+/* dgp_ehvi2d with its partial derivatives: grads [N][4] = (dE/dm0, dE/dv0, dE/dm1, dE/dv1). Chained to the candidates with
+ * dgp_acq_grad kind 4 (one call per objective model), this is the gradient the Adam stage of optimize_EHVI takes with
+ * tf.GradientTape (dgp_dace/EHVI.py:218-234). */
+int dgp_ehvi2d_grad(dgp_ctx* ctx, const double* m0, const double* v0, const double* m1, const double* v1, int64_t N,
+                    const double* ynd0, const double* ynd1, int n, double* out, double* grads);
 
 /* Debug / test hook for the DMMA GEMM engine: C = alpha * A * op(B) + beta * C (row-major, tile-aligned shapes). */
 int dgp_debug_gemm(dgp_ctx* ctx, int nt, int M, int N, int K, double alpha, const double* A, const double* B, double beta,

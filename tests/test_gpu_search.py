@@ -234,3 +234,47 @@ def test_wb2s_pof_and_ehvi_searches_run():
     g = D.EHVI([model, obj2], grid, ynd, S=256, seed=[9, 10]).cpu().numpy().reshape(-1)
     at = float(D.EHVI([model, obj2], x3.reshape(1, 1), ynd, S=256, seed=[9, 10]))
     assert x3.shape == (1, 1) and -1.0 <= x3.item() <= 1.0 and at >= 0.7 * g.max()
+
+
+def test_ehvi_gradient_and_adam_stage():
+    """dgp_ehvi2d_grad (value + partial derivatives w.r.t. the four moments) and EHVI_with_grad (the gradient w.r.t. the candidates
+    through both models' adjoint chains, dgp_acq_grad kind 4) against autograd through the oracle; optimize_EHVI('DE+Adam') and
+    ('Adam') run the stage the reference takes with tf.GradientTape (EHVI.py:218-234)."""
+    import dgp_toolbox_b200 as D
+    prob, om, pm = both_models(3, [3], 20, 15, 6)
+    prob2, om2, pm2 = both_models(3, [3], 20, 15, 6, seed_shift=40)
+    S, N = 6, 15
+    zs = [[torch.as_tensor(O.philox_normal(8 + k, l, S, N, layer.D_out)) for l, layer in enumerate(m.layers)] for k, m in enumerate((om, om2))]
+    y0 = np.linspace(-0.9, 0.7, 6)
+    ynd = D.Y_ND([y0[:, None], (0.8 - y0)[:, None]], list(np.argsort(-y0)), nadir=[1.6, 1.6], ideal=[-1.6, -1.6])
+    X = torch.as_tensor(prob["X"]).clone().requires_grad_(True)
+    mom = [O.mixture_moments(*O.predict_f(m, X, S, z)) for m, z in zip((om, om2), zs)]
+    y0t, y1t = [torch.as_tensor(np.asarray(a, dtype=np.float64).reshape(-1)) for a in (ynd[0], ynd[1])]
+    e_o = O.ehvi_exact(mom[0][0], mom[0][1], mom[1][0], mom[1][1], y0t, y1t)
+    (-e_o).sum().backward()
+    val, dx = D.EHVI_with_grad([pm, pm2], prob["X"], ynd, S=S, seed=[8, 9])
+    assert tuple(val.shape) == (N, 1) and rel_err(val, -e_o.detach()) < 1e-8
+    assert rel_err(dx, X.grad) < 1e-7, rel_err(dx, X.grad)
+    assert rel_err(D.EHVI([pm, pm2], prob["X"], ynd, S=S, seed=[8, 9]), e_o.detach()) < 1e-8
+    # the moment partials alone
+    mm = [t.detach().clone().requires_grad_(True) for t in (mom[0][0], mom[0][1], mom[1][0], mom[1][1])]
+    O.ehvi_exact(*mm, y0t, y1t).sum().backward()
+    ctx = D._lib.get_context(0)
+    dv = [D._lib.as_device(t.detach().numpy()) for t in mm]
+    out = torch.empty((N, 1), dtype=torch.float64, device="cuda")
+    g = torch.empty((N, 4), dtype=torch.float64, device="cuda")
+    y0d, y1d = D._lib.as_device(y0t.numpy()), D._lib.as_device(y1t.numpy())   # named: the pointers must outlive the call
+    ctx.call("dgp_ehvi2d_grad", *[D._lib.ptr(t) for t in dv], N, D._lib.ptr(y0d), D._lib.ptr(y1d), int(y0t.numel()), D._lib.ptr(out),
+             D._lib.ptr(g))
+    torch.cuda.synchronize()
+    g_o = torch.cat([t.grad for t in mm], 1)
+    assert rel_err(g, g_o) < 1e-9
+    # the search stages
+    box = (np.full(3, -1.0), np.full(3, 1.0))
+    base = float(D.EHVI([pm, pm2], np.zeros((1, 3)), ynd, S=64, seed=[3, 4]))
+    for method in ("Adam", "DE+Adam"):
+        x = D.optimize_EHVI([pm, pm2], ynd, popsize_DE=12, iterations_DE=4, iterations_adam=15, lr_adam=0.05, method=method, S=16, seed=5,
+                            bounds=box, init_adam=np.zeros(3) if method == "Adam" else None)
+        assert x.shape == (3, 1) and np.all(x >= -1.0) and np.all(x <= 1.0)
+        if method == "Adam":   # 15 Adam steps from the origin do not make the criterion worse (up to Monte-Carlo noise)
+            assert float(D.EHVI([pm, pm2], x.reshape(1, 3), ynd, S=64, seed=[3, 4])) >= base - 0.1 * abs(base) - 1e-6
