@@ -53,7 +53,9 @@ struct GemmCfg {
 
 __device__ __forceinline__ bool gemm_tri_skip_enabled() { return true; }
 
-template <int BM, int BN, int BK, int WM, int WN, bool NT, int STAGES>
+// TSEL (lower-only products): 0 = every tile, 1 = strictly-lower tiles only and the diagonal-tile code compiled out (124 instead of
+// 204 registers, so three CTAs fit an SM with a 2-stage ring), 2 = diagonal tiles only.
+template <int BM, int BN, int BK, int WM, int WN, bool NT, int STAGES, int TSEL = 0>
 __global__ void __launch_bounds__(WM* WN * 32) gemm_kernel(GemmArgs g) {
   using Cfg = GemmCfg<BM, BN, BK, WM, WN, NT, STAGES>;
   constexpr int THREADS = Cfg::THREADS, TM = Cfg::TM, TN = Cfg::TN, LDA = Cfg::LDA, LDB = Cfg::LDB;
@@ -79,6 +81,8 @@ __global__ void __launch_bounds__(WM* WN * 32) gemm_kernel(GemmArgs g) {
   const int split = (int)bid;
   const int m0 = mt * BM, n0 = nt * BN;
   if (g.c_lower && n0 >= m0 + BM) return;
+  if (TSEL == 1 && n0 == m0) return;
+  if (TSEL == 2 && n0 != m0) return;
 
   // split-K: chunks of whole k-tiles, the last one may be shorter (any split count works, so the launcher can pick the
   // count that fills whole waves of CTAs)
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(WM* WN * 32) gemm_kernel(GemmArgs g) {
   // would leave one warp idle and two half-used while the CTA still takes the full time, so instead every warp computes ALL
   // 36 units for a quarter of each k-tile's k-steps; the four partial sums are added through shared memory at the end.
   // The CTA then takes 36/64 of the time of an off-diagonal tile.
-  if constexpr (NT && BM == 64 && BN == 64 && BK == 32 && WM * WN == 4) {
+  if constexpr (TSEL != 1 && NT && BM == 64 && BN == 64 && BK == 32 && WM * WN == 4) {
     if (g.c_lower && n0 == m0 && g.a_tri == 0 && g.kblocks <= 1) {
       const int w = tid >> 5;
       double d0[8][8], d1[8][8];
@@ -340,10 +344,10 @@ __global__ void gemm_splitk_reduce(GemmArgs g, int BM, int BN) {
   }
 }
 
-template <int BM, int BN, int BK, int WM, int WN, bool NT, int STAGES>
-inline cudaError_t gemm_launch_cfg(const GemmArgs& g, cudaStream_t st) {
+template <int BM, int BN, int BK, int WM, int WN, bool NT, int STAGES, int TSEL = 0>
+inline cudaError_t gemm_launch_cfg(const GemmArgs& g, cudaStream_t st, bool reduce = true) {
   using Cfg = GemmCfg<BM, BN, BK, WM, WN, NT, STAGES>;
-  auto kern = gemm_kernel<BM, BN, BK, WM, WN, NT, STAGES>;
+  auto kern = gemm_kernel<BM, BN, BK, WM, WN, NT, STAGES, TSEL>;
   static bool configured[64] = {false};   // the opt-in shared-memory size is a per-device function attribute
   int dev = 0;
   cudaGetDevice(&dev);
@@ -356,7 +360,7 @@ inline cudaError_t gemm_launch_cfg(const GemmArgs& g, cudaStream_t st) {
   kern<<<(unsigned)blocks, Cfg::THREADS, Cfg::SMEM, st>>>(g);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (g.splitk > 1) {
+  if (g.splitk > 1 && reduce) {
     long total = (long)g.batch * g.M * g.N;
     int rb = (int)((total + 255) / 256);
     if (rb > 148 * 8) rb = 148 * 8;
@@ -369,12 +373,12 @@ inline cudaError_t gemm_launch_cfg(const GemmArgs& g, cudaStream_t st) {
 // Tile shape the launcher will use and how many CTAs of it fit on the device at once (for wave-aware split-K choices).
 struct GemmPlan { int BM, BN; long tiles; int slots; };
 
-template <int BM, int BN, int BK, int WM, int WN, bool NT, int STAGES>
+template <int BM, int BN, int BK, int WM, int WN, bool NT, int STAGES, int TSEL = 0>
 inline int gemm_ctas_per_sm() {
   using Cfg = GemmCfg<BM, BN, BK, WM, WN, NT, STAGES>;
   static int cached = 0;
   if (!cached) {
-    auto kern = gemm_kernel<BM, BN, BK, WM, WN, NT, STAGES>;
+    auto kern = gemm_kernel<BM, BN, BK, WM, WN, NT, STAGES, TSEL>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     int n = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, Cfg::THREADS, Cfg::SMEM) != cudaSuccess || n < 1) n = 1;
@@ -392,6 +396,13 @@ inline bool gemm_small_bk32(const GemmArgs& g, bool nt) {
   if (g.kblocks > 1 && g.kblk % 32) return false;
   if (g.splitk > 1 && ((g.K / 32 + g.splitk - 1) / g.splitk) < 1) return false;
   return true;
+}
+
+// lower-only contraction over the point-samples on 64 x 64 x 32 tiles: strictly-lower and diagonal tiles as two launches (TSEL)
+inline bool gemm_split_diag(const GemmArgs& g, bool nt) {
+  static const bool enabled = getenv("DGP_B200_GEMM_ONE_LAUNCH") == nullptr;
+  return enabled && nt && g.c_lower && g.a_tri == 0 && g.kblocks <= 1 && g.M == g.N && g.M > 64 && g.K % 32 == 0 &&
+         !((g.M % 128 == 0) && (g.N % 128 == 0) && ((long)g.M * g.N * g.batch >= 128L * 128 * 64));
 }
 
 inline bool gemm_uses_big_tiles(const GemmArgs& g) {
@@ -418,6 +429,10 @@ inline GemmPlan gemm_plan(const GemmArgs& g, bool nt, int num_sms) {
       for (long j = 0; j < ntl; ++j)
         if (j * p.BN < i * p.BM + p.BM) ++tiles;
   }
+  if (p.BM == 64 && gemm_small_bk32(g, nt) && gemm_split_diag(g, nt)) {   // the wave that matters is the strictly-lower launch
+    per_sm = gemm_ctas_per_sm<64, 64, 32, 2, 2, true, 2, 1>();
+    tiles -= mt;
+  }
   p.tiles = tiles * g.batch;
   p.slots = per_sm * num_sms;
   return p;
@@ -433,7 +448,15 @@ inline cudaError_t gemm_launch(const GemmArgs& g, bool nt, cudaStream_t st) {
   if (gemm_uses_big_tiles(g)) {
     return nt ? gemm_launch_cfg<128, 128, 16, 4, 4, true, 3>(g, st) : gemm_launch_cfg<128, 128, 16, 4, 4, false, 3>(g, st);
   }
-  if (gemm_small_bk32(g, nt)) return nt ? gemm_launch_cfg<64, 64, 32, 2, 2, true, 3>(g, st) : gemm_launch_cfg<64, 64, 32, 2, 2, false, 3>(g, st);
+  if (gemm_small_bk32(g, nt)) {
+    // lower-only contraction over the point-samples: the strictly-lower tiles and the diagonal tiles as two launches (see TSEL)
+    if (gemm_split_diag(g, nt)) {
+      cudaError_t e = gemm_launch_cfg<64, 64, 32, 2, 2, true, 2, 1>(g, st, false);
+      if (e != cudaSuccess) return e;
+      return gemm_launch_cfg<64, 64, 32, 2, 2, true, 3, 2>(g, st, true);
+    }
+    return nt ? gemm_launch_cfg<64, 64, 32, 2, 2, true, 3>(g, st) : gemm_launch_cfg<64, 64, 32, 2, 2, false, 3>(g, st);
+  }
   return nt ? gemm_launch_cfg<64, 64, 16, 2, 2, true, 3>(g, st) : gemm_launch_cfg<64, 64, 16, 2, 2, false, 3>(g, st);
 }
 
