@@ -13,7 +13,7 @@ for k in fused_forward fused_backward; do
       python bench.py --steps 1 --warmup 0 --no-extras --no-cpu-baseline > gpurun_out/${tag}_ncu_$k.log 2>&1
 done
 # parameter contraction: the batched lower-only NT product of the first full-size layer (grid > 1000)
-ncu --set full --import-source on --clock-control none -k regex:gemm_kernel -c 40 -f -o /tmp/${tag}_gemm \
+ncu --set full --import-source on --clock-control none -k regex:gemm_kernel -c 90 -f -o /tmp/${tag}_gemm \
     python bench.py --steps 1 --warmup 0 --no-extras --no-cpu-baseline > gpurun_out/${tag}_ncu_gemm.log 2>&1
 python tools/ncu_summary.py raw /tmp/${tag}_fused_forward.ncu-rep gpurun_out/${tag}_fused_fwd_ncu.txt > /dev/null
 python tools/ncu_summary.py raw /tmp/${tag}_fused_backward.ncu-rep gpurun_out/${tag}_fused_bwd_ncu.txt > /dev/null
