@@ -69,19 +69,50 @@ def psi(a, b, mu, sigma):
     return sigma * pdf + (a - mu) * cdf
 
 
+def _is_mo(model_Y):
+    return not isinstance(model_Y, list) and getattr(model_Y, "name", None) == 'mo_dgp'
+
+
+def _mo_ehvi_with_grad(model_Y, Xcand, YND, S):
+    """EHVI_with_grad for the multi-objective object: the chain is differentiated by torch.autograd through the library's layer /
+    kernel adjoints (models/MO_DGP.py), the criterion's partial derivatives w.r.t. the four moments come from dgp_ehvi2d_grad."""
+    m = model_Y.model
+    dev = m.device
+    X = _lib.as_device(Xcand, dev).detach().clone().requires_grad_(True)
+    N = X.shape[0]
+    _, Fmeans, Fvars = m.propagate(X, S=S)
+    mom = []
+    for o in (-2, -1):     # EHVI.py:126-130
+        mu = Fmeans[o].mean(0).reshape(-1)
+        mom += [mu, (Fvars[o] + Fmeans[o] ** 2).mean(0).reshape(-1) - mu ** 2]
+    val = torch.empty((N, 1), dtype=torch.float64, device=dev)
+    g = torch.empty((N, 4), dtype=torch.float64, device=dev)
+    y0 = _lib.as_device(np.asarray(YND[0], dtype=np.float64).reshape(-1), dev)
+    y1 = _lib.as_device(np.asarray(YND[1], dtype=np.float64).reshape(-1), dev)
+    d = [t.detach().contiguous() for t in mom]
+    _lib.get_context(dev).call("dgp_ehvi2d_grad", _lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), _lib.ptr(d[3]), N, _lib.ptr(y0),
+                               _lib.ptr(y1), int(y0.numel()), _lib.ptr(val), _lib.ptr(g))
+    dx, = torch.autograd.grad(mom, X, grad_outputs=[-g[:, k].contiguous() for k in range(4)])
+    return -val, dx
+
+
 def EHVI(model_Y, Xcand, YND, corr=False, approximation='None', S=1000, zs=None, seed=None):
-    """EHVI.py:107-157 for `model_Y` = [dgp0, dgp1], approximation='None', corr=False -> [N, 1]."""
-    if not isinstance(model_Y, list) or len(model_Y) != 2 or any(getattr(m, "name", None) != 'dgp' for m in model_Y):
-        raise NotImplementedError("only a list of two DGP models is on the accelerated path (SURVEY §8 a12)")
+    """EHVI.py:107-157, approximation='None', corr=False -> [N, 1], for `model_Y` = [dgp0, dgp1] (:110-119) or a multi-objective
+    DGP object (`name == 'mo_dgp'`, :124-130: both objectives' moments from ONE chain of `model_Y.model`)."""
     if approximation != 'None' or corr:
         raise NotImplementedError("only the exact uncorrelated EHVI is on the accelerated path")
-    zs = zs or [None, None]
-    seeds = seed if isinstance(seed, (list, tuple)) else [seed, seed]
-    # moment matching over the S propagated samples (EHVI.py:112-119), predict_f moments (no likelihood variance)
-    m0, v0 = model_Y[0].predict_moments(Xcand, S, add_lik_var=False, zs=zs[0], seed=seeds[0])
-    m1, v1 = model_Y[1].predict_moments(Xcand, S, add_lik_var=False, zs=zs[1], seed=seeds[1])
-    if m0.shape[1] != 1 or m1.shape[1] != 1:
-        raise ValueError("each objective model must have one output")
+    if _is_mo(model_Y):
+        (m0, v0), (m1, v1) = model_Y.model.mixture_moments(Xcand, S)
+    else:
+        if not isinstance(model_Y, list) or len(model_Y) != 2 or any(getattr(m, "name", None) != 'dgp' for m in model_Y):
+            raise NotImplementedError("a list of two DGP models or a MultiObjDeepGP is expected (SURVEY §8 a12)")
+        zs = zs or [None, None]
+        seeds = seed if isinstance(seed, (list, tuple)) else [seed, seed]
+        # moment matching over the S propagated samples (EHVI.py:112-119), predict_f moments (no likelihood variance)
+        m0, v0 = model_Y[0].predict_moments(Xcand, S, add_lik_var=False, zs=zs[0], seed=seeds[0])
+        m1, v1 = model_Y[1].predict_moments(Xcand, S, add_lik_var=False, zs=zs[1], seed=seeds[1])
+        if m0.shape[1] != 1 or m1.shape[1] != 1:
+            raise ValueError("each objective model must have one output")
     N = m0.shape[0]
     dev = m0.device
     y0 = _lib.as_device(np.asarray(YND[0], dtype=np.float64).reshape(-1), dev)
@@ -99,6 +130,8 @@ def EHVI_with_grad(model_Y, Xcand, YND, S=1000, zs=None, seed=None):
     (EHVI.py:218-234) takes with tf.GradientTape. One propagation per model for the moments, dgp_ehvi2d_grad for the criterion and its
     partial derivatives w.r.t. the four moments, then one adjoint chain per model (dgp_acq_grad kind 4) with the SAME draws."""
     import ctypes as C
+    if _is_mo(model_Y):
+        return _mo_ehvi_with_grad(model_Y, Xcand, YND, S)
     if not isinstance(model_Y, list) or len(model_Y) != 2 or any(getattr(m, "name", None) != 'dgp' for m in model_Y):
         raise NotImplementedError("a list of two DGP models is expected")
     dev = model_Y[0].device
@@ -163,28 +196,33 @@ def optimize_EHVI(model, YND, popsize_DE=300, popstd_DE=1.5, iterations_DE=400, 
     differential evolution (rand/1/bin, TFP defaults) on u with x = lw + (up - lw) / (1 + exp(u)) minimising -EHVI, every
     generation one EHVI evaluation of the whole population on the device; then (method 'Adam' / 'DE+Adam') Keras Adam on u started
     from the DE result (or `init_adam`, or zeros as in the reference), with the gradient of -EHVI w.r.t. the candidate from EHVI_with_grad
-    (fresh draws every step, like the reference's loss). Returns x_opt [d, 1] like the reference."""
+    (fresh draws every step, like the reference's loss). `model` may also be the multi-objective object (`MultiObjDeepGP`, the case
+    the reference's `model._X` was written for). Returns x_opt [d, 1] like the reference."""
     from . import search
-    if not isinstance(model, list) or len(model) != 2:
-        raise NotImplementedError("optimize_EHVI is implemented for a list of two DGP models (the MO-DGP object is SURVEY §8 f2)")
+    mo = _is_mo(model)
+    if not mo and (not isinstance(model, list) or len(model) != 2):
+        raise NotImplementedError("optimize_EHVI expects a list of two DGP models or a MultiObjDeepGP")
     if method not in ('DE', 'Adam', 'DE+Adam'):
         raise ValueError(f"unknown method {method!r}")
     if corr or approximation != 'None':
         raise NotImplementedError("only the exact uncorrelated EHVI is on the accelerated path")
-    d = model[0].layers[0].feature.Z.shape[1]
+    d = model._X[0].shape[1] if mo else model[0].layers[0].feature.Z.shape[1]     # EHVI.py:210
     lw = np.broadcast_to(np.asarray(bounds[0], dtype=np.float64).reshape(-1), (d,)).copy()
     up = np.broadcast_to(np.asarray(bounds[1], dtype=np.float64).reshape(-1), (d,)).copy()
-    dev = model[0].device
+    dev = model.model.device if mo else model[0].device
+    first = model.model if mo else model[0]
     x_opt = None
     if method in ('DE', 'DE+Adam'):
-        with search.GraphScope(dev):
+        import contextlib
+        with (contextlib.nullcontext() if mo else search.GraphScope(dev)):     # the MO chain is host-chained library calls: no replay
             def objective(X, out):
                 v = -EHVI(model, X, YND, corr=corr, approximation=approximation, S=S)
                 if out is None:
                     return v.contiguous()
                 out.copy_(v)
                 return out
-            res = search.de_minimize(objective, lw, up, d, dev, popsize_DE, popstd_DE, iterations_DE, seed=model[0]._next_seed(seed))
+            res = search.de_minimize(objective, lw, up, d, dev, popsize_DE, popstd_DE, iterations_DE,
+                                     seed=(0 if seed is None else int(seed)) if mo else first._next_seed(seed))
         x_opt = res["x"].cpu().numpy().reshape(d)
     if method in ('Adam', 'DE+Adam'):
         if init_adam is None:

@@ -16,3 +16,5 @@ from .models import MF_DGP  # noqa: F401
 from .models.MF_DGP import MultiFidelityDeepGP  # noqa: F401
 from .models import MF_DGP_EM  # noqa: F401
 from .models.MF_DGP_EM import MultiFidelityDeepGP_EM  # noqa: F401
+from .models import MO_DGP  # noqa: F401
+from .models.MO_DGP import MultiObjDeepGP  # noqa: F401

@@ -110,6 +110,7 @@ _SIG = {
     "dgp_box_from_u": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "dgp_adam_box_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i64, _d, _d, _d, _d, _vp]),
     "dgp_ev_mc": (C.c_int, [_vp, _vp, _i64, _i64, _d, _vp]),
+    "dgp_mixture_moments": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "dgp_ehvi2d": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp]),
     "dgp_ehvi2d_grad": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp]),
     "dgp_debug_gemm": (C.c_int, [_vp, _i, _i, _i, _i, _d, _vp, _vp, _d, _vp, _i, _i, _i, _i, _vp]),

@@ -2360,6 +2360,15 @@ int dgp_ev_mc(dgp_ctx* c, const double* F, int64_t S, int64_t ND, double zero_c,
   return DGP_OK;
 }
 
+int dgp_mixture_moments(dgp_ctx* c, const double* Fmean, const double* Fvar, int64_t S, int64_t ND, const double* lik_variance,
+                        double* mean, double* var) {
+  if (!c || !Fmean || !Fvar || !mean || !var || S < 1 || ND < 1) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  LAUNCH(mixture_moments_kernel, (unsigned)((ND + 255) / 256), 256, 0, Fmean, Fvar, (long)S, (long)ND, lik_variance,
+         lik_variance ? 1 : 0, mean, var);
+  return DGP_OK;
+}
+
 int dgp_ehvi2d(dgp_ctx* c, const double* m0, const double* v0, const double* m1, const double* v1, int64_t N, const double* ynd0,
                const double* ynd1, int n, double* out) {
   if (!c || !m0 || !v0 || !m1 || !v1 || !ynd0 || !ynd1 || !out || N < 1 || n < 2 || n > 2048) return DGP_ERR_ARG;

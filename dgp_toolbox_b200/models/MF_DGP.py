@@ -28,7 +28,8 @@ class _Feature(_Module):
 class MFLayer(_Module):
     """SVGP_Layer(kern, Z, num_outputs, Zero(), augmented=…, layers=…) of utils/layers.py:180-224 for composite kernels."""
 
-    def __init__(self, kern, Z, num_outputs, mean_function=None, augmented=False, layers=None, draw=None, layers_red=None):
+    def __init__(self, kern, Z, num_outputs, mean_function=None, augmented=False, layers=None, draw=None, layers_red=None,
+                 Z_right=None):
         Z = np.asarray(Z.numpy() if hasattr(Z, "numpy") else Z, dtype=np.float64)
         self.kern = kern
         self.num_outputs = int(num_outputs)
@@ -43,7 +44,9 @@ class MFLayer(_Module):
         else:
             self.feature.Z_left = Parameter(Z, name="Z_left")
             with torch.no_grad():      # utils/layers.py:210-213: 100 propagated samples of Z_left through the earlier layers
-                if layers_red is None:
+                if Z_right is not None:      # supplied by the caller (MO_DGP.py: the multi-objective chain samples it its own way)
+                    self.feature.Z_right = Z_right
+                elif layers_red is None:
                     self.feature.Z_right = sample_Z_right_array_all_layers(layers, self.feature.Z_left.value, 100, draw)
                 else:      # embedded mapping: Z_left lives in this fidelity's input space (utils/layers_red.py:110-129)
                     from .MF_DGP_EM import sample_Z_right as _szr_em
@@ -70,6 +73,8 @@ class MFLayer(_Module):
         """(mean, var [P, D_out], kl) -- utils/layers.py:237-278 + :280-308, white = False, Zero mean function. Extra input columns
         beyond the kernel's are ignored, as GPflow's active_dims slicing does (MF_DGP.py:42-43 feeds layer 0 augmented inputs)."""
         values = values or {}
+        if X.shape[1] < self.D:
+            raise ValueError(f"the layer's kernel addresses {self.D} input columns, got {X.shape[1]}")
         X = X[:, :self.D]
         Z = self.Zfull(values)
         M = self.num_inducing

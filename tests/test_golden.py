@@ -12,7 +12,7 @@ import torch
 from oracle import dgp_oracle as O
 
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-FILES = sorted(f for f in glob.glob(os.path.join(HERE, "*.npz")) if not os.path.basename(f).startswith(("aux_", "mf_")))   # mf_dgp.npz: tests/test_gpu_mf.py
+FILES = sorted(f for f in glob.glob(os.path.join(HERE, "*.npz")) if not os.path.basename(f).startswith(("aux_", "mf_", "mo_")))   # mf_dgp.npz: tests/test_gpu_mf.py, mo_dgp.npz: tests/test_gpu_mo.py
 AUX = os.path.join(HERE, "aux_adam_de.npz")
 
 
