@@ -48,6 +48,11 @@ class AdamParam(C.Structure):
                 ("transform", C.c_int32), ("M", C.c_int32), ("mirror", C.c_void_p), ("mirror_count", C.c_int64)]
 
 
+class NatPair(C.Structure):       # dgp_nat_pair
+    _fields_ = [("q_mu", C.c_void_p), ("q_sqrt", C.c_void_p), ("g_mu", C.c_void_p), ("g_sqrt", C.c_void_p), ("M", C.c_int32),
+                ("D_out", C.c_int32)]
+
+
 _vp, _i, _i64, _u64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_double
 _SIG = {
     "dgp_version": (C.c_int, []),
@@ -94,6 +99,7 @@ _SIG = {
     "dgp_comm_destroy": (C.c_int, [_vp]),
     "dgp_elbo_grad_sharded": (C.c_int, [_vp, C.POINTER(ModelDesc), _vp, _vp, _i64, _i64, _d, _u64, _i64, _i, _vp]),
     "dgp_natgrad_step": (C.c_int, [_vp, C.POINTER(ModelDesc), C.POINTER(C.c_int), _i, _d, _vp]),
+    "dgp_natgrad_pairs": (C.c_int, [_vp, C.POINTER(NatPair), _i, _d]),
     "dgp_train_nat_adam": (C.c_int, [_vp, C.POINTER(ModelDesc), _vp, _vp, _i64, _i64, _d, _d, _u64, _u64, _i64, C.POINTER(AdamParam), _i,
                                      _vp, _vp, _i64, _i64, _d, _d, _d, _d, C.POINTER(C.c_int), _i, _d, _vp, _vp]),
     "dgp_propagate_full_cov": (C.c_int, [_vp, C.POINTER(ModelDesc), _vp, _i64, _i64, C.POINTER(_vp), _u64, _i64, C.POINTER(_vp),

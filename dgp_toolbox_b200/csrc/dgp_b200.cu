@@ -2116,6 +2116,25 @@ int dgp_train_adam(dgp_ctx* c, const dgp_model_desc* model, const double* X, con
 
 namespace {
 // One natural-gradient step on the listed layers from the gradients in grad_flat; all device work, batched over (layer, d).
+// the (layer, d) outputs of one (q_mu [M, D], q_sqrt [D, M, M]) pair with its ELBO gradients, appended to `outs`
+void natgrad_add_pair(std::vector<NatOut>& outs, long& off, int& maxMp, int& maxM, double* q_mu, double* q_sqrt, const double* g_mu,
+                      const double* g_sqrt, int M, int D) {
+  const int Mp = (int)round_up(M, kTileM);
+  for (int j = 0; j < D; ++j) {
+    NatOut o;
+    o.q_sqrt = q_sqrt + (long)j * M * M; o.q_sqrt_out = const_cast<double*>(o.q_sqrt);
+    o.g_sqrt = g_sqrt + (long)j * M * M;
+    o.g_mu = g_mu; o.q_mu = q_mu;
+    o.M = M; o.Mp = Mp; o.D = D; o.d = j; o.off = off;
+    off += (long)Mp * Mp;
+    outs.push_back(o);
+  }
+  if (Mp > maxMp) maxMp = Mp;
+  if (M > maxM) maxM = M;
+}
+
+int natgrad_outs(dgp_ctx* c, const std::vector<NatOut>& outs, long off, int maxMp, int maxM, double gamma);
+
 int natgrad_run(dgp_ctx* c, const dgp_model_desc* model, const int* layer_ids, int n_layers, double gamma, const double* grad_flat) {
   std::vector<dgp_layer_grad_offsets> offs(model->num_layers);
   dgp_grad_layout(model, offs.data());
@@ -2127,19 +2146,26 @@ int natgrad_run(dgp_ctx* c, const dgp_model_desc* model, const int* layer_ids, i
     if (l < 0 || l >= model->num_layers) { c->err = "natural gradient: layer index out of range"; return DGP_ERR_ARG; }
     const dgp_layer_desc& d = model->layers[l];
     RC(check_layer(c, d));
-    const int Mp = (int)round_up(d.M, kTileM);
-    for (int j = 0; j < d.D_out; ++j) {
-      NatOut o;
-      o.q_sqrt = d.q_sqrt + (long)j * d.M * d.M; o.q_sqrt_out = const_cast<double*>(o.q_sqrt);
-      o.g_sqrt = grad_flat + offs[l].dq_sqrt + (long)j * d.M * d.M;
-      o.g_mu = grad_flat + offs[l].dq_mu; o.q_mu = const_cast<double*>(d.q_mu);
-      o.M = d.M; o.Mp = Mp; o.D = d.D_out; o.d = j; o.off = off;
-      off += (long)Mp * Mp;
-      outs.push_back(o);
-    }
-    if (Mp > maxMp) maxMp = Mp;
-    if (d.M > maxM) maxM = d.M;
+    natgrad_add_pair(outs, off, maxMp, maxM, const_cast<double*>(d.q_mu), const_cast<double*>(d.q_sqrt), grad_flat + offs[l].dq_mu,
+                     grad_flat + offs[l].dq_sqrt, d.M, d.D_out);
   }
+  return natgrad_outs(c, outs, off, maxMp, maxM, gamma);
+}
+
+int natgrad_pairs_run(dgp_ctx* c, const dgp_nat_pair* pairs, int n_pairs, double gamma) {
+  std::vector<NatOut> outs;
+  int maxMp = 0, maxM = 0;
+  long off = 0;
+  for (int k = 0; k < n_pairs; ++k) {
+    const dgp_nat_pair& p = pairs[k];
+    if (!p.q_mu || !p.q_sqrt || !p.g_mu || !p.g_sqrt || p.M < 1 || p.D_out < 1) { c->err = "natural gradient: null pointer or empty pair"; return DGP_ERR_ARG; }
+    if (p.M > 768) { c->err = "natural gradient: M <= 768 (one CTA factorises an M x M block)"; return DGP_ERR_ARG; }
+    natgrad_add_pair(outs, off, maxMp, maxM, p.q_mu, p.q_sqrt, p.g_mu, p.g_sqrt, p.M, p.D_out);
+  }
+  return natgrad_outs(c, outs, off, maxMp, maxM, gamma);
+}
+
+int natgrad_outs(dgp_ctx* c, const std::vector<NatOut>& outs, long off, int maxMp, int maxM, double gamma) {
   const int nout = (int)outs.size();
   if (nout == 0) return DGP_OK;
   double *R = walloc(c, off), *RT = walloc(c, off), *GR = walloc(c, off), *T = walloc(c, off), *Bf = walloc(c, off);
@@ -2203,6 +2229,18 @@ int dgp_natgrad_step(dgp_ctx* c, const dgp_model_desc* model, const int* layer_i
   if (!c || !model || !layer_ids || n_layers < 0 || !grad_flat) return DGP_ERR_ARG;
   CK(cudaSetDevice(c->device));
   return natgrad_planned(c, model, layer_ids, n_layers, gamma, grad_flat);
+}
+
+int dgp_natgrad_pairs(dgp_ctx* c, const dgp_nat_pair* pairs, int n_pairs, double gamma) {
+  if (!c || !pairs || n_pairs < 0) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  c->dry = true; c->used = 0;
+  int rc = natgrad_pairs_run(c, pairs, n_pairs, gamma);
+  c->dry = false;
+  if (rc != DGP_OK) return rc;
+  RC(ensure_ws(c, c->used));
+  c->used = 0;
+  return natgrad_pairs_run(c, pairs, n_pairs, gamma);
 }
 
 int dgp_train_nat_adam(dgp_ctx* c, const dgp_model_desc* model, const double* X, const double* Y, int64_t N, int64_t S, double scale,

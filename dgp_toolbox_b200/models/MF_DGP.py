@@ -361,6 +361,71 @@ class MultiFidelityDeepGP(_Module):
             m.refresh_Z_right()
 
 
+    def optimize_nat_adam(self, lr_adam=0.01, lr_gamma=0.01, iterations1=2000, iterations2=5000, iterations3=7500, beta_1=0.9, beta_2=0.999,
+                          epsilon=1e-07, messages=500):
+        """MF_DGP.py:426-512: Adam on the kernel parameters; + inducing inputs; then per iteration an Adam step on those and the
+        likelihood variance plus a natural-gradient step on every layer's (q_mu, q_sqrt) (two ELBO evaluations per iteration)."""
+        m = self.model
+        data = (self._X, self._Y)
+        for i, layer in enumerate(m.layers[:-1]):
+            layer.q_mu.assign(self._Y[i]); set_trainable(layer.q_mu, False)
+            layer.q_sqrt.assign(layer.q_sqrt.value * 1e-2 * self._Y[i].var()); set_trainable(layer.q_sqrt, False)
+        m.layers[-1].q_sqrt.assign(m.layers[-1].q_sqrt.value * self._Y[-1].var() * 1e-2)
+        set_trainable(m.layers[-1].q_sqrt, False); set_trainable(m.layers[-1].q_mu, False)
+        m.layers[-1].q_mu.assign(self._Y[-1])
+        m.likelihood.likelihood.variance.assign(self._Y[-1].var() * 1e-2)
+        set_trainable(m.likelihood.likelihood.variance, False)
+        set_trainable(m.layers[0].feature.Z, False)
+        for layer in m.layers[1:]:
+            set_trainable(layer.feature.Z_left, False)
+        state = {}
+        t = self._adam_phase(m.trainable_parameters, state, 1, iterations1, lr_adam, beta_1, beta_2, epsilon, messages)
+        set_trainable(m.layers[0].feature.Z, True)
+        for layer in m.layers[1:]:
+            set_trainable(layer.feature.Z_left, True)
+        t = self._adam_phase(m.trainable_parameters, state, t, iterations2, lr_adam, beta_1, beta_2, epsilon, messages)
+        with torch.no_grad():
+            m.refresh_Z_right()
+        set_trainable(m.likelihood.likelihood.variance, True)
+        nat_adam_phase(m, data, state, t, iterations3, lr_adam, beta_1, beta_2, epsilon, lr_gamma, list(m.layers), messages)
+        with torch.no_grad():
+            m.refresh_Z_right()
+        _lib.get_context(m.device).check()
+
+
+def natgrad_pairs(model, data, gamma, layers):
+    """GPflow `NaturalGradient(gamma).minimize(lambda: -ELBO(data), var_list=[(q_mu, q_sqrt) of layers])` (MF_DGP.py:501-507,
+    MF_DGP_EM.py, MO_DGP.py:480-487): a FRESH ELBO evaluation (new draws, Z_right re-sampled) differentiated w.r.t. the variational
+    parameters through the library's layer adjoints, then one dgp_natgrad_pairs call (XiNat step, batched over layers and outputs,
+    in place). Returns that evaluation's ELBO."""
+    params = [p for l in layers for p in (l.q_mu, l.q_sqrt)]
+    elbo, grads = model.ELBO_and_grads(data, params)
+    arr = (_lib.NatPair * len(layers))()
+    keep = []
+    for i, l in enumerate(layers):
+        gm, gs = grads[l.q_mu].contiguous(), grads[l.q_sqrt].contiguous()
+        keep += [gm, gs]
+        arr[i].q_mu, arr[i].q_sqrt = l.q_mu.value.data_ptr(), l.q_sqrt.value.data_ptr()
+        arr[i].g_mu, arr[i].g_sqrt = gm.data_ptr(), gs.data_ptr()
+        arr[i].M, arr[i].D_out = int(l.q_mu.value.shape[0]), int(l.q_mu.value.shape[1])
+    _lib.get_context(model.device).call("dgp_natgrad_pairs", arr, len(layers), float(gamma))
+    return elbo
+
+
+def nat_adam_phase(model, data, state, t0, iterations, lr, beta_1, beta_2, epsilon, gamma, layers, messages):
+    """Part 3 of the reference's optimize_nat_adam loops (MF_DGP.py:499-509): per iteration one Adam step on the trainable
+    (non-variational) parameters and one natural-gradient step on `layers`, each with its own ELBO evaluation."""
+    for it in range(iterations):
+        params = model.trainable_parameters
+        elbo, grads = model.ELBO_and_grads(data, params)
+        if params:
+            _adam_step(model.device, params, torch.cat([grads[p].reshape(-1) for p in params]), state, t0 + it, lr, beta_1, beta_2, epsilon)
+        natgrad_pairs(model, data, gamma, layers)
+        if it % messages == 0:
+            print(f"ELBO: {float(elbo)}")
+    return t0 + iterations
+
+
 def _adam_step(device, params, flat, state, t, lr, beta_1, beta_2, epsilon):
     """dgp_adam_step (one launch, GPflow bijectors inside) on `params`, gradients concatenated in `flat` in the same order. `state`
     maps a Parameter to its (m, v) slots, so the phases of the reference's loop -- whose trainable sets differ -- share one

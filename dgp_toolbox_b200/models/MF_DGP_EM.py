@@ -238,3 +238,39 @@ class MultiFidelityDeepGP_EM(_Module):
         self._phase(state, t, iterations3, lr, beta_1, beta_2, epsilon, messages)
         with torch.no_grad():
             m.refresh_Z_right()
+
+    def optimize_nat_adam(self, lr_adam=0.01, lr_gamma=0.01, iterations1=2000, iterations2=5000, iterations3=7500, beta_1=0.9, beta_2=0.999,
+                          epsilon=1e-07, messages=500):
+        """MF_DGP_EM.py:501-582, as written: start scalings 1e-3 / 1e-5, the likelihood variances stay frozen in part 3 (:563), the
+        natural-gradient step covers the fidelity layers and the projection layers (:564-565)."""
+        from .MF_DGP import nat_adam_phase
+        m = self.model
+        data = (self._X, self._Y, self._X_red)
+        for i, layer in enumerate(m.layers[:-1]):
+            layer.q_mu.assign(self._Y[i]); set_trainable(layer.q_mu, False)
+            layer.q_sqrt.assign(layer.q_sqrt.value * 1e-3 * self._Y[i].var()); set_trainable(layer.q_sqrt, False)
+        m.layers[-1].q_sqrt.assign(m.layers[-1].q_sqrt.value * self._Y[-1].var() * 1e-3)
+        set_trainable(m.layers[-1].q_sqrt, False); set_trainable(m.layers[-1].q_mu, False)
+        m.layers[-1].q_mu.assign(self._Y[-1])
+        for i, layer in enumerate(m.layers_red):
+            layer.q_sqrt.assign(layer.q_sqrt.value * 1e-5); set_trainable(layer.q_sqrt, False)
+            layer.q_mu.assign(self._X_red[-(i + 1)]); set_trainable(layer.q_mu, False)
+        m.likelihood_projection.likelihood.variance.assign(self._X_red[-1].var() * 1e-3)
+        set_trainable(m.likelihood_projection.likelihood.variance, False)
+        m.likelihood.likelihood.variance.assign(self._Y[-1].var() * 1e-3)
+        set_trainable(m.likelihood.likelihood.variance, False)
+        set_trainable(m.layers[0].feature.Z, False)
+        for layer in m.layers[1:]:
+            set_trainable(layer.feature.Z_left, False)
+        state = {}
+        t = self._phase(state, 1, iterations1, lr_adam, beta_1, beta_2, epsilon, messages)
+        set_trainable(m.layers[0].feature.Z, True)
+        for layer in m.layers[1:]:
+            set_trainable(layer.feature.Z_left, True)
+        t = self._phase(state, t, iterations2, lr_adam, beta_1, beta_2, epsilon, messages)
+        with torch.no_grad():
+            m.refresh_Z_right()
+        nat_adam_phase(m, data, state, t, iterations3, lr_adam, beta_1, beta_2, epsilon, lr_gamma, list(m.layers) + list(m.layers_red), messages)
+        with torch.no_grad():
+            m.refresh_Z_right()
+        _lib.get_context(m.device).check()

@@ -218,10 +218,10 @@ class MultiObjDeepGP(_Module):
         with torch.no_grad():
             return self.model.ELBO((self._X, self._Y))
 
-    def _adam_phase(self, params, state, t0, iterations, lr, epsilon, messages):
+    def _adam_phase(self, params, state, t0, iterations, lr, epsilon, messages, tf_sample_Z_right=True):
         m = self.model
         for it in range(iterations):
-            elbo, grads = m.ELBO_and_grads((self._X, self._Y), params)
+            elbo, grads = m.ELBO_and_grads((self._X, self._Y), params, tf_sample_Z_right=tf_sample_Z_right)
             if params:
                 flat = torch.cat([grads[p].reshape(-1) for p in params])
                 _adam_step(m.device, params, flat, state, t0 + it, lr, 0.9, 0.999, epsilon)
@@ -261,6 +261,38 @@ class MultiObjDeepGP(_Module):
             set_trainable(layer.q_mu, True); set_trainable(layer.q_sqrt, True)
         print('Training part 3')
         self._adam_phase(m.trainable_parameters, state, t, iterations3, lr, 1e-8, messages)
+        with torch.no_grad():
+            m.refresh_Z_right()
+        _lib.get_context(m.device).check()
+
+    def optimize_nat_adam(self, lr_adam=0.01, lr_gamma=0.01, iterations1=2000, iterations2=5000, iterations3=7500, messages=500):
+        """MO_DGP.py:418-494, as written: part 1 without re-sampling Z_right (:462), start scalings 1e-2, then Adam + a natural-gradient
+        step on both layers per iteration."""
+        from .MF_DGP import nat_adam_phase
+        m = self.model
+        m.layers[0].q_mu.assign(self._Y[0]); set_trainable(m.layers[0].q_mu, False)
+        for i, layer in enumerate(m.layers[1:]):
+            layer.q_mu.assign(self._Y[i + 1]); set_trainable(layer.q_mu, False)
+            layer.q_sqrt.assign(layer.q_sqrt.value * 1e-2 * self._Y[i].var()); set_trainable(layer.q_sqrt, False)
+        m.layers[-1].q_sqrt.assign(m.layers[-1].q_sqrt.value * self._Y[-1].var() * 1e-2); set_trainable(m.layers[-1].q_sqrt, False)
+        m.likelihood.likelihood.variance.assign(self._Y[-1].var() * 1e-2)
+        set_trainable(m.likelihood.likelihood.variance, False)
+        set_trainable(m.layers[0].feature.Z, False)
+        for layer in m.layers[1:]:
+            set_trainable(layer.feature.Z_left, False)
+        state = {}
+        print('Training part 1')
+        t = self._adam_phase(m.trainable_parameters, state, 1, iterations1, lr_adam, 1e-8, messages, tf_sample_Z_right=False)
+        set_trainable(m.layers[0].feature.Z, True)
+        for layer in m.layers[1:]:
+            set_trainable(layer.feature.Z_left, True)
+        print('Training part 2')
+        t = self._adam_phase(m.trainable_parameters, state, t, iterations2, lr_adam, 1e-8, messages)
+        with torch.no_grad():
+            m.refresh_Z_right()
+        set_trainable(m.likelihood.likelihood.variance, True)
+        print('Training part 3')
+        nat_adam_phase(m, (self._X, self._Y), state, t, iterations3, lr_adam, 0.9, 0.999, 1e-8, lr_gamma, list(m.layers), messages)
         with torch.no_grad():
             m.refresh_Z_right()
         _lib.get_context(m.device).check()

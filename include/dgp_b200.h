@@ -236,6 +236,13 @@ int dgp_elbo_grad_sharded(dgp_ctx* ctx, const dgp_model_desc* model, const doubl
 int dgp_natgrad_step(dgp_ctx* ctx, const dgp_model_desc* model, const int* layer_ids, int n_layers, double gamma,
                      const double* grad_flat);
 
+/* The same natural-gradient step on caller-supplied pairs (the multi-fidelity / multi-objective models, whose ELBO gradients come from
+ * the supplied-matrix layer calls rather than from dgp_elbo_grad's flat buffer: MF_DGP.py:456,507, MF_DGP_EM.py, MO_DGP.py:446,487):
+ * q_mu [M, D_out], q_sqrt [D_out, M, M] (lower) are updated in place from g_mu / g_sqrt = d ELBO / d q_mu, d ELBO / d q_sqrt (same
+ * shapes; only the lower triangle of g_sqrt is read). M <= 768. HOST array of DEVICE pointers. */
+typedef struct { double* q_mu; double* q_sqrt; const double* g_mu; const double* g_sqrt; int M; int D_out; } dgp_nat_pair;
+int dgp_natgrad_pairs(dgp_ctx* ctx, const dgp_nat_pair* pairs, int n_pairs, double gamma);
+
 /* `steps` iterations of part 2 of the reference's optimize_nat_adam (models/dgp.py:206-220,331-345) without returning to the host:
  * iteration k runs dgp_elbo_grad(seed0 + 2k seed_stride) + dgp_adam_step(t0 + k) on `params` (the non-variational parameters; n_params
  * may be 0), then dgp_elbo_grad(seed0 + (2k+1) seed_stride) + dgp_natgrad_step(nat_layers, gamma) -- two evaluations per iteration,

@@ -210,3 +210,34 @@ def test_multi_objective_model_trains_and_searches(capsys):
     x = D.optimize_EHVI(mo, YND, popsize_DE=12, popstd_DE=1.5, iterations_DE=3, iterations_adam=3, method='DE+Adam', S=8, seed=1)
     assert x.shape == (2, 1) and np.all((x >= 0) & (x <= 1))
     capsys.readouterr()
+
+
+def test_mo_and_em_optimize_nat_adam_run(capsys):
+    """optimize_nat_adam of the multi-objective (MO_DGP.py:418-494) and embedded-mapping (MF_DGP_EM.py:501-582) models: the
+    natural-gradient step (dgp_natgrad_pairs; pinned to the reference by tests/test_gpu_mf.py's MF run) moves every (q_mu, q_sqrt)
+    pair it is given, keeps q_sqrt lower-triangular with a positive diagonal, and leaves finite ELBO values."""
+    import dgp_toolbox_b200 as D
+    X, Y = _toy()
+    mo = D.MultiObjDeepGP(X, Y, loop=1)
+    mo.model.num_samples = 3
+    mo.optimize_nat_adam(lr_adam=0.01, lr_gamma=0.01, iterations1=1, iterations2=1, iterations3=2, messages=1)
+    trace = [float(l.split("ELBO:")[1]) for l in capsys.readouterr().out.splitlines() if l.startswith("ELBO:")]
+    assert len(trace) == 4 and all(np.isfinite(trace))
+    for k, layer in enumerate(mo.model.layers):
+        q = layer.q_sqrt.value
+        assert float(torch.triu(q, 1).abs().max()) == 0 and float(torch.diagonal(q, dim1=1, dim2=2).min()) > 0
+        assert _rel(layer.q_mu.value, Y[k]) > 0                      # moved away from the start value by the natural-gradient step
+    rng = np.random.default_rng(5)
+    Xe = [rng.uniform(0, 1, (12, 2)), rng.uniform(0, 1, (8, 3))]
+    f = lambda x: np.sin(4 * x[:, :1]) + x[:, 1:2]
+    Ye = [f(Xe[0]), 1.3 * f(Xe[1]) + 0.2 * Xe[1][:, 2:3]]
+    em = D.MultiFidelityDeepGP_EM(Xe, Ye, [Xe[1][:, :2].copy()])
+    em.model.num_samples = 3
+    start = [l.q_sqrt.value.clone() for l in list(em.model.layers) + list(em.model.layers_red)]
+    em.optimize_nat_adam(lr_adam=0.01, lr_gamma=0.01, iterations1=1, iterations2=1, iterations3=2, messages=1)
+    trace = [float(l.split("ELBO:")[1]) for l in capsys.readouterr().out.splitlines() if l.startswith("ELBO:")]
+    assert len(trace) == 4 and all(np.isfinite(trace))
+    for l, q0 in zip(list(em.model.layers) + list(em.model.layers_red), start):
+        q = l.q_sqrt.value
+        assert torch.isfinite(q).all() and float(torch.triu(q, 1).abs().max()) == 0 and float(torch.diagonal(q, dim1=1, dim2=2).min()) > 0
+    assert np.isfinite(float(em.objective()))
