@@ -291,6 +291,45 @@ def forward_extras(D, synthetic, torch, steps, peak, with_cpu):
         "cpu_baseline": None,
         "note": "composite-kernel layers run the unfused GEMM pipeline on supplied kernel matrices (DESIGN.md §6); no CPU port of this model "
                 "exists in oracle/ (parity is against the reference's own MF_DGP_EM.py executed under tests/ref_shim, tests/golden/mf_dgp_em.npz)"}
+    del em, d4
+    torch.cuda.empty_cache()
+
+    # ---- config 5 through the multi-objective DGP object (MO_DGP.py; EHVI.py:124-130 `mo_dgp` branch): two composite-kernel layers,
+    # loop = 2 (6 layer applications per chain), both objectives' moments from ONE chain, exact EHVI; chunks of 16384 candidates ----
+    import types
+    from dgp_toolbox_b200.models import MO_DGP
+    rng = np.random.default_rng(0)
+    g0 = lambda x: np.sin(3 * x[:, :1]) + 0.5 * x[:, 1:2]
+    g1 = lambda x: np.cos(2 * x[:, :1]) * x[:, 1:2] - 0.3
+    Zx = rng.uniform(0, 1, (256, 8))
+    mo = MO_DGP.DGP_Base.make_mf_dgp([np.concatenate([Zx, g1(Zx)], 1), Zx.copy()], loop=2)
+    mo.layers[0].kern.kernels[-1].variance.assign(1e-2)
+    for k5, layer in enumerate(mo.layers):
+        layer.q_mu.assign((g0, g1)[k5](Zx) + 0.05 * rng.standard_normal((256, 1)))
+        layer.q_sqrt.assign(0.1 * layer.q_sqrt.value)
+    obj = types.SimpleNamespace(name="mo_dgp", model=mo, _X=[Zx, Zx])
+    host = [torch.from_numpy(rng.uniform(0, 1, (nb5, 8))).pin_memory() for i in range(3)]
+    dev = [h.cuda() for h in host]
+    ms = timed(lambda i: D.EHVI(obj, dev[i % 3], ynd, S=32), steps)
+    res_mo = torch.empty((nb5, 1), dtype=torch.float64).pin_memory()
+
+    def mo_host(i):
+        x = host[i % 3].to("cuda", non_blocking=True)
+        res_mo.copy_(D.EHVI(obj, x, ynd, S=32), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    ms_h = timed(mo_host, steps)
+    D._lib.get_context(0).check()
+    out["c5_mo_dgp_ehvi"] = {
+        "metric": "MO-DGP EHVI candidates/s", "value": nb5 / (ms * 1e-3), "unit": "candidates/s", "ms_per_step": ms,
+        "config": {"workload": "exact 2-objective EHVI through the multi-objective DGP object (MO_DGP.py: 2 composite-kernel layers, D=8, M=256, "
+                               "loop=2 = 6 layer applications per chain), S=32, 32-point Pareto front, float64; one step = one 16384-candidate chunk",
+                   "candidates_per_step": nb5, "samples": 32},
+        "roofline": None,
+        "e2e": {"value": nb5 / (ms_h * 1e-3), "unit": "candidates/s", "ms_per_step": ms_h, "h2d_bytes_per_step": nb5 * 8 * 8,
+                "d2h_bytes_per_step": nb5 * 8},
+        "cpu_baseline": None,
+        "note": "composite-kernel layers run the unfused GEMM pipeline on supplied kernel matrices (DESIGN.md §6); parity is against the "
+                "reference's own MO_DGP.py / EHVI.py executed under tests/ref_shim (tests/golden/mo_dgp.npz)"}
     return out
 
 
