@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from tests import refexec as R  # noqa: E402
 
-HERE = os.path.dirname(os.path.abspath(__file__))
+HERE = os.environ.get("DGP_GOLDEN_OUT") or os.path.dirname(os.path.abspath(__file__))      # tests/test_reference_exec.py regenerates into a temp dir
 ns = R.load()
 MF = importlib.import_module("dgp_dace.models.MF_DGP")
 assert MF.__file__.startswith(R.REFERENCE)

@@ -6,6 +6,7 @@ quantity the oracle restates is compared with what the reference code returns on
 Runs in the build container only (the reference tree is absent on the GPU box, where the committed vectors of
 tests/golden/, generated from these same runs, take over)."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -365,3 +366,24 @@ def test_ehvi_and_pareto_helpers():
             pr = PE.Y_ND(Y, nd, [1.2, 1.2])
             rr = E.Y_ND(Y, nd, [1.2, 1.2])
             assert all(np.array_equal(p, q) for p, q in zip(pr, rr))
+
+
+@pytest.mark.parametrize("script,fixture", [("make_golden_mo.py", "mo_dgp.npz"), ("make_golden_mf_nat.py", "mf_nat_adam.npz")])
+def test_committed_fixture_is_what_the_reference_produces(script, fixture, tmp_path):
+    """The multi-objective and natural-gradient fixtures consumed by the GPU tests are regenerated by executing the reference's source
+    under tests/ref_shim into a temp dir (the generating scripts are deterministic) and must equal the committed files array by
+    array: the committed vectors are reference outputs, not edited ones."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, DGP_GOLDEN_OUT=str(tmp_path), OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, os.path.join(here, "golden", script)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    new = np.load(os.path.join(str(tmp_path), fixture), allow_pickle=False)
+    old = np.load(os.path.join(here, "golden", fixture), allow_pickle=False)
+    assert sorted(new.files) == sorted(old.files)
+    for k in old.files:
+        if old[k].dtype.kind in "US":
+            assert str(old[k]) == str(new[k])
+        else:
+            assert old[k].shape == new[k].shape and np.allclose(old[k], new[k], rtol=1e-12, atol=1e-14), k
