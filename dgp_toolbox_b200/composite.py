@@ -213,34 +213,61 @@ class CompKdiag(torch.autograd.Function):
         return (None, dX) + tuple(grads)
 
 
+class PrepCache:
+    """Device buffer for the replicated per-evaluation work of one layer (dgp_svgp_from_k_cached): valid while Ku, q_mu and q_sqrt
+    keep their values, i.e. for all applications of a layer inside ONE ELBO evaluation and their adjoints."""
+
+    def __init__(self, M, D_out, device):
+        ctx = _lib.get_context(device)
+        self.nbytes = int(_lib.lib.dgp_svgp_prep_cache_bytes(ctx.h, int(M), int(D_out)))
+        if self.nbytes <= 0:
+            raise _lib.DGPError(f"dgp_svgp_prep_cache_bytes({M}, {D_out}) failed: {_lib.lib.dgp_last_error(ctx.h).decode()}")
+        self.buf = torch.empty((self.nbytes + 7) // 8, dtype=torch.float64, device=device)
+        self.filled = False
+
+
+EVAL_CACHE = "_eval_cache"      # key of the per-evaluation cache dict inside a `values` dict (models/MF_DGP.py: MFLayer.conditional_ND)
+
+
 class SVGPFromK(torch.autograd.Function):
     """(mean [P, D], var [P, D], kl) of SVGP_Layer.conditional_ND + KL (utils/layers.py:237-308) on supplied Ku = Kuu + jitter I,
-    Kuf, Kdiag: dgp_svgp_from_k / dgp_svgp_from_k_grad."""
+    Kuf, Kdiag: dgp_svgp_from_k / dgp_svgp_from_k_grad, or their `_cached` forms when the caller supplies a PrepCache."""
 
     @staticmethod
-    def forward(ctx, Ku, Kuf, Kdiag, q_mu, q_sqrt):
+    def forward(ctx, Ku, Kuf, Kdiag, q_mu, q_sqrt, cache=None):
         Ku, Kuf, Kdiag, q_mu, q_sqrt = [t.detach().contiguous() for t in (Ku, Kuf, Kdiag, q_mu, q_sqrt)]
         M, P, D = Ku.shape[0], Kuf.shape[1], q_mu.shape[1]
         mean = torch.empty((P, D), dtype=torch.float64, device=Ku.device)
         var = torch.empty_like(mean)
         kl = torch.empty(1, dtype=torch.float64, device=Ku.device)
-        _lib.get_context(Ku.device).call("dgp_svgp_from_k", M, D, P, _lib.ptr(Ku), _lib.ptr(Kuf), _lib.ptr(Kdiag), _lib.ptr(q_mu),
-                                         _lib.ptr(q_sqrt), _lib.ptr(mean), _lib.ptr(var), _lib.ptr(kl))
+        if cache is None:
+            _lib.get_context(Ku.device).call("dgp_svgp_from_k", M, D, P, _lib.ptr(Ku), _lib.ptr(Kuf), _lib.ptr(Kdiag), _lib.ptr(q_mu),
+                                             _lib.ptr(q_sqrt), _lib.ptr(mean), _lib.ptr(var), _lib.ptr(kl))
+        else:
+            _lib.get_context(Ku.device).call("dgp_svgp_from_k_cached", M, D, P, _lib.ptr(Ku), _lib.ptr(Kuf), _lib.ptr(Kdiag),
+                                             _lib.ptr(q_mu), _lib.ptr(q_sqrt), _lib.ptr(mean), _lib.ptr(var), _lib.ptr(kl),
+                                             _lib.ptr(cache.buf), cache.nbytes, 1 if cache.filled else 0)
+            cache.filled = True
+        ctx.cache = cache
         ctx.save_for_backward(Ku, Kuf, Kdiag, q_mu, q_sqrt)
         return mean, var, kl.reshape(())
 
     @staticmethod
     def backward(ctx, gmean, gvar, gkl):
         Ku, Kuf, Kdiag, q_mu, q_sqrt = ctx.saved_tensors
+        cache = ctx.cache
         M, P, D = Ku.shape[0], Kuf.shape[1], q_mu.shape[1]
         gmean = torch.zeros((P, D), dtype=torch.float64, device=Ku.device) if gmean is None else gmean.contiguous()
         gvar = torch.zeros((P, D), dtype=torch.float64, device=Ku.device) if gvar is None else gvar.contiguous()
         dKu, dKuf, dKdiag = torch.empty_like(Ku), torch.empty_like(Kuf), torch.empty_like(Kdiag)
         dq_mu, dq_sqrt = torch.empty_like(q_mu), torch.empty_like(q_sqrt)
-        _lib.get_context(Ku.device).call("dgp_svgp_from_k_grad", M, D, P, _lib.ptr(Ku), _lib.ptr(Kuf), _lib.ptr(Kdiag), _lib.ptr(q_mu),
-                                         _lib.ptr(q_sqrt), _lib.ptr(gmean), _lib.ptr(gvar), float(gkl) if gkl is not None else 0.0,
-                                         _lib.ptr(dKu), _lib.ptr(dKuf), _lib.ptr(dKdiag), _lib.ptr(dq_mu), _lib.ptr(dq_sqrt))
-        return dKu, dKuf, dKdiag, dq_mu, dq_sqrt
+        args = (M, D, P, _lib.ptr(Ku), _lib.ptr(Kuf), _lib.ptr(Kdiag), _lib.ptr(q_mu), _lib.ptr(q_sqrt), _lib.ptr(gmean), _lib.ptr(gvar),
+                float(gkl) if gkl is not None else 0.0, _lib.ptr(dKu), _lib.ptr(dKuf), _lib.ptr(dKdiag), _lib.ptr(dq_mu), _lib.ptr(dq_sqrt))
+        if cache is None:
+            _lib.get_context(Ku.device).call("dgp_svgp_from_k_grad", *args)
+        else:
+            _lib.get_context(Ku.device).call("dgp_svgp_from_k_grad_cached", *args, _lib.ptr(cache.buf), cache.nbytes)
+        return dKu, dKuf, dKdiag, dq_mu, dq_sqrt, None
 
 
 class CompositeKernelEval:

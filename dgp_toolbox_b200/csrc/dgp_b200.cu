@@ -35,6 +35,7 @@ struct dgp_ctx {
   char* ws = nullptr;
   size_t cap = 0, used = 0;
   bool dry = false;
+  bool replay = false;                  // allocate as usual but launch nothing: the caller restores the region from a saved copy (dgp_svgp_from_k_cached)
   size_t ws_limit = (size_t)24 << 30;   // chunks of the minibatch are sized to stay under this
   int num_sms = 148;
   int splitk_max = 64;                  // most splits of a contraction over the point-samples (sizes the split-K scratch)
@@ -132,7 +133,7 @@ struct ProfScope {   // records an event pair around the launches issued during 
 // kernel launch, skipped while planning the workspace
 #define LAUNCH(kern, grid, block, smem, ...)                          \
   do {                                                                \
-    if (!c->dry) {                                                    \
+    if (!c->dry && !c->replay) {                                      \
       ProfScope ps__(c);                                              \
       kern<<<grid, block, smem, c->stream>>>(__VA_ARGS__);            \
       ++c->launches;                                                  \
@@ -258,7 +259,7 @@ int ensure_ws(dgp_ctx* c, size_t need) {
 }
 
 int gemm(dgp_ctx* c, GemmArgs g, bool nt) {
-  if (c->dry) return DGP_OK;
+  if (c->dry || c->replay) return DGP_OK;
   ProfScope ps(c);
   cudaError_t e = gemm_launch(g, nt, c->stream);
   c->launches += g.splitk > 1 ? 2 : 1;
@@ -1848,7 +1849,8 @@ int comp_check(dgp_ctx* c, const dgp_comp_kernel* k) {
 // The layer's conditional (and, with Gm, its adjoint) on supplied kernel matrices: A-form GEMM pipeline, one pass over all P.
 int svgp_from_k_run(dgp_ctx* c, int M, int D, long P, const double* Ku, const double* Kuf, const double* Kdiag, const double* q_mu,
                     const double* q_sqrt, double* mean, double* var, double* kl, const double* Gm, const double* Gv, double gkl,
-                    double* dKu, double* dKuf, double* dKdiag, double* dq_mu, double* dq_sqrt) {
+                    double* dKu, double* dKuf, double* dKdiag, double* dq_mu, double* dq_sqrt, double* cache = nullptr,
+                    size_t cache_bytes = 0, bool cache_load = false) {
   const bool grad = Gm != nullptr;
   // a descriptor that satisfies check_layer: the kernel fields are never read (Ku is supplied, the fused kernels are off)
   dgp_layer_desc d;
@@ -1860,9 +1862,21 @@ int svgp_from_k_run(dgp_ctx* c, int M, int D, long P, const double* Ku, const do
   const bool fused_saved = c->use_fused;
   c->use_fused = false;
   const double* kext[1] = {Ku};
-  int rc = prep_layers(c, &model, lw, grad ? PREP_GRAD : PREP_KL, false, false, kext);
+  // With a cache the per-layer replicated work (Kuu factorisation, inverse, the M^3 products, KL) is done ONCE for all applications
+  // of the layer inside one ELBO evaluation and their adjoints: the first call stores the prepared region of the arena, the others
+  // lay the region out again without launching anything and copy it back (a few MB, device to device).
+  const size_t prep_start = c->used;
+  c->replay = cache != nullptr && cache_load;
+  int rc = prep_layers(c, &model, lw, (grad || cache) ? PREP_GRAD : PREP_KL, false, false, kext);
+  c->replay = false;
   c->use_fused = fused_saved;
   RC(rc);
+  if (cache && !c->dry) {
+    const size_t prep_bytes = c->used - prep_start;
+    if (prep_bytes > cache_bytes) { c->err = "dgp_svgp_from_k_cached: cache smaller than dgp_svgp_prep_cache_bytes"; return DGP_ERR_ARG; }
+    if (cache_load) CK(cudaMemcpyAsync(c->ws + prep_start, cache, prep_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    else CK(cudaMemcpyAsync(cache, c->ws + prep_start, prep_bytes, cudaMemcpyDeviceToDevice, c->stream));
+  }
   LayerWs& w = lw[0];
   const int Mp = w.Mp;
   const long Pp = round_up(P, kTileP);
@@ -1971,12 +1985,32 @@ int dgp_comp_K_grad(dgp_ctx* c, const dgp_comp_kernel* k, const double* X, int64
   CK(cudaSetDevice(c->device));
   const long n2 = X2 ? P2 : P;
   const int nt = kCompTheta + (k->in_ard ? k->Da : 1);
-  RC(ensure_ws(c, (size_t)P * nt * sizeof(double)));
+  // rows of X against column chunks of X2: enough CTAs to fill the machine when X is the M inducing inputs and X2 the point-samples
+  int nsplit = 1;
+  while (nsplit < 32 && (long)P * nsplit < 148L * 16 && n2 / (2 * nsplit) >= 1024) nsplit *= 2;
+  const long chunk = (n2 + nsplit - 1) / nsplit;
+  RC(ensure_ws(c, (size_t)P * nsplit * (nt + k->D) * sizeof(double)));
   double* part = reinterpret_cast<double*>(c->ws);
+  double* dXp = nsplit > 1 ? part + (size_t)P * nsplit * nt : dX;
   CAT(DGP_CAT_RBF_BWD);
-  LAUNCH(compk_grad_rows_kernel, (unsigned)P, 128, 0, comp_view(k), X, (long)P, X2, n2, Kbar, dX, part);
-  LAUNCH(reduce_partials_kernel, nt, 256, 0, part, (long)P, nt, dtheta, 0);
-  if (X2) LAUNCH(compk_grad_cols_kernel, (unsigned)((P2 + 127) / 128), 128, 0, comp_view(k), X, (long)P, X2, (long)P2, Kbar, dX2);
+  if (k->D <= 8) {
+    LAUNCH(compk_grad_rows_kernel<8>, dim3((unsigned)P, (unsigned)nsplit), 128, 0, comp_view(k), X, (long)P, X2, n2, chunk, Kbar, dXp, part);
+  } else if (k->D <= 16) {
+    LAUNCH(compk_grad_rows_kernel<16>, dim3((unsigned)P, (unsigned)nsplit), 128, 0, comp_view(k), X, (long)P, X2, n2, chunk, Kbar, dXp, part);
+  } else {
+    LAUNCH(compk_grad_rows_kernel<32>, dim3((unsigned)P, (unsigned)nsplit), 128, 0, comp_view(k), X, (long)P, X2, n2, chunk, Kbar, dXp, part);
+  }
+  if (nsplit > 1) LAUNCH(compk_sum_splits_kernel, (unsigned)((P * k->D + 255) / 256), 256, 0, dXp, nsplit, (long)P * k->D, dX);
+  LAUNCH(reduce_partials_kernel, nt, 256, 0, part, (long)P * nsplit, nt, dtheta, 0);
+  if (X2) {
+    if (k->D <= 8) {
+      LAUNCH(compk_grad_cols_kernel<8>, (unsigned)((P2 + 127) / 128), 128, 0, comp_view(k), X, (long)P, X2, (long)P2, Kbar, dX2);
+    } else if (k->D <= 16) {
+      LAUNCH(compk_grad_cols_kernel<16>, (unsigned)((P2 + 127) / 128), 128, 0, comp_view(k), X, (long)P, X2, (long)P2, Kbar, dX2);
+    } else {
+      LAUNCH(compk_grad_cols_kernel<32>, (unsigned)((P2 + 127) / 128), 128, 0, comp_view(k), X, (long)P, X2, (long)P2, Kbar, dX2);
+    }
+  }
   return DGP_OK;
 }
 
@@ -2020,6 +2054,60 @@ int dgp_svgp_from_k_grad(dgp_ctx* c, int M, int D_out, int64_t P, const double* 
   RC(ensure_ws(c, c->used));
   c->used = 0;
   return svgp_from_k_run(c, M, D_out, P, Ku, Kuf, Kdiag, q_mu, q_sqrt, nullptr, nullptr, nullptr, Gm, Gv, gkl, dKu, dKuf, dKdiag, dq_mu, dq_sqrt);
+}
+
+int64_t dgp_svgp_prep_cache_bytes(dgp_ctx* c, int M, int D_out) {
+  if (!c || M < 1 || D_out < 1 || D_out > kMaxD) return -1;
+  dgp_layer_desc d;
+  memset(&d, 0, sizeof(d));
+  d.D_in = 1; d.D_out = D_out; d.M = M;
+  static const double unread = 0.0;      // the dry pass only lays the arena out: no pointer of the descriptor is dereferenced
+  d.Z = &unread; d.lengthscales = &unread; d.variance = &unread; d.q_mu = &unread; d.q_sqrt = &unread;
+  dgp_model_desc model{1, &d, nullptr};
+  std::vector<LayerWs> lw;
+  const bool fused_saved = c->use_fused, dry_saved = c->dry;
+  const size_t used_saved = c->used;
+  c->use_fused = false; c->dry = true; c->used = 0;
+  int rc = prep_layers(c, &model, lw, PREP_GRAD, false, false, nullptr);
+  const size_t bytes = c->used;
+  c->use_fused = fused_saved; c->dry = dry_saved; c->used = used_saved;
+  return rc == DGP_OK ? (int64_t)bytes : -1;
+}
+
+int dgp_svgp_from_k_cached(dgp_ctx* c, int M, int D_out, int64_t P, const double* Ku, const double* Kuf, const double* Kdiag,
+                           const double* q_mu, const double* q_sqrt, double* mean, double* var, double* kl, double* cache,
+                           int64_t cache_bytes, int load) {
+  if (!c || !Ku || !Kuf || !Kdiag || !q_mu || !q_sqrt || !mean || !var || !cache || cache_bytes < 1 || M < 1 || D_out < 1 ||
+      D_out > kMaxD || P < 1) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  c->dry = true; c->used = 0;
+  int rc = svgp_from_k_run(c, M, D_out, P, Ku, Kuf, Kdiag, q_mu, q_sqrt, mean, var, kl, nullptr, nullptr, 0.0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                           cache, (size_t)cache_bytes, load != 0);
+  c->dry = false;
+  if (rc != DGP_OK) return rc;
+  RC(ensure_ws(c, c->used));
+  c->used = 0;
+  return svgp_from_k_run(c, M, D_out, P, Ku, Kuf, Kdiag, q_mu, q_sqrt, mean, var, kl, nullptr, nullptr, 0.0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                         cache, (size_t)cache_bytes, load != 0);
+}
+
+int dgp_svgp_from_k_grad_cached(dgp_ctx* c, int M, int D_out, int64_t P, const double* Ku, const double* Kuf, const double* Kdiag,
+                                const double* q_mu, const double* q_sqrt, const double* Gm, const double* Gv, double gkl,
+                                double* dKu, double* dKuf, double* dKdiag, double* dq_mu, double* dq_sqrt, const double* cache,
+                                int64_t cache_bytes) {
+  if (!c || !Ku || !Kuf || !Kdiag || !q_mu || !q_sqrt || !Gm || !Gv || !dKu || !dKuf || !dKdiag || !dq_mu || !dq_sqrt || !cache ||
+      cache_bytes < 1 || M < 1 || D_out < 1 || D_out > kMaxD || P < 1) return DGP_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  double* cc = const_cast<double*>(cache);
+  c->dry = true; c->used = 0;
+  int rc = svgp_from_k_run(c, M, D_out, P, Ku, Kuf, Kdiag, q_mu, q_sqrt, nullptr, nullptr, nullptr, Gm, Gv, gkl, dKu, dKuf, dKdiag, dq_mu, dq_sqrt,
+                           cc, (size_t)cache_bytes, true);
+  c->dry = false;
+  if (rc != DGP_OK) return rc;
+  RC(ensure_ws(c, c->used));
+  c->used = 0;
+  return svgp_from_k_run(c, M, D_out, P, Ku, Kuf, Kdiag, q_mu, q_sqrt, nullptr, nullptr, nullptr, Gm, Gv, gkl, dKu, dKuf, dKdiag, dq_mu, dq_sqrt,
+                         cc, (size_t)cache_bytes, true);
 }
 
 int64_t dgp_grad_size(const dgp_model_desc* model) {

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..composite import RBF, CompositeKernelEval, LinearKernel, SVGPFromK, White
+from ..composite import EVAL_CACHE, RBF, CompositeKernelEval, LinearKernel, PrepCache, SVGPFromK, White
 from ..gpflow_shim import DEFAULT_JITTER, Gaussian, Parameter, _Module, set_trainable
 
 
@@ -78,10 +78,19 @@ class MFLayer(_Module):
         X = X[:, :self.D]
         Z = self.Zfull(values)
         M = self.num_inducing
-        Ku = self.eval.K(Z, None, values) + DEFAULT_JITTER * torch.eye(M, dtype=torch.float64, device=X.device)
+        # one ELBO evaluation applies a layer several times with the same inducing inputs and q(u): Kuu + jitter I (one autograd node
+        # whose adjoint collects every use) and the library's factorisation / M^3 products / KL are then shared (PrepCache)
+        shared = values.get(EVAL_CACHE)
+        ent = None if shared is None else shared.get((id(self), id(Z)))
+        if ent is None:
+            Ku = self.eval.K(Z, None, values) + DEFAULT_JITTER * torch.eye(M, dtype=torch.float64, device=X.device)
+            ent = {"Z": Z, "Ku": Ku, "prep": None if shared is None else PrepCache(M, self.num_outputs, X.device)}
+            if shared is not None:
+                shared[(id(self), id(Z))] = ent       # holds Z: its id stays unique while the entry lives
         Kuf = self.eval.K(Z, X.contiguous(), values)
         Kdiag = self.eval.K_diag(X.contiguous(), values)
-        return SVGPFromK.apply(Ku, Kuf, Kdiag, values.get(self.q_mu, self.q_mu.value), values.get(self.q_sqrt, self.q_sqrt.value))
+        return SVGPFromK.apply(ent["Ku"], Kuf, Kdiag, values.get(self.q_mu, self.q_mu.value), values.get(self.q_sqrt, self.q_sqrt.value),
+                               ent["prep"])
 
     def sample_from_conditional(self, X, z=None, values=None, draw=None):
         """utils/layers.py:87-130, full_cov = False: X [S, N, D] -> samples, mean, var [S, N, D_out]."""
@@ -244,6 +253,7 @@ class DGP_Base(_Module):
         """ELBO and its constrained-space gradients w.r.t. `params` (default: the trainable parameters): {Parameter: tensor}."""
         params = self.trainable_parameters if params is None else params
         values = {p: p.value.detach().clone().requires_grad_(True) for p in params}
+        values[EVAL_CACHE] = {}
         elbo = self.ELBO(data, values=values)
         grads = torch.autograd.grad(elbo, [values[p] for p in params], allow_unused=True)
         self._detach_features()

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..composite import RBF, LinearKernel, White
+from ..composite import EVAL_CACHE, RBF, LinearKernel, White
 from ..gpflow_shim import Gaussian, _Module, set_trainable
 from .MF_DGP import MFLayer, _Lik, _adam_step, sample
 
@@ -143,6 +143,7 @@ class DGP_Base(_Module):
     def ELBO_and_grads(self, data, params=None):
         params = self.trainable_parameters if params is None else params
         values = {p: p.value.detach().clone().requires_grad_(True) for p in params}
+        values[EVAL_CACHE] = {}
         elbo = self.ELBO(data, values=values)
         grads = torch.autograd.grad(elbo, [values[p] for p in params], allow_unused=True)
         for layer in self.layers[1:]:

@@ -138,6 +138,7 @@ class DGP_Base(_MF.DGP_Base):
         """ELBO and its constrained-space gradients w.r.t. `params` (default: the trainable parameters): {Parameter: tensor}."""
         params = self.trainable_parameters if params is None else params
         values = {p: p.value.detach().clone().requires_grad_(True) for p in params}
+        values[_MF.EVAL_CACHE] = {}
         elbo = self.ELBO(data, tf_sample_Z_right=tf_sample_Z_right, values=values)
         grads = torch.autograd.grad(elbo, [values[p] for p in params], allow_unused=True)
         self._detach_features()
