@@ -224,6 +224,14 @@ class PrepCache:
             raise _lib.DGPError(f"dgp_svgp_prep_cache_bytes({M}, {D_out}) failed: {_lib.lib.dgp_last_error(ctx.h).decode()}")
         self.buf = torch.empty((self.nbytes + 7) // 8, dtype=torch.float64, device=device)
         self.filled = False
+        self.budget = None       # [bytes left] for the forward-plane stashes of this ELBO evaluation, shared by all its layers
+
+
+def stash_budget_bytes():
+    """Device memory one ELBO evaluation may spend on keeping the A / T_d planes of its layer applications for their adjoints
+    (env DGP_B200_STASH_GB, default 48): applications beyond it recompute the planes in the adjoint call, as the uncached path does."""
+    import os
+    return int(float(os.environ.get("DGP_B200_STASH_GB", "48")) * (1 << 30))
 
 
 EVAL_CACHE = "_eval_cache"      # key of the per-evaluation cache dict inside a `values` dict (models/MF_DGP.py: MFLayer.conditional_ND)
@@ -244,10 +252,17 @@ class SVGPFromK(torch.autograd.Function):
             _lib.get_context(Ku.device).call("dgp_svgp_from_k", M, D, P, _lib.ptr(Ku), _lib.ptr(Kuf), _lib.ptr(Kdiag), _lib.ptr(q_mu),
                                              _lib.ptr(q_sqrt), _lib.ptr(mean), _lib.ptr(var), _lib.ptr(kl))
         else:
+            stash = None
+            if cache.budget is not None and any(ctx.needs_input_grad):
+                nb = int(_lib.lib.dgp_svgp_stash_bytes(M, D, P))
+                if 0 < nb <= cache.budget[0]:
+                    cache.budget[0] -= nb
+                    stash = torch.empty(nb // 8, dtype=torch.float64, device=Ku.device)
             _lib.get_context(Ku.device).call("dgp_svgp_from_k_cached", M, D, P, _lib.ptr(Ku), _lib.ptr(Kuf), _lib.ptr(Kdiag),
                                              _lib.ptr(q_mu), _lib.ptr(q_sqrt), _lib.ptr(mean), _lib.ptr(var), _lib.ptr(kl),
-                                             _lib.ptr(cache.buf), cache.nbytes, 1 if cache.filled else 0)
+                                             _lib.ptr(cache.buf), cache.nbytes, 1 if cache.filled else 0, _lib.ptr(stash))
             cache.filled = True
+            ctx.stash = stash
         ctx.cache = cache
         ctx.save_for_backward(Ku, Kuf, Kdiag, q_mu, q_sqrt)
         return mean, var, kl.reshape(())
@@ -266,7 +281,8 @@ class SVGPFromK(torch.autograd.Function):
         if cache is None:
             _lib.get_context(Ku.device).call("dgp_svgp_from_k_grad", *args)
         else:
-            _lib.get_context(Ku.device).call("dgp_svgp_from_k_grad_cached", *args, _lib.ptr(cache.buf), cache.nbytes)
+            _lib.get_context(Ku.device).call("dgp_svgp_from_k_grad_cached", *args, _lib.ptr(cache.buf), cache.nbytes, _lib.ptr(ctx.stash))
+            ctx.stash = None
         return dKu, dKuf, dKdiag, dq_mu, dq_sqrt, None
 
 

@@ -1850,7 +1850,7 @@ int comp_check(dgp_ctx* c, const dgp_comp_kernel* k) {
 int svgp_from_k_run(dgp_ctx* c, int M, int D, long P, const double* Ku, const double* Kuf, const double* Kdiag, const double* q_mu,
                     const double* q_sqrt, double* mean, double* var, double* kl, const double* Gm, const double* Gv, double gkl,
                     double* dKu, double* dKuf, double* dKdiag, double* dq_mu, double* dq_sqrt, double* cache = nullptr,
-                    size_t cache_bytes = 0, bool cache_load = false) {
+                    size_t cache_bytes = 0, bool cache_load = false, double* stash = nullptr) {
   const bool grad = Gm != nullptr;
   // a descriptor that satisfies check_layer: the kernel fields are never read (Ku is supplied, the fused kernels are off)
   dgp_layer_desc d;
@@ -1881,10 +1881,17 @@ int svgp_from_k_run(dgp_ctx* c, int M, int D, long P, const double* Ku, const do
   const int Mp = w.Mp;
   const long Pp = round_up(P, kTileP);
   const size_t plane = (size_t)Mp * Pp;
-  if ((plane * (size_t)(5 + D) + (size_t)Pp * 80) * sizeof(double) + c->used > c->ws_limit) {
+  // `stash` (caller-owned, (1 + D) planes): the forward call leaves A and the T_d planes there and the adjoint call reads them back
+  // instead of running the three forward products again
+  const bool reuse = stash != nullptr && grad;
+  const size_t nplanes = (reuse ? 0 : 2) + (stash ? 0 : 1 + (size_t)D) + (grad ? 2 : 0);
+  if ((plane * nplanes + (size_t)Pp * 80) * sizeof(double) + c->used > c->ws_limit) {
     c->err = "dgp_svgp_from_k: P too large for the workspace limit (dgp_set_workspace_limit); split the points"; return DGP_ERR_UNSUPPORTED;
   }
-  double *K = walloc(c, plane), *V = walloc(c, plane), *A = walloc(c, plane), *T = walloc(c, plane * D);
+  double *K = nullptr, *V = nullptr, *A = nullptr, *T = nullptr;
+  if (!reuse) { K = walloc(c, plane); V = walloc(c, plane); }
+  if (stash) { A = stash; T = stash + plane; }
+  else { A = walloc(c, plane); T = walloc(c, plane * D); }
   double *dA = nullptr, *W = nullptr, *GvT = nullptr, *GmPad = nullptr, *gq = nullptr, *part = nullptr, *dummy = nullptr;
   size_t partcap = 0;
   if (grad) {
@@ -1896,16 +1903,19 @@ int svgp_from_k_run(dgp_ctx* c, int M, int D, long P, const double* Ku, const do
   }
   if (c->dry) return DGP_OK;
   CAT(DGP_CAT_GEMM_FWD);
-  LAUNCH(pad_plane_kernel, (unsigned)((plane + 255) / 256), 256, 0, Kuf, M, Mp, P, Pp, K);
-  GemmArgs g = gargs(w.Linv, Mp, K, Pp, V, Pp, Mp, (int)Pp, Mp);       // V = Lu^-1 Kuf          (layers.py:245)
-  g.a_tri = 1;
-  RC(gemm(c, g, false));
-  g = gargs(w.LinvT, Mp, V, Pp, A, Pp, Mp, (int)Pp, Mp);               // A = Lu^-T V            (layers.py:247)
-  g.a_tri = 2;
-  RC(gemm(c, g, false));
-  g = gargs(w.RpT, Mp, A, Pp, T, Pp, Mp, (int)Pp, Mp);                 // T_d = q_sqrt_d^T A     (layers.py:257-271)
-  g.a_tri = 2; g.batch = D; g.sA = (long)Mp * Mp; g.sB = 0; g.sC = (long)Mp * Pp;
-  RC(gemm(c, g, false));
+  GemmArgs g;
+  if (!reuse) {
+    LAUNCH(pad_plane_kernel, (unsigned)((plane + 255) / 256), 256, 0, Kuf, M, Mp, P, Pp, K);
+    g = gargs(w.Linv, Mp, K, Pp, V, Pp, Mp, (int)Pp, Mp);                // V = Lu^-1 Kuf          (layers.py:245)
+    g.a_tri = 1;
+    RC(gemm(c, g, false));
+    g = gargs(w.LinvT, Mp, V, Pp, A, Pp, Mp, (int)Pp, Mp);               // A = Lu^-T V            (layers.py:247)
+    g.a_tri = 2;
+    RC(gemm(c, g, false));
+    g = gargs(w.RpT, Mp, A, Pp, T, Pp, Mp, (int)Pp, Mp);                 // T_d = q_sqrt_d^T A     (layers.py:257-271)
+    g.a_tri = 2; g.batch = D; g.sA = (long)Mp * Mp; g.sB = 0; g.sC = (long)Mp * Pp;
+    RC(gemm(c, g, false));
+  }
   if (mean) {
     CAT(DGP_CAT_MOMENTS);
     LAUNCH(moments_ext_kernel, (unsigned)((P + 127) / 128), 128, 0, V, A, T, w.qmuP, Kdiag, M, Mp, D, P, Pp, mean, var);
@@ -2074,40 +2084,45 @@ int64_t dgp_svgp_prep_cache_bytes(dgp_ctx* c, int M, int D_out) {
   return rc == DGP_OK ? (int64_t)bytes : -1;
 }
 
+int64_t dgp_svgp_stash_bytes(int M, int D_out, int64_t P) {
+  if (M < 1 || D_out < 1 || P < 1) return -1;
+  return (int64_t)((size_t)(1 + D_out) * round_up(M, kTileM) * round_up(P, kTileP) * sizeof(double));
+}
+
 int dgp_svgp_from_k_cached(dgp_ctx* c, int M, int D_out, int64_t P, const double* Ku, const double* Kuf, const double* Kdiag,
                            const double* q_mu, const double* q_sqrt, double* mean, double* var, double* kl, double* cache,
-                           int64_t cache_bytes, int load) {
+                           int64_t cache_bytes, int load, double* stash) {
   if (!c || !Ku || !Kuf || !Kdiag || !q_mu || !q_sqrt || !mean || !var || !cache || cache_bytes < 1 || M < 1 || D_out < 1 ||
       D_out > kMaxD || P < 1) return DGP_ERR_ARG;
   CK(cudaSetDevice(c->device));
   c->dry = true; c->used = 0;
   int rc = svgp_from_k_run(c, M, D_out, P, Ku, Kuf, Kdiag, q_mu, q_sqrt, mean, var, kl, nullptr, nullptr, 0.0, nullptr, nullptr, nullptr, nullptr, nullptr,
-                           cache, (size_t)cache_bytes, load != 0);
+                           cache, (size_t)cache_bytes, load != 0, stash);
   c->dry = false;
   if (rc != DGP_OK) return rc;
   RC(ensure_ws(c, c->used));
   c->used = 0;
   return svgp_from_k_run(c, M, D_out, P, Ku, Kuf, Kdiag, q_mu, q_sqrt, mean, var, kl, nullptr, nullptr, 0.0, nullptr, nullptr, nullptr, nullptr, nullptr,
-                         cache, (size_t)cache_bytes, load != 0);
+                         cache, (size_t)cache_bytes, load != 0, stash);
 }
 
 int dgp_svgp_from_k_grad_cached(dgp_ctx* c, int M, int D_out, int64_t P, const double* Ku, const double* Kuf, const double* Kdiag,
                                 const double* q_mu, const double* q_sqrt, const double* Gm, const double* Gv, double gkl,
                                 double* dKu, double* dKuf, double* dKdiag, double* dq_mu, double* dq_sqrt, const double* cache,
-                                int64_t cache_bytes) {
+                                int64_t cache_bytes, const double* stash) {
   if (!c || !Ku || !Kuf || !Kdiag || !q_mu || !q_sqrt || !Gm || !Gv || !dKu || !dKuf || !dKdiag || !dq_mu || !dq_sqrt || !cache ||
       cache_bytes < 1 || M < 1 || D_out < 1 || D_out > kMaxD || P < 1) return DGP_ERR_ARG;
   CK(cudaSetDevice(c->device));
   double* cc = const_cast<double*>(cache);
   c->dry = true; c->used = 0;
   int rc = svgp_from_k_run(c, M, D_out, P, Ku, Kuf, Kdiag, q_mu, q_sqrt, nullptr, nullptr, nullptr, Gm, Gv, gkl, dKu, dKuf, dKdiag, dq_mu, dq_sqrt,
-                           cc, (size_t)cache_bytes, true);
+                           cc, (size_t)cache_bytes, true, const_cast<double*>(stash));
   c->dry = false;
   if (rc != DGP_OK) return rc;
   RC(ensure_ws(c, c->used));
   c->used = 0;
   return svgp_from_k_run(c, M, D_out, P, Ku, Kuf, Kdiag, q_mu, q_sqrt, nullptr, nullptr, nullptr, Gm, Gv, gkl, dKu, dKuf, dKdiag, dq_mu, dq_sqrt,
-                         cc, (size_t)cache_bytes, true);
+                         cc, (size_t)cache_bytes, true, const_cast<double*>(stash));
 }
 
 int64_t dgp_grad_size(const dgp_model_desc* model) {

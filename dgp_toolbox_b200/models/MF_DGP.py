@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..composite import EVAL_CACHE, RBF, CompositeKernelEval, LinearKernel, PrepCache, SVGPFromK, White
+from ..composite import EVAL_CACHE, RBF, CompositeKernelEval, LinearKernel, PrepCache, SVGPFromK, White, stash_budget_bytes
 from ..gpflow_shim import DEFAULT_JITTER, Gaussian, Parameter, _Module, set_trainable
 
 
@@ -87,6 +87,7 @@ class MFLayer(_Module):
             ent = {"Z": Z, "Ku": Ku, "prep": None if shared is None else PrepCache(M, self.num_outputs, X.device)}
             if shared is not None:
                 shared[(id(self), id(Z))] = ent       # holds Z: its id stays unique while the entry lives
+                ent["prep"].budget = shared.setdefault("_stash_budget", [stash_budget_bytes()])
         Kuf = self.eval.K(Z, X.contiguous(), values)
         Kdiag = self.eval.K_diag(X.contiguous(), values)
         return SVGPFromK.apply(ent["Ku"], Kuf, Kdiag, values.get(self.q_mu, self.q_mu.value), values.get(self.q_sqrt, self.q_sqrt.value),

@@ -215,15 +215,18 @@ int dgp_svgp_from_k_grad(dgp_ctx* ctx, int M, int D_out, int64_t P, const double
  * MO_DGP.py:88-122: the cyclic chain); the factorisation, the M^3 products and the KL depend on those three only. `cache` is a caller-owned
  * DEVICE buffer of dgp_svgp_prep_cache_bytes(ctx, M, D_out) bytes: the first forward call (load = 0) factorises Kuu, forms the M^3
  * products and the KL and saves them; every later call with the same (Ku, q_mu, q_sqrt) -- forward with load = 1, and every adjoint --
- * restores them instead of recomputing. Results are identical to the uncached calls. */
+ * restores them instead of recomputing. `stash` (may be NULL): a caller-owned DEVICE buffer of dgp_svgp_stash_bytes(M, D_out, P)
+ * bytes per APPLICATION; the forward call leaves A = Ku^-1 Kuf and the T_d = q_sqrt_d^T A planes there and the adjoint call of the same
+ * application reads them instead of running the three M^2 P forward products again. Results are identical to the uncached calls. */
 int64_t dgp_svgp_prep_cache_bytes(dgp_ctx* ctx, int M, int D_out);
+int64_t dgp_svgp_stash_bytes(int M, int D_out, int64_t P);
 int dgp_svgp_from_k_cached(dgp_ctx* ctx, int M, int D_out, int64_t P, const double* Ku, const double* Kuf, const double* Kdiag,
                            const double* q_mu, const double* q_sqrt, double* mean, double* var, double* kl, double* cache,
-                           int64_t cache_bytes, int load);
+                           int64_t cache_bytes, int load, double* stash);
 int dgp_svgp_from_k_grad_cached(dgp_ctx* ctx, int M, int D_out, int64_t P, const double* Ku, const double* Kuf, const double* Kdiag,
                                 const double* q_mu, const double* q_sqrt, const double* Gm, const double* Gv, double gkl,
                                 double* dKu, double* dKuf, double* dKdiag, double* dq_mu, double* dq_sqrt, const double* cache,
-                                int64_t cache_bytes);
+                                int64_t cache_bytes, const double* stash);
 
 /* ---- multi-GPU: one process (or thread) and one ctx per GPU. The minibatch's points are sharded over the ranks by
  * the caller; parameters, Kuu, its Cholesky and the KL term are replicated; the path's only exchange step is ONE sum-allreduce of the
