@@ -413,6 +413,9 @@ def main():
         return sharded.step_host(X, Y, n_offset=(i * world + rank) * nb, scale=scale, seed=1234 + i)
 
     def timed(fn, k):
+        import gc
+        gc.collect()
+        gc.disable()       # a collector pause between launches shows up as GPU idle time in a region of only k steps
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -420,6 +423,7 @@ def main():
             out = fn(i)
         e1.record()
         sync_all()
+        gc.enable()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
